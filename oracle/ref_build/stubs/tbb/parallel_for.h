@@ -1,0 +1,3 @@
+// ORACLE SCAFFOLDING: see _shim.h
+#pragma once
+#include "_shim.h"
