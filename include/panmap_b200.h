@@ -1,0 +1,184 @@
+/*
+ * panmap_b200.h -- C ABI of the B200-native placement hot path (drop-in for panmap's place stage).
+ *
+ * panmap itself has no plugin/FFI layer: the boundary of the path is two C++ headers,
+ *   placement::placeLite(...)              /root/reference/src/placement.hpp:237-244
+ *   seeding::rollingSyncmers(...)          /root/reference/src/seeding.hpp:126-127
+ * plus the unit-test-pinned helpers hashSeq (seeding.hpp:123), NodeMetrics::computeChildMetrics
+ * (placement.hpp:151-154), resolveMinReadSupport / computeReadSeedMagnitudes (placement.hpp:99-105).
+ * Every entry point below names the reference interface it replaces.  panmap_b200/host/ holds C++ shims
+ * with the reference's own names/signatures that call this ABI; INTEGRATION.md shows how a panmap
+ * maintainer binds them.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Functions return PM_OK (0) or a negative
+ * pm_status; pm_last_error() gives the message for the calling thread.  There is NO CPU fallback: every
+ * compute entry point fails with PM_ERR_NO_DEVICE when no CUDA device is usable.
+ * Handles: pm_index is immutable after creation and may be shared by any number of pm_workspace objects;
+ * each pm_workspace owns one CUDA stream plus per-sample scratch, so distinct workspaces may be driven
+ * concurrently from distinct host threads (the reference's batch mode, main.cpp:1574-1592).
+ */
+#ifndef PANMAP_B200_H
+#define PANMAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_ABI_VERSION 1
+#define PM_NONE 0xFFFFFFFFu /* "no node" (reference: UINT32_MAX, placement.hpp:159) */
+#define PM_NUM_METRICS 5    /* log_raw, log_cosine, containment, weighted_containment, log_containment */
+
+typedef enum pm_status {
+    PM_OK = 0,
+    PM_ERR_INVALID = -1,     /* bad argument / malformed index (reference throws std::runtime_error) */
+    PM_ERR_NO_DEVICE = -2,   /* CUDA device missing or unusable: there is no CPU fallback */
+    PM_ERR_CUDA = -3,        /* CUDA runtime error */
+    PM_ERR_IO = -4,          /* file could not be read */
+    PM_ERR_UNSUPPORTED = -5, /* option not implemented on the GPU path yet */
+    PM_ERR_CAPACITY = -6     /* internal capacity exceeded after retry */
+} pm_status;
+
+typedef struct pm_host_index pm_host_index; /* a parsed .idx on the host */
+typedef struct pm_index pm_index;           /* flattened index resident in HBM on one device */
+typedef struct pm_workspace pm_workspace;   /* per-sample state: stream, read table, scores */
+
+/* Seeding parameters; authoritative source is the index (placement.cpp:1094-1101). */
+typedef struct pm_seed_params {
+    int32_t k, s, t, l;
+    int32_t open; /* 0 = closed syncmers */
+    int32_t hpc;  /* homopolymer-compressed index: reads must be compressed by the caller (seeding.cpp:286-306) */
+} pm_seed_params;
+
+/* Flat view of the per-node seed-delta index (index_lite.capnp LiteIndex: seedChangeHashes /
+ * seedChangeParentCounts / seedChangeChildCounts / nodeChangeOffsets + LiteTree.liteNodes[].parentIndex;
+ * the reference's own flat view is built at placement.cpp:1021-1092).  Nodes are in DFS pre-order with
+ * parent_index[v] < v (panmap_utils.cpp:273-286); node 0 is the root. */
+typedef struct pm_index_desc {
+    uint64_t n_nodes;
+    uint64_t n_deltas;
+    const uint64_t* delta_hash;   /* [n_deltas] */
+    const int16_t* delta_parent;  /* [n_deltas] */
+    const int16_t* delta_child;   /* [n_deltas] */
+    const uint64_t* node_offsets; /* [n_nodes+1] */
+    const uint32_t* parent_index; /* [n_nodes], entry 0 ignored */
+    pm_seed_params seed;
+} pm_index_desc;
+
+/* Per-call options == placement::TraversalParams (placement.hpp:28-54), hot-path subset. */
+typedef struct pm_place_params {
+    int32_t trim_start;        /* trimStart */
+    int32_t trim_end;          /* trimEnd */
+    int32_t min_read_support;  /* minReadSupport: -1 = auto (placement.cpp:931-955) */
+    int32_t dedup_reads;       /* dedupReads (PM_ERR_UNSUPPORTED when non-zero, for now) */
+    int32_t force_leaf;        /* forceLeaf: only leaves are eligible (placement.cpp:794-795) */
+    uint32_t skip_node_index;  /* leave-one-out node, PM_NONE = none (placement.hpp:91) */
+    double seed_mask_fraction; /* seedMaskFraction; CLI default 0 (main.cpp:1967) */
+    int32_t want_node_scores;  /* keep the [n_nodes][5] f64 score matrix for pm_get_node_scores */
+    int32_t reserved;
+} pm_place_params;
+
+/* == the scalar part of placement::PlacementResult (placement.hpp:157-235) */
+typedef struct pm_place_result {
+    double best_score[PM_NUM_METRICS];   /* best*Score */
+    uint32_t best_index[PM_NUM_METRICS]; /* best*NodeIndex after finalizeTiedIndices (lowest DFS index of the ties) */
+    uint64_t tied_count[PM_NUM_METRICS]; /* tied*NodeIndices.size() after sort+unique */
+    uint64_t total_reads;                /* totalReadsProcessed */
+    uint64_t unique_seeds;               /* seedFreqInReads.size() after homopolymer removal / masking */
+    uint64_t read_unique_seed_count;     /* readUniqueSeedCount (U') */
+    int64_t total_read_seed_frequency;   /* totalReadSeedFrequency */
+    int64_t min_read_support;            /* resolved value */
+    double read_magnitude;               /* logReadMagnitude */
+    double log_containment_denominator;
+    double weighted_containment_denominator;
+    float stage_ms[8];                   /* device time: 0 h2d, 1 seeding+table, 2 finalize, 3 deltas, 4 prefix+scores,
+                                            5 selection, 6 d2h, 7 total (CUDA events on the workspace stream) */
+} pm_place_result;
+
+const char* pm_last_error(void);
+int pm_abi_version(void);
+/* number of usable CUDA devices (0 when none; never fails) */
+int pm_device_count(void);
+
+/* ---- .idx container (index_single_mode.cpp:1561-1636, main.cpp:193-236): 32-byte "PMI1" header + raw
+ *      Cap'n Proto LiteIndex message.  zstd-framed payloads are reported as PM_ERR_UNSUPPORTED. ---- */
+int pm_host_index_read(const char* path, pm_host_index** out);
+void pm_host_index_free(pm_host_index* h);
+int pm_host_index_desc(const pm_host_index* h, pm_index_desc* out); /* pointers stay owned by h */
+const char* pm_host_index_node_id(const pm_host_index* h, uint64_t node); /* LiteNode.id */
+
+/* ---- device index (replaces LiteTree::initialize + the SoA hookup, placement.cpp:1021-1092).
+ *      node_begin/node_end select a shard of whole tiles for multi-GPU runs (0,0 = all nodes). ---- */
+int pm_index_create(const pm_index_desc* desc, int device, pm_index** out);
+int pm_index_create_shard(const pm_index_desc* desc, int device, uint32_t shard, uint32_t n_shards, pm_index** out);
+void pm_index_destroy(pm_index* idx);
+uint64_t pm_index_num_nodes(const pm_index* idx);
+uint64_t pm_index_num_deltas(const pm_index* idx);
+uint64_t pm_index_num_distinct_seeds(const pm_index* idx);
+/* shard extent in DFS node indices: [begin, end) */
+int pm_index_shard_range(const pm_index* idx, uint64_t* node_begin, uint64_t* node_end);
+/* sample-independent per-node accumulators (NodeMetrics::genomeMagnitudeSquared / genomeUniqueSeedCount,
+ * placement.cpp:292-302), precomputed at creation; out arrays are [n_nodes] */
+int pm_index_genome_metrics(const pm_index* idx, double* genome_mag_sq, int64_t* genome_unique);
+
+int pm_workspace_create(pm_index* idx, pm_workspace** out);
+void pm_workspace_destroy(pm_workspace* ws);
+
+/* ---- placement::placeLite compute part (placement.cpp:986-1950) for one sample.
+ *      reads: concatenated read bytes (ASCII, any case, non-ACGT = ambiguous); read_offsets[n_reads+1].
+ *      Buffers are HOST memory; the call uploads them, runs every stage on the GPU and returns the result. */
+int pm_place(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads,
+             const pm_place_params* params, pm_place_result* result);
+/* "inputs already resident in HBM": pm_reads_upload copies + lays out the reads once (untimed by callers that
+ * measure device throughput), pm_place_resident then runs every stage on them; may be called repeatedly. */
+int pm_reads_upload(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads);
+int pm_place_resident(pm_workspace* ws, const pm_place_params* params, pm_place_result* result);
+/* page-locked host buffers for callers that want the H2D copies of pm_place to run at full PCIe speed */
+void* pm_host_alloc(uint64_t bytes);
+void pm_host_free(void* p);
+
+/* after pm_place: tied node lists (sorted ascending, == tied*NodeIndices), per-node scores, read seed table */
+int pm_get_tied(pm_workspace* ws, int metric, uint32_t* out, uint64_t cap);
+int pm_get_node_scores(pm_workspace* ws, double* out /* [n_nodes][5] */);
+int pm_get_node_metrics(pm_workspace* ws, double* out /* [n_nodes][5]: logRawNum, logCosNum, presence, wcNum, logContNum */);
+int pm_get_seed_table(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap); /* unsorted; returns n or <0 */
+
+/* ---- seeding::rollingSyncmers (seeding.cpp:47-229) for a batch of sequences, returnAll=false form:
+ *      per sequence i the syncmers are written at out_*[win_offsets[i] ...] where
+ *      win_offsets[i] = sum_{j<i} max(0, len_j - k + 1); out_count[i] = number of syncmers of sequence i. ---- */
+int pm_rolling_syncmers(int device, const char* seqs, const uint64_t* seq_offsets, uint64_t n_seqs,
+                        int k, int s, int open, int t,
+                        uint64_t* out_hash, uint8_t* out_is_reverse, int64_t* out_pos, uint64_t* out_count);
+/* per-read seeds as placeLite counts them (k-min-mers for l>1, placement.cpp:1598-1686); same output layout */
+int pm_read_seeds(int device, const char* seqs, const uint64_t* seq_offsets, uint64_t n_seqs,
+                  const pm_seed_params* sp, int trim_start, int trim_end, uint64_t* out_hash, uint64_t* out_count);
+
+/* ---- staged entry points for multi-GPU runs: one process per GPU, each holding one shard of the node range
+ *      (pm_index_create_shard) and a slice of the reads; the caller moves the small exchange buffers between
+ *      ranks (NCCL / gloo all-gather).  All pointers are HOST pointers.
+ *        A  pm_stage_seed            seed this rank's reads into the workspace table
+ *        B  pm_stage_table_*         export (hash,count); import the concatenation of every rank's export
+ *        C  pm_stage_score           filters, min-support, magnitudes, deltas, exact prefix, scores, local records
+ *        D  pm_stage_records_*       local prefix-maximum records (global BFS rank, node, score) per metric
+ *        E  pm_stage_select          tolerance chain over ALL ranks' records (on the device) + this shard's ties;
+ *                                    the union over ranks of pm_get_tied() is the reference's tied list ---- */
+int pm_stage_seed(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads,
+                  const pm_place_params* params);
+int64_t pm_stage_table_size(pm_workspace* ws);
+int pm_stage_table_export(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap);
+int pm_stage_table_import(pm_workspace* ws, const uint64_t* hash, const int64_t* count, uint64_t n);
+int pm_stage_score(pm_workspace* ws, const pm_place_params* params);
+int64_t pm_stage_records_size(pm_workspace* ws, int metric);
+int pm_stage_records_export(pm_workspace* ws, int metric, uint32_t* bfs_rank, uint32_t* node, double* score, uint64_t cap);
+int pm_stage_select(pm_workspace* ws, const uint32_t* counts /* [5] */, const uint32_t* const* bfs_rank /* [5] */,
+                    const uint32_t* const* node /* [5] */, const double* const* score /* [5] */, uint64_t total_reads,
+                    pm_place_result* result);
+
+/* reference BFS visit rank of every node (children ascending, level by level; placement.cpp:742-827) */
+int pm_index_bfs_ranks(const pm_index* idx, uint32_t* out /* [n_nodes] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANMAP_B200_H */

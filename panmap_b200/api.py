@@ -1,0 +1,402 @@
+"""ctypes binding of include/panmap_b200.h (mirrors placement::placeLite / seeding::rollingSyncmers)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+METRICS = ("log_raw", "log_cosine", "containment", "weighted_containment", "log_containment")
+PM_NONE = 0xFFFFFFFF
+
+
+class PanmapError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"panmap_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(_HERE, "libpanmap_b200.so")
+
+
+def build(force=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    mk = os.path.join(_HERE, "csrc", "Makefile")
+    args = ["make", "-f", mk] + (["-B"] if force else [])
+    subprocess.run(args, check=True, cwd=os.path.dirname(_HERE))
+
+
+class SeedParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("s", C.c_int32), ("t", C.c_int32), ("l", C.c_int32), ("open", C.c_int32), ("hpc", C.c_int32)]
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("n_deltas", C.c_uint64), ("delta_hash", C.c_void_p), ("delta_parent", C.c_void_p),
+                ("delta_child", C.c_void_p), ("node_offsets", C.c_void_p), ("parent_index", C.c_void_p), ("seed", SeedParams)]
+
+
+class PlaceParams(C.Structure):
+    """== placement::TraversalParams (placement.hpp:28-54), hot-path subset; defaults are the CLI defaults."""
+    _fields_ = [("trim_start", C.c_int32), ("trim_end", C.c_int32), ("min_read_support", C.c_int32), ("dedup_reads", C.c_int32),
+                ("force_leaf", C.c_int32), ("skip_node_index", C.c_uint32), ("seed_mask_fraction", C.c_double),
+                ("want_node_scores", C.c_int32), ("reserved", C.c_int32)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.min_read_support = -1
+        self.skip_node_index = PM_NONE
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class PlaceResult(C.Structure):
+    _fields_ = [("best_score", C.c_double * 5), ("best_index", C.c_uint32 * 5), ("tied_count", C.c_uint64 * 5),
+                ("total_reads", C.c_uint64), ("unique_seeds", C.c_uint64), ("read_unique_seed_count", C.c_uint64),
+                ("total_read_seed_frequency", C.c_int64), ("min_read_support", C.c_int64), ("read_magnitude", C.c_double),
+                ("log_containment_denominator", C.c_double), ("weighted_containment_denominator", C.c_double),
+                ("stage_ms", C.c_float * 8)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libpanmap_b200.so; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise PanmapError(-2, f"{p} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(p)
+    L.pm_last_error.restype = C.c_char_p
+    L.pm_host_index_node_id.restype = C.c_char_p
+    L.pm_host_index_node_id.argtypes = [C.c_void_p, C.c_uint64]
+    L.pm_host_index_read.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.pm_host_index_free.argtypes = [C.c_void_p]
+    L.pm_host_index_desc.argtypes = [C.c_void_p, C.POINTER(IndexDesc)]
+    L.pm_index_create.argtypes = [C.POINTER(IndexDesc), C.c_int, C.POINTER(C.c_void_p)]
+    L.pm_index_create_shard.argtypes = [C.POINTER(IndexDesc), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
+    L.pm_index_destroy.argtypes = [C.c_void_p]
+    for f in ("pm_index_num_nodes", "pm_index_num_deltas", "pm_index_num_distinct_seeds"):
+        getattr(L, f).restype = C.c_uint64
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.pm_index_shard_range.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.pm_index_genome_metrics.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pm_index_bfs_ranks.argtypes = [C.c_void_p, C.c_void_p]
+    L.pm_workspace_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.pm_workspace_destroy.argtypes = [C.c_void_p]
+    L.pm_place.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_reads_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_place_resident.argtypes = [C.c_void_p, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_get_tied.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+    L.pm_get_node_scores.argtypes = [C.c_void_p, C.c_void_p]
+    L.pm_get_node_metrics.argtypes = [C.c_void_p, C.c_void_p]
+    L.pm_get_seed_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_rolling_syncmers.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pm_read_seeds.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SeedParams), C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p]
+    L.pm_stage_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams)]
+    L.pm_stage_table_size.restype = C.c_int64
+    L.pm_stage_table_size.argtypes = [C.c_void_p]
+    L.pm_stage_table_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_stage_table_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_stage_score.argtypes = [C.c_void_p, C.POINTER(PlaceParams)]
+    L.pm_stage_records_size.restype = C.c_int64
+    L.pm_stage_records_size.argtypes = [C.c_void_p, C.c_int]
+    L.pm_stage_records_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_stage_select.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceResult)]
+    L.pm_host_alloc.restype = C.c_void_p
+    L.pm_host_alloc.argtypes = [C.c_uint64]
+    L.pm_host_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _ck(rc):
+    if rc < 0:
+        raise PanmapError(rc, lib().pm_last_error().decode(errors="replace"))
+    return rc
+
+
+def device_count():
+    return lib().pm_device_count()
+
+
+def pack_reads(reads):
+    """list of bytes/str -> (uint8 array of concatenated bases, uint64 offsets[n+1])"""
+    bs = [r.encode() if isinstance(r, str) else bytes(r) for r in reads]
+    off = np.zeros(len(bs) + 1, dtype=np.uint64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, dtype=np.uint8)
+    return buf, off
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class HostIndex:
+    """A parsed ``.idx`` (index_single_mode.cpp:1561-1636) or a set of flat arrays in reference-native widths."""
+
+    def __init__(self, hash, parent, child, offsets, parent_index, k, s, t, l, open=0, hpc=0, node_ids=None):
+        self.hash = np.ascontiguousarray(hash, dtype=np.uint64)
+        self.parent = np.ascontiguousarray(parent, dtype=np.int16)
+        self.child = np.ascontiguousarray(child, dtype=np.int16)
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        self.parent_index = np.ascontiguousarray(parent_index, dtype=np.uint32)
+        self.k, self.s, self.t, self.l, self.open, self.hpc = int(k), int(s), int(t), int(l), int(open), int(hpc)
+        self.node_ids = node_ids
+        self.n_nodes = int(self.parent_index.size)
+        self.n_deltas = int(self.hash.size)
+
+    @classmethod
+    def read(cls, path):
+        L = lib()
+        h = C.c_void_p()
+        _ck(L.pm_host_index_read(os.fsencode(path), C.byref(h)))
+        try:
+            d = IndexDesc()
+            _ck(L.pm_host_index_desc(h, C.byref(d)))
+            N, D = d.n_nodes, d.n_deltas
+
+            def arr(p, n, dt):
+                if n == 0:
+                    return np.zeros(0, dtype=dt)
+                return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
+            ids = [L.pm_host_index_node_id(h, i).decode() for i in range(N)]
+            return cls(arr(d.delta_hash, D, np.uint64), arr(d.delta_parent, D, np.int16), arr(d.delta_child, D, np.int16),
+                       arr(d.node_offsets, N + 1, np.uint64), arr(d.parent_index, N, np.uint32),
+                       d.seed.k, d.seed.s, d.seed.t, d.seed.l, d.seed.open, d.seed.hpc, ids)
+        finally:
+            L.pm_host_index_free(h)
+
+    def desc(self):
+        d = IndexDesc()
+        d.n_nodes, d.n_deltas = self.n_nodes, self.n_deltas
+        d.delta_hash, d.delta_parent, d.delta_child = _ptr(self.hash), _ptr(self.parent), _ptr(self.child)
+        d.node_offsets, d.parent_index = _ptr(self.offsets), _ptr(self.parent_index)
+        d.seed = SeedParams(self.k, self.s, self.t, self.l, self.open, self.hpc)
+        return d
+
+
+class Index:
+    """Flattened index resident in HBM (replaces LiteTree + the SoA hookup of placement.cpp:1021-1092)."""
+
+    def __init__(self, host, device=0, shard=0, n_shards=1):
+        self.host = host
+        self._h = C.c_void_p()
+        d = host.desc()
+        _ck(lib().pm_index_create_shard(C.byref(d), device, shard, n_shards, C.byref(self._h)))
+        self.n_nodes = host.n_nodes
+
+    def close(self):
+        if self._h:
+            lib().pm_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_distinct_seeds(self):
+        return lib().pm_index_num_distinct_seeds(self._h)
+
+    def shard_range(self):
+        b, e = C.c_uint64(), C.c_uint64()
+        _ck(lib().pm_index_shard_range(self._h, C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def genome_metrics(self):
+        m = np.zeros(self.n_nodes, dtype=np.float64)
+        u = np.zeros(self.n_nodes, dtype=np.int64)
+        _ck(lib().pm_index_genome_metrics(self._h, _ptr(m), _ptr(u)))
+        return m, u
+
+    def bfs_ranks(self):
+        r = np.zeros(self.n_nodes, dtype=np.uint32)
+        _ck(lib().pm_index_bfs_ranks(self._h, _ptr(r)))
+        return r
+
+
+class Placement:
+    """== placement::PlacementResult (placement.hpp:157-235): scores, best node, tied nodes per metric + read stats."""
+
+    def __init__(self, res, tied, node_ids=None):
+        self.raw = res
+        self.best_score = {m: res.best_score[i] for i, m in enumerate(METRICS)}
+        self.best_index = {m: res.best_index[i] for i, m in enumerate(METRICS)}
+        self.tied = {m: tied[i] for i, m in enumerate(METRICS)}
+        self.node_ids = node_ids
+        self.stage_ms = list(res.stage_ms)
+
+    def tsv(self):
+        """the <prefix>.placement.tsv the reference writes (placement.cpp:1952-1985)"""
+        def name(i):
+            return self.node_ids[i] if self.node_ids is not None and i < len(self.node_ids) else ""
+        lines = ["metric\tscore\tnodes"]
+        for m in METRICS:
+            t = self.tied[m]
+            nodes = ",".join(name(int(i)) for i in t) if len(t) else (name(self.best_index[m]) if self.best_index[m] != PM_NONE else "")
+            lines.append(f"{m}\t{self.best_score[m]:.6f}\t{nodes}")
+        return "\n".join(lines) + "\n"
+
+
+class Workspace:
+    """Per-sample state (one CUDA stream); ``place`` == the compute part of placement::placeLite."""
+
+    def __init__(self, index):
+        self.index = index
+        self._h = C.c_void_p()
+        _ck(lib().pm_workspace_create(index._h, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().pm_workspace_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _finish(self, res):
+        tied = []
+        for m in range(5):
+            n = int(res.tied_count[m])
+            t = np.zeros(n, dtype=np.uint32)
+            if n:
+                _ck(lib().pm_get_tied(self._h, m, _ptr(t), n))
+            tied.append(t)
+        return Placement(res, tied, self.index.host.node_ids)
+
+    def place(self, reads, offsets, params=None):
+        params = params or PlaceParams()
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        res = PlaceResult()
+        _ck(lib().pm_place(self._h, _ptr(reads), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params), C.byref(res)))
+        return self._finish(res)
+
+    def place_raw(self, reads_ptr, offsets_ptr, n_reads, params):
+        """host pointers (e.g. pinned buffers); returns the PlaceResult struct only"""
+        res = PlaceResult()
+        _ck(lib().pm_place(self._h, reads_ptr, offsets_ptr, n_reads, C.byref(params), C.byref(res)))
+        return res
+
+    def upload(self, reads, offsets):
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _ck(lib().pm_reads_upload(self._h, _ptr(reads), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1))
+
+    def place_resident(self, params=None, full=True):
+        params = params or PlaceParams()
+        res = PlaceResult()
+        _ck(lib().pm_place_resident(self._h, C.byref(params), C.byref(res)))
+        return self._finish(res) if full else res
+
+    def node_scores(self):
+        out = np.zeros((self.index.n_nodes, 5), dtype=np.float64)
+        _ck(lib().pm_get_node_scores(self._h, _ptr(out)))
+        return out
+
+    def node_metrics(self):
+        out = np.zeros((self.index.n_nodes, 5), dtype=np.float64)
+        _ck(lib().pm_get_node_metrics(self._h, _ptr(out)))
+        return out
+
+    def seed_table(self, cap=None):
+        cap = int(cap or (1 << 22))
+        while True:
+            h = np.zeros(cap, dtype=np.uint64)
+            c = np.zeros(cap, dtype=np.int64)
+            n = _ck(lib().pm_get_seed_table(self._h, _ptr(h), _ptr(c), cap))
+            if n <= cap:
+                o = np.argsort(h[:n], kind="stable")
+                return h[:n][o], c[:n][o]
+            cap = n
+
+    # ---- staged multi-GPU protocol (see include/panmap_b200.h) ----
+    def stage_seed(self, reads, offsets, params):
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _ck(lib().pm_stage_seed(self._h, _ptr(reads), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params)))
+
+    def stage_table_export(self):
+        n = _ck(lib().pm_stage_table_size(self._h))
+        h = np.zeros(max(n, 1), dtype=np.uint64)
+        c = np.zeros(max(n, 1), dtype=np.int64)
+        if n:
+            _ck(lib().pm_stage_table_export(self._h, _ptr(h), _ptr(c), n))
+        return h[:n], c[:n]
+
+    def stage_table_import(self, h, c):
+        h = np.ascontiguousarray(h, dtype=np.uint64)
+        c = np.ascontiguousarray(c, dtype=np.int64)
+        _ck(lib().pm_stage_table_import(self._h, _ptr(h), _ptr(c), h.size))
+
+    def stage_score(self, params):
+        _ck(lib().pm_stage_score(self._h, C.byref(params)))
+
+    def stage_records(self):
+        out = []
+        for m in range(5):
+            n = _ck(lib().pm_stage_records_size(self._h, m))
+            r = np.zeros(max(n, 1), dtype=np.uint32)
+            v = np.zeros(max(n, 1), dtype=np.uint32)
+            s = np.zeros(max(n, 1), dtype=np.float64)
+            if n:
+                _ck(lib().pm_stage_records_export(self._h, m, _ptr(r), _ptr(v), _ptr(s), n))
+            out.append((r[:n], v[:n], s[:n]))
+        return out
+
+    def stage_select(self, records, total_reads):
+        """records: per metric (rank, node, score) arrays holding ALL ranks' records"""
+        counts = np.array([len(r[0]) for r in records], dtype=np.uint32)
+        keep = [tuple(np.ascontiguousarray(a) for a in r) for r in records]
+        P = C.c_void_p * 5
+        pr = P(*[a[0].ctypes.data if a[0].size else None for a in keep])
+        pn = P(*[a[1].ctypes.data if a[1].size else None for a in keep])
+        ps = P(*[a[2].ctypes.data if a[2].size else None for a in keep])
+        res = PlaceResult()
+        _ck(lib().pm_stage_select(self._h, _ptr(counts), pr, pn, ps, total_reads, C.byref(res)))
+        return self._finish(res)
+
+
+def rolling_syncmers(seqs, k, s, open=False, t=0, device=0):
+    """GPU seeding::rollingSyncmers(seq,k,s,open,t,returnAll=false) for a batch: list of (hash[], is_reverse[], pos[])."""
+    buf, off = pack_reads(seqs)
+    n = len(seqs)
+    lens = np.diff(off.astype(np.int64))
+    win = np.maximum(lens - k + 1, 0)
+    woff = np.concatenate([[0], np.cumsum(win)]).astype(np.int64)
+    tot = int(woff[-1])
+    h = np.zeros(max(tot, 1), dtype=np.uint64)
+    r = np.zeros(max(tot, 1), dtype=np.uint8)
+    p = np.zeros(max(tot, 1), dtype=np.int64)
+    c = np.zeros(max(n, 1), dtype=np.uint64)
+    _ck(lib().pm_rolling_syncmers(device, _ptr(buf), off.ctypes.data_as(C.c_void_p), n, k, s, int(bool(open)), t,
+                                  _ptr(h), _ptr(r), _ptr(p), _ptr(c)))
+    return [(h[woff[i]:woff[i] + int(c[i])], r[woff[i]:woff[i] + int(c[i])], p[woff[i]:woff[i] + int(c[i])]) for i in range(n)]
+
+
+def read_seeds(seqs, k, s, t, l, open=False, trim_start=0, trim_end=0, device=0):
+    """per-read seeds exactly as placeLite counts them (placement.cpp:1598-1686): list of hash arrays"""
+    buf, off = pack_reads(seqs)
+    n = len(seqs)
+    lens = np.diff(off.astype(np.int64))
+    win = np.maximum(lens - k + 1, 0)
+    woff = np.concatenate([[0], np.cumsum(win)]).astype(np.int64)
+    tot = int(woff[-1])
+    h = np.zeros(max(tot, 1), dtype=np.uint64)
+    c = np.zeros(max(n, 1), dtype=np.uint64)
+    sp = SeedParams(k, s, t, l, int(bool(open)), 0)
+    _ck(lib().pm_read_seeds(device, _ptr(buf), off.ctypes.data_as(C.c_void_p), n, C.byref(sp), trim_start, trim_end, _ptr(h), _ptr(c)))
+    return [h[woff[i]:woff[i] + int(c[i])] for i in range(n)]

@@ -1,0 +1,745 @@
+// pm_api.cu -- the C ABI (include/panmap_b200.h): index upload, per-sample workspaces, the placement pipeline.
+// All compute runs in the kernels of pm_kernels.cu; the host code here only prepares launches, moves the
+// inputs/outputs and assembles the result structure.  There is no CPU compute fallback.
+#include "pm_host.h"
+#include "pm_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace pm;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+template <class F>
+int guarded(F&& f) {
+    try { return f(); }
+    catch (const CudaError& e) { return fail(PM_ERR_CUDA, e.what()); }
+    catch (const IoError& e) { return fail(PM_ERR_IO, e.what()); }
+    catch (const Unsupported& e) { return fail(PM_ERR_UNSUPPORTED, e.what()); }
+    catch (const std::bad_alloc&) { return fail(PM_ERR_CAPACITY, "out of host memory"); }
+    catch (const std::exception& e) { return fail(PM_ERR_INVALID, e.what()); }
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void alloc(size_t count) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void ensure(size_t count) { if (count > n) alloc(count + count / 8); }
+    void upload(const std::vector<T>& v, cudaStream_t st = 0) {
+        alloc(v.size());
+        if (!v.empty()) { CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
+    }
+};
+template <class T>
+struct PinBuf {
+    T* p = nullptr; size_t n = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    void ensure(size_t count) {
+        if (count <= n) return;
+        if (p) { cudaFreeHost(p); p = nullptr; }
+        n = count + count / 8;
+        CK(cudaMallocHost(&p, n * sizeof(T)));
+    }
+};
+
+int deviceCountNoThrow() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+}  // namespace
+
+struct pm_host_index { HostIndex h; };
+
+struct pm_index {
+    int device = 0; int nSM = 148;
+    FlatIndex F;  // host copy of the small arrays (tree) is kept for result assembly; big vectors are released
+    DevBuf<u32> seedId, pc, lNode, parent, closeOff, closeList, carrySlot, chainOff, chainNodes, bfsNodes, bfsRanks, dictVals;
+    DevBuf<u64> lOff, dictKeys, dictHash, homo;
+    DevBuf<double> gMag, log1pLut, log1pSmall;
+    DevBuf<unsigned char> isLeaf;
+    DevBuf<K1Tile> k1Tiles;
+    DevBuf<BigNode> bigNodes;
+    DevBuf<SeedTables> seedTables;
+    DevIndexView view{};
+    std::vector<double> gMagSqHost; std::vector<int64_t> gUniqueHost;
+};
+
+struct pm_workspace {
+    pm_index* idx = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[9]{};
+    // inputs
+    DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed;
+    PinBuf<u64> hPackedOff;
+    u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
+    // table
+    DevBuf<u64> keys; DevBuf<u32> counts; u64 tableCap = 0;
+    DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
+    DevBuf<double> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist;
+    DevBuf<NodeDelta> delta, bigPartial; DevBuf<unsigned> bigDone;
+    DevBuf<u64> chainA;
+    DevBuf<double> scores, metrics, blockMaxAndBfs;
+    DevBuf<u32> recRank, recNode; DevBuf<double> recScore; u32 recCap = 0;
+    DevBuf<u32> tieNode; u32 tieCap = 0;
+    DevBuf<u64> expHash; DevBuf<long long> expCount; DevBuf<unsigned> expCounter;
+    // host staging (pinned)
+    PinBuf<unsigned char> hStage;
+    // results of the last sample
+    bool haveResult = false; bool wantMetrics = false;
+    pm_place_params lastParams{};
+    Selection hSel[5]{}; SampleAcc hAcc{}; SampleScalars hScal{};
+    std::vector<u32> tied[5];
+    WorkspaceView view{};
+};
+
+namespace {
+
+void setDevice(int dev) { CK(cudaSetDevice(dev)); }
+
+void buildViews(pm_index* I) {
+    FlatIndex& F = I->F;
+    DevIndexView& V = I->view;
+    V.nNodes = F.N; V.nodeBegin = F.nodeBegin; V.nodeEnd = F.nodeEnd; V.nLocal = F.nLocal; V.nAnc = F.nAnc;
+    V.nLocalDeltas = F.nLocalDeltas; V.nSeeds = F.S;
+    V.seedId = I->seedId.p; V.pc = I->pc.p; V.lOff = I->lOff.p; V.lNode = I->lNode.p;
+    V.k1Tiles = I->k1Tiles.p; V.nK1Tiles = (u32)F.k1Tiles.size();
+    V.bigNodes = I->bigNodes.p; V.nBigNodes = (u32)F.bigNodes.size(); V.nBigPartials = F.nBigPartials;
+    V.parent = I->parent.p; V.gMag = I->gMag.p; V.closeOff = I->closeOff.p; V.closeList = I->closeList.p;
+    V.carrySlot = I->carrySlot.p; V.chainOff = I->chainOff.p; V.chainNodes = I->chainNodes.p;
+    V.nK2Tiles = F.nK2Tiles; V.chainTotal = (u32)F.chainNodes.size();
+    V.isLeaf = I->isLeaf.p;
+    V.bfsNodes = I->bfsNodes.p; V.bfsRanks = I->bfsRanks.p; V.nShardNodes = F.nodeEnd - F.nodeBegin;
+    V.nBfsBlocks = (V.nShardNodes + kBfsBlock - 1) / kBfsBlock;
+    V.dictKeys = I->dictKeys.p; V.dictVals = I->dictVals.p; V.dictMask = F.dictMask; V.dictHash = I->dictHash.p;
+    V.rootDBegin = F.rootDBegin; V.rootDCount = F.rootDCount; V.hasRoot = 1;
+    V.log1pLut = I->log1pLut.p; V.log1pSmall = I->log1pSmall.p;
+    V.ln2 = std::log1p(1.0);
+}
+
+int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t nShards, pm_index** out) {
+    if (!desc || !out) return fail(PM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (deviceCountNoThrow() <= device || device < 0)
+        return fail(PM_ERR_NO_DEVICE, "no usable CUDA device " + std::to_string(device) + " (this library has no CPU fallback)");
+    return guarded([&]() -> int {
+        std::unique_ptr<pm_index> I(new pm_index());
+        I->device = device;
+        flattenIndex(*desc, shard, nShards, I->F);
+        setDevice(device);
+        cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+        I->nSM = prop.multiProcessorCount;
+        FlatIndex& F = I->F;
+        I->seedId.upload(F.seedId); I->pc.upload(F.pc); I->lNode.upload(F.lNode); I->lOff.upload(F.lOff);
+        I->parent.upload(F.parent); I->gMag.upload(F.gMag); I->closeOff.upload(F.closeOff); I->closeList.upload(F.closeList);
+        I->carrySlot.upload(F.carrySlot); I->chainOff.upload(F.chainOff); I->chainNodes.upload(F.chainNodes);
+        I->isLeaf.upload(F.isLeaf); I->bfsNodes.upload(F.bfsNodes); I->bfsRanks.upload(F.bfsRanks);
+        I->dictKeys.upload(F.dictKeys); I->dictVals.upload(F.dictVals); I->dictHash.upload(F.dictHash);
+        {
+            std::vector<K1Tile> t(F.k1Tiles.size());
+            for (size_t i = 0; i < t.size(); ++i) {
+                t[i].dBegin = F.k1Tiles[i].dBegin; t[i].dCount = F.k1Tiles[i].dCount; t[i].lnBegin = F.k1Tiles[i].lnBegin;
+                t[i].lnEnd = F.k1Tiles[i].lnEnd; t[i].kind = F.k1Tiles[i].kind; t[i].bigSlot = F.k1Tiles[i].bigSlot; t[i].bigNode = F.k1Tiles[i].bigNode;
+            }
+            I->k1Tiles.upload(t);
+            std::vector<BigNode> b(F.bigNodes.size());
+            for (size_t i = 0; i < b.size(); ++i) { b[i].localNode = F.bigNodes[i].localNode; b[i].firstPartial = F.bigNodes[i].firstPartial; b[i].nPartials = F.bigNodes[i].nPartials; b[i].pad = 0; }
+            I->bigNodes.upload(b);
+        }
+        {
+            std::vector<double> lut(kLog1pLut), small(32768);
+            for (int c = 0; c < kLog1pLut; ++c) lut[c] = std::log1p((double)c);
+            for (int c = 0; c < 32768; ++c) small[c] = std::log1p((double)c);
+            I->log1pLut.upload(lut); I->log1pSmall.upload(small);
+            std::vector<u64> homo(F.homo, F.homo + 4);
+            I->homo.upload(homo);
+            std::vector<SeedTables> st(1);
+            buildSeedTables(st[0], F.sp.k, F.sp.s);
+            I->seedTables.upload(st);
+        }
+        I->gMagSqHost = F.gMagSq; I->gUniqueHost = F.gUnique;
+        buildViews(I.get());
+        // release the big host vectors (the device now owns them)
+        std::vector<u32>().swap(F.seedId); std::vector<u32>().swap(F.pc); std::vector<u64>().swap(F.dictKeys);
+        std::vector<u32>().swap(F.dictVals); std::vector<u64>().swap(F.dictHash);
+        std::vector<double>().swap(F.gMagSq); std::vector<int64_t>().swap(F.gUnique);
+        *out = I.release();
+        return PM_OK;
+    });
+}
+
+void refreshView(pm_workspace* W) {
+    WorkspaceView& V = W->view;
+    V.keys = W->keys.p; V.counts = W->counts.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
+    V.acc = W->acc.p; V.ell = W->ell.p; V.touched = W->touched.p; V.touchedCap = (u32)W->touched.n; V.countHist = W->countHist.p;
+    V.delta = W->delta.p; V.bigPartial = W->bigPartial.p; V.bigDone = W->bigDone.p; V.chainA = W->chainA.p;
+    V.scores = W->scores.p; V.metrics = W->wantMetrics ? W->metrics.p : nullptr; V.blockMax = W->blockMaxAndBfs.p;
+    V.recRank = W->recRank.p; V.recNode = W->recNode.p; V.recScore = W->recScore.p; V.recCap = W->recCap;
+    V.tieNode = W->tieNode.p; V.tieCap = W->tieCap; V.sel = W->sel.p; V.scalars = W->scalars.p;
+}
+
+void ensureTable(pm_workspace* W, u64 wantCap) {
+    u64 cap = 1 << 12;
+    while (cap < wantCap) cap <<= 1;
+    if (cap <= W->tableCap) return;
+    W->keys.alloc(cap); W->counts.alloc(cap); W->tableCap = cap;
+    refreshView(W);
+}
+
+PlaceOpts makeOpts(const pm_place_params& p, bool wantMetrics) {
+    PlaceOpts o; o.minReadSupport = p.min_read_support; o.forceLeaf = p.force_leaf; o.skipNode = p.skip_node_index;
+    o.wantMetrics = wantMetrics ? 1 : 0; return o;
+}
+
+void checkParams(const pm_place_params* p) {
+    if (!p) throw std::runtime_error("null params");
+    if (p->dedup_reads) throw Unsupported("dedup_reads is not implemented on the GPU path yet");
+    if (p->seed_mask_fraction > 0.0) throw Unsupported("seed_mask_fraction > 0 is not implemented on the GPU path yet");
+    if (p->trim_start < 0 || p->trim_end < 0) throw std::runtime_error("negative trim");
+}
+
+// host side: chunk offsets of the packed layout (ceil(len/32) 16-byte chunks per read)
+void hostPackedOffsets(pm_workspace* W, const uint64_t* off, u64 n, int k) {
+    W->hPackedOff.ensure(n + 1);
+    u64 acc = 0, win = 0;
+    for (u64 i = 0; i < n; ++i) {
+        W->hPackedOff.p[i] = acc;
+        if (off[i + 1] < off[i]) throw std::runtime_error("read offsets not monotone");
+        const u64 L = off[i + 1] - off[i];
+        if (L > 0x7FFFFFF0ull) throw std::runtime_error("read longer than 2^31 bases");
+        acc += (L + 31) >> 5;
+        if (L >= (u64)k) win += L - (u64)k + 1;
+    }
+    W->hPackedOff.p[n] = acc;
+    W->nChunks = acc; W->totalWindows = win;
+}
+
+void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n) {
+    pm_index* I = W->idx;
+    const u64 base0 = n ? off[0] : 0;
+    const u64 total = n ? off[n] - base0 : 0;
+    hostPackedOffsets(W, off, n, I->F.sp.k);
+    W->nReads = n; W->totalBases = total;
+    W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1); W->packed.ensure(W->nChunks + 1);
+    if (base0 != 0) throw std::runtime_error("read_offsets[0] must be 0");
+    if (total) CK(cudaMemcpyAsync(W->reads.p, reads, total, cudaMemcpyHostToDevice, W->st));
+    CK(cudaMemcpyAsync(W->off.p, off, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->st));
+    CK(cudaMemcpyAsync(W->packedOff.p, W->hPackedOff.p, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->st));
+}
+
+void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
+    pm_index* I = W->idx;
+    const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
+    if (clearFirst) {
+        CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
+        launchTableClear(W->view, W->st);
+    }
+    launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->nReads, W->nChunks, W->packed.p, W->st);
+    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st);
+}
+
+void stageScore(pm_workspace* W, const pm_place_params& prm) {
+    pm_index* I = W->idx;
+    const PlaceOpts O = makeOpts(prm, W->wantMetrics);
+    launchFinalize(I->view, W->view, O, I->homo.p, W->st);
+    CK(cudaEventRecord(W->ev[3], W->st));
+    launchDeltas(I->view, W->view, I->nSM, W->st);
+    CK(cudaEventRecord(W->ev[4], W->st));
+    launchPrefixScores(I->view, W->view, O, W->st);
+    CK(cudaEventRecord(W->ev[5], W->st));
+    launchRecords(I->view, W->view, O, W->st);
+}
+
+// D2H of the small result block; returns after the stream is idle
+void fetchSmall(pm_workspace* W) {
+    W->hStage.ensure(sizeof(SampleAcc) + sizeof(SampleScalars) + 5 * sizeof(Selection));
+    unsigned char* h = W->hStage.p;
+    CK(cudaMemcpyAsync(h, W->acc.p, sizeof(SampleAcc), cudaMemcpyDeviceToHost, W->st));
+    CK(cudaMemcpyAsync(h + sizeof(SampleAcc), W->scalars.p, sizeof(SampleScalars), cudaMemcpyDeviceToHost, W->st));
+    CK(cudaMemcpyAsync(h + sizeof(SampleAcc) + sizeof(SampleScalars), W->sel.p, 5 * sizeof(Selection), cudaMemcpyDeviceToHost, W->st));
+    CK(cudaStreamSynchronize(W->st));
+    std::memcpy(&W->hAcc, h, sizeof(SampleAcc));
+    std::memcpy(&W->hScal, h + sizeof(SampleAcc), sizeof(SampleScalars));
+    std::memcpy(W->hSel, h + sizeof(SampleAcc) + sizeof(SampleScalars), 5 * sizeof(Selection));
+}
+
+void fillResult(pm_workspace* W, pm_place_result* r, u64 totalReads) {
+    const SampleScalars& S = W->hScal;
+    for (int m = 0; m < 5; ++m) {
+        r->best_score[m] = W->hSel[m].best;
+        r->tied_count[m] = W->tied[m].size();
+        r->best_index[m] = W->tied[m].empty() ? W->hSel[m].bestNode : W->tied[m].front();
+    }
+    r->total_reads = totalReads;
+    r->unique_seeds = (uint64_t)S.uniqueSeeds;
+    r->read_unique_seed_count = (uint64_t)S.uniqueKeptInt;
+    r->total_read_seed_frequency = S.totalFrequency;
+    r->min_read_support = S.minSupport;
+    r->read_magnitude = S.readMagnitude;
+    r->log_containment_denominator = S.logContDenom;
+    r->weighted_containment_denominator = S.wcDenom;
+}
+
+// tie lists -> host, finalizeTiedIndices semantics (placement.cpp:395-401): sort, unique, best = front
+void fetchTies(pm_workspace* W) {
+    for (int m = 0; m < 5; ++m) {
+        unsigned n = W->hAcc.tieCount[m];
+        if (n > W->tieCap) n = W->tieCap;
+        std::vector<u32>& t = W->tied[m];
+        t.assign(n, 0);
+        if (n) CK(cudaMemcpyAsync(t.data(), W->tieNode.p + (size_t)m * W->tieCap, n * sizeof(u32), cudaMemcpyDeviceToHost, W->st));
+    }
+    CK(cudaStreamSynchronize(W->st));
+    for (int m = 0; m < 5; ++m) {
+        std::vector<u32>& t = W->tied[m];
+        const Selection& s = W->hSel[m];
+        // the reference pushes bestNodeIndex (possibly UINT32_MAX before any improvement) next to every tie, and
+        // an improvement leaves [node] in the list
+        if (s.bestNode != kNone || !t.empty()) t.push_back(s.bestNode);
+        std::sort(t.begin(), t.end());
+        t.erase(std::unique(t.begin(), t.end()), t.end());
+    }
+}
+
+int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, bool inputsResident, const char* reads,
+             const uint64_t* off, u64 n) {
+    pm_index* I = W->idx;
+    setDevice(I->device);
+    checkParams(prm);
+    if (!res) throw std::runtime_error("null result");
+    std::memset(res, 0, sizeof(*res));
+    W->wantMetrics = false;
+    W->lastParams = *prm;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        CK(cudaEventRecord(W->ev[0], W->st));
+        if (!inputsResident) uploadReads(W, reads, off, n);
+        if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, W->totalWindows / 4));
+        refreshView(W);
+        CK(cudaEventRecord(W->ev[1], W->st));
+        stageSeed(W, true, *prm);
+        CK(cudaEventRecord(W->ev[2], W->st));
+        stageScore(W, *prm);
+        launchChain(W->view, nullptr, W->st);
+        launchTies(I->view, W->view, makeOpts(*prm, false), W->st);
+        CK(cudaEventRecord(W->ev[6], W->st));
+        fetchSmall(W);
+        launchResetEll(W->view, W->st);
+        const bool tableTight = (u64)W->hAcc.entries * 10 > W->tableCap * 7;
+        if (W->hAcc.overflow || tableTight) {
+            // grow and redo: the table (or a list) was too small for this sample
+            CK(cudaStreamSynchronize(W->st));
+            if (W->hAcc.overflow && !tableTight && attempt >= 2) throw std::runtime_error("internal capacity exceeded");
+            ensureTable(W, W->tableCap * 4);
+            continue;
+        }
+        fetchTies(W);
+        CK(cudaEventRecord(W->ev[7], W->st));
+        CK(cudaStreamSynchronize(W->st));
+        fillResult(W, res, W->nReads);
+        float ms = 0;
+        const int a[7] = {0, 1, 2, 3, 4, 5, 6}, b[7] = {1, 2, 3, 4, 5, 6, 7};
+        for (int i = 0; i < 7; ++i) { cudaEventElapsedTime(&ms, W->ev[a[i]], W->ev[b[i]]); res->stage_ms[i] = ms; }
+        cudaEventElapsedTime(&ms, W->ev[0], W->ev[7]); res->stage_ms[7] = ms;
+        W->haveResult = true;
+        return PM_OK;
+    }
+    throw std::runtime_error("read seed table kept overflowing");
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+const char* pm_last_error(void) { return g_err.c_str(); }
+int pm_abi_version(void) { return PM_ABI_VERSION; }
+int pm_device_count(void) { return deviceCountNoThrow(); }
+
+int pm_host_index_read(const char* path, pm_host_index** out) {
+    if (!path || !out) return fail(PM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    return guarded([&]() -> int {
+        std::unique_ptr<pm_host_index> h(new pm_host_index());
+        readIdxFile(path, h->h);
+        *out = h.release();
+        return PM_OK;
+    });
+}
+void pm_host_index_free(pm_host_index* h) { delete h; }
+int pm_host_index_desc(const pm_host_index* h, pm_index_desc* out) {
+    if (!h || !out) return fail(PM_ERR_INVALID, "null argument");
+    const HostIndex& x = h->h;
+    out->n_nodes = x.parentIndex.size(); out->n_deltas = x.hash.size();
+    out->delta_hash = x.hash.data(); out->delta_parent = x.parentCount.data(); out->delta_child = x.childCount.data();
+    out->node_offsets = x.nodeOffsets.data(); out->parent_index = x.parentIndex.data(); out->seed = x.sp;
+    return PM_OK;
+}
+const char* pm_host_index_node_id(const pm_host_index* h, uint64_t node) {
+    if (!h || node >= h->h.nodeIds.size()) return "";
+    return h->h.nodeIds[node].c_str();
+}
+
+int pm_index_create(const pm_index_desc* desc, int device, pm_index** out) { return createIndex(desc, device, 0, 1, out); }
+int pm_index_create_shard(const pm_index_desc* desc, int device, uint32_t shard, uint32_t n_shards, pm_index** out) {
+    return createIndex(desc, device, shard, n_shards, out);
+}
+void pm_index_destroy(pm_index* idx) { if (idx) { cudaSetDevice(idx->device); delete idx; } }
+uint64_t pm_index_num_nodes(const pm_index* idx) { return idx ? idx->F.N : 0; }
+uint64_t pm_index_num_deltas(const pm_index* idx) { return idx ? idx->F.D : 0; }
+uint64_t pm_index_num_distinct_seeds(const pm_index* idx) { return idx ? idx->F.S : 0; }
+int pm_index_shard_range(const pm_index* idx, uint64_t* b, uint64_t* e) {
+    if (!idx || !b || !e) return fail(PM_ERR_INVALID, "null argument");
+    *b = idx->F.nodeBegin; *e = idx->F.nodeEnd; return PM_OK;
+}
+int pm_index_genome_metrics(const pm_index* idx, double* magSq, int64_t* uniq) {
+    if (!idx) return fail(PM_ERR_INVALID, "null argument");
+    if (magSq) std::memcpy(magSq, idx->gMagSqHost.data(), idx->gMagSqHost.size() * sizeof(double));
+    if (uniq) std::memcpy(uniq, idx->gUniqueHost.data(), idx->gUniqueHost.size() * sizeof(int64_t));
+    return PM_OK;
+}
+int pm_index_bfs_ranks(const pm_index* idx, uint32_t* out) {
+    if (!idx || !out) return fail(PM_ERR_INVALID, "null argument");
+    std::memcpy(out, idx->F.bfsRank.data(), idx->F.bfsRank.size() * sizeof(uint32_t));
+    return PM_OK;
+}
+
+int pm_workspace_create(pm_index* idx, pm_workspace** out) {
+    if (!idx || !out) return fail(PM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    return guarded([&]() -> int {
+        setDevice(idx->device);
+        std::unique_ptr<pm_workspace> W(new pm_workspace());
+        W->idx = idx;
+        CK(cudaStreamCreateWithFlags(&W->st, cudaStreamNonBlocking));
+        for (auto& e : W->ev) CK(cudaEventCreate(&e));
+        const FlatIndex& F = idx->F;
+        const DevIndexView& V = idx->view;
+        W->acc.alloc(1); W->scalars.alloc(1); W->sel.alloc(5);
+        W->ell.alloc(F.S ? F.S : 1); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(double), W->st));
+        W->touched.alloc(F.S ? F.S : 1);
+        W->countHist.alloc(kLog1pLut);
+        W->delta.alloc(F.N); CK(cudaMemsetAsync(W->delta.p, 0, F.N * sizeof(NodeDelta), W->st));
+        W->bigPartial.alloc(F.nBigPartials ? F.nBigPartials : 1);
+        W->bigDone.alloc(F.bigNodes.size() ? F.bigNodes.size() : 1);
+        CK(cudaMemsetAsync(W->bigDone.p, 0, W->bigDone.n * sizeof(unsigned), W->st));
+        W->chainA.alloc((size_t)(V.chainTotal ? V.chainTotal : 1) * 9);
+        W->scores.alloc(F.N * 5); CK(cudaMemsetAsync(W->scores.p, 0, F.N * 5 * sizeof(double), W->st));
+        W->blockMaxAndBfs.alloc((size_t)V.nBfsBlocks * 5 + (size_t)V.nShardNodes * 5 + 8);
+        W->recCap = V.nShardNodes ? V.nShardNodes : 1;
+        W->recRank.alloc((size_t)5 * W->recCap); W->recNode.alloc((size_t)5 * W->recCap); W->recScore.alloc((size_t)5 * W->recCap);
+        W->tieCap = V.nShardNodes ? V.nShardNodes : 1;
+        W->tieNode.alloc((size_t)5 * W->tieCap);
+        W->expCounter.alloc(1);
+        CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
+        CK(cudaStreamSynchronize(W->st));
+        refreshView(W.get());
+        *out = W.release();
+        return PM_OK;
+    });
+}
+void pm_workspace_destroy(pm_workspace* ws) {
+    if (!ws) return;
+    cudaSetDevice(ws->idx->device);
+    if (ws->st) { cudaStreamSynchronize(ws->st); cudaStreamDestroy(ws->st); }
+    for (auto& e : ws->ev) if (e) cudaEventDestroy(e);
+    delete ws;
+}
+
+int pm_place(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads, const pm_place_params* params,
+             pm_place_result* result) {
+    if (!ws || !read_offsets || (!reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int { return runPlace(ws, params, result, false, reads, read_offsets, n_reads); });
+}
+int pm_reads_upload(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads) {
+    if (!ws || !read_offsets || (!reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        uploadReads(ws, reads, read_offsets, n_reads);
+        CK(cudaStreamSynchronize(ws->st));
+        return PM_OK;
+    });
+}
+int pm_place_resident(pm_workspace* ws, const pm_place_params* params, pm_place_result* result) {
+    if (!ws) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int { return runPlace(ws, params, result, true, nullptr, nullptr, 0); });
+}
+
+int pm_get_tied(pm_workspace* ws, int metric, uint32_t* out, uint64_t cap) {
+    if (!ws || !ws->haveResult || metric < 0 || metric >= 5) return fail(PM_ERR_INVALID, "no result / bad metric");
+    const auto& t = ws->tied[metric];
+    if (out) std::memcpy(out, t.data(), std::min<uint64_t>(cap, t.size()) * sizeof(uint32_t));
+    return PM_OK;
+}
+int pm_get_node_scores(pm_workspace* ws, double* out) {
+    if (!ws || !out || !ws->haveResult) return fail(PM_ERR_INVALID, "no result");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        CK(cudaMemcpyAsync(out, ws->scores.p, ws->idx->F.N * 5 * sizeof(double), cudaMemcpyDeviceToHost, ws->st));
+        CK(cudaStreamSynchronize(ws->st));
+        return PM_OK;
+    });
+}
+// re-runs the scoring stages of the last sample with the numerator dump enabled (debug / parity tests)
+int pm_get_node_metrics(pm_workspace* ws, double* out) {
+    if (!ws || !out || !ws->haveResult) return fail(PM_ERR_INVALID, "no result");
+    return guarded([&]() -> int {
+        pm_index* I = ws->idx;
+        setDevice(I->device);
+        ws->metrics.ensure(I->F.N * 5);
+        CK(cudaMemsetAsync(ws->metrics.p, 0, I->F.N * 5 * sizeof(double), ws->st));
+        ws->wantMetrics = true; refreshView(ws);
+        // ell was reset after the sample: rebuild it from the (still intact) table, then K1 + K2 only
+        CK(cudaMemsetAsync(&ws->acc.p->touchedCount, 0, sizeof(unsigned), ws->st));
+        CK(cudaMemsetAsync(ws->acc.p->magSq, 0, 6 * sizeof(u64) + 6 * sizeof(long long), ws->st));
+        const PlaceOpts O = makeOpts(ws->lastParams, true);
+        launchFinalize(I->view, ws->view, O, I->homo.p, ws->st);
+        launchDeltas(I->view, ws->view, I->nSM, ws->st);
+        launchPrefixScores(I->view, ws->view, O, ws->st);
+        launchResetEll(ws->view, ws->st);
+        CK(cudaMemcpyAsync(out, ws->metrics.p, I->F.N * 5 * sizeof(double), cudaMemcpyDeviceToHost, ws->st));
+        CK(cudaStreamSynchronize(ws->st));
+        ws->wantMetrics = false; refreshView(ws);
+        return PM_OK;
+    });
+}
+int pm_get_seed_table(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap) {
+    if (!ws || !hash || !count) return fail(PM_ERR_INVALID, "null argument");
+    int n = 0;
+    const int rc = guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        ws->expHash.ensure(cap ? cap : 1); ws->expCount.ensure(cap ? cap : 1);
+        CK(cudaMemsetAsync(ws->expCounter.p, 0, sizeof(unsigned), ws->st));
+        launchTableExport(ws->view, ws->expHash.p, ws->expCount.p, ws->expCounter.p, cap, ws->st);
+        unsigned cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, ws->expCounter.p, sizeof(unsigned), cudaMemcpyDeviceToHost, ws->st));
+        CK(cudaStreamSynchronize(ws->st));
+        const u64 m = std::min<u64>(cnt, cap);
+        if (m) {
+            CK(cudaMemcpyAsync(hash, ws->expHash.p, m * sizeof(u64), cudaMemcpyDeviceToHost, ws->st));
+            CK(cudaMemcpyAsync(count, ws->expCount.p, m * sizeof(long long), cudaMemcpyDeviceToHost, ws->st));
+            CK(cudaStreamSynchronize(ws->st));
+        }
+        n = (int)cnt;
+        return PM_OK;
+    });
+    return rc == PM_OK ? n : rc;
+}
+
+// ---- seeding::rollingSyncmers / per-read seeds on the GPU (parity + drop-in for the host shim) ----
+static int seedListImpl(int device, const char* seqs, const uint64_t* off, uint64_t n, const pm_seed_params* sp, int trimStart,
+                        int trimEnd, int mode, uint64_t* outHash, uint8_t* outRev, int64_t* outPos, uint64_t* outCount) {
+    if (!off || (!seqs && n) || !sp || !outHash || !outCount) return fail(PM_ERR_INVALID, "null argument");
+    if (deviceCountNoThrow() <= device || device < 0) return fail(PM_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    return guarded([&]() -> int {
+        if (sp->k < 1 || sp->k > kMaxK || sp->s < 1 || sp->s > sp->k || sp->t < 0 || sp->t > sp->k - sp->s)
+            throw std::runtime_error("unsupported seeding parameters (need 1 <= s <= k <= 32, 0 <= t <= k-s)");
+        setDevice(device);
+        cudaStream_t st; CK(cudaStreamCreate(&st));
+        std::vector<u64> pOff(n + 1), wOff(n + 1);
+        u64 ch = 0, win = 0;
+        for (u64 i = 0; i < n; ++i) {
+            const u64 L = off[i + 1] - off[i];
+            pOff[i] = ch; wOff[i] = win;
+            ch += (L + 31) >> 5;
+            if (L >= (u64)sp->k) win += L - (u64)sp->k + 1;
+        }
+        pOff[n] = ch; wOff[n] = win;
+        const u64 total = n ? off[n] : 0;
+        DevBuf<char> dReads; DevBuf<u64> dOff, dPOff, dWOff, dHash, dCount; DevBuf<uint4> dPacked;
+        DevBuf<unsigned char> dRev; DevBuf<long long> dPos; DevBuf<SeedTables> dT;
+        dReads.alloc(total + 64); dOff.alloc(n + 1); dPOff.alloc(n + 1); dWOff.alloc(n + 1); dPacked.alloc(ch + 1);
+        dHash.alloc(win + 1); dCount.alloc(n + 1);
+        if (mode == 1) { dRev.alloc(win + 1); dPos.alloc(win + 1); }
+        if (total) CK(cudaMemcpyAsync(dReads.p, seqs, total, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dOff.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dPOff.p, pOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dWOff.p, wOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+        std::vector<SeedTables> T(1); buildSeedTables(T[0], sp->k, sp->s);
+        dT.alloc(1); CK(cudaMemcpyAsync(dT.p, T.data(), sizeof(SeedTables), cudaMemcpyHostToDevice, st));
+        const SeederParams P = makeSeederParams(sp->k, sp->s, sp->t, mode == 1 ? 1 : sp->l, sp->open, trimStart, trimEnd);
+        launchPackReads(dReads.p, dOff.p, dPOff.p, n, ch, dPacked.p, st);
+        launchSeedList(dPacked.p, dOff.p, dPOff.p, dWOff.p, n, P, dT.p, mode, dHash.p, dRev.p, dPos.p, dCount.p, st);
+        CK(cudaGetLastError());
+        if (win) CK(cudaMemcpyAsync(outHash, dHash.p, win * 8, cudaMemcpyDeviceToHost, st));
+        if (mode == 1 && win) {
+            if (outRev) CK(cudaMemcpyAsync(outRev, dRev.p, win, cudaMemcpyDeviceToHost, st));
+            if (outPos) CK(cudaMemcpyAsync(outPos, dPos.p, win * 8, cudaMemcpyDeviceToHost, st));
+        }
+        if (n) CK(cudaMemcpyAsync(outCount, dCount.p, n * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        cudaStreamDestroy(st);
+        return PM_OK;
+    });
+}
+int pm_rolling_syncmers(int device, const char* seqs, const uint64_t* seq_offsets, uint64_t n_seqs, int k, int s, int open, int t,
+                        uint64_t* out_hash, uint8_t* out_is_reverse, int64_t* out_pos, uint64_t* out_count) {
+    pm_seed_params sp{k, s, t, 1, open, 0};
+    return seedListImpl(device, seqs, seq_offsets, n_seqs, &sp, 0, 0, 1, out_hash, out_is_reverse, out_pos, out_count);
+}
+int pm_read_seeds(int device, const char* seqs, const uint64_t* seq_offsets, uint64_t n_seqs, const pm_seed_params* sp,
+                  int trim_start, int trim_end, uint64_t* out_hash, uint64_t* out_count) {
+    return seedListImpl(device, seqs, seq_offsets, n_seqs, sp, trim_start, trim_end, 2, out_hash, nullptr, nullptr, out_count);
+}
+
+// ---- staged entry points (multi-GPU) ----
+int pm_stage_seed(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads, const pm_place_params* params) {
+    if (!ws || !read_offsets || (!reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        checkParams(params);
+        ws->lastParams = *params; ws->wantMetrics = false; ws->haveResult = false;
+        uploadReads(ws, reads, read_offsets, n_reads);
+        if (ws->tableCap == 0) ensureTable(ws, std::max<u64>(1 << 16, ws->totalWindows / 4));
+        refreshView(ws);
+        stageSeed(ws, true, *params);
+        CK(cudaStreamSynchronize(ws->st));
+        SampleAcc a; CK(cudaMemcpy(&a, ws->acc.p, sizeof(a), cudaMemcpyDeviceToHost));
+        if (a.overflow) {  // grow and reseed
+            ensureTable(ws, ws->tableCap * 4);
+            stageSeed(ws, true, *params);
+            CK(cudaStreamSynchronize(ws->st));
+        }
+        return PM_OK;
+    });
+}
+int64_t pm_stage_table_size(pm_workspace* ws) {
+    if (!ws) return fail(PM_ERR_INVALID, "null argument");
+    int64_t n = 0;
+    const int rc = guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        CK(cudaMemsetAsync(ws->expCounter.p, 0, sizeof(unsigned), ws->st));
+        launchTableExport(ws->view, nullptr, nullptr, ws->expCounter.p, 0, ws->st);
+        unsigned cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, ws->expCounter.p, sizeof(unsigned), cudaMemcpyDeviceToHost, ws->st));
+        CK(cudaStreamSynchronize(ws->st));
+        n = cnt; return PM_OK;
+    });
+    return rc == PM_OK ? n : rc;
+}
+int pm_stage_table_export(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap) {
+    const int n = pm_get_seed_table(ws, hash, count, cap);
+    return n < 0 ? n : PM_OK;
+}
+// replaces this rank's table content by the union of all ranks' exports (the caller passes the concatenation)
+int pm_stage_table_import(pm_workspace* ws, const uint64_t* hash, const int64_t* count, uint64_t n) {
+    if (!ws || (n && (!hash || !count))) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        for (int attempt = 0; attempt < 6; ++attempt) {
+            if (ws->tableCap < 2 * n + 16) ensureTable(ws, 2 * n + 16);
+            refreshView(ws);
+            ws->expHash.ensure(n ? n : 1); ws->expCount.ensure(n ? n : 1);
+            if (n) {
+                CK(cudaMemcpyAsync(ws->expHash.p, hash, n * 8, cudaMemcpyHostToDevice, ws->st));
+                CK(cudaMemcpyAsync(ws->expCount.p, count, n * 8, cudaMemcpyHostToDevice, ws->st));
+            }
+            CK(cudaMemsetAsync(ws->acc.p, 0, sizeof(SampleAcc), ws->st));
+            launchTableClear(ws->view, ws->st);
+            launchTableImport(ws->view, ws->expHash.p, ws->expCount.p, n, ws->st);
+            CK(cudaStreamSynchronize(ws->st));
+            SampleAcc a; CK(cudaMemcpy(&a, ws->acc.p, sizeof(a), cudaMemcpyDeviceToHost));
+            if (!a.overflow) return PM_OK;
+            ensureTable(ws, ws->tableCap * 4);
+        }
+        throw std::runtime_error("table import kept overflowing");
+    });
+}
+int pm_stage_score(pm_workspace* ws, const pm_place_params* params) {
+    if (!ws) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        checkParams(params);
+        ws->lastParams = *params;
+        refreshView(ws);
+        stageScore(ws, *params);
+        fetchSmall(ws);
+        if (ws->hAcc.overflow) throw std::runtime_error("internal capacity exceeded while scoring");
+        return PM_OK;
+    });
+}
+int64_t pm_stage_records_size(pm_workspace* ws, int metric) {
+    if (!ws || metric < 0 || metric >= 5) return fail(PM_ERR_INVALID, "bad argument");
+    return std::min<unsigned>(ws->hAcc.recordCount[metric], ws->recCap);
+}
+int pm_stage_records_export(pm_workspace* ws, int metric, uint32_t* bfs_rank, uint32_t* node, double* score, uint64_t cap) {
+    if (!ws || metric < 0 || metric >= 5) return fail(PM_ERR_INVALID, "bad argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        const u64 n = std::min<u64>(std::min<unsigned>(ws->hAcc.recordCount[metric], ws->recCap), cap);
+        if (n) {
+            CK(cudaMemcpyAsync(bfs_rank, ws->recRank.p + (size_t)metric * ws->recCap, n * 4, cudaMemcpyDeviceToHost, ws->st));
+            CK(cudaMemcpyAsync(node, ws->recNode.p + (size_t)metric * ws->recCap, n * 4, cudaMemcpyDeviceToHost, ws->st));
+            CK(cudaMemcpyAsync(score, ws->recScore.p + (size_t)metric * ws->recCap, n * 8, cudaMemcpyDeviceToHost, ws->st));
+            CK(cudaStreamSynchronize(ws->st));
+        }
+        return PM_OK;
+    });
+}
+// all ranks' records of every metric (concatenated per metric; counts[5]) -> chain on the device -> this shard's ties
+int pm_stage_select(pm_workspace* ws, const uint32_t* counts, const uint32_t* const* bfs_rank, const uint32_t* const* node,
+                    const double* const* score, uint64_t total_reads, pm_place_result* result) {
+    if (!ws || !counts || !bfs_rank || !node || !score || !result) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        pm_index* I = ws->idx;
+        setDevice(I->device);
+        u32 maxN = 1;
+        for (int m = 0; m < 5; ++m) maxN = std::max(maxN, counts[m]);
+        if (maxN > ws->recCap) {
+            ws->recCap = maxN;
+            ws->recRank.alloc((size_t)5 * maxN); ws->recNode.alloc((size_t)5 * maxN); ws->recScore.alloc((size_t)5 * maxN);
+            refreshView(ws);
+        }
+        DevBuf<u32> dCounts; dCounts.alloc(5);
+        CK(cudaMemcpyAsync(dCounts.p, counts, 5 * sizeof(u32), cudaMemcpyHostToDevice, ws->st));
+        for (int m = 0; m < 5; ++m) {
+            if (!counts[m]) continue;
+            CK(cudaMemcpyAsync(ws->recRank.p + (size_t)m * ws->recCap, bfs_rank[m], counts[m] * 4ull, cudaMemcpyHostToDevice, ws->st));
+            CK(cudaMemcpyAsync(ws->recNode.p + (size_t)m * ws->recCap, node[m], counts[m] * 4ull, cudaMemcpyHostToDevice, ws->st));
+            CK(cudaMemcpyAsync(ws->recScore.p + (size_t)m * ws->recCap, score[m], counts[m] * 8ull, cudaMemcpyHostToDevice, ws->st));
+        }
+        launchChain(ws->view, dCounts.p, ws->st);
+        launchTies(I->view, ws->view, makeOpts(ws->lastParams, false), ws->st);
+        fetchSmall(ws);
+        launchResetEll(ws->view, ws->st);
+        fetchTies(ws);  // local ties + the best node (every rank adds it; the caller unions the lists)
+        std::memset(result, 0, sizeof(*result));
+        fillResult(ws, result, total_reads);
+        ws->haveResult = true;
+        return PM_OK;
+    });
+}
+
+void* pm_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pm_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+// pm_flatten.cpp -- one-time, sample-independent preparation of the seed-delta index for the GPU (host side).
+//
+// Input: the reference's flat view of a LiteIndex (pm_index_desc; placement.cpp:1021-1092).  Output (FlatIndex):
+//   * dense seed ids in first-appearance order along the DFS + per-node deltas re-sorted by seed id
+//     (12 B/delta -> 8 B/delta, and the per-delta hash probe becomes an array gather with locality: a node's
+//     lost seeds are mostly ancestral low ids, its new seeds are a contiguous fresh id range)
+//   * NodeMetrics::genomeMagnitudeSquared / genomeUniqueSeedCount per node, accumulated in exactly the reference's
+//     order (parent's value, then the node's deltas in stored order; placement.cpp:289-302,772-774) -> bit-identical
+//   * DFS subtree ends, depth, reference BFS ranks, leaf flags
+//   * "closers" CSR for the in-tile Euler-tour difference, ancestor chains + carry slots of the K2 tiles
+//   * K1 tile schedule (whole nodes per tile, nodes above kTileDeltas split into chunks)
+#include "pm_host.h"
+#include "pm_logic.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+
+namespace pm {
+
+static constexpr uint32_t kTileDeltasH = 4096, kTileNodesK1H = 2048, kTileNodesK2H = 512;
+static constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+void bfsRanks(const uint32_t* parent, uint64_t N, std::vector<uint32_t>& rank) {
+    rank.assign(N, 0);
+    if (N == 0) return;
+    std::vector<uint32_t> cOff(N + 1, 0), kids(N), order(N);
+    for (uint64_t v = 1; v < N; ++v) cOff[parent[v] + 1]++;
+    for (uint64_t v = 0; v < N; ++v) cOff[v + 1] += cOff[v];
+    std::vector<uint32_t> fill(cOff.begin(), cOff.end() - 1);
+    for (uint64_t v = 1; v < N; ++v) kids[fill[parent[v]]++] = static_cast<uint32_t>(v);
+    uint64_t head = 0, tail = 0;
+    order[tail++] = 0;
+    while (head < tail) {
+        const uint32_t v = order[head++];
+        for (uint32_t e = cOff[v]; e < cOff[v + 1]; ++e) order[tail++] = kids[e];
+    }
+    if (tail != N) throw std::runtime_error("index tree is not connected to node 0");
+    for (uint64_t r = 0; r < N; ++r) rank[order[r]] = static_cast<uint32_t>(r);
+}
+
+void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, FlatIndex& F) {
+    const uint64_t N = d.n_nodes, D = d.n_deltas;
+    if (N == 0) throw std::runtime_error("index has no nodes");
+    if (N >= 0xFFFFFFFFull) throw std::runtime_error("index has too many nodes");
+    if (!d.node_offsets || !d.parent_index || (D && (!d.delta_hash || !d.delta_parent || !d.delta_child)))
+        throw std::runtime_error("index descriptor has null arrays");
+    if (d.node_offsets[N] != D) throw std::runtime_error("nodeChangeOffsets[N] does not equal the number of seed changes");
+    if (d.seed.k < 1 || d.seed.k > kMaxK || d.seed.s < 1 || d.seed.s > d.seed.k || d.seed.t < 0 || d.seed.t > d.seed.k - d.seed.s)
+        throw std::runtime_error("unsupported seeding parameters (need 1 <= s <= k <= 32, 0 <= t <= k-s)");
+    if (nShards == 0 || shard >= nShards) throw std::runtime_error("bad shard index");
+    F.N = N; F.D = D; F.sp = d.seed;
+
+    // ---- tree ----
+    F.parent.assign(d.parent_index, d.parent_index + N);
+    F.parent[0] = NONE;
+    F.depth.assign(N, 0); F.subEnd.assign(N, 0); F.isLeaf.assign(N, 1);
+    for (uint64_t v = 1; v < N; ++v) {
+        if (F.parent[v] >= v) throw std::runtime_error("nodes are not in DFS pre-order (parentIndex >= index)");
+        if (d.node_offsets[v] < d.node_offsets[v - 1]) throw std::runtime_error("nodeChangeOffsets not monotone");
+        F.depth[v] = F.depth[F.parent[v]] + 1;
+        F.isLeaf[F.parent[v]] = 0;
+    }
+    if (d.node_offsets[N] < d.node_offsets[N - 1]) throw std::runtime_error("nodeChangeOffsets not monotone");
+    {   // pre-order validity + subtree ends in one sweep: keep the current root->v path on a stack
+        std::vector<uint32_t> path;
+        path.push_back(0);
+        for (uint64_t v = 1; v < N; ++v) {
+            const uint32_t p = F.parent[v];
+            while (!path.empty() && path.back() != p) { F.subEnd[path.back()] = static_cast<uint32_t>(v); path.pop_back(); }
+            if (path.empty()) throw std::runtime_error("tree is not in DFS pre-order");
+            path.push_back(static_cast<uint32_t>(v));
+        }
+        for (uint32_t u : path) F.subEnd[u] = static_cast<uint32_t>(N);
+    }
+    bfsRanks(F.parent.data(), N, F.bfsRank);
+
+    // closers: u closes right before w  <=>  subEnd[u] == w
+    F.closeOff.assign(N + 2, 0);
+    for (uint64_t u = 0; u < N; ++u) F.closeOff[F.subEnd[u] + 1]++;
+    for (uint64_t w = 0; w <= N; ++w) F.closeOff[w + 1] += F.closeOff[w];
+    F.closeList.assign(N, 0);
+    {
+        std::vector<uint32_t> fill(F.closeOff.begin(), F.closeOff.end() - 1);
+        for (uint64_t u = 0; u < N; ++u) F.closeList[fill[F.subEnd[u]]++] = static_cast<uint32_t>(u);
+    }
+    F.closeOff.resize(N + 1);  // entries for w == N (nodes closing at the very end) are never used
+
+    // ---- genome-only accumulators in the reference's order ----
+    F.gMagSq.assign(N, 0.0); F.gMag.assign(N, 0.0); F.gUnique.assign(N, 0);
+    {
+        std::vector<double> l1p(32768);
+        for (int c = 0; c < 32768; ++c) l1p[c] = std::log1p(static_cast<double>(c));
+        // parents precede children in DFS order, so a forward sweep sees the parent's final value first
+        for (uint64_t v = 0; v < N; ++v) {
+            double mag = v ? F.gMagSq[F.parent[v]] : 0.0;
+            int64_t uq = v ? F.gUnique[F.parent[v]] : 0;
+            for (uint64_t i = d.node_offsets[v]; i < d.node_offsets[v + 1]; ++i) {
+                const int p = d.delta_parent[i], c = d.delta_child[i];
+                const double lc = c > 0 ? l1p[c] : 0.0, lp = p > 0 ? l1p[p] : 0.0;
+                const double a = lc * lc, b = lp * lp;
+                mag += a - b;
+                uq += (c > 0) - (p > 0);
+            }
+            F.gMagSq[v] = mag; F.gUnique[v] = uq; F.gMag[v] = std::sqrt(mag);
+        }
+    }
+
+    // ---- dictionary: dense ids in first-appearance order ----
+    std::vector<uint32_t> idAll(D);
+    {
+        std::unordered_map<uint64_t, uint32_t> dict;
+        dict.reserve(static_cast<size_t>(D / 2 + 16));
+        for (uint64_t i = 0; i < D; ++i) {
+            auto it = dict.find(d.delta_hash[i]);
+            if (it == dict.end()) {
+                const uint32_t id = static_cast<uint32_t>(F.dictHash.size());
+                dict.emplace(d.delta_hash[i], id);
+                F.dictHash.push_back(d.delta_hash[i]);
+                idAll[i] = id;
+            } else idAll[i] = it->second;
+        }
+    }
+    F.S = F.dictHash.size();
+    {
+        uint64_t cap = 16;
+        while (cap < 2 * F.S + 2) cap <<= 1;
+        F.dictMask = cap - 1;
+        F.dictKeys.assign(cap, kEmptyKey); F.dictVals.assign(cap, NONE);
+        for (uint64_t id = 0; id < F.S; ++id) {
+            const uint64_t h = F.dictHash[id];
+            if (h == kEmptyKey) continue;  // cannot be stored; such a seed can never match (2^-64 event)
+            uint64_t s = mixKey(h) & F.dictMask;
+            while (F.dictKeys[s] != kEmptyKey) s = (s + 1) & F.dictMask;
+            F.dictKeys[s] = h; F.dictVals[s] = static_cast<uint32_t>(id);
+        }
+    }
+
+    // ---- shard extent: contiguous DFS ranges balanced by delta count ----
+    auto cut = [&](uint32_t g) -> uint32_t {
+        if (g == 0) return 0;
+        if (g >= nShards) return static_cast<uint32_t>(N);
+        const uint64_t target = (D / nShards) * g + std::min<uint64_t>(g, D % nShards);
+        const uint64_t* lo = std::lower_bound(d.node_offsets, d.node_offsets + N, target);
+        uint64_t v = static_cast<uint64_t>(lo - d.node_offsets);
+        const uint64_t even = (N * g) / nShards;  // degenerate trees with very few deltas: fall back to node balance
+        if (D < 16ull * nShards) v = even;
+        return static_cast<uint32_t>(std::min<uint64_t>(v, N));
+    };
+    F.nodeBegin = cut(shard); F.nodeEnd = cut(shard + 1);
+    if (F.nodeEnd < F.nodeBegin) F.nodeEnd = F.nodeBegin;
+
+    // ---- local nodes: ancestors of nodeBegin (root first) ++ shard nodes ----
+    std::vector<uint32_t> anc;
+    if (F.nodeBegin < F.nodeEnd) {
+        for (uint32_t a = F.parent[F.nodeBegin]; a != NONE; a = F.parent[a]) anc.push_back(a);
+        std::reverse(anc.begin(), anc.end());
+    } else {
+        anc.push_back(0);  // an empty shard still needs the root for the weighted-containment denominator
+    }
+    F.nAnc = static_cast<uint32_t>(anc.size());
+    F.nLocal = F.nAnc + (F.nodeEnd - F.nodeBegin);
+    F.lNode.resize(F.nLocal);
+    for (uint32_t i = 0; i < F.nAnc; ++i) F.lNode[i] = anc[i];
+    for (uint32_t v = F.nodeBegin; v < F.nodeEnd; ++v) F.lNode[F.nAnc + (v - F.nodeBegin)] = v;
+    F.lOff.assign(F.nLocal + 1, 0);
+    for (uint32_t i = 0; i < F.nLocal; ++i) {
+        const uint32_t v = F.lNode[i];
+        F.lOff[i + 1] = F.lOff[i] + (d.node_offsets[v + 1] - d.node_offsets[v]);
+    }
+    F.nLocalDeltas = F.lOff[F.nLocal];
+    F.seedId.resize(F.nLocalDeltas); F.pc.resize(F.nLocalDeltas);
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> tmp;
+        for (uint32_t i = 0; i < F.nLocal; ++i) {
+            const uint32_t v = F.lNode[i];
+            const uint64_t b = d.node_offsets[v], e = d.node_offsets[v + 1];
+            tmp.resize(static_cast<size_t>(e - b));
+            for (uint64_t j = b; j < e; ++j)
+                tmp[j - b] = {idAll[j], static_cast<uint32_t>(static_cast<uint16_t>(d.delta_parent[j])) |
+                                             (static_cast<uint32_t>(static_cast<uint16_t>(d.delta_child[j])) << 16)};
+            std::sort(tmp.begin(), tmp.end());
+            for (uint64_t j = 0; j < e - b; ++j) { F.seedId[F.lOff[i] + j] = tmp[j].first; F.pc[F.lOff[i] + j] = tmp[j].second; }
+        }
+    }
+    // root's deltas in local storage (root is local node 0 whenever anything is local)
+    F.rootDBegin = 0; F.rootDCount = 0;
+    if (F.nLocal > 0 && F.lNode[0] == 0) { F.rootDBegin = F.lOff[0]; F.rootDCount = static_cast<uint32_t>(F.lOff[1] - F.lOff[0]); }
+
+    // ---- K1 tiles ----
+    {
+        uint32_t i = 0;
+        while (i < F.nLocal) {
+            const uint64_t n0 = F.lOff[i + 1] - F.lOff[i];
+            if (n0 > kTileDeltasH) {
+                HostBigNode bn; bn.localNode = i; bn.firstPartial = F.nBigPartials; bn.pad = 0;
+                bn.nPartials = static_cast<uint32_t>((n0 + kTileDeltasH - 1) / kTileDeltasH);
+                for (uint32_t c = 0; c < bn.nPartials; ++c) {
+                    HostK1Tile t; t.dBegin = F.lOff[i] + static_cast<uint64_t>(c) * kTileDeltasH;
+                    t.dCount = static_cast<uint32_t>(std::min<uint64_t>(kTileDeltasH, F.lOff[i + 1] - t.dBegin));
+                    t.lnBegin = i; t.lnEnd = i + 1; t.kind = 1; t.bigSlot = F.nBigPartials + c;
+                    t.bigNode = static_cast<uint32_t>(F.bigNodes.size());
+                    F.k1Tiles.push_back(t);
+                }
+                F.nBigPartials += bn.nPartials;
+                F.bigNodes.push_back(bn);
+                ++i;
+                continue;
+            }
+            HostK1Tile t; t.dBegin = F.lOff[i]; t.lnBegin = i; t.kind = 0; t.bigSlot = 0; t.bigNode = 0;
+            uint64_t cnt = 0; uint32_t j = i;
+            while (j < F.nLocal && j - i < kTileNodesK1H) {
+                const uint64_t nj = F.lOff[j + 1] - F.lOff[j];
+                if (nj > kTileDeltasH || cnt + nj > kTileDeltasH) break;
+                cnt += nj; ++j;
+            }
+            t.lnEnd = j; t.dCount = static_cast<uint32_t>(cnt);
+            F.k1Tiles.push_back(t);
+            i = j;
+        }
+    }
+
+    // ---- K2 tiles: ancestor chains and carry slots ----
+    const uint32_t nShardNodes = F.nodeEnd - F.nodeBegin;
+    F.nK2Tiles = (nShardNodes + kTileNodesK2H - 1) / kTileNodesK2H;
+    F.chainOff.assign(F.nK2Tiles + 1, 0);
+    F.carrySlot.assign(N, NONE);
+    for (uint32_t t = 0; t < F.nK2Tiles; ++t) {
+        const uint32_t a0 = F.nodeBegin + t * kTileNodesK2H;
+        const uint32_t a1 = std::min(a0 + kTileNodesK2H, F.nodeEnd);
+        std::vector<uint32_t> ch;
+        for (uint32_t a = F.parent[a0]; a != NONE; a = F.parent[a]) ch.push_back(a);
+        std::reverse(ch.begin(), ch.end());
+        F.chainNodes.insert(F.chainNodes.end(), ch.begin(), ch.end());
+        F.chainOff[t + 1] = static_cast<uint32_t>(F.chainNodes.size());
+        for (uint32_t w = a0; w < a1; ++w) {
+            const uint32_t p = F.parent[w];
+            if (p != NONE && p < a0) F.carrySlot[w] = F.depth[p];
+        }
+    }
+
+    // ---- selection: shard nodes in global BFS order ----
+    F.bfsNodes.resize(nShardNodes); F.bfsRanks.resize(nShardNodes);
+    {
+        std::vector<uint32_t> idx(nShardNodes);
+        std::iota(idx.begin(), idx.end(), F.nodeBegin);
+        std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return F.bfsRank[a] < F.bfsRank[b]; });
+        for (uint32_t i = 0; i < nShardNodes; ++i) { F.bfsNodes[i] = idx[i]; F.bfsRanks[i] = F.bfsRank[idx[i]]; }
+    }
+
+    // ---- canonical hashes of the four homopolymer k-mers (placement.cpp:41-76) ----
+    for (int b = 0; b < 4; ++b) {
+        const uint64_t bv = codeHash(static_cast<unsigned>(b)), cv = codeHash(static_cast<unsigned>(3 - b));
+        uint64_t f = 0, r = 0;
+        for (int i = 0; i < d.seed.k; ++i) { f ^= rol64(bv, static_cast<unsigned>(d.seed.k - i - 1)); r ^= rol64(cv, static_cast<unsigned>(d.seed.k - i - 1)); }
+        F.homo[b] = f < r ? f : r;
+    }
+}
+
+}  // namespace pm

@@ -1,0 +1,144 @@
+// pm_idx.cpp -- reader for panmap's `.idx` container (host side, no CUDA).
+//
+// Format (reference: /root/reference/src/index_single_mode.cpp:1561-1636, index_single_mode.hpp:24-38,
+// main.cpp:193-236, schema src/index_lite.capnp):
+//   32-byte header: u32 magic 0x31494D50 "PMI1", u32 version 1, i32 k,s,t,l, u8 hpc, u8 open, u8 uncompressed
+//   payload: raw Cap'n Proto flat-array message (when `uncompressed`) whose root is LiteIndex.
+// The message is walked with a small schema-less pointer decoder (struct / list / far pointers); the struct
+// shapes used are LiteIndex (2 data words, 11 pointers), LiteTree (0,2) and LiteNode (1,1).
+#include "pm_host.h"
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace pm {
+namespace {
+
+struct Msg {
+    const uint8_t* base = nullptr;
+    std::vector<size_t> segStart, segWords;
+    uint64_t word(uint32_t seg, size_t w) const {
+        if (seg >= segStart.size() || w >= segWords[seg]) throw std::runtime_error("index: pointer out of range");
+        uint64_t v; std::memcpy(&v, base + segStart[seg] + 8 * w, 8); return v;
+    }
+    const uint8_t* at(uint32_t seg, size_t w) const { return base + segStart[seg] + 8 * w; }
+};
+struct Ref { int kind = 0; uint32_t seg = 0; size_t off = 0; uint32_t dataWords = 0, ptrWords = 0, elemSize = 0; uint64_t count = 0; };
+
+Ref decode(const Msg& m, uint64_t p, uint32_t seg, size_t base) {
+    Ref r; r.seg = seg;
+    const int64_t off = static_cast<int32_t>(p & 0xffffffffu) >> 2;
+    r.off = static_cast<size_t>(static_cast<int64_t>(base) + off);
+    if ((p & 3) == 0) { r.kind = 1; r.dataWords = (p >> 32) & 0xffff; r.ptrWords = (p >> 48) & 0xffff; }
+    else {
+        r.kind = 2; r.elemSize = (p >> 32) & 7; r.count = p >> 35;
+        if (r.elemSize == 7) {
+            const uint64_t tag = m.word(seg, r.off);
+            r.count = static_cast<uint32_t>(tag & 0xffffffffu) >> 2;
+            r.dataWords = (tag >> 32) & 0xffff; r.ptrWords = (tag >> 48) & 0xffff;
+            r.off += 1;
+        }
+    }
+    return r;
+}
+Ref resolve(const Msg& m, uint32_t seg, size_t w) {
+    const uint64_t p = m.word(seg, w);
+    if (p == 0) return Ref{};
+    if ((p & 3) == 2) {
+        const bool dbl = (p >> 2) & 1;
+        const size_t padOff = (p & 0xffffffffu) >> 3;
+        const uint32_t padSeg = static_cast<uint32_t>(p >> 32);
+        if (!dbl) { const uint64_t q = m.word(padSeg, padOff); return q ? decode(m, q, padSeg, padOff + 1) : Ref{}; }
+        const uint64_t far2 = m.word(padSeg, padOff), tag = m.word(padSeg, padOff + 1);
+        return decode(m, tag & 0xFFFFFFFF00000003ULL, static_cast<uint32_t>(far2 >> 32), (far2 & 0xffffffffu) >> 3);
+    }
+    if ((p & 3) == 3) throw std::runtime_error("index: unexpected capability pointer");
+    return decode(m, p, seg, w + 1);
+}
+Ref ptrOf(const Msg& m, const Ref& s, uint32_t i) { return (s.kind == 1 && i < s.ptrWords) ? resolve(m, s.seg, s.off + s.dataWords + i) : Ref{}; }
+static const size_t kElemBytes[8] = {0, 0, 1, 2, 4, 8, 8, 0};
+
+}  // namespace
+
+void readIdxFile(const std::string& path, HostIndex& out) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw IoError("cannot open index file: " + path);
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    out.raw.resize(static_cast<size_t>(sz > 0 ? sz : 0));
+    if (sz > 0 && std::fread(out.raw.data(), 1, static_cast<size_t>(sz), f) != static_cast<size_t>(sz)) { std::fclose(f); throw IoError("short read: " + path); }
+    std::fclose(f);
+    if (out.raw.size() < 40) throw std::runtime_error("index file too small: " + path);
+    uint32_t magic, ver; std::memcpy(&magic, out.raw.data(), 4); std::memcpy(&ver, out.raw.data() + 4, 4);
+    size_t payload = 0;
+    if (magic == 0x31494D50u && ver == 1) {
+        if (out.raw[26] == 0) throw Unsupported("zstd-framed .idx payloads are not supported yet; write the index uncompressed");
+        payload = 32;
+    }
+    Msg m; m.base = out.raw.data() + payload;
+    const size_t avail = out.raw.size() - payload;
+    uint32_t nseg; std::memcpy(&nseg, m.base, 4); nseg += 1;
+    size_t hdr = (4 + 4 * static_cast<size_t>(nseg) + 7) & ~size_t(7);
+    size_t pos = hdr;
+    for (uint32_t i = 0; i < nseg; ++i) {
+        uint32_t w; std::memcpy(&w, m.base + 4 + 4 * i, 4);
+        m.segStart.push_back(pos); m.segWords.push_back(w); pos += 8 * static_cast<size_t>(w);
+    }
+    if (pos > avail) throw std::runtime_error("index message truncated: " + path);
+
+    const Ref root = resolve(m, 0, 0);
+    if (root.kind != 1 || root.dataWords < 2) throw std::runtime_error("index root is not a LiteIndex struct");
+    const uint64_t d0 = m.word(root.seg, root.off), d1 = m.word(root.seg, root.off + 1);
+    out.sp.k = static_cast<int>(d0 & 0xffff); out.sp.s = static_cast<int>((d0 >> 16) & 0xffff);
+    out.sp.t = static_cast<int>((d0 >> 32) & 0xffff); out.sp.l = static_cast<int>((d0 >> 48) & 0xffff);
+    out.sp.open = static_cast<int>(d1 & 1); out.sp.hpc = static_cast<int>((d1 >> 1) & 1);
+    const unsigned formatVersion = static_cast<unsigned>((d1 >> 16) & 0xffff);
+    // same check and wording as placement.cpp:1013-1019
+    if (formatVersion != 4)
+        throw std::runtime_error("Index format version " + std::to_string(formatVersion) +
+                                 " is incompatible with this panmap (expects 4). Rebuild the index (delete the .idx and rerun).");
+    const Ref tree = ptrOf(m, root, 0), hashes = ptrOf(m, root, 1), parents = ptrOf(m, root, 2), childs = ptrOf(m, root, 3),
+              offs = ptrOf(m, root, 4);
+    if (hashes.kind != 2 || parents.kind != 2 || childs.kind != 2 || offs.kind != 2)
+        throw std::runtime_error("Index missing required V3 fields (seedChangeHashes, etc). V2 is no longer supported.");
+    const Ref nodes = ptrOf(m, tree, 0);
+    const uint64_t N = nodes.kind == 2 ? nodes.count : 0;
+    if (offs.count < N + 1)
+        throw std::runtime_error("Struct-of-arrays format offsets size mismatch: " + std::to_string(offs.count) + " vs " + std::to_string(N + 1));
+    out.nodeOffsets.resize(N + 1);
+    std::memcpy(out.nodeOffsets.data(), m.at(offs.seg, offs.off), 8 * (N + 1));
+    const uint64_t D = out.nodeOffsets[N];
+    out.hash.resize(D); out.parentCount.resize(D); out.childCount.resize(D);
+    auto gatherSegs = [&](const Ref& outer, void* dst, size_t elemBytes, unsigned wantCode) {
+        uint64_t done = 0;
+        for (uint64_t sgi = 0; sgi < outer.count; ++sgi) {  // 5e8-element segments (placement.cpp:1052-1071)
+            const Ref inner = resolve(m, outer.seg, outer.off + sgi);
+            if (inner.kind != 2) continue;
+            if (inner.elemSize != wantCode) throw std::runtime_error("index: unexpected list element size");
+            const uint64_t n = inner.count < D - done ? inner.count : D - done;
+            std::memcpy(static_cast<uint8_t*>(dst) + done * elemBytes, m.at(inner.seg, inner.off), n * elemBytes);
+            done += n;
+        }
+        if (done != D) throw std::runtime_error("index: seed-change arrays shorter than nodeChangeOffsets says");
+    };
+    (void)kElemBytes;
+    gatherSegs(hashes, out.hash.data(), 8, 5);
+    gatherSegs(parents, out.parentCount.data(), 2, 3);
+    gatherSegs(childs, out.childCount.data(), 2, 3);
+    out.parentIndex.resize(N); out.nodeIds.resize(N);
+    for (uint64_t i = 0; i < N; ++i) {
+        const size_t eo = nodes.off + i * (nodes.dataWords + nodes.ptrWords);
+        out.parentIndex[i] = nodes.dataWords ? static_cast<uint32_t>(m.word(nodes.seg, eo) & 0xffffffffu) : 0;
+        Ref e; e.kind = 1; e.seg = nodes.seg; e.off = eo; e.dataWords = nodes.dataWords; e.ptrWords = nodes.ptrWords;
+        const Ref id = ptrOf(m, e, 0);
+        if (id.kind == 2 && id.count > 0) out.nodeIds[i].assign(reinterpret_cast<const char*>(m.at(id.seg, id.off)), id.count - 1);
+        if (i > 0 && out.parentIndex[i] >= i) throw std::runtime_error("index: nodes are not in DFS pre-order (parentIndex >= index)");
+    }
+    out.raw.clear(); out.raw.shrink_to_fit();
+}
+
+}  // namespace pm

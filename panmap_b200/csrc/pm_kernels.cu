@@ -1,0 +1,851 @@
+// pm_kernels.cu -- hand-written sm_100a kernels of the placement hot path.
+//
+//   pack_reads      ASCII reads -> 4-bit base codes, 32 per 16-byte chunk, every read 16-byte aligned
+//   seed_reads      lane-per-read rolling hashes (k-mer + s-mer, both strands), sliding s-mer minimum,
+//                   closed/open syncmer test, k-min-mers, insertion into the open-addressing count table
+//   table_*         homopolymer removal, auto min-support statistics, log1p + exact magnitude sums,
+//                   scatter of log1p(count) into the dense per-seed-id array the delta kernel gathers from
+//   node_deltas     K1: streams the (seedId, parent|child) delta arrays once, per-node parent-relative sums
+//   prefix_scores   K2: exact (128-bit fixed point) tree prefix over the DFS order, the five scores
+//   bfs_* / chain / ties   selection with the reference's order-dependent tolerance chain (placement.cpp:355-401)
+//
+// This is integer/byte streaming work bounded by HBM and issue rate; no tensor cores are involved.
+#include "pm_kernels.cuh"
+
+namespace pm {
+
+// ------------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 shflU64(u64 v, int srcLane) {
+    return __shfl_sync(0xffffffffu, v, srcLane);
+}
+__device__ __forceinline__ u64 shflUpU64(u64 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ u64 shflXorU64(u64 v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shflXorF64(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
+
+__device__ __forceinline__ void fxAtomicAdd(u64* acc /* lo, hi */, fx128 v) {
+    // exact 128-bit accumulation with two 64-bit atomics: the number of carries out of the low word does not
+    // depend on the order of the additions, so the result is deterministic.
+    const u64 old = atomicAdd(reinterpret_cast<unsigned long long*>(&acc[0]), v.lo);
+    const u64 carry = (old + v.lo < old) ? 1ULL : 0ULL;
+    const u64 hiAdd = (u64)v.hi + carry;
+    if (hiAdd) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[1]), hiAdd);
+}
+__device__ __forceinline__ fx128 fxWarpSum(fx128 v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        fx128 o; o.lo = shflXorU64(v.lo, d); o.hi = (i64)shflXorU64((u64)v.hi, d);
+        v = fxAdd(v, o);
+    }
+    return v;
+}
+__device__ __forceinline__ long long warpSumLL(long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += (long long)shflXorU64((u64)v, d);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// pack_reads: one thread per 32-base chunk
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads, const u64* __restrict__ off,
+                                                  const u64* __restrict__ packedOff, u64 nReads, u64 nChunks,
+                                                  uint4* __restrict__ packed) {
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nChunks) return;
+    // read r with packedOff[r] <= g < packedOff[r+1]
+    u64 lo = 0, hi = nReads;
+    while (hi - lo > 1) {
+        const u64 mid = (lo + hi) >> 1;
+        if (__ldg(&packedOff[mid]) <= g) lo = mid; else hi = mid;
+    }
+    const u64 r = lo;
+    const u64 c = g - __ldg(&packedOff[r]);
+    const u64 b = __ldg(&off[r]), e = __ldg(&off[r + 1]);
+    const u64 src = b + 32 * c;
+    const int n = (int)((e - src) < 32 ? (e - src) : 32);
+    unsigned w[4] = {0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u};
+    for (int j = 0; j < n; ++j) {
+        const unsigned code = baseCode((unsigned char)__ldg(&reads[src + j]));
+        const int sh = 4 * (j & 7);
+        w[j >> 3] = (w[j >> 3] & ~(0xFu << sh)) | (code << sh);
+    }
+    packed[g] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+void launchPackReads(const char* reads, const u64* off, const u64* packedOff, u64 nReads, u64 nChunks, uint4* packed,
+                     cudaStream_t st) {
+    if (nChunks == 0) return;
+    const unsigned grid = (unsigned)((nChunks + 255) / 256);
+    pack_reads<<<grid, 256, 0, st>>>(reads, off, packedOff, nReads, nChunks, packed);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// count table insert (open addressing, linear probing; keys are 64-bit seed hashes)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tableInsert(u64* __restrict__ keys, u32* __restrict__ counts, u64 mask, u64 h, u32 add,
+                                            SampleAcc* acc) {
+    if (h == kEmptyKey) { atomicAdd((unsigned long long*)&acc->emptyKeyCount, (unsigned long long)add); return; }
+    u64 slot = mixKey(h) & mask;
+    for (int probe = 0; probe < 8192; ++probe) {
+        u64 cur = *((volatile u64*)&keys[slot]);
+        if (cur == kEmptyKey) {
+            cur = atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)h);
+            if (cur == kEmptyKey) cur = h;
+        }
+        if (cur == h) { atomicAdd(&counts[slot], add); return; }
+        slot = (slot + 1) & mask;
+    }
+    acc->overflow = 1;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// seed_reads: one lane per read, all lanes of a warp at the same read position (lock-step), so the
+// block-end pass of the sliding minimum is convergent.  MODE 0: count table; 1: syncmer list; 2: seed list.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kSeedThreads = 128;
+
+template <int MODE>
+__global__ void __launch_bounds__(kSeedThreads) seed_reads(const uint4* __restrict__ packed, const u64* __restrict__ off,
+                                                           const u64* __restrict__ packedOff, const u64* __restrict__ winOff,
+                                                           u64 nReads, SeederParams P, const SeedTables* __restrict__ gT,
+                                                           u64* keys, u32* counts, u64 mask, SampleAcc* acc,
+                                                           u64* outHash, unsigned char* outRev, long long* outPos, u64* outCount) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
+    u64* rings = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables));
+    for (int i = threadIdx.x; i < (int)(sizeof(SeedTables) / 8); i += blockDim.x)
+        reinterpret_cast<u64*>(sT)[i] = reinterpret_cast<const u64*>(gT)[i];
+    __syncthreads();
+    const SeedTables& T = *sT;
+
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < nReads; r += (u64)gridDim.x * blockDim.x) {
+        const u64 b = off[r];
+        const int L = (int)(off[r + 1] - b);
+        const u64 pOff = packedOff[r];
+        const int nCh = (L + 31) >> 5;
+        ReadSeeder sd;
+        sd.reset(rings + threadIdx.x, blockDim.x);
+        u64 cnt = 0;
+        const u64 wbase = (MODE != 0) ? winOff[r] : 0;
+        if (L >= P.k) {
+            for (int c = 0; c < nCh; ++c) {
+                const uint4 v = packed[pOff + c];
+                const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    const unsigned word = wv[wi];
+#pragma unroll
+                    for (int bi = 0; bi < 8; ++bi) {
+                        const int i = c * 32 + wi * 8 + bi;
+                        if (i < L) {
+                            const unsigned code = (word >> (4 * bi)) & 0xFu;
+                            u64 h; bool rev;
+                            if (sd.pushBase(i, code, T, P, h, rev)) {
+                                const int pos = i - P.k + 1;
+                                if (MODE == 1) {
+                                    outHash[wbase + cnt] = h; outRev[wbase + cnt] = rev ? 1 : 0; outPos[wbase + cnt] = pos; ++cnt;
+                                } else {
+                                    u64 seed;
+                                    if (sd.pushSyncmer(pos, L, h, P, seed)) {
+                                        if (MODE == 0) tableInsert(keys, counts, mask, seed, 1u, acc);
+                                        else { outHash[wbase + cnt] = seed; ++cnt; }
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (MODE != 0) outCount[r] = cnt;
+    }
+}
+
+static size_t seedSmemBytes(const SeederParams& P) {
+    return sizeof(SeedTables) + (size_t)seederRingWords(P.k, P.s, P.l) * kSeedThreads * sizeof(u64);
+}
+static unsigned seedGrid(u64 nReads) {
+    u64 g = (nReads + kSeedThreads - 1) / kSeedThreads;
+    if (g > 148ull * 64) g = 148ull * 64;
+    return (unsigned)(g ? g : 1);
+}
+void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
+                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
+    if (nReads == 0) return;
+    const size_t sm = seedSmemBytes(P);
+    cudaFuncSetAttribute(seed_reads<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    seed_reads<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dTables, W.keys,
+                                                               W.counts, W.tableMask, W.acc, nullptr, nullptr, nullptr, nullptr);
+}
+void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
+                    const SeederParams& P, const SeedTables* dTables, int mode, u64* outHash, unsigned char* outRev,
+                    long long* outPos, u64* outCount, cudaStream_t st) {
+    if (nReads == 0) return;
+    const size_t sm = seedSmemBytes(P);
+    if (mode == 1) {
+        cudaFuncSetAttribute(seed_reads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        seed_reads<1><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr,
+                                                                   nullptr, 0, nullptr, outHash, outRev, outPos, outCount);
+    } else {
+        cudaFuncSetAttribute(seed_reads<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        seed_reads<2><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr,
+                                                                   nullptr, 0, nullptr, outHash, outRev, outPos, outCount);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// table maintenance
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) table_clear(u64* keys, u32* counts, u64 cap) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
+        keys[i] = kEmptyKey; counts[i] = 0;
+    }
+}
+void launchTableClear(WorkspaceView W, cudaStream_t st) {
+    u64 g = (W.tableCap + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    table_clear<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableCap);
+}
+
+__global__ void __launch_bounds__(256) table_import(u64* keys, u32* counts, u64 mask, SampleAcc* acc,
+                                                    const u64* __restrict__ hash, const long long* __restrict__ count, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        if (count[i] > 0) tableInsert(keys, counts, mask, hash[i], (u32)count[i], acc);
+}
+void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st) {
+    if (!n) return;
+    u64 g = (n + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    table_import<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableMask, W.acc, hash, count, n);
+}
+
+__global__ void __launch_bounds__(256) table_export(const u64* __restrict__ keys, const u32* __restrict__ counts, u64 cap,
+                                                    const SampleAcc* acc, u64* outHash, long long* outCount, unsigned* counter,
+                                                    u64 outCap) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = keys[i]; const u32 c = counts[i];
+        if (k != kEmptyKey && c > 0) {
+            const unsigned o = atomicAdd(counter, 1u);
+            if (o < outCap) { outHash[o] = k; outCount[o] = (long long)c; }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {
+        const unsigned o = atomicAdd(counter, 1u);
+        if (o < outCap) { outHash[o] = kEmptyKey; outCount[o] = acc->emptyKeyCount; }
+    }
+}
+void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st) {
+    u64 g = (W.tableCap + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    table_export<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableCap, W.acc, hash, count, counter, cap);
+}
+
+// pass 1: erase the four homopolymer k-mer hashes (placement.cpp:1708-1718) and gather the statistics of the
+// auto min-read-support rule (placement.cpp:931-955)
+__global__ void __launch_bounds__(256) table_stats(u64* keys, u32* counts, u64 cap, SampleAcc* acc, const u64* __restrict__ homo) {
+    const u64 h0 = homo[0], h1 = homo[1], h2 = homo[2], h3 = homo[3];
+    long long ms = 0, mc = 0, en = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
+        const u64 k = keys[i];
+        if (k == kEmptyKey) continue;
+        if (k == h0 || k == h1 || k == h2 || k == h3) { counts[i] = 0; continue; }
+        const long long c = counts[i];
+        if (c > 0) { ++en; if (c >= 2) { ms += c; ++mc; } }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {
+        const long long c = acc->emptyKeyCount; ++en; if (c >= 2) { ms += c; ++mc; }
+    }
+    ms = warpSumLL(ms); mc = warpSumLL(mc); en = warpSumLL(en);
+    if ((threadIdx.x & 31) == 0) {
+        if (ms) atomicAdd((unsigned long long*)&acc->multiSum, (unsigned long long)ms);
+        if (mc) atomicAdd((unsigned long long*)&acc->multiCount, (unsigned long long)mc);
+        if (en) atomicAdd((unsigned long long*)&acc->entries, (unsigned long long)en);
+    }
+}
+
+__device__ __forceinline__ long long resolveMinSupport(const SampleAcc* acc, int configured) {
+    if (configured >= 0) return configured;
+    const double est = acc->multiCount > 0 ? (double)(u64)acc->multiSum / (double)(u64)acc->multiCount : 0.0;
+    return est > 3.0 ? 2 : 1;
+}
+
+// pass 2: computeReadSeedMagnitudes (placement.cpp:957-984) + scatter of log1p(count) to the seed-id array
+constexpr int kHistSmem = 2048;
+__global__ void __launch_bounds__(256) table_finalize(DevIndexView I, WorkspaceView W, int configuredMinSupport) {
+    __shared__ unsigned sHist[kHistSmem];
+    for (int i = threadIdx.x; i < kHistSmem; i += blockDim.x) sHist[i] = 0;
+    __syncthreads();
+    SampleAcc* acc = W.acc;
+    const long long minSup = resolveMinSupport(acc, configuredMinSupport);
+    fx128 mag = fxZero(), lsum = fxZero();
+    long long kept = 0, total = 0, uniq = 0;
+    const u64 cap = W.tableCap;
+    const bool extra = (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap + (extra ? 1 : 0); i += (u64)gridDim.x * blockDim.x) {
+        u64 k; long long c;
+        if (i < cap) { k = W.keys[i]; if (k == kEmptyKey) continue; c = W.counts[i]; }
+        else { k = kEmptyKey; c = acc->emptyKeyCount; }
+        if (c <= 0) continue;
+        total += c; ++uniq;
+        if (c < minSup) continue;
+        const double l = c < kLog1pLut ? __ldg(&I.log1pLut[c]) : log1p((double)c);
+        ++kept;
+        if (c < kLog1pLut) {
+            if (c < kHistSmem) atomicAdd(&sHist[c], 1u); else atomicAdd(&W.countHist[c], 1u);
+        }
+        mag = fxAdd(mag, fxFromDouble(l * l));
+        lsum = fxAdd(lsum, fxFromDouble(l));
+        // dictionary probe: is this seed anywhere in the index?
+        u64 s = mixKey(k) & I.dictMask;
+        while (true) {
+            const u64 dk = __ldg(&I.dictKeys[s]);
+            if (dk == k) {
+                const u32 id = __ldg(&I.dictVals[s]);
+                if (id != kNone) {
+                    W.ell[id] = l;
+                    const unsigned t = atomicAdd(&acc->touchedCount, 1u);
+                    if (t < W.touchedCap) W.touched[t] = id; else acc->overflow = 1;
+                }
+                break;
+            }
+            if (__ldg(&I.dictVals[s]) == kNone && dk == kEmptyKey) break;
+            s = (s + 1) & I.dictMask;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistSmem; i += blockDim.x) if (sHist[i]) atomicAdd(&W.countHist[i], sHist[i]);
+    mag = fxWarpSum(mag); lsum = fxWarpSum(lsum);
+    kept = warpSumLL(kept); total = warpSumLL(total); uniq = warpSumLL(uniq);
+    if ((threadIdx.x & 31) == 0) {
+        fxAtomicAdd(acc->magSq, mag); fxAtomicAdd(acc->logSum, lsum);
+        if (kept) atomicAdd((unsigned long long*)&acc->kept, (unsigned long long)kept);
+        if (total) atomicAdd((unsigned long long*)&acc->total, (unsigned long long)total);
+        if (uniq) atomicAdd((unsigned long long*)&acc->unique, (unsigned long long)uniq);
+    }
+}
+
+// weighted-containment denominator over the ROOT's deltas (placement.cpp:1863-1876)
+__global__ void __launch_bounds__(256) root_denominator(DevIndexView I, WorkspaceView W) {
+    fx128 s = fxZero();
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < I.rootDCount; i += (u64)gridDim.x * blockDim.x) {
+        const u32 id = __ldg(&I.seedId[I.rootDBegin + i]);
+        const int c = (int)(short)(__ldg(&I.pc[I.rootDBegin + i]) >> 16);
+        if (c > 0 && W.ell[id] > 0.0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
+    }
+    s = fxWarpSum(s);
+    if ((threadIdx.x & 31) == 0) fxAtomicAdd(W.acc->wcDen, s);
+}
+
+// The reference adds the U' values log1p(count) (and their squares) one by one into an f64 (placement.cpp:967-977).
+// That sequential sum drifts from the exact sum by O(U' * 2^-53) -- 1.7e-12 relative on the sars_20000 sample, more than the
+// 1e-12 parity tolerance, and nearly independent of the (unspecified, hash-map) order because the addends repeat.
+// sequentialDrift() returns the expectation of that drift over random orders, in closed form from the histogram of
+// read counts: while the running sum is in binade [2^e, 2^(e+1)) every addition of x is rounded to a multiple of
+// u = 2^(e-52), i.e. contributes rint(x/u)*u - x, and a fraction (hi-lo)/T of the additions happens in that binade.
+// Adding it to the exact fixed-point sum reproduces the reference's value to ~1e-14 relative.
+__device__ double sequentialDrift(const unsigned* __restrict__ hist, const double* __restrict__ lut, double T, bool squared,
+                                  double* sRed) {
+    double e = 0.0;
+    if (T > 0.0) {
+        const int eTop = (int)((dblBits(T) >> 52) & 0x7FF) - 1023;
+        for (int c = threadIdx.x; c < kLog1pLut; c += blockDim.x) {
+            const unsigned m = hist[c];
+            if (!m) continue;
+            double x = lut[c];
+            if (squared) x = x * x;
+            double acc = 0.0;
+            for (int j = 0; j < 20; ++j) {
+                const int ex = eTop - j;
+                const double lo = j == 19 ? 0.0 : ldexp(1.0, ex);
+                const double hi = fmin(T, ldexp(1.0, ex + 1));
+                const double u = ldexp(1.0, ex - 52);
+                acc += ((hi - lo) / T) * (rint(x / u) * u - x);
+            }
+            e += acc * (double)m;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) e += shflXorF64(e, d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = e;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sRed[w];
+    return tot;
+}
+
+__global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, WorkspaceView W, int configuredMinSupport) {
+    __shared__ double sRed[32];
+    const SampleAcc* a = W.acc;
+    fx128 m; m.lo = a->magSq[0]; m.hi = (i64)a->magSq[1];
+    fx128 l; l.lo = a->logSum[0]; l.hi = (i64)a->logSum[1];
+    fx128 w; w.lo = a->wcDen[0]; w.hi = (i64)a->wcDen[1];
+    const double magSqExact = fxToDouble(m), logSumExact = fxToDouble(l);
+    const double dMag = sequentialDrift(W.countHist, I.log1pLut, magSqExact, true, sRed);
+    const double dLog = sequentialDrift(W.countHist, I.log1pLut, logSumExact, false, sRed);
+    if (threadIdx.x != 0) return;
+    SampleScalars S;
+    S.readMagnitude = sqrt(magSqExact + dMag);
+    S.logContDenom = logSumExact + dLog;
+    S.wcDenom = fxToDouble(w);
+    S.uniqueKept = (double)a->kept;
+    S.minSupport = resolveMinSupport(a, configuredMinSupport);
+    S.uniqueSeeds = a->unique;
+    S.uniqueKeptInt = a->kept;
+    S.totalFrequency = a->total;
+    S.multiSum = a->multiSum; S.multiCount = a->multiCount;
+    S.tableEntries = a->entries;
+    S.overflow = a->overflow;
+    *W.scalars = S;
+}
+
+void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, cudaStream_t st) {
+    u64 g = (W.tableCap + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
+    table_stats<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableCap, W.acc, homo);
+    table_finalize<<<(unsigned)g, 256, 0, st>>>(I, W, O.minReadSupport);
+    if (I.hasRoot && I.rootDCount) {
+        u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
+        root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);
+    }
+    finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport);
+}
+
+__global__ void __launch_bounds__(256) reset_ell(WorkspaceView W) {
+    const unsigned n = W.acc->touchedCount < W.touchedCap ? W.acc->touchedCount : W.touchedCap;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) W.ell[W.touched[i]] = 0.0;
+}
+void launchResetEll(WorkspaceView W, cudaStream_t st) { reset_ell<<<148, 256, 0, st>>>(W); }
+
+// ------------------------------------------------------------------------------------------------------
+// K1 node_deltas: one pass over the delta arrays.
+// phase 1 (coalesced, 16 independent gathers in flight per thread): v[i] = +-log1p(readCount) for the common
+//   0<->1 genome-count transitions, 0 when the seed is not in the reads, NaN for counts >= 2 (general formula)
+// phase 2: lane-per-node sequential sums for nodes with <= 32 deltas, warp-per-node for larger ones; sums are
+//   taken relative to the node's own first delta, so they do not depend on how nodes are tiled or sharded.
+// ------------------------------------------------------------------------------------------------------
+struct NodeAcc { double S, gRaw, gCos, gWc, gCont; int cnt, gPres; };
+__device__ __forceinline__ void nodeAccInit(NodeAcc& a) { a.S = a.gRaw = a.gCos = a.gWc = a.gCont = 0.0; a.cnt = a.gPres = 0; }
+
+__device__ __forceinline__ void accumulateDelta(NodeAcc& a, double v, u64 gIdx, const DevIndexView& I, const double* __restrict__ ell) {
+    if (v == v) {
+        a.S += v;
+        a.cnt += (v > 0.0) - (v < 0.0);
+    } else {
+        const u32 pc = __ldg(&I.pc[gIdx]);
+        const int p = (int)(short)(pc & 0xFFFFu), c = (int)(short)(pc >> 16);
+        const double lr = ell[__ldg(&I.seedId[gIdx])];
+        const double logP = p > 0 ? __ldg(&I.log1pSmall[p]) : 0.0;
+        const double logC = c > 0 ? __ldg(&I.log1pSmall[c]) : 0.0;
+        const DeltaTerms d = deltaTerms(lr, p, c, logP, logC);
+        a.gRaw += d.raw; a.gCos += d.cos; a.gWc += d.wc; a.gCont += d.cont; a.gPres += d.pres;
+    }
+}
+__device__ __forceinline__ NodeDelta finishNode(const NodeAcc& a, double ln2) {
+    NodeDelta d;
+    d.raw = a.S + a.gRaw;
+    d.cos = a.S * ln2 + a.gCos;
+    d.wc = (double)a.cnt + a.gWc;
+    d.cont = a.S + a.gCont;
+    d.pres = (long long)a.cnt + (long long)a.gPres;
+    return d;
+}
+__device__ __forceinline__ NodeAcc warpReduceNodeAcc(NodeAcc a) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a.S += shflXorF64(a.S, d); a.gRaw += shflXorF64(a.gRaw, d); a.gCos += shflXorF64(a.gCos, d);
+        a.gWc += shflXorF64(a.gWc, d); a.gCont += shflXorF64(a.gCont, d);
+        a.cnt += __shfl_xor_sync(0xffffffffu, a.cnt, d); a.gPres += __shfl_xor_sync(0xffffffffu, a.gPres, d);
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(256) node_deltas(DevIndexView I, WorkspaceView W) {
+    __shared__ double sV[kTileDeltas];
+    __shared__ u32 sBig[160];
+    __shared__ int sBigCount;
+    __shared__ NodeAcc sWarpAcc[8];
+    const double* __restrict__ ell = W.ell;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sBigCount = 0;
+    __syncthreads();
+    for (u32 ti = blockIdx.x; ti < I.nK1Tiles; ti += gridDim.x) {
+        const K1Tile t = I.k1Tiles[ti];
+        for (u32 i = tid; i < t.dCount; i += 256) {
+            const u32 pc = __ldg(&I.pc[t.dBegin + i]);
+            const int p = (int)(short)(pc & 0xFFFFu), c = (int)(short)(pc >> 16);
+            double v = 0.0;
+            if (p != c) {
+                const double lr = ell[__ldg(&I.seedId[t.dBegin + i])];
+                if (lr > 0.0) {
+                    if ((unsigned)p <= 1u && (unsigned)c <= 1u) v = c > p ? lr : -lr;
+                    else v = __longlong_as_double(0x7FF8000000000000LL);
+                }
+            }
+            sV[i] = v;
+        }
+        __syncthreads();
+        if (t.kind == 0) {
+            for (u32 ln = t.lnBegin + tid; ln < t.lnEnd; ln += 256) {
+                const u64 b = I.lOff[ln], e = I.lOff[ln + 1];
+                const u32 n = (u32)(e - b);
+                if (n <= 32) {
+                    NodeAcc a; nodeAccInit(a);
+                    const u32 o = (u32)(b - t.dBegin);
+                    for (u32 j = 0; j < n; ++j) accumulateDelta(a, sV[o + j], b + j, I, ell);
+                    W.delta[I.lNode[ln]] = finishNode(a, I.ln2);
+                } else {
+                    const int q = atomicAdd(&sBigCount, 1);
+                    sBig[q] = ln;
+                }
+            }
+            __syncthreads();
+            const int nb = sBigCount;
+            for (int q = warp; q < nb; q += 8) {
+                const u32 ln = sBig[q];
+                const u64 b = I.lOff[ln], e = I.lOff[ln + 1];
+                const u32 n = (u32)(e - b), o = (u32)(b - t.dBegin);
+                NodeAcc a; nodeAccInit(a);
+                for (u32 j = lane; j < n; j += 32) accumulateDelta(a, sV[o + j], b + j, I, ell);
+                a = warpReduceNodeAcc(a);
+                if (lane == 0) W.delta[I.lNode[ln]] = finishNode(a, I.ln2);
+            }
+            __syncthreads();
+            if (tid == 0) sBigCount = 0;
+        } else {
+            // chunk of one large node: block-wide sum, partial to global, last chunk adds the partials in order
+            NodeAcc a; nodeAccInit(a);
+            for (u32 j = tid; j < t.dCount; j += 256) accumulateDelta(a, sV[j], t.dBegin + j, I, ell);
+            a = warpReduceNodeAcc(a);
+            if (lane == 0) sWarpAcc[warp] = a;
+            __syncthreads();
+            if (tid == 0) {
+                NodeAcc s = sWarpAcc[0];
+                for (int w = 1; w < 8; ++w) {
+                    const NodeAcc o = sWarpAcc[w];
+                    s.S += o.S; s.gRaw += o.gRaw; s.gCos += o.gCos; s.gWc += o.gWc; s.gCont += o.gCont; s.cnt += o.cnt; s.gPres += o.gPres;
+                }
+                W.bigPartial[t.bigSlot] = finishNode(s, I.ln2);
+                __threadfence();
+                const BigNode bn = I.bigNodes[t.bigNode];
+                const unsigned done = atomicAdd(&W.bigDone[t.bigNode], 1u);
+                if (done == bn.nPartials - 1) {
+                    __threadfence();
+                    NodeDelta d; d.raw = d.cos = d.wc = d.cont = 0.0; d.pres = 0;
+                    for (u32 k = 0; k < bn.nPartials; ++k) {
+                        const volatile NodeDelta* pp = &W.bigPartial[bn.firstPartial + k];
+                        d.raw += pp->raw; d.cos += pp->cos; d.wc += pp->wc; d.cont += pp->cont; d.pres += pp->pres;
+                    }
+                    W.delta[I.lNode[bn.localNode]] = d;
+                    W.bigDone[t.bigNode] = 0;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st) {
+    if (I.nK1Tiles == 0) return;
+    unsigned grid = (unsigned)nSM * 6u;
+    if (grid > I.nK1Tiles) grid = I.nK1Tiles;
+    node_deltas<<<grid, 256, 0, st>>>(I, W);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2 prefix_scores: A[v] = sum of delta over the root->v path, exact.
+// Tile = kTileNodesK2 consecutive DFS nodes.  The carry-in of a tile is the path root -> parent(first node),
+// whose per-node deltas were all written by K1, so every tile is independent (no inter-CTA dependency):
+//   1. exact inclusive scan along the precomputed ancestor chain -> A[ancestor j]
+//   2. d'[w] = delta[w] (+ A[parent(w)] when the parent lies outside the tile)
+//   3. Euler-tour difference inside the tile: diff[w] = d'[w] - sum_{u in tile, subtree(u) ends right before w} d'[u]
+//   4. inclusive scan of diff = A[w]; scores; store
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Acc5 accZero() { Acc5 a; a.f[0] = a.f[1] = a.f[2] = a.f[3] = fxZero(); a.pres = 0; return a; }
+__device__ __forceinline__ Acc5 accAdd(const Acc5& a, const Acc5& b) {
+    Acc5 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.f[i] = fxAdd(a.f[i], b.f[i]);
+    r.pres = a.pres + b.pres; return r;
+}
+__device__ __forceinline__ Acc5 accSub(const Acc5& a, const Acc5& b) {
+    Acc5 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.f[i] = fxSub(a.f[i], b.f[i]);
+    r.pres = a.pres - b.pres; return r;
+}
+__device__ __forceinline__ Acc5 accFromDelta(const NodeDelta& d) {
+    Acc5 a; a.f[0] = fxFromDouble(d.raw); a.f[1] = fxFromDouble(d.cos); a.f[2] = fxFromDouble(d.wc); a.f[3] = fxFromDouble(d.cont);
+    a.pres = d.pres; return a;
+}
+__device__ __forceinline__ Acc5 accShflUp(const Acc5& a, int d) {
+    Acc5 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r.f[i].lo = shflUpU64(a.f[i].lo, d); r.f[i].hi = (i64)shflUpU64((u64)a.f[i].hi, d); }
+    r.pres = (i64)shflUpU64((u64)a.pres, d); return r;
+}
+__device__ __forceinline__ void accStore(u64* p, const Acc5& a) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { p[2 * i] = a.f[i].lo; p[2 * i + 1] = (u64)a.f[i].hi; }
+    p[8] = (u64)a.pres;
+}
+__device__ __forceinline__ Acc5 accLoad(const u64* p) {
+    Acc5 a;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a.f[i].lo = p[2 * i]; a.f[i].hi = (i64)p[2 * i + 1]; }
+    a.pres = (i64)p[8]; return a;
+}
+// block-wide inclusive scan over 256 threads (one Acc5 each); sWarp: 8*9 u64 of shared scratch
+__device__ __forceinline__ Acc5 blockInclusiveScan(Acc5 v, u64* sWarp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Acc5 o = accShflUp(v, d);
+        if (lane >= d) v = accAdd(v, o);
+    }
+    __syncthreads();
+    if (lane == 31) accStore(sWarp + 9 * warp, v);
+    __syncthreads();
+    Acc5 pre = accZero();
+    for (int w = 0; w < warp; ++w) pre = accAdd(pre, accLoad(sWarp + 9 * w));
+    return accAdd(v, pre);
+}
+
+__global__ void __launch_bounds__(256) prefix_scores(DevIndexView I, WorkspaceView W, PlaceOpts O) {
+    __shared__ u64 sD[kTileNodesK2 * 9];
+    __shared__ u64 sWarp[8 * 9];
+    __shared__ u64 sCarry[9];
+    const u32 tile = blockIdx.x;
+    const u32 a0 = I.nodeBegin + tile * kTileNodesK2;
+    const u32 a1 = min(a0 + (u32)kTileNodesK2, I.nodeEnd);
+    const int tid = threadIdx.x;
+    const SampleScalars S = *W.scalars;
+
+    // 1. ancestor chain
+    const u32 cb = I.chainOff[tile], ce = I.chainOff[tile + 1];
+    Acc5 carry = accZero();
+    for (u32 base = cb; base < ce; base += 256) {
+        Acc5 v = accZero();
+        const u32 j = base + tid;
+        if (j < ce) v = accFromDelta(W.delta[I.chainNodes[j]]);
+        v = blockInclusiveScan(v, sWarp);
+        v = accAdd(v, carry);
+        if (j < ce) accStore(W.chainA + (size_t)j * 9, v);
+        if (tid == 255) accStore(sCarry, v);
+        __syncthreads();
+        carry = accLoad(sCarry);
+        __syncthreads();
+    }
+    __syncthreads();
+    // 2. d'
+    for (u32 w = a0 + tid; w < a1; w += 256) {
+        Acc5 v = accFromDelta(W.delta[w]);
+        const u32 cs = I.carrySlot[w];
+        if (cs != kNone) v = accAdd(v, accLoad(W.chainA + (size_t)(cb + cs) * 9));
+        accStore(sD + (size_t)(w - a0) * 9, v);
+    }
+    __syncthreads();
+    // 3+4. two consecutive nodes per thread
+    const u32 w0 = a0 + 2 * tid;
+    Acc5 d[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const u32 w = w0 + q;
+        d[q] = accZero();
+        if (w < a1) {
+            d[q] = accLoad(sD + (size_t)(w - a0) * 9);
+            const u32 c0 = I.closeOff[w], c1 = I.closeOff[w + 1];
+            for (u32 c = c0; c < c1; ++c) {
+                const u32 u = I.closeList[c];
+                if (u >= a0) d[q] = accSub(d[q], accLoad(sD + (size_t)(u - a0) * 9));
+            }
+        }
+    }
+    const Acc5 mine = accAdd(d[0], d[1]);
+    const Acc5 incl = blockInclusiveScan(mine, sWarp);
+    Acc5 run = accSub(incl, mine);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const u32 w = w0 + q;
+        if (w < a1) {
+            run = accAdd(run, d[q]);
+            const double raw = fxToDouble(run.f[0]), cs = fxToDouble(run.f[1]), wc = fxToDouble(run.f[2]), ct = fxToDouble(run.f[3]);
+            double sc[5];
+            nodeScores(raw, cs, (double)(u64)run.pres, wc, ct, I.gMag[w], S, sc);
+            double* o = W.scores + (size_t)w * 5;
+            o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3]; o[4] = sc[4];
+            if (W.metrics) {
+                double* m = W.metrics + (size_t)w * 5;
+                m[0] = raw; m[1] = cs; m[2] = (double)run.pres; m[3] = wc; m[4] = ct;
+            }
+        }
+    }
+}
+void launchPrefixScores(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st) {
+    if (I.nK2Tiles == 0) return;
+    prefix_scores<<<I.nK2Tiles, 256, 0, st>>>(I, W, O);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// selection.  The reference scores nodes in BFS order and keeps (best, tie list) with a relative tolerance:
+// a node becomes the new best only if score > best + max(best*1e-4, 1e-9) (placement.cpp:355-371).  Every such
+// "event" is a strict prefix maximum of the BFS-ordered score sequence, so:
+//   bfs_gather   scores -> BFS order (ineligible nodes get -1), per-block maxima
+//   bfs_records  prefix maxima ("records"), a short list per metric
+//   chain        replays the tolerance chain over the records only
+//   ties         nodes after the last event with score >= best - tol and > 0
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warpMaxF64(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, shflXorF64(v, d));
+    return v;
+}
+
+__global__ void __launch_bounds__(256) bfs_gather(DevIndexView I, WorkspaceView W, PlaceOpts O, double* __restrict__ bfsScores) {
+    __shared__ double sMax[8][5];
+    const u32 base = blockIdx.x * kBfsBlock;
+    double mx[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
+    for (int q = 0; q < 4; ++q) {
+        const u32 r = base + q * 256 + threadIdx.x;
+        if (r < I.nShardNodes) {
+            const u32 v = I.bfsNodes[r];
+            const bool ok = (v != O.skipNode) && (!O.forceLeaf || I.isLeaf[v]);
+            const double* s = W.scores + (size_t)v * 5;
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                const double x = ok ? s[m] : -1.0;
+                bfsScores[(size_t)m * I.nShardNodes + r] = x;
+                mx[m] = fmax(mx[m], x);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m) mx[m] = warpMaxF64(mx[m]);
+    if ((threadIdx.x & 31) == 0)
+        for (int m = 0; m < 5; ++m) sMax[threadIdx.x >> 5][m] = mx[m];
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double v = sMax[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) v = fmax(v, sMax[w][threadIdx.x]);
+        W.blockMax[(size_t)blockIdx.x * 5 + threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) bfs_records(DevIndexView I, WorkspaceView W, const double* __restrict__ bfsScores) {
+    // grid: (nBfsBlocks, 5)
+    __shared__ double sRed[8];
+    __shared__ double sPrev;
+    __shared__ double sThread[256];
+    const int m = blockIdx.y;
+    const u32 blk = blockIdx.x;
+    // exclusive prefix maximum over earlier blocks (records must also be > 0)
+    double pm = 0.0;
+    for (u32 j = threadIdx.x; j < blk; j += 256) pm = fmax(pm, W.blockMax[(size_t)j * 5 + m]);
+    pm = warpMaxF64(pm);
+    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = pm;
+    __syncthreads();
+    if (threadIdx.x == 0) { double v = sRed[0]; for (int w = 1; w < 8; ++w) v = fmax(v, sRed[w]); sPrev = v; }
+    __syncthreads();
+    const double prev = sPrev;
+    if (W.blockMax[(size_t)blk * 5 + m] <= prev) return;  // no record in this block
+    // 4 consecutive positions per thread
+    const u32 r0 = blk * kBfsBlock + threadIdx.x * 4;
+    double x[4]; double tmax = -1.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const u32 r = r0 + q;
+        x[q] = r < I.nShardNodes ? bfsScores[(size_t)m * I.nShardNodes + r] : -1.0;
+        tmax = fmax(tmax, x[q]);
+    }
+    sThread[threadIdx.x] = tmax;
+    __syncthreads();
+    double run = prev;
+    for (int j = 0; j < (int)threadIdx.x; ++j) run = fmax(run, sThread[j]);  // 256x256/2 smem reads, rare blocks only
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const u32 r = r0 + q;
+        if (r < I.nShardNodes && x[q] > run) {
+            const unsigned o = atomicAdd(&W.acc->recordCount[m], 1u);
+            if (o < W.recCap) {
+                W.recRank[(size_t)m * W.recCap + o] = I.bfsRanks[r];
+                W.recNode[(size_t)m * W.recCap + o] = I.bfsNodes[r];
+                W.recScore[(size_t)m * W.recCap + o] = x[q];
+            } else W.acc->overflow = 1;
+        }
+        run = fmax(run, x[q]);
+    }
+}
+
+// tolerance chain over the records of one metric (block m).  Records are unordered: every step finds the
+// lowest-rank record after the last event that beats best + tol.
+__global__ void __launch_bounds__(256) chain_select(WorkspaceView W, const u32* __restrict__ countOverride) {
+    __shared__ unsigned long long sMin[8];
+    __shared__ unsigned long long sPick;
+    const int m = blockIdx.x;
+    unsigned n = countOverride ? countOverride[m] : W.acc->recordCount[m];
+    if (n > W.recCap) n = W.recCap;
+    const u32* rk = W.recRank + (size_t)m * W.recCap;
+    const u32* nd = W.recNode + (size_t)m * W.recCap;
+    const double* sc = W.recScore + (size_t)m * W.recCap;
+    double best = 0.0; u32 bestNode = kNone; long long lastRank = -1;
+    while (true) {
+        const double tol = fmax(best * 0.0001, 1e-9);
+        const double thr = best + tol;
+        unsigned long long pick = ~0ULL;
+        for (unsigned i = threadIdx.x; i < n; i += 256) {
+            if ((long long)rk[i] > lastRank && sc[i] > thr) {
+                const unsigned long long key = ((unsigned long long)rk[i] << 32) | i;
+                pick = key < pick ? key : pick;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = shflXorU64(pick, d); pick = o < pick ? o : pick; }
+        if ((threadIdx.x & 31) == 0) sMin[threadIdx.x >> 5] = pick;
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned long long v = sMin[0]; for (int w = 1; w < 8; ++w) v = sMin[w] < v ? sMin[w] : v; sPick = v; }
+        __syncthreads();
+        const unsigned long long p = sPick;
+        __syncthreads();
+        if (p == ~0ULL) break;
+        const unsigned i = (unsigned)(p & 0xFFFFFFFFu);
+        best = sc[i]; bestNode = nd[i]; lastRank = (long long)(p >> 32);
+    }
+    if (threadIdx.x == 0) {
+        Selection s; s.best = best; s.bestNode = bestNode; s.lastRank = lastRank < 0 ? kNone : (u32)lastRank;
+        W.sel[m] = s;
+    }
+}
+void launchChain(WorkspaceView W, const u32* recCountOverride, cudaStream_t st) { chain_select<<<5, 256, 0, st>>>(W, recCountOverride); }
+
+__global__ void __launch_bounds__(256) collect_ties(DevIndexView I, WorkspaceView W, const double* __restrict__ bfsScores) {
+    const int m = blockIdx.y;
+    const Selection s = W.sel[m];
+    const double tol = fmax(s.best * 0.0001, 1e-9);
+    const double lo = s.best - tol;
+    if (W.blockMax[(size_t)blockIdx.x * 5 + m] < lo) return;
+    for (int q = 0; q < 4; ++q) {
+        const u32 r = blockIdx.x * kBfsBlock + q * 256 + threadIdx.x;
+        if (r >= I.nShardNodes) continue;
+        const u32 rank = I.bfsRanks[r];
+        if (s.lastRank != kNone && rank <= s.lastRank) continue;
+        const double x = bfsScores[(size_t)m * I.nShardNodes + r];
+        if (x >= lo && x > 0.0) {
+            const unsigned o = atomicAdd(&W.acc->tieCount[m], 1u);
+            if (o < W.tieCap) W.tieNode[(size_t)m * W.tieCap + o] = I.bfsNodes[r]; else W.acc->overflow = 1;
+        }
+    }
+}
+
+// bfsScores lives right after blockMax in the workspace (allocated by the host as one buffer)
+static double* bfsScoresOf(const DevIndexView& I, const WorkspaceView& W) { return W.blockMax + (size_t)I.nBfsBlocks * 5; }
+
+void launchRecords(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st) {
+    if (I.nBfsBlocks == 0) return;
+    double* bs = bfsScoresOf(I, W);
+    bfs_gather<<<I.nBfsBlocks, 256, 0, st>>>(I, W, O, bs);
+    bfs_records<<<dim3(I.nBfsBlocks, 5), 256, 0, st>>>(I, W, bs);
+}
+void launchTies(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st) {
+    if (I.nBfsBlocks == 0) return;
+    collect_ties<<<dim3(I.nBfsBlocks, 5), 256, 0, st>>>(I, W, bfsScoresOf(I, W));
+}
+
+}  // namespace pm

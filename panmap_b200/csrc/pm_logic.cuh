@@ -1,0 +1,310 @@
+// pm_logic.cuh -- arithmetic shared by every kernel of the placement path, written as PM_HD
+// (__host__ __device__) so tests/hostcheck can run the exact same code on the CPU against the oracle
+// before it ever reaches a GPU.  Nothing here is a CPU fallback: the product library only instantiates it
+// inside __global__ kernels.
+//
+// Reference semantics restated here (paths relative to /root/reference/):
+//   seeding.hpp:86-120        chash / comp / rol / ror
+//   seeding.cpp:47-229        rollingSyncmers (rolling k-mer and s-mer hashes on both strands, window minima)
+//   placement.cpp:1598-1686   per-read k-min-mer construction (l > 1) and trim filter
+//   placement.cpp:242-345     per-delta contributions of computeChildMetrics
+//   placement.hpp:120-149     the five score getters
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PM_HD __host__ __device__ __forceinline__
+#else
+#define PM_HD inline
+#endif
+
+namespace pm {
+
+typedef uint64_t u64;
+typedef int64_t i64;
+typedef uint32_t u32;
+
+constexpr u64 kHashA = 0x3c8bfbb395c60474ULL;
+constexpr u64 kHashC = 0x3193c18562a02b4cULL;
+constexpr u64 kHashG = 0x20323ed082572324ULL;
+constexpr u64 kHashT = 0x295549f54be24456ULL;
+constexpr u64 kEmptyKey = 0xFFFFFFFFFFFFFFFFULL;
+constexpr int kMaxK = 32;  // 4-bit base codes in a 128-bit history register
+
+PM_HD u64 rol64(u64 h, unsigned r) { r &= 63u; return r ? (h << r) | (h >> (64u - r)) : h; }
+PM_HD u64 ror64(u64 h, unsigned r) { r &= 63u; return r ? (h >> r) | (h << (64u - r)) : h; }
+PM_HD u64 rol1(u64 h) { return (h << 1) | (h >> 63); }
+PM_HD u64 ror1(u64 h) { return (h >> 1) | (h << 63); }
+PM_HD u64 umin64(u64 a, u64 b) { return a < b ? a : b; }
+
+// base code: A 0, C 1, G 2, T 3 (either case), anything else 4 (ambiguous, hash contribution 0)
+PM_HD unsigned baseCode(unsigned char c) {
+    switch (c) {
+        case 'A': case 'a': return 0; case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2; case 'T': case 't': return 3;
+        default: return 4;
+    }
+}
+PM_HD u64 codeHash(unsigned code) {
+    return code == 0 ? kHashA : code == 1 ? kHashC : code == 2 ? kHashG : code == 3 ? kHashT : 0ULL;
+}
+
+// Per-(k,s) rotated constants, 8 entries each (4..7 are zero so that "ambiguous / not yet seen" needs no branch).
+struct SeedTables {
+    u64 fwdNew[8];   // c(b)
+    u64 fwdOldK[8];  // rol(c(b), k)
+    u64 fwdOldS[8];  // rol(c(b), s)
+    u64 revNewK[8];  // rol(c(comp b), k-1)
+    u64 revNewS[8];  // rol(c(comp b), s-1)
+    u64 revOld[8];   // ror(c(comp b), 1)
+};
+inline void buildSeedTables(SeedTables& T, int k, int s) {
+    for (unsigned c = 0; c < 8; ++c) {
+        const u64 f = codeHash(c), r = c < 4 ? codeHash(3 - c) : 0ULL;
+        T.fwdNew[c] = f;
+        T.fwdOldK[c] = rol64(f, (unsigned)k);
+        T.fwdOldS[c] = rol64(f, (unsigned)s);
+        T.revNewK[c] = rol64(r, (unsigned)(k - 1));
+        T.revNewS[c] = rol64(r, (unsigned)(s - 1));
+        T.revOld[c] = ror64(r, 1);
+    }
+}
+
+struct SeederParams {
+    int k, s, t, l, open;
+    int w;           // k - s + 1
+    unsigned rotK;   // k mod 64
+    unsigned rotKL;  // k*l mod 64
+    unsigned rotKL1; // k*(l-1) mod 64
+    int trimStart, trimEnd;
+};
+inline SeederParams makeSeederParams(int k, int s, int t, int l, int open, int trimStart, int trimEnd) {
+    SeederParams p;
+    p.k = k; p.s = s; p.t = t; p.l = l; p.open = open; p.w = k - s + 1;
+    p.rotK = (unsigned)k & 63u;
+    p.rotKL = (unsigned)((long long)k * l) & 63u;
+    p.rotKL1 = (unsigned)((long long)k * (l > 0 ? l - 1 : 0)) & 63u;
+    p.trimStart = trimStart; p.trimEnd = trimEnd;
+    return p;
+}
+
+// Sequential per-read seeder: feed bases one at a time; emits syncmers (and k-min-mers for l > 1).
+// Ring storage (4*w + max(l,1) u64 words) is supplied by the caller as a strided view so that a CUDA block can
+// lay the rings out [slot][thread] in shared memory (conflict-free) and the host check can use a plain array.
+struct ReadSeeder {
+    u64 fk, rk, fs, rs;      // rolling k-mer / s-mer hashes, both strands
+    u64 histLo, histHi;      // last 32 base codes, 4 bits each, newest in bits 0..3 of histLo
+    u64 preF, preR;          // running minima of the current block (van Herk / Gil-Werman sliding minimum)
+    u64 kmF, kmR;            // rolling k-min-mer hashes
+    int lastAmb;             // index of the most recent ambiguous base
+    int slot;                // (s-mer index) mod w
+    int synCount;            // in-range syncmers seen so far
+    unsigned kmRot;          // (k * synCount) mod 64 during the first l syncmers
+    u64* ring;               // strided storage
+    int stride;
+
+    PM_HD u64& F(int i) { return ring[(size_t)i * stride]; }
+    PM_HD u64& Fsuf(int i, int w) { return ring[(size_t)(w + i) * stride]; }
+    PM_HD u64& R(int i, int w) { return ring[(size_t)(2 * w + i) * stride]; }
+    PM_HD u64& Rsuf(int i, int w) { return ring[(size_t)(3 * w + i) * stride]; }
+    PM_HD u64& H(int i, int w) { return ring[(size_t)(4 * w + i) * stride]; }
+
+    PM_HD void reset(u64* ringBase, int ringStride) {
+        fk = rk = fs = rs = 0; kmF = kmR = 0;
+        histLo = histHi = 0x4444444444444444ULL;  // every past base "ambiguous": table entry 0
+        preF = preR = kEmptyKey;
+        lastAmb = -1; slot = -1; synCount = 0; kmRot = 0;
+        ring = ringBase; stride = ringStride;
+    }
+    PM_HD unsigned codeBack(int dist) const {  // code of the base `dist` positions before the one being pushed (dist >= 1)
+        const int sh = 4 * (dist - 1);
+        return (unsigned)((sh < 64 ? (histLo >> sh) : (histHi >> (sh - 64))) & 0xFULL);
+    }
+
+    // Push base `code` at read position i (0-based).  Returns true when k-mer window i-k+1 is a syncmer;
+    // hash / isReverse are then set.  (seeding.cpp:147-226 restated with no per-step rescans.)
+    PM_HD bool pushBase(int i, unsigned code, const SeedTables& T, const SeederParams& P, u64& hash, bool& isReverse) {
+        const unsigned oldK = codeBack(P.k), oldS = codeBack(P.s);
+        fk = rol1(fk) ^ T.fwdOldK[oldK] ^ T.fwdNew[code];
+        rk = ror1(rk) ^ T.revOld[oldK] ^ T.revNewK[code];
+        fs = rol1(fs) ^ T.fwdOldS[oldS] ^ T.fwdNew[code];
+        rs = ror1(rs) ^ T.revOld[oldS] ^ T.revNewS[code];
+        histHi = (histHi << 4) | (histLo >> 60);
+        histLo = (histLo << 4) | (u64)code;
+        if (code >= 4) lastAmb = i;
+        if (i < P.s - 1) return false;
+        const int w = P.w;
+        slot = (slot + 1 == w) ? 0 : slot + 1;
+        F(slot) = fs; R(slot, w) = rs;
+        if (slot == 0) { preF = fs; preR = rs; } else { preF = umin64(preF, fs); preR = umin64(preR, rs); }
+        bool syn = false;
+        if (i >= P.k - 1) {
+            const int pslot = (slot + 1 == w) ? 0 : slot + 1;  // slot of the oldest s-mer of the window
+            u64 mf = preF, mr = preR;
+            if (pslot != 0) { mf = umin64(mf, Fsuf(pslot, w)); mr = umin64(mr, Rsuf(pslot, w)); }
+            int ia = pslot + P.t; if (ia >= w) ia -= w;            // s-mer p+t
+            int ib = slot - P.t; if (ib < 0) ib += w;              // s-mer p+k-s-t
+            bool fsyn, rsyn;
+            if (P.open) { fsyn = F(ia) == mf; rsyn = R(ib, w) == mr; }
+            else { fsyn = (F(ia) == mf) || (F(ib) == mf); rsyn = (R(ib, w) == mr) || (R(ia, w) == mr); }
+            syn = (i - lastAmb >= P.k) && (fsyn || rsyn) && (fk != rk);
+            hash = umin64(fk, rk);
+            isReverse = rk < fk;
+        }
+        if (slot == w - 1) {  // block complete: suffix minima for the windows that straddle into the next block
+            u64 a = kEmptyKey, b = kEmptyKey;
+            for (int q = w - 1; q >= 0; --q) {
+                a = umin64(a, F(q)); Fsuf(q, w) = a;
+                b = umin64(b, R(q, w)); Rsuf(q, w) = b;
+            }
+        }
+        return syn;
+    }
+
+    // A syncmer (start position pos, canonical hash h) of a read of length len was found: apply the trim filter
+    // and the k-min-mer construction.  Returns true when a seed is to be counted (placement.cpp:1627-1682).
+    PM_HD bool pushSyncmer(int pos, int len, u64 h, const SeederParams& P, u64& seed) {
+        if (pos < P.trimStart || pos > len - P.trimEnd - P.k) return false;
+        if (P.l <= 1) { seed = h; return true; }
+        const int w = P.w, l = P.l;
+        const int hs = synCount % l;
+        if (synCount < l) {
+            kmF = rol64(kmF, P.rotK) ^ h;
+            kmR ^= rol64(h, kmRot);
+            kmRot = (kmRot + P.rotK) & 63u;
+        } else {
+            const u64 prev = H(hs, w);
+            kmF = rol64(kmF, P.rotK) ^ rol64(prev, P.rotKL) ^ h;
+            kmR = ror64(kmR, P.rotK) ^ ror64(prev, P.rotK) ^ rol64(h, P.rotKL1);
+        }
+        H(hs, w) = h;
+        ++synCount;
+        if (synCount >= l && kmF != kmR) { seed = umin64(kmF, kmR); return true; }
+        return false;
+    }
+};
+PM_HD int seederRingWords(int k, int s, int l) { return 4 * (k - s + 1) + (l > 1 ? l : 1); }
+
+// ---- exact accumulation: signed 128-bit fixed point, 64 fractional bits --------------------------------
+// Every f64 quantity that is summed across nodes (tree prefix) or across table slots (read magnitudes) is first
+// truncated to a multiple of 2^-64 and then added as an integer, so sums are associative: the Euler-tour
+// +delta/-delta cancellation is exact and results do not depend on tile shape, GPU count or atomics order.
+// |x| < 2^62 is required (numerators are bounded by (#seeds) * log1p(count) << 2^62).
+struct fx128 { u64 lo; i64 hi; };
+PM_HD fx128 fxZero() { fx128 z; z.lo = 0; z.hi = 0; return z; }
+PM_HD fx128 fxAdd(fx128 a, fx128 b) {
+    fx128 r; r.lo = a.lo + b.lo; r.hi = (i64)((u64)a.hi + (u64)b.hi + (r.lo < a.lo ? 1ULL : 0ULL)); return r;
+}
+PM_HD fx128 fxNeg(fx128 a) {
+    fx128 r; r.lo = ~a.lo + 1ULL; r.hi = (i64)(~(u64)a.hi + (r.lo == 0 ? 1ULL : 0ULL)); return r;
+}
+PM_HD fx128 fxSub(fx128 a, fx128 b) { return fxAdd(a, fxNeg(b)); }
+PM_HD fx128 fxFromInt(i64 v) { fx128 r; r.lo = 0; r.hi = v; return r; }
+PM_HD u64 dblBits(double x) {
+#if defined(__CUDA_ARCH__)
+    return (u64)__double_as_longlong(x);
+#else
+    union { double d; u64 u; } c; c.d = x; return c.u;
+#endif
+}
+PM_HD double bitsDbl(u64 b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    union { double d; u64 u; } c; c.u = b; return c.d;
+#endif
+}
+PM_HD fx128 fxFromDouble(double x) {  // truncates |x| toward zero at 2^-64; fx(-x) == -fx(x)
+    const u64 b = dblBits(x);
+    const int e = (int)((b >> 52) & 0x7FF);
+    if (e == 0 || e == 0x7FF) return fxZero();  // zero / subnormal / non-finite contribute nothing
+    const u64 m = (b & 0xFFFFFFFFFFFFFULL) | 0x10000000000000ULL;
+    const int sh = e - 1075 + 64;  // value * 2^64 = m * 2^sh
+    fx128 r;
+    if (sh >= 64) { r.lo = 0; r.hi = (sh - 64 < 10) ? (i64)(m << (sh - 64)) : (i64)0x3FFFFFFFFFFFFFFFLL; }
+    else if (sh > 0) { r.lo = m << sh; r.hi = (i64)(m >> (64 - sh)); }
+    else if (sh == 0) { r.lo = m; r.hi = 0; }
+    else if (sh > -53) { r.lo = m >> (-sh); r.hi = 0; }
+    else return fxZero();
+    return (b >> 63) ? fxNeg(r) : r;
+}
+PM_HD int clz64(u64 x) {
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
+}
+PM_HD double fxToDouble(fx128 a) {  // round-to-nearest-even of the exact value
+    const bool neg = a.hi < 0;
+    if (neg) a = fxNeg(a);
+    const u64 hi = (u64)a.hi, lo = a.lo;
+    if (hi == 0 && lo == 0) return 0.0;
+    // normalise to a 64-bit mantissa t with sticky bit, value = t * 2^ex
+    u64 t; int ex;
+    if (hi == 0) { const int z = clz64(lo); t = lo << z; ex = -64 - z; }
+    else {
+        const int z = clz64(hi);
+        t = z ? (hi << z) | (lo >> (64 - z)) : hi;
+        const u64 rest = z ? (lo << z) : lo;
+        if (rest) t |= 1ULL;
+        ex = -z;
+    }
+    // t has its top bit set: keep 53 bits, round to nearest even using the low 11 bits
+    u64 mant = t >> 11;
+    const u64 rem = t & 0x7FFULL;
+    if (rem > 0x400ULL || (rem == 0x400ULL && (mant & 1ULL))) ++mant;
+    int e2 = ex + 11;  // value = mant * 2^e2, mant in [2^52, 2^53]
+    if (mant == (1ULL << 53)) { mant >>= 1; ++e2; }
+    const u64 bits = ((u64)(e2 + 52 + 1023) << 52) | (mant & 0xFFFFFFFFFFFFFULL);
+    const double d = bitsDbl(bits);
+    return neg ? -d : d;
+}
+
+// ---- per-delta contribution (placement.cpp:282-339) ---------------------------------------------------
+struct DeltaTerms { double raw, cos, wc, cont; int pres; };
+// lr = log1p(readCount) of the seed (> 0), p/c = parent/child genome counts, logP/logC = log1p of them (0 when count<=0)
+PM_HD DeltaTerms deltaTerms(double lr, int p, int c, double logP, double logC) {
+    DeltaTerms d;
+    d.pres = (int)((p == 0) & (c != 0)) - (int)((c == 0) & (p != 0));
+    d.raw = (c > 0 ? lr / (double)c : 0.0) - (p > 0 ? lr / (double)p : 0.0);
+    d.cos = lr * (logC - logP);
+    d.wc = (c > 0 ? 1.0 / (double)c : 0.0) - (p > 0 ? 1.0 / (double)p : 0.0);
+    d.cont = (double)d.pres * lr;
+    return d;
+}
+
+// ---- the five scores (placement.hpp:120-149) ----
+struct SampleScalars {
+    double readMagnitude;       // sqrt(sum log1p(count)^2)
+    double logContDenom;        // sum log1p(count)
+    double wcDenom;             // sum over root seeds in reads of 1/childCount
+    double uniqueKept;          // U' as double
+    long long minSupport;
+    long long uniqueSeeds;      // table entries after homopolymer removal / masking
+    long long uniqueKeptInt;    // U'
+    long long totalFrequency;   // sum of all counts (pre-filter)
+    long long multiSum, multiCount;  // auto min-support statistics
+    long long tableEntries;     // occupied slots before filters
+    long long overflow;         // set when the table or a list ran out of room
+};
+PM_HD void nodeScores(double raw, double cosn, double pres, double wc, double cont, double gMag,
+                      const SampleScalars& S, double* out) {
+    // gMag = sqrt(genomeMagnitudeSquared), precomputed per node at index creation (sample independent)
+    out[0] = S.readMagnitude > 0.0 ? raw / S.readMagnitude : 0.0;
+    double v = 0.0;
+    if (!(S.readMagnitude <= 0.0 || gMag <= 0.0)) {
+        v = cosn / (S.readMagnitude * gMag);
+        v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+    }
+    out[1] = v;
+    out[2] = S.uniqueKept > 0.0 ? pres / S.uniqueKept : 0.0;
+    out[3] = S.wcDenom > 0.0 ? wc / S.wcDenom : 0.0;
+    out[4] = S.logContDenom > 0.0 ? cont / S.logContDenom : 0.0;
+}
+
+// table slot hash (keys are already hashes, but their low bits come from XORs of rotations: mix once)
+PM_HD u64 mixKey(u64 h) { h ^= h >> 32; h *= 0x9E3779B97F4A7C15ULL; h ^= h >> 29; return h; }
+
+}  // namespace pm

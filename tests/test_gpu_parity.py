@@ -1,0 +1,153 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+Integer / byte / index results are bit-exact; f64 scores agree to 1e-12 relative (absolute floor 1e-9 for values that
+are mathematically zero), the tolerance BASELINE.json's north_star states."""
+import os
+
+import numpy as np
+import pytest
+
+import panmap_b200 as pm
+from oracle import cpu
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12
+
+
+def test_rolling_syncmers_matches_oracle():
+    rng = np.random.default_rng(11)
+    for (k, s, t, op) in [(19, 8, 0, False), (15, 8, 0, False), (31, 8, 3, False), (19, 8, 2, True), (32, 1, 0, False), (8, 8, 0, False), (5, 2, 3, True)]:
+        reads = H.random_reads(rng, 300, lo=1, hi=200) + [b"", b"A", b"N" * 50, b"ACGT" * 100, b"a" * 60]
+        got = pm.rolling_syncmers(reads, k, s, op, t)
+        for r, (h, rev, pos) in zip(reads, got):
+            eh, erev, esyn, epos = cpu.rolling_syncmers(r, k, s, op, t, return_all=False)
+            assert np.array_equal(h, eh) and np.array_equal(rev, erev) and np.array_equal(pos, epos), (k, s, t, op, r)
+
+
+def test_read_seeds_match_oracle_including_trim_and_long_reads():
+    rng = np.random.default_rng(12)
+    reads = H.random_reads(rng, 400, lo=10, hi=180) + H.random_reads(rng, 3, lo=5000, hi=16000, p_n=0.0005)
+    for (k, s, t, l, op, ts, te) in [(19, 8, 0, 3, False, 0, 0), (15, 8, 0, 1, False, 0, 0), (19, 8, 0, 3, False, 7, 12),
+                                     (21, 10, 1, 2, True, 0, 0), (19, 8, 0, 0, False, 0, 5), (31, 8, 0, 5, False, 0, 0)]:
+        got = pm.read_seeds(reads, k, s, t, l, op, ts, te)
+        for r, g in zip(reads, got):
+            e = cpu.read_seeds(r, k, s, t, l, op, ts, te)
+            assert np.array_equal(g, e), (k, s, t, l, op, ts, te, len(r))
+
+
+def _place_and_check(idx, reads, params=None, **okw):
+    buf, off = pm.pack_reads(reads)
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open)
+    index = pm.Index(host)
+    ws = pm.Workspace(index)
+    res = ws.place(buf, off, params)
+    exp = cpu.place(buf, off, idx, want_scores=True, **okw)
+    # integers: bit-exact
+    assert res.raw.unique_seeds == exp["unique_seeds"]
+    assert res.raw.read_unique_seed_count == exp["kept"]
+    assert res.raw.total_read_seed_frequency == exp["total_frequency"]
+    assert res.raw.min_read_support == exp["min_support"]
+    th, tc = ws.seed_table()
+    eh, ec = cpu.seed_table(buf, off, idx.k, idx.s, idx.t, idx.l, idx.open, okw.get("trim_start", 0), okw.get("trim_end", 0))
+    keep = tc > 0
+    assert np.array_equal(th[keep], eh) and np.array_equal(tc[keep], ec)
+    # f64
+    assert H.relerr(res.raw.read_magnitude, exp["magnitude"]).max() < RTOL
+    assert H.relerr(res.raw.log_containment_denominator, exp["log_sum"]).max() < RTOL
+    assert H.relerr(res.raw.weighted_containment_denominator, exp["wc_denominator"]).max() < RTOL
+    sc = ws.node_scores()
+    assert H.relerr(sc, exp["scores"]).max() < RTOL
+    for m, name in enumerate(pm.METRICS):
+        assert H.relerr(res.best_score[name], exp["best_score"][m]).max() < RTOL, name
+        assert res.best_index[name] == exp["best_index"][m], name
+        assert np.array_equal(res.tied[name], exp["tied"][m]), name
+    return res, exp, ws, index
+
+
+def test_place_synthetic_index_with_table_only_reads():
+    """reads drawn so that seeds rarely hit the synthetic index: exercises table/filters/empty intersections"""
+    rng = np.random.default_rng(5)
+    idx, _, _ = H.synthetic_index(700, rng)
+    reads = H.random_reads(rng, 500)
+    _place_and_check(idx, reads)
+
+
+def test_place_empty_and_short_reads():
+    rng = np.random.default_rng(6)
+    idx, _, _ = H.synthetic_index(50, rng)
+    _place_and_check(idx, [b"ACGT", b"", b"NNNNNNNNNNNNNNNNNNNNNNNNN"])
+    _place_and_check(idx, [])
+
+
+@pytest.mark.skipif(not os.path.exists(H.SARS_IDX), reason="reference-built sars_20000 index not staged")
+def test_place_sars20000_isolate_matches_reference_golden_tsv():
+    """BASELINE config 1: the reference's only numeric golden for the path (examples/expected/single_sample/
+    isolate.placement.tsv), reproduced byte for byte through the C ABI."""
+    host = pm.HostIndex.read(H.SARS_IDX)
+    reads = H.isolate_reads()
+    buf, off = pm.pack_reads(reads)
+    index = pm.Index(host)
+    ws = pm.Workspace(index)
+    res = ws.place(buf, off)
+    with open(H.ISOLATE_TSV) as f:
+        assert res.tsv() == f.read()
+    exp = cpu.place(buf, off, host, want_scores=True)
+    assert res.raw.read_unique_seed_count == exp["kept"] == 117645
+    assert res.raw.unique_seeds == exp["unique_seeds"] == 317148
+    sc = ws.node_scores()
+    assert H.relerr(sc, exp["scores"]).max() < RTOL
+    for m, name in enumerate(pm.METRICS):
+        assert res.best_index[name] == exp["best_index"][m]
+        assert np.array_equal(res.tied[name], exp["tied"][m])
+    met = ws.node_metrics()
+    gold = np.load(os.path.join(H.GOLDEN, "sars_isolate_node_metrics_sample.npz"))
+    assert np.array_equal(met[gold["nodes"], 2], gold["metrics"][:, 2])          # presence: exact
+    assert H.relerr(met[gold["nodes"]], gold["metrics"][:, :5]).max() < RTOL
+
+
+@pytest.mark.skipif(not os.path.exists(H.SARS_IDX), reason="reference-built sars_20000 index not staged")
+def test_place_options_force_leaf_skip_node_min_support():
+    host = pm.HostIndex.read(H.SARS_IDX)
+    reads = H.isolate_reads()[:6000]
+    buf, off = pm.pack_reads(reads)
+    index = pm.Index(host)
+    ws = pm.Workspace(index)
+    for kw, okw in [(dict(force_leaf=1), dict(force_leaf=True)), (dict(skip_node_index=15189), dict(skip_node=15189)),
+                    (dict(min_read_support=1), dict(min_read_support=1)), (dict(min_read_support=3, trim_start=5, trim_end=9), dict(min_read_support=3, trim_start=5, trim_end=9))]:
+        res = ws.place(buf, off, pm.PlaceParams(**kw))
+        exp = cpu.place(buf, off, host, **okw)
+        for m, name in enumerate(pm.METRICS):
+            assert res.best_index[name] == exp["best_index"][m], (kw, name)
+            assert np.array_equal(res.tied[name], exp["tied"][m]), (kw, name)
+            assert H.relerr(res.best_score[name], exp["best_score"][m]).max() < RTOL
+
+
+def test_sharded_scoring_is_identical_to_single_shard():
+    """node-sharded runs (multi-GPU layout) on one device: scores of every shard equal the 1-shard scores bit for bit."""
+    rng = np.random.default_rng(9)
+    idx, hashes, genomes = H.synthetic_index(3000, rng, big_node=(40, 900))
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, 19, 8, 0, 3)
+    reads = H.random_reads(rng, 200)
+    buf, off = pm.pack_reads(reads)
+    # a read table that hits the index: import (hash,count) pairs directly through the staged API
+    leaf = 2999
+    th = np.array([hashes[j] for j in genomes[leaf].keys()], np.uint64)
+    tc = rng.integers(1, 50, size=th.size).astype(np.int64)
+    full = None
+    for n_sh in (1, 2, 5):
+        scores = np.zeros((3000, 5))
+        for sh in range(n_sh):
+            index = pm.Index(host, shard=sh, n_shards=n_sh)
+            ws = pm.Workspace(index)
+            p = pm.PlaceParams()
+            ws.stage_seed(buf, off, p)
+            ws.stage_table_import(th, tc)
+            ws.stage_score(p)
+            b, e = index.shard_range()
+            recs = ws.stage_records()
+            r = ws.stage_select(recs, len(reads))
+            scores[b:e] = ws.node_scores()[b:e]
+        if full is None:
+            full = scores
+        else:
+            assert np.array_equal(scores, full)
