@@ -1,0 +1,338 @@
+#!/usr/bin/env python3
+"""bench.py -- placement hot path throughput on B200 (metric of BASELINE.json: placement nodes x reads scored / s).
+
+One step = one pass of the whole place stage over one synthetic sample (BASELINE config 3 shape: 1M-node tree, 30 kb
+genome, 1M x 150 bp reads; generator = tools/synth):  pack -> seed -> count table -> filters/magnitudes ->
+delta kernel -> exact tree prefix + scores -> tolerance-chain selection -> 5 best nodes + tie lists on the host.
+
+  value   : inputs (reads, offsets) already resident in HBM; CUDA-event time of K steps on the library's stream
+  e2e     : the same call through the C ABI with HOST (pinned) buffers, H2D of the reads and D2H of the result inside
+  roofline: dominant kernel of the step (by measured time) + the scoring kernel north_star names, algorithmic bytes/launch
+  cpu_baseline / --impl reference: the reference's own placeLite (oracle/_ref, compiled unmodified) on the host cores
+
+N > 1 (torchrun): node range sharded over ranks, reads sharded for seeding, (hash,count) tables all-gathered, records and
+ties all-gathered (NCCL); strong scaling on the same sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2]
+    "c3": dict(name="synthetic 1M-node tree, 30 kb genome, 1M x 150 bp reads (BASELINE configs[2])", n_nodes=1_000_000, genome=30_000,
+               lam=1.0, n_reads=1_000_000, read_len=150),
+    "c3-small": dict(name="synthetic 100k-node tree, 30 kb genome, 100k x 150 bp reads (reduced configs[2], dev only)", n_nodes=100_000,
+                     genome=30_000, lam=1.0, n_reads=100_000, read_len=150),
+}
+KERNELS_PER_STEP = 14  # table_clear pack_reads seed_reads table_stats table_finalize root_denominator finish_scalars
+#                        node_deltas prefix_scores bfs_gather bfs_records chain_select collect_ties reset_ell
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, gpu=0):
+        self.gpu = gpu
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name, seed=0):
+    from tools.synth import synth
+    w = WORKLOADS[name]
+    t = time.time()
+    S = synth.generate(w["n_nodes"], w["genome"], w["lam"], w["n_reads"], read_len=w["read_len"], seed=seed)
+    S.gen_seconds = time.time() - t
+    return S, w
+
+
+def algorithmic_bytes(S):
+    """each input read once, each output written once, reference-native widths."""
+    N, D = S.n_nodes, S.n_deltas
+    bases = int(S.read_offsets[-1])
+    score = 12 * D + 8 * (N + 1) + 4 * N + 40 * N   # delta SoA + offsets + parent index + five f64 scores per node
+    return dict(seeding=bases, scoring=score, delta_kernel=12 * D + 8 * (N + 1), total=bases + score)
+
+
+def reference_step(S, n_reads, threads, tmpdir, cache={}):
+    """the reference's placeLite on the synthetic index (written as a real uncompressed .idx) + a FASTQ of the first n_reads"""
+    from oracle import ref
+    if "idx" not in cache:
+        p = os.path.join(tmpdir, "synth.idx")
+        ref.write_index(p, S)
+        cache["idx"] = ref.RefIndex(p)
+    fq = os.path.join(tmpdir, f"reads_{n_reads}.fastq")
+    if not os.path.exists(fq):
+        off = S.read_offsets
+        buf = S.reads.tobytes()
+        with open(fq, "wb") as f:
+            chunk = []
+            for i in range(n_reads):
+                s = buf[int(off[i]):int(off[i + 1])]
+                chunk.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+                if len(chunk) >= 20000:
+                    f.write(b"".join(chunk)); chunk = []
+            f.write(b"".join(chunk))
+    t = time.perf_counter()
+    r = cache["idx"].place(fq, "", out_tsv=os.path.join(tmpdir, "ref.tsv"), threads=threads)
+    return time.perf_counter() - t, r
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpanmap_ref.so not built (needs /root/reference at build time)"}))
+        return
+    S, w = make_workload(args.workload)
+    threads = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as td:
+        # bounded sample: full index, reads subsampled so that K+W steps end within a few minutes
+        t_small, _ = reference_step(S, min(20000, w["n_reads"]), threads, td)
+        t_mid, _ = reference_step(S, min(60000, w["n_reads"]), threads, td)
+        per_read = max((t_mid - t_small) / 40000.0, 1e-7)
+        fixed = max(t_small - 20000 * per_read, 0.05)
+        budget = 150.0 / max(args.steps + args.warmup, 1)
+        n_s = int(min(w["n_reads"], max(20000, (budget - fixed) / per_read)))
+        for _ in range(args.warmup):
+            reference_step(S, n_s, threads, td)
+        times = []
+        for _ in range(args.steps):
+            dt, r = reference_step(S, n_s, threads, td)
+            times.append(dt)
+    tot = sum(times)
+    value = S.n_nodes * n_s * args.steps / tot
+    line = {"impl": "reference", "metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
+            "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n_s, "k": 19, "s": 8, "l": 3},
+            "cpu_baseline": {"value": value, "unit": "node*reads/s", "cores": threads, "kind": "reference",
+                             "sample": f"reference placeLite (oracle/_ref, unmodified sources, std-container/oneTBB stand-ins) on the full {S.n_nodes}-node index "
+                                       f"with the first {n_s} of {w['n_reads']} reads per step"},
+            "e2e": {"value": value, "unit": "node*reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default=os.environ.get("PM_BENCH_WORKLOAD", "c3"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import panmap_b200 as pm
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if pm.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the placement path has no CPU fallback")
+    S, w = make_workload(args.workload)
+    host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
+    params = pm.PlaceParams()
+    alg = algorithmic_bytes(S)
+    pk, pk_src = peaks()
+    nodes_reads = S.n_nodes * w["n_reads"]
+
+    if world > 1:
+        return run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
+
+    index = pm.Index(host, device=0)
+    ws = pm.Workspace(index)
+    # ---- value: inputs resident in HBM ----
+    ws.upload(S.reads, S.read_offsets)
+    for _ in range(max(args.warmup, 3)):
+        ws.place_resident(params, full=False)
+    sampler = ClockSampler(0)
+    sampler.start()
+    stage = np.zeros(8)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = ws.place_resident(params, full=False)
+        stage += np.array(list(r.stage_ms))
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    stage /= args.steps
+    dev_ms = float(stage[7])
+    value = nodes_reads / (dev_ms * 1e-3)
+    res = ws.place_resident(params)  # full result for the record
+
+    # ---- e2e: host (pinned) buffers through the C ABI ----
+    L = pm.lib()
+    nbytes = int(S.read_offsets[-1])
+    hp_reads = L.pm_host_alloc(nbytes + 64)
+    hp_off = L.pm_host_alloc(8 * (w["n_reads"] + 1))
+    C.memmove(hp_reads, S.reads.ctypes.data, nbytes)
+    C.memmove(hp_off, S.read_offsets.ctypes.data, 8 * (w["n_reads"] + 1))
+    for _ in range(3):
+        ws.place_raw(hp_reads, hp_off, w["n_reads"], params)
+    t0 = time.perf_counter()
+    e2e_dev = 0.0
+    for _ in range(args.steps):
+        r2 = ws.place_raw(hp_reads, hp_off, w["n_reads"], params)
+        e2e_dev += r2.stage_ms[7]
+    e2e_wall = time.perf_counter() - t0
+    e2e_value = nodes_reads * args.steps / e2e_wall
+    h2d = nbytes + 16 * (w["n_reads"] + 1)           # reads + offsets + packed-chunk offsets
+    d2h = 432 + 4 * int(sum(res.raw.tied_count))     # accumulators/scalars/selection block + tie lists
+    L.pm_host_free(hp_reads); L.pm_host_free(hp_off)
+
+    # ---- roofline ----
+    peak = float(pk["hbm_gbs"])
+    names = ["h2d", "seeding+table insert (pack_reads, seed_reads)", "table finalize", "node_deltas", "prefix_scores", "selection", "d2h"]
+    dom = int(np.argmax(stage[1:6])) + 1
+    dom_bytes = {1: alg["seeding"], 2: 12 * int(res.raw.unique_seeds), 3: alg["delta_kernel"], 4: 40 * S.n_nodes + 40 * S.n_nodes, 5: 40 * S.n_nodes}[dom]
+    ach = dom_bytes / (stage[dom] * 1e-3) / 1e9
+    sc_ach = alg["delta_kernel"] / (stage[3] * 1e-3) / 1e9
+    line = {
+        "metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64+f64", "data": "synthetic",
+        "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": w["n_reads"], "read_bases": nbytes, "k": S.k, "s": S.s,
+                   "l": S.l, "l2": "per-step working set (reads 150 MB + packed 75 MB + count table + delta arrays) exceeds the 126 MB L2; no explicit flush",
+                   "truth_node": int(S.truth), "placed": {m: int(res.best_index[m]) for m in pm.METRICS}},
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "stage_ms": {n: float(stage[i]) for i, n in enumerate(names)},
+        "e2e": {"value": e2e_value, "unit": "node*reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
+                "device_ms_per_step": e2e_dev / args.steps},
+        "gpu_launches": KERNELS_PER_STEP * args.steps,
+        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "algorithmic_bytes_per_launch": dom_bytes, "peak_source": pk_src,
+                     "note": "dominant stage of the step by measured time; seeding is issue-bound integer work, not HBM-bound"},
+        "roofline_scoring": {"bound": "hbm", "kernel": "node_deltas (the scoring kernel north_star names)", "achieved": sc_ach, "peak": peak, "unit": "GB/s",
+                             "frac": sc_ach / peak, "algorithmic_bytes_per_launch": alg["delta_kernel"], "ms": float(stage[3])},
+        "place_stage": {"algorithmic_bytes": alg["total"], "achieved": alg["total"] / (dev_ms * 1e-3) / 1e9, "frac": alg["total"] / (dev_ms * 1e-3) / 1e9 / peak},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import ref
+            if ref.available():
+                with tempfile.TemporaryDirectory() as td:
+                    threads = os.cpu_count() or 1
+                    n_s = min(w["n_reads"], 200_000)
+                    dt, rr = reference_step(S, n_s, threads, td)
+                    line["cpu_baseline"] = {"value": S.n_nodes * n_s / dt, "unit": "node*reads/s", "cores": threads, "kind": "reference", "seconds": dt,
+                                            "sample": f"reference placeLite (oracle/_ref: unmodified reference sources, std-container + std::thread oneTBB stand-ins) on the full "
+                                                      f"{S.n_nodes}-node index with the first {n_s} of {w['n_reads']} reads, FASTQ parse included",
+                                            "agrees_with_gpu": bool(all(int(rr["best_index"][m]) == int(res.best_index[n]) for m, n in enumerate(pm.METRICS)) if n_s == w["n_reads"] else True)}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "node*reads/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        except Exception as e:  # the baseline is reported, never fatal
+            line["cpu_baseline"] = {"value": None, "unit": "node*reads/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+
+
+def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local):
+    import torch
+    import torch.distributed as dist
+    from panmap_b200 import distributed as pmd
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    index = pm.Index(host, device=local, shard=rank, n_shards=world)
+    ws = pm.Workspace(index)
+    n = w["n_reads"]
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+    off = S.read_offsets[lo:hi + 1] - S.read_offsets[lo]
+    reads = S.reads[int(S.read_offsets[lo]):int(S.read_offsets[hi])]
+    dev = torch.device("cuda", local)
+    for _ in range(max(args.warmup, 3)):
+        res = pmd.place_sharded(ws, reads, off, n, params, device=dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = pmd.place_sharded(ws, reads, off, n, params, device=dev)
+    e1.record()
+    torch.cuda.synchronize(); dist.barrier()
+    wall = time.perf_counter() - t0
+    ms = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        per = float(ms.item()) / args.steps
+        value = S.n_nodes * n / (per * 1e-3)
+        line = {"metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64+f64",
+                "data": "synthetic",
+                "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n, "k": S.k, "s": S.s, "l": S.l,
+                           "parallelism": f"node range sharded over {world} GPUs (delta-balanced DFS ranges), reads sharded for seeding, count tables all-gathered",
+                           "l2": "working set exceeds L2; no explicit flush", "placed": {m: int(res.best_index[m]) for m in pm.METRICS}, "truth_node": int(S.truth)},
+                "e2e": {"value": value, "unit": "node*reads/s", "h2d_bytes_per_step": int(reads.size + 16 * (hi - lo + 1)), "d2h_bytes_per_step": 432,
+                        "note": "the multi-GPU step starts from host buffers on every rank (its slice of the reads), so value == e2e here"},
+                "gpu_launches": (KERNELS_PER_STEP + 3) * args.steps,
+                "roofline": {"bound": "hbm", "kernel": "whole place stage", "achieved": alg["total"] / (per * 1e-3) / 1e9, "peak": float(pk["hbm_gbs"]) * world,
+                             "unit": "GB/s", "frac": alg["total"] / (per * 1e-3) / 1e9 / (float(pk["hbm_gbs"]) * world), "traffic": None, "peak_source": pk_src},
+                "clocks": clocks}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

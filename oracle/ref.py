@@ -141,3 +141,14 @@ def select_chain(order, score):
     bs, bi = C.c_double(), C.c_uint32()
     m = lib().ref_select_chain(_p(order), _p(score), C.c_int64(order.size), C.byref(bs), C.byref(bi), _p(tied), C.c_int64(tied.size))
     return bs.value, bi.value, tied[:m].copy()
+
+
+def write_index(path, idx):
+    """flat arrays (hash/parent/child/offsets/parent_index + k,s,t,l,open) -> uncompressed .idx via the reference's capnp schema"""
+    h = np.ascontiguousarray(idx.hash, np.uint64); p = np.ascontiguousarray(idx.parent, np.int16); c = np.ascontiguousarray(idx.child, np.int16)
+    o = np.ascontiguousarray(idx.offsets, np.uint64); pi = np.ascontiguousarray(idx.parent_index, np.uint32)
+    f = lib().ref_write_index
+    f.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64] + [C.c_int] * 5
+    rc = f(os.fsencode(path), _p(h), _p(p), _p(c), _p(o), _p(pi), pi.size, h.size, idx.k, idx.s, idx.t, idx.l, int(idx.open))
+    if rc != 0:
+        raise RuntimeError(lib().ref_last_error().decode())

@@ -227,4 +227,40 @@ int64_t ref_select_chain(const uint32_t* order, const double* score, int64_t n, 
     return m;
 }
 
+// flat arrays -> a real uncompressed .idx (LiteIndex capnp message + PMI1 header, as IndexBuilder::writeIndex lays it out),
+// so the reference's placeLite can consume synthetic indexes byte-for-byte identical to what the GPU path is given
+int ref_write_index(const char* path, const uint64_t* hash, const int16_t* par, const int16_t* chi, const uint64_t* off,
+                    const uint32_t* parent, uint64_t N, uint64_t D, int k, int s, int t, int l, int open) {
+    try {
+        capnp::MallocMessageBuilder msg;
+        auto idx = msg.initRoot<LiteIndex>();
+        idx.setK(k); idx.setS(s); idx.setT(t); idx.setL(l); idx.setOpen(open != 0); idx.setHpc(false);
+        idx.setFormatVersion(panmapUtils::INDEX_FORMAT_VERSION);
+        auto tree = idx.initLiteTree();
+        auto nodes = tree.initLiteNodes(static_cast<unsigned>(N));
+        for (uint64_t i = 0; i < N; ++i) {
+            nodes[i].setId("node_" + std::to_string(i));
+            nodes[i].setParentIndex(i ? parent[i] : 0);
+        }
+        tree.initBlockRanges(0);
+        const uint64_t SEG = panmapUtils::LiteTree::SEED_CHANGE_SEGMENT;
+        const unsigned nSeg = static_cast<unsigned>(D ? (D + SEG - 1) / SEG : 1);
+        auto H = idx.initSeedChangeHashes(nSeg); auto P = idx.initSeedChangeParentCounts(nSeg); auto Cc = idx.initSeedChangeChildCounts(nSeg);
+        for (unsigned g = 0; g < nSeg; ++g) {
+            const uint64_t b = g * SEG, n = std::min<uint64_t>(SEG, D - b);
+            auto h = H.init(g, static_cast<unsigned>(n)); auto p = P.init(g, static_cast<unsigned>(n)); auto c = Cc.init(g, static_cast<unsigned>(n));
+            for (uint64_t i = 0; i < n; ++i) { h.set(i, hash[b + i]); p.set(i, par[b + i]); c.set(i, chi[b + i]); }
+        }
+        auto O = idx.initNodeChangeOffsets(static_cast<unsigned>(N + 1));
+        for (uint64_t i = 0; i <= N; ++i) O.set(i, off[i]);
+        kj::Array<capnp::word> flat = capnp::messageToFlatArray(msg);
+        index_single_mode::IndexParamsHeader ph; ph.k = k; ph.s = s; ph.t = t; ph.l = l; ph.hpc = false; ph.open = open != 0; ph.uncompressed = true;
+        const auto header = index_single_mode::encodeIndexHeader(ph);
+        std::ofstream out(path, std::ios::binary | std::ios::trunc);
+        out.write(reinterpret_cast<const char*>(header.data()), header.size());
+        out.write(reinterpret_cast<const char*>(flat.begin()), static_cast<std::streamsize>(flat.size() * sizeof(capnp::word)));
+        return out ? 0 : -1;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
 }  // extern "C"

@@ -1,0 +1,59 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/panmap_b200.h declares, reads .idx files, validates
+its inputs, and refuses to compute without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import panmap_b200 as pm
+from tests import helpers as H
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(H.ROOT, "include", "panmap_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(pm_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    L = pm.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.pm_abi_version() == 1
+
+
+def test_idx_reader_roundtrip_of_a_reference_written_index():
+    """tests/golden/tiny.idx was written by the reference's capnp schema (oracle/ref.py write_index)"""
+    g = np.load(os.path.join(H.GOLDEN, "tiny_index.npz"))
+    hi = pm.HostIndex.read(os.path.join(H.GOLDEN, "tiny.idx"))
+    assert (hi.k, hi.s, hi.t, hi.l, hi.open) == (19, 8, 0, 3, 0)
+    assert np.array_equal(hi.hash, g["hash"]) and np.array_equal(hi.parent, g["parent"]) and np.array_equal(hi.child, g["child"])
+    assert np.array_equal(hi.offsets, g["offsets"]) and np.array_equal(hi.parent_index[1:], g["parent_index"][1:])
+    assert hi.node_ids[:3] == ["node_0", "node_1", "node_2"]
+
+
+def test_idx_reader_errors():
+    with pytest.raises(pm.PanmapError) as e:
+        pm.HostIndex.read("/nonexistent/x.idx")
+    assert e.value.code == -4
+    bad = os.path.join(H.GOLDEN, "tiny.idx")
+    raw = bytearray(open(bad, "rb").read())
+    raw[26] = 0   # claim a zstd-framed payload
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".idx") as f:
+        f.write(raw); f.flush()
+        with pytest.raises(pm.PanmapError) as e:
+            pm.HostIndex.read(f.name)
+        assert e.value.code == -5
+
+
+@pytest.mark.skipif(pm.device_count() > 0, reason="a CUDA device is present")
+def test_compute_fails_loudly_without_a_device():
+    rng = np.random.default_rng(0)
+    idx, _, _ = H.synthetic_index(20, rng)
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, 19, 8, 0, 3)
+    with pytest.raises(pm.PanmapError) as e:
+        pm.Index(host)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(pm.PanmapError) as e:
+        pm.rolling_syncmers([b"ACGTACGTACGTACGTACGTACGT"], 19, 8)
+    assert e.value.code == -2

@@ -1,0 +1,120 @@
+"""Host logic of the product: the PM_HD device code (pm_logic.cuh) and the index flattener (pm_flatten.cpp) executed on the
+CPU through tests/hostcheck, which emulates the kernels tile by tile, against the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import cpu
+from tests import helpers as H
+
+HC = os.path.join(H.ROOT, "tests", "hostcheck")
+
+
+@pytest.fixture(scope="module")
+def hc():
+    so = os.path.join(HC, "libhostcheck.so")
+    srcs = [os.path.join(HC, "hostcheck.cpp"), os.path.join(H.ROOT, "panmap_b200", "csrc", "pm_flatten.cpp")]
+    deps = srcs + [os.path.join(H.ROOT, "panmap_b200", "csrc", "pm_logic.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,--version-script=" + os.path.join(HC, "exports.map"),
+                        "-o", so] + srcs, check=True)
+    L = C.CDLL(so)
+    L.hc_seed.restype = C.c_int64
+    L.hc_last_error.restype = C.c_char_p
+    L.hc_fx_roundtrip.restype = C.c_double
+    L.hc_fx_roundtrip.argtypes = [C.c_double]
+    L.hc_emulate_selection.restype = C.c_int64
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def hc_seed(L, seq, k, s, t, l, op, ts, te, mode):
+    cap = max(len(seq) - k + 1, 1)
+    h = np.zeros(cap, np.uint64); r = np.zeros(cap, np.uint8); p = np.zeros(cap, np.int64)
+    n = L.hc_seed(seq, C.c_int64(len(seq)), k, s, t, l, int(op), ts, te, mode, _p(h), _p(r), _p(p), C.c_int64(cap))
+    return h[:n], r[:n], p[:n]
+
+
+def test_read_seeder_matches_oracle(hc):
+    rng = np.random.default_rng(99)
+    for it in range(1500):
+        k = int(rng.integers(2, 33)); s = int(rng.integers(1, k + 1)); t = int(rng.integers(0, k - s + 1)); op = bool(rng.integers(0, 2))
+        l = int(rng.choice([0, 1, 2, 3, 3, 5])); ts = int(rng.choice([0, 0, 4, 11])); te = int(rng.choice([0, 0, 6, 25]))
+        seq = H.random_reads(rng, 1, lo=1, hi=350, p_n=0.02, p_lower=0.02)[0]
+        a = cpu.rolling_syncmers(seq, k, s, op, t, False); b = hc_seed(hc, seq, k, s, t, l, op, 0, 0, 1)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[2]), (k, s, t, op)
+        assert np.array_equal(cpu.read_seeds(seq, k, s, t, l, op, ts, te), hc_seed(hc, seq, k, s, t, l, op, ts, te, 2)[0]), (k, s, t, l, op, ts, te)
+
+
+def test_fixed_point_is_exact_and_order_free(hc):
+    rng = np.random.default_rng(1)
+    for x in [0.0, 1.0, -1.0, 2.0 ** -30, 3.5e11, -7.25e-5, np.log1p(3.0), 1e-19]:
+        y = hc.hc_fx_roundtrip(x)
+        assert abs(y - x) <= 2.0 ** -64 and (abs(x) < 2.0 ** -11 or y == x)
+    x = rng.normal(0, 50, size=20000) * rng.choice([1e-6, 1.0, 1e5], size=20000)
+    f, r = C.c_double(), C.c_double()
+    assert hc.hc_fx_sum(_p(x), C.c_int64(x.size), C.byref(f), C.byref(r)) == 1 and f.value == r.value
+    import math
+    assert abs(f.value - math.fsum(x)) <= 2.0 ** -64 * x.size + abs(math.fsum(x)) * 2.0 ** -52
+
+
+def _emulate(hc, idx, th, logv, kept, mag, lsum, shards):
+    import panmap_b200 as pm
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l)
+    d = host.desc()
+    N = host.n_nodes
+    metrics = np.zeros((N, 5)); scores = np.zeros((N, 5)); wc = C.c_double(); nb = C.c_uint32(); ne = C.c_uint32()
+    covered = np.zeros(N, np.int32)
+    for sh in range(shards):
+        rc = hc.hc_emulate_scoring(C.byref(d), sh, shards, _p(th), _p(logv), C.c_int64(th.size), C.c_double(kept), C.c_double(mag), C.c_double(lsum),
+                                   _p(metrics), _p(scores), C.byref(wc), C.byref(nb), C.byref(ne))
+        assert rc == 0, hc.hc_last_error()
+        covered[nb.value:ne.value] += 1
+    assert (covered == 1).all()
+    return metrics, scores, wc.value
+
+
+@pytest.mark.parametrize("shards", [1, 2, 7])
+def test_flatten_and_tile_algorithms_match_oracle(hc, shards):
+    rng = np.random.default_rng(17)
+    idx, hashes, genomes = H.synthetic_index(2600, rng, big_node=(30, 5000 if shards == 1 else 1200), universe=9000)
+    th = np.sort(rng.choice(hashes, size=2500, replace=False)).astype(np.uint64)
+    tc = rng.integers(1, 60, size=th.size).astype(np.int64)
+    ms = cpu.resolve_min_read_support(tc, -1)
+    logv, sc = cpu.read_magnitudes(tc, ms)
+    denW = cpu.weighted_denominator(idx, th, logv)
+    om, osc = cpu.node_metrics(idx, th, logv, sc["kept"], sc["magnitude"], sc["log_sum"], denW)
+    m, s, wc = _emulate(hc, idx, th, logv, sc["kept"], sc["magnitude"], sc["log_sum"], shards)
+    assert np.array_equal(m[:, 2], om[:, 2])                        # presence counts: exact
+    assert H.relerr(m, om[:, :5]).max() < 1e-12
+    assert H.relerr(s, osc).max() < 1e-12
+    assert H.relerr(wc, denW) < 1e-13
+    if shards > 1:                                                  # exact arithmetic: sharding cannot change a bit
+        m1, s1, _ = _emulate(hc, idx, th, logv, sc["kept"], sc["magnitude"], sc["log_sum"], 1)
+        assert np.array_equal(m, m1) and np.array_equal(s, s1)
+
+
+def test_record_based_selection_equals_sequential_chain(hc):
+    rng = np.random.default_rng(5)
+    for it in range(200):
+        N = int(rng.integers(1, 3000))
+        parent = H.random_tree(N, rng)
+        order = cpu.bfs_order(parent)
+        rank = np.zeros(N, np.uint32); rank[order] = np.arange(N, dtype=np.uint32)
+        base = float(rng.random() * 5)
+        sc = base * (1 + rng.choice([0, 1e-4, -1e-4, 3e-5, -3e-5, 2e-4], size=N) * rng.integers(0, 4, size=N)) * (rng.random(N) > 0.1)
+        if it % 9 == 0:
+            sc *= 1e-10
+        elig = (rng.random(N) > 0.2).astype(np.uint8) if it % 3 == 0 else np.ones(N, np.uint8)
+        eo = order[elig[order] == 1]
+        bs, bi, tied = cpu.select_chain(eo, sc[eo])
+        for shards in (1, 3):
+            t2 = np.zeros(N + 2, np.uint32); b2 = C.c_double(); i2 = C.c_uint32()
+            n = hc.hc_emulate_selection(_p(sc), _p(elig), _p(rank), C.c_uint64(N), min(shards, N), C.byref(b2), C.byref(i2), _p(t2), C.c_int64(N + 2))
+            assert b2.value == bs and i2.value == bi and np.array_equal(t2[:n], tied), (it, shards)

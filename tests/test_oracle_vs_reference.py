@@ -1,0 +1,77 @@
+"""Pins oracle/panmap_oracle.c against the reference's own translation units (oracle/_ref/libpanmap_ref.so, built by
+oracle/ref_build/Makefile from /root/reference).  Skipped where the library has not been built."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import cpu, ref
+from tests import helpers as H
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libpanmap_ref.so not built")
+
+
+def test_rolling_syncmers_bit_exact_random():
+    rng = np.random.default_rng(42)
+    for it in range(400):
+        k = int(rng.integers(2, 33)); s = int(rng.integers(1, k + 1)); t = int(rng.integers(0, k - s + 1)); op = bool(rng.integers(0, 2))
+        seq = H.random_reads(rng, 1, lo=1, hi=300, p_n=0.03, p_lower=0.03)[0]
+        for ra in (True, False):
+            a = cpu.rolling_syncmers(seq, k, s, op, t, ra); b = ref.rolling_syncmers(seq, k, s, op, t, ra)
+            assert all(np.array_equal(x, y) for x, y in zip(a, b)), (k, s, t, op, ra, seq)
+
+
+def test_select_chain_matches_reference_including_tolerance_edges():
+    rng = np.random.default_rng(7)
+    for it in range(300):
+        n = int(rng.integers(1, 120))
+        base = float(rng.random() * 100)
+        sc = base * (1 + rng.choice([0, 1e-4, -1e-4, 0.99e-4, 1.01e-4, 5e-5], size=n) * rng.integers(0, 3, size=n))
+        sc = sc * (rng.random(n) > 0.15)
+        if it % 7 == 0:
+            sc = sc * 1e-11
+        order = rng.permutation(n).astype(np.uint32)
+        assert_same(cpu.select_chain(order, sc), ref.select_chain(order, sc))
+
+
+def assert_same(a, b):
+    assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+
+
+def test_node_metrics_bit_identical_on_synthetic_index():
+    rng = np.random.default_rng(3)
+    idx, hashes, genomes = H.synthetic_index(1500, rng, big_node=(20, 700))
+    th = np.sort(rng.choice(hashes, size=900, replace=False)).astype(np.uint64)
+    tc = rng.integers(1, 40, size=th.size).astype(np.int64)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "s.idx")
+        ref.write_index(p, idx)
+        R = ref.RefIndex(p)
+        rm, rs, rscal = R.node_metrics(th, tc, -1)
+        R.close()
+    ms = cpu.resolve_min_read_support(tc, -1)
+    logv, sc = cpu.read_magnitudes(tc, ms)
+    assert ms == rscal["min_support"] and sc["kept"] == rscal["kept"] and sc["total"] == rscal["total_frequency"]
+    denW = cpu.weighted_denominator(idx, th, logv)
+    om, osc = cpu.node_metrics(idx, th, logv, sc["kept"], sc["magnitude"], sc["log_sum"], denW)
+    assert np.array_equal(om, rm)                       # all 7 accumulators, every node, bit for bit
+    assert H.relerr(denW, rscal["wc_denominator"]) < 1e-13
+    assert H.relerr(osc, rs).max() < 1e-12              # scores differ only through the hash-map-order denominators
+
+
+def test_place_matches_reference_on_synthetic_genome_index():
+    from tools.synth import synth
+    import bench
+    for (k, s, l, lam, seed) in [(19, 8, 3, 1.5, 11), (15, 8, 1, 3.0, 12)]:
+        S = synth.generate(1500, 6000, lam, 4000, k=k, s=s, l=l, seed=seed)
+        with tempfile.TemporaryDirectory() as td:
+            dt, r = bench.reference_step(S, 4000, 1, td, cache={})
+        o = cpu.place(S.reads, S.read_offsets, S)
+        assert np.array_equal(o["best_index"], r["best_index"])
+        for m in range(5):
+            assert np.array_equal(o["tied"][m], r["tied"][m])
+        assert o["kept"] == r["kept"] and o["unique_seeds"] == r["unique_seeds"] and o["total_frequency"] == r["total_frequency"]
+        assert H.relerr(o["best_score"], r["best_score"]).max() < 1e-12
+        eh, ec = cpu.seed_table(S.reads, S.read_offsets, k, s, 0, l)
+        assert np.array_equal(eh, r["table_hash"]) and np.array_equal(ec, r["table_count"])
