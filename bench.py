@@ -35,7 +35,7 @@ WORKLOADS = {
     "c3-small": dict(name="synthetic 100k-node tree, 30 kb genome, 100k x 150 bp reads (reduced configs[2], dev only)", n_nodes=100_000,
                      genome=30_000, lam=1.0, n_reads=100_000, read_len=150),
 }
-KERNELS_PER_STEP = 14  # table_clear pack_reads seed_reads table_stats table_finalize root_denominator finish_scalars
+KERNELS_PER_STEP = 15  # table_clear pack_reads syncmers_fast seeds_from_syncmers table_stats table_finalize root_denominator finish_scalars
 #                        node_deltas prefix_scores bfs_gather bfs_records chain_select collect_ties reset_ell
 
 

@@ -101,6 +101,7 @@ struct pm_workspace {
     u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
     // table
     DevBuf<u64> keys; DevBuf<u32> counts; u64 tableCap = 0;
+    DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
     DevBuf<double> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist;
     DevBuf<NodeDelta> delta, bigPartial; DevBuf<unsigned> bigDone;
@@ -197,6 +198,7 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
 void refreshView(pm_workspace* W) {
     WorkspaceView& V = W->view;
     V.keys = W->keys.p; V.counts = W->counts.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
+    V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
     V.acc = W->acc.p; V.ell = W->ell.p; V.touched = W->touched.p; V.touchedCap = (u32)W->touched.n; V.countHist = W->countHist.p;
     V.delta = W->delta.p; V.bigPartial = W->bigPartial.p; V.bigDone = W->bigDone.p; V.chainA = W->chainA.p;
     V.scores = W->scores.p; V.metrics = W->wantMetrics ? W->metrics.p : nullptr; V.blockMax = W->blockMaxAndBfs.p;
@@ -246,6 +248,7 @@ void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n)
     const u64 total = n ? off[n] - base0 : 0;
     hostPackedOffsets(W, off, n, I->F.sp.k);
     W->nReads = n; W->totalBases = total;
+    W->synBuf.ensure(W->nChunks * 32 + 32); W->synCount.ensure(n + 1);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1); W->packed.ensure(W->nChunks + 1);
     if (base0 != 0) throw std::runtime_error("read_offsets[0] must be 0");
     if (total) CK(cudaMemcpyAsync(W->reads.p, reads, total, cudaMemcpyHostToDevice, W->st));
@@ -572,19 +575,19 @@ static int seedListImpl(int device, const char* seqs, const uint64_t* off, uint6
         pOff[n] = ch; wOff[n] = win;
         const u64 total = n ? off[n] : 0;
         DevBuf<char> dReads; DevBuf<u64> dOff, dPOff, dWOff, dHash, dCount; DevBuf<uint4> dPacked;
-        DevBuf<unsigned char> dRev; DevBuf<long long> dPos; DevBuf<SeedTables> dT;
+        DevBuf<unsigned char> dRev; DevBuf<long long> dPos; DevBuf<SeedTables> dT; DevBuf<u64> dSyn; DevBuf<unsigned> dSynCount;
         dReads.alloc(total + 64); dOff.alloc(n + 1); dPOff.alloc(n + 1); dWOff.alloc(n + 1); dPacked.alloc(ch + 1);
         dHash.alloc(win + 1); dCount.alloc(n + 1);
-        if (mode == 1) { dRev.alloc(win + 1); dPos.alloc(win + 1); }
+        if (mode == 1) { dRev.alloc(win + 1); dPos.alloc(win + 1); } else { dSyn.alloc(ch * 32 + 32); dSynCount.alloc(n + 1); }
         if (total) CK(cudaMemcpyAsync(dReads.p, seqs, total, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dOff.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dPOff.p, pOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dWOff.p, wOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
         std::vector<SeedTables> T(1); buildSeedTables(T[0], sp->k, sp->s);
         dT.alloc(1); CK(cudaMemcpyAsync(dT.p, T.data(), sizeof(SeedTables), cudaMemcpyHostToDevice, st));
-        const SeederParams P = makeSeederParams(sp->k, sp->s, sp->t, mode == 1 ? 1 : sp->l, sp->open, trimStart, trimEnd);
+        const SeederParams P = makeSeederParams(sp->k, sp->s, sp->t, sp->l, sp->open, trimStart, trimEnd);
         launchPackReads(dReads.p, dOff.p, dPOff.p, n, ch, dPacked.p, st);
-        launchSeedList(dPacked.p, dOff.p, dPOff.p, dWOff.p, n, P, dT.p, mode, dHash.p, dRev.p, dPos.p, dCount.p, st);
+        launchSeedList(dPacked.p, dOff.p, dPOff.p, dWOff.p, n, P, dT.p, mode, dSyn.p, dSynCount.p, dHash.p, dRev.p, dPos.p, dCount.p, st);
         CK(cudaGetLastError());
         if (win) CK(cudaMemcpyAsync(outHash, dHash.p, win * 8, cudaMemcpyDeviceToHost, st));
         if (mode == 1 && win) {

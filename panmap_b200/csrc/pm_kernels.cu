@@ -101,17 +101,24 @@ __device__ __forceinline__ void tableInsert(u64* __restrict__ keys, u32* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------
-// seed_reads: one lane per read, all lanes of a warp at the same read position (lock-step), so the
-// block-end pass of the sliding minimum is convergent.  MODE 0: count table; 1: syncmer list; 2: seed list.
+// Seeding = two kernels, mirroring the reference's own split:
+//   syncmers_*          seeding::rollingSyncmers (seeding.cpp:47-229): one lane per read, all lanes of a warp at the same
+//                       read position (lock-step, so the block-end pass of the sliding minimum is convergent); each lane
+//                       appends the canonical hashes of its read's syncmers (trim filter applied) to the read's own
+//                       region of synBuf.  No table traffic, no warp collectives in the hot loop.
+//   seeds_from_syncmers placement.cpp:1598-1686: one warp per read, lanes over consecutive syncmers; k-min-mers in closed
+//                       form, then the open-addressing count table (latency-bound probes, hidden by full occupancy).
+// A read's syncmer region starts at slot 32 * packedOff[r] (its packed chunks cover >= len slots).
 // ------------------------------------------------------------------------------------------------------
 constexpr int kSeedThreads = 128;
 
+// generic (any k <= 32, s, t, open/closed).  MODE 0: hashes -> synBuf (+ count); MODE 1: (hash, isReverse, pos) lists.
 template <int MODE>
-__global__ void __launch_bounds__(kSeedThreads) seed_reads(const uint4* __restrict__ packed, const u64* __restrict__ off,
-                                                           const u64* __restrict__ packedOff, const u64* __restrict__ winOff,
-                                                           u64 nReads, SeederParams P, const SeedTables* __restrict__ gT,
-                                                           u64* keys, u32* counts, u64 mask, SampleAcc* acc,
-                                                           u64* outHash, unsigned char* outRev, long long* outPos, u64* outCount) {
+__global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __restrict__ packed, const u64* __restrict__ off,
+                                                                 const u64* __restrict__ packedOff, const u64* __restrict__ winOff,
+                                                                 u64 nReads, SeederParams P, const SeedTables* __restrict__ gT,
+                                                                 u64* __restrict__ synBuf, unsigned* __restrict__ synCount,
+                                                                 u64* outHash, unsigned char* outRev, long long* outPos, u64* outCount) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
     u64* rings = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables));
@@ -119,79 +126,264 @@ __global__ void __launch_bounds__(kSeedThreads) seed_reads(const uint4* __restri
         reinterpret_cast<u64*>(sT)[i] = reinterpret_cast<const u64*>(gT)[i];
     __syncthreads();
     const SeedTables& T = *sT;
-
-    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < nReads; r += (u64)gridDim.x * blockDim.x) {
-        const u64 b = off[r];
-        const int L = (int)(off[r + 1] - b);
-        const u64 pOff = packedOff[r];
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    const u64 warpId = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (u64 r0 = warpId * 32; r0 < nReads; r0 += warpsTotal * 32) {
+        const u64 r = r0 + lane;
+        const bool valid = r < nReads;
+        const u64 b = valid ? off[r] : 0;
+        int L = valid ? (int)(off[r + 1] - b) : 0;
+        if (L < P.k) L = 0;  // shorter than k: no windows (seeding.cpp:50)
+        const u64 pOff = valid ? packedOff[r] : 0;
         const int nCh = (L + 31) >> 5;
-        ReadSeeder sd;
-        sd.reset(rings + threadIdx.x, blockDim.x);
-        u64 cnt = 0;
-        const u64 wbase = (MODE != 0) ? winOff[r] : 0;
-        if (L >= P.k) {
-            for (int c = 0; c < nCh; ++c) {
-                const uint4 v = packed[pOff + c];
-                const unsigned wv[4] = {v.x, v.y, v.z, v.w};
+        int maxL = L;
 #pragma unroll
-                for (int wi = 0; wi < 4; ++wi) {
-                    const unsigned word = wv[wi];
-#pragma unroll
-                    for (int bi = 0; bi < 8; ++bi) {
-                        const int i = c * 32 + wi * 8 + bi;
-                        if (i < L) {
-                            const unsigned code = (word >> (4 * bi)) & 0xFu;
-                            u64 h; bool rev;
-                            if (sd.pushBase(i, code, T, P, h, rev)) {
-                                const int pos = i - P.k + 1;
-                                if (MODE == 1) {
-                                    outHash[wbase + cnt] = h; outRev[wbase + cnt] = rev ? 1 : 0; outPos[wbase + cnt] = pos; ++cnt;
-                                } else {
-                                    u64 seed;
-                                    if (sd.pushSyncmer(pos, L, h, P, seed)) {
-                                        if (MODE == 0) tableInsert(keys, counts, mask, seed, 1u, acc);
-                                        else { outHash[wbase + cnt] = seed; ++cnt; }
-                                    }
-                                }
-                            }
+        for (int d = 16; d > 0; d >>= 1) maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, d));
+        const int nChMax = (maxL + 31) >> 5;
+        const int validEnd = L - P.trimEnd - P.k;
+        ReadSeederT<kSeedThreads> sd;
+        sd.reset(rings + threadIdx.x, P.w);
+        unsigned cnt = 0;
+        const u64 obase = MODE == 0 ? pOff * 32 : (valid ? winOff[r] : 0);
+#pragma unroll 1
+        for (int c = 0; c < nChMax; ++c) {
+            uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            if (c < nCh) v = packed[pOff + c];
+#pragma unroll 1
+            for (int wi = 0; wi < 4; ++wi) {
+                const unsigned word = wi == 0 ? v.x : wi == 1 ? v.y : wi == 2 ? v.z : v.w;
+                if (c * 32 + wi * 8 >= maxL) break;
+#pragma unroll 2
+                for (int bi = 0; bi < 8; ++bi) {
+                    const int i = c * 32 + wi * 8 + bi;
+                    if (i < L) {
+                        const unsigned code = (word >> (4 * bi)) & 0xFu;
+                        u64 h; bool rev;
+                        if (sd.pushBase(i, code, T, P, h, rev)) {
+                            const int pos = i - P.k + 1;
+                            if (MODE == 1) { outHash[obase + cnt] = h; outRev[obase + cnt] = rev ? 1 : 0; outPos[obase + cnt] = pos; ++cnt; }
+                            else if (pos >= P.trimStart && pos <= validEnd) { synBuf[obase + cnt] = h; ++cnt; }
                         }
                     }
                 }
             }
         }
-        if (MODE != 0) outCount[r] = cnt;
+        if (valid) { if (MODE == 0) synCount[r] = cnt; else outCount[r] = cnt; }
     }
 }
 
-static size_t seedSmemBytes(const SeederParams& P) {
-    return sizeof(SeedTables) + (size_t)seederRingWords(P.k, P.s, P.l) * kSeedThreads * sizeof(u64);
+// Closed syncmers with t == 0 (panmap's default) and compile-time (k, s): the main loop is unrolled over one block of
+// W = k-s+1 s-mers so that the ring slot is a compile-time constant -- ring addresses are immediates and the block-start /
+// block-end cases and the window geometry are resolved statically.  With t == 0 the closed-syncmer test only asks whether
+// the OLDEST or the NEWEST s-mer of the window attains the window minimum:
+//   newest: fs == min(window)                    (fs is in a register)
+//   oldest: F[p] == min(window)  <=>  F[p] is the suffix minimum of its block tail (one bit per slot, produced by the
+//           block-end pass) and that suffix minimum is <= the running minimum of the current block
+// so the ring keeps only the in-place suffix minima (2*W words per lane instead of 4*W) plus two W-bit masks.
+template <int K, int S>
+__global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
+                                                              const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
+                                                              const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
+                                                              unsigned* __restrict__ synCount) {
+    constexpr int W = K - S + 1;
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
+    u64* rings = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables));
+    for (int i = threadIdx.x; i < (int)(sizeof(SeedTables) / 8); i += blockDim.x)
+        reinterpret_cast<u64*>(sT)[i] = reinterpret_cast<const u64*>(gT)[i];
+    __syncthreads();
+    const SeedTables& T = *sT;
+    u64* const rF = rings + threadIdx.x;                       // F / suffix-min ring, slot j at rF[j * kSeedThreads]
+    u64* const rR = rings + (size_t)W * kSeedThreads + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    const u64 warpId = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (u64 r0 = warpId * 32; r0 < nReads; r0 += warpsTotal * 32) {
+        const u64 r = r0 + lane;
+        const bool valid = r < nReads;
+        const u64 b = valid ? off[r] : 0;
+        int L = valid ? (int)(off[r + 1] - b) : 0;
+        if (L < K) L = 0;
+        const u64 pOff = valid ? packedOff[r] : 0;
+        const uint4* __restrict__ src = packed + pOff;
+        u64* __restrict__ dst = synBuf + pOff * 32;
+        int maxL = L;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, d));
+        const int validEnd = L - P.trimEnd - K;
+        const int trimStart = P.trimStart;
+
+        u64 fk = 0, rk = 0, fs = 0, rs = 0, hist2 = 0, preF = kEmptyKey, preR = kEmptyKey, firstF = 0, firstR = 0;
+        unsigned histAmb = 0xFFFFFFFFu, maskF = 0, maskR = 0, word = 0, cnt = 0;
+        uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        int lastAmb = -1;
+
+        auto fetch = [&](int i) -> unsigned {   // 4-bit code of base i; i advances by one per call
+            if ((i & 7) == 0) {
+                if ((i & 31) == 0) { if (i < L) v = src[i >> 5]; }
+                word = v.x; v.x = v.y; v.y = v.z; v.z = v.w;
+            }
+            const unsigned c = word & 0xFu;
+            word >>= 4;
+            return c;
+        };
+        auto roll = [&](int i, unsigned code) {
+            const unsigned oldK = (unsigned)((hist2 >> (2 * (K - 1))) & 3ULL) | (((histAmb >> (K - 1)) & 1u) << 2);
+            const unsigned oldS = (unsigned)((hist2 >> (2 * (S - 1))) & 3ULL) | (((histAmb >> (S - 1)) & 1u) << 2);
+            const unsigned tc = code & 7u;
+            fk = rol1(fk) ^ T.fwdOldK[oldK] ^ T.fwdNew[tc];
+            rk = ror1(rk) ^ T.revOld[oldK] ^ T.revNewK[tc];
+            fs = rol1(fs) ^ T.fwdOldS[oldS] ^ T.fwdNew[tc];
+            rs = ror1(rs) ^ T.revOld[oldS] ^ T.revNewS[tc];
+            hist2 = (hist2 << 2) | (u64)(code & 3u);
+            histAmb = (histAmb << 1) | (code >= 4 ? 1u : 0u);
+            if (code >= 4) lastAmb = i;
+        };
+        // prologue: the first S-1 bases only feed the rolling hashes
+#pragma unroll 1
+        for (int i = 0; i < S - 1 && i < maxL; ++i) {
+            const unsigned code = fetch(i);
+            if (i < L) roll(i, code);
+        }
+        // main loop: one block of W s-mers per iteration; s-mer index q = i - (S-1), slot j = q mod W
+#pragma unroll 1
+        for (int q0 = 0; q0 + S - 1 < maxL; q0 += W) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const int i = q0 + j + S - 1;
+                if (i < maxL) {   // warp-uniform
+                    const unsigned code = fetch(i);
+                    if (i < L) {
+                        roll(i, code);
+                        if (j == 0) { preF = fs; preR = rs; firstF = fs; firstR = rs; }
+                        else { preF = umin64(preF, fs); preR = umin64(preR, rs); }
+                        if (q0 + j >= W - 1) {
+                            const int pslot = (j + 1 == W) ? 0 : j + 1;
+                            bool fA, rA; u64 mf, mr;
+                            if (pslot == 0) { mf = preF; mr = preR; fA = firstF == preF; rA = firstR == preR; }
+                            else {
+                                const u64 sf = rF[pslot * kSeedThreads], sr = rR[pslot * kSeedThreads];
+                                mf = umin64(sf, preF); mr = umin64(sr, preR);
+                                fA = ((maskF >> pslot) & 1u) && sf <= preF;
+                                rA = ((maskR >> pslot) & 1u) && sr <= preR;
+                            }
+                            const bool fsyn = fA || fs == mf, rsyn = rA || rs == mr;
+                            const int pos = i - K + 1;
+                            if ((i - lastAmb >= K) && (fsyn || rsyn) && (fk != rk) && pos >= trimStart && pos <= validEnd) {
+                                dst[cnt] = umin64(fk, rk);
+                                ++cnt;
+                            }
+                        }
+                        rF[j * kSeedThreads] = fs; rR[j * kSeedThreads] = rs;
+                        if (j == W - 1) {   // block complete: in-place suffix minima + "is its own suffix minimum" masks
+                            u64 a = kEmptyKey, bb = kEmptyKey; unsigned mF = 0, mR = 0;
+#pragma unroll
+                            for (int q = W - 1; q >= 0; --q) {
+                                const u64 x = rF[q * kSeedThreads], y = rR[q * kSeedThreads];
+                                a = umin64(a, x); bb = umin64(bb, y);
+                                mF |= (a == x ? 1u : 0u) << q; mR |= (bb == y ? 1u : 0u) << q;
+                                rF[q * kSeedThreads] = a; rR[q * kSeedThreads] = bb;
+                            }
+                            maskF = mF; maskR = mR;
+                        }
+                    }
+                }
+            }
+        }
+        if (valid) synCount[r] = cnt;
+    }
+}
+
+// placement.cpp:1625-1682: one warp per read; lane j builds the k-min-mer of syncmers j..j+l-1 in closed form
+//   Fw = XOR_w rol(h[j+w], k*(l-1-w)),  Rw = XOR_w rol(h[j+w], k*w),  seed = min(Fw,Rw) unless Fw == Rw     (l > 1)
+//   seed = h[j]                                                                                                 (l <= 1)
+// MODE 0: count in the open-addressing table; MODE 2: ordered per-read list at outHash[winOff[r] ...]
+template <int MODE>
+__global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
+                                                           const u64* __restrict__ packedOff, const u64* __restrict__ winOff, u64 nReads,
+                                                           int k, int l, u64* keys, u32* counts, u64 mask, SampleAcc* acc,
+                                                           u64* outHash, u64* outCount) {
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nReads; r += warpsTotal) {
+        const int n = (int)synCount[r];
+        const u64* __restrict__ h = synBuf + packedOff[r] * 32;
+        const int nSeeds = l <= 1 ? n : (n >= l ? n - l + 1 : 0);
+        u64 written = 0;
+        for (int j0 = 0; j0 < nSeeds; j0 += 32) {
+            const int j = j0 + (int)lane;
+            bool has = false; u64 seed = 0;
+            if (j < nSeeds) {
+                if (l <= 1) { seed = h[j]; has = true; }
+                else {
+                    u64 fw = 0, rw = 0;
+                    for (int w = 0; w < l; ++w) {
+                        const u64 x = h[j + w];
+                        fw ^= rol64(x, (unsigned)(k * (l - 1 - w)));
+                        rw ^= rol64(x, (unsigned)(k * w));
+                    }
+                    has = fw != rw; seed = umin64(fw, rw);
+                }
+            }
+            if (MODE == 0) { if (has) tableInsert(keys, counts, mask, seed, 1u, acc); }
+            else {
+                const unsigned m = __ballot_sync(0xffffffffu, has);
+                if (has) outHash[winOff[r] + written + __popc(m & ((1u << lane) - 1u))] = seed;
+                written += __popc(m);
+            }
+        }
+        if (MODE != 0 && lane == 0) outCount[r] = written;
+    }
+}
+
+static size_t genericSmemBytes(const SeederParams& P) {
+    return sizeof(SeedTables) + (size_t)seederRingWords(P.k, P.s, 1) * kSeedThreads * sizeof(u64);
 }
 static unsigned seedGrid(u64 nReads) {
     u64 g = (nReads + kSeedThreads - 1) / kSeedThreads;
-    if (g > 148ull * 64) g = 148ull * 64;
+    if (g > 148ull * 16) g = 148ull * 16;
     return (unsigned)(g ? g : 1);
+}
+template <int K, int S>
+static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
+                       u64* synBuf, unsigned* synCount, cudaStream_t st) {
+    const size_t sm = sizeof(SeedTables) + (size_t)2 * (K - S + 1) * kSeedThreads * sizeof(u64);
+    cudaFuncSetAttribute(syncmers_fast<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    syncmers_fast<K, S><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount);
+}
+static void launchSyncmers(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
+                           u64* synBuf, unsigned* synCount, cudaStream_t st) {
+    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, st);
+    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, st);
+    const size_t sm = genericSmemBytes(P);
+    cudaFuncSetAttribute(syncmers_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
+                                                                     nullptr, nullptr, nullptr);
 }
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
     if (nReads == 0) return;
-    const size_t sm = seedSmemBytes(P);
-    cudaFuncSetAttribute(seed_reads<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    seed_reads<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dTables, W.keys,
-                                                               W.counts, W.tableMask, W.acc, nullptr, nullptr, nullptr, nullptr);
+    launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, st);
+    u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
+    seeds_from_syncmers<0><<<(unsigned)g, 256, 0, st>>>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.keys, W.counts, W.tableMask,
+                                                       W.acc, nullptr, nullptr);
 }
+// mode 1: syncmer (hash, isReverse, pos) lists == seeding::rollingSyncmers(returnAll=false); mode 2: per-read seed lists
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
-                    const SeederParams& P, const SeedTables* dTables, int mode, u64* outHash, unsigned char* outRev,
-                    long long* outPos, u64* outCount, cudaStream_t st) {
+                    const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
+                    unsigned char* outRev, long long* outPos, u64* outCount, cudaStream_t st) {
     if (nReads == 0) return;
-    const size_t sm = seedSmemBytes(P);
     if (mode == 1) {
-        cudaFuncSetAttribute(seed_reads<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        seed_reads<1><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr,
-                                                                   nullptr, 0, nullptr, outHash, outRev, outPos, outCount);
+        const size_t sm = genericSmemBytes(P);
+        cudaFuncSetAttribute(syncmers_generic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        syncmers_generic<1><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr, nullptr,
+                                                                         outHash, outRev, outPos, outCount);
     } else {
-        cudaFuncSetAttribute(seed_reads<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        seed_reads<2><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr,
-                                                                   nullptr, 0, nullptr, outHash, outRev, outPos, outCount);
+        launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, st);
+        u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
+        seeds_from_syncmers<2><<<(unsigned)g, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, P.k, P.l, nullptr, nullptr, 0, nullptr,
+                                                           outHash, outCount);
     }
 }
 
@@ -347,19 +539,24 @@ __device__ double sequentialDrift(const unsigned* __restrict__ hist, const doubl
     double e = 0.0;
     if (T > 0.0) {
         const int eTop = (int)((dblBits(T) >> 52) & 0x7FF) - 1023;
+        double fr[20], u[20], iu[20];  // share of the additions that land in each binade, its ulp and 1/ulp
+#pragma unroll
+        for (int j = 0; j < 20; ++j) {
+            const int ex = eTop - j;
+            const double lo = j == 19 ? 0.0 : bitsDbl((u64)(ex + 1023) << 52);
+            const double hi = fmin(T, bitsDbl((u64)(ex + 1024) << 52));
+            fr[j] = (hi - lo) / T;
+            u[j] = bitsDbl((u64)(ex - 52 + 1023) << 52);
+            iu[j] = bitsDbl((u64)(52 - ex + 1023) << 52);
+        }
         for (int c = threadIdx.x; c < kLog1pLut; c += blockDim.x) {
             const unsigned m = hist[c];
             if (!m) continue;
             double x = lut[c];
             if (squared) x = x * x;
             double acc = 0.0;
-            for (int j = 0; j < 20; ++j) {
-                const int ex = eTop - j;
-                const double lo = j == 19 ? 0.0 : ldexp(1.0, ex);
-                const double hi = fmin(T, ldexp(1.0, ex + 1));
-                const double u = ldexp(1.0, ex - 52);
-                acc += ((hi - lo) / T) * (rint(x / u) * u - x);
-            }
+#pragma unroll
+            for (int j = 0; j < 20; ++j) acc += fr[j] * (rint(x * iu[j]) * u[j] - x);
             e += acc * (double)m;
         }
     }
@@ -402,7 +599,8 @@ void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* hom
     u64 g = (W.tableCap + 255) / 256; if (g > 148 * 16) g = 148 * 16;
     cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
     table_stats<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableCap, W.acc, homo);
-    table_finalize<<<(unsigned)g, 256, 0, st>>>(I, W, O.minReadSupport);
+    u64 gf = g > 148 * 8 ? 148 * 8 : g;
+    table_finalize<<<(unsigned)gf, 256, 0, st>>>(I, W, O.minReadSupport);
     if (I.hasRoot && I.rootDCount) {
         u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
         root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);

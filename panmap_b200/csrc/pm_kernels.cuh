@@ -89,6 +89,7 @@ struct WorkspaceView {
     // read table
     u64* keys; u32* counts; u64 tableMask; u64 tableCap;
     SampleAcc* acc;
+    u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
     double* ell;          // [nSeeds] log1p(read count) of seed id, 0 when absent
     u32* touched; u32 touchedCap;
     unsigned* countHist;  // [kLog1pLut] multiplicity of every read count among the kept seeds (rounding-drift model)
@@ -118,8 +119,8 @@ void launchPackReads(const char* reads, const u64* off, const u64* packedOff, u6
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st);
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
-                    const SeederParams& P, const SeedTables* dTables, int mode, u64* outHash, unsigned char* outRev,
-                    long long* outPos, u64* outCount, cudaStream_t st);
+                    const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
+                    unsigned char* outRev, long long* outPos, u64* outCount, cudaStream_t st);
 void launchTableClear(WorkspaceView W, cudaStream_t st);
 void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st);
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st);

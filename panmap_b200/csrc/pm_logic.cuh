@@ -92,62 +92,63 @@ inline SeederParams makeSeederParams(int k, int s, int t, int l, int open, int t
 // Sequential per-read seeder: feed bases one at a time; emits syncmers (and k-min-mers for l > 1).
 // Ring storage (4*w + max(l,1) u64 words) is supplied by the caller as a strided view so that a CUDA block can
 // lay the rings out [slot][thread] in shared memory (conflict-free) and the host check can use a plain array.
-struct ReadSeeder {
+// STRIDE is a compile-time constant (the CUDA block size) so that ring addressing is shifts, not 64-bit multiplies.
+template <int STRIDE>
+struct ReadSeederT {
     u64 fk, rk, fs, rs;      // rolling k-mer / s-mer hashes, both strands
-    u64 histLo, histHi;      // last 32 base codes, 4 bits each, newest in bits 0..3 of histLo
+    u64 hist2;               // last 32 base codes, 2 bits each, newest in bits 0..1
+    unsigned histAmb;        // last 32 "ambiguous" flags, newest in bit 0
     u64 preF, preR;          // running minima of the current block (van Herk / Gil-Werman sliding minimum)
     u64 kmF, kmR;            // rolling k-min-mer hashes
     int lastAmb;             // index of the most recent ambiguous base
     int slot;                // (s-mer index) mod w
-    int synCount;            // in-range syncmers seen so far
+    int synCount;            // in-range syncmers seen so far (saturates at l)
+    int hslot;               // synCount mod l
     unsigned kmRot;          // (k * synCount) mod 64 during the first l syncmers
-    u64* ring;               // strided storage
-    int stride;
+    u64 *pF, *pFsuf, *pR, *pRsuf, *pH;  // ring views
 
-    PM_HD u64& F(int i) { return ring[(size_t)i * stride]; }
-    PM_HD u64& Fsuf(int i, int w) { return ring[(size_t)(w + i) * stride]; }
-    PM_HD u64& R(int i, int w) { return ring[(size_t)(2 * w + i) * stride]; }
-    PM_HD u64& Rsuf(int i, int w) { return ring[(size_t)(3 * w + i) * stride]; }
-    PM_HD u64& H(int i, int w) { return ring[(size_t)(4 * w + i) * stride]; }
-
-    PM_HD void reset(u64* ringBase, int ringStride) {
+    PM_HD void reset(u64* ringBase, int w) {
         fk = rk = fs = rs = 0; kmF = kmR = 0;
-        histLo = histHi = 0x4444444444444444ULL;  // every past base "ambiguous": table entry 0
+        hist2 = 0; histAmb = 0xFFFFFFFFu;  // every past base "ambiguous": table entries 4..7 are zero
         preF = preR = kEmptyKey;
-        lastAmb = -1; slot = -1; synCount = 0; kmRot = 0;
-        ring = ringBase; stride = ringStride;
+        lastAmb = -1; slot = -1; synCount = 0; hslot = 0; kmRot = 0;
+        pF = ringBase; pFsuf = ringBase + (size_t)w * STRIDE; pR = ringBase + (size_t)2 * w * STRIDE;
+        pRsuf = ringBase + (size_t)3 * w * STRIDE; pH = ringBase + (size_t)4 * w * STRIDE;
     }
-    PM_HD unsigned codeBack(int dist) const {  // code of the base `dist` positions before the one being pushed (dist >= 1)
-        const int sh = 4 * (dist - 1);
-        return (unsigned)((sh < 64 ? (histLo >> sh) : (histHi >> (sh - 64))) & 0xFULL);
+    PM_HD unsigned codeBack(int dist) const {  // table index of the base `dist` positions before the one being pushed (1 <= dist <= 32)
+        return (unsigned)((hist2 >> (2 * (dist - 1))) & 3ULL) | (((histAmb >> (dist - 1)) & 1u) << 2);
     }
 
-    // Push base `code` at read position i (0-based).  Returns true when k-mer window i-k+1 is a syncmer;
-    // hash / isReverse are then set.  (seeding.cpp:147-226 restated with no per-step rescans.)
+    // Push base `code` (0..3 ACGT, >=4 ambiguous) at read position i (0-based).  Returns true when k-mer window i-k+1 is a
+    // syncmer; hash / isReverse are then set.  (seeding.cpp:147-226 restated with no per-step rescans.)
     PM_HD bool pushBase(int i, unsigned code, const SeedTables& T, const SeederParams& P, u64& hash, bool& isReverse) {
         const unsigned oldK = codeBack(P.k), oldS = codeBack(P.s);
-        fk = rol1(fk) ^ T.fwdOldK[oldK] ^ T.fwdNew[code];
-        rk = ror1(rk) ^ T.revOld[oldK] ^ T.revNewK[code];
-        fs = rol1(fs) ^ T.fwdOldS[oldS] ^ T.fwdNew[code];
-        rs = ror1(rs) ^ T.revOld[oldS] ^ T.revNewS[code];
-        histHi = (histHi << 4) | (histLo >> 60);
-        histLo = (histLo << 4) | (u64)code;
+        const unsigned tc = code & 7u;
+        fk = rol1(fk) ^ T.fwdOldK[oldK] ^ T.fwdNew[tc];
+        rk = ror1(rk) ^ T.revOld[oldK] ^ T.revNewK[tc];
+        fs = rol1(fs) ^ T.fwdOldS[oldS] ^ T.fwdNew[tc];
+        rs = ror1(rs) ^ T.revOld[oldS] ^ T.revNewS[tc];
+        hist2 = (hist2 << 2) | (u64)(code & 3u);
+        histAmb = (histAmb << 1) | (code >= 4 ? 1u : 0u);
         if (code >= 4) lastAmb = i;
         if (i < P.s - 1) return false;
         const int w = P.w;
         slot = (slot + 1 == w) ? 0 : slot + 1;
-        F(slot) = fs; R(slot, w) = rs;
+        pF[slot * STRIDE] = fs; pR[slot * STRIDE] = rs;
         if (slot == 0) { preF = fs; preR = rs; } else { preF = umin64(preF, fs); preR = umin64(preR, rs); }
         bool syn = false;
         if (i >= P.k - 1) {
             const int pslot = (slot + 1 == w) ? 0 : slot + 1;  // slot of the oldest s-mer of the window
             u64 mf = preF, mr = preR;
-            if (pslot != 0) { mf = umin64(mf, Fsuf(pslot, w)); mr = umin64(mr, Rsuf(pslot, w)); }
+            if (pslot != 0) { mf = umin64(mf, pFsuf[pslot * STRIDE]); mr = umin64(mr, pRsuf[pslot * STRIDE]); }
             int ia = pslot + P.t; if (ia >= w) ia -= w;            // s-mer p+t
             int ib = slot - P.t; if (ib < 0) ib += w;              // s-mer p+k-s-t
             bool fsyn, rsyn;
-            if (P.open) { fsyn = F(ia) == mf; rsyn = R(ib, w) == mr; }
-            else { fsyn = (F(ia) == mf) || (F(ib) == mf); rsyn = (R(ib, w) == mr) || (R(ia, w) == mr); }
+            if (P.open) { fsyn = pF[ia * STRIDE] == mf; rsyn = pR[ib * STRIDE] == mr; }
+            else {
+                fsyn = (pF[ia * STRIDE] == mf) || (pF[ib * STRIDE] == mf);
+                rsyn = (pR[ib * STRIDE] == mr) || (pR[ia * STRIDE] == mr);
+            }
             syn = (i - lastAmb >= P.k) && (fsyn || rsyn) && (fk != rk);
             hash = umin64(fk, rk);
             isReverse = rk < fk;
@@ -155,8 +156,8 @@ struct ReadSeeder {
         if (slot == w - 1) {  // block complete: suffix minima for the windows that straddle into the next block
             u64 a = kEmptyKey, b = kEmptyKey;
             for (int q = w - 1; q >= 0; --q) {
-                a = umin64(a, F(q)); Fsuf(q, w) = a;
-                b = umin64(b, R(q, w)); Rsuf(q, w) = b;
+                a = umin64(a, pF[q * STRIDE]); pFsuf[q * STRIDE] = a;
+                b = umin64(b, pR[q * STRIDE]); pRsuf[q * STRIDE] = b;
             }
         }
         return syn;
@@ -167,19 +168,19 @@ struct ReadSeeder {
     PM_HD bool pushSyncmer(int pos, int len, u64 h, const SeederParams& P, u64& seed) {
         if (pos < P.trimStart || pos > len - P.trimEnd - P.k) return false;
         if (P.l <= 1) { seed = h; return true; }
-        const int w = P.w, l = P.l;
-        const int hs = synCount % l;
+        const int l = P.l;
         if (synCount < l) {
             kmF = rol64(kmF, P.rotK) ^ h;
             kmR ^= rol64(h, kmRot);
             kmRot = (kmRot + P.rotK) & 63u;
+            ++synCount;
         } else {
-            const u64 prev = H(hs, w);
+            const u64 prev = pH[hslot * STRIDE];
             kmF = rol64(kmF, P.rotK) ^ rol64(prev, P.rotKL) ^ h;
             kmR = ror64(kmR, P.rotK) ^ ror64(prev, P.rotK) ^ rol64(h, P.rotKL1);
         }
-        H(hs, w) = h;
-        ++synCount;
+        pH[hslot * STRIDE] = h;
+        hslot = (hslot + 1 == l) ? 0 : hslot + 1;
         if (synCount >= l && kmF != kmR) { seed = umin64(kmF, kmR); return true; }
         return false;
     }

@@ -23,7 +23,7 @@ int64_t hc_seed(const char* seq, int64_t len, int k, int s, int t, int l, int op
     SeedTables T; buildSeedTables(T, k, s);
     const SeederParams P = makeSeederParams(k, s, t, mode == 1 ? 1 : l, open, trimS, trimE);
     std::vector<u64> ring((size_t)seederRingWords(k, s, l) * 3, 0);
-    ReadSeeder sd; sd.reset(ring.data() + 1, 3);  // stride 3 to exercise the strided view
+    ReadSeederT<3> sd; sd.reset(ring.data() + 1, k - s + 1);  // stride 3 to exercise the strided view
     int64_t n = 0;
     if (len < k) return 0;
     for (int i = 0; i < (int)len; ++i) {

@@ -36,7 +36,7 @@ struct Gen {
         const int G = (int)g.size();
         a = std::max(a, 0); b = std::min(b, G - k);
         if (a > b) return;
-        ReadSeeder sd; sd.reset(ring.data(), 1);
+        ReadSeederT<1> sd; sd.reset(ring.data(), k - s + 1);
         for (int i = a; i <= b + k - 1; ++i) {
             u64 h; bool rev;
             if (sd.pushBase(i - a, baseCode((unsigned char)g[i]), T, P, h, rev)) out.push_back({i - k + 1, h});
