@@ -80,8 +80,9 @@ struct pm_host_index { HostIndex h; };
 struct pm_index {
     int device = 0; int nSM = 148;
     FlatIndex F;  // host copy of the small arrays (tree) is kept for result assembly; big vectors are released
-    DevBuf<u32> seedId, pc, lNode, parent, closeOff, closeList, carrySlot, chainOff, chainNodes, bfsNodes, bfsRanks, dictVals;
-    DevBuf<u64> lOff, dictKeys, dictHash, homo;
+    DevBuf<u32> seedId, pc, lNode, parent, closeOff, closeList, carrySlot, chainOff, chainNodes, bfsNodes, bfsRanks;
+    DevBuf<u64> lOff, dictHash, homo;
+    DevBuf<DictSlot> dict;
     DevBuf<double> gMag, log1pLut, log1pSmall;
     DevBuf<unsigned char> isLeaf;
     DevBuf<K1Tile> k1Tiles;
@@ -96,11 +97,11 @@ struct pm_workspace {
     cudaStream_t st = nullptr;
     cudaEvent_t ev[9]{};
     // inputs
-    DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed;
-    PinBuf<u64> hPackedOff;
+    DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
+    PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
     u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
     // table
-    DevBuf<u64> keys; DevBuf<u32> counts; u64 tableCap = 0;
+    DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0;
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
     DevBuf<double> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist;
@@ -138,7 +139,7 @@ void buildViews(pm_index* I) {
     V.isLeaf = I->isLeaf.p;
     V.bfsNodes = I->bfsNodes.p; V.bfsRanks = I->bfsRanks.p; V.nShardNodes = F.nodeEnd - F.nodeBegin;
     V.nBfsBlocks = (V.nShardNodes + kBfsBlock - 1) / kBfsBlock;
-    V.dictKeys = I->dictKeys.p; V.dictVals = I->dictVals.p; V.dictMask = F.dictMask; V.dictHash = I->dictHash.p;
+    V.dict = I->dict.p; V.dictMask = F.dictMask; V.dictHash = I->dictHash.p;
     V.rootDBegin = F.rootDBegin; V.rootDCount = F.rootDCount; V.hasRoot = 1;
     V.log1pLut = I->log1pLut.p; V.log1pSmall = I->log1pSmall.p;
     V.ln2 = std::log1p(1.0);
@@ -161,7 +162,12 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
         I->parent.upload(F.parent); I->gMag.upload(F.gMag); I->closeOff.upload(F.closeOff); I->closeList.upload(F.closeList);
         I->carrySlot.upload(F.carrySlot); I->chainOff.upload(F.chainOff); I->chainNodes.upload(F.chainNodes);
         I->isLeaf.upload(F.isLeaf); I->bfsNodes.upload(F.bfsNodes); I->bfsRanks.upload(F.bfsRanks);
-        I->dictKeys.upload(F.dictKeys); I->dictVals.upload(F.dictVals); I->dictHash.upload(F.dictHash);
+        {
+            std::vector<DictSlot> d(F.dictKeys.size());
+            for (size_t i = 0; i < d.size(); ++i) { d[i].key = F.dictKeys[i]; d[i].id = F.dictVals[i]; d[i].pad = 0; }
+            I->dict.upload(d);
+        }
+        I->dictHash.upload(F.dictHash);
         {
             std::vector<K1Tile> t(F.k1Tiles.size());
             for (size_t i = 0; i < t.size(); ++i) {
@@ -197,7 +203,7 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
 
 void refreshView(pm_workspace* W) {
     WorkspaceView& V = W->view;
-    V.keys = W->keys.p; V.counts = W->counts.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
+    V.table = W->table.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
     V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
     V.acc = W->acc.p; V.ell = W->ell.p; V.touched = W->touched.p; V.touchedCap = (u32)W->touched.n; V.countHist = W->countHist.p;
     V.delta = W->delta.p; V.bigPartial = W->bigPartial.p; V.bigDone = W->bigDone.p; V.chainA = W->chainA.p;
@@ -210,7 +216,7 @@ void ensureTable(pm_workspace* W, u64 wantCap) {
     u64 cap = 1 << 12;
     while (cap < wantCap) cap <<= 1;
     if (cap <= W->tableCap) return;
-    W->keys.alloc(cap); W->counts.alloc(cap); W->tableCap = cap;
+    W->table.alloc(cap); W->tableCap = cap;
     refreshView(W);
 }
 
@@ -240,6 +246,8 @@ void hostPackedOffsets(pm_workspace* W, const uint64_t* off, u64 n, int k) {
     }
     W->hPackedOff.p[n] = acc;
     W->nChunks = acc; W->totalWindows = win;
+    W->hBlockFirst.ensure((acc + 255) / 256 + 1);
+    packBlockFirst(W->hPackedOff.p, n, acc, W->hBlockFirst.p);
 }
 
 void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n) {
@@ -254,6 +262,8 @@ void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n)
     if (total) CK(cudaMemcpyAsync(W->reads.p, reads, total, cudaMemcpyHostToDevice, W->st));
     CK(cudaMemcpyAsync(W->off.p, off, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->st));
     CK(cudaMemcpyAsync(W->packedOff.p, W->hPackedOff.p, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->st));
+    W->blockFirst.ensure((W->nChunks + 255) / 256 + 1);
+    CK(cudaMemcpyAsync(W->blockFirst.p, W->hBlockFirst.p, ((W->nChunks + 255) / 256 + 1) * sizeof(u32), cudaMemcpyHostToDevice, W->st));
 }
 
 void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
@@ -263,7 +273,7 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
         launchTableClear(W->view, W->st);
     }
-    launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->nReads, W->nChunks, W->packed.p, W->st);
+    launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, W->nChunks, W->packed.p, W->st);
     launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st);
 }
 
@@ -343,6 +353,12 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
         CK(cudaEventRecord(W->ev[0], W->st));
         if (!inputsResident) uploadReads(W, reads, off, n);
         if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, W->totalWindows / 4));
+        else if (W->lastEntries && W->tableCap > (1u << 16) && W->tableCap > 4 * W->lastEntries) {
+            // the previous sample filled under a quarter of the slots: every pass over the table is cheaper with a tighter one
+            u64 cap = 1 << 16;
+            while (cap < 2 * W->lastEntries) cap <<= 1;
+            if (cap < W->tableCap) { W->tableCap = cap; }   // keep the allocation, use a prefix
+        }
         refreshView(W);
         CK(cudaEventRecord(W->ev[1], W->st));
         stageSeed(W, true, *prm);
@@ -362,6 +378,7 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
             continue;
         }
         fetchTies(W);
+        W->lastEntries = (u64)W->hAcc.entries;
         CK(cudaEventRecord(W->ev[7], W->st));
         CK(cudaStreamSynchronize(W->st));
         fillResult(W, res, W->nReads);
@@ -519,7 +536,7 @@ int pm_get_node_metrics(pm_workspace* ws, double* out) {
         ws->wantMetrics = true; refreshView(ws);
         // ell was reset after the sample: rebuild it from the (still intact) table, then K1 + K2 only
         CK(cudaMemsetAsync(&ws->acc.p->touchedCount, 0, sizeof(unsigned), ws->st));
-        CK(cudaMemsetAsync(ws->acc.p->magSq, 0, 6 * sizeof(u64) + 6 * sizeof(long long), ws->st));
+        CK(cudaMemsetAsync(ws->acc.p->magSq, 0, 6 * sizeof(u64) + 7 * sizeof(long long), ws->st));
         const PlaceOpts O = makeOpts(ws->lastParams, true);
         launchFinalize(I->view, ws->view, O, I->homo.p, ws->st);
         launchDeltas(I->view, ws->view, I->nSM, ws->st);
@@ -586,7 +603,11 @@ static int seedListImpl(int device, const char* seqs, const uint64_t* off, uint6
         std::vector<SeedTables> T(1); buildSeedTables(T[0], sp->k, sp->s);
         dT.alloc(1); CK(cudaMemcpyAsync(dT.p, T.data(), sizeof(SeedTables), cudaMemcpyHostToDevice, st));
         const SeederParams P = makeSeederParams(sp->k, sp->s, sp->t, sp->l, sp->open, trimStart, trimEnd);
-        launchPackReads(dReads.p, dOff.p, dPOff.p, n, ch, dPacked.p, st);
+        std::vector<u32> bf((ch + 255) / 256 + 1);
+        packBlockFirst(pOff.data(), n, ch, bf.data());
+        DevBuf<u32> dBF; dBF.alloc(bf.size());
+        CK(cudaMemcpyAsync(dBF.p, bf.data(), bf.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+        launchPackReads(dReads.p, dOff.p, dPOff.p, dBF.p, n, ch, dPacked.p, st);
         launchSeedList(dPacked.p, dOff.p, dPOff.p, dWOff.p, n, P, dT.p, mode, dSyn.p, dSynCount.p, dHash.p, dRev.p, dPos.p, dCount.p, st);
         CK(cudaGetLastError());
         if (win) CK(cudaMemcpyAsync(outHash, dHash.p, win * 8, cudaMemcpyDeviceToHost, st));

@@ -23,6 +23,18 @@ namespace pm {
 static constexpr uint32_t kTileDeltasH = 4096, kTileNodesK1H = 2048, kTileNodesK2H = 512;
 static constexpr uint32_t NONE = 0xFFFFFFFFu;
 
+// for every block of 256 packed chunks: the read r with packedOff[r] <= firstChunk < packedOff[r+1]
+void packBlockFirst(const uint64_t* packedOff, uint64_t nReads, uint64_t nChunks, uint32_t* out) {
+    uint64_t r = 0;
+    const uint64_t nBlocks = (nChunks + 255) / 256;
+    for (uint64_t b = 0; b < nBlocks; ++b) {
+        const uint64_t g = b * 256;
+        while (r + 1 < nReads && packedOff[r + 1] <= g) ++r;
+        out[b] = static_cast<uint32_t>(r);
+    }
+    out[nBlocks] = static_cast<uint32_t>(nReads ? nReads - 1 : 0);
+}
+
 void bfsRanks(const uint32_t* parent, uint64_t N, std::vector<uint32_t>& rank) {
     rank.assign(N, 0);
     if (N == 0) return;

@@ -59,6 +59,8 @@ struct FlatIndex {
 // shard `shard` of `nShards` (contiguous DFS ranges balanced by delta count); throws std::runtime_error on bad input
 void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, FlatIndex& out);
 
+void packBlockFirst(const uint64_t* packedOff, uint64_t nReads, uint64_t nChunks, uint32_t* out);
+
 // reference BFS visit order (children ascending, level by level): rank of every node
 void bfsRanks(const uint32_t* parent, uint64_t N, std::vector<uint32_t>& rank);
 

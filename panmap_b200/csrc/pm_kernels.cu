@@ -47,54 +47,94 @@ __device__ __forceinline__ long long warpSumLL(long long v) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// pack_reads: one thread per 32-base chunk
+// pack_reads
 // ------------------------------------------------------------------------------------------------------
+// One thread per 32-base chunk.  The block gets the read of its first chunk from a small host-built table, stages the
+// chunk/byte offsets of the <= 257 reads it can touch in shared memory, and every thread then locates its read there.
+// Source bytes are fetched as nine aligned 32-bit words per thread (neighbouring threads read neighbouring 32-byte
+// segments, so the lines are shared through L1) and realigned with funnel shifts; base -> code via a shared 256-byte table.
 __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads, const u64* __restrict__ off,
-                                                  const u64* __restrict__ packedOff, u64 nReads, u64 nChunks,
-                                                  uint4* __restrict__ packed) {
-    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nChunks) return;
-    // read r with packedOff[r] <= g < packedOff[r+1]
-    u64 lo = 0, hi = nReads;
-    while (hi - lo > 1) {
-        const u64 mid = (lo + hi) >> 1;
-        if (__ldg(&packedOff[mid]) <= g) lo = mid; else hi = mid;
+                                                  const u64* __restrict__ packedOff, const u32* __restrict__ blockFirst, u64 nReads,
+                                                  u64 nChunks, uint4* __restrict__ packed) {
+    __shared__ u64 sPO[258];
+    __shared__ u64 sOff[258];
+    __shared__ unsigned char sLut[256];
+    __shared__ u64 sFirst;
+    const u64 g0 = (u64)blockIdx.x * 256;
+    sLut[threadIdx.x] = (unsigned char)baseCode((unsigned char)threadIdx.x);
+    if (threadIdx.x == 0) sFirst = blockFirst[blockIdx.x];   // read owning this block's first chunk (computed with the chunk offsets on the host)
+    __syncthreads();
+    const u64 rFirst = sFirst;
+    for (int i = threadIdx.x; i < 258; i += 256) {
+        const u64 r = rFirst + i;
+        sPO[i] = r <= nReads ? __ldg(&packedOff[r]) : ~0ULL;
+        sOff[i] = r <= nReads ? __ldg(&off[r]) : 0;
     }
-    const u64 r = lo;
-    const u64 c = g - __ldg(&packedOff[r]);
-    const u64 b = __ldg(&off[r]), e = __ldg(&off[r + 1]);
-    const u64 src = b + 32 * c;
+    __syncthreads();
+    const u64 g = g0 + threadIdx.x;
+    if (g >= nChunks) return;
+    int lo = 0, hi = 257;   // largest i with sPO[i] <= g
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sPO[mid] <= g) lo = mid; else hi = mid;
+    }
+    u64 c, src, e;
+    if (sPO[hi] <= g) {
+        // more than 256 reads behind this block's first chunk (runs of empty reads): locate the read in global memory
+        u64 glo = rFirst + 257, ghi = nReads;
+        while (ghi - glo > 1) {
+            const u64 mid = (glo + ghi) >> 1;
+            if (__ldg(&packedOff[mid]) <= g) glo = mid; else ghi = mid;
+        }
+        c = g - __ldg(&packedOff[glo]); src = __ldg(&off[glo]) + 32 * c; e = __ldg(&off[glo + 1]);
+    } else {
+        c = g - sPO[lo]; src = sOff[lo] + 32 * c; e = sOff[lo + 1];
+    }
     const int n = (int)((e - src) < 32 ? (e - src) : 32);
-    unsigned w[4] = {0x44444444u, 0x44444444u, 0x44444444u, 0x44444444u};
-    for (int j = 0; j < n; ++j) {
-        const unsigned code = baseCode((unsigned char)__ldg(&reads[src + j]));
-        const int sh = 4 * (j & 7);
-        w[j >> 3] = (w[j >> 3] & ~(0xFu << sh)) | (code << sh);
+    const unsigned* __restrict__ wsrc = reinterpret_cast<const unsigned*>(reads + (src & ~3ULL));
+    const unsigned sh = (unsigned)(src & 3ULL) * 8u;
+    unsigned x[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) x[q] = __ldg(wsrc + q);
+    unsigned w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned out = 0;
+#pragma unroll
+        for (int hw = 0; hw < 2; ++hw) {
+            const unsigned bytes = __funnelshift_r(x[2 * q + hw], x[2 * q + hw + 1], sh);
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                const int j = 8 * q + 4 * hw + bb;
+                const unsigned code = j < n ? sLut[(bytes >> (8 * bb)) & 0xFFu] : 4u;
+                out |= code << (4 * (4 * hw + bb));
+            }
+        }
+        w[q] = out;
     }
     packed[g] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-void launchPackReads(const char* reads, const u64* off, const u64* packedOff, u64 nReads, u64 nChunks, uint4* packed,
+void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 nChunks, uint4* packed,
                      cudaStream_t st) {
     if (nChunks == 0) return;
     const unsigned grid = (unsigned)((nChunks + 255) / 256);
-    pack_reads<<<grid, 256, 0, st>>>(reads, off, packedOff, nReads, nChunks, packed);
+    pack_reads<<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, nChunks, packed);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // count table insert (open addressing, linear probing; keys are 64-bit seed hashes)
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tableInsert(u64* __restrict__ keys, u32* __restrict__ counts, u64 mask, u64 h, u32 add,
-                                            SampleAcc* acc) {
+__device__ __forceinline__ void tableInsert(TableSlot* __restrict__ table, u64 mask, u64 h, u32 add, SampleAcc* acc) {
     if (h == kEmptyKey) { atomicAdd((unsigned long long*)&acc->emptyKeyCount, (unsigned long long)add); return; }
     u64 slot = mixKey(h) & mask;
     for (int probe = 0; probe < 8192; ++probe) {
-        u64 cur = *((volatile u64*)&keys[slot]);
+        u64 cur = *((volatile u64*)&table[slot].key);
         if (cur == kEmptyKey) {
-            cur = atomicCAS((unsigned long long*)&keys[slot], (unsigned long long)kEmptyKey, (unsigned long long)h);
+            cur = atomicCAS((unsigned long long*)&table[slot].key, (unsigned long long)kEmptyKey, (unsigned long long)h);
             if (cur == kEmptyKey) cur = h;
         }
-        if (cur == h) { atomicAdd(&counts[slot], add); return; }
+        if (cur == h) { atomicAdd(&table[slot].count, add); return; }
         slot = (slot + 1) & mask;
     }
     acc->overflow = 1;
@@ -299,11 +339,13 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
 //   Fw = XOR_w rol(h[j+w], k*(l-1-w)),  Rw = XOR_w rol(h[j+w], k*w),  seed = min(Fw,Rw) unless Fw == Rw     (l > 1)
 //   seed = h[j]                                                                                                 (l <= 1)
 // MODE 0: count in the open-addressing table; MODE 2: ordered per-read list at outHash[winOff[r] ...]
-template <int MODE>
+// KT/LT > 0: k and l are compile-time constants (rotations become immediates); KT == 0: runtime k, l.
+template <int MODE, int KT, int LT>
 __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
                                                            const u64* __restrict__ packedOff, const u64* __restrict__ winOff, u64 nReads,
-                                                           int k, int l, u64* keys, u32* counts, u64 mask, SampleAcc* acc,
+                                                           int kRt, int lRt, TableSlot* table, u64 mask, SampleAcc* acc,
                                                            u64* outHash, u64* outCount) {
+    const int k = KT > 0 ? KT : kRt, l = KT > 0 ? LT : lRt;
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
     for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nReads; r += warpsTotal) {
@@ -316,7 +358,16 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
             bool has = false; u64 seed = 0;
             if (j < nSeeds) {
                 if (l <= 1) { seed = h[j]; has = true; }
-                else {
+                else if (KT > 0) {
+                    u64 fw = 0, rw = 0;
+#pragma unroll
+                    for (int w = 0; w < (LT > 0 ? LT : 1); ++w) {
+                        const u64 x = h[j + w];
+                        fw ^= rol64(x, (unsigned)((KT * (LT - 1 - w)) & 63));
+                        rw ^= rol64(x, (unsigned)((KT * w) & 63));
+                    }
+                    has = fw != rw; seed = umin64(fw, rw);
+                } else {
                     u64 fw = 0, rw = 0;
                     for (int w = 0; w < l; ++w) {
                         const u64 x = h[j + w];
@@ -326,7 +377,7 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
                     has = fw != rw; seed = umin64(fw, rw);
                 }
             }
-            if (MODE == 0) { if (has) tableInsert(keys, counts, mask, seed, 1u, acc); }
+            if (MODE == 0) { if (has) tableInsert(table, mask, seed, 1u, acc); }
             else {
                 const unsigned m = __ballot_sync(0xffffffffu, has);
                 if (has) outHash[winOff[r] + written + __popc(m & ((1u << lane) - 1u))] = seed;
@@ -335,6 +386,18 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
         }
         if (MODE != 0 && lane == 0) outCount[r] = written;
     }
+}
+template <int MODE>
+static void launchSeedsFromSyncmers(const u64* synBuf, const unsigned* synCount, const u64* packedOff, const u64* winOff, u64 nReads, int k, int l,
+                                    TableSlot* table, u64 mask, SampleAcc* acc, u64* outHash, u64* outCount, cudaStream_t st) {
+    u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
+    const unsigned grid = (unsigned)(g ? g : 1);
+    if (k == 19 && l == 3)
+        seeds_from_syncmers<MODE, 19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount);
+    else if (k == 15 && l == 3)
+        seeds_from_syncmers<MODE, 15, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount);
+    else
+        seeds_from_syncmers<MODE, 0, 0><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount);
 }
 
 static size_t genericSmemBytes(const SeederParams& P) {
@@ -365,9 +428,7 @@ void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, 
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
     if (nReads == 0) return;
     launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, st);
-    u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
-    seeds_from_syncmers<0><<<(unsigned)g, 256, 0, st>>>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.keys, W.counts, W.tableMask,
-                                                       W.acc, nullptr, nullptr);
+    launchSeedsFromSyncmers<0>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table, W.tableMask, W.acc, nullptr, nullptr, st);
 }
 // mode 1: syncmer (hash, isReverse, pos) lists == seeding::rollingSyncmers(returnAll=false); mode 2: per-read seed lists
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
@@ -381,41 +442,43 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
                                                                          outHash, outRev, outPos, outCount);
     } else {
         launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, st);
-        u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
-        seeds_from_syncmers<2><<<(unsigned)g, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, P.k, P.l, nullptr, nullptr, 0, nullptr,
-                                                           outHash, outCount);
+        launchSeedsFromSyncmers<2>(synBuf, synCount, packedOff, winOff, nReads, P.k, P.l, nullptr, 0, nullptr, outHash, outCount, st);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // table maintenance
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) table_clear(u64* keys, u32* counts, u64 cap) {
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
-        keys[i] = kEmptyKey; counts[i] = 0;
-    }
+__global__ void __launch_bounds__(256) table_clear(TableSlot* table, u64 cap) {
+    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+    uint4* t = reinterpret_cast<uint4*>(table);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) t[i] = e;
 }
-void launchTableClear(WorkspaceView W, cudaStream_t st) {
-    u64 g = (W.tableCap + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-    table_clear<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableCap);
+static unsigned streamGrid(u64 n, unsigned perThread) {
+    u64 g = (n + 256ull * perThread - 1) / (256ull * perThread);
+    if (g > 148 * 16) g = 148 * 16;
+    return (unsigned)(g ? g : 1);
 }
+void launchTableClear(WorkspaceView W, cudaStream_t st) { table_clear<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W.table, W.tableCap); }
 
-__global__ void __launch_bounds__(256) table_import(u64* keys, u32* counts, u64 mask, SampleAcc* acc,
-                                                    const u64* __restrict__ hash, const long long* __restrict__ count, u64 n) {
+__global__ void __launch_bounds__(256) table_import(TableSlot* table, u64 mask, SampleAcc* acc, const u64* __restrict__ hash,
+                                                    const long long* __restrict__ count, u64 n) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
-        if (count[i] > 0) tableInsert(keys, counts, mask, hash[i], (u32)count[i], acc);
+        if (count[i] > 0) tableInsert(table, mask, hash[i], (u32)count[i], acc);
 }
 void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st) {
     if (!n) return;
-    u64 g = (n + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-    table_import<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableMask, W.acc, hash, count, n);
+    table_import<<<streamGrid(n, 1), 256, 0, st>>>(W.table, W.tableMask, W.acc, hash, count, n);
 }
 
-__global__ void __launch_bounds__(256) table_export(const u64* __restrict__ keys, const u32* __restrict__ counts, u64 cap,
-                                                    const SampleAcc* acc, u64* outHash, long long* outCount, unsigned* counter,
-                                                    u64 outCap) {
+__device__ __forceinline__ uint4 ldSlot(const TableSlot* t, u64 i) { return __ldcs(reinterpret_cast<const uint4*>(t) + i); }
+__device__ __forceinline__ u64 slotKey(const uint4& v) { return (u64)v.x | ((u64)v.y << 32); }
+
+__global__ void __launch_bounds__(256) table_export(const TableSlot* __restrict__ table, u64 cap, const SampleAcc* acc, u64* outHash,
+                                                    long long* outCount, unsigned* counter, u64 outCap) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
-        const u64 k = keys[i]; const u32 c = counts[i];
+        const uint4 v = ldSlot(table, i);
+        const u64 k = slotKey(v); const u32 c = v.z;
         if (k != kEmptyKey && c > 0) {
             const unsigned o = atomicAdd(counter, 1u);
             if (o < outCap) { outHash[o] = k; outCount[o] = (long long)c; }
@@ -427,21 +490,27 @@ __global__ void __launch_bounds__(256) table_export(const u64* __restrict__ keys
     }
 }
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st) {
-    u64 g = (W.tableCap + 255) / 256; if (g > 148 * 16) g = 148 * 16;
-    table_export<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableCap, W.acc, hash, count, counter, cap);
+    table_export<<<streamGrid(W.tableCap, 2), 256, 0, st>>>(W.table, W.tableCap, W.acc, hash, count, counter, cap);
 }
 
 // pass 1: erase the four homopolymer k-mer hashes (placement.cpp:1708-1718) and gather the statistics of the
-// auto min-read-support rule (placement.cpp:931-955)
-__global__ void __launch_bounds__(256) table_stats(u64* keys, u32* counts, u64 cap, SampleAcc* acc, const u64* __restrict__ homo) {
+// auto min-read-support rule (placement.cpp:931-955).  Four independent 16-byte loads in flight per thread.
+__global__ void __launch_bounds__(256) table_stats(TableSlot* table, u64 cap, SampleAcc* acc, const u64* __restrict__ homo) {
     const u64 h0 = homo[0], h1 = homo[1], h2 = homo[2], h3 = homo[3];
     long long ms = 0, mc = 0, en = 0;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) {
-        const u64 k = keys[i];
-        if (k == kEmptyKey) continue;
-        if (k == h0 || k == h1 || k == h2 || k == h3) { counts[i] = 0; continue; }
-        const long long c = counts[i];
-        if (c > 0) { ++en; if (c >= 2) { ms += c; ++mc; } }
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < cap; i0 += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const u64 i = i0 + q * stride; v[q] = i < cap ? ldSlot(table, i) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u64 k = slotKey(v[q]);
+            if (k == kEmptyKey) continue;
+            if (k == h0 || k == h1 || k == h2 || k == h3) { table[i0 + q * stride].count = 0; continue; }
+            const long long c = v[q].z;
+            if (c > 0) { ++en; if (c >= 2) { ms += c; ++mc; } }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {
         const long long c = acc->emptyKeyCount; ++en; if (c >= 2) { ms += c; ++mc; }
@@ -460,54 +529,100 @@ __device__ __forceinline__ long long resolveMinSupport(const SampleAcc* acc, int
     return est > 3.0 ? 2 : 1;
 }
 
-// pass 2: computeReadSeedMagnitudes (placement.cpp:957-984) + scatter of log1p(count) to the seed-id array
+// pass 2: computeReadSeedMagnitudes (placement.cpp:957-984) + scatter of log1p(count) to the seed-id array.
+// The table is streamed with four independent 16-byte loads per thread; the seeds that survive the min-support filter
+// (a small minority at high coverage) are compacted per warp through a shared-memory queue and then handled 32 at a time
+// with every lane busy: log1p table, exact sums, count histogram, dictionary probe, scatter.
 constexpr int kHistSmem = 2048;
+struct FinalizeAcc { fx128 mag, lsum; long long kept; u32 maxc; };
+__device__ __forceinline__ u32 finalizeKept(const DevIndexView& I, const WorkspaceView& W, u64 k, u32 c, FinalizeAcc& A, unsigned* sHist) {
+    const double l = c < (u32)kLog1pLut ? __ldg(&I.log1pLut[c]) : log1p((double)c);
+    ++A.kept; A.maxc = max(A.maxc, c);
+    if (c < (u32)kLog1pLut) { if (c < (u32)kHistSmem) atomicAdd(&sHist[c], 1u); else atomicAdd(&W.countHist[c], 1u); }
+    A.mag = fxAdd(A.mag, fxFromDouble(l * l));
+    A.lsum = fxAdd(A.lsum, fxFromDouble(l));
+    if (k == kEmptyKey) return kNone;
+    u64 s = mixKey(k) & I.dictMask;
+    while (true) {  // is this seed anywhere in the index?
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(I.dict) + s);
+        const u64 dk = (u64)d.x | ((u64)d.y << 32);
+        if (dk == k) { W.ell[d.z] = l; return d.z; }
+        if (dk == kEmptyKey) return kNone;
+        s = (s + 1) & I.dictMask;
+    }
+}
+// one atomic per warp for the list of touched seed ids (reset_ell clears exactly these after the sample)
+__device__ __forceinline__ void appendTouched(const WorkspaceView& W, u32 id, unsigned activeMask) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned m = __ballot_sync(activeMask, id != kNone);
+    if (!m) return;
+    unsigned base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(&W.acc->touchedCount, (unsigned)__popc(m));
+    base = __shfl_sync(activeMask, base, leader);
+    if (id != kNone) {
+        const unsigned t = base + __popc(m & ((1u << lane) - 1u));
+        if (t < W.touchedCap) W.touched[t] = id; else W.acc->overflow = 1;
+    }
+}
 __global__ void __launch_bounds__(256) table_finalize(DevIndexView I, WorkspaceView W, int configuredMinSupport) {
     __shared__ unsigned sHist[kHistSmem];
+    __shared__ u64 sQKey[8][64];
+    __shared__ u32 sQCnt[8][64];
     for (int i = threadIdx.x; i < kHistSmem; i += blockDim.x) sHist[i] = 0;
     __syncthreads();
     SampleAcc* acc = W.acc;
-    const long long minSup = resolveMinSupport(acc, configuredMinSupport);
-    fx128 mag = fxZero(), lsum = fxZero();
-    long long kept = 0, total = 0, uniq = 0;
+    const u32 minSup = (u32)resolveMinSupport(acc, configuredMinSupport);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    FinalizeAcc A; A.mag = fxZero(); A.lsum = fxZero(); A.kept = 0; A.maxc = 0;
+    long long total = 0, uniq = 0;
+    unsigned qn = 0;  // warp-uniform queue fill
     const u64 cap = W.tableCap;
-    const bool extra = (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0);
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap + (extra ? 1 : 0); i += (u64)gridDim.x * blockDim.x) {
-        u64 k; long long c;
-        if (i < cap) { k = W.keys[i]; if (k == kEmptyKey) continue; c = W.counts[i]; }
-        else { k = kEmptyKey; c = acc->emptyKeyCount; }
-        if (c <= 0) continue;
-        total += c; ++uniq;
-        if (c < minSup) continue;
-        const double l = c < kLog1pLut ? __ldg(&I.log1pLut[c]) : log1p((double)c);
-        ++kept;
-        if (c < kLog1pLut) {
-            if (c < kHistSmem) atomicAdd(&sHist[c], 1u); else atomicAdd(&W.countHist[c], 1u);
-        }
-        mag = fxAdd(mag, fxFromDouble(l * l));
-        lsum = fxAdd(lsum, fxFromDouble(l));
-        // dictionary probe: is this seed anywhere in the index?
-        u64 s = mixKey(k) & I.dictMask;
-        while (true) {
-            const u64 dk = __ldg(&I.dictKeys[s]);
-            if (dk == k) {
-                const u32 id = __ldg(&I.dictVals[s]);
-                if (id != kNone) {
-                    W.ell[id] = l;
-                    const unsigned t = atomicAdd(&acc->touchedCount, 1u);
-                    if (t < W.touchedCap) W.touched[t] = id; else acc->overflow = 1;
+    const u64 warpsTotal = (u64)gridDim.x * 8;
+    const u64 gw = (u64)blockIdx.x * 8 + warp;
+    for (u64 base = gw * 128; base < cap; base += warpsTotal * 128) {
+        uint4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const u64 i = base + q * 32 + lane; v[q] = i < cap ? ldSlot(W.table, i) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u64 k = slotKey(v[q]); const u32 c = v[q].z;
+            const bool occ = k != kEmptyKey && c > 0;
+            if (occ) { total += c; ++uniq; }
+            const bool kept = occ && c >= minSup;
+            const unsigned m = __ballot_sync(0xffffffffu, kept);
+            if (m) {
+                if (kept) { const unsigned o = qn + __popc(m & ((1u << lane) - 1u)); sQKey[warp][o] = k; sQCnt[warp][o] = c; }
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    qn -= 32;
+                    const u32 id = finalizeKept(I, W, sQKey[warp][qn + lane], sQCnt[warp][qn + lane], A, sHist);
+                    appendTouched(W, id, 0xffffffffu);
+                    __syncwarp();
                 }
-                break;
             }
-            if (__ldg(&I.dictVals[s]) == kNone && dk == kEmptyKey) break;
-            s = (s + 1) & I.dictMask;
         }
+    }
+    {
+        u32 id = kNone;
+        if (lane < qn) id = finalizeKept(I, W, sQKey[warp][lane], sQCnt[warp][lane], A, sHist);
+        appendTouched(W, id, 0xffffffffu);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {
+        const u32 c = (u32)acc->emptyKeyCount;
+        total += c; ++uniq;
+        if (c >= minSup) finalizeKept(I, W, kEmptyKey, c, A, sHist);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kHistSmem; i += blockDim.x) if (sHist[i]) atomicAdd(&W.countHist[i], sHist[i]);
-    mag = fxWarpSum(mag); lsum = fxWarpSum(lsum);
-    kept = warpSumLL(kept); total = warpSumLL(total); uniq = warpSumLL(uniq);
-    if ((threadIdx.x & 31) == 0) {
+    const fx128 mag = fxWarpSum(A.mag), lsum = fxWarpSum(A.lsum);
+    const long long kept = warpSumLL(A.kept); total = warpSumLL(total); uniq = warpSumLL(uniq);
+    unsigned mx = A.maxc;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (lane == 0) {
+        if (mx) atomicMax((unsigned long long*)&acc->maxKeptCount, (unsigned long long)mx);
         fxAtomicAdd(acc->magSq, mag); fxAtomicAdd(acc->logSum, lsum);
         if (kept) atomicAdd((unsigned long long*)&acc->kept, (unsigned long long)kept);
         if (total) atomicAdd((unsigned long long*)&acc->total, (unsigned long long)total);
@@ -534,32 +649,21 @@ __global__ void __launch_bounds__(256) root_denominator(DevIndexView I, Workspac
 // read counts: while the running sum is in binade [2^e, 2^(e+1)) every addition of x is rounded to a multiple of
 // u = 2^(e-52), i.e. contributes rint(x/u)*u - x, and a fraction (hi-lo)/T of the additions happens in that binade.
 // Adding it to the exact fixed-point sum reproduces the reference's value to ~1e-14 relative.
-__device__ double sequentialDrift(const unsigned* __restrict__ hist, const double* __restrict__ lut, double T, bool squared,
-                                  double* sRed) {
-    double e = 0.0;
-    if (T > 0.0) {
-        const int eTop = (int)((dblBits(T) >> 52) & 0x7FF) - 1023;
-        double fr[20], u[20], iu[20];  // share of the additions that land in each binade, its ulp and 1/ulp
+constexpr int kBinades = 10;  // each lower binade carries 1/4 of the drift of the one above it
+struct Binades { double fr[kBinades], u[kBinades], iu[kBinades]; };
+__device__ __forceinline__ void makeBinades(double T, Binades& B) {
+    const int eTop = (int)((dblBits(T) >> 52) & 0x7FF) - 1023;
 #pragma unroll
-        for (int j = 0; j < 20; ++j) {
-            const int ex = eTop - j;
-            const double lo = j == 19 ? 0.0 : bitsDbl((u64)(ex + 1023) << 52);
-            const double hi = fmin(T, bitsDbl((u64)(ex + 1024) << 52));
-            fr[j] = (hi - lo) / T;
-            u[j] = bitsDbl((u64)(ex - 52 + 1023) << 52);
-            iu[j] = bitsDbl((u64)(52 - ex + 1023) << 52);
-        }
-        for (int c = threadIdx.x; c < kLog1pLut; c += blockDim.x) {
-            const unsigned m = hist[c];
-            if (!m) continue;
-            double x = lut[c];
-            if (squared) x = x * x;
-            double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < 20; ++j) acc += fr[j] * (rint(x * iu[j]) * u[j] - x);
-            e += acc * (double)m;
-        }
+    for (int j = 0; j < kBinades; ++j) {   // share of the additions that land in each binade, its ulp and 1/ulp
+        const int ex = eTop - j;
+        const double lo = j == kBinades - 1 ? 0.0 : bitsDbl((u64)(ex + 1023) << 52);
+        const double hi = fmin(T, bitsDbl((u64)(ex + 1024) << 52));
+        B.fr[j] = (hi - lo) / T;
+        B.u[j] = bitsDbl((u64)(ex - 52 + 1023) << 52);
+        B.iu[j] = bitsDbl((u64)(52 - ex + 1023) << 52);
     }
+}
+__device__ __forceinline__ double blockSumF64(double e, double* sRed) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) e += shflXorF64(e, d);
     __syncthreads();
@@ -577,8 +681,26 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
     fx128 l; l.lo = a->logSum[0]; l.hi = (i64)a->logSum[1];
     fx128 w; w.lo = a->wcDen[0]; w.hi = (i64)a->wcDen[1];
     const double magSqExact = fxToDouble(m), logSumExact = fxToDouble(l);
-    const double dMag = sequentialDrift(W.countHist, I.log1pLut, magSqExact, true, sRed);
-    const double dLog = sequentialDrift(W.countHist, I.log1pLut, logSumExact, false, sRed);
+    double eMag = 0.0, eLog = 0.0;
+    if (logSumExact > 0.0 && magSqExact > 0.0) {
+        Binades BM, BL;
+        makeBinades(magSqExact, BM); makeBinades(logSumExact, BL);
+        const int cMax = (int)min((long long)kLog1pLut - 1, a->maxKeptCount);
+        for (int c = threadIdx.x; c <= cMax; c += blockDim.x) {
+            const unsigned mult = W.countHist[c];
+            if (!mult) continue;
+            const double x = I.log1pLut[c], x2 = x * x;
+            double am = 0.0, al = 0.0;
+#pragma unroll
+            for (int j = 0; j < kBinades; ++j) {
+                am += BM.fr[j] * (rint(x2 * BM.iu[j]) * BM.u[j] - x2);
+                al += BL.fr[j] * (rint(x * BL.iu[j]) * BL.u[j] - x);
+            }
+            eMag += am * (double)mult; eLog += al * (double)mult;
+        }
+    }
+    const double dMag = blockSumF64(eMag, sRed);
+    const double dLog = blockSumF64(eLog, sRed);
     if (threadIdx.x != 0) return;
     SampleScalars S;
     S.readMagnitude = sqrt(magSqExact + dMag);
@@ -596,11 +718,9 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
 }
 
 void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, cudaStream_t st) {
-    u64 g = (W.tableCap + 255) / 256; if (g > 148 * 16) g = 148 * 16;
     cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
-    table_stats<<<(unsigned)g, 256, 0, st>>>(W.keys, W.counts, W.tableCap, W.acc, homo);
-    u64 gf = g > 148 * 8 ? 148 * 8 : g;
-    table_finalize<<<(unsigned)gf, 256, 0, st>>>(I, W, O.minReadSupport);
+    table_stats<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W.table, W.tableCap, W.acc, homo);
+    table_finalize<<<streamGrid(W.tableCap, 8), 256, 0, st>>>(I, W, O.minReadSupport);
     if (I.hasRoot && I.rootDCount) {
         u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
         root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);
@@ -668,18 +788,31 @@ __global__ void __launch_bounds__(256) node_deltas(DevIndexView I, WorkspaceView
     __syncthreads();
     for (u32 ti = blockIdx.x; ti < I.nK1Tiles; ti += gridDim.x) {
         const K1Tile t = I.k1Tiles[ti];
-        for (u32 i = tid; i < t.dCount; i += 256) {
-            const u32 pc = __ldg(&I.pc[t.dBegin + i]);
-            const int p = (int)(short)(pc & 0xFFFFu), c = (int)(short)(pc >> 16);
-            double v = 0.0;
-            if (p != c) {
-                const double lr = ell[__ldg(&I.seedId[t.dBegin + i])];
-                if (lr > 0.0) {
-                    if ((unsigned)p <= 1u && (unsigned)c <= 1u) v = c > p ? lr : -lr;
-                    else v = __longlong_as_double(0x7FF8000000000000LL);
+        {   // 16 deltas per thread, all loads issued before the first use: pc + seedId (coalesced), then the ell gathers
+            u32 pcv[16], idv[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const u32 i = tid + q * 256;
+                const bool in = i < t.dCount;
+                pcv[q] = in ? __ldcs(&I.pc[t.dBegin + i]) : 0u;
+                idv[q] = in ? __ldcs(&I.seedId[t.dBegin + i]) : 0u;
+            }
+            double lv[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) lv[q] = (tid + q * 256 < t.dCount) ? __ldg(&ell[idv[q]]) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const u32 i = tid + q * 256;
+                if (i < t.dCount) {
+                    const int p = (int)(short)(pcv[q] & 0xFFFFu), c = (int)(short)(pcv[q] >> 16);
+                    double v = 0.0;
+                    if (p != c && lv[q] > 0.0) {
+                        if ((unsigned)p <= 1u && (unsigned)c <= 1u) v = c > p ? lv[q] : -lv[q];
+                        else v = __longlong_as_double(0x7FF8000000000000LL);
+                    }
+                    sV[i] = v;
                 }
             }
-            sV[i] = v;
         }
         __syncthreads();
         if (t.kind == 0) {

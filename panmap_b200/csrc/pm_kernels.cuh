@@ -27,6 +27,8 @@ struct K1Tile {
     u32 bigNode;    // kind 1: index into bigNodes
 };
 struct BigNode { u32 localNode, firstPartial, nPartials, pad; };
+struct __align__(16) TableSlot { u64 key; u32 count; u32 pad; };  // read seed table: one 16-byte slot = one 32-byte sector half
+struct __align__(16) DictSlot { u64 key; u32 id; u32 pad; };       // index dictionary: seed hash -> dense seed id
 
 struct Acc5 {  // exact accumulator of the 5 per-node numerators
     fx128 f[4];  // raw, cos, wc, cont
@@ -35,7 +37,7 @@ struct Acc5 {  // exact accumulator of the 5 per-node numerators
 
 struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample)
     u64 magSq[2], logSum[2], wcDen[2];  // fx128 as (lo, hi)
-    long long kept, total, unique, multiSum, multiCount, entries, overflow, emptyKeyCount;
+    long long kept, total, unique, multiSum, multiCount, entries, maxKeptCount, overflow, emptyKeyCount;
     unsigned touchedCount, pad0;
     unsigned recordCount[8];
     unsigned tieCount[8];
@@ -76,7 +78,7 @@ struct DevIndexView {
     const u32* bfsRanks;   // [nShardNodes] their global BFS ranks
     u32 nShardNodes; u32 nBfsBlocks;
     // dictionary: seed hash -> seed id
-    const u64* dictKeys; const u32* dictVals; u64 dictMask;
+    const DictSlot* dict; u64 dictMask;
     const u64* dictHash;   // [nSeeds] id -> hash
     // root's deltas (for the weighted-containment denominator): local range of global node 0
     u64 rootDBegin; u32 rootDCount; u32 hasRoot;
@@ -87,7 +89,7 @@ struct DevIndexView {
 
 struct WorkspaceView {
     // read table
-    u64* keys; u32* counts; u64 tableMask; u64 tableCap;
+    TableSlot* table; u64 tableMask; u64 tableCap;
     SampleAcc* acc;
     u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
     double* ell;          // [nSeeds] log1p(read count) of seed id, 0 when absent
@@ -115,7 +117,8 @@ struct PlaceOpts {
 };
 
 // launches (all asynchronous on `st`)
-void launchPackReads(const char* reads, const u64* off, const u64* packedOff, u64 nReads, u64 nChunks, uint4* packed, cudaStream_t st);
+void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 nChunks, uint4* packed,
+                     cudaStream_t st);
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st);
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,

@@ -151,3 +151,15 @@ def test_sharded_scoring_is_identical_to_single_shard():
             full = scores
         else:
             assert np.array_equal(scores, full)
+
+
+def test_many_empty_reads_between_real_ones():
+    """runs of zero-length reads (more than a pack block can index locally) must not disturb the chunk -> read mapping"""
+    rng = np.random.default_rng(21)
+    reads = []
+    for r in H.random_reads(rng, 40, lo=40, hi=150):
+        reads.append(r)
+        reads.extend([b""] * int(rng.integers(0, 700)))
+    got = pm.read_seeds(reads, 19, 8, 0, 3)
+    for r, g in zip(reads, got):
+        assert np.array_equal(g, cpu.read_seeds(r, 19, 8, 0, 3))
