@@ -175,6 +175,15 @@ int pm_stage_select(pm_workspace* ws, const uint32_t* counts /* [5] */, const ui
                     const uint32_t* const* node /* [5] */, const double* const* score /* [5] */, uint64_t total_reads,
                     pm_place_result* result);
 
+/* placement::placeLite through the C++ host shim (panmap_b200/host/placement.hpp): FASTA/FASTQ(.gz) files in, result + <out_tsv> out.
+ * node_ids = LiteNode ids by DFS index (for the TSV); err receives the exception text on failure. */
+int pm_place_files(pm_index* idx, pm_workspace* ws, const char* const* node_ids, uint64_t n_ids, const char* reads1, const char* reads2,
+                   const char* out_tsv, const pm_place_params* params, pm_place_result* result, char* err, uint64_t err_cap);
+
+/* extractReadSequences (placement.cpp:164-197) alone: malloc'd bases/offsets of reads1 (+ reads2, pairs interleaved); free with pm_free */
+int pm_read_fastx(const char* reads1, const char* reads2, char** bases, uint64_t** offsets, uint64_t* n_reads, char* err, uint64_t err_cap);
+void pm_free(void* p);
+
 /* reference BFS visit rank of every node (children ascending, level by level; placement.cpp:742-827) */
 int pm_index_bfs_ranks(const pm_index* idx, uint32_t* out /* [n_nodes] */);
 

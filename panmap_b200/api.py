@@ -108,6 +108,10 @@ def lib():
     L.pm_stage_records_size.argtypes = [C.c_void_p, C.c_int]
     L.pm_stage_records_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_stage_select.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceResult)]
+    L.pm_read_fastx.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64]
+    L.pm_free.argtypes = [C.c_void_p]
+    L.pm_place_files.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(PlaceParams),
+                                 C.POINTER(PlaceResult), C.c_char_p, C.c_uint64]
     L.pm_host_alloc.restype = C.c_void_p
     L.pm_host_alloc.argtypes = [C.c_uint64]
     L.pm_host_free.argtypes = [C.c_void_p]
@@ -400,3 +404,31 @@ def read_seeds(seqs, k, s, t, l, open=False, trim_start=0, trim_end=0, device=0)
     sp = SeedParams(k, s, t, l, int(bool(open)), 0)
     _ck(lib().pm_read_seeds(device, _ptr(buf), off.ctypes.data_as(C.c_void_p), n, C.byref(sp), trim_start, trim_end, _ptr(h), _ptr(c)))
     return [h[woff[i]:woff[i] + int(c[i])] for i in range(n)]
+
+
+def read_fastx(reads1, reads2=""):
+    """extractReadSequences (placement.cpp:164-197) of the C++ host shim: (uint8 bases, uint64 offsets)"""
+    b, o, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+    err = C.create_string_buffer(512)
+    rc = lib().pm_read_fastx(os.fsencode(reads1), os.fsencode(reads2), C.byref(b), C.byref(o), C.byref(n), err, 512)
+    if rc < 0:
+        raise PanmapError(rc, err.value.decode(errors="replace"))
+    off = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_uint64)), shape=(n.value + 1,)).copy()
+    tot = int(off[-1])
+    buf = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint8)), shape=(max(tot, 1),))[:tot].copy()
+    lib().pm_free(b); lib().pm_free(o)
+    return buf, off
+
+
+def place_files(workspace, reads1, reads2="", out_tsv="", params=None):
+    """placement::placeLite through the C++ host shim (files in, TSV out); returns the PlaceResult struct"""
+    params = params or PlaceParams()
+    ids = workspace.index.host.node_ids or []
+    arr = (C.c_char_p * max(len(ids), 1))(*[i.encode() for i in ids])
+    res = PlaceResult()
+    err = C.create_string_buffer(512)
+    rc = lib().pm_place_files(workspace.index._h, workspace._h, arr, len(ids), os.fsencode(reads1), os.fsencode(reads2), os.fsencode(out_tsv),
+                              C.byref(params), C.byref(res), err, 512)
+    if rc < 0:
+        raise PanmapError(rc, err.value.decode(errors="replace"))
+    return res

@@ -353,34 +353,43 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
         const u64* __restrict__ h = synBuf + packedOff[r] * 32;
         const int nSeeds = l <= 1 ? n : (n >= l ? n - l + 1 : 0);
         u64 written = 0;
-        for (int j0 = 0; j0 < nSeeds; j0 += 32) {
-            const int j = j0 + (int)lane;
-            bool has = false; u64 seed = 0;
-            if (j < nSeeds) {
-                if (l <= 1) { seed = h[j]; has = true; }
-                else if (KT > 0) {
-                    u64 fw = 0, rw = 0;
+        auto seedAt = [&](int j, u64& seed) -> bool {
+            if (j >= nSeeds) return false;
+            if (l <= 1) { seed = h[j]; return true; }
+            u64 fw = 0, rw = 0;
+            if (KT > 0) {
 #pragma unroll
-                    for (int w = 0; w < (LT > 0 ? LT : 1); ++w) {
-                        const u64 x = h[j + w];
-                        fw ^= rol64(x, (unsigned)((KT * (LT - 1 - w)) & 63));
-                        rw ^= rol64(x, (unsigned)((KT * w) & 63));
-                    }
-                    has = fw != rw; seed = umin64(fw, rw);
-                } else {
-                    u64 fw = 0, rw = 0;
-                    for (int w = 0; w < l; ++w) {
-                        const u64 x = h[j + w];
-                        fw ^= rol64(x, (unsigned)(k * (l - 1 - w)));
-                        rw ^= rol64(x, (unsigned)(k * w));
-                    }
-                    has = fw != rw; seed = umin64(fw, rw);
+                for (int w = 0; w < (LT > 0 ? LT : 1); ++w) {
+                    const u64 x = h[j + w];
+                    fw ^= rol64(x, (unsigned)((KT * (LT - 1 - w)) & 63));
+                    rw ^= rol64(x, (unsigned)((KT * w) & 63));
+                }
+            } else {
+                for (int w = 0; w < l; ++w) {
+                    const u64 x = h[j + w];
+                    fw ^= rol64(x, (unsigned)(k * (l - 1 - w)));
+                    rw ^= rol64(x, (unsigned)(k * w));
                 }
             }
-            if (MODE == 0) { if (has) tableInsert(table, mask, seed, 1u, acc); }
-            else {
-                const unsigned m = __ballot_sync(0xffffffffu, has);
-                if (has) outHash[winOff[r] + written + __popc(m & ((1u << lane) - 1u))] = seed;
+            seed = umin64(fw, rw);
+            return fw != rw;
+        };
+        for (int j0 = 0; j0 < nSeeds; j0 += 64) {
+            // two seeds per lane so that both table probes are in flight together
+            u64 s0 = 0, s1 = 0;
+            const bool h0 = seedAt(j0 + (int)lane, s0), h1 = seedAt(j0 + 32 + (int)lane, s1);
+            if (MODE == 0) {
+                u64 k0 = 0, k1 = 0, p0 = 0, p1 = 0;
+                if (h0) { p0 = mixKey(s0) & mask; k0 = *((volatile u64*)&table[p0].key); }
+                if (h1) { p1 = mixKey(s1) & mask; k1 = *((volatile u64*)&table[p1].key); }
+                if (h0) { if (k0 == s0) atomicAdd(&table[p0].count, 1u); else tableInsert(table, mask, s0, 1u, acc); }
+                if (h1) { if (k1 == s1) atomicAdd(&table[p1].count, 1u); else tableInsert(table, mask, s1, 1u, acc); }
+            } else {
+                unsigned m = __ballot_sync(0xffffffffu, h0);
+                if (h0) outHash[winOff[r] + written + __popc(m & ((1u << lane) - 1u))] = s0;
+                written += __popc(m);
+                m = __ballot_sync(0xffffffffu, h1);
+                if (h1) outHash[winOff[r] + written + __popc(m & ((1u << lane) - 1u))] = s1;
                 written += __popc(m);
             }
         }

@@ -57,3 +57,26 @@ def test_compute_fails_loudly_without_a_device():
     with pytest.raises(pm.PanmapError) as e:
         pm.rolling_syncmers([b"ACGTACGTACGTACGTACGTACGT"], 19, 8)
     assert e.value.code == -2
+
+
+@pytest.mark.skipif(not os.path.exists(H.ISOLATE_R1), reason="isolate reads not staged (oracle/_ref/data)")
+def test_fastx_ingest_matches_kseq_semantics():
+    """extractReadSequences of the C++ host shim (placement.cpp:164-197): gz FASTQ pairs interleaved, FASTA, plain FASTQ"""
+    b, o = pm.read_fastx(H.ISOLATE_R1, H.ISOLATE_R2)
+    eb, eo = pm.pack_reads(H.isolate_reads())
+    assert np.array_equal(b, eb) and np.array_equal(o, eo) and o.size - 1 == 102338
+    b, o = pm.read_fastx(os.path.join(H.REF_DATA, "MZ515733.1.fa"))
+    assert o.size - 1 == 1 and int(o[-1]) == 14942
+    with pytest.raises(pm.PanmapError):     # R1/R2 count mismatch (placement.cpp:189-192)
+        pm.read_fastx(H.ISOLATE_R1, os.path.join(H.REF_DATA, "MZ515733.1.fastq"))
+
+
+def test_fastx_ingest_small_cases(tmp_path):
+    p = tmp_path / "a.fq"
+    p.write_text("@r1 x\nACGT\nNN\n+\nIIIIII\n@r2\nGG\n+r2\n@@\n")      # multi-line sequence, '@' inside a quality line
+    b, o = pm.read_fastx(str(p))
+    assert bytes(b) == b"ACGTNNGG" and list(o) == [0, 6, 8]
+    q = tmp_path / "b.fa"
+    q.write_text(">s1\nAC\r\nGT\n>s2\n\n>s3\nTT")
+    b, o = pm.read_fastx(str(q))
+    assert bytes(b) == b"ACGTTT" and list(o) == [0, 4, 4, 6]

@@ -163,3 +163,19 @@ def test_many_empty_reads_between_real_ones():
     got = pm.read_seeds(reads, 19, 8, 0, 3)
     for r, g in zip(reads, got):
         assert np.array_equal(g, cpu.read_seeds(r, 19, 8, 0, 3))
+
+
+@pytest.mark.skipif(not os.path.exists(H.SARS_IDX), reason="reference-built sars_20000 index not staged")
+def test_place_files_through_cpp_shim_writes_the_golden_tsv(tmp_path):
+    """placement::placeLite mirror (panmap_b200/host/placement.cpp): .fastq.gz files in, <prefix>.placement.tsv out"""
+    host = pm.HostIndex.read(H.SARS_IDX)
+    ws = pm.Workspace(pm.Index(host))
+    out = str(tmp_path / "isolate.placement.tsv")
+    res = pm.place_files(ws, H.ISOLATE_R1, H.ISOLATE_R2, out)
+    assert open(out).read() == open(H.ISOLATE_TSV).read()
+    assert res.best_index[4] == 15189 and res.total_reads == 102338
+    # whole genome as ONE long read (the reference's e2e test feeds a FASTA, run_e2e.sh:50-56)
+    res = pm.place_files(ws, os.path.join(H.REF_DATA, "MZ515733.1.fa"), "", str(tmp_path / "g.tsv"))
+    buf, off = pm.read_fastx(os.path.join(H.REF_DATA, "MZ515733.1.fa"))
+    exp = cpu.place(buf, off, host)
+    assert list(res.best_index) == list(exp["best_index"])
