@@ -252,7 +252,9 @@ def main():
         "dtype": "u64+f64", "data": "synthetic",
         "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": w["n_reads"], "read_bases": nbytes, "k": S.k, "s": S.s,
                    "l": S.l, "l2": "per-step working set (reads 150 MB + packed 75 MB + count table + delta arrays) exceeds the 126 MB L2; no explicit flush",
-                   "truth_node": int(S.truth), "placed": {m: int(res.best_index[m]) for m in pm.METRICS}},
+                   "truth_node": int(S.truth), "placed": {m: int(res.best_index[m]) for m in pm.METRICS},
+                   "unique_seeds": int(res.raw.unique_seeds), "kept_seeds": int(res.raw.read_unique_seed_count),
+                   "min_read_support": int(res.raw.min_read_support), "index_distinct_seeds": int(index.num_distinct_seeds)},
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "stage_ms": {n: float(stage[i]) for i, n in enumerate(names)},
         "e2e": {"value": e2e_value, "unit": "node*reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,

@@ -168,6 +168,9 @@ int pm_stage_seed(pm_workspace* ws, const char* reads, const uint64_t* read_offs
 int64_t pm_stage_table_size(pm_workspace* ws);
 int pm_stage_table_export(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap);
 int pm_stage_table_import(pm_workspace* ws, const uint64_t* hash, const int64_t* count, uint64_t n);
+/* same exchange with DEVICE buffers owned by the caller (e.g. tensors handed to NCCL); export with d_hash == NULL only counts */
+int pm_stage_table_export_dev(pm_workspace* ws, uint64_t* d_hash, int64_t* d_count, uint64_t cap, uint64_t* n_out);
+int pm_stage_table_import_dev(pm_workspace* ws, const uint64_t* d_hash, const int64_t* d_count, uint64_t n);
 int pm_stage_score(pm_workspace* ws, const pm_place_params* params);
 int64_t pm_stage_records_size(pm_workspace* ws, int metric);
 int pm_stage_records_export(pm_workspace* ws, int metric, uint32_t* bfs_rank, uint32_t* node, double* score, uint64_t cap);

@@ -103,6 +103,8 @@ def lib():
     L.pm_stage_table_size.argtypes = [C.c_void_p]
     L.pm_stage_table_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_stage_table_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_stage_table_export_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.pm_stage_table_import_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_stage_score.argtypes = [C.c_void_p, C.POINTER(PlaceParams)]
     L.pm_stage_records_size.restype = C.c_int64
     L.pm_stage_records_size.argtypes = [C.c_void_p, C.c_int]
@@ -345,6 +347,14 @@ class Workspace:
         h = np.ascontiguousarray(h, dtype=np.uint64)
         c = np.ascontiguousarray(c, dtype=np.int64)
         _ck(lib().pm_stage_table_import(self._h, _ptr(h), _ptr(c), h.size))
+
+    def stage_table_export_dev(self, d_hash_ptr, d_count_ptr, cap):
+        n = C.c_uint64()
+        _ck(lib().pm_stage_table_export_dev(self._h, d_hash_ptr, d_count_ptr, cap, C.byref(n)))
+        return n.value
+
+    def stage_table_import_dev(self, d_hash_ptr, d_count_ptr, n):
+        _ck(lib().pm_stage_table_import_dev(self._h, d_hash_ptr, d_count_ptr, n))
 
     def stage_score(self, params):
         _ck(lib().pm_stage_score(self._h, C.byref(params)))

@@ -694,6 +694,39 @@ int pm_stage_table_import(pm_workspace* ws, const uint64_t* hash, const int64_t*
         throw std::runtime_error("table import kept overflowing");
     });
 }
+// device-pointer variants of the table exchange (the caller owns the buffers, e.g. torch CUDA tensors handed to NCCL)
+int pm_stage_table_export_dev(pm_workspace* ws, uint64_t* d_hash, int64_t* d_count, uint64_t cap, uint64_t* n_out) {
+    if (!ws || !n_out) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        CK(cudaMemsetAsync(ws->expCounter.p, 0, sizeof(unsigned), ws->st));
+        launchTableExport(ws->view, reinterpret_cast<u64*>(d_hash), reinterpret_cast<long long*>(d_count), ws->expCounter.p, d_hash ? cap : 0, ws->st);
+        unsigned cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, ws->expCounter.p, sizeof(unsigned), cudaMemcpyDeviceToHost, ws->st));
+        CK(cudaStreamSynchronize(ws->st));
+        *n_out = cnt;
+        return PM_OK;
+    });
+}
+int pm_stage_table_import_dev(pm_workspace* ws, const uint64_t* d_hash, const int64_t* d_count, uint64_t n) {
+    if (!ws || (n && (!d_hash || !d_count))) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        for (int attempt = 0; attempt < 6; ++attempt) {
+            if (ws->tableCap < 2 * n + 16) ensureTable(ws, 2 * n + 16);
+            refreshView(ws);
+            CK(cudaMemsetAsync(ws->acc.p, 0, sizeof(SampleAcc), ws->st));
+            launchTableClear(ws->view, ws->st);
+            launchTableImport(ws->view, reinterpret_cast<const u64*>(d_hash), reinterpret_cast<const long long*>(d_count), n, ws->st);
+            SampleAcc a;
+            CK(cudaMemcpyAsync(&a, ws->acc.p, sizeof(a), cudaMemcpyDeviceToHost, ws->st));
+            CK(cudaStreamSynchronize(ws->st));
+            if (!a.overflow) return PM_OK;
+            ensureTable(ws, ws->tableCap * 4);
+        }
+        throw std::runtime_error("table import kept overflowing");
+    });
+}
 int pm_stage_score(pm_workspace* ws, const pm_place_params* params) {
     if (!ws) return fail(PM_ERR_INVALID, "null argument");
     return guarded([&]() -> int {

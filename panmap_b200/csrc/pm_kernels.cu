@@ -129,7 +129,9 @@ __device__ __forceinline__ void tableInsert(TableSlot* __restrict__ table, u64 m
     if (h == kEmptyKey) { atomicAdd((unsigned long long*)&acc->emptyKeyCount, (unsigned long long)add); return; }
     u64 slot = mixKey(h) & mask;
     for (int probe = 0; probe < 8192; ++probe) {
-        u64 cur = *((volatile u64*)&table[slot].key);
+        // keys are write-once (EMPTY -> key), so a possibly stale L1 copy is safe: a stale EMPTY is resolved by the CAS, a cached
+        // non-EMPTY key is final.  Hot seeds therefore hit L1 and only the count update travels to L2.
+        u64 cur = __ldca(&table[slot].key);
         if (cur == kEmptyKey) {
             cur = atomicCAS((unsigned long long*)&table[slot].key, (unsigned long long)kEmptyKey, (unsigned long long)h);
             if (cur == kEmptyKey) cur = h;
@@ -380,8 +382,8 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
             const bool h0 = seedAt(j0 + (int)lane, s0), h1 = seedAt(j0 + 32 + (int)lane, s1);
             if (MODE == 0) {
                 u64 k0 = 0, k1 = 0, p0 = 0, p1 = 0;
-                if (h0) { p0 = mixKey(s0) & mask; k0 = *((volatile u64*)&table[p0].key); }
-                if (h1) { p1 = mixKey(s1) & mask; k1 = *((volatile u64*)&table[p1].key); }
+                if (h0) { p0 = mixKey(s0) & mask; k0 = __ldca(&table[p0].key); }
+                if (h1) { p1 = mixKey(s1) & mask; k1 = __ldca(&table[p1].key); }
                 if (h0) { if (k0 == s0) atomicAdd(&table[p0].count, 1u); else tableInsert(table, mask, s0, 1u, acc); }
                 if (h1) { if (k1 == s1) atomicAdd(&table[p1].count, 1u); else tableInsert(table, mask, s1, 1u, acc); }
             } else {
