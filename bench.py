@@ -300,8 +300,9 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
     off = S.read_offsets[lo:hi + 1] - S.read_offsets[lo]
     reads = S.reads[int(S.read_offsets[lo]):int(S.read_offsets[hi])]
     dev = torch.device("cuda", local)
+    ws.upload(reads, off)   # this rank's slice of the reads, resident in HBM before the timed region (as at N=1)
     for _ in range(max(args.warmup, 3)):
-        res = pmd.place_sharded(ws, reads, off, n, params, device=dev)
+        res = pmd.place_sharded(ws, reads, off, n, params, device=dev, resident=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -310,13 +311,23 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
     e0.record()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res = pmd.place_sharded(ws, reads, off, n, params, device=dev)
+        res = pmd.place_sharded(ws, reads, off, n, params, device=dev, resident=True)
     e1.record()
     torch.cuda.synchronize(); dist.barrier()
     wall = time.perf_counter() - t0
     ms = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
+    # e2e: the same step starting from HOST buffers on every rank (its slice of the reads is copied inside the timed region)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = pmd.place_sharded(ws, reads, off, n, params, device=dev, resident=False)
+    torch.cuda.synchronize(); dist.barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e = {"value": S.n_nodes * n / (float(e2e_ms.item()) / args.steps * 1e-3), "unit": "node*reads/s",
+           "h2d_bytes_per_step": int(reads.size + 16 * (hi - lo + 1)), "d2h_bytes_per_step": 432, "ms_per_step": float(e2e_ms.item()) / args.steps}
     if rank == 0:
         per = float(ms.item()) / args.steps
         value = S.n_nodes * n / (per * 1e-3)
@@ -326,8 +337,7 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
                 "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n, "k": S.k, "s": S.s, "l": S.l,
                            "parallelism": f"node range sharded over {world} GPUs (delta-balanced DFS ranges), reads sharded for seeding, count tables all-gathered",
                            "l2": "working set exceeds L2; no explicit flush", "placed": {m: int(res.best_index[m]) for m in pm.METRICS}, "truth_node": int(S.truth)},
-                "e2e": {"value": value, "unit": "node*reads/s", "h2d_bytes_per_step": int(reads.size + 16 * (hi - lo + 1)), "d2h_bytes_per_step": 432,
-                        "note": "the multi-GPU step starts from host buffers on every rank (its slice of the reads), so value == e2e here"},
+                "e2e": e2e,
                 "gpu_launches": (KERNELS_PER_STEP + 3) * args.steps,
                 "roofline": {"bound": "hbm", "kernel": "whole place stage", "achieved": alg["total"] / (per * 1e-3) / 1e9, "peak": float(pk["hbm_gbs"]) * world,
                              "unit": "GB/s", "frac": alg["total"] / (per * 1e-3) / 1e9 / (float(pk["hbm_gbs"]) * world), "traffic": None, "peak_source": pk_src},

@@ -165,6 +165,7 @@ int pm_read_seeds(int device, const char* seqs, const uint64_t* seq_offsets, uin
  *                                    the union over ranks of pm_get_tied() is the reference's tied list ---- */
 int pm_stage_seed(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads,
                   const pm_place_params* params);
+int pm_stage_seed_resident(pm_workspace* ws, const pm_place_params* params); /* reads laid out earlier by pm_reads_upload */
 int64_t pm_stage_table_size(pm_workspace* ws);
 int pm_stage_table_export(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap);
 int pm_stage_table_import(pm_workspace* ws, const uint64_t* hash, const int64_t* count, uint64_t n);

@@ -99,6 +99,7 @@ def lib():
     L.pm_read_seeds.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SeedParams), C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p]
     L.pm_stage_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams)]
+    L.pm_stage_seed_resident.argtypes = [C.c_void_p, C.POINTER(PlaceParams)]
     L.pm_stage_table_size.restype = C.c_int64
     L.pm_stage_table_size.argtypes = [C.c_void_p]
     L.pm_stage_table_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
@@ -334,6 +335,9 @@ class Workspace:
         reads = np.ascontiguousarray(reads, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         _ck(lib().pm_stage_seed(self._h, _ptr(reads), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params)))
+
+    def stage_seed_resident(self, params):
+        _ck(lib().pm_stage_seed_resident(self._h, C.byref(params)))
 
     def stage_table_export(self):
         n = _ck(lib().pm_stage_table_size(self._h))

@@ -94,12 +94,13 @@ struct pm_index {
 
 struct pm_workspace {
     pm_index* idx = nullptr;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev[9]{};
+    cudaStream_t st = nullptr, stCopy = nullptr;
+    cudaEvent_t ev[9]{}, evCopy[8]{};
     // inputs
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
     u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
+    bool residentValid = false;  // the device copy of the reads was laid out by pm_reads_upload (not by the sliced pm_place path)
     // table
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0;
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
@@ -266,6 +267,54 @@ void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n)
     CK(cudaMemcpyAsync(W->blockFirst.p, W->hBlockFirst.p, ((W->nChunks + 255) / 256 + 1) * sizeof(u32), cudaMemcpyHostToDevice, W->st));
 }
 
+// Host buffers -> table, pipelined: the sample is cut into slices of reads; slice i+1 is copied (copy stream) while slice i is
+// packed, seeded and counted (compute stream).  Host-side chunk offsets of a slice are computed just before its copy.
+void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* off, u64 n, const pm_place_params& prm) {
+    pm_index* I = W->idx;
+    const int k = I->F.sp.k;
+    if (n && off[0] != 0) throw std::runtime_error("read_offsets[0] must be 0");
+    const u64 total = n ? off[n] : 0;
+    const int nSlices = n >= (1u << 16) ? 6 : 1;
+    W->nReads = n; W->totalBases = total;
+    W->hPackedOff.ensure(n + 1); W->hBlockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 16);
+    W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
+    W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1);
+    W->blockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 16);
+    if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, (total > (u64)k * n ? total - (u64)(k - 1) * n : 0) / 4));
+    refreshView(W);
+    const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
+    CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
+    launchTableClear(W->view, W->st);
+    u64 chunkAcc = 0, win = 0, bfBase = 0;
+    for (int sl = 0; sl < nSlices; ++sl) {
+        const u64 r0 = n * sl / nSlices, r1 = n * (sl + 1) / nSlices;
+        if (r1 == r0) continue;
+        const u64 gBase = chunkAcc;
+        for (u64 i = r0; i < r1; ++i) {
+            if (off[i + 1] < off[i]) throw std::runtime_error("read offsets not monotone");
+            const u64 L = off[i + 1] - off[i];
+            if (L > 0x7FFFFFF0ull) throw std::runtime_error("read longer than 2^31 bases");
+            W->hPackedOff.p[i] = chunkAcc;
+            chunkAcc += (L + 31) >> 5;
+            if (L >= (u64)k) win += L - (u64)k + 1;
+        }
+        W->hPackedOff.p[r1] = chunkAcc;
+        const u64 nCh = chunkAcc - gBase, nBlk = (nCh + 255) / 256;
+        packBlockFirst(W->hPackedOff.p + r0, r1 - r0, nCh, W->hBlockFirst.p + bfBase);
+        const u64 b0 = off[r0], b1 = off[r1];
+        if (b1 > b0) CK(cudaMemcpyAsync(W->reads.p + b0, reads + b0, b1 - b0, cudaMemcpyHostToDevice, W->stCopy));
+        CK(cudaMemcpyAsync(W->off.p + r0, off + r0, (r1 - r0 + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->stCopy));
+        CK(cudaMemcpyAsync(W->packedOff.p + r0, W->hPackedOff.p + r0, (r1 - r0 + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->stCopy));
+        CK(cudaMemcpyAsync(W->blockFirst.p + bfBase, W->hBlockFirst.p + bfBase, (nBlk + 1) * sizeof(u32), cudaMemcpyHostToDevice, W->stCopy));
+        CK(cudaEventRecord(W->evCopy[sl], W->stCopy));
+        CK(cudaStreamWaitEvent(W->st, W->evCopy[sl], 0));
+        launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st);
+        launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st);
+        bfBase += nBlk + 1;
+    }
+    W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false;
+}
+
 void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
     pm_index* I = W->idx;
     const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
@@ -273,7 +322,7 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
         launchTableClear(W->view, W->st);
     }
-    launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, W->nChunks, W->packed.p, W->st);
+    launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st);
     launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st);
 }
 
@@ -351,8 +400,7 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
     W->lastParams = *prm;
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaEventRecord(W->ev[0], W->st));
-        if (!inputsResident) uploadReads(W, reads, off, n);
-        if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, W->totalWindows / 4));
+        if (W->tableCap == 0 && inputsResident) ensureTable(W, std::max<u64>(1 << 16, W->totalWindows / 4));
         else if (W->lastEntries && W->tableCap > (1u << 16) && W->tableCap > 4 * W->lastEntries) {
             // the previous sample filled under a quarter of the slots: every pass over the table is cheaper with a tighter one
             u64 cap = 1 << 16;
@@ -361,7 +409,8 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
         }
         refreshView(W);
         CK(cudaEventRecord(W->ev[1], W->st));
-        stageSeed(W, true, *prm);
+        if (inputsResident) stageSeed(W, true, *prm);
+        else uploadAndSeedPipelined(W, reads, off, n, *prm);   // H2D of the slices overlaps pack + seeding of earlier slices
         CK(cudaEventRecord(W->ev[2], W->st));
         stageScore(W, *prm);
         launchChain(W->view, nullptr, W->st);
@@ -457,7 +506,9 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         std::unique_ptr<pm_workspace> W(new pm_workspace());
         W->idx = idx;
         CK(cudaStreamCreateWithFlags(&W->st, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&W->stCopy, cudaStreamNonBlocking));
         for (auto& e : W->ev) CK(cudaEventCreate(&e));
+        for (auto& e : W->evCopy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
         W->acc.alloc(1); W->scalars.alloc(1); W->sel.alloc(5);
@@ -487,7 +538,9 @@ void pm_workspace_destroy(pm_workspace* ws) {
     if (!ws) return;
     cudaSetDevice(ws->idx->device);
     if (ws->st) { cudaStreamSynchronize(ws->st); cudaStreamDestroy(ws->st); }
+    if (ws->stCopy) { cudaStreamSynchronize(ws->stCopy); cudaStreamDestroy(ws->stCopy); }
     for (auto& e : ws->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ws->evCopy) if (e) cudaEventDestroy(e);
     delete ws;
 }
 
@@ -502,11 +555,13 @@ int pm_reads_upload(pm_workspace* ws, const char* reads, const uint64_t* read_of
         setDevice(ws->idx->device);
         uploadReads(ws, reads, read_offsets, n_reads);
         CK(cudaStreamSynchronize(ws->st));
+        ws->residentValid = true;
         return PM_OK;
     });
 }
 int pm_place_resident(pm_workspace* ws, const pm_place_params* params, pm_place_result* result) {
     if (!ws) return fail(PM_ERR_INVALID, "null argument");
+    if (!ws->residentValid) return fail(PM_ERR_INVALID, "pm_place_resident: call pm_reads_upload first");
     return guarded([&]() -> int { return runPlace(ws, params, result, true, nullptr, nullptr, 0); });
 }
 
@@ -607,7 +662,7 @@ static int seedListImpl(int device, const char* seqs, const uint64_t* off, uint6
         packBlockFirst(pOff.data(), n, ch, bf.data());
         DevBuf<u32> dBF; dBF.alloc(bf.size());
         CK(cudaMemcpyAsync(dBF.p, bf.data(), bf.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
-        launchPackReads(dReads.p, dOff.p, dPOff.p, dBF.p, n, ch, dPacked.p, st);
+        launchPackReads(dReads.p, dOff.p, dPOff.p, dBF.p, n, 0, ch, dPacked.p, st);
         launchSeedList(dPacked.p, dOff.p, dPOff.p, dWOff.p, n, P, dT.p, mode, dSyn.p, dSynCount.p, dHash.p, dRev.p, dPos.p, dCount.p, st);
         CK(cudaGetLastError());
         if (win) CK(cudaMemcpyAsync(outHash, dHash.p, win * 8, cudaMemcpyDeviceToHost, st));
@@ -632,25 +687,35 @@ int pm_read_seeds(int device, const char* seqs, const uint64_t* seq_offsets, uin
 }
 
 // ---- staged entry points (multi-GPU) ----
-int pm_stage_seed(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads, const pm_place_params* params) {
-    if (!ws || !read_offsets || (!reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");
+static int stageSeedImpl(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads, const pm_place_params* params,
+                         bool resident) {
     return guarded([&]() -> int {
         setDevice(ws->idx->device);
         checkParams(params);
         ws->lastParams = *params; ws->wantMetrics = false; ws->haveResult = false;
-        uploadReads(ws, reads, read_offsets, n_reads);
+        if (!resident) uploadReads(ws, reads, read_offsets, n_reads);
         if (ws->tableCap == 0) ensureTable(ws, std::max<u64>(1 << 16, ws->totalWindows / 4));
         refreshView(ws);
-        stageSeed(ws, true, *params);
-        CK(cudaStreamSynchronize(ws->st));
-        SampleAcc a; CK(cudaMemcpy(&a, ws->acc.p, sizeof(a), cudaMemcpyDeviceToHost));
-        if (a.overflow) {  // grow and reseed
-            ensureTable(ws, ws->tableCap * 4);
+        for (int attempt = 0; attempt < 6; ++attempt) {
             stageSeed(ws, true, *params);
+            SampleAcc a;
+            CK(cudaMemcpyAsync(&a, ws->acc.p, sizeof(a), cudaMemcpyDeviceToHost, ws->st));
             CK(cudaStreamSynchronize(ws->st));
+            if (!a.overflow) return PM_OK;
+            ensureTable(ws, ws->tableCap * 4);   // grow and reseed
         }
-        return PM_OK;
+        throw std::runtime_error("read seed table kept overflowing");
     });
+}
+int pm_stage_seed(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads, const pm_place_params* params) {
+    if (!ws || !read_offsets || (!reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");
+    return stageSeedImpl(ws, reads, read_offsets, n_reads, params, false);
+}
+// same, on the reads previously laid out by pm_reads_upload ("inputs resident in HBM")
+int pm_stage_seed_resident(pm_workspace* ws, const pm_place_params* params) {
+    if (!ws) return fail(PM_ERR_INVALID, "null argument");
+    if (!ws->residentValid) return fail(PM_ERR_INVALID, "pm_stage_seed_resident: call pm_reads_upload first");
+    return stageSeedImpl(ws, nullptr, nullptr, 0, params, true);
 }
 int64_t pm_stage_table_size(pm_workspace* ws) {
     if (!ws) return fail(PM_ERR_INVALID, "null argument");

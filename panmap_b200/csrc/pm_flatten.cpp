@@ -23,12 +23,14 @@ namespace pm {
 static constexpr uint32_t kTileDeltasH = 4096, kTileNodesK1H = 2048, kTileNodesK2H = 512;
 static constexpr uint32_t NONE = 0xFFFFFFFFu;
 
-// for every block of 256 packed chunks: the read r with packedOff[r] <= firstChunk < packedOff[r+1]
+// for every block of 256 packed chunks counted from chunk gBase (= packedOff[0] of the slice): the slice-local read r with
+// packedOff[r] <= firstChunk < packedOff[r+1]
 void packBlockFirst(const uint64_t* packedOff, uint64_t nReads, uint64_t nChunks, uint32_t* out) {
     uint64_t r = 0;
+    const uint64_t gBase = nReads ? packedOff[0] : 0;
     const uint64_t nBlocks = (nChunks + 255) / 256;
     for (uint64_t b = 0; b < nBlocks; ++b) {
-        const uint64_t g = b * 256;
+        const uint64_t g = gBase + b * 256;
         while (r + 1 < nReads && packedOff[r + 1] <= g) ++r;
         out[b] = static_cast<uint32_t>(r);
     }

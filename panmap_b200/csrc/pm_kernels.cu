@@ -55,12 +55,12 @@ __device__ __forceinline__ long long warpSumLL(long long v) {
 // segments, so the lines are shared through L1) and realigned with funnel shifts; base -> code via a shared 256-byte table.
 __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads, const u64* __restrict__ off,
                                                   const u64* __restrict__ packedOff, const u32* __restrict__ blockFirst, u64 nReads,
-                                                  u64 nChunks, uint4* __restrict__ packed) {
+                                                  u64 gBase, u64 nChunks, uint4* __restrict__ packed) {
     __shared__ u64 sPO[258];
     __shared__ u64 sOff[258];
     __shared__ unsigned char sLut[256];
     __shared__ u64 sFirst;
-    const u64 g0 = (u64)blockIdx.x * 256;
+    const u64 g0 = gBase + (u64)blockIdx.x * 256;   // gBase: first chunk of the read slice this launch covers
     sLut[threadIdx.x] = (unsigned char)baseCode((unsigned char)threadIdx.x);
     if (threadIdx.x == 0) sFirst = blockFirst[blockIdx.x];   // read owning this block's first chunk (computed with the chunk offsets on the host)
     __syncthreads();
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads
     }
     __syncthreads();
     const u64 g = g0 + threadIdx.x;
-    if (g >= nChunks) return;
+    if (g >= gBase + nChunks) return;
     int lo = 0, hi = 257;   // largest i with sPO[i] <= g
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -115,11 +115,11 @@ __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads
     packed[g] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 nChunks, uint4* packed,
-                     cudaStream_t st) {
+void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
+                     uint4* packed, cudaStream_t st) {
     if (nChunks == 0) return;
     const unsigned grid = (unsigned)((nChunks + 255) / 256);
-    pack_reads<<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, nChunks, packed);
+    pack_reads<<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed);
 }
 
 // ------------------------------------------------------------------------------------------------------

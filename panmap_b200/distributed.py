@@ -54,12 +54,15 @@ def exchange_tables_device(ws, device, group=None):
     return sizes
 
 
-def place_sharded(ws, reads, offsets, total_reads, params, device=None, group=None):
+def place_sharded(ws, reads, offsets, total_reads, params, device=None, group=None, resident=False):
     """reads/offsets: this rank's slice of the sample; ws: workspace over this rank's shard of the index.
     Returns the same Placement on every rank (== the single-GPU result)."""
     from .api import METRICS
     on_gpu = device is not None and getattr(device, "type", "cpu") == "cuda" and hasattr(ws, "stage_table_export_dev")
-    ws.stage_seed(reads, offsets, params)                                # A
+    if resident:
+        ws.stage_seed_resident(params)                                   # A (reads uploaded earlier with ws.upload)
+    else:
+        ws.stage_seed(reads, offsets, params)                            # A
     if on_gpu:
         exchange_tables_device(ws, device, group)                        # B (NCCL, device buffers)
     else:
