@@ -172,9 +172,13 @@ int pm_stage_table_import(pm_workspace* ws, const uint64_t* hash, const int64_t*
 /* same exchange with DEVICE buffers owned by the caller (e.g. tensors handed to NCCL); export with d_hash == NULL only counts */
 int pm_stage_table_export_dev(pm_workspace* ws, uint64_t* d_hash, int64_t* d_count, uint64_t cap, uint64_t* n_out);
 int pm_stage_table_import_dev(pm_workspace* ws, const uint64_t* d_hash, const int64_t* d_count, uint64_t n);
+/* enqueue only (no wait; an overflow surfaces in pm_stage_score); clear_first starts a new table sized for expected_total entries */
+int pm_stage_table_import_dev_async(pm_workspace* ws, const uint64_t* d_hash, const int64_t* d_count, uint64_t n, int clear_first,
+                                    uint64_t expected_total);
 int pm_stage_score(pm_workspace* ws, const pm_place_params* params);
 int64_t pm_stage_records_size(pm_workspace* ws, int metric);
 int pm_stage_records_export(pm_workspace* ws, int metric, uint32_t* bfs_rank, uint32_t* node, double* score, uint64_t cap);
+int pm_stage_records_export_all(pm_workspace* ws, uint32_t* counts /* [5] */, uint32_t* bfs_rank, uint32_t* node, double* score /* [5][cap] */, uint64_t cap);
 int pm_stage_select(pm_workspace* ws, const uint32_t* counts /* [5] */, const uint32_t* const* bfs_rank /* [5] */,
                     const uint32_t* const* node /* [5] */, const double* const* score /* [5] */, uint64_t total_reads,
                     pm_place_result* result);

@@ -106,6 +106,8 @@ def lib():
     L.pm_stage_table_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_stage_table_export_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.pm_stage_table_import_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_stage_table_import_dev_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint64]
+    L.pm_stage_records_export_all.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_stage_score.argtypes = [C.c_void_p, C.POINTER(PlaceParams)]
     L.pm_stage_records_size.restype = C.c_int64
     L.pm_stage_records_size.argtypes = [C.c_void_p, C.c_int]
@@ -359,6 +361,22 @@ class Workspace:
 
     def stage_table_import_dev(self, d_hash_ptr, d_count_ptr, n):
         _ck(lib().pm_stage_table_import_dev(self._h, d_hash_ptr, d_count_ptr, n))
+
+    def stage_table_import_dev_async(self, d_hash_ptr, d_count_ptr, n, clear_first=True, expected_total=None):
+        _ck(lib().pm_stage_table_import_dev_async(self._h, d_hash_ptr, d_count_ptr, n, int(clear_first), n if expected_total is None else expected_total))
+
+    def stage_records_all(self, cap=512):
+        """all five record lists with one device synchronisation (buffers are kept on the object)"""
+        while True:
+            b = getattr(self, "_recbuf", None)
+            if b is None or b[0] != cap:
+                b = (cap, np.zeros(5, np.uint32), np.zeros((5, cap), np.uint32), np.zeros((5, cap), np.uint32), np.zeros((5, cap), np.float64))
+                self._recbuf = b
+            _, cnt, r, v, s = b
+            _ck(lib().pm_stage_records_export_all(self._h, _ptr(cnt), _ptr(r), _ptr(v), _ptr(s), cap))
+            if int(cnt.max()) < cap:
+                return [(r[m, :cnt[m]].copy(), v[m, :cnt[m]].copy(), s[m, :cnt[m]].copy()) for m in range(5)]
+            cap = max(_ck(lib().pm_stage_records_size(self._h, m)) for m in range(5)) + 1
 
     def stage_score(self, params):
         _ck(lib().pm_stage_score(self._h, C.byref(params)))

@@ -110,10 +110,10 @@ struct pm_workspace {
     DevBuf<u64> chainA;
     DevBuf<double> scores, metrics, blockMaxAndBfs;
     DevBuf<u32> recRank, recNode; DevBuf<double> recScore; u32 recCap = 0;
-    DevBuf<u32> tieNode; u32 tieCap = 0;
+    DevBuf<u32> tieNode; u32 tieCap = 0; DevBuf<u32> selCounts;
     DevBuf<u64> expHash; DevBuf<long long> expCount; DevBuf<unsigned> expCounter;
     // host staging (pinned)
-    PinBuf<unsigned char> hStage;
+    PinBuf<unsigned char> hStage; PinBuf<u32> hTies; PinBuf<unsigned char> hRec;
     // results of the last sample
     bool haveResult = false; bool wantMetrics = false;
     pm_place_params lastParams{};
@@ -370,16 +370,21 @@ void fillResult(pm_workspace* W, pm_place_result* r, u64 totalReads) {
 
 // tie lists -> host, finalizeTiedIndices semantics (placement.cpp:395-401): sort, unique, best = front
 void fetchTies(pm_workspace* W) {
+    // one pinned staging buffer, one synchronisation
+    size_t tot = 0; unsigned n[5];
+    for (int m = 0; m < 5; ++m) { n[m] = std::min<unsigned>(W->hAcc.tieCount[m], W->tieCap); tot += n[m]; }
+    W->hTies.ensure(tot + 1);
+    size_t o = 0;
     for (int m = 0; m < 5; ++m) {
-        unsigned n = W->hAcc.tieCount[m];
-        if (n > W->tieCap) n = W->tieCap;
-        std::vector<u32>& t = W->tied[m];
-        t.assign(n, 0);
-        if (n) CK(cudaMemcpyAsync(t.data(), W->tieNode.p + (size_t)m * W->tieCap, n * sizeof(u32), cudaMemcpyDeviceToHost, W->st));
+        if (n[m]) CK(cudaMemcpyAsync(W->hTies.p + o, W->tieNode.p + (size_t)m * W->tieCap, n[m] * sizeof(u32), cudaMemcpyDeviceToHost, W->st));
+        o += n[m];
     }
-    CK(cudaStreamSynchronize(W->st));
+    if (tot) CK(cudaStreamSynchronize(W->st));
+    o = 0;
     for (int m = 0; m < 5; ++m) {
         std::vector<u32>& t = W->tied[m];
+        t.assign(W->hTies.p + o, W->hTies.p + o + n[m]);
+        o += n[m];
         const Selection& s = W->hSel[m];
         // the reference pushes bestNodeIndex (possibly UINT32_MAX before any improvement) next to every tie, and
         // an improvement leaves [node] in the list
@@ -770,6 +775,10 @@ int pm_stage_table_export_dev(pm_workspace* ws, uint64_t* d_hash, int64_t* d_cou
         CK(cudaMemcpyAsync(&cnt, ws->expCounter.p, sizeof(unsigned), cudaMemcpyDeviceToHost, ws->st));
         CK(cudaStreamSynchronize(ws->st));
         *n_out = cnt;
+        if (d_count && cnt < cap) {   // unused entries get count 0 so that importers skip them
+            CK(cudaMemsetAsync(d_count + cnt, 0, (cap - cnt) * sizeof(int64_t), ws->st));
+            CK(cudaStreamSynchronize(ws->st));
+        }
         return PM_OK;
     });
 }
@@ -790,6 +799,22 @@ int pm_stage_table_import_dev(pm_workspace* ws, const uint64_t* d_hash, const in
             ensureTable(ws, ws->tableCap * 4);
         }
         throw std::runtime_error("table import kept overflowing");
+    });
+}
+// enqueue-only variant: clears the table and inserts the pairs without waiting; an overflow is reported by pm_stage_score
+int pm_stage_table_import_dev_async(pm_workspace* ws, const uint64_t* d_hash, const int64_t* d_count, uint64_t n, int clear_first,
+                                    uint64_t expected_total) {
+    if (!ws || (n && (!d_hash || !d_count))) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        if (clear_first) {
+            if (ws->tableCap < 2 * expected_total + 16) ensureTable(ws, 2 * expected_total + 16);
+            refreshView(ws);
+            CK(cudaMemsetAsync(ws->acc.p, 0, sizeof(SampleAcc), ws->st));
+            launchTableClear(ws->view, ws->st);
+        }
+        launchTableImport(ws->view, reinterpret_cast<const u64*>(d_hash), reinterpret_cast<const long long*>(d_count), n, ws->st);
+        return PM_OK;
     });
 }
 int pm_stage_score(pm_workspace* ws, const pm_place_params* params) {
@@ -823,6 +848,33 @@ int pm_stage_records_export(pm_workspace* ws, int metric, uint32_t* bfs_rank, ui
         return PM_OK;
     });
 }
+// all five record lists with one synchronisation: arrays are [5][cap], counts[5] receives the list lengths
+int pm_stage_records_export_all(pm_workspace* ws, uint32_t* counts, uint32_t* bfs_rank, uint32_t* node, double* score, uint64_t cap) {
+    if (!ws || !counts) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        size_t tot = 0; u64 n[5];
+        for (int m = 0; m < 5; ++m) { n[m] = std::min<u64>(std::min<unsigned>(ws->hAcc.recordCount[m], ws->recCap), cap); counts[m] = (uint32_t)n[m]; tot += n[m]; }
+        ws->hRec.ensure(tot * 16 + 16);
+        unsigned char* h = ws->hRec.p;
+        size_t o = 0;
+        for (int m = 0; m < 5; ++m) {
+            if (!n[m]) continue;
+            CK(cudaMemcpyAsync(h + o, ws->recScore.p + (size_t)m * ws->recCap, n[m] * 8, cudaMemcpyDeviceToHost, ws->st)); o += n[m] * 8;
+            CK(cudaMemcpyAsync(h + o, ws->recRank.p + (size_t)m * ws->recCap, n[m] * 4, cudaMemcpyDeviceToHost, ws->st)); o += n[m] * 4;
+            CK(cudaMemcpyAsync(h + o, ws->recNode.p + (size_t)m * ws->recCap, n[m] * 4, cudaMemcpyDeviceToHost, ws->st)); o += n[m] * 4;
+        }
+        if (tot) CK(cudaStreamSynchronize(ws->st));
+        o = 0;
+        for (int m = 0; m < 5; ++m) {
+            if (!n[m]) continue;
+            std::memcpy(score + (size_t)m * cap, h + o, n[m] * 8); o += n[m] * 8;
+            std::memcpy(bfs_rank + (size_t)m * cap, h + o, n[m] * 4); o += n[m] * 4;
+            std::memcpy(node + (size_t)m * cap, h + o, n[m] * 4); o += n[m] * 4;
+        }
+        return PM_OK;
+    });
+}
 // all ranks' records of every metric (concatenated per metric; counts[5]) -> chain on the device -> this shard's ties
 int pm_stage_select(pm_workspace* ws, const uint32_t* counts, const uint32_t* const* bfs_rank, const uint32_t* const* node,
                     const double* const* score, uint64_t total_reads, pm_place_result* result) {
@@ -837,14 +889,25 @@ int pm_stage_select(pm_workspace* ws, const uint32_t* counts, const uint32_t* co
             ws->recRank.alloc((size_t)5 * maxN); ws->recNode.alloc((size_t)5 * maxN); ws->recScore.alloc((size_t)5 * maxN);
             refreshView(ws);
         }
-        DevBuf<u32> dCounts; dCounts.alloc(5);
-        CK(cudaMemcpyAsync(dCounts.p, counts, 5 * sizeof(u32), cudaMemcpyHostToDevice, ws->st));
+        size_t tot = 0;
+        for (int m = 0; m < 5; ++m) tot += counts[m];
+        ws->hRec.ensure(tot * 16 + 64);
+        unsigned char* h = ws->hRec.p;
+        std::memcpy(h, counts, 5 * sizeof(u32));
+        if (!ws->selCounts.p) ws->selCounts.alloc(8);
+        CK(cudaMemcpyAsync(ws->selCounts.p, h, 5 * sizeof(u32), cudaMemcpyHostToDevice, ws->st));
+        size_t o = 32;
         for (int m = 0; m < 5; ++m) {
             if (!counts[m]) continue;
-            CK(cudaMemcpyAsync(ws->recRank.p + (size_t)m * ws->recCap, bfs_rank[m], counts[m] * 4ull, cudaMemcpyHostToDevice, ws->st));
-            CK(cudaMemcpyAsync(ws->recNode.p + (size_t)m * ws->recCap, node[m], counts[m] * 4ull, cudaMemcpyHostToDevice, ws->st));
-            CK(cudaMemcpyAsync(ws->recScore.p + (size_t)m * ws->recCap, score[m], counts[m] * 8ull, cudaMemcpyHostToDevice, ws->st));
+            const size_t n = counts[m];
+            std::memcpy(h + o, score[m], n * 8);
+            CK(cudaMemcpyAsync(ws->recScore.p + (size_t)m * ws->recCap, h + o, n * 8, cudaMemcpyHostToDevice, ws->st)); o += n * 8;
+            std::memcpy(h + o, bfs_rank[m], n * 4);
+            CK(cudaMemcpyAsync(ws->recRank.p + (size_t)m * ws->recCap, h + o, n * 4, cudaMemcpyHostToDevice, ws->st)); o += n * 4;
+            std::memcpy(h + o, node[m], n * 4);
+            CK(cudaMemcpyAsync(ws->recNode.p + (size_t)m * ws->recCap, h + o, n * 4, cudaMemcpyHostToDevice, ws->st)); o += n * 4;
         }
+        DevBuf<u32>& dCounts = ws->selCounts;
         launchChain(ws->view, dCounts.p, ws->st);
         launchTies(I->view, ws->view, makeOpts(ws->lastParams, false), ws->st);
         fetchSmall(ws);
