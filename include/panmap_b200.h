@@ -102,7 +102,7 @@ int pm_abi_version(void);
 int pm_device_count(void);
 
 /* ---- .idx container (index_single_mode.cpp:1561-1636, main.cpp:193-236): 32-byte "PMI1" header + raw
- *      Cap'n Proto LiteIndex message.  zstd-framed payloads are reported as PM_ERR_UNSUPPORTED. ---- */
+ *      Cap'n Proto LiteIndex message, raw or as independent zstd frames (libzstd.so.1 is loaded at run time when needed). ---- */
 int pm_host_index_read(const char* path, pm_host_index** out);
 void pm_host_index_free(pm_host_index* h);
 int pm_host_index_desc(const pm_host_index* h, pm_index_desc* out); /* pointers stay owned by h */

@@ -8,6 +8,8 @@
 // shapes used are LiteIndex (2 data words, 11 pointers), LiteTree (0,2) and LiteNode (1,1).
 #include "pm_host.h"
 
+#include <dlfcn.h>
+
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -61,6 +63,31 @@ Ref resolve(const Msg& m, uint32_t seg, size_t w) {
 Ref ptrOf(const Msg& m, const Ref& s, uint32_t i) { return (s.kind == 1 && i < s.ptrWords) ? resolve(m, s.seg, s.off + s.dataWords + i) : Ref{}; }
 static const size_t kElemBytes[8] = {0, 0, 1, 2, 4, 8, 8, 0};
 
+// zstd-framed payloads (the reference's default: independent 64 MB frames, index_single_mode.cpp:1615-1633,
+// zstd_compression.cpp:31-60).  libzstd is a runtime dependency only: resolved with dlopen, no headers needed.
+void inflateZstdFrames(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+    void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libzstd.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) throw Unsupported("zstd-compressed .idx needs libzstd.so.1 at run time (or write the index uncompressed)");
+    auto decompress = reinterpret_cast<size_t (*)(void*, size_t, const void*, size_t)>(dlsym(h, "ZSTD_decompress"));
+    auto contentSize = reinterpret_cast<unsigned long long (*)(const void*, size_t)>(dlsym(h, "ZSTD_getFrameContentSize"));
+    auto frameSize = reinterpret_cast<size_t (*)(const void*, size_t)>(dlsym(h, "ZSTD_findFrameCompressedSize"));
+    auto isError = reinterpret_cast<unsigned (*)(size_t)>(dlsym(h, "ZSTD_isError"));
+    if (!decompress || !contentSize || !frameSize || !isError) throw Unsupported("libzstd lacks the frame API");
+    size_t pos = 0;
+    while (pos < n) {
+        const size_t csz = frameSize(src + pos, n - pos);
+        if (isError(csz)) throw std::runtime_error("Failed to decompress index: bad zstd frame");
+        const unsigned long long dsz = contentSize(src + pos, csz);
+        if (dsz >= 0xFFFFFFFFFFFFFFFEULL) throw std::runtime_error("Failed to decompress index: frame without content size");
+        const size_t o = out.size();
+        out.resize(o + static_cast<size_t>(dsz));
+        const size_t got = decompress(out.data() + o, static_cast<size_t>(dsz), src + pos, csz);
+        if (isError(got) || got != dsz) throw std::runtime_error("Failed to decompress index: zstd error");
+        pos += csz;
+    }
+}
+
 }  // namespace
 
 void readIdxFile(const std::string& path, HostIndex& out) {
@@ -75,13 +102,17 @@ void readIdxFile(const std::string& path, HostIndex& out) {
     if (out.raw.size() < 40) throw std::runtime_error("index file too small: " + path);
     uint32_t magic, ver; std::memcpy(&magic, out.raw.data(), 4); std::memcpy(&ver, out.raw.data() + 4, 4);
     size_t payload = 0;
-    if (magic == 0x31494D50u && ver == 1) {
-        if (out.raw[26] == 0) throw Unsupported("zstd-framed .idx payloads are not supported yet; write the index uncompressed");
-        payload = 32;
-    }
-    Msg m; m.base = out.raw.data() + payload;
-    const size_t avail = out.raw.size() - payload;
+    std::vector<uint8_t> inflated;
+    bool compressed = false;
+    if (magic == 0x31494D50u && ver != 1) throw std::runtime_error("unsupported .idx header version " + std::to_string(ver) + ": " + path);
+    if (magic == 0x31494D50u && ver == 1) { payload = 32; compressed = out.raw[26] == 0; }
+    else if (magic == 0xFD2FB528u) compressed = true;   // header-less legacy file that starts with a zstd frame
+    if (compressed) inflateZstdFrames(out.raw.data() + payload, out.raw.size() - payload, inflated);
+    Msg m; m.base = compressed ? inflated.data() : out.raw.data() + payload;
+    const size_t avail = compressed ? inflated.size() : out.raw.size() - payload;
+    if (avail < 8) throw std::runtime_error("index message truncated: " + path);
     uint32_t nseg; std::memcpy(&nseg, m.base, 4); nseg += 1;
+    if (nseg == 0 || nseg > 4096 || 4 + 4 * static_cast<size_t>(nseg) > avail) throw std::runtime_error("not a Cap'n Proto index message: " + path);
     size_t hdr = (4 + 4 * static_cast<size_t>(nseg) + 7) & ~size_t(7);
     size_t pos = hdr;
     for (uint32_t i = 0; i < nseg; ++i) {

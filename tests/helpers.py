@@ -8,6 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DATA = os.path.join(ROOT, "oracle", "_ref", "data")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 SARS_IDX = os.path.join(REF_DATA, "sars_20000.k19s8t0l3.idx")
+RSV_IDX = os.path.join(REF_DATA, "rsv_4K.k19s8t0l3.idx")
+MAMMOTH_IDX = os.path.join(REF_DATA, "extended_mammoth.k15s8t0l1.idx")
 ISOLATE_R1 = os.path.join(REF_DATA, "isolate_R1.fastq.gz")
 ISOLATE_R2 = os.path.join(REF_DATA, "isolate_R2.fastq.gz")
 ISOLATE_TSV = os.path.join(REF_DATA, "isolate.placement.tsv")

@@ -35,15 +35,32 @@ def test_idx_reader_errors():
     with pytest.raises(pm.PanmapError) as e:
         pm.HostIndex.read("/nonexistent/x.idx")
     assert e.value.code == -4
-    bad = os.path.join(H.GOLDEN, "tiny.idx")
-    raw = bytearray(open(bad, "rb").read())
-    raw[26] = 0   # claim a zstd-framed payload
     import tempfile
     with tempfile.NamedTemporaryFile(suffix=".idx") as f:
-        f.write(raw); f.flush()
-        with pytest.raises(pm.PanmapError) as e:
+        f.write(b"PMI1" + b"\x00" * 60); f.flush()      # right magic, wrong header version / truncated message
+        with pytest.raises(pm.PanmapError):
             pm.HostIndex.read(f.name)
-        assert e.value.code == -5
+
+
+def test_idx_reader_zstd_framed_payload(tmp_path):
+    """the reference writes the payload as independent zstd frames by default (index_single_mode.cpp:1615-1633)"""
+    import ctypes.util
+    z = C.CDLL(ctypes.util.find_library("zstd") or "libzstd.so.1")
+    z.ZSTD_compressBound.restype = C.c_size_t; z.ZSTD_compressBound.argtypes = [C.c_size_t]
+    z.ZSTD_compress.restype = C.c_size_t; z.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    raw = open(os.path.join(H.GOLDEN, "tiny.idx"), "rb").read()
+    hdr, payload = bytearray(raw[:32]), raw[32:]
+    hdr[26] = 0
+    frames = b""
+    cut = (len(payload) // 2) & ~7
+    for part in (payload[:cut], payload[cut:]):           # two frames, like the reference's 64 MB framing
+        cap = z.ZSTD_compressBound(len(part)); dst = C.create_string_buffer(cap)
+        n = z.ZSTD_compress(dst, cap, part, len(part), 3)
+        frames += dst.raw[:n]
+    p = tmp_path / "z.idx"
+    p.write_bytes(bytes(hdr) + frames)
+    a = pm.HostIndex.read(str(p)); b = pm.HostIndex.read(os.path.join(H.GOLDEN, "tiny.idx"))
+    assert np.array_equal(a.hash, b.hash) and np.array_equal(a.offsets, b.offsets) and a.node_ids == b.node_ids and (a.k, a.l) == (b.k, b.l)
 
 
 @pytest.mark.skipif(pm.device_count() > 0, reason="a CUDA device is present")

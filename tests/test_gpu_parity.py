@@ -179,3 +179,75 @@ def test_place_files_through_cpp_shim_writes_the_golden_tsv(tmp_path):
     buf, off = pm.read_fastx(os.path.join(H.REF_DATA, "MZ515733.1.fa"))
     exp = cpu.place(buf, off, host)
     assert list(res.best_index) == list(exp["best_index"])
+
+
+@pytest.mark.skipif(not os.path.exists(H.RSV_IDX), reason="reference-built rsv_4K index not staged")
+def test_rsv4k_fastq_places_on_its_genome_like_the_reference_e2e(tmp_path):
+    """src/test/e2e/run_e2e.sh:93-99: MZ515733.1.fastq -> node MZ515733.1.  The root of rsv_4K has no seeds, so the
+    weighted-containment denominator is 0 and that row has score 0 and an empty node field (golden TSV from the reference)."""
+    host = pm.HostIndex.read(H.RSV_IDX)
+    ws = pm.Workspace(pm.Index(host))
+    out = str(tmp_path / "rsv.tsv")
+    res = pm.place_files(ws, os.path.join(H.REF_DATA, "MZ515733.1.fastq"), "", out)
+    assert open(out).read() == open(os.path.join(H.GOLDEN, "rsv4k_MZ515733.placement.tsv")).read()
+    assert host.node_ids[res.best_index[0]] == "MZ515733.1" and res.best_index[3] == 0xFFFFFFFF
+    buf, off = pm.read_fastx(os.path.join(H.REF_DATA, "MZ515733.1.fastq"))
+    exp = cpu.place(buf, off, host, want_scores=True)
+    r = ws.place(buf, off)
+    assert H.relerr(ws.node_scores(), exp["scores"]).max() < RTOL
+    for m, name in enumerate(pm.METRICS):
+        assert r.best_index[name] == exp["best_index"][m] and np.array_equal(r.tied[name], exp["tied"][m])
+
+
+@pytest.mark.skipif(not os.path.exists(H.MAMMOTH_IDX), reason="reference-built extended_mammoth index not staged")
+def test_mammoth_mtdna_k15_s8_l1_matches_oracle():
+    """BASELINE config 2 stand-in (v_mtdna inputs are absent): a real mtDNA PanMAN indexed by the reference at k=15 s=8 l=1 and
+    reads simulated from the reference's own reconstruction of node_5 (tests/golden/mammoth_node5_reads.fa.gz)."""
+    host = pm.HostIndex.read(H.MAMMOTH_IDX)
+    assert (host.k, host.s, host.l) == (15, 8, 1)
+    buf, off = pm.read_fastx(os.path.join(H.GOLDEN, "mammoth_node5_reads.fa.gz"))
+    ws = pm.Workspace(pm.Index(host))
+    res = ws.place(buf, off)
+    exp = cpu.place(buf, off, host, want_scores=True)
+    assert res.raw.unique_seeds == exp["unique_seeds"] and res.raw.read_unique_seed_count == exp["kept"]
+    th, tc = ws.seed_table()
+    eh, ec = cpu.seed_table(buf, off, 15, 8, 0, 1)
+    assert np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec)
+    assert H.relerr(ws.node_scores(), exp["scores"]).max() < RTOL
+    for m, name in enumerate(pm.METRICS):
+        assert res.best_index[name] == exp["best_index"][m] and np.array_equal(res.tied[name], exp["tied"][m])
+    assert "node_5" in [host.node_ids[int(i)] for i in res.tied["log_containment"]] or host.node_ids[res.best_index["log_containment"]] == "node_5"
+
+
+def test_batch_mode_concurrent_workspaces_share_one_index():
+    """the reference's batch mode places samples from TBB worker threads on one shared tree (main.cpp:1581-1653): here one
+    pm_index, one pm_workspace (stream) per thread, results identical to serial placement"""
+    import threading
+    from tools.synth import synth
+    S = synth.generate(3000, 8000, 1.5, 6000, seed=8)
+    host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
+    index = pm.Index(host)
+    n = 6000
+    samples = []
+    for j in range(4):
+        lo, hi = j * 1500, (j + 1) * 1500
+        samples.append((S.reads[int(S.read_offsets[lo]):int(S.read_offsets[hi])].copy(), (S.read_offsets[lo:hi + 1] - S.read_offsets[lo]).copy()))
+    serial = []
+    ws0 = pm.Workspace(index)
+    for b, o in samples:
+        serial.append(ws0.place(b, o))
+    out = [None] * 4
+
+    def work(j):
+        ws = pm.Workspace(index)
+        for _ in range(5):
+            out[j] = ws.place(*samples[j])
+    ts = [threading.Thread(target=work, args=(j,)) for j in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for j in range(4):
+        exp = cpu.place(samples[j][0], samples[j][1], S)
+        for m, name in enumerate(pm.METRICS):
+            assert out[j].best_index[name] == serial[j].best_index[name] == exp["best_index"][m]
+            assert out[j].best_score[name] == serial[j].best_score[name]
+            assert np.array_equal(out[j].tied[name], exp["tied"][m])
