@@ -85,8 +85,7 @@ struct pm_index {
     DevBuf<DictSlot> dict;
     DevBuf<double> gMag, log1pLut, log1pSmall;
     DevBuf<unsigned char> isLeaf;
-    DevBuf<K1Tile> k1Tiles;
-    DevBuf<BigNode> bigNodes;
+    DevBuf<u32> chunkNode, boundaryNodes; DevBuf<unsigned char> isBoundary;
     DevBuf<SeedTables> seedTables;
     DevIndexView view{};
     std::vector<double> gMagSqHost; std::vector<int64_t> gUniqueHost;
@@ -106,7 +105,7 @@ struct pm_workspace {
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
     DevBuf<double> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist;
-    DevBuf<NodeDelta> delta, bigPartial; DevBuf<unsigned> bigDone;
+    DevBuf<u64> deltaFx;
     DevBuf<u64> chainA;
     DevBuf<double> scores, metrics, blockMaxAndBfs;
     DevBuf<u32> recRank, recNode; DevBuf<double> recScore; u32 recCap = 0;
@@ -132,8 +131,8 @@ void buildViews(pm_index* I) {
     V.nNodes = F.N; V.nodeBegin = F.nodeBegin; V.nodeEnd = F.nodeEnd; V.nLocal = F.nLocal; V.nAnc = F.nAnc;
     V.nLocalDeltas = F.nLocalDeltas; V.nSeeds = F.S;
     V.seedId = I->seedId.p; V.pc = I->pc.p; V.lOff = I->lOff.p; V.lNode = I->lNode.p;
-    V.k1Tiles = I->k1Tiles.p; V.nK1Tiles = (u32)F.k1Tiles.size();
-    V.bigNodes = I->bigNodes.p; V.nBigNodes = (u32)F.bigNodes.size(); V.nBigPartials = F.nBigPartials;
+    V.nDeltaChunks = F.nDeltaChunks; V.nRealDeltas = F.nLocalDeltas; V.chunkNode = I->chunkNode.p; V.isBoundary = I->isBoundary.p;
+    V.boundaryNodes = I->boundaryNodes.p; V.nBoundary = (u32)F.boundaryNodes.size();
     V.parent = I->parent.p; V.gMag = I->gMag.p; V.closeOff = I->closeOff.p; V.closeList = I->closeList.p;
     V.carrySlot = I->carrySlot.p; V.chainOff = I->chainOff.p; V.chainNodes = I->chainNodes.p;
     V.nK2Tiles = F.nK2Tiles; V.chainTotal = (u32)F.chainNodes.size();
@@ -169,17 +168,7 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
             I->dict.upload(d);
         }
         I->dictHash.upload(F.dictHash);
-        {
-            std::vector<K1Tile> t(F.k1Tiles.size());
-            for (size_t i = 0; i < t.size(); ++i) {
-                t[i].dBegin = F.k1Tiles[i].dBegin; t[i].dCount = F.k1Tiles[i].dCount; t[i].lnBegin = F.k1Tiles[i].lnBegin;
-                t[i].lnEnd = F.k1Tiles[i].lnEnd; t[i].kind = F.k1Tiles[i].kind; t[i].bigSlot = F.k1Tiles[i].bigSlot; t[i].bigNode = F.k1Tiles[i].bigNode;
-            }
-            I->k1Tiles.upload(t);
-            std::vector<BigNode> b(F.bigNodes.size());
-            for (size_t i = 0; i < b.size(); ++i) { b[i].localNode = F.bigNodes[i].localNode; b[i].firstPartial = F.bigNodes[i].firstPartial; b[i].nPartials = F.bigNodes[i].nPartials; b[i].pad = 0; }
-            I->bigNodes.upload(b);
-        }
+        I->chunkNode.upload(F.chunkNode); I->isBoundary.upload(F.isBoundary); I->boundaryNodes.upload(F.boundaryNodes);
         {
             std::vector<double> lut(kLog1pLut), small(32768);
             for (int c = 0; c < kLog1pLut; ++c) lut[c] = std::log1p((double)c);
@@ -207,7 +196,7 @@ void refreshView(pm_workspace* W) {
     V.table = W->table.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
     V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
     V.acc = W->acc.p; V.ell = W->ell.p; V.touched = W->touched.p; V.touchedCap = (u32)W->touched.n; V.countHist = W->countHist.p;
-    V.delta = W->delta.p; V.bigPartial = W->bigPartial.p; V.bigDone = W->bigDone.p; V.chainA = W->chainA.p;
+    V.deltaFx = W->deltaFx.p; V.chainA = W->chainA.p;
     V.scores = W->scores.p; V.metrics = W->wantMetrics ? W->metrics.p : nullptr; V.blockMax = W->blockMaxAndBfs.p;
     V.recRank = W->recRank.p; V.recNode = W->recNode.p; V.recScore = W->recScore.p; V.recCap = W->recCap;
     V.tieNode = W->tieNode.p; V.tieCap = W->tieCap; V.sel = W->sel.p; V.scalars = W->scalars.p;
@@ -520,10 +509,7 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         W->ell.alloc(F.S ? F.S : 1); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(double), W->st));
         W->touched.alloc(F.S ? F.S : 1);
         W->countHist.alloc(kLog1pLut);
-        W->delta.alloc(F.N); CK(cudaMemsetAsync(W->delta.p, 0, F.N * sizeof(NodeDelta), W->st));
-        W->bigPartial.alloc(F.nBigPartials ? F.nBigPartials : 1);
-        W->bigDone.alloc(F.bigNodes.size() ? F.bigNodes.size() : 1);
-        CK(cudaMemsetAsync(W->bigDone.p, 0, W->bigDone.n * sizeof(unsigned), W->st));
+        W->deltaFx.alloc(F.N * kDeltaWords); CK(cudaMemsetAsync(W->deltaFx.p, 0, F.N * kDeltaWords * sizeof(u64), W->st));   // nodes without deltas stay 0
         W->chainA.alloc((size_t)(V.chainTotal ? V.chainTotal : 1) * 9);
         W->scores.alloc(F.N * 5); CK(cudaMemsetAsync(W->scores.p, 0, F.N * 5 * sizeof(double), W->st));
         W->blockMaxAndBfs.alloc((size_t)V.nBfsBlocks * 5 + (size_t)V.nShardNodes * 5 + 8);

@@ -8,7 +8,7 @@
 //     order (parent's value, then the node's deltas in stored order; placement.cpp:289-302,772-774) -> bit-identical
 //   * DFS subtree ends, depth, reference BFS ranks, leaf flags
 //   * "closers" CSR for the in-tile Euler-tour difference, ancestor chains + carry slots of the K2 tiles
-//   * K1 tile schedule (whole nodes per tile, nodes above kTileDeltas split into chunks)
+//   * delta-kernel schedule: 512-delta chunks, owner node of every chunk, nodes that span chunks
 #include "pm_host.h"
 #include "pm_logic.cuh"
 
@@ -20,7 +20,7 @@
 
 namespace pm {
 
-static constexpr uint32_t kTileDeltasH = 4096, kTileNodesK1H = 2048, kTileNodesK2H = 512;
+static constexpr uint32_t kTileNodesK2H = 512;
 static constexpr uint32_t NONE = 0xFFFFFFFFu;
 
 // for every block of 256 packed chunks counted from chunk gBase (= packedOff[0] of the slice): the slice-local read r with
@@ -203,36 +203,22 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
     F.rootDBegin = 0; F.rootDCount = 0;
     if (F.nLocal > 0 && F.lNode[0] == 0) { F.rootDBegin = F.lOff[0]; F.rootDCount = static_cast<uint32_t>(F.lOff[1] - F.lOff[0]); }
 
-    // ---- K1 tiles ----
+    // ---- delta kernel schedule: chunks of 512 deltas ----
     {
-        uint32_t i = 0;
-        while (i < F.nLocal) {
-            const uint64_t n0 = F.lOff[i + 1] - F.lOff[i];
-            if (n0 > kTileDeltasH) {
-                HostBigNode bn; bn.localNode = i; bn.firstPartial = F.nBigPartials; bn.pad = 0;
-                bn.nPartials = static_cast<uint32_t>((n0 + kTileDeltasH - 1) / kTileDeltasH);
-                for (uint32_t c = 0; c < bn.nPartials; ++c) {
-                    HostK1Tile t; t.dBegin = F.lOff[i] + static_cast<uint64_t>(c) * kTileDeltasH;
-                    t.dCount = static_cast<uint32_t>(std::min<uint64_t>(kTileDeltasH, F.lOff[i + 1] - t.dBegin));
-                    t.lnBegin = i; t.lnEnd = i + 1; t.kind = 1; t.bigSlot = F.nBigPartials + c;
-                    t.bigNode = static_cast<uint32_t>(F.bigNodes.size());
-                    F.k1Tiles.push_back(t);
-                }
-                F.nBigPartials += bn.nPartials;
-                F.bigNodes.push_back(bn);
-                ++i;
-                continue;
-            }
-            HostK1Tile t; t.dBegin = F.lOff[i]; t.lnBegin = i; t.kind = 0; t.bigSlot = 0; t.bigNode = 0;
-            uint64_t cnt = 0; uint32_t j = i;
-            while (j < F.nLocal && j - i < kTileNodesK1H) {
-                const uint64_t nj = F.lOff[j + 1] - F.lOff[j];
-                if (nj > kTileDeltasH || cnt + nj > kTileDeltasH) break;
-                cnt += nj; ++j;
-            }
-            t.lnEnd = j; t.dCount = static_cast<uint32_t>(cnt);
-            F.k1Tiles.push_back(t);
-            i = j;
+        const uint64_t CH = 512;
+        F.nDeltaChunks = (F.nLocalDeltas + CH - 1) / CH;
+        F.seedId.resize(F.nDeltaChunks * CH, 0); F.pc.resize(F.nDeltaChunks * CH, 0);   // padding: parent == child == 0 contributes nothing
+        F.chunkNode.assign(F.nDeltaChunks + 1, F.nLocal ? F.nLocal - 1 : 0);
+        F.isBoundary.assign(F.nLocal, 0);
+        uint32_t ln = 0;
+        for (uint64_t c = 0; c < F.nDeltaChunks; ++c) {
+            const uint64_t d = c * CH;
+            while (ln + 1 < F.nLocal && F.lOff[ln + 1] <= d) ++ln;   // node with lOff[ln] <= d < lOff[ln+1]
+            F.chunkNode[c] = ln;
+        }
+        for (uint32_t i = 0; i < F.nLocal; ++i) {
+            const uint64_t b0 = F.lOff[i], e0 = F.lOff[i + 1];
+            if (e0 > b0 && b0 / CH != (e0 - 1) / CH) { F.isBoundary[i] = 1; F.boundaryNodes.push_back(F.lNode[i]); }
         }
     }
 

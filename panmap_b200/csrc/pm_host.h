@@ -23,8 +23,6 @@ struct HostIndex {
 };
 void readIdxFile(const std::string& path, HostIndex& out);
 
-struct HostK1Tile { uint64_t dBegin; uint32_t dCount, lnBegin, lnEnd, kind, bigSlot, bigNode; };
-struct HostBigNode { uint32_t localNode, firstPartial, nPartials, pad; };
 
 // everything pm_index_create derives from a pm_index_desc before uploading (see DESIGN.md "HBM layout")
 struct FlatIndex {
@@ -45,9 +43,11 @@ struct FlatIndex {
     // shard-local delta storage
     std::vector<uint32_t> seedId, pc, lNode;
     std::vector<uint64_t> lOff;
-    std::vector<HostK1Tile> k1Tiles;
-    std::vector<HostBigNode> bigNodes;
-    uint32_t nBigPartials = 0;
+    // delta kernel schedule: fixed chunks of 512 deltas (one warp each)
+    uint64_t nDeltaChunks = 0;                 // seedId / pc are padded to nDeltaChunks * 512 entries
+    std::vector<uint32_t> chunkNode;           // [nDeltaChunks+1] local node owning the chunk's first delta
+    std::vector<uint8_t> isBoundary;           // [nLocal] node has deltas in more than one chunk (its sums are combined with atomics)
+    std::vector<uint32_t> boundaryNodes;       // global ids of those nodes (their accumulators are zeroed per sample)
     // K2 tiles
     std::vector<uint32_t> carrySlot, chainOff, chainNodes;
     uint32_t nK2Tiles = 0;

@@ -746,150 +746,157 @@ __global__ void __launch_bounds__(256) reset_ell(WorkspaceView W) {
 void launchResetEll(WorkspaceView W, cudaStream_t st) { reset_ell<<<148, 256, 0, st>>>(W); }
 
 // ------------------------------------------------------------------------------------------------------
-// K1 node_deltas: one pass over the delta arrays.
-// phase 1 (coalesced, 16 independent gathers in flight per thread): v[i] = +-log1p(readCount) for the common
-//   0<->1 genome-count transitions, 0 when the seed is not in the reads, NaN for counts >= 2 (general formula)
-// phase 2: lane-per-node sequential sums for nodes with <= 32 deltas, warp-per-node for larger ones; sums are
-//   taken relative to the node's own first delta, so they do not depend on how nodes are tiled or sharded.
+// K1 node_deltas: one pass over the delta arrays, no shared memory, no block barriers.
+// A warp owns a chunk of 512 consecutive deltas; lane l owns deltas [16 l, 16 l + 16) of it, fetched with eight 16-byte
+// loads (the warp's loads are one contiguous 2 KB + 2 KB stream) followed by 16 independent gathers of log1p(read count).
+// Every per-delta term is converted to 128-bit fixed point before it is added, so all sums are exact and independent of
+// how deltas are split over lanes, warps, shards or GPUs:
+//   * nodes that begin and end inside a lane are stored directly;
+//   * a node spread over several lanes is combined with a segmented warp scan and stored by the lane where it ends;
+//   * a node spread over several chunks (flagged at flatten time, zeroed by zero_boundary first) is combined with
+//     fixed-point atomics;
+//   * deltas whose genome counts are >= 2 (repeats; rare) take the general formula afterwards and are added atomically.
+// Output: deltaFx[node] = {raw, cos, wc, cont as fx128, presence} parent-relative sums, read by prefix_scores.
 // ------------------------------------------------------------------------------------------------------
-struct NodeAcc { double S, gRaw, gCos, gWc, gCont; int cnt, gPres; };
-__device__ __forceinline__ void nodeAccInit(NodeAcc& a) { a.S = a.gRaw = a.gCos = a.gWc = a.gCont = 0.0; a.cnt = a.gPres = 0; }
-
-__device__ __forceinline__ void accumulateDelta(NodeAcc& a, double v, u64 gIdx, const DevIndexView& I, const double* __restrict__ ell) {
-    if (v == v) {
-        a.S += v;
-        a.cnt += (v > 0.0) - (v < 0.0);
-    } else {
-        const u32 pc = __ldg(&I.pc[gIdx]);
-        const int p = (int)(short)(pc & 0xFFFFu), c = (int)(short)(pc >> 16);
-        const double lr = ell[__ldg(&I.seedId[gIdx])];
-        const double logP = p > 0 ? __ldg(&I.log1pSmall[p]) : 0.0;
-        const double logC = c > 0 ? __ldg(&I.log1pSmall[c]) : 0.0;
-        const DeltaTerms d = deltaTerms(lr, p, c, logP, logC);
-        a.gRaw += d.raw; a.gCos += d.cos; a.gWc += d.wc; a.gCont += d.cont; a.gPres += d.pres;
-    }
+struct SegTot { fx128 raw, cos, wc, cont; i64 pres; };
+__device__ __forceinline__ SegTot segZero() { SegTot t; t.raw = t.cos = t.wc = t.cont = fxZero(); t.pres = 0; return t; }
+__device__ __forceinline__ SegTot segAdd(const SegTot& a, const SegTot& b) {
+    SegTot r; r.raw = fxAdd(a.raw, b.raw); r.cos = fxAdd(a.cos, b.cos); r.wc = fxAdd(a.wc, b.wc); r.cont = fxAdd(a.cont, b.cont);
+    r.pres = a.pres + b.pres; return r;
 }
-__device__ __forceinline__ NodeDelta finishNode(const NodeAcc& a, double ln2) {
-    NodeDelta d;
-    d.raw = a.S + a.gRaw;
-    d.cos = a.S * ln2 + a.gCos;
-    d.wc = (double)a.cnt + a.gWc;
-    d.cont = a.S + a.gCont;
-    d.pres = (long long)a.cnt + (long long)a.gPres;
-    return d;
+__device__ __forceinline__ SegTot segShflUp(const SegTot& a, int d) {
+    SegTot r;
+    r.raw.lo = shflUpU64(a.raw.lo, d); r.raw.hi = (i64)shflUpU64((u64)a.raw.hi, d);
+    r.cos.lo = shflUpU64(a.cos.lo, d); r.cos.hi = (i64)shflUpU64((u64)a.cos.hi, d);
+    r.wc.lo = shflUpU64(a.wc.lo, d); r.wc.hi = (i64)shflUpU64((u64)a.wc.hi, d);
+    r.cont.lo = shflUpU64(a.cont.lo, d); r.cont.hi = (i64)shflUpU64((u64)a.cont.hi, d);
+    r.pres = (i64)shflUpU64((u64)a.pres, d); return r;
 }
-__device__ __forceinline__ NodeAcc warpReduceNodeAcc(NodeAcc a) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        a.S += shflXorF64(a.S, d); a.gRaw += shflXorF64(a.gRaw, d); a.gCos += shflXorF64(a.gCos, d);
-        a.gWc += shflXorF64(a.gWc, d); a.gCont += shflXorF64(a.gCont, d);
-        a.cnt += __shfl_xor_sync(0xffffffffu, a.cnt, d); a.gPres += __shfl_xor_sync(0xffffffffu, a.gPres, d);
-    }
-    return a;
+__device__ __forceinline__ void segStore(u64* __restrict__ p, const SegTot& t) {
+    p[0] = t.raw.lo; p[1] = (u64)t.raw.hi; p[2] = t.cos.lo; p[3] = (u64)t.cos.hi; p[4] = t.wc.lo; p[5] = (u64)t.wc.hi;
+    p[6] = t.cont.lo; p[7] = (u64)t.cont.hi; p[8] = (u64)t.pres;
+}
+__device__ __forceinline__ void segAtomicAdd(u64* p, const SegTot& t) {
+    fxAtomicAdd(p + 0, t.raw); fxAtomicAdd(p + 2, t.cos); fxAtomicAdd(p + 4, t.wc); fxAtomicAdd(p + 6, t.cont);
+    if (t.pres) atomicAdd(reinterpret_cast<unsigned long long*>(p + 8), (unsigned long long)t.pres);
+}
+__device__ __forceinline__ void emitNode(const DevIndexView& I, u64* __restrict__ deltaFx, u32 ln, const SegTot& t) {
+    u64* p = deltaFx + (size_t)I.lNode[ln] * kDeltaWords;
+    if (I.isBoundary[ln]) segAtomicAdd(p, t); else segStore(p, t);
+}
+// local node owning delta d, searched in [lo, hi]
+__device__ __forceinline__ u32 nodeOfDelta(const u64* __restrict__ lOff, u32 lo, u32 hi, u64 d) {
+    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (__ldg(&lOff[mid + 1]) > d) hi = mid; else lo = mid + 1; }
+    return lo;
 }
 
-__global__ void __launch_bounds__(256) node_deltas(DevIndexView I, WorkspaceView W) {
-    __shared__ double sV[kTileDeltas];
-    __shared__ u32 sBig[160];
-    __shared__ int sBigCount;
-    __shared__ NodeAcc sWarpAcc[8];
+__global__ void __launch_bounds__(256) zero_boundary(DevIndexView I, WorkspaceView W) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nBoundary * (u32)kDeltaWords; i += gridDim.x * blockDim.x)
+        W.deltaFx[(size_t)I.boundaryNodes[i / kDeltaWords] * kDeltaWords + (i % kDeltaWords)] = 0;
+}
+
+__global__ void __launch_bounds__(128) node_deltas(DevIndexView I, WorkspaceView W) {
     const double* __restrict__ ell = W.ell;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sBigCount = 0;
-    __syncthreads();
-    for (u32 ti = blockIdx.x; ti < I.nK1Tiles; ti += gridDim.x) {
-        const K1Tile t = I.k1Tiles[ti];
-        {   // 16 deltas per thread, all loads issued before the first use: pc + seedId (coalesced), then the ell gathers
-            u32 pcv[16], idv[16];
+    const u64* __restrict__ lOff = I.lOff;
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    const u64 dReal = I.nRealDeltas;
+    const double ln2 = I.ln2;
+    for (u64 c = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < I.nDeltaChunks; c += warpsTotal) {
+        const u64 d0 = c * kChunkDeltas + lane * 16;
+        u32 id[16], pc[16];
+        {
+            const uint4* pi = reinterpret_cast<const uint4*>(I.seedId + d0);
+            const uint4* pp = reinterpret_cast<const uint4*>(I.pc + d0);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const u32 i = tid + q * 256;
-                const bool in = i < t.dCount;
-                pcv[q] = in ? __ldcs(&I.pc[t.dBegin + i]) : 0u;
-                idv[q] = in ? __ldcs(&I.seedId[t.dBegin + i]) : 0u;
+            for (int q = 0; q < 4; ++q) {
+                const uint4 a = __ldcs(pi + q), b = __ldcs(pp + q);
+                id[4 * q] = a.x; id[4 * q + 1] = a.y; id[4 * q + 2] = a.z; id[4 * q + 3] = a.w;
+                pc[4 * q] = b.x; pc[4 * q + 1] = b.y; pc[4 * q + 2] = b.z; pc[4 * q + 3] = b.w;
             }
-            double lv[16];
+        }
+        double lv[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) lv[q] = (tid + q * 256 < t.dCount) ? __ldg(&ell[idv[q]]) : 0.0;
+        for (int j = 0; j < 16; ++j) lv[j] = __ldg(&ell[id[j]]);
+
+        const bool has = d0 < dReal;
+        const u32 n0 = I.chunkNode[c], n1 = I.chunkNode[c + 1];
+        u32 node = has ? nodeOfDelta(lOff, n0, n1, d0) : 0u;
+        const u32 nf = node;
+        u64 nextOff = has ? __ldg(&lOff[node + 1]) : ~0ULL;
+        SegTot acc = segZero(), tFirst = segZero();
+        bool firstDone = false;
+        unsigned genMask = 0;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const u32 i = tid + q * 256;
-                if (i < t.dCount) {
-                    const int p = (int)(short)(pcv[q] & 0xFFFFu), c = (int)(short)(pcv[q] >> 16);
-                    double v = 0.0;
-                    if (p != c && lv[q] > 0.0) {
-                        if ((unsigned)p <= 1u && (unsigned)c <= 1u) v = c > p ? lv[q] : -lv[q];
-                        else v = __longlong_as_double(0x7FF8000000000000LL);
-                    }
-                    sV[i] = v;
+        for (int j = 0; j < 16; ++j) {
+            const u64 idx = d0 + j;
+            if (idx < dReal) {
+                if (idx >= nextOff) {   // the current node ended before this delta
+                    if (!firstDone) { tFirst = acc; firstDone = true; }
+                    else segStore(W.deltaFx + (size_t)I.lNode[node] * kDeltaWords, acc);   // began and ended inside this lane
+                    acc = segZero();
+                    do { ++node; nextOff = __ldg(&lOff[node + 1]); } while (idx >= nextOff);   // skips nodes without deltas
+                }
+                const int p = (int)(short)(pc[j] & 0xFFFFu), cc = (int)(short)(pc[j] >> 16);
+                const double lr = lv[j];
+                if (p != cc && lr > 0.0) {
+                    if ((unsigned)p <= 1u && (unsigned)cc <= 1u) {
+                        // 0 <-> 1 genome count: raw = cont = +-lr, cos = +-fl(lr * log1p(1)), wc = pres = +-1 (placement.cpp:315-339)
+                        const fx128 fl = fxFromDouble(lr), fc = fxFromDouble(lr * ln2);
+                        if (cc > p) { acc.raw = fxAdd(acc.raw, fl); acc.cont = fxAdd(acc.cont, fl); acc.cos = fxAdd(acc.cos, fc); acc.wc.hi += 1; acc.pres += 1; }
+                        else { acc.raw = fxSub(acc.raw, fl); acc.cont = fxSub(acc.cont, fl); acc.cos = fxSub(acc.cos, fc); acc.wc.hi -= 1; acc.pres -= 1; }
+                    } else genMask |= 1u << j;
                 }
             }
         }
-        __syncthreads();
-        if (t.kind == 0) {
-            for (u32 ln = t.lnBegin + tid; ln < t.lnEnd; ln += 256) {
-                const u64 b = I.lOff[ln], e = I.lOff[ln + 1];
-                const u32 n = (u32)(e - b);
-                if (n <= 32) {
-                    NodeAcc a; nodeAccInit(a);
-                    const u32 o = (u32)(b - t.dBegin);
-                    for (u32 j = 0; j < n; ++j) accumulateDelta(a, sV[o + j], b + j, I, ell);
-                    W.delta[I.lNode[ln]] = finishNode(a, I.ln2);
-                } else {
-                    const int q = atomicAdd(&sBigCount, 1);
-                    sBig[q] = ln;
-                }
-            }
-            __syncthreads();
-            const int nb = sBigCount;
-            for (int q = warp; q < nb; q += 8) {
-                const u32 ln = sBig[q];
-                const u64 b = I.lOff[ln], e = I.lOff[ln + 1];
-                const u32 n = (u32)(e - b), o = (u32)(b - t.dBegin);
-                NodeAcc a; nodeAccInit(a);
-                for (u32 j = lane; j < n; j += 32) accumulateDelta(a, sV[o + j], b + j, I, ell);
-                a = warpReduceNodeAcc(a);
-                if (lane == 0) W.delta[I.lNode[ln]] = finishNode(a, I.ln2);
-            }
-            __syncthreads();
-            if (tid == 0) sBigCount = 0;
-        } else {
-            // chunk of one large node: block-wide sum, partial to global, last chunk adds the partials in order
-            NodeAcc a; nodeAccInit(a);
-            for (u32 j = tid; j < t.dCount; j += 256) accumulateDelta(a, sV[j], t.dBegin + j, I, ell);
-            a = warpReduceNodeAcc(a);
-            if (lane == 0) sWarpAcc[warp] = a;
-            __syncthreads();
-            if (tid == 0) {
-                NodeAcc s = sWarpAcc[0];
-                for (int w = 1; w < 8; ++w) {
-                    const NodeAcc o = sWarpAcc[w];
-                    s.S += o.S; s.gRaw += o.gRaw; s.gCos += o.gCos; s.gWc += o.gWc; s.gCont += o.gCont; s.cnt += o.cnt; s.gPres += o.gPres;
-                }
-                W.bigPartial[t.bigSlot] = finishNode(s, I.ln2);
-                __threadfence();
-                const BigNode bn = I.bigNodes[t.bigNode];
-                const unsigned done = atomicAdd(&W.bigDone[t.bigNode], 1u);
-                if (done == bn.nPartials - 1) {
-                    __threadfence();
-                    NodeDelta d; d.raw = d.cos = d.wc = d.cont = 0.0; d.pres = 0;
-                    for (u32 k = 0; k < bn.nPartials; ++k) {
-                        const volatile NodeDelta* pp = &W.bigPartial[bn.firstPartial + k];
-                        d.raw += pp->raw; d.cos += pp->cos; d.wc += pp->wc; d.cont += pp->cont; d.pres += pp->pres;
-                    }
-                    W.delta[I.lNode[bn.localNode]] = d;
-                    W.bigDone[t.bigNode] = 0;
-                }
+        const u32 nl = node;
+        const bool single = !firstDone;
+        // ---- combine the lanes' trailing partials: segmented inclusive scan, a run = consecutive lanes inside one node ----
+        const u32 nlPrev = __shfl_up_sync(0xffffffffu, nl, 1);
+        const bool hasPrev = __shfl_up_sync(0xffffffffu, (int)has, 1) != 0 && lane > 0;
+        const u32 nfNext = __shfl_down_sync(0xffffffffu, nf, 1);
+        const bool hasNext = __shfl_down_sync(0xffffffffu, (int)has, 1) != 0 && lane < 31;
+        const bool contPrev = has && hasPrev && nlPrev == nf;           // this lane starts inside the previous lane's last node
+        SegTot incl = acc;
+        int head = (single && contPrev) ? 0 : 1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const SegTot up = segShflUp(incl, d);
+            const int hup = __shfl_up_sync(0xffffffffu, head, d);
+            if ((int)lane >= d && !head) { incl = segAdd(incl, up); head = hup; }
+        }
+        const SegTot inclPrev = segShflUp(incl, 1);
+        if (has) {
+            if (!single) emitNode(I, W.deltaFx, nf, contPrev ? segAdd(inclPrev, tFirst) : tFirst);   // first node of the lane ends here
+            if (!(hasNext && nfNext == nl)) emitNode(I, W.deltaFx, nl, incl);                           // the run of the last node ends here
+        }
+        // ---- repeats (a genome count >= 2 on either side): general formula, added atomically after the stores above ----
+        if (__any_sync(0xffffffffu, genMask != 0)) {
+            __syncwarp();
+            while (genMask) {
+                const int j = __ffs(genMask) - 1;
+                genMask &= genMask - 1;
+                const u64 idx = d0 + j;
+                const u32 pcv = __ldg(&I.pc[idx]);
+                const int p = (int)(short)(pcv & 0xFFFFu), cc = (int)(short)(pcv >> 16);
+                const double lr = __ldg(&ell[__ldg(&I.seedId[idx])]);
+                const DeltaTerms t = deltaTerms(lr, p, cc, p > 0 ? __ldg(&I.log1pSmall[p]) : 0.0, cc > 0 ? __ldg(&I.log1pSmall[cc]) : 0.0);
+                SegTot g; g.raw = fxFromDouble(t.raw); g.cos = fxFromDouble(t.cos); g.wc = fxFromDouble(t.wc); g.cont = fxFromDouble(t.cont); g.pres = t.pres;
+                const u32 ln = nodeOfDelta(lOff, n0, n1, idx);
+                segAtomicAdd(W.deltaFx + (size_t)I.lNode[ln] * kDeltaWords, g);
             }
         }
-        __syncthreads();
     }
 }
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st) {
-    if (I.nK1Tiles == 0) return;
-    unsigned grid = (unsigned)nSM * 6u;
-    if (grid > I.nK1Tiles) grid = I.nK1Tiles;
-    node_deltas<<<grid, 256, 0, st>>>(I, W);
+    if (I.nDeltaChunks == 0) return;
+    if (I.nBoundary) {
+        unsigned g = (I.nBoundary * kDeltaWords + 255) / 256; if (g > 148 * 4) g = 148 * 4;
+        zero_boundary<<<g, 256, 0, st>>>(I, W);
+    }
+    u64 grid = (I.nDeltaChunks + 3) / 4;
+    if (grid > (u64)nSM * 16) grid = (u64)nSM * 16;
+    node_deltas<<<(unsigned)grid, 128, 0, st>>>(I, W);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -913,10 +920,6 @@ __device__ __forceinline__ Acc5 accSub(const Acc5& a, const Acc5& b) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) r.f[i] = fxSub(a.f[i], b.f[i]);
     r.pres = a.pres - b.pres; return r;
-}
-__device__ __forceinline__ Acc5 accFromDelta(const NodeDelta& d) {
-    Acc5 a; a.f[0] = fxFromDouble(d.raw); a.f[1] = fxFromDouble(d.cos); a.f[2] = fxFromDouble(d.wc); a.f[3] = fxFromDouble(d.cont);
-    a.pres = d.pres; return a;
 }
 __device__ __forceinline__ Acc5 accShflUp(const Acc5& a, int d) {
     Acc5 r;
@@ -967,7 +970,7 @@ __global__ void __launch_bounds__(256) prefix_scores(DevIndexView I, WorkspaceVi
     for (u32 base = cb; base < ce; base += 256) {
         Acc5 v = accZero();
         const u32 j = base + tid;
-        if (j < ce) v = accFromDelta(W.delta[I.chainNodes[j]]);
+        if (j < ce) v = accLoad(W.deltaFx + (size_t)I.chainNodes[j] * kDeltaWords);
         v = blockInclusiveScan(v, sWarp);
         v = accAdd(v, carry);
         if (j < ce) accStore(W.chainA + (size_t)j * 9, v);
@@ -979,7 +982,7 @@ __global__ void __launch_bounds__(256) prefix_scores(DevIndexView I, WorkspaceVi
     __syncthreads();
     // 2. d'
     for (u32 w = a0 + tid; w < a1; w += 256) {
-        Acc5 v = accFromDelta(W.delta[w]);
+        Acc5 v = accLoad(W.deltaFx + (size_t)w * kDeltaWords);
         const u32 cs = I.carrySlot[w];
         if (cs != kNone) v = accAdd(v, accLoad(W.chainA + (size_t)(cb + cs) * 9));
         accStore(sD + (size_t)(w - a0) * 9, v);

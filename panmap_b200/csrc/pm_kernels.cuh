@@ -6,27 +6,14 @@
 
 namespace pm {
 
-constexpr int kTileDeltas = 4096;   // K1: deltas staged per CTA tile (32 KB of f64 in shared memory)
-constexpr int kTileNodesK1 = 2048;  // K1: max nodes per tile
+constexpr int kChunkDeltas = 512;   // K1: deltas per warp chunk (16 consecutive deltas per lane)
 constexpr int kTileNodesK2 = 512;   // K2: nodes per prefix tile
 constexpr int kBfsBlock = 1024;     // selection: BFS positions per block
 constexpr int kLog1pLut = 1 << 16;  // log1p(count) table computed on the host with glibc (bit-identical terms)
 constexpr u32 kNone = 0xFFFFFFFFu;
 
-struct NodeDelta {  // per-node parent-relative sums written by K1, read by K2 (40 B)
-    double raw, cos, wc, cont;
-    long long pres;
-};
-struct K1Tile {
-    u64 dBegin;     // first delta (local delta arrays)
-    u32 dCount;     // deltas in tile (<= kTileDeltas)
-    u32 lnBegin;    // first local node (kind 0) / the local node (kind 1)
-    u32 lnEnd;      // one past last local node (kind 0)
-    u32 kind;       // 0: whole nodes, 1: chunk of a node with more than kTileDeltas deltas
-    u32 bigSlot;    // kind 1: index of this chunk's partial
-    u32 bigNode;    // kind 1: index into bigNodes
-};
-struct BigNode { u32 localNode, firstPartial, nPartials, pad; };
+// per-node parent-relative sums written by K1 and read by K2: 9 u64 per node = raw, cos, wc, cont as fx128 (lo, hi) + presence
+constexpr int kDeltaWords = 9;
 struct __align__(16) TableSlot { u64 key; u32 count; u32 pad; };  // read seed table: one 16-byte slot = one 32-byte sector half
 struct __align__(16) DictSlot { u64 key; u32 id; u32 pad; };       // index dictionary: seed hash -> dense seed id
 
@@ -41,7 +28,6 @@ struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample
     unsigned touchedCount, pad0;
     unsigned recordCount[8];
     unsigned tieCount[8];
-    unsigned bigDone[1];  // (array of per-big-node counters lives elsewhere)
 };
 struct Selection {  // outcome of the tolerance chain for one metric
     double best;
@@ -61,8 +47,10 @@ struct DevIndexView {
     const u32* pc;     // [nLocalDeltas] parentCount (low 16) | childCount (high 16), int16 each
     const u64* lOff;   // [nLocal+1] delta offsets of local nodes
     const u32* lNode;  // [nLocal] global node id of a local node
-    const K1Tile* k1Tiles; u32 nK1Tiles;
-    const BigNode* bigNodes; u32 nBigNodes; u32 nBigPartials;
+    u64 nDeltaChunks; u64 nRealDeltas;
+    const u32* chunkNode;            // [nDeltaChunks+1]
+    const unsigned char* isBoundary; // [nLocal]
+    const u32* boundaryNodes; u32 nBoundary;
     // tree (global arrays)
     const u32* parent;     // [nNodes]
     const double* gMag;    // [nNodes] sqrt(genomeMagnitudeSquared)
@@ -95,9 +83,7 @@ struct WorkspaceView {
     double* ell;          // [nSeeds] log1p(read count) of seed id, 0 when absent
     u32* touched; u32 touchedCap;
     unsigned* countHist;  // [kLog1pLut] multiplicity of every read count among the kept seeds (rounding-drift model)
-    NodeDelta* delta;     // [nNodes]
-    NodeDelta* bigPartial;
-    unsigned* bigDone;    // [nBigNodes]
+    u64* deltaFx;         // [nNodes][kDeltaWords]
     u64* chainA;          // [chainTotal][9]
     double* scores;       // [nNodes][5]
     double* metrics;      // [nNodes][5] or null

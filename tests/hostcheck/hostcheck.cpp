@@ -80,46 +80,87 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
         }
         const double denW = fxToDouble(wc);
         *wcDenOut = denW;
-        // K1: every K1 tile must cover its nodes exactly once
-        struct ND { double raw, cos, wc, cont; long long pres; };
-        std::vector<ND> delta(F.N, ND{0, 0, 0, 0, 0});
-        std::vector<int> seen(F.nLocal, 0);
+        // K1 (node_deltas): warp-per-chunk emulation -- 32 lanes x 16 deltas, interior stores, segmented scan over the lanes'
+        // trailing partials, boundary nodes through (here: plain) accumulation, repeats added afterwards
+        struct Tot { fx128 raw, cos, wc, cont; long long pres; };
+        auto tz = []() { Tot t; t.raw = t.cos = t.wc = t.cont = fxZero(); t.pres = 0; return t; };
+        auto tadd = [](const Tot& x, const Tot& y) { Tot r; r.raw = fxAdd(x.raw, y.raw); r.cos = fxAdd(x.cos, y.cos); r.wc = fxAdd(x.wc, y.wc); r.cont = fxAdd(x.cont, y.cont); r.pres = x.pres + y.pres; return r; };
+        std::vector<Tot> delta(F.N, tz());
+        std::vector<int> written(F.nLocal, 0);
         std::vector<double> l1p(32768); for (int c = 0; c < 32768; ++c) l1p[c] = std::log1p((double)c);
         const double ln2 = std::log1p(1.0);
-        auto contrib = [&](u64 gi, double& S, int& cnt, double& gr, double& gc, double& gw, double& gt, int& gp) {
-            const uint32_t pcv = F.pc[gi]; const int p = (int)(short)(pcv & 0xFFFF), c = (int)(short)(pcv >> 16);
-            if (p == c) return;
-            const double lr = ell[F.seedId[gi]];
-            if (!(lr > 0.0)) return;
-            if ((unsigned)p <= 1u && (unsigned)c <= 1u) { const double v = c > p ? lr : -lr; S += v; cnt += (v > 0) - (v < 0); }
-            else { const DeltaTerms t = deltaTerms(lr, p, c, p > 0 ? l1p[p] : 0.0, c > 0 ? l1p[c] : 0.0); gr += t.raw; gc += t.cos; gw += t.wc; gt += t.cont; gp += t.pres; }
+        const u64 dReal = F.nLocalDeltas;
+        auto nodeOf = [&](uint32_t lo, uint32_t hi, u64 d) { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.lOff[mid + 1] > d) hi = mid; else lo = mid + 1; } return lo; };
+        auto emit = [&](uint32_t ln, const Tot& t) {
+            if (F.isBoundary[ln]) delta[F.lNode[ln]] = tadd(delta[F.lNode[ln]], t);
+            else { if (written[ln]++) throw std::runtime_error("non-boundary node emitted twice"); delta[F.lNode[ln]] = t; }
         };
-        std::vector<ND> partial(F.nBigPartials ? F.nBigPartials : 1);
-        for (const HostK1Tile& t : F.k1Tiles) {
-            if (t.dCount > 4096) throw std::runtime_error("tile too large");
-            if (t.kind == 0) {
-                if (t.dBegin != F.lOff[t.lnBegin]) throw std::runtime_error("tile delta begin mismatch");
-                if (F.lOff[t.lnEnd] - F.lOff[t.lnBegin] != t.dCount) throw std::runtime_error("tile delta count mismatch");
-                for (uint32_t ln = t.lnBegin; ln < t.lnEnd; ++ln) {
-                    double S = 0, gr = 0, gc = 0, gw = 0, gt = 0; int cnt = 0, gp = 0;
-                    for (u64 j = F.lOff[ln]; j < F.lOff[ln + 1]; ++j) contrib(j, S, cnt, gr, gc, gw, gt, gp);
-                    delta[F.lNode[ln]] = ND{S + gr, S * ln2 + gc, (double)cnt + gw, S + gt, (long long)cnt + gp};
-                    seen[ln]++;
+        if (F.seedId.size() != F.nDeltaChunks * 512 || F.chunkNode.size() != F.nDeltaChunks + 1) throw std::runtime_error("chunk schedule size mismatch");
+        for (u64 c = 0; c < F.nDeltaChunks; ++c) {
+            bool has[32], single[32]; uint32_t nf[32], nl[32]; Tot acc[32], tFirst[32];
+            std::vector<std::pair<u64, int>> general;
+            const uint32_t n0 = F.chunkNode[c], n1 = F.chunkNode[c + 1];
+            for (int lane = 0; lane < 32; ++lane) {
+                const u64 d0 = c * 512 + (u64)lane * 16;
+                has[lane] = d0 < dReal; acc[lane] = tz(); tFirst[lane] = tz(); single[lane] = true; nf[lane] = nl[lane] = 0;
+                if (!has[lane]) continue;
+                uint32_t node = nodeOf(n0, n1, d0);
+                if (!(F.lOff[node] <= d0 && d0 < F.lOff[node + 1])) throw std::runtime_error("nodeOfDelta landed on the wrong node");
+                nf[lane] = node;
+                u64 nextOff = F.lOff[node + 1];
+                bool firstDone = false;
+                for (int j = 0; j < 16; ++j) {
+                    const u64 idx = d0 + j;
+                    if (idx >= dReal) continue;
+                    if (idx >= nextOff) {
+                        if (!firstDone) { tFirst[lane] = acc[lane]; firstDone = true; }
+                        else { if (F.isBoundary[node]) throw std::runtime_error("interior node flagged boundary"); if (written[node]++) throw std::runtime_error("interior node written twice"); delta[F.lNode[node]] = acc[lane]; }
+                        acc[lane] = tz();
+                        do { ++node; nextOff = F.lOff[node + 1]; } while (idx >= nextOff);
+                    }
+                    const uint32_t pcv = F.pc[idx]; const int p = (int)(short)(pcv & 0xFFFF), cc = (int)(short)(pcv >> 16);
+                    const double lr = ell[F.seedId[idx]];
+                    if (p != cc && lr > 0.0) {
+                        if ((unsigned)p <= 1u && (unsigned)cc <= 1u) {
+                            const fx128 fl = fxFromDouble(lr), fc = fxFromDouble(lr * ln2);
+                            Tot& a = acc[lane];
+                            if (cc > p) { a.raw = fxAdd(a.raw, fl); a.cont = fxAdd(a.cont, fl); a.cos = fxAdd(a.cos, fc); a.wc.hi += 1; a.pres += 1; }
+                            else { a.raw = fxSub(a.raw, fl); a.cont = fxSub(a.cont, fl); a.cos = fxSub(a.cos, fc); a.wc.hi -= 1; a.pres -= 1; }
+                        } else general.push_back({idx, lane});
+                    }
                 }
-            } else {
-                double S = 0, gr = 0, gc = 0, gw = 0, gt = 0; int cnt = 0, gp = 0;
-                for (u64 j = t.dBegin; j < t.dBegin + t.dCount; ++j) contrib(j, S, cnt, gr, gc, gw, gt, gp);
-                partial[t.bigSlot] = ND{S + gr, S * ln2 + gc, (double)cnt + gw, S + gt, (long long)cnt + gp};
+                nl[lane] = node; single[lane] = !firstDone;
+            }
+            Tot incl[32]; int head[32]; bool contPrev[32];
+            for (int lane = 0; lane < 32; ++lane) {
+                contPrev[lane] = has[lane] && lane > 0 && has[lane - 1] && nl[lane - 1] == nf[lane];
+                head[lane] = (single[lane] && contPrev[lane]) ? 0 : 1;
+                incl[lane] = acc[lane];
+            }
+            for (int d = 1; d < 32; d <<= 1) {   // Hillis-Steele segmented scan, all lanes read the previous step's values
+                Tot up[32]; int hup[32];
+                for (int lane = 0; lane < 32; ++lane) { up[lane] = incl[lane >= d ? lane - d : lane]; hup[lane] = head[lane >= d ? lane - d : lane]; }
+                for (int lane = 0; lane < 32; ++lane) if (lane >= d && !head[lane]) { incl[lane] = tadd(incl[lane], up[lane]); head[lane] = hup[lane]; }
+            }
+            for (int lane = 0; lane < 32; ++lane) {
+                if (!has[lane]) continue;
+                if (!single[lane]) emit(nf[lane], contPrev[lane] ? tadd(incl[lane - 1], tFirst[lane]) : tFirst[lane]);
+                const bool hasNext = lane < 31 && has[lane + 1];
+                if (!(hasNext && nf[lane + 1] == nl[lane])) emit(nl[lane], incl[lane]);
+            }
+            for (auto& g : general) {
+                const u64 idx = g.first;
+                const uint32_t pcv = F.pc[idx]; const int p = (int)(short)(pcv & 0xFFFF), cc = (int)(short)(pcv >> 16);
+                const DeltaTerms t = deltaTerms(ell[F.seedId[idx]], p, cc, p > 0 ? l1p[p] : 0.0, cc > 0 ? l1p[cc] : 0.0);
+                Tot gt; gt.raw = fxFromDouble(t.raw); gt.cos = fxFromDouble(t.cos); gt.wc = fxFromDouble(t.wc); gt.cont = fxFromDouble(t.cont); gt.pres = t.pres;
+                const uint32_t ln = nodeOf(n0, n1, idx);
+                delta[F.lNode[ln]] = tadd(delta[F.lNode[ln]], gt);
             }
         }
-        for (const HostBigNode& b : F.bigNodes) {
-            ND s{0, 0, 0, 0, 0};
-            for (uint32_t k = 0; k < b.nPartials; ++k) { const ND& p = partial[b.firstPartial + k]; s.raw += p.raw; s.cos += p.cos; s.wc += p.wc; s.cont += p.cont; s.pres += p.pres; }
-            delta[F.lNode[b.localNode]] = s; seen[b.localNode]++;
-        }
-        for (uint32_t i = 0; i < F.nLocal; ++i) if (seen[i] != 1) throw std::runtime_error("local node not covered exactly once by K1 tiles");
+        for (uint32_t i = 0; i < F.nLocal; ++i)
+            if (F.lOff[i + 1] > F.lOff[i] && !F.isBoundary[i] && written[i] != 1) throw std::runtime_error("a node with deltas was not written exactly once");
         // K2 tile algorithm
-        auto fromND = [](const ND& n) { Acc a; a.f[0] = fxFromDouble(n.raw); a.f[1] = fxFromDouble(n.cos); a.f[2] = fxFromDouble(n.wc); a.f[3] = fxFromDouble(n.cont); a.pres = n.pres; return a; };
+        auto fromND = [](const Tot& n) { Acc a; a.f[0] = n.raw; a.f[1] = n.cos; a.f[2] = n.wc; a.f[3] = n.cont; a.pres = n.pres; return a; };
         SampleScalars S; std::memset(&S, 0, sizeof(S));
         S.readMagnitude = mag; S.logContDenom = denL; S.wcDenom = denW; S.uniqueKept = U1;
         for (uint32_t tile = 0; tile < F.nK2Tiles; ++tile) {
