@@ -80,12 +80,12 @@ struct pm_host_index { HostIndex h; };
 struct pm_index {
     int device = 0; int nSM = 148;
     FlatIndex F;  // host copy of the small arrays (tree) is kept for result assembly; big vectors are released
-    DevBuf<u32> seedId, pc, lNode, parent, closeOff, closeList, carrySlot, chainOff, chainNodes, bfsNodes, bfsRanks;
-    DevBuf<u64> lOff, dictHash, homo;
+    DevBuf<u32> dw, chunkSeg, nodeSeg, boundarySegs, genSlot, genId, genPc, evSlot, evIdx, rootId, rootChild;
+    DevBuf<u32> parent, closeOff, closeList, carrySlot, chainOff, chainNodes, bfsNodes, bfsRanks;
+    DevBuf<u64> dictHash, homo;
     DevBuf<DictSlot> dict;
     DevBuf<double> gMag, log1pLut, log1pSmall;
     DevBuf<unsigned char> isLeaf;
-    DevBuf<u32> chunkNode, boundaryNodes; DevBuf<unsigned char> isBoundary;
     DevBuf<SeedTables> seedTables;
     DevIndexView view{};
     std::vector<double> gMagSqHost; std::vector<int64_t> gUniqueHost;
@@ -104,9 +104,9 @@ struct pm_workspace {
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0;
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
-    DevBuf<double> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist;
-    DevBuf<u64> deltaFx;
-    DevBuf<u64> chainA;
+    DevBuf<long long> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist;
+    DevBuf<SegRec> segRec, chainA;
+    DevBuf<u64> genRec, evPrefix;
     DevBuf<double> scores, metrics, blockMaxAndBfs;
     DevBuf<u32> recRank, recNode; DevBuf<double> recScore; u32 recCap = 0;
     DevBuf<u32> tieNode; u32 tieCap = 0; DevBuf<u32> selCounts;
@@ -130,9 +130,10 @@ void buildViews(pm_index* I) {
     DevIndexView& V = I->view;
     V.nNodes = F.N; V.nodeBegin = F.nodeBegin; V.nodeEnd = F.nodeEnd; V.nLocal = F.nLocal; V.nAnc = F.nAnc;
     V.nLocalDeltas = F.nLocalDeltas; V.nSeeds = F.S;
-    V.seedId = I->seedId.p; V.pc = I->pc.p; V.lOff = I->lOff.p; V.lNode = I->lNode.p;
-    V.nDeltaChunks = F.nDeltaChunks; V.nRealDeltas = F.nLocalDeltas; V.chunkNode = I->chunkNode.p; V.isBoundary = I->isBoundary.p;
-    V.boundaryNodes = I->boundaryNodes.p; V.nBoundary = (u32)F.boundaryNodes.size();
+    V.dw = I->dw.p; V.nDeltaChunks = F.nDeltaChunks; V.chunkSeg = I->chunkSeg.p; V.nodeSeg = I->nodeSeg.p;
+    V.boundarySegs = I->boundarySegs.p; V.nBoundary = (u32)F.boundarySegs.size(); V.nSeg = F.nSeg;
+    V.genSlot = I->genSlot.p; V.genId = I->genId.p; V.genPc = I->genPc.p; V.nGenDeltas = (u32)F.genSlot.size(); V.nGenNodes = F.nGenNodes;
+    V.evSlot = I->evSlot.p; V.nEvents = (u32)F.evSlot.size(); V.evIdx = F.nGenNodes ? I->evIdx.p : nullptr;
     V.parent = I->parent.p; V.gMag = I->gMag.p; V.closeOff = I->closeOff.p; V.closeList = I->closeList.p;
     V.carrySlot = I->carrySlot.p; V.chainOff = I->chainOff.p; V.chainNodes = I->chainNodes.p;
     V.nK2Tiles = F.nK2Tiles; V.chainTotal = (u32)F.chainNodes.size();
@@ -140,7 +141,7 @@ void buildViews(pm_index* I) {
     V.bfsNodes = I->bfsNodes.p; V.bfsRanks = I->bfsRanks.p; V.nShardNodes = F.nodeEnd - F.nodeBegin;
     V.nBfsBlocks = (V.nShardNodes + kBfsBlock - 1) / kBfsBlock;
     V.dict = I->dict.p; V.dictMask = F.dictMask; V.dictHash = I->dictHash.p;
-    V.rootDBegin = F.rootDBegin; V.rootDCount = F.rootDCount; V.hasRoot = 1;
+    V.rootId = I->rootId.p; V.rootChild = I->rootChild.p; V.rootDCount = (u32)F.rootId.size(); V.hasRoot = 1;
     V.log1pLut = I->log1pLut.p; V.log1pSmall = I->log1pSmall.p;
     V.ln2 = std::log1p(1.0);
 }
@@ -158,7 +159,9 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
         I->nSM = prop.multiProcessorCount;
         FlatIndex& F = I->F;
-        I->seedId.upload(F.seedId); I->pc.upload(F.pc); I->lNode.upload(F.lNode); I->lOff.upload(F.lOff);
+        I->dw.upload(F.dw); I->chunkSeg.upload(F.chunkSeg); I->nodeSeg.upload(F.nodeSeg); I->boundarySegs.upload(F.boundarySegs);
+        I->genSlot.upload(F.genSlot); I->genId.upload(F.genId); I->genPc.upload(F.genPc); I->evSlot.upload(F.evSlot); I->evIdx.upload(F.evIdx);
+        I->rootId.upload(F.rootId); I->rootChild.upload(F.rootChild);
         I->parent.upload(F.parent); I->gMag.upload(F.gMag); I->closeOff.upload(F.closeOff); I->closeList.upload(F.closeList);
         I->carrySlot.upload(F.carrySlot); I->chainOff.upload(F.chainOff); I->chainNodes.upload(F.chainNodes);
         I->isLeaf.upload(F.isLeaf); I->bfsNodes.upload(F.bfsNodes); I->bfsRanks.upload(F.bfsRanks);
@@ -168,7 +171,6 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
             I->dict.upload(d);
         }
         I->dictHash.upload(F.dictHash);
-        I->chunkNode.upload(F.chunkNode); I->isBoundary.upload(F.isBoundary); I->boundaryNodes.upload(F.boundaryNodes);
         {
             std::vector<double> lut(kLog1pLut), small(32768);
             for (int c = 0; c < kLog1pLut; ++c) lut[c] = std::log1p((double)c);
@@ -183,7 +185,7 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
         I->gMagSqHost = F.gMagSq; I->gUniqueHost = F.gUnique;
         buildViews(I.get());
         // release the big host vectors (the device now owns them)
-        std::vector<u32>().swap(F.seedId); std::vector<u32>().swap(F.pc); std::vector<u64>().swap(F.dictKeys);
+        std::vector<u32>().swap(F.dw); std::vector<u32>().swap(F.nodeSeg); std::vector<u32>().swap(F.evIdx); std::vector<u64>().swap(F.dictKeys);
         std::vector<u32>().swap(F.dictVals); std::vector<u64>().swap(F.dictHash);
         std::vector<double>().swap(F.gMagSq); std::vector<int64_t>().swap(F.gUnique);
         *out = I.release();
@@ -196,7 +198,7 @@ void refreshView(pm_workspace* W) {
     V.table = W->table.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
     V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
     V.acc = W->acc.p; V.ell = W->ell.p; V.touched = W->touched.p; V.touchedCap = (u32)W->touched.n; V.countHist = W->countHist.p;
-    V.deltaFx = W->deltaFx.p; V.chainA = W->chainA.p;
+    V.segRec = W->segRec.p; V.chainA = W->chainA.p; V.genRec = W->genRec.p; V.evPrefix = W->evPrefix.p;
     V.scores = W->scores.p; V.metrics = W->wantMetrics ? W->metrics.p : nullptr; V.blockMax = W->blockMaxAndBfs.p;
     V.recRank = W->recRank.p; V.recNode = W->recNode.p; V.recScore = W->recScore.p; V.recCap = W->recCap;
     V.tieNode = W->tieNode.p; V.tieCap = W->tieCap; V.sel = W->sel.p; V.scalars = W->scalars.p;
@@ -321,6 +323,7 @@ void stageScore(pm_workspace* W, const pm_place_params& prm) {
     launchFinalize(I->view, W->view, O, I->homo.p, W->st);
     CK(cudaEventRecord(W->ev[3], W->st));
     launchDeltas(I->view, W->view, I->nSM, W->st);
+    launchGeneral(I->view, W->view, W->st);
     CK(cudaEventRecord(W->ev[4], W->st));
     launchPrefixScores(I->view, W->view, O, W->st);
     CK(cudaEventRecord(W->ev[5], W->st));
@@ -411,7 +414,7 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
         launchTies(I->view, W->view, makeOpts(*prm, false), W->st);
         CK(cudaEventRecord(W->ev[6], W->st));
         fetchSmall(W);
-        launchResetEll(W->view, W->st);
+        launchResetSample(I->view, W->view, W->st);
         const bool tableTight = (u64)W->hAcc.entries * 10 > W->tableCap * 7;
         if (W->hAcc.overflow || tableTight) {
             // grow and redo: the table (or a list) was too small for this sample
@@ -506,11 +509,12 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
         W->acc.alloc(1); W->scalars.alloc(1); W->sel.alloc(5);
-        W->ell.alloc(F.S ? F.S : 1); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(double), W->st));
+        W->ell.alloc(F.S + 1); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(long long), W->st));   // [S] is the always-zero slot of the padding words
         W->touched.alloc(F.S ? F.S : 1);
         W->countHist.alloc(kLog1pLut);
-        W->deltaFx.alloc(F.N * kDeltaWords); CK(cudaMemsetAsync(W->deltaFx.p, 0, F.N * kDeltaWords * sizeof(u64), W->st));   // nodes without deltas stay 0
-        W->chainA.alloc((size_t)(V.chainTotal ? V.chainTotal : 1) * 9);
+        W->segRec.alloc(F.nSeg + 1); CK(cudaMemsetAsync(W->segRec.p, 0, W->segRec.n * sizeof(SegRec), W->st));
+        W->chainA.alloc(V.chainTotal ? V.chainTotal : 1);
+        W->genRec.alloc((size_t)(F.nGenNodes ? F.nGenNodes : 1) * kGenWords); W->evPrefix.alloc((size_t)(V.nEvents ? V.nEvents : 1) * kGenWords);
         W->scores.alloc(F.N * 5); CK(cudaMemsetAsync(W->scores.p, 0, F.N * 5 * sizeof(double), W->st));
         W->blockMaxAndBfs.alloc((size_t)V.nBfsBlocks * 5 + (size_t)V.nShardNodes * 5 + 8);
         W->recCap = V.nShardNodes ? V.nShardNodes : 1;
@@ -587,7 +591,7 @@ int pm_get_node_metrics(pm_workspace* ws, double* out) {
         launchFinalize(I->view, ws->view, O, I->homo.p, ws->st);
         launchDeltas(I->view, ws->view, I->nSM, ws->st);
         launchPrefixScores(I->view, ws->view, O, ws->st);
-        launchResetEll(ws->view, ws->st);
+        launchResetSample(ws->idx->view, ws->view, ws->st);
         CK(cudaMemcpyAsync(out, ws->metrics.p, I->F.N * 5 * sizeof(double), cudaMemcpyDeviceToHost, ws->st));
         CK(cudaStreamSynchronize(ws->st));
         ws->wantMetrics = false; refreshView(ws);
@@ -897,7 +901,7 @@ int pm_stage_select(pm_workspace* ws, const uint32_t* counts, const uint32_t* co
         launchChain(ws->view, dCounts.p, ws->st);
         launchTies(I->view, ws->view, makeOpts(ws->lastParams, false), ws->st);
         fetchSmall(ws);
-        launchResetEll(ws->view, ws->st);
+        launchResetSample(ws->idx->view, ws->view, ws->st);
         fetchTies(ws);  // local ties + the best node (every rank adds it; the caller unions the lists)
         std::memset(result, 0, sizeof(*result));
         fillResult(ws, result, total_reads);

@@ -2,13 +2,14 @@
 //
 // Input: the reference's flat view of a LiteIndex (pm_index_desc; placement.cpp:1021-1092).  Output (FlatIndex):
 //   * dense seed ids in first-appearance order along the DFS + per-node deltas re-sorted by seed id
-//     (12 B/delta -> 8 B/delta, and the per-delta hash probe becomes an array gather with locality: a node's
+//     (12 B/delta -> 4 B/delta, and the per-delta hash probe becomes an array gather with locality: a node's
 //     lost seeds are mostly ancestral low ids, its new seeds are a contiguous fresh id range)
 //   * NodeMetrics::genomeMagnitudeSquared / genomeUniqueSeedCount per node, accumulated in exactly the reference's
 //     order (parent's value, then the node's deltas in stored order; placement.cpp:289-302,772-774) -> bit-identical
 //   * DFS subtree ends, depth, reference BFS ranks, leaf flags
 //   * "closers" CSR for the in-tile Euler-tour difference, ancestor chains + carry slots of the K2 tiles
-//   * delta-kernel schedule: 512-delta chunks, owner node of every chunk, nodes that span chunks
+//   * delta streams: one packed 32-bit word per 0<->1 delta in 512-word chunks with in-band segment ends, a side list for
+//     the rare deltas with a genome count >= 2 and the DFS-interval events of their tree prefix
 #include "pm_host.h"
 #include "pm_logic.cuh"
 
@@ -179,47 +180,81 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
     F.lNode.resize(F.nLocal);
     for (uint32_t i = 0; i < F.nAnc; ++i) F.lNode[i] = anc[i];
     for (uint32_t v = F.nodeBegin; v < F.nodeEnd; ++v) F.lNode[F.nAnc + (v - F.nodeBegin)] = v;
-    F.lOff.assign(F.nLocal + 1, 0);
-    for (uint32_t i = 0; i < F.nLocal; ++i) {
-        const uint32_t v = F.lNode[i];
-        F.lOff[i + 1] = F.lOff[i] + (d.node_offsets[v + 1] - d.node_offsets[v]);
-    }
-    F.nLocalDeltas = F.lOff[F.nLocal];
-    F.seedId.resize(F.nLocalDeltas); F.pc.resize(F.nLocalDeltas);
+    if (F.S >= (1ull << 30)) throw std::runtime_error("index has too many distinct seeds (2^30 limit of the packed delta word)");
     {
-        std::vector<std::pair<uint32_t, uint32_t>> tmp;
+        uint64_t nLocalDeltas = 0;
+        for (uint32_t i = 0; i < F.nLocal; ++i) nLocalDeltas += d.node_offsets[F.lNode[i] + 1] - d.node_offsets[F.lNode[i]];
+        F.nLocalDeltas = nLocalDeltas;
+    }
+    // ---- delta streams: one packed word per fast delta (sorted by seed id inside a node), side list for the rest ----
+    F.nodeSeg.assign(N, NONE);
+    F.dw.clear(); F.dw.reserve(static_cast<size_t>(F.nLocalDeltas + 512));
+    F.nSeg = 0; F.nGenNodes = 0;
+    std::vector<uint32_t> genNodes;   // global ids of the nodes that own general deltas, ascending
+    {
+        std::vector<uint32_t> ids;
         for (uint32_t i = 0; i < F.nLocal; ++i) {
             const uint32_t v = F.lNode[i];
             const uint64_t b = d.node_offsets[v], e = d.node_offsets[v + 1];
-            tmp.resize(static_cast<size_t>(e - b));
-            for (uint64_t j = b; j < e; ++j)
-                tmp[j - b] = {idAll[j], static_cast<uint32_t>(static_cast<uint16_t>(d.delta_parent[j])) |
-                                             (static_cast<uint32_t>(static_cast<uint16_t>(d.delta_child[j])) << 16)};
-            std::sort(tmp.begin(), tmp.end());
-            for (uint64_t j = 0; j < e - b; ++j) { F.seedId[F.lOff[i] + j] = tmp[j].first; F.pc[F.lOff[i] + j] = tmp[j].second; }
+            ids.clear();
+            bool hasGen = false;
+            for (uint64_t j = b; j < e; ++j) {
+                const int p = d.delta_parent[j], c = d.delta_child[j];
+                if (p == 0 && c == 1) ids.push_back(idAll[j]);
+                else if (p == 1 && c == 0) ids.push_back(idAll[j] | 0x40000000u);
+                else if (p != c) {
+                    if (!hasGen) { hasGen = true; genNodes.push_back(v); }
+                    F.genSlot.push_back(static_cast<uint32_t>(genNodes.size() - 1)); F.genId.push_back(idAll[j]);
+                    F.genPc.push_back(static_cast<uint32_t>(static_cast<uint16_t>(d.delta_parent[j])) |
+                                      (static_cast<uint32_t>(static_cast<uint16_t>(d.delta_child[j])) << 16));
+                }
+            }
+            if (ids.empty()) continue;
+            std::sort(ids.begin(), ids.end(), [](uint32_t x, uint32_t y) { return (x & 0x3FFFFFFFu) < (y & 0x3FFFFFFFu); });
+            ids.back() |= 0x80000000u;
+            F.dw.insert(F.dw.end(), ids.begin(), ids.end());
+            F.nodeSeg[v] = F.nSeg++;
         }
     }
-    // root's deltas in local storage (root is local node 0 whenever anything is local)
-    F.rootDBegin = 0; F.rootDCount = 0;
-    if (F.nLocal > 0 && F.lNode[0] == 0) { F.rootDBegin = F.lOff[0]; F.rootDCount = static_cast<uint32_t>(F.lOff[1] - F.lOff[0]); }
-
-    // ---- delta kernel schedule: chunks of 512 deltas ----
+    F.nFast = F.dw.size();
+    F.nGenNodes = static_cast<uint32_t>(genNodes.size());
     {
         const uint64_t CH = 512;
-        F.nDeltaChunks = (F.nLocalDeltas + CH - 1) / CH;
-        F.seedId.resize(F.nDeltaChunks * CH, 0); F.pc.resize(F.nDeltaChunks * CH, 0);   // padding: parent == child == 0 contributes nothing
-        F.chunkNode.assign(F.nDeltaChunks + 1, F.nLocal ? F.nLocal - 1 : 0);
-        F.isBoundary.assign(F.nLocal, 0);
-        uint32_t ln = 0;
+        F.nDeltaChunks = (F.nFast + CH - 1) / CH;
+        F.dw.resize(F.nDeltaChunks * CH, static_cast<uint32_t>(F.S));   // padding gathers ell[S] == 0, no sign, no segment end
+        F.chunkSeg.assign(F.nDeltaChunks + 1, 0);
+        uint32_t seg = 0;
         for (uint64_t c = 0; c < F.nDeltaChunks; ++c) {
-            const uint64_t d = c * CH;
-            while (ln + 1 < F.nLocal && F.lOff[ln + 1] <= d) ++ln;   // node with lOff[ln] <= d < lOff[ln+1]
-            F.chunkNode[c] = ln;
+            const bool inside = c > 0 && !(F.dw[c * CH - 1] >> 31) && c * CH < F.nFast;   // previous word did not end its segment
+            F.chunkSeg[c] = seg | (inside ? 0x80000000u : 0u);
+            if (inside) F.boundarySegs.push_back(seg);
+            for (uint64_t j = c * CH; j < (c + 1) * CH; ++j) seg += F.dw[j] >> 31;
         }
-        for (uint32_t i = 0; i < F.nLocal; ++i) {
-            const uint64_t b0 = F.lOff[i], e0 = F.lOff[i + 1];
-            if (e0 > b0 && b0 / CH != (e0 - 1) / CH) { F.isBoundary[i] = 1; F.boundaryNodes.push_back(F.lNode[i]); }
+        F.chunkSeg[F.nDeltaChunks] = seg;
+        if (seg != F.nSeg) throw std::runtime_error("internal: segment count mismatch");
+        F.boundarySegs.erase(std::unique(F.boundarySegs.begin(), F.boundarySegs.end()), F.boundarySegs.end());
+    }
+    // general deltas: A_gen[w] = sum over nodes u with general deltas and u <= w < subEnd[u]  ->  +u at position u, -u at subEnd[u]
+    if (!genNodes.empty()) {
+        std::vector<std::pair<uint32_t, uint32_t>> ev;   // (position, slot | sign)
+        for (uint32_t g = 0; g < genNodes.size(); ++g) {
+            ev.push_back({genNodes[g], g});
+            if (F.subEnd[genNodes[g]] < N) ev.push_back({F.subEnd[genNodes[g]], g | 0x80000000u});
         }
+        std::sort(ev.begin(), ev.end());
+        F.evSlot.resize(ev.size());
+        F.evIdx.assign(N, 0);
+        size_t e = 0;
+        for (uint64_t w = 0; w < N; ++w) {
+            while (e < ev.size() && ev[e].first <= w) { F.evSlot[e] = ev[e].second; ++e; }
+            F.evIdx[w] = static_cast<uint32_t>(e);
+        }
+        for (; e < ev.size(); ++e) F.evSlot[e] = ev[e].second;
+    }
+    // root's deltas (the root is always local)
+    for (uint64_t j = d.node_offsets[0]; j < d.node_offsets[1]; ++j) {
+        F.rootId.push_back(idAll[j]);
+        F.rootChild.push_back(static_cast<uint32_t>(static_cast<int32_t>(d.delta_child[j])));
     }
 
     // ---- K2 tiles: ancestor chains and carry slots ----

@@ -40,20 +40,29 @@ struct FlatIndex {
     std::vector<uint64_t> dictHash, dictKeys;
     std::vector<uint32_t> dictVals;
     uint64_t dictMask = 0;
-    // shard-local delta storage
-    std::vector<uint32_t> seedId, pc, lNode;
-    std::vector<uint64_t> lOff;
-    // delta kernel schedule: fixed chunks of 512 deltas (one warp each)
-    uint64_t nDeltaChunks = 0;                 // seedId / pc are padded to nDeltaChunks * 512 entries
-    std::vector<uint32_t> chunkNode;           // [nDeltaChunks+1] local node owning the chunk's first delta
-    std::vector<uint8_t> isBoundary;           // [nLocal] node has deltas in more than one chunk (its sums are combined with atomics)
-    std::vector<uint32_t> boundaryNodes;       // global ids of those nodes (their accumulators are zeroed per sample)
+    // shard-local delta storage (local nodes = ancestors of nodeBegin, root first, then the shard's nodes)
+    std::vector<uint32_t> lNode;               // [nLocal] global node id
+    // "fast" deltas = genome count 0 <-> 1 (all but a handful): one 32-bit word each, in node order.
+    //   bits 0..29 seed id | bit 30 seed lost (parent 1 -> child 0) | bit 31 last fast delta of its node ("segment" end)
+    // padded to whole 512-word chunks with words that gather the always-zero slot ell[S]
+    std::vector<uint32_t> dw;
+    uint64_t nFast = 0, nDeltaChunks = 0;
+    uint32_t nSeg = 0;                         // nodes with at least one fast delta, in local order
+    std::vector<uint32_t> chunkSeg;            // [nDeltaChunks+1] segments ending before the chunk | bit 31: chunk starts inside a segment
+    std::vector<uint32_t> nodeSeg;             // [N] segment of a (local) node, NONE otherwise
+    std::vector<uint32_t> boundarySegs;        // segments that span chunks: combined with atomics, zeroed per sample
+    // "general" deltas (a genome count >= 2 on either side; rare): side list + DFS-interval events for their tree prefix
+    std::vector<uint32_t> genSlot, genId, genPc;   // per general delta: slot of its node, seed id, parent | child << 16
+    uint32_t nGenNodes = 0;
+    std::vector<uint32_t> evSlot;              // events sorted by DFS position: slot | bit 31 = subtract (subtree of the node ended)
+    std::vector<uint32_t> evIdx;               // [N] number of events at positions <= w (empty when there are no general deltas)
+    // root's deltas (weighted-containment denominator)
+    std::vector<uint32_t> rootId, rootChild;
     // K2 tiles
     std::vector<uint32_t> carrySlot, chainOff, chainNodes;
     uint32_t nK2Tiles = 0;
     // selection
     std::vector<uint32_t> bfsNodes, bfsRanks;
-    uint64_t rootDBegin = 0; uint32_t rootDCount = 0;
     uint64_t homo[4] = {0, 0, 0, 0};
 };
 // shard `shard` of `nShards` (contiguous DFS ranges balanced by delta count); throws std::runtime_error on bad input

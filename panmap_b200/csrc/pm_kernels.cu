@@ -557,7 +557,7 @@ __device__ __forceinline__ u32 finalizeKept(const DevIndexView& I, const Workspa
     while (true) {  // is this seed anywhere in the index?
         const uint4 d = __ldg(reinterpret_cast<const uint4*>(I.dict) + s);
         const u64 dk = (u64)d.x | ((u64)d.y << 32);
-        if (dk == k) { W.ell[d.z] = l; return d.z; }
+        if (dk == k) { W.ell[d.z] = __double2ll_rn(l * kEllScale); return d.z; }   // l >= ln 2: an exact multiple of 2^-53
         if (dk == kEmptyKey) return kNone;
         s = (s + 1) & I.dictMask;
     }
@@ -645,9 +645,8 @@ __global__ void __launch_bounds__(256) table_finalize(DevIndexView I, WorkspaceV
 __global__ void __launch_bounds__(256) root_denominator(DevIndexView I, WorkspaceView W) {
     fx128 s = fxZero();
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < I.rootDCount; i += (u64)gridDim.x * blockDim.x) {
-        const u32 id = __ldg(&I.seedId[I.rootDBegin + i]);
-        const int c = (int)(short)(__ldg(&I.pc[I.rootDBegin + i]) >> 16);
-        if (c > 0 && W.ell[id] > 0.0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
+        const int c = (int)__ldg(&I.rootChild[i]);
+        if (c > 0 && W.ell[__ldg(&I.rootId[i])] != 0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
     }
     s = fxWarpSum(s);
     if ((threadIdx.x & 31) == 0) fxAtomicAdd(W.acc->wcDen, s);
@@ -739,174 +738,122 @@ void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* hom
     finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport);
 }
 
-__global__ void __launch_bounds__(256) reset_ell(WorkspaceView W) {
+// after a sample: clear exactly the ell entries it touched and the segment records that are combined with atomics
+__global__ void __launch_bounds__(256) reset_sample(DevIndexView I, WorkspaceView W) {
     const unsigned n = W.acc->touchedCount < W.touchedCap ? W.acc->touchedCount : W.touchedCap;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) W.ell[W.touched[i]] = 0.0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) W.ell[W.touched[i]] = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nBoundary; i += gridDim.x * blockDim.x)
+        *reinterpret_cast<uint4*>(W.segRec + I.boundarySegs[i]) = make_uint4(0u, 0u, 0u, 0u);
 }
-void launchResetEll(WorkspaceView W, cudaStream_t st) { reset_ell<<<148, 256, 0, st>>>(W); }
+void launchResetSample(DevIndexView I, WorkspaceView W, cudaStream_t st) { reset_sample<<<148, 256, 0, st>>>(I, W); }
 
 // ------------------------------------------------------------------------------------------------------
-// K1 node_deltas: one pass over the delta arrays, no shared memory, no block barriers.
-// A warp owns a chunk of 512 consecutive deltas; lane l owns deltas [16 l, 16 l + 16) of it, fetched with eight 16-byte
-// loads (the warp's loads are one contiguous 2 KB + 2 KB stream) followed by 16 independent gathers of log1p(read count).
-// Every per-delta term is converted to 128-bit fixed point before it is added, so all sums are exact and independent of
-// how deltas are split over lanes, warps, shards or GPUs:
-//   * nodes that begin and end inside a lane are stored directly;
-//   * a node spread over several lanes is combined with a segmented warp scan and stored by the lane where it ends;
-//   * a node spread over several chunks (flagged at flatten time, zeroed by zero_boundary first) is combined with
-//     fixed-point atomics;
-//   * deltas whose genome counts are >= 2 (repeats; rare) take the general formula afterwards and are added atomically.
-// Output: deltaFx[node] = {raw, cos, wc, cont as fx128, presence} parent-relative sums, read by prefix_scores.
+// K1 node_deltas: one pass over the packed delta words (4 B per delta), no shared memory, no block barriers.
+// A warp owns a chunk of 512 consecutive words; lane l owns words [16 l, 16 l + 16): four 16-byte loads, then 16
+// independent gathers of ell[seed id] (log1p(read count) as an exact integer, 0 when the seed is not in the reads).
+// Node boundaries travel in-band (bit 31 = last delta of its node), so no offset array is read and no search is needed:
+//   * a node that begins and ends inside a lane is stored directly (sums of <= 16 terms fit 64 bits);
+//   * a node spread over several lanes is combined with a segmented warp scan (96-bit) and stored by the lane where it ends;
+//   * a node spread over several chunks (listed at flatten time, zeroed by reset_sample) is combined with integer atomics.
+// All sums are integers, hence exact and independent of how deltas are split over lanes, warps, shards or GPUs.
+// Output: segRec[segment] = {sum of +-ell, #gained - #lost}, read by prefix_scores through nodeSeg[].
 // ------------------------------------------------------------------------------------------------------
-struct SegTot { fx128 raw, cos, wc, cont; i64 pres; };
-__device__ __forceinline__ SegTot segZero() { SegTot t; t.raw = t.cos = t.wc = t.cont = fxZero(); t.pres = 0; return t; }
-__device__ __forceinline__ SegTot segAdd(const SegTot& a, const SegTot& b) {
-    SegTot r; r.raw = fxAdd(a.raw, b.raw); r.cos = fxAdd(a.cos, b.cos); r.wc = fxAdd(a.wc, b.wc); r.cont = fxAdd(a.cont, b.cont);
-    r.pres = a.pres + b.pres; return r;
+__device__ __forceinline__ void segAtomicAdd(SegRec* r, u64 lo, int hi, int cnt) {
+    if (lo | (u64)(u32)hi) {
+        const u64 old = atomicAdd(reinterpret_cast<unsigned long long*>(&r->lo), (unsigned long long)lo);
+        const int h = hi + ((old + lo < old) ? 1 : 0);
+        if (h) atomicAdd(&r->hi, h);
+    }
+    if (cnt) atomicAdd(&r->cnt, cnt);
 }
-__device__ __forceinline__ SegTot segShflUp(const SegTot& a, int d) {
-    SegTot r;
-    r.raw.lo = shflUpU64(a.raw.lo, d); r.raw.hi = (i64)shflUpU64((u64)a.raw.hi, d);
-    r.cos.lo = shflUpU64(a.cos.lo, d); r.cos.hi = (i64)shflUpU64((u64)a.cos.hi, d);
-    r.wc.lo = shflUpU64(a.wc.lo, d); r.wc.hi = (i64)shflUpU64((u64)a.wc.hi, d);
-    r.cont.lo = shflUpU64(a.cont.lo, d); r.cont.hi = (i64)shflUpU64((u64)a.cont.hi, d);
-    r.pres = (i64)shflUpU64((u64)a.pres, d); return r;
-}
-__device__ __forceinline__ void segStore(u64* __restrict__ p, const SegTot& t) {
-    p[0] = t.raw.lo; p[1] = (u64)t.raw.hi; p[2] = t.cos.lo; p[3] = (u64)t.cos.hi; p[4] = t.wc.lo; p[5] = (u64)t.wc.hi;
-    p[6] = t.cont.lo; p[7] = (u64)t.cont.hi; p[8] = (u64)t.pres;
-}
-__device__ __forceinline__ void segAtomicAdd(u64* p, const SegTot& t) {
-    fxAtomicAdd(p + 0, t.raw); fxAtomicAdd(p + 2, t.cos); fxAtomicAdd(p + 4, t.wc); fxAtomicAdd(p + 6, t.cont);
-    if (t.pres) atomicAdd(reinterpret_cast<unsigned long long*>(p + 8), (unsigned long long)t.pres);
-}
-__device__ __forceinline__ void emitNode(const DevIndexView& I, u64* __restrict__ deltaFx, u32 ln, const SegTot& t) {
-    u64* p = deltaFx + (size_t)I.lNode[ln] * kDeltaWords;
-    if (I.isBoundary[ln]) segAtomicAdd(p, t); else segStore(p, t);
-}
-// local node owning delta d, searched in [lo, hi]
-__device__ __forceinline__ u32 nodeOfDelta(const u64* __restrict__ lOff, u32 lo, u32 hi, u64 d) {
-    while (lo < hi) { const u32 mid = (lo + hi) >> 1; if (__ldg(&lOff[mid + 1]) > d) hi = mid; else lo = mid + 1; }
-    return lo;
+__device__ __forceinline__ void segStore(SegRec* r, u64 lo, int hi, int cnt) {
+    *reinterpret_cast<uint4*>(r) = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)cnt);
 }
 
-__global__ void __launch_bounds__(256) zero_boundary(DevIndexView I, WorkspaceView W) {
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nBoundary * (u32)kDeltaWords; i += gridDim.x * blockDim.x)
-        W.deltaFx[(size_t)I.boundaryNodes[i / kDeltaWords] * kDeltaWords + (i % kDeltaWords)] = 0;
-}
-
-__global__ void __launch_bounds__(128) node_deltas(DevIndexView I, WorkspaceView W) {
-    const double* __restrict__ ell = W.ell;
-    const u64* __restrict__ lOff = I.lOff;
+__global__ void __launch_bounds__(256) node_deltas(DevIndexView I, WorkspaceView W) {
+    const long long* __restrict__ ell = W.ell;
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned ltMask = (1u << lane) - 1u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
-    const u64 dReal = I.nRealDeltas;
-    const double ln2 = I.ln2;
     for (u64 c = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < I.nDeltaChunks; c += warpsTotal) {
-        const u64 d0 = c * kChunkDeltas + lane * 16;
-        u32 id[16], pc[16];
+        u32 w[16];
         {
-            const uint4* pi = reinterpret_cast<const uint4*>(I.seedId + d0);
-            const uint4* pp = reinterpret_cast<const uint4*>(I.pc + d0);
+            const uint4* p = reinterpret_cast<const uint4*>(I.dw + c * kChunkWords + lane * 16);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint4 a = __ldcs(pi + q), b = __ldcs(pp + q);
-                id[4 * q] = a.x; id[4 * q + 1] = a.y; id[4 * q + 2] = a.z; id[4 * q + 3] = a.w;
-                pc[4 * q] = b.x; pc[4 * q + 1] = b.y; pc[4 * q + 2] = b.z; pc[4 * q + 3] = b.w;
+                const uint4 a = __ldg(p + q);
+                w[4 * q] = a.x; w[4 * q + 1] = a.y; w[4 * q + 2] = a.z; w[4 * q + 3] = a.w;
             }
         }
-        double lv[16];
+        long long e[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) lv[j] = __ldg(&ell[id[j]]);
-
-        const bool has = d0 < dReal;
-        const u32 n0 = I.chunkNode[c], n1 = I.chunkNode[c + 1];
-        u32 node = has ? nodeOfDelta(lOff, n0, n1, d0) : 0u;
-        const u32 nf = node;
-        u64 nextOff = has ? __ldg(&lOff[node + 1]) : ~0ULL;
-        SegTot acc = segZero(), tFirst = segZero();
-        bool firstDone = false;
-        unsigned genMask = 0;
+        for (int j = 0; j < 16; ++j) e[j] = __ldg(&ell[w[j] & 0x3FFFFFFFu]);
+        const u32 cs = __ldg(&I.chunkSeg[c]);
+        // segment index of this lane's first segment end: segments ending in earlier chunks + in earlier lanes
+        unsigned nEnd = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) nEnd += w[j] >> 31;
+        unsigned endsBefore = nEnd;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, endsBefore, d); if (lane >= (unsigned)d) endsBefore += o; }
+        const unsigned endsInChunk = __shfl_sync(0xffffffffu, endsBefore, 31);
+        endsBefore -= nEnd;
+        const u32 segFirst = (cs & 0x7FFFFFFFu) + endsBefore;
+        // ---- walk the 16 words: interior segments are stored, the first end is kept for after the scan ----
+        long long acc = 0, headV = 0; int cn = 0, headC = 0; unsigned k = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const u64 idx = d0 + j;
-            if (idx < dReal) {
-                if (idx >= nextOff) {   // the current node ended before this delta
-                    if (!firstDone) { tFirst = acc; firstDone = true; }
-                    else segStore(W.deltaFx + (size_t)I.lNode[node] * kDeltaWords, acc);   // began and ended inside this lane
-                    acc = segZero();
-                    do { ++node; nextOff = __ldg(&lOff[node + 1]); } while (idx >= nextOff);   // skips nodes without deltas
-                }
-                const int p = (int)(short)(pc[j] & 0xFFFFu), cc = (int)(short)(pc[j] >> 16);
-                const double lr = lv[j];
-                if (p != cc && lr > 0.0) {
-                    if ((unsigned)p <= 1u && (unsigned)cc <= 1u) {
-                        // 0 <-> 1 genome count: raw = cont = +-lr, cos = +-fl(lr * log1p(1)), wc = pres = +-1 (placement.cpp:315-339)
-                        const fx128 fl = fxFromDouble(lr), fc = fxFromDouble(lr * ln2);
-                        if (cc > p) { acc.raw = fxAdd(acc.raw, fl); acc.cont = fxAdd(acc.cont, fl); acc.cos = fxAdd(acc.cos, fc); acc.wc.hi += 1; acc.pres += 1; }
-                        else { acc.raw = fxSub(acc.raw, fl); acc.cont = fxSub(acc.cont, fl); acc.cos = fxSub(acc.cos, fc); acc.wc.hi -= 1; acc.pres -= 1; }
-                    } else genMask |= 1u << j;
-                }
+            const bool lost = (w[j] >> 30) & 1u;
+            acc += lost ? -e[j] : e[j];
+            cn += e[j] ? (lost ? -1 : 1) : 0;
+            if (w[j] >> 31) {
+                if (k == 0) { headV = acc; headC = cn; }
+                else segStore(W.segRec + segFirst + k, (u64)acc, (int)(acc >> 63), cn);
+                ++k; acc = 0; cn = 0;
             }
         }
-        const u32 nl = node;
-        const bool single = !firstDone;
-        // ---- combine the lanes' trailing partials: segmented inclusive scan, a run = consecutive lanes inside one node ----
-        const u32 nlPrev = __shfl_up_sync(0xffffffffu, nl, 1);
-        const bool hasPrev = __shfl_up_sync(0xffffffffu, (int)has, 1) != 0 && lane > 0;
-        const u32 nfNext = __shfl_down_sync(0xffffffffu, nf, 1);
-        const bool hasNext = __shfl_down_sync(0xffffffffu, (int)has, 1) != 0 && lane < 31;
-        const bool contPrev = has && hasPrev && nlPrev == nf;           // this lane starts inside the previous lane's last node
-        SegTot incl = acc;
-        int head = (single && contPrev) ? 0 : 1;
+        // ---- segmented inclusive scan over the lanes' trailing partials (a lane with a segment end restarts the run) ----
+        const unsigned endMask = __ballot_sync(0xffffffffu, nEnd != 0);
+        u64 lo = (u64)acc; int hi = (int)(acc >> 63); int rc = cn;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const SegTot up = segShflUp(incl, d);
-            const int hup = __shfl_up_sync(0xffffffffu, head, d);
-            if ((int)lane >= d && !head) { incl = segAdd(incl, up); head = hup; }
-        }
-        const SegTot inclPrev = segShflUp(incl, 1);
-        if (has) {
-            if (!single) emitNode(I, W.deltaFx, nf, contPrev ? segAdd(inclPrev, tFirst) : tFirst);   // first node of the lane ends here
-            if (!(hasNext && nfNext == nl)) emitNode(I, W.deltaFx, nl, incl);                           // the run of the last node ends here
-        }
-        // ---- repeats (a genome count >= 2 on either side): general formula, added atomically after the stores above ----
-        if (__any_sync(0xffffffffu, genMask != 0)) {
-            __syncwarp();
-            while (genMask) {
-                const int j = __ffs(genMask) - 1;
-                genMask &= genMask - 1;
-                const u64 idx = d0 + j;
-                const u32 pcv = __ldg(&I.pc[idx]);
-                const int p = (int)(short)(pcv & 0xFFFFu), cc = (int)(short)(pcv >> 16);
-                const double lr = __ldg(&ell[__ldg(&I.seedId[idx])]);
-                const DeltaTerms t = deltaTerms(lr, p, cc, p > 0 ? __ldg(&I.log1pSmall[p]) : 0.0, cc > 0 ? __ldg(&I.log1pSmall[cc]) : 0.0);
-                SegTot g; g.raw = fxFromDouble(t.raw); g.cos = fxFromDouble(t.cos); g.wc = fxFromDouble(t.wc); g.cont = fxFromDouble(t.cont); g.pres = t.pres;
-                const u32 ln = nodeOfDelta(lOff, n0, n1, idx);
-                segAtomicAdd(W.deltaFx + (size_t)I.lNode[ln] * kDeltaWords, g);
+            const u64 olo = shflUpU64(lo, d);
+            const int ohi = __shfl_up_sync(0xffffffffu, hi, d), oc = __shfl_up_sync(0xffffffffu, rc, d);
+            // lanes (lane-d, lane] must all be free of segment ends for the value of lane-d to flow into this lane
+            const unsigned span = (d == 31 ? 0x7FFFFFFFu : ((1u << d) - 1u)) << (lane - d + 1);
+            if (lane >= (unsigned)d && !(endMask & span)) {
+                const u64 nlo = lo + olo;
+                hi += ohi + (nlo < lo ? 1 : 0);
+                lo = nlo; rc += oc;
             }
+        }
+        // carry into this lane's first segment end = inclusive value of the previous lane
+        const u64 plo = shflUpU64(lo, 1);
+        const int phi = __shfl_up_sync(0xffffffffu, hi, 1), pc = __shfl_up_sync(0xffffffffu, rc, 1);
+        if (nEnd) {
+            u64 flo = (u64)headV; int fhi = (int)(headV >> 63); int fc = headC;
+            if (lane) { const u64 t = flo + plo; fhi += phi + (t < flo ? 1 : 0); flo = t; fc += pc; }
+            SegRec* dst = W.segRec + segFirst;
+            if ((cs >> 31) && !(endMask & ltMask)) segAtomicAdd(dst, flo, fhi, fc);   // the segment began in an earlier chunk
+            else segStore(dst, flo, fhi, fc);
+        }
+        if (lane == 31 && !(w[15] >> 31)) {   // the chunk ends inside a segment: hand the open run to the chunk where it ends
+            const u32 sNext = (cs & 0x7FFFFFFFu) + endsInChunk;
+            if (sNext < I.nSeg) segAtomicAdd(W.segRec + sNext, lo, hi, rc);
         }
     }
 }
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st) {
     if (I.nDeltaChunks == 0) return;
-    if (I.nBoundary) {
-        unsigned g = (I.nBoundary * kDeltaWords + 255) / 256; if (g > 148 * 4) g = 148 * 4;
-        zero_boundary<<<g, 256, 0, st>>>(I, W);
-    }
-    u64 grid = (I.nDeltaChunks + 3) / 4;
-    if (grid > (u64)nSM * 16) grid = (u64)nSM * 16;
-    node_deltas<<<(unsigned)grid, 128, 0, st>>>(I, W);
+    u64 grid = (I.nDeltaChunks + 7) / 8;
+    if (grid > (u64)nSM * 8) grid = (u64)nSM * 8;
+    node_deltas<<<(unsigned)grid, 256, 0, st>>>(I, W);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// K2 prefix_scores: A[v] = sum of delta over the root->v path, exact.
-// Tile = kTileNodesK2 consecutive DFS nodes.  The carry-in of a tile is the path root -> parent(first node),
-// whose per-node deltas were all written by K1, so every tile is independent (no inter-CTA dependency):
-//   1. exact inclusive scan along the precomputed ancestor chain -> A[ancestor j]
-//   2. d'[w] = delta[w] (+ A[parent(w)] when the parent lies outside the tile)
-//   3. Euler-tour difference inside the tile: diff[w] = d'[w] - sum_{u in tile, subtree(u) ends right before w} d'[u]
-//   4. inclusive scan of diff = A[w]; scores; store
+// general deltas (a genome count >= 2 on either side; 76 of 2.4 M deltas on sars_20000): the reference's formula per delta
+// (placement.cpp:282-339), exact fx128 atomics into the owning node's record, then the tree prefix of those records as an
+// inclusive scan over DFS-interval events (+node at its DFS index, -node where its subtree ends).
 // ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ Acc5 accZero() { Acc5 a; a.f[0] = a.f[1] = a.f[2] = a.f[3] = fxZero(); a.pres = 0; return a; }
 __device__ __forceinline__ Acc5 accAdd(const Acc5& a, const Acc5& b) {
@@ -915,11 +862,11 @@ __device__ __forceinline__ Acc5 accAdd(const Acc5& a, const Acc5& b) {
     for (int i = 0; i < 4; ++i) r.f[i] = fxAdd(a.f[i], b.f[i]);
     r.pres = a.pres + b.pres; return r;
 }
-__device__ __forceinline__ Acc5 accSub(const Acc5& a, const Acc5& b) {
+__device__ __forceinline__ Acc5 accNeg(const Acc5& a) {
     Acc5 r;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r.f[i] = fxSub(a.f[i], b.f[i]);
-    r.pres = a.pres - b.pres; return r;
+    for (int i = 0; i < 4; ++i) r.f[i] = fxNeg(a.f[i]);
+    r.pres = -a.pres; return r;
 }
 __device__ __forceinline__ Acc5 accShflUp(const Acc5& a, int d) {
     Acc5 r;
@@ -938,26 +885,106 @@ __device__ __forceinline__ Acc5 accLoad(const u64* p) {
     for (int i = 0; i < 4; ++i) { a.f[i].lo = p[2 * i]; a.f[i].hi = (i64)p[2 * i + 1]; }
     a.pres = (i64)p[8]; return a;
 }
-// block-wide inclusive scan over 256 threads (one Acc5 each); sWarp: 8*9 u64 of shared scratch
-__device__ __forceinline__ Acc5 blockInclusiveScan(Acc5 v, u64* sWarp) {
+__global__ void __launch_bounds__(256) gen_deltas(DevIndexView I, WorkspaceView W) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nGenDeltas; i += gridDim.x * blockDim.x) {
+        const long long e = __ldg(&W.ell[I.genId[i]]);
+        if (!e) continue;
+        const u32 pcv = I.genPc[i];
+        const int p = (int)(short)(pcv & 0xFFFFu), c = (int)(short)(pcv >> 16);
+        const DeltaTerms t = deltaTerms((double)e * kEllInvScale, p, c, p > 0 ? __ldg(&I.log1pSmall[p]) : 0.0, c > 0 ? __ldg(&I.log1pSmall[c]) : 0.0);
+        u64* r = W.genRec + (size_t)I.genSlot[i] * kGenWords;
+        fxAtomicAdd(r + 0, fxFromDouble(t.raw)); fxAtomicAdd(r + 2, fxFromDouble(t.cos));
+        fxAtomicAdd(r + 4, fxFromDouble(t.wc)); fxAtomicAdd(r + 6, fxFromDouble(t.cont));
+        if (t.pres) atomicAdd(reinterpret_cast<unsigned long long*>(r + 8), (unsigned long long)(long long)t.pres);
+    }
+}
+// single block: inclusive scan of the signed node records in event order
+__global__ void __launch_bounds__(256) gen_prefix(DevIndexView I, WorkspaceView W) {
+    __shared__ u64 sWarp[8 * kGenWords];
+    __shared__ u64 sCarry[kGenWords];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Acc5 carry = accZero();
+    for (u32 base = 0; base < I.nEvents; base += 256) {
+        const u32 j = base + threadIdx.x;
+        Acc5 v = accZero();
+        if (j < I.nEvents) {
+            const u32 s = I.evSlot[j];
+            v = accLoad(W.genRec + (size_t)(s & 0x7FFFFFFFu) * kGenWords);
+            if (s >> 31) v = accNeg(v);
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const Acc5 o = accShflUp(v, d); if (lane >= d) v = accAdd(v, o); }
+        if (lane == 31) accStore(sWarp + kGenWords * warp, v);
+        __syncthreads();
+        Acc5 pre = carry;
+        for (int q = 0; q < warp; ++q) pre = accAdd(pre, accLoad(sWarp + kGenWords * q));
+        v = accAdd(v, pre);
+        if (j < I.nEvents) accStore(W.evPrefix + (size_t)j * kGenWords, v);
+        if (threadIdx.x == 255) accStore(sCarry, v);
+        __syncthreads();
+        carry = accLoad(sCarry);
+        __syncthreads();
+    }
+}
+void launchGeneral(DevIndexView I, WorkspaceView W, cudaStream_t st) {
+    if (I.nGenNodes == 0) return;
+    cudaMemsetAsync(W.genRec, 0, (size_t)I.nGenNodes * kGenWords * sizeof(u64), st);
+    unsigned g = (I.nGenDeltas + 255) / 256; if (g > 148 * 8) g = 148 * 8;
+    gen_deltas<<<g, 256, 0, st>>>(I, W);
+    gen_prefix<<<1, 256, 0, st>>>(I, W);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K2 prefix_scores: A[v] = sum of the segment records over the root->v path, exact (96-bit integers + counts).
+// Tile = kTileNodesK2 consecutive DFS nodes.  The carry-in of a tile is the path root -> parent(first node),
+// whose records were all written by K1, so every tile is independent (no inter-CTA dependency):
+//   1. inclusive scan along the precomputed ancestor chain -> A[ancestor j]
+//   2. d'[w] = rec[w] (+ A[parent(w)] when the parent lies outside the tile)
+//   3. Euler-tour difference inside the tile: diff[w] = d'[w] - sum_{u in tile, subtree(u) ends right before w} d'[u]
+//   4. inclusive scan of diff = A[w]; add the general-delta prefix (event lookup) when the index has any; scores; store
+// ------------------------------------------------------------------------------------------------------
+struct Seg3 { u64 lo; int hi; int cnt; };
+__device__ __forceinline__ Seg3 s3Zero() { Seg3 z; z.lo = 0; z.hi = 0; z.cnt = 0; return z; }
+__device__ __forceinline__ Seg3 s3Add(const Seg3& a, const Seg3& b) {
+    Seg3 r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo ? 1 : 0); r.cnt = a.cnt + b.cnt; return r;
+}
+__device__ __forceinline__ Seg3 s3Sub(const Seg3& a, const Seg3& b) {
+    Seg3 r; r.lo = a.lo - b.lo; r.hi = a.hi - b.hi - (a.lo < b.lo ? 1 : 0); r.cnt = a.cnt - b.cnt; return r;
+}
+__device__ __forceinline__ Seg3 s3ShflUp(const Seg3& a, int d) {
+    Seg3 r; r.lo = shflUpU64(a.lo, d); r.hi = __shfl_up_sync(0xffffffffu, a.hi, d); r.cnt = __shfl_up_sync(0xffffffffu, a.cnt, d); return r;
+}
+__device__ __forceinline__ Seg3 s3Load(const SegRec* p) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    Seg3 r; r.lo = (u64)v.x | ((u64)v.y << 32); r.hi = (int)v.z; r.cnt = (int)v.w; return r;
+}
+__device__ __forceinline__ void s3Store(SegRec* p, const Seg3& a) {
+    *reinterpret_cast<uint4*>(p) = make_uint4((u32)a.lo, (u32)(a.lo >> 32), (u32)a.hi, (u32)a.cnt);
+}
+__device__ __forceinline__ Seg3 s3OfNode(const DevIndexView& I, const WorkspaceView& W, u32 v) {
+    const u32 s = __ldg(&I.nodeSeg[v]);
+    return s == kNone ? s3Zero() : s3Load(W.segRec + s);
+}
+// block-wide inclusive scan over 256 threads (one Seg3 each); sWarp: 8 records of shared scratch
+__device__ __forceinline__ Seg3 blockInclusiveScan(Seg3 v, SegRec* sWarp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const Acc5 o = accShflUp(v, d);
-        if (lane >= d) v = accAdd(v, o);
+        const Seg3 o = s3ShflUp(v, d);
+        if (lane >= d) v = s3Add(v, o);
     }
     __syncthreads();
-    if (lane == 31) accStore(sWarp + 9 * warp, v);
+    if (lane == 31) s3Store(sWarp + warp, v);
     __syncthreads();
-    Acc5 pre = accZero();
-    for (int w = 0; w < warp; ++w) pre = accAdd(pre, accLoad(sWarp + 9 * w));
-    return accAdd(v, pre);
+    Seg3 pre = s3Zero();
+    for (int q = 0; q < warp; ++q) pre = s3Add(pre, s3Load(sWarp + q));
+    return s3Add(v, pre);
 }
 
 __global__ void __launch_bounds__(256) prefix_scores(DevIndexView I, WorkspaceView W, PlaceOpts O) {
-    __shared__ u64 sD[kTileNodesK2 * 9];
-    __shared__ u64 sWarp[8 * 9];
-    __shared__ u64 sCarry[9];
+    __shared__ SegRec sD[kTileNodesK2];
+    __shared__ SegRec sWarp[8];
+    __shared__ SegRec sCarry;
     const u32 tile = blockIdx.x;
     const u32 a0 = I.nodeBegin + tile * kTileNodesK2;
     const u32 a1 = min(a0 + (u32)kTileNodesK2, I.nodeEnd);
@@ -966,60 +993,63 @@ __global__ void __launch_bounds__(256) prefix_scores(DevIndexView I, WorkspaceVi
 
     // 1. ancestor chain
     const u32 cb = I.chainOff[tile], ce = I.chainOff[tile + 1];
-    Acc5 carry = accZero();
+    Seg3 carry = s3Zero();
     for (u32 base = cb; base < ce; base += 256) {
-        Acc5 v = accZero();
+        Seg3 v = s3Zero();
         const u32 j = base + tid;
-        if (j < ce) v = accLoad(W.deltaFx + (size_t)I.chainNodes[j] * kDeltaWords);
+        if (j < ce) v = s3OfNode(I, W, I.chainNodes[j]);
         v = blockInclusiveScan(v, sWarp);
-        v = accAdd(v, carry);
-        if (j < ce) accStore(W.chainA + (size_t)j * 9, v);
-        if (tid == 255) accStore(sCarry, v);
+        v = s3Add(v, carry);
+        if (j < ce) s3Store(W.chainA + j, v);
+        if (tid == 255) s3Store(&sCarry, v);
         __syncthreads();
-        carry = accLoad(sCarry);
+        carry = s3Load(&sCarry);
         __syncthreads();
     }
     __syncthreads();
     // 2. d'
     for (u32 w = a0 + tid; w < a1; w += 256) {
-        Acc5 v = accLoad(W.deltaFx + (size_t)w * kDeltaWords);
+        Seg3 v = s3OfNode(I, W, w);
         const u32 cs = I.carrySlot[w];
-        if (cs != kNone) v = accAdd(v, accLoad(W.chainA + (size_t)(cb + cs) * 9));
-        accStore(sD + (size_t)(w - a0) * 9, v);
+        if (cs != kNone) v = s3Add(v, s3Load(W.chainA + cb + cs));
+        s3Store(sD + (w - a0), v);
     }
     __syncthreads();
     // 3+4. two consecutive nodes per thread
     const u32 w0 = a0 + 2 * tid;
-    Acc5 d[2];
+    Seg3 d[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const u32 w = w0 + q;
-        d[q] = accZero();
+        d[q] = s3Zero();
         if (w < a1) {
-            d[q] = accLoad(sD + (size_t)(w - a0) * 9);
+            d[q] = s3Load(sD + (w - a0));
             const u32 c0 = I.closeOff[w], c1 = I.closeOff[w + 1];
             for (u32 c = c0; c < c1; ++c) {
                 const u32 u = I.closeList[c];
-                if (u >= a0) d[q] = accSub(d[q], accLoad(sD + (size_t)(u - a0) * 9));
+                if (u >= a0) d[q] = s3Sub(d[q], s3Load(sD + (u - a0)));
             }
         }
     }
-    const Acc5 mine = accAdd(d[0], d[1]);
-    const Acc5 incl = blockInclusiveScan(mine, sWarp);
-    Acc5 run = accSub(incl, mine);
+    const Seg3 mine = s3Add(d[0], d[1]);
+    const Seg3 incl = blockInclusiveScan(mine, sWarp);
+    Seg3 run = s3Sub(incl, mine);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const u32 w = w0 + q;
         if (w < a1) {
-            run = accAdd(run, d[q]);
-            const double raw = fxToDouble(run.f[0]), cs = fxToDouble(run.f[1]), wc = fxToDouble(run.f[2]), ct = fxToDouble(run.f[3]);
+            run = s3Add(run, d[q]);
+            double num[5];
+            const u32 ne = I.nGenNodes ? __ldg(&I.evIdx[w]) : 0u;
+            if (ne) { const Acc5 g = accLoad(W.evPrefix + (size_t)(ne - 1) * kGenWords); nodeNumerators(run.lo, run.hi, run.cnt, &g, I.ln2, num); }
+            else nodeNumerators(run.lo, run.hi, run.cnt, nullptr, I.ln2, num);
             double sc[5];
-            nodeScores(raw, cs, (double)(u64)run.pres, wc, ct, I.gMag[w], S, sc);
+            nodeScores(num[0], num[1], num[2], num[3], num[4], I.gMag[w], S, sc);
             double* o = W.scores + (size_t)w * 5;
             o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3]; o[4] = sc[4];
             if (W.metrics) {
                 double* m = W.metrics + (size_t)w * 5;
-                m[0] = raw; m[1] = cs; m[2] = (double)run.pres; m[3] = wc; m[4] = ct;
+                m[0] = num[0]; m[1] = num[1]; m[2] = num[2]; m[3] = num[3]; m[4] = num[4];
             }
         }
     }

@@ -6,21 +6,23 @@
 
 namespace pm {
 
-constexpr int kChunkDeltas = 512;   // K1: deltas per warp chunk (16 consecutive deltas per lane)
+constexpr int kChunkWords = 512;    // K1: packed delta words per warp chunk (16 consecutive words per lane)
 constexpr int kTileNodesK2 = 512;   // K2: nodes per prefix tile
 constexpr int kBfsBlock = 1024;     // selection: BFS positions per block
 constexpr int kLog1pLut = 1 << 16;  // log1p(count) table computed on the host with glibc (bit-identical terms)
 constexpr u32 kNone = 0xFFFFFFFFu;
 
-// per-node parent-relative sums written by K1 and read by K2: 9 u64 per node = raw, cos, wc, cont as fx128 (lo, hi) + presence
-constexpr int kDeltaWords = 9;
+// Per-segment (= node with 0<->1 deltas) parent-relative sums written by K1 and read by K2, 16 bytes:
+//   sum = hi * 2^64 + lo, a signed 96-bit integer in units of 2^-53: the exact sum of +-log1p(readCount) over the node's seeds
+//   that are in the reads (log1p(count >= 1) >= ln 2, so every addend is a multiple of 2^-53);  cnt = #gained - #lost among those.
+// With genome counts 0 <-> 1 the reference's five numerators are functions of these two (placement.cpp:315-339):
+//   logRaw = logContainment = sum, logCosine = sum * log1p(1), weightedContainment = presence = cnt.
+struct __align__(16) SegRec { u64 lo; int hi; int cnt; };
+constexpr double kEllScale = 9007199254740992.0;           // 2^53
+constexpr double kEllInvScale = 1.0 / 9007199254740992.0;  // 2^-53
+constexpr int kGenWords = 9;   // general-delta accumulators per node: raw, cos, wc, cont as fx128 (lo, hi) + presence
 struct __align__(16) TableSlot { u64 key; u32 count; u32 pad; };  // read seed table: one 16-byte slot = one 32-byte sector half
 struct __align__(16) DictSlot { u64 key; u32 id; u32 pad; };       // index dictionary: seed hash -> dense seed id
-
-struct Acc5 {  // exact accumulator of the 5 per-node numerators
-    fx128 f[4];  // raw, cos, wc, cont
-    i64 pres;
-};
 
 struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample)
     u64 magSq[2], logSum[2], wcDen[2];  // fx128 as (lo, hi)
@@ -43,14 +45,15 @@ struct DevIndexView {
     u32 nAnc;
     u64 nLocalDeltas;
     u64 nSeeds;        // distinct seed hashes of the whole index
-    const u32* seedId; // [nLocalDeltas] dense seed id (first-appearance order along the DFS)
-    const u32* pc;     // [nLocalDeltas] parentCount (low 16) | childCount (high 16), int16 each
-    const u64* lOff;   // [nLocal+1] delta offsets of local nodes
-    const u32* lNode;  // [nLocal] global node id of a local node
-    u64 nDeltaChunks; u64 nRealDeltas;
-    const u32* chunkNode;            // [nDeltaChunks+1]
-    const unsigned char* isBoundary; // [nLocal]
-    const u32* boundaryNodes; u32 nBoundary;
+    const u32* dw;         // [nDeltaChunks*512] packed fast deltas: seed id | lost << 30 | segment end << 31
+    u64 nDeltaChunks;
+    const u32* chunkSeg;   // [nDeltaChunks+1] segments ending before the chunk | bit 31: the chunk starts inside a segment
+    const u32* nodeSeg;    // [nNodes] segment of a node, kNone when it has no fast deltas (or is not local)
+    const u32* boundarySegs; u32 nBoundary; u32 nSeg;
+    // general deltas (genome count >= 2 on a side)
+    const u32* genSlot; const u32* genId; const u32* genPc; u32 nGenDeltas; u32 nGenNodes;
+    const u32* evSlot; u32 nEvents;   // DFS-interval events of the nodes with general deltas
+    const u32* evIdx;      // [nNodes] events at positions <= w (null when nGenNodes == 0)
     // tree (global arrays)
     const u32* parent;     // [nNodes]
     const double* gMag;    // [nNodes] sqrt(genomeMagnitudeSquared)
@@ -68,8 +71,8 @@ struct DevIndexView {
     // dictionary: seed hash -> seed id
     const DictSlot* dict; u64 dictMask;
     const u64* dictHash;   // [nSeeds] id -> hash
-    // root's deltas (for the weighted-containment denominator): local range of global node 0
-    u64 rootDBegin; u32 rootDCount; u32 hasRoot;
+    // root's deltas (for the weighted-containment denominator)
+    const u32* rootId; const u32* rootChild; u32 rootDCount; u32 hasRoot;
     const double* log1pLut;  // [kLog1pLut]
     const double* log1pSmall; // [32768] log1p(genome count)
     double ln2;            // log1p(1.0) from the host libm
@@ -80,11 +83,13 @@ struct WorkspaceView {
     TableSlot* table; u64 tableMask; u64 tableCap;
     SampleAcc* acc;
     u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
-    double* ell;          // [nSeeds] log1p(read count) of seed id, 0 when absent
+    long long* ell;       // [nSeeds+1] log1p(read count) * 2^53 of seed id (an exact integer), 0 when absent; [nSeeds] stays 0
     u32* touched; u32 touchedCap;
     unsigned* countHist;  // [kLog1pLut] multiplicity of every read count among the kept seeds (rounding-drift model)
-    u64* deltaFx;         // [nNodes][kDeltaWords]
-    u64* chainA;          // [chainTotal][9]
+    SegRec* segRec;       // [nSeg]
+    SegRec* chainA;       // [chainTotal] prefix along each K2 tile's ancestor chain
+    u64* genRec;          // [nGenNodes][kGenWords]
+    u64* evPrefix;        // [nEvents][kGenWords] inclusive prefix of the events
     double* scores;       // [nNodes][5]
     double* metrics;      // [nNodes][5] or null
     double* blockMax;     // [nBfsBlocks][5]
@@ -115,10 +120,11 @@ void launchTableImport(WorkspaceView W, const u64* hash, const long long* count,
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st);
 void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, cudaStream_t st);
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st);
+void launchGeneral(DevIndexView I, WorkspaceView W, cudaStream_t st);
 void launchPrefixScores(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st);
 void launchRecords(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st);
 void launchChain(WorkspaceView W, const u32* recCountOverride, cudaStream_t st);
 void launchTies(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st);
-void launchResetEll(WorkspaceView W, cudaStream_t st);
+void launchResetSample(DevIndexView I, WorkspaceView W, cudaStream_t st);
 
 }  // namespace pm

@@ -263,6 +263,30 @@ PM_HD double fxToDouble(fx128 a) {  // round-to-nearest-even of the exact value
     return neg ? -d : d;
 }
 
+// ---- per-node numerators from the two accumulator families --------------------------------------------
+// Deltas with genome counts 0 <-> 1 ("fast", all but a handful) are summed as a signed 96-bit integer in units of 2^-53
+// (every log1p(readCount >= 1) is an exact multiple of 2^-53) plus a signed count; deltas with a genome count >= 2
+// ("general") keep the reference's five separate sums in fx128.  Both families are exact, so the tree prefix is
+// associative and the only roundings are the final conversions below.
+struct Acc5 {    // general-delta accumulators: raw, cos, wc, cont numerators + presence
+    fx128 f[4];
+    i64 pres;
+};
+PM_HD fx128 fxFromSeg(u64 lo, int hi) {  // 96-bit integer in units of 2^-53 -> fx128 (units of 2^-64)
+    fx128 r; r.lo = lo << 11; r.hi = (i64)((((u64)(i64)hi) << 11) | (lo >> 53)); return r;
+}
+// out: logRawNum, logCosNum, presence, weightedContainmentNum, logContainmentNum (placement.hpp:108-118)
+PM_HD void nodeNumerators(u64 lo, int hi, int cnt, const Acc5* g, double ln2, double* out) {
+    const fx128 S = fxFromSeg(lo, hi);
+    const double sd = fxToDouble(S);
+    if (!g) { out[0] = sd; out[1] = sd * ln2; out[2] = (double)cnt; out[3] = (double)cnt; out[4] = sd; return; }
+    out[0] = fxToDouble(fxAdd(S, g->f[0]));
+    out[1] = fxToDouble(fxAdd(fxFromDouble(sd * ln2), g->f[1]));
+    out[2] = (double)((i64)cnt + g->pres);
+    out[3] = fxToDouble(fxAdd(fxFromInt((i64)cnt), g->f[2]));
+    out[4] = fxToDouble(fxAdd(S, g->f[3]));
+}
+
 // ---- per-delta contribution (placement.cpp:282-339) ---------------------------------------------------
 struct DeltaTerms { double raw, cos, wc, cont; int pres; };
 // lr = log1p(readCount) of the seed (> 0), p/c = parent/child genome counts, logP/logC = log1p of them (0 when count<=0)

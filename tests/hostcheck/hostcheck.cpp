@@ -47,13 +47,17 @@ int hc_fx_sum(const double* x, int64_t n, double* fwd, double* rev) {
     return (a.lo == b.lo && a.hi == b.hi) ? 1 : 0;
 }
 
-struct Acc { fx128 f[4]; i64 pres; };
-static Acc accZ() { Acc a; for (auto& x : a.f) x = fxZero(); a.pres = 0; return a; }
-static Acc accAdd(const Acc& a, const Acc& b) { Acc r; for (int i = 0; i < 4; ++i) r.f[i] = fxAdd(a.f[i], b.f[i]); r.pres = a.pres + b.pres; return r; }
-static Acc accSub(const Acc& a, const Acc& b) { Acc r; for (int i = 0; i < 4; ++i) r.f[i] = fxSub(a.f[i], b.f[i]); r.pres = a.pres - b.pres; return r; }
+static Acc5 accZ() { Acc5 a; for (auto& x : a.f) x = fxZero(); a.pres = 0; return a; }
+static Acc5 accAdd(const Acc5& a, const Acc5& b) { Acc5 r; for (int i = 0; i < 4; ++i) r.f[i] = fxAdd(a.f[i], b.f[i]); r.pres = a.pres + b.pres; return r; }
+static Acc5 accNeg(const Acc5& a) { Acc5 r; for (int i = 0; i < 4; ++i) r.f[i] = fxNeg(a.f[i]); r.pres = -a.pres; return r; }
+struct Seg { u64 lo; int hi; int cnt; };
+static Seg segZ() { return Seg{0, 0, 0}; }
+static Seg segAdd(const Seg& a, const Seg& b) { Seg r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo ? 1 : 0); r.cnt = a.cnt + b.cnt; return r; }
+static Seg segSub(const Seg& a, const Seg& b) { Seg r; r.lo = a.lo - b.lo; r.hi = a.hi - b.hi - (a.lo < b.lo ? 1 : 0); r.cnt = a.cnt - b.cnt; return r; }
+static Seg segOf(long long v, int c) { return Seg{(u64)v, (int)(v >> 63), c}; }
 
-// CPU emulation of finalize + K1 + K2 for shard `shard` of `nShards`.
-// table: (hash sorted ascending, logv = log1p(count) or 0).  metrics out: [N][5] (only shard nodes are written),
+// CPU emulation of finalize + K1 (node_deltas, warp by warp) + general deltas + K2 (prefix_scores, tile by tile) for shard
+// `shard` of `nShards`.  table: (hash, logv = log1p(count) or 0).  metrics out: [N][5] (only shard nodes are written),
 // scores out: [N][5].  scal: U', magnitude, logSum, wcDenom.
 int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards, const uint64_t* tHash, const double* tLog, int64_t U,
                        double U1, double mag, double denL, double* metrics, double* scores, double* wcDenOut,
@@ -61,129 +65,141 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
     try {
         FlatIndex F; flattenIndex(*d, shard, nShards, F);
         *nodeBegin = F.nodeBegin; *nodeEnd = F.nodeEnd;
-        // ell by seed id through the dictionary table (as table_finalize does)
-        std::vector<double> ell(F.S, 0.0);
+        // ell by seed id through the dictionary table (as table_finalize does): log1p(count) * 2^53, an exact integer
+        std::vector<long long> ell(F.S + 1, 0);
         for (int64_t i = 0; i < U; ++i) {
             if (!(tLog[i] > 0.0)) continue;
             u64 s = mixKey(tHash[i]) & F.dictMask;
             while (true) {
-                if (F.dictKeys[s] == tHash[i]) { if (F.dictVals[s] != 0xFFFFFFFFu) ell[F.dictVals[s]] = tLog[i]; break; }
+                if (F.dictKeys[s] == tHash[i]) {
+                    if (F.dictVals[s] != 0xFFFFFFFFu) {
+                        const double sc = tLog[i] * 9007199254740992.0;
+                        if (sc != std::floor(sc) || sc >= 9.2e18) throw std::runtime_error("log1p(count) is not a multiple of 2^-53");
+                        ell[F.dictVals[s]] = (long long)sc;
+                    }
+                    break;
+                }
                 if (F.dictVals[s] == 0xFFFFFFFFu && F.dictKeys[s] == kEmptyKey) break;
                 s = (s + 1) & F.dictMask;
             }
         }
         // root denominator
         fx128 wc = fxZero();
-        for (uint32_t i = 0; i < F.rootDCount; ++i) {
-            const int c = (int)(short)(F.pc[F.rootDBegin + i] >> 16);
-            if (c > 0 && ell[F.seedId[F.rootDBegin + i]] > 0.0) wc = fxAdd(wc, fxFromDouble(1.0 / (double)c));
+        for (size_t i = 0; i < F.rootId.size(); ++i) {
+            const int c = (int)F.rootChild[i];
+            if (c > 0 && ell[F.rootId[i]] != 0) wc = fxAdd(wc, fxFromDouble(1.0 / (double)c));
         }
         const double denW = fxToDouble(wc);
         *wcDenOut = denW;
-        // K1 (node_deltas): warp-per-chunk emulation -- 32 lanes x 16 deltas, interior stores, segmented scan over the lanes'
-        // trailing partials, boundary nodes through (here: plain) accumulation, repeats added afterwards
-        struct Tot { fx128 raw, cos, wc, cont; long long pres; };
-        auto tz = []() { Tot t; t.raw = t.cos = t.wc = t.cont = fxZero(); t.pres = 0; return t; };
-        auto tadd = [](const Tot& x, const Tot& y) { Tot r; r.raw = fxAdd(x.raw, y.raw); r.cos = fxAdd(x.cos, y.cos); r.wc = fxAdd(x.wc, y.wc); r.cont = fxAdd(x.cont, y.cont); r.pres = x.pres + y.pres; return r; };
-        std::vector<Tot> delta(F.N, tz());
-        std::vector<int> written(F.nLocal, 0);
-        std::vector<double> l1p(32768); for (int c = 0; c < 32768; ++c) l1p[c] = std::log1p((double)c);
-        const double ln2 = std::log1p(1.0);
-        const u64 dReal = F.nLocalDeltas;
-        auto nodeOf = [&](uint32_t lo, uint32_t hi, u64 d) { while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (F.lOff[mid + 1] > d) hi = mid; else lo = mid + 1; } return lo; };
-        auto emit = [&](uint32_t ln, const Tot& t) {
-            if (F.isBoundary[ln]) delta[F.lNode[ln]] = tadd(delta[F.lNode[ln]], t);
-            else { if (written[ln]++) throw std::runtime_error("non-boundary node emitted twice"); delta[F.lNode[ln]] = t; }
+        // ---- K1: 32 lanes x 16 words per chunk ----
+        if (F.dw.size() != F.nDeltaChunks * 512 || F.chunkSeg.size() != F.nDeltaChunks + 1) throw std::runtime_error("chunk schedule size mismatch");
+        std::vector<Seg> segRec(F.nSeg + 1, segZ());
+        std::vector<int> stored(F.nSeg + 1, 0);
+        std::vector<char> isBoundary(F.nSeg + 1, 0);
+        for (uint32_t b : F.boundarySegs) isBoundary[b] = 1;
+        auto store = [&](uint32_t sg, const Seg& v) {
+            if (sg >= F.nSeg) throw std::runtime_error("segment index out of range");
+            if (isBoundary[sg]) throw std::runtime_error("plain store to a segment that spans chunks");
+            if (stored[sg]++) throw std::runtime_error("segment stored twice");
+            segRec[sg] = v;
         };
-        if (F.seedId.size() != F.nDeltaChunks * 512 || F.chunkNode.size() != F.nDeltaChunks + 1) throw std::runtime_error("chunk schedule size mismatch");
+        auto atomic = [&](uint32_t sg, const Seg& v) {
+            if (!v.lo && !v.hi && !v.cnt) return;
+            if (sg >= F.nSeg) throw std::runtime_error("atomic segment index out of range");
+            if (!isBoundary[sg]) throw std::runtime_error("atomic add to a segment that is not zeroed per sample");
+            segRec[sg] = segAdd(segRec[sg], v);
+        };
         for (u64 c = 0; c < F.nDeltaChunks; ++c) {
-            bool has[32], single[32]; uint32_t nf[32], nl[32]; Tot acc[32], tFirst[32];
-            std::vector<std::pair<u64, int>> general;
-            const uint32_t n0 = F.chunkNode[c], n1 = F.chunkNode[c + 1];
+            const uint32_t cs = F.chunkSeg[c];
+            unsigned nEnd[32], endsBefore[32]; Seg tail[32], head[32]; unsigned endMask = 0, total = 0;
             for (int lane = 0; lane < 32; ++lane) {
-                const u64 d0 = c * 512 + (u64)lane * 16;
-                has[lane] = d0 < dReal; acc[lane] = tz(); tFirst[lane] = tz(); single[lane] = true; nf[lane] = nl[lane] = 0;
-                if (!has[lane]) continue;
-                uint32_t node = nodeOf(n0, n1, d0);
-                if (!(F.lOff[node] <= d0 && d0 < F.lOff[node + 1])) throw std::runtime_error("nodeOfDelta landed on the wrong node");
-                nf[lane] = node;
-                u64 nextOff = F.lOff[node + 1];
-                bool firstDone = false;
+                const uint32_t* w = &F.dw[c * 512 + (u64)lane * 16];
+                nEnd[lane] = 0; for (int j = 0; j < 16; ++j) nEnd[lane] += w[j] >> 31;
+                endsBefore[lane] = total; total += nEnd[lane];
+                if (nEnd[lane]) endMask |= 1u << lane;
+                const uint32_t segFirst = (cs & 0x7FFFFFFFu) + endsBefore[lane];
+                long long acc = 0; int cn = 0; unsigned k = 0; head[lane] = segZ();
                 for (int j = 0; j < 16; ++j) {
-                    const u64 idx = d0 + j;
-                    if (idx >= dReal) continue;
-                    if (idx >= nextOff) {
-                        if (!firstDone) { tFirst[lane] = acc[lane]; firstDone = true; }
-                        else { if (F.isBoundary[node]) throw std::runtime_error("interior node flagged boundary"); if (written[node]++) throw std::runtime_error("interior node written twice"); delta[F.lNode[node]] = acc[lane]; }
-                        acc[lane] = tz();
-                        do { ++node; nextOff = F.lOff[node + 1]; } while (idx >= nextOff);
-                    }
-                    const uint32_t pcv = F.pc[idx]; const int p = (int)(short)(pcv & 0xFFFF), cc = (int)(short)(pcv >> 16);
-                    const double lr = ell[F.seedId[idx]];
-                    if (p != cc && lr > 0.0) {
-                        if ((unsigned)p <= 1u && (unsigned)cc <= 1u) {
-                            const fx128 fl = fxFromDouble(lr), fc = fxFromDouble(lr * ln2);
-                            Tot& a = acc[lane];
-                            if (cc > p) { a.raw = fxAdd(a.raw, fl); a.cont = fxAdd(a.cont, fl); a.cos = fxAdd(a.cos, fc); a.wc.hi += 1; a.pres += 1; }
-                            else { a.raw = fxSub(a.raw, fl); a.cont = fxSub(a.cont, fl); a.cos = fxSub(a.cos, fc); a.wc.hi -= 1; a.pres -= 1; }
-                        } else general.push_back({idx, lane});
+                    const bool lost = (w[j] >> 30) & 1u;
+                    const long long e = ell[w[j] & 0x3FFFFFFFu];
+                    acc += lost ? -e : e; cn += e ? (lost ? -1 : 1) : 0;
+                    if (w[j] >> 31) {
+                        if (k == 0) head[lane] = segOf(acc, cn); else store(segFirst + k, segOf(acc, cn));
+                        ++k; acc = 0; cn = 0;
                     }
                 }
-                nl[lane] = node; single[lane] = !firstDone;
+                tail[lane] = segOf(acc, cn);
             }
-            Tot incl[32]; int head[32]; bool contPrev[32];
-            for (int lane = 0; lane < 32; ++lane) {
-                contPrev[lane] = has[lane] && lane > 0 && has[lane - 1] && nl[lane - 1] == nf[lane];
-                head[lane] = (single[lane] && contPrev[lane]) ? 0 : 1;
-                incl[lane] = acc[lane];
-            }
-            for (int d = 1; d < 32; d <<= 1) {   // Hillis-Steele segmented scan, all lanes read the previous step's values
-                Tot up[32]; int hup[32];
-                for (int lane = 0; lane < 32; ++lane) { up[lane] = incl[lane >= d ? lane - d : lane]; hup[lane] = head[lane >= d ? lane - d : lane]; }
-                for (int lane = 0; lane < 32; ++lane) if (lane >= d && !head[lane]) { incl[lane] = tadd(incl[lane], up[lane]); head[lane] = hup[lane]; }
+            Seg incl[32];
+            for (int lane = 0; lane < 32; ++lane) incl[lane] = tail[lane];
+            for (int dd = 1; dd < 32; dd <<= 1) {   // Hillis-Steele, all lanes read the previous step's values
+                Seg prev[32]; for (int lane = 0; lane < 32; ++lane) prev[lane] = incl[lane];
+                for (int lane = dd; lane < 32; ++lane) {
+                    const unsigned span = ((1u << dd) - 1u) << (lane - dd + 1);
+                    if (!(endMask & span)) incl[lane] = segAdd(incl[lane], prev[lane - dd]);
+                }
             }
             for (int lane = 0; lane < 32; ++lane) {
-                if (!has[lane]) continue;
-                if (!single[lane]) emit(nf[lane], contPrev[lane] ? tadd(incl[lane - 1], tFirst[lane]) : tFirst[lane]);
-                const bool hasNext = lane < 31 && has[lane + 1];
-                if (!(hasNext && nf[lane + 1] == nl[lane])) emit(nl[lane], incl[lane]);
+                if (!nEnd[lane]) continue;
+                Seg f = head[lane];
+                if (lane) f = segAdd(f, incl[lane - 1]);
+                const uint32_t sg = (cs & 0x7FFFFFFFu) + endsBefore[lane];
+                if ((cs >> 31) && !(endMask & ((1u << lane) - 1u))) atomic(sg, f); else store(sg, f);
             }
-            for (auto& g : general) {
-                const u64 idx = g.first;
-                const uint32_t pcv = F.pc[idx]; const int p = (int)(short)(pcv & 0xFFFF), cc = (int)(short)(pcv >> 16);
-                const DeltaTerms t = deltaTerms(ell[F.seedId[idx]], p, cc, p > 0 ? l1p[p] : 0.0, cc > 0 ? l1p[cc] : 0.0);
-                Tot gt; gt.raw = fxFromDouble(t.raw); gt.cos = fxFromDouble(t.cos); gt.wc = fxFromDouble(t.wc); gt.cont = fxFromDouble(t.cont); gt.pres = t.pres;
-                const uint32_t ln = nodeOf(n0, n1, idx);
-                delta[F.lNode[ln]] = tadd(delta[F.lNode[ln]], gt);
+            if (!(F.dw[c * 512 + 511] >> 31)) {
+                const uint32_t sNext = (cs & 0x7FFFFFFFu) + total;
+                if (sNext < F.nSeg) atomic(sNext, incl[31]);
+                else if (incl[31].lo || incl[31].hi || incl[31].cnt) throw std::runtime_error("open run after the last segment");
             }
         }
-        for (uint32_t i = 0; i < F.nLocal; ++i)
-            if (F.lOff[i + 1] > F.lOff[i] && !F.isBoundary[i] && written[i] != 1) throw std::runtime_error("a node with deltas was not written exactly once");
-        // K2 tile algorithm
-        auto fromND = [](const Tot& n) { Acc a; a.f[0] = n.raw; a.f[1] = n.cos; a.f[2] = n.wc; a.f[3] = n.cont; a.pres = n.pres; return a; };
+        for (uint32_t sg = 0; sg < F.nSeg; ++sg)
+            if (!isBoundary[sg] && stored[sg] != 1) throw std::runtime_error("a segment was not stored exactly once");
+        // ---- general deltas + event prefix ----
+        std::vector<double> l1p(32768); for (int c = 0; c < 32768; ++c) l1p[c] = std::log1p((double)c);
+        const double ln2 = std::log1p(1.0);
+        std::vector<Acc5> genRec(F.nGenNodes, accZ()), evPrefix(F.evSlot.size(), accZ());
+        for (size_t i = 0; i < F.genSlot.size(); ++i) {
+            const long long e = ell[F.genId[i]];
+            if (!e) continue;
+            const int p = (int)(short)(F.genPc[i] & 0xFFFF), cc = (int)(short)(F.genPc[i] >> 16);
+            const DeltaTerms t = deltaTerms((double)e / 9007199254740992.0, p, cc, p > 0 ? l1p[p] : 0.0, cc > 0 ? l1p[cc] : 0.0);
+            Acc5 g; g.f[0] = fxFromDouble(t.raw); g.f[1] = fxFromDouble(t.cos); g.f[2] = fxFromDouble(t.wc); g.f[3] = fxFromDouble(t.cont); g.pres = t.pres;
+            genRec[F.genSlot[i]] = accAdd(genRec[F.genSlot[i]], g);
+        }
+        {
+            Acc5 run = accZ();
+            for (size_t e = 0; e < F.evSlot.size(); ++e) {
+                const Acc5 v = genRec[F.evSlot[e] & 0x7FFFFFFFu];
+                run = accAdd(run, (F.evSlot[e] >> 31) ? accNeg(v) : v);
+                evPrefix[e] = run;
+            }
+        }
+        // ---- K2 tile algorithm ----
+        auto recOf = [&](uint32_t v) { return F.nodeSeg[v] == 0xFFFFFFFFu ? segZ() : segRec[F.nodeSeg[v]]; };
         SampleScalars S; std::memset(&S, 0, sizeof(S));
         S.readMagnitude = mag; S.logContDenom = denL; S.wcDenom = denW; S.uniqueKept = U1;
         for (uint32_t tile = 0; tile < F.nK2Tiles; ++tile) {
             const uint32_t a0 = F.nodeBegin + tile * 512, a1 = std::min(a0 + 512u, F.nodeEnd);
             const uint32_t cb = F.chainOff[tile], ce = F.chainOff[tile + 1];
-            std::vector<Acc> chainA(ce - cb);
-            Acc run = accZ();
-            for (uint32_t j = cb; j < ce; ++j) { run = accAdd(run, fromND(delta[F.chainNodes[j]])); chainA[j - cb] = run; }
-            std::vector<Acc> dp(a1 - a0);
+            std::vector<Seg> chainA(ce - cb);
+            Seg run = segZ();
+            for (uint32_t j = cb; j < ce; ++j) { run = segAdd(run, recOf(F.chainNodes[j])); chainA[j - cb] = run; }
+            std::vector<Seg> dp(a1 - a0);
             for (uint32_t w = a0; w < a1; ++w) {
-                Acc v = fromND(delta[w]);
+                Seg v = recOf(w);
                 const uint32_t cs = F.carrySlot[w];
-                if (cs != 0xFFFFFFFFu) { if (cs >= ce - cb) throw std::runtime_error("carry slot outside chain"); v = accAdd(v, chainA[cs]); }
+                if (cs != 0xFFFFFFFFu) { if (cs >= ce - cb) throw std::runtime_error("carry slot outside chain"); v = segAdd(v, chainA[cs]); }
                 dp[w - a0] = v;
             }
-            Acc pre = accZ();
+            Seg pre = segZ();
             for (uint32_t w = a0; w < a1; ++w) {
-                Acc dd = dp[w - a0];
-                for (uint32_t c = F.closeOff[w]; c < F.closeOff[w + 1]; ++c) { const uint32_t u = F.closeList[c]; if (u >= a0) dd = accSub(dd, dp[u - a0]); }
-                pre = accAdd(pre, dd);
+                Seg dd = dp[w - a0];
+                for (uint32_t c = F.closeOff[w]; c < F.closeOff[w + 1]; ++c) { const uint32_t u = F.closeList[c]; if (u >= a0) dd = segSub(dd, dp[u - a0]); }
+                pre = segAdd(pre, dd);
                 double* m = metrics + (size_t)w * 5;
-                m[0] = fxToDouble(pre.f[0]); m[1] = fxToDouble(pre.f[1]); m[2] = (double)pre.pres; m[3] = fxToDouble(pre.f[2]); m[4] = fxToDouble(pre.f[3]);
-                nodeScores(m[0], m[1], (double)(u64)pre.pres, m[3], m[4], F.gMag[w], S, scores + (size_t)w * 5);
+                const uint32_t ne = F.nGenNodes ? F.evIdx[w] : 0u;
+                nodeNumerators(pre.lo, pre.hi, pre.cnt, ne ? &evPrefix[ne - 1] : nullptr, ln2, m);
+                nodeScores(m[0], m[1], m[2], m[3], m[4], F.gMag[w], S, scores + (size_t)w * 5);
             }
         }
         return 0;
