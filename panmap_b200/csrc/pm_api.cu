@@ -80,8 +80,8 @@ struct pm_host_index { HostIndex h; };
 struct pm_index {
     int device = 0; int nSM = 148;
     FlatIndex F;  // host copy of the small arrays (tree) is kept for result assembly; big vectors are released
-    DevBuf<u32> dw, chunkSeg, nodeSeg, boundarySegs, genSlot, genId, genPc, evSlot, evIdx, rootId, rootChild;
-    DevBuf<u32> parent, closeOff, closeList, carrySlot, chainOff, chainNodes, bfsNodes, bfsRanks;
+    DevBuf<u32> dw, endMask, chunkSeg, nodeSeg, boundarySegs, genSlot, genId, genPc, evSlot, evIdx, rootId, rootChild;
+    DevBuf<u32> parent, subEnd, carrySlot, chainOff, chainNodes, bfsNodes, bfsRanks;
     DevBuf<u64> dictHash, homo;
     DevBuf<DictSlot> dict;
     DevBuf<double> gMag, log1pLut, log1pSmall;
@@ -104,7 +104,7 @@ struct pm_workspace {
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0;
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
-    DevBuf<long long> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist;
+    DevBuf<long long> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist; DevBuf<u64> entKey; DevBuf<u32> entCnt;
     DevBuf<SegRec> segRec, chainA;
     DevBuf<u64> genRec, evPrefix;
     DevBuf<double> scores, metrics, blockMaxAndBfs;
@@ -130,11 +130,11 @@ void buildViews(pm_index* I) {
     DevIndexView& V = I->view;
     V.nNodes = F.N; V.nodeBegin = F.nodeBegin; V.nodeEnd = F.nodeEnd; V.nLocal = F.nLocal; V.nAnc = F.nAnc;
     V.nLocalDeltas = F.nLocalDeltas; V.nSeeds = F.S;
-    V.dw = I->dw.p; V.nDeltaChunks = F.nDeltaChunks; V.chunkSeg = I->chunkSeg.p; V.nodeSeg = I->nodeSeg.p;
+    V.dw = I->dw.p; V.endMask = I->endMask.p; V.nDeltaChunks = F.nDeltaChunks; V.chunkSeg = I->chunkSeg.p; V.nodeSeg = I->nodeSeg.p;
     V.boundarySegs = I->boundarySegs.p; V.nBoundary = (u32)F.boundarySegs.size(); V.nSeg = F.nSeg;
     V.genSlot = I->genSlot.p; V.genId = I->genId.p; V.genPc = I->genPc.p; V.nGenDeltas = (u32)F.genSlot.size(); V.nGenNodes = F.nGenNodes;
     V.evSlot = I->evSlot.p; V.nEvents = (u32)F.evSlot.size(); V.evIdx = F.nGenNodes ? I->evIdx.p : nullptr;
-    V.parent = I->parent.p; V.gMag = I->gMag.p; V.closeOff = I->closeOff.p; V.closeList = I->closeList.p;
+    V.parent = I->parent.p; V.gMag = I->gMag.p; V.subEnd = I->subEnd.p;
     V.carrySlot = I->carrySlot.p; V.chainOff = I->chainOff.p; V.chainNodes = I->chainNodes.p;
     V.nK2Tiles = F.nK2Tiles; V.chainTotal = (u32)F.chainNodes.size();
     V.isLeaf = I->isLeaf.p;
@@ -159,10 +159,10 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
         I->nSM = prop.multiProcessorCount;
         FlatIndex& F = I->F;
-        I->dw.upload(F.dw); I->chunkSeg.upload(F.chunkSeg); I->nodeSeg.upload(F.nodeSeg); I->boundarySegs.upload(F.boundarySegs);
+        I->dw.upload(F.dw); I->endMask.upload(F.endMask); I->chunkSeg.upload(F.chunkSeg); I->nodeSeg.upload(F.nodeSeg); I->boundarySegs.upload(F.boundarySegs);
         I->genSlot.upload(F.genSlot); I->genId.upload(F.genId); I->genPc.upload(F.genPc); I->evSlot.upload(F.evSlot); I->evIdx.upload(F.evIdx);
         I->rootId.upload(F.rootId); I->rootChild.upload(F.rootChild);
-        I->parent.upload(F.parent); I->gMag.upload(F.gMag); I->closeOff.upload(F.closeOff); I->closeList.upload(F.closeList);
+        I->parent.upload(F.parent); I->gMag.upload(F.gMag); I->subEnd.upload(F.subEnd);
         I->carrySlot.upload(F.carrySlot); I->chainOff.upload(F.chainOff); I->chainNodes.upload(F.chainNodes);
         I->isLeaf.upload(F.isLeaf); I->bfsNodes.upload(F.bfsNodes); I->bfsRanks.upload(F.bfsRanks);
         {
@@ -185,7 +185,7 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
         I->gMagSqHost = F.gMagSq; I->gUniqueHost = F.gUnique;
         buildViews(I.get());
         // release the big host vectors (the device now owns them)
-        std::vector<u32>().swap(F.dw); std::vector<u32>().swap(F.nodeSeg); std::vector<u32>().swap(F.evIdx); std::vector<u64>().swap(F.dictKeys);
+        std::vector<u32>().swap(F.dw); std::vector<u32>().swap(F.endMask); std::vector<u32>().swap(F.nodeSeg); std::vector<u32>().swap(F.evIdx); std::vector<u64>().swap(F.dictKeys);
         std::vector<u32>().swap(F.dictVals); std::vector<u64>().swap(F.dictHash);
         std::vector<double>().swap(F.gMagSq); std::vector<int64_t>().swap(F.gUnique);
         *out = I.release();
@@ -197,7 +197,7 @@ void refreshView(pm_workspace* W) {
     WorkspaceView& V = W->view;
     V.table = W->table.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
     V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
-    V.acc = W->acc.p; V.ell = W->ell.p; V.touched = W->touched.p; V.touchedCap = (u32)W->touched.n; V.countHist = W->countHist.p;
+    V.acc = W->acc.p; V.ell = W->ell.p; V.touched = W->touched.p; V.touchedCap = (u32)W->touched.n; V.countHist = W->countHist.p; V.entKey = W->entKey.p; V.entCnt = W->entCnt.p;
     V.segRec = W->segRec.p; V.chainA = W->chainA.p; V.genRec = W->genRec.p; V.evPrefix = W->evPrefix.p;
     V.scores = W->scores.p; V.metrics = W->wantMetrics ? W->metrics.p : nullptr; V.blockMax = W->blockMaxAndBfs.p;
     V.recRank = W->recRank.p; V.recNode = W->recNode.p; V.recScore = W->recScore.p; V.recCap = W->recCap;
@@ -208,7 +208,7 @@ void ensureTable(pm_workspace* W, u64 wantCap) {
     u64 cap = 1 << 12;
     while (cap < wantCap) cap <<= 1;
     if (cap <= W->tableCap) return;
-    W->table.alloc(cap); W->tableCap = cap;
+    W->table.alloc(cap); W->tableCap = cap; W->entKey.alloc(cap); W->entCnt.alloc(cap);
     refreshView(W);
 }
 
@@ -320,7 +320,7 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
 void stageScore(pm_workspace* W, const pm_place_params& prm) {
     pm_index* I = W->idx;
     const PlaceOpts O = makeOpts(prm, W->wantMetrics);
-    launchFinalize(I->view, W->view, O, I->homo.p, W->st);
+    launchFinalize(I->view, W->view, O, I->homo.p, W->lastEntries ? W->lastEntries : W->tableCap / 4, W->st);
     CK(cudaEventRecord(W->ev[3], W->st));
     launchDeltas(I->view, W->view, I->nSM, W->st);
     launchGeneral(I->view, W->view, W->st);
@@ -509,7 +509,7 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
         W->acc.alloc(1); W->scalars.alloc(1); W->sel.alloc(5);
-        W->ell.alloc(F.S + 1); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(long long), W->st));   // [S] is the always-zero slot of the padding words
+        W->ell.alloc(2 * (F.S + 1)); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(long long), W->st));   // [S] is the always-zero slot of the padding words
         W->touched.alloc(F.S ? F.S : 1);
         W->countHist.alloc(kLog1pLut);
         W->segRec.alloc(F.nSeg + 1); CK(cudaMemsetAsync(W->segRec.p, 0, W->segRec.n * sizeof(SegRec), W->st));
@@ -585,11 +585,12 @@ int pm_get_node_metrics(pm_workspace* ws, double* out) {
         CK(cudaMemsetAsync(ws->metrics.p, 0, I->F.N * 5 * sizeof(double), ws->st));
         ws->wantMetrics = true; refreshView(ws);
         // ell was reset after the sample: rebuild it from the (still intact) table, then K1 + K2 only
-        CK(cudaMemsetAsync(&ws->acc.p->touchedCount, 0, sizeof(unsigned), ws->st));
+        CK(cudaMemsetAsync(&ws->acc.p->touchedCount, 0, 2 * sizeof(unsigned), ws->st));   // touchedCount + entCount
         CK(cudaMemsetAsync(ws->acc.p->magSq, 0, 6 * sizeof(u64) + 7 * sizeof(long long), ws->st));
         const PlaceOpts O = makeOpts(ws->lastParams, true);
-        launchFinalize(I->view, ws->view, O, I->homo.p, ws->st);
+        launchFinalize(I->view, ws->view, O, I->homo.p, ws->lastEntries ? ws->lastEntries : ws->tableCap / 4, ws->st);
         launchDeltas(I->view, ws->view, I->nSM, ws->st);
+        launchGeneral(I->view, ws->view, ws->st);
         launchPrefixScores(I->view, ws->view, O, ws->st);
         launchResetSample(ws->idx->view, ws->view, ws->st);
         CK(cudaMemcpyAsync(out, ws->metrics.p, I->F.N * 5 * sizeof(double), cudaMemcpyDeviceToHost, ws->st));

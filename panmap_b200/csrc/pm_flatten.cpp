@@ -7,7 +7,7 @@
 //   * NodeMetrics::genomeMagnitudeSquared / genomeUniqueSeedCount per node, accumulated in exactly the reference's
 //     order (parent's value, then the node's deltas in stored order; placement.cpp:289-302,772-774) -> bit-identical
 //   * DFS subtree ends, depth, reference BFS ranks, leaf flags
-//   * "closers" CSR for the in-tile Euler-tour difference, ancestor chains + carry slots of the K2 tiles
+//   * ancestor chains + carry slots of the K2 tiles (the in-tile Euler-tour difference uses the subtree ends)
 //   * delta streams: one packed 32-bit word per 0<->1 delta in 512-word chunks with in-band segment ends, a side list for
 //     the rare deltas with a genome count >= 2 and the DFS-interval events of their tree prefix
 #include "pm_host.h"
@@ -21,7 +21,7 @@
 
 namespace pm {
 
-static constexpr uint32_t kTileNodesK2H = 512;
+static constexpr uint32_t kTileNodesK2H = kTileNodesK2;
 static constexpr uint32_t NONE = 0xFFFFFFFFu;
 
 // for every block of 256 packed chunks counted from chunk gBase (= packedOff[0] of the slice): the slice-local read r with
@@ -91,17 +91,6 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
         for (uint32_t u : path) F.subEnd[u] = static_cast<uint32_t>(N);
     }
     bfsRanks(F.parent.data(), N, F.bfsRank);
-
-    // closers: u closes right before w  <=>  subEnd[u] == w
-    F.closeOff.assign(N + 2, 0);
-    for (uint64_t u = 0; u < N; ++u) F.closeOff[F.subEnd[u] + 1]++;
-    for (uint64_t w = 0; w <= N; ++w) F.closeOff[w + 1] += F.closeOff[w];
-    F.closeList.assign(N, 0);
-    {
-        std::vector<uint32_t> fill(F.closeOff.begin(), F.closeOff.end() - 1);
-        for (uint64_t u = 0; u < N; ++u) F.closeList[fill[F.subEnd[u]]++] = static_cast<uint32_t>(u);
-    }
-    F.closeOff.resize(N + 1);  // entries for w == N (nodes closing at the very end) are never used
 
     // ---- genome-only accumulators in the reference's order ----
     F.gMagSq.assign(N, 0.0); F.gMag.assign(N, 0.0); F.gUnique.assign(N, 0);
@@ -180,7 +169,7 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
     F.lNode.resize(F.nLocal);
     for (uint32_t i = 0; i < F.nAnc; ++i) F.lNode[i] = anc[i];
     for (uint32_t v = F.nodeBegin; v < F.nodeEnd; ++v) F.lNode[F.nAnc + (v - F.nodeBegin)] = v;
-    if (F.S >= (1ull << 30)) throw std::runtime_error("index has too many distinct seeds (2^30 limit of the packed delta word)");
+    if (F.S >= (1ull << 31) - 1) throw std::runtime_error("index has too many distinct seeds (2^31 limit of the packed delta word)");
     {
         uint64_t nLocalDeltas = 0;
         for (uint32_t i = 0; i < F.nLocal; ++i) nLocalDeltas += d.node_offsets[F.lNode[i] + 1] - d.node_offsets[F.lNode[i]];
@@ -191,6 +180,7 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
     F.dw.clear(); F.dw.reserve(static_cast<size_t>(F.nLocalDeltas + 512));
     F.nSeg = 0; F.nGenNodes = 0;
     std::vector<uint32_t> genNodes;   // global ids of the nodes that own general deltas, ascending
+    std::vector<uint64_t> segEnd;     // position (in dw) of the last word of every segment
     {
         std::vector<uint32_t> ids;
         for (uint32_t i = 0; i < F.nLocal; ++i) {
@@ -200,8 +190,8 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
             bool hasGen = false;
             for (uint64_t j = b; j < e; ++j) {
                 const int p = d.delta_parent[j], c = d.delta_child[j];
-                if (p == 0 && c == 1) ids.push_back(idAll[j]);
-                else if (p == 1 && c == 0) ids.push_back(idAll[j] | 0x40000000u);
+                if (p == 0 && c == 1) ids.push_back(2 * idAll[j]);
+                else if (p == 1 && c == 0) ids.push_back(2 * idAll[j] + 1);
                 else if (p != c) {
                     if (!hasGen) { hasGen = true; genNodes.push_back(v); }
                     F.genSlot.push_back(static_cast<uint32_t>(genNodes.size() - 1)); F.genId.push_back(idAll[j]);
@@ -210,9 +200,9 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
                 }
             }
             if (ids.empty()) continue;
-            std::sort(ids.begin(), ids.end(), [](uint32_t x, uint32_t y) { return (x & 0x3FFFFFFFu) < (y & 0x3FFFFFFFu); });
-            ids.back() |= 0x80000000u;
+            std::sort(ids.begin(), ids.end());
             F.dw.insert(F.dw.end(), ids.begin(), ids.end());
+            segEnd.push_back(F.dw.size() - 1);
             F.nodeSeg[v] = F.nSeg++;
         }
     }
@@ -221,14 +211,16 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
     {
         const uint64_t CH = 512;
         F.nDeltaChunks = (F.nFast + CH - 1) / CH;
-        F.dw.resize(F.nDeltaChunks * CH, static_cast<uint32_t>(F.S));   // padding gathers ell[S] == 0, no sign, no segment end
+        F.dw.resize(F.nDeltaChunks * CH, static_cast<uint32_t>(2 * F.S));   // padding gathers the always-zero slot, never ends a segment
+        F.endMask.assign(F.nDeltaChunks * 32, 0);
+        for (uint64_t e : segEnd) F.endMask[e >> 4] |= 1u << (e & 15);
         F.chunkSeg.assign(F.nDeltaChunks + 1, 0);
         uint32_t seg = 0;
         for (uint64_t c = 0; c < F.nDeltaChunks; ++c) {
-            const bool inside = c > 0 && !(F.dw[c * CH - 1] >> 31) && c * CH < F.nFast;   // previous word did not end its segment
+            const bool inside = c > 0 && !(F.endMask[c * 32 - 1] >> 15);   // the previous word did not end its segment
             F.chunkSeg[c] = seg | (inside ? 0x80000000u : 0u);
             if (inside) F.boundarySegs.push_back(seg);
-            for (uint64_t j = c * CH; j < (c + 1) * CH; ++j) seg += F.dw[j] >> 31;
+            for (uint64_t j = c * 32; j < (c + 1) * 32; ++j) seg += static_cast<uint32_t>(__builtin_popcount(F.endMask[j]));
         }
         F.chunkSeg[F.nDeltaChunks] = seg;
         if (seg != F.nSeg) throw std::runtime_error("internal: segment count mismatch");

@@ -35,7 +35,6 @@ struct FlatIndex {
     std::vector<uint8_t> isLeaf;
     std::vector<double> gMagSq, gMag;
     std::vector<int64_t> gUnique;
-    std::vector<uint32_t> closeOff, closeList;
     // dictionary (id -> hash) and open-addressing table (hash -> id)
     std::vector<uint64_t> dictHash, dictKeys;
     std::vector<uint32_t> dictVals;
@@ -43,9 +42,10 @@ struct FlatIndex {
     // shard-local delta storage (local nodes = ancestors of nodeBegin, root first, then the shard's nodes)
     std::vector<uint32_t> lNode;               // [nLocal] global node id
     // "fast" deltas = genome count 0 <-> 1 (all but a handful): one 32-bit word each, in node order.
-    //   bits 0..29 seed id | bit 30 seed lost (parent 1 -> child 0) | bit 31 last fast delta of its node ("segment" end)
-    // padded to whole 512-word chunks with words that gather the always-zero slot ell[S]
+    //   word = 2 * seed id + (seed lost: parent 1 -> child 0); the last fast delta of a node ends a "segment"
+    // padded to whole 512-word chunks with words that gather the always-zero slot of seed id S
     std::vector<uint32_t> dw;
+    std::vector<uint32_t> endMask;             // [nDeltaChunks*32] bit j: word 16*lane + j of the chunk ends a segment
     uint64_t nFast = 0, nDeltaChunks = 0;
     uint32_t nSeg = 0;                         // nodes with at least one fast delta, in local order
     std::vector<uint32_t> chunkSeg;            // [nDeltaChunks+1] segments ending before the chunk | bit 31: chunk starts inside a segment

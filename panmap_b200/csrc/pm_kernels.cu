@@ -504,33 +504,50 @@ void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* c
     table_export<<<streamGrid(W.tableCap, 2), 256, 0, st>>>(W.table, W.tableCap, W.acc, hash, count, counter, cap);
 }
 
-// pass 1: erase the four homopolymer k-mer hashes (placement.cpp:1708-1718) and gather the statistics of the
-// auto min-read-support rule (placement.cpp:931-955).  Four independent 16-byte loads in flight per thread.
-__global__ void __launch_bounds__(256) table_stats(TableSlot* table, u64 cap, SampleAcc* acc, const u64* __restrict__ homo) {
+// pass 1 (the only pass over the whole table): erase the four homopolymer k-mer hashes (placement.cpp:1708-1718), gather the
+// statistics of the auto min-read-support rule (placement.cpp:931-955) and the pre-filter totals, and compact the occupied
+// slots into a dense (key, count) list -- one warp-aggregated atomic per 128 slots -- so that everything that follows works
+// on U entries instead of the table's capacity.  Four independent 16-byte loads in flight per thread.
+__global__ void __launch_bounds__(256) table_scan(WorkspaceView W, const u64* __restrict__ homo) {
     const u64 h0 = homo[0], h1 = homo[1], h2 = homo[2], h3 = homo[3];
-    long long ms = 0, mc = 0, en = 0;
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < cap; i0 += 4 * stride) {
+    TableSlot* table = W.table; const u64 cap = W.tableCap; SampleAcc* acc = W.acc;
+    long long ms = 0, mc = 0, en = 0, total = 0;
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * 8;
+    for (u64 base = ((u64)blockIdx.x * 8 + (threadIdx.x >> 5)) * 128; base < cap; base += warpsTotal * 128) {
         uint4 v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const u64 i = i0 + q * stride; v[q] = i < cap ? ldSlot(table, i) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); }
+        for (int q = 0; q < 4; ++q) { const u64 i = base + q * 32 + lane; v[q] = i < cap ? ldSlot(table, i) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); }
+        bool occ[4]; unsigned m[4], n = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const u64 k = slotKey(v[q]);
-            if (k == kEmptyKey) continue;
-            if (k == h0 || k == h1 || k == h2 || k == h3) { table[i0 + q * stride].count = 0; continue; }
-            const long long c = v[q].z;
-            if (c > 0) { ++en; if (c >= 2) { ms += c; ++mc; } }
+            occ[q] = k != kEmptyKey && v[q].z > 0;
+            if (occ[q] && (k == h0 || k == h1 || k == h2 || k == h3)) { table[base + q * 32 + lane].count = 0; occ[q] = false; }
+            if (occ[q]) { const long long c = v[q].z; ++en; total += c; if (c >= 2) { ms += c; ++mc; } }
+            m[q] = __ballot_sync(0xffffffffu, occ[q]);
+            n += __popc(m[q]);
+        }
+        if (n) {
+            unsigned o = 0;
+            if (lane == 0) o = atomicAdd(&acc->entCount, n);
+            o = __shfl_sync(0xffffffffu, o, 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (occ[q]) { const unsigned d = o + __popc(m[q] & ((1u << lane) - 1u)); W.entKey[d] = slotKey(v[q]); W.entCnt[d] = v[q].z; }
+                o += __popc(m[q]);
+            }
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {
-        const long long c = acc->emptyKeyCount; ++en; if (c >= 2) { ms += c; ++mc; }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {   // the one key that cannot live in the table
+        const long long c = acc->emptyKeyCount; ++en; total += c; if (c >= 2) { ms += c; ++mc; }
     }
-    ms = warpSumLL(ms); mc = warpSumLL(mc); en = warpSumLL(en);
-    if ((threadIdx.x & 31) == 0) {
+    ms = warpSumLL(ms); mc = warpSumLL(mc); en = warpSumLL(en); total = warpSumLL(total);
+    if (lane == 0) {
         if (ms) atomicAdd((unsigned long long*)&acc->multiSum, (unsigned long long)ms);
         if (mc) atomicAdd((unsigned long long*)&acc->multiCount, (unsigned long long)mc);
-        if (en) atomicAdd((unsigned long long*)&acc->entries, (unsigned long long)en);
+        if (en) { atomicAdd((unsigned long long*)&acc->entries, (unsigned long long)en); atomicAdd((unsigned long long*)&acc->unique, (unsigned long long)en); }
+        if (total) atomicAdd((unsigned long long*)&acc->total, (unsigned long long)total);
     }
 }
 
@@ -540,10 +557,9 @@ __device__ __forceinline__ long long resolveMinSupport(const SampleAcc* acc, int
     return est > 3.0 ? 2 : 1;
 }
 
-// pass 2: computeReadSeedMagnitudes (placement.cpp:957-984) + scatter of log1p(count) to the seed-id array.
-// The table is streamed with four independent 16-byte loads per thread; the seeds that survive the min-support filter
-// (a small minority at high coverage) are compacted per warp through a shared-memory queue and then handled 32 at a time
-// with every lane busy: log1p table, exact sums, count histogram, dictionary probe, scatter.
+// pass 2: computeReadSeedMagnitudes (placement.cpp:957-984) + scatter of log1p(count) to the seed-id array, one thread per
+// compacted entry: log1p table, exact sums, count histogram, dictionary probe, scatter -- all independent, so the random
+// accesses of many entries are in flight at once.
 constexpr int kHistSmem = 2048;
 struct FinalizeAcc { fx128 mag, lsum; long long kept; u32 maxc; };
 __device__ __forceinline__ u32 finalizeKept(const DevIndexView& I, const WorkspaceView& W, u64 k, u32 c, FinalizeAcc& A, unsigned* sHist) {
@@ -557,12 +573,16 @@ __device__ __forceinline__ u32 finalizeKept(const DevIndexView& I, const Workspa
     while (true) {  // is this seed anywhere in the index?
         const uint4 d = __ldg(reinterpret_cast<const uint4*>(I.dict) + s);
         const u64 dk = (u64)d.x | ((u64)d.y << 32);
-        if (dk == k) { W.ell[d.z] = __double2ll_rn(l * kEllScale); return d.z; }   // l >= ln 2: an exact multiple of 2^-53
+        if (dk == k) {   // l >= ln 2 is an exact multiple of 2^-53; the entry holds +l for a gained seed and -l for a lost one
+            const long long e = __double2ll_rn(l * kEllScale);
+            *reinterpret_cast<longlong2*>(W.ell + 2 * (size_t)d.z) = make_longlong2(e, -e);
+            return d.z;
+        }
         if (dk == kEmptyKey) return kNone;
         s = (s + 1) & I.dictMask;
     }
 }
-// one atomic per warp for the list of touched seed ids (reset_ell clears exactly these after the sample)
+// one atomic per warp for the list of touched seed ids (reset_sample clears exactly these after the sample)
 __device__ __forceinline__ void appendTouched(const WorkspaceView& W, u32 id, unsigned activeMask) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned m = __ballot_sync(activeMask, id != kNone);
@@ -576,68 +596,49 @@ __device__ __forceinline__ void appendTouched(const WorkspaceView& W, u32 id, un
         if (t < W.touchedCap) W.touched[t] = id; else W.acc->overflow = 1;
     }
 }
-__global__ void __launch_bounds__(256) table_finalize(DevIndexView I, WorkspaceView W, int configuredMinSupport) {
+__global__ void __launch_bounds__(256) entries_finalize(DevIndexView I, WorkspaceView W, int configuredMinSupport) {
     __shared__ unsigned sHist[kHistSmem];
-    __shared__ u64 sQKey[8][64];
-    __shared__ u32 sQCnt[8][64];
+    __shared__ u64 sRed[8][4];
+    __shared__ long long sKept[8];
+    __shared__ unsigned sMax[8];
     for (int i = threadIdx.x; i < kHistSmem; i += blockDim.x) sHist[i] = 0;
     __syncthreads();
     SampleAcc* acc = W.acc;
     const u32 minSup = (u32)resolveMinSupport(acc, configuredMinSupport);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     FinalizeAcc A; A.mag = fxZero(); A.lsum = fxZero(); A.kept = 0; A.maxc = 0;
-    long long total = 0, uniq = 0;
-    unsigned qn = 0;  // warp-uniform queue fill
-    const u64 cap = W.tableCap;
-    const u64 warpsTotal = (u64)gridDim.x * 8;
-    const u64 gw = (u64)blockIdx.x * 8 + warp;
-    for (u64 base = gw * 128; base < cap; base += warpsTotal * 128) {
-        uint4 v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const u64 i = base + q * 32 + lane; v[q] = i < cap ? ldSlot(W.table, i) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const u64 k = slotKey(v[q]); const u32 c = v[q].z;
-            const bool occ = k != kEmptyKey && c > 0;
-            if (occ) { total += c; ++uniq; }
-            const bool kept = occ && c >= minSup;
-            const unsigned m = __ballot_sync(0xffffffffu, kept);
-            if (m) {
-                if (kept) { const unsigned o = qn + __popc(m & ((1u << lane) - 1u)); sQKey[warp][o] = k; sQCnt[warp][o] = c; }
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32) {
-                    qn -= 32;
-                    const u32 id = finalizeKept(I, W, sQKey[warp][qn + lane], sQCnt[warp][qn + lane], A, sHist);
-                    appendTouched(W, id, 0xffffffffu);
-                    __syncwarp();
-                }
-            }
-        }
-    }
-    {
+    const unsigned n = acc->entCount;
+    const unsigned nRound = (n + 31u) & ~31u;   // whole warps stay in the loop for the ballot
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += gridDim.x * blockDim.x) {
         u32 id = kNone;
-        if (lane < qn) id = finalizeKept(I, W, sQKey[warp][lane], sQCnt[warp][lane], A, sHist);
+        if (i < n) {
+            const u32 c = __ldcs(&W.entCnt[i]);
+            if (c >= minSup) id = finalizeKept(I, W, __ldcs(&W.entKey[i]), c, A, sHist);
+        }
         appendTouched(W, id, 0xffffffffu);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {
         const u32 c = (u32)acc->emptyKeyCount;
-        total += c; ++uniq;
         if (c >= minSup) finalizeKept(I, W, kEmptyKey, c, A, sHist);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kHistSmem; i += blockDim.x) if (sHist[i]) atomicAdd(&W.countHist[i], sHist[i]);
     const fx128 mag = fxWarpSum(A.mag), lsum = fxWarpSum(A.lsum);
-    const long long kept = warpSumLL(A.kept); total = warpSumLL(total); uniq = warpSumLL(uniq);
+    const long long kept = warpSumLL(A.kept);
     unsigned mx = A.maxc;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if (lane == 0) {
-        if (mx) atomicMax((unsigned long long*)&acc->maxKeptCount, (unsigned long long)mx);
-        fxAtomicAdd(acc->magSq, mag); fxAtomicAdd(acc->logSum, lsum);
-        if (kept) atomicAdd((unsigned long long*)&acc->kept, (unsigned long long)kept);
-        if (total) atomicAdd((unsigned long long*)&acc->total, (unsigned long long)total);
-        if (uniq) atomicAdd((unsigned long long*)&acc->unique, (unsigned long long)uniq);
+    if (lane == 0) { sRed[warp][0] = mag.lo; sRed[warp][1] = (u64)mag.hi; sRed[warp][2] = lsum.lo; sRed[warp][3] = (u64)lsum.hi; sKept[warp] = kept; sMax[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fx128 m = fxZero(), l = fxZero(); long long kp = 0; unsigned mm = 0;
+        for (int q = 0; q < 8; ++q) {
+            fx128 t; t.lo = sRed[q][0]; t.hi = (i64)sRed[q][1]; m = fxAdd(m, t);
+            t.lo = sRed[q][2]; t.hi = (i64)sRed[q][3]; l = fxAdd(l, t);
+            kp += sKept[q]; mm = max(mm, sMax[q]);
+        }
+        if (mm) atomicMax((unsigned long long*)&acc->maxKeptCount, (unsigned long long)mm);
+        if (kp) { fxAtomicAdd(acc->magSq, m); fxAtomicAdd(acc->logSum, l); atomicAdd((unsigned long long*)&acc->kept, (unsigned long long)kp); }
     }
 }
 
@@ -646,7 +647,7 @@ __global__ void __launch_bounds__(256) root_denominator(DevIndexView I, Workspac
     fx128 s = fxZero();
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < I.rootDCount; i += (u64)gridDim.x * blockDim.x) {
         const int c = (int)__ldg(&I.rootChild[i]);
-        if (c > 0 && W.ell[__ldg(&I.rootId[i])] != 0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
+        if (c > 0 && W.ell[2 * (size_t)__ldg(&I.rootId[i])] != 0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
     }
     s = fxWarpSum(s);
     if ((threadIdx.x & 31) == 0) fxAtomicAdd(W.acc->wcDen, s);
@@ -727,10 +728,12 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
     *W.scalars = S;
 }
 
-void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, cudaStream_t st) {
+void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, cudaStream_t st) {
     cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
-    table_stats<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W.table, W.tableCap, W.acc, homo);
-    table_finalize<<<streamGrid(W.tableCap, 8), 256, 0, st>>>(I, W, O.minReadSupport);
+    table_scan<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W, homo);
+    // sized from the previous sample's entry count (the kernel grid-strides, so any grid is correct)
+    u64 g = (expectedEntries + 255) / 256; if (g < 148) g = 148; if (g > 148 * 32) g = 148 * 32;
+    entries_finalize<<<(unsigned)g, 256, 0, st>>>(I, W, O.minReadSupport);
     if (I.hasRoot && I.rootDCount) {
         u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
         root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);
@@ -741,17 +744,18 @@ void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* hom
 // after a sample: clear exactly the ell entries it touched and the segment records that are combined with atomics
 __global__ void __launch_bounds__(256) reset_sample(DevIndexView I, WorkspaceView W) {
     const unsigned n = W.acc->touchedCount < W.touchedCap ? W.acc->touchedCount : W.touchedCap;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) W.ell[W.touched[i]] = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) *reinterpret_cast<longlong2*>(W.ell + 2 * (size_t)W.touched[i]) = make_longlong2(0, 0);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nBoundary; i += gridDim.x * blockDim.x)
         *reinterpret_cast<uint4*>(W.segRec + I.boundarySegs[i]) = make_uint4(0u, 0u, 0u, 0u);
 }
 void launchResetSample(DevIndexView I, WorkspaceView W, cudaStream_t st) { reset_sample<<<148, 256, 0, st>>>(I, W); }
 
 // ------------------------------------------------------------------------------------------------------
-// K1 node_deltas: one pass over the packed delta words (4 B per delta), no shared memory, no block barriers.
+// K1 node_deltas: one pass over the packed delta words (4 B per delta), no block barriers.
 // A warp owns a chunk of 512 consecutive words; lane l owns words [16 l, 16 l + 16): four 16-byte loads, then 16
-// independent gathers of ell[seed id] (log1p(read count) as an exact integer, 0 when the seed is not in the reads).
-// Node boundaries travel in-band (bit 31 = last delta of its node), so no offset array is read and no search is needed:
+// independent gathers of ell[word] (word = 2 * seed id + lost; the entry is +-log1p(read count) as an exact integer, 0 when the
+// seed is not in the reads -- the sign of a lost seed is already in the table).  Node boundaries come as one 16-bit mask per
+// lane (bit j = word j is the last delta of its node), so no offset array is read and no search is needed:
 //   * a node that begins and ends inside a lane is stored directly (sums of <= 16 terms fit 64 bits);
 //   * a node spread over several lanes is combined with a segmented warp scan (96-bit) and stored by the lane where it ends;
 //   * a node spread over several chunks (listed at flatten time, zeroed by reset_sample) is combined with integer atomics.
@@ -770,12 +774,25 @@ __device__ __forceinline__ void segStore(SegRec* r, u64 lo, int hi, int cnt) {
     *reinterpret_cast<uint4*>(r) = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)cnt);
 }
 
-__global__ void __launch_bounds__(256) node_deltas(DevIndexView I, WorkspaceView W) {
+constexpr int kK1Threads = 128;
+__global__ void __launch_bounds__(kK1Threads, 6) node_deltas(DevIndexView I, WorkspaceView W, u32 chunksPerWarp) {
+    // lane-local running sums after every word, [word][thread]: read back only at the (few) segment ends of the lane
+    __shared__ long long sP[16][kK1Threads];
+    __shared__ int sC[16][kK1Threads];
     const long long* __restrict__ ell = W.ell;
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
-    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
-    for (u64 c = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < I.nDeltaChunks; c += warpsTotal) {
+    // a warp owns a run of consecutive chunks: the open run at the end of a chunk is carried in registers into the next one,
+    // so atomics are only needed for a segment that crosses the first or the last chunk boundary of the run
+    const u64 c0 = ((u64)blockIdx.x * (kK1Threads >> 5) + (tid >> 5)) * chunksPerWarp;
+    if (c0 >= I.nDeltaChunks) return;
+    const u64 c1 = min(c0 + (u64)chunksPerWarp, I.nDeltaChunks);
+    const u32 cs0 = __ldg(&I.chunkSeg[c0]);
+    u32 segBase = cs0 & 0x7FFFFFFFu;        // segments that end before the current chunk
+    bool outside = (cs0 >> 31) != 0;        // the next segment end closes a segment that began before this warp's run
+    u64 clo = 0; int chi = 0, ccn = 0;      // open run carried over from the previous chunk (warp-uniform)
+    for (u64 c = c0; c < c1; ++c) {
+        const unsigned F = __ldg(&I.endMask[c * 32 + lane]);   // bit j: word j of this lane is the last delta of its node
         u32 w[16];
         {
             const uint4* p = reinterpret_cast<const uint4*>(I.dw + c * kChunkWords + lane * 16);
@@ -785,69 +802,82 @@ __global__ void __launch_bounds__(256) node_deltas(DevIndexView I, WorkspaceView
                 w[4 * q] = a.x; w[4 * q + 1] = a.y; w[4 * q + 2] = a.z; w[4 * q + 3] = a.w;
             }
         }
-        long long e[16];
+        long long v[16];   // w = 2 * seed id + lost: ell[w] is +log1p(read count) for a gained seed, -log1p for a lost one, 0 if absent
 #pragma unroll
-        for (int j = 0; j < 16; ++j) e[j] = __ldg(&ell[w[j] & 0x3FFFFFFFu]);
-        const u32 cs = __ldg(&I.chunkSeg[c]);
+        for (int j = 0; j < 16; ++j) v[j] = __ldg(&ell[w[j]]);
         // segment index of this lane's first segment end: segments ending in earlier chunks + in earlier lanes
-        unsigned nEnd = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) nEnd += w[j] >> 31;
+        const unsigned nEnd = __popc(F);
         unsigned endsBefore = nEnd;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const unsigned o = __shfl_up_sync(0xffffffffu, endsBefore, d); if (lane >= (unsigned)d) endsBefore += o; }
         const unsigned endsInChunk = __shfl_sync(0xffffffffu, endsBefore, 31);
         endsBefore -= nEnd;
-        const u32 segFirst = (cs & 0x7FFFFFFFu) + endsBefore;
-        // ---- walk the 16 words: interior segments are stored, the first end is kept for after the scan ----
-        long long acc = 0, headV = 0; int cn = 0, headC = 0; unsigned k = 0;
+        const u32 segFirst = segBase + endsBefore;
+        const unsigned endMask = __ballot_sync(0xffffffffu, nEnd != 0);
+        // ---- running sums of the 16 words (sums of <= 16 terms fit 64 bits) ----
+        long long acc = 0; int cn = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const bool lost = (w[j] >> 30) & 1u;
-            acc += lost ? -e[j] : e[j];
-            cn += e[j] ? (lost ? -1 : 1) : 0;
-            if (w[j] >> 31) {
-                if (k == 0) { headV = acc; headC = cn; }
-                else segStore(W.segRec + segFirst + k, (u64)acc, (int)(acc >> 63), cn);
-                ++k; acc = 0; cn = 0;
+            acc += v[j];
+            cn += (v[j] > 0) - (v[j] < 0);
+            sP[j][tid] = acc; sC[j][tid] = cn;
+        }
+        // trailing partial of the lane: everything after its last segment end (the whole lane when it has none)
+        long long headV = 0; int headC = 0;
+        if (F) {
+            const int first = __ffs(F) - 1, last = 31 - __clz(F);
+            headV = sP[first][tid]; headC = sC[first][tid];
+            long long pv = headV; int pcn = headC; unsigned k = 1;
+            for (unsigned Fm = F & (F - 1); Fm; Fm &= Fm - 1, ++k) {   // segments that begin and end inside the lane
+                const int j = __ffs(Fm) - 1;
+                const long long pj = sP[j][tid]; const int cj = sC[j][tid];
+                const long long sv = pj - pv;
+                segStore(W.segRec + segFirst + k, (u64)sv, (int)(sv >> 63), cj - pcn);
+                pv = pj; pcn = cj;
             }
+            acc -= sP[last][tid]; cn -= sC[last][tid];
         }
         // ---- segmented inclusive scan over the lanes' trailing partials (a lane with a segment end restarts the run) ----
-        const unsigned endMask = __ballot_sync(0xffffffffu, nEnd != 0);
         u64 lo = (u64)acc; int hi = (int)(acc >> 63); int rc = cn;
+        if (lane == 0 && !nEnd) { const u64 t = lo + clo; hi += chi + (t < lo ? 1 : 0); lo = t; rc += ccn; }
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const u64 olo = shflUpU64(lo, d);
             const int ohi = __shfl_up_sync(0xffffffffu, hi, d), oc = __shfl_up_sync(0xffffffffu, rc, d);
             // lanes (lane-d, lane] must all be free of segment ends for the value of lane-d to flow into this lane
-            const unsigned span = (d == 31 ? 0x7FFFFFFFu : ((1u << d) - 1u)) << (lane - d + 1);
-            if (lane >= (unsigned)d && !(endMask & span)) {
+            if (lane >= (unsigned)d && !(endMask & (((1u << d) - 1u) << (lane - d + 1)))) {
                 const u64 nlo = lo + olo;
                 hi += ohi + (nlo < lo ? 1 : 0);
                 lo = nlo; rc += oc;
             }
         }
-        // carry into this lane's first segment end = inclusive value of the previous lane
-        const u64 plo = shflUpU64(lo, 1);
-        const int phi = __shfl_up_sync(0xffffffffu, hi, 1), pc = __shfl_up_sync(0xffffffffu, rc, 1);
+        // carry into this lane's first segment end = inclusive value of the previous lane (lane 0: the run carried in)
+        u64 plo = shflUpU64(lo, 1);
+        int phi = __shfl_up_sync(0xffffffffu, hi, 1), pc = __shfl_up_sync(0xffffffffu, rc, 1);
+        if (lane == 0) { plo = clo; phi = chi; pc = ccn; }
         if (nEnd) {
             u64 flo = (u64)headV; int fhi = (int)(headV >> 63); int fc = headC;
-            if (lane) { const u64 t = flo + plo; fhi += phi + (t < flo ? 1 : 0); flo = t; fc += pc; }
+            { const u64 t = flo + plo; fhi += phi + (t < flo ? 1 : 0); flo = t; fc += pc; }
             SegRec* dst = W.segRec + segFirst;
-            if ((cs >> 31) && !(endMask & ltMask)) segAtomicAdd(dst, flo, fhi, fc);   // the segment began in an earlier chunk
+            if (outside && !(endMask & ltMask)) segAtomicAdd(dst, flo, fhi, fc);   // the segment began before this warp's run
             else segStore(dst, flo, fhi, fc);
         }
-        if (lane == 31 && !(w[15] >> 31)) {   // the chunk ends inside a segment: hand the open run to the chunk where it ends
-            const u32 sNext = (cs & 0x7FFFFFFFu) + endsInChunk;
-            if (sNext < I.nSeg) segAtomicAdd(W.segRec + sNext, lo, hi, rc);
-        }
+        if (endMask) outside = false;
+        // the open run after the chunk's last segment end travels on in registers
+        const bool open = !((__shfl_sync(0xffffffffu, F, 31) >> 15) & 1u);
+        clo = shflU64(lo, 31); chi = __shfl_sync(0xffffffffu, hi, 31); ccn = __shfl_sync(0xffffffffu, rc, 31);
+        if (!open) { clo = 0; chi = 0; ccn = 0; }
+        segBase += endsInChunk;
     }
+    if (lane == 0 && segBase < I.nSeg) segAtomicAdd(W.segRec + segBase, clo, chi, ccn);   // run ends inside a segment (no-op when zero)
 }
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st) {
     if (I.nDeltaChunks == 0) return;
-    u64 grid = (I.nDeltaChunks + 7) / 8;
-    if (grid > (u64)nSM * 8) grid = (u64)nSM * 8;
-    node_deltas<<<(unsigned)grid, 256, 0, st>>>(I, W);
+    const u64 warps = (u64)nSM * 6 * (kK1Threads / 32);   // 6 blocks per SM
+    const u32 per = (u32)((I.nDeltaChunks + warps - 1) / warps);
+    const u64 wpb = kK1Threads / 32;
+    const u64 grid = ((I.nDeltaChunks + per - 1) / per + wpb - 1) / wpb;
+    node_deltas<<<(unsigned)grid, kK1Threads, 0, st>>>(I, W, per);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -887,7 +917,7 @@ __device__ __forceinline__ Acc5 accLoad(const u64* p) {
 }
 __global__ void __launch_bounds__(256) gen_deltas(DevIndexView I, WorkspaceView W) {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nGenDeltas; i += gridDim.x * blockDim.x) {
-        const long long e = __ldg(&W.ell[I.genId[i]]);
+        const long long e = __ldg(&W.ell[2 * (size_t)I.genId[i]]);
         if (!e) continue;
         const u32 pcv = I.genPc[i];
         const int p = (int)(short)(pcv & 0xFFFFu), c = (int)(short)(pcv >> 16);
@@ -936,11 +966,13 @@ void launchGeneral(DevIndexView I, WorkspaceView W, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------------
 // K2 prefix_scores: A[v] = sum of the segment records over the root->v path, exact (96-bit integers + counts).
-// Tile = kTileNodesK2 consecutive DFS nodes.  The carry-in of a tile is the path root -> parent(first node),
+// Tile = kTileNodesK2 consecutive DFS nodes, 4 per thread.  The carry-in of a tile is the path root -> parent(first node),
 // whose records were all written by K1, so every tile is independent (no inter-CTA dependency):
-//   1. inclusive scan along the precomputed ancestor chain -> A[ancestor j]
+//   1. inclusive scan along the precomputed ancestor chain -> A[ancestor j]   (shared memory; global for very deep chains)
 //   2. d'[w] = rec[w] (+ A[parent(w)] when the parent lies outside the tile)
-//   3. Euler-tour difference inside the tile: diff[w] = d'[w] - sum_{u in tile, subtree(u) ends right before w} d'[u]
+//   3. Euler-tour difference inside the tile: diff[w] = d'[w] - sum_{u in tile, subtree(u) ends right before w} d'[u],
+//      built with one shared-memory reduction per node (u subtracts itself at subEnd[u]): perfectly balanced, no lists.
+//      The 96-bit values are split into carry-free limbs {sum of low 32-bit pieces, sum of the upper pieces} for this.
 //   4. inclusive scan of diff = A[w]; add the general-delta prefix (event lookup) when the index has any; scores; store
 // ------------------------------------------------------------------------------------------------------
 struct Seg3 { u64 lo; int hi; int cnt; };
@@ -980,62 +1012,95 @@ __device__ __forceinline__ Seg3 blockInclusiveScan(Seg3 v, SegRec* sWarp) {
     for (int q = 0; q < warp; ++q) pre = s3Add(pre, s3Load(sWarp + q));
     return s3Add(v, pre);
 }
+constexpr int kChainSmem = 256;   // ancestor chains up to this length are kept in shared memory
+constexpr int kK2Per = kTileNodesK2 / 256;
 
 __global__ void __launch_bounds__(256) prefix_scores(DevIndexView I, WorkspaceView W, PlaceOpts O) {
-    __shared__ SegRec sD[kTileNodesK2];
+    __shared__ long long sA[kTileNodesK2];   // diff, low limb: sum of the low 32-bit pieces
+    __shared__ long long sB[kTileNodesK2];   // diff, upper limb: sum of (value >> 32)
+    __shared__ int sC[kTileNodesK2];         // diff, count
+    __shared__ SegRec sChain[kChainSmem];
     __shared__ SegRec sWarp[8];
     __shared__ SegRec sCarry;
     const u32 tile = blockIdx.x;
     const u32 a0 = I.nodeBegin + tile * kTileNodesK2;
     const u32 a1 = min(a0 + (u32)kTileNodesK2, I.nodeEnd);
     const int tid = threadIdx.x;
-    const SampleScalars S = *W.scalars;
 
     // 1. ancestor chain
     const u32 cb = I.chainOff[tile], ce = I.chainOff[tile + 1];
-    Seg3 carry = s3Zero();
-    for (u32 base = cb; base < ce; base += 256) {
-        Seg3 v = s3Zero();
-        const u32 j = base + tid;
-        if (j < ce) v = s3OfNode(I, W, I.chainNodes[j]);
-        v = blockInclusiveScan(v, sWarp);
-        v = s3Add(v, carry);
-        if (j < ce) s3Store(W.chainA + j, v);
-        if (tid == 255) s3Store(&sCarry, v);
-        __syncthreads();
-        carry = s3Load(&sCarry);
-        __syncthreads();
-    }
-    __syncthreads();
-    // 2. d'
-    for (u32 w = a0 + tid; w < a1; w += 256) {
-        Seg3 v = s3OfNode(I, W, w);
-        const u32 cs = I.carrySlot[w];
-        if (cs != kNone) v = s3Add(v, s3Load(W.chainA + cb + cs));
-        s3Store(sD + (w - a0), v);
-    }
-    __syncthreads();
-    // 3+4. two consecutive nodes per thread
-    const u32 w0 = a0 + 2 * tid;
-    Seg3 d[2];
+    SegRec* const chainA = (ce - cb <= (u32)kChainSmem) ? sChain : W.chainA + cb;
+    if (ce - cb <= 32u) {   // the common case: one warp, no block barriers
+        if (tid < 32) {
+            Seg3 v = s3Zero();
+            if (cb + tid < ce) v = s3OfNode(I, W, I.chainNodes[cb + tid]);
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const u32 w = w0 + q;
-        d[q] = s3Zero();
-        if (w < a1) {
-            d[q] = s3Load(sD + (w - a0));
-            const u32 c0 = I.closeOff[w], c1 = I.closeOff[w + 1];
-            for (u32 c = c0; c < c1; ++c) {
-                const u32 u = I.closeList[c];
-                if (u >= a0) d[q] = s3Sub(d[q], s3Load(sD + (u - a0)));
-            }
+            for (int d = 1; d < 32; d <<= 1) { const Seg3 o = s3ShflUp(v, d); if (tid >= d) v = s3Add(v, o); }
+            if (cb + tid < ce) s3Store(chainA + tid, v);
+        }
+    } else {
+        Seg3 carry = s3Zero();
+        for (u32 base = cb; base < ce; base += 256) {
+            Seg3 v = s3Zero();
+            const u32 j = base + tid;
+            if (j < ce) v = s3OfNode(I, W, I.chainNodes[j]);
+            v = blockInclusiveScan(v, sWarp);
+            v = s3Add(v, carry);
+            if (j < ce) s3Store(chainA + (j - cb), v);
+            if (tid == 255) s3Store(&sCarry, v);
+            __syncthreads();
+            carry = s3Load(&sCarry);
+            __syncthreads();
         }
     }
-    const Seg3 mine = s3Add(d[0], d[1]);
+    // 2. d' of this thread's consecutive nodes; their own records are fetched while the chain settles
+    const u32 w0 = a0 + kK2Per * tid;
+    Seg3 d[kK2Per]; u32 cslot[kK2Per], send[kK2Per];
+#pragma unroll
+    for (int q = 0; q < kK2Per; ++q) {
+        const u32 w = w0 + q;
+        d[q] = s3Zero(); cslot[q] = kNone; send[q] = kNone;
+        if (w < a1) { d[q] = s3OfNode(I, W, w); cslot[q] = __ldg(&I.carrySlot[w]); send[q] = __ldg(&I.subEnd[w]); }
+    }
+    __syncthreads();
+    if (ce - cb > (u32)kChainSmem) __threadfence_block();
+#pragma unroll
+    for (int q = 0; q < kK2Per; ++q) {
+        if (cslot[q] != kNone) d[q] = s3Add(d[q], s3Load(chainA + cslot[q]));
+        const int li = kK2Per * tid + q;
+        const long long up = (long long)((d[q].lo >> 32) | ((u64)(i64)d[q].hi << 32));
+        sA[li] = (long long)(d[q].lo & 0xFFFFFFFFULL); sB[li] = up; sC[li] = d[q].cnt;
+    }
+    __syncthreads();
+    // 3. every node subtracts itself where its subtree ends (if that is inside the tile)
+#pragma unroll
+    for (int q = 0; q < kK2Per; ++q) {
+        if (send[q] < a1) {
+            const int li = (int)(send[q] - a0);
+            const long long up = (long long)((d[q].lo >> 32) | ((u64)(i64)d[q].hi << 32));
+            atomicAdd(reinterpret_cast<unsigned long long*>(&sA[li]), (unsigned long long)(-(long long)(d[q].lo & 0xFFFFFFFFULL)));
+            atomicAdd(reinterpret_cast<unsigned long long*>(&sB[li]), (unsigned long long)(-up));
+            if (d[q].cnt) atomicAdd(&sC[li], -d[q].cnt);
+        }
+    }
+    __syncthreads();
+    // 4. scan of the differences
+    Seg3 mine = s3Zero();
+#pragma unroll
+    for (int q = 0; q < kK2Per; ++q) {
+        const int li = kK2Per * tid + q;
+        const long long a = sA[li], b = sB[li];
+        // value = a + b * 2^32 as a signed 96-bit integer
+        Seg3 x; x.lo = (u64)a; x.hi = (int)(a >> 63); x.cnt = sC[li];
+        Seg3 y; y.lo = (u64)b << 32; y.hi = (int)(b >> 32); y.cnt = 0;
+        d[q] = s3Add(x, y);
+        mine = s3Add(mine, d[q]);
+    }
     const Seg3 incl = blockInclusiveScan(mine, sWarp);
     Seg3 run = s3Sub(incl, mine);
+    const SampleScalars S = *W.scalars;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
+    for (int q = 0; q < kK2Per; ++q) {
         const u32 w = w0 + q;
         if (w < a1) {
             run = s3Add(run, d[q]);

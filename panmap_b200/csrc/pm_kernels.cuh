@@ -7,7 +7,6 @@
 namespace pm {
 
 constexpr int kChunkWords = 512;    // K1: packed delta words per warp chunk (16 consecutive words per lane)
-constexpr int kTileNodesK2 = 512;   // K2: nodes per prefix tile
 constexpr int kBfsBlock = 1024;     // selection: BFS positions per block
 constexpr int kLog1pLut = 1 << 16;  // log1p(count) table computed on the host with glibc (bit-identical terms)
 constexpr u32 kNone = 0xFFFFFFFFu;
@@ -27,7 +26,7 @@ struct __align__(16) DictSlot { u64 key; u32 id; u32 pad; };       // index dict
 struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample)
     u64 magSq[2], logSum[2], wcDen[2];  // fx128 as (lo, hi)
     long long kept, total, unique, multiSum, multiCount, entries, maxKeptCount, overflow, emptyKeyCount;
-    unsigned touchedCount, pad0;
+    unsigned touchedCount, entCount;
     unsigned recordCount[8];
     unsigned tieCount[8];
 };
@@ -45,7 +44,8 @@ struct DevIndexView {
     u32 nAnc;
     u64 nLocalDeltas;
     u64 nSeeds;        // distinct seed hashes of the whole index
-    const u32* dw;         // [nDeltaChunks*512] packed fast deltas: seed id | lost << 30 | segment end << 31
+    const u32* dw;         // [nDeltaChunks*512] packed fast deltas: 2 * seed id + lost
+    const u32* endMask;    // [nDeltaChunks*32] per lane (16 words): bit j = word j is the last fast delta of its node
     u64 nDeltaChunks;
     const u32* chunkSeg;   // [nDeltaChunks+1] segments ending before the chunk | bit 31: the chunk starts inside a segment
     const u32* nodeSeg;    // [nNodes] segment of a node, kNone when it has no fast deltas (or is not local)
@@ -57,8 +57,7 @@ struct DevIndexView {
     // tree (global arrays)
     const u32* parent;     // [nNodes]
     const double* gMag;    // [nNodes] sqrt(genomeMagnitudeSquared)
-    const u32* closeOff;   // [nNodes+1] CSR: nodes whose subtree ends right before node w
-    const u32* closeList;
+    const u32* subEnd;     // [nNodes] one past the last DFS index of the node's subtree
     const u32* carrySlot;  // [nNodes] (shard-specific) chain position of the parent when it lies outside w's K2 tile
     const u32* chainOff;   // [nK2Tiles+1]
     const u32* chainNodes; // ancestors (root first) of each K2 tile's first node
@@ -83,8 +82,9 @@ struct WorkspaceView {
     TableSlot* table; u64 tableMask; u64 tableCap;
     SampleAcc* acc;
     u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
-    long long* ell;       // [nSeeds+1] log1p(read count) * 2^53 of seed id (an exact integer), 0 when absent; [nSeeds] stays 0
+    long long* ell;       // [2*(nSeeds+1)] {+l, -l} with l = log1p(read count) * 2^53 of the seed (an exact integer), 0 when absent; slot nSeeds stays 0
     u32* touched; u32 touchedCap;
+    u64* entKey; u32* entCnt;   // [tableCap] occupied (key, count) pairs compacted by table_scan
     unsigned* countHist;  // [kLog1pLut] multiplicity of every read count among the kept seeds (rounding-drift model)
     SegRec* segRec;       // [nSeg]
     SegRec* chainA;       // [chainTotal] prefix along each K2 tile's ancestor chain
@@ -118,7 +118,7 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
 void launchTableClear(WorkspaceView W, cudaStream_t st);
 void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st);
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st);
-void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, cudaStream_t st);
+void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, cudaStream_t st);
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st);
 void launchGeneral(DevIndexView I, WorkspaceView W, cudaStream_t st);
 void launchPrefixScores(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st);

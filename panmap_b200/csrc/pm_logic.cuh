@@ -31,6 +31,7 @@ constexpr u64 kHashG = 0x20323ed082572324ULL;
 constexpr u64 kHashT = 0x295549f54be24456ULL;
 constexpr u64 kEmptyKey = 0xFFFFFFFFFFFFFFFFULL;
 constexpr int kMaxK = 32;  // 4-bit base codes in a 128-bit history register
+constexpr int kTileNodesK2 = 1024;  // prefix_scores: consecutive DFS nodes per tile (4 per thread)
 
 PM_HD u64 rol64(u64 h, unsigned r) { r &= 63u; return r ? (h << r) | (h >> (64u - r)) : h; }
 PM_HD u64 ror64(u64 h, unsigned r) { r &= 63u; return r ? (h >> r) | (h << (64u - r)) : h; }

@@ -53,7 +53,6 @@ static Acc5 accNeg(const Acc5& a) { Acc5 r; for (int i = 0; i < 4; ++i) r.f[i] =
 struct Seg { u64 lo; int hi; int cnt; };
 static Seg segZ() { return Seg{0, 0, 0}; }
 static Seg segAdd(const Seg& a, const Seg& b) { Seg r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo ? 1 : 0); r.cnt = a.cnt + b.cnt; return r; }
-static Seg segSub(const Seg& a, const Seg& b) { Seg r; r.lo = a.lo - b.lo; r.hi = a.hi - b.hi - (a.lo < b.lo ? 1 : 0); r.cnt = a.cnt - b.cnt; return r; }
 static Seg segOf(long long v, int c) { return Seg{(u64)v, (int)(v >> 63), c}; }
 
 // CPU emulation of finalize + K1 (node_deltas, warp by warp) + general deltas + K2 (prefix_scores, tile by tile) for shard
@@ -61,12 +60,12 @@ static Seg segOf(long long v, int c) { return Seg{(u64)v, (int)(v >> 63), c}; }
 // scores out: [N][5].  scal: U', magnitude, logSum, wcDenom.
 int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards, const uint64_t* tHash, const double* tLog, int64_t U,
                        double U1, double mag, double denL, double* metrics, double* scores, double* wcDenOut,
-                       uint32_t* nodeBegin, uint32_t* nodeEnd) {
+                       uint32_t* nodeBegin, uint32_t* nodeEnd, uint32_t chunksPerWarp) {
     try {
         FlatIndex F; flattenIndex(*d, shard, nShards, F);
         *nodeBegin = F.nodeBegin; *nodeEnd = F.nodeEnd;
         // ell by seed id through the dictionary table (as table_finalize does): log1p(count) * 2^53, an exact integer
-        std::vector<long long> ell(F.S + 1, 0);
+        std::vector<long long> ell(2 * (F.S + 1), 0);   // {+l, -l} per seed id
         for (int64_t i = 0; i < U; ++i) {
             if (!(tLog[i] > 0.0)) continue;
             u64 s = mixKey(tHash[i]) & F.dictMask;
@@ -75,7 +74,7 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
                     if (F.dictVals[s] != 0xFFFFFFFFu) {
                         const double sc = tLog[i] * 9007199254740992.0;
                         if (sc != std::floor(sc) || sc >= 9.2e18) throw std::runtime_error("log1p(count) is not a multiple of 2^-53");
-                        ell[F.dictVals[s]] = (long long)sc;
+                        ell[2 * (size_t)F.dictVals[s]] = (long long)sc; ell[2 * (size_t)F.dictVals[s] + 1] = -(long long)sc;
                     }
                     break;
                 }
@@ -87,51 +86,71 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
         fx128 wc = fxZero();
         for (size_t i = 0; i < F.rootId.size(); ++i) {
             const int c = (int)F.rootChild[i];
-            if (c > 0 && ell[F.rootId[i]] != 0) wc = fxAdd(wc, fxFromDouble(1.0 / (double)c));
+            if (c > 0 && ell[2 * (size_t)F.rootId[i]] != 0) wc = fxAdd(wc, fxFromDouble(1.0 / (double)c));
         }
         const double denW = fxToDouble(wc);
         *wcDenOut = denW;
         // ---- K1: 32 lanes x 16 words per chunk ----
-        if (F.dw.size() != F.nDeltaChunks * 512 || F.chunkSeg.size() != F.nDeltaChunks + 1) throw std::runtime_error("chunk schedule size mismatch");
+        if (F.dw.size() != F.nDeltaChunks * 512 || F.chunkSeg.size() != F.nDeltaChunks + 1 || F.endMask.size() != F.nDeltaChunks * 32)
+            throw std::runtime_error("chunk schedule size mismatch");
         std::vector<Seg> segRec(F.nSeg + 1, segZ());
         std::vector<int> stored(F.nSeg + 1, 0);
         std::vector<char> isBoundary(F.nSeg + 1, 0);
         for (uint32_t b : F.boundarySegs) isBoundary[b] = 1;
+        std::vector<char> atomicked(F.nSeg + 1, 0);
         auto store = [&](uint32_t sg, const Seg& v) {
             if (sg >= F.nSeg) throw std::runtime_error("segment index out of range");
-            if (isBoundary[sg]) throw std::runtime_error("plain store to a segment that spans chunks");
+            if (atomicked[sg]) throw std::runtime_error("plain store to a segment that also receives atomic adds");
             if (stored[sg]++) throw std::runtime_error("segment stored twice");
             segRec[sg] = v;
         };
         auto atomic = [&](uint32_t sg, const Seg& v) {
-            if (!v.lo && !v.hi && !v.cnt) return;
             if (sg >= F.nSeg) throw std::runtime_error("atomic segment index out of range");
             if (!isBoundary[sg]) throw std::runtime_error("atomic add to a segment that is not zeroed per sample");
+            if (stored[sg]) throw std::runtime_error("atomic add to a segment that was plainly stored");
+            atomicked[sg] = 1;
             segRec[sg] = segAdd(segRec[sg], v);
         };
-        for (u64 c = 0; c < F.nDeltaChunks; ++c) {
-            const uint32_t cs = F.chunkSeg[c];
+        const u64 per = chunksPerWarp ? chunksPerWarp : 1;
+        for (u64 c0 = 0; c0 < F.nDeltaChunks; c0 += per) {   // one warp = a run of `per` consecutive chunks
+          const u64 c1 = std::min<u64>(c0 + per, F.nDeltaChunks);
+          uint32_t segBase = F.chunkSeg[c0] & 0x7FFFFFFFu;
+          bool outside = (F.chunkSeg[c0] >> 31) != 0;
+          Seg carry = segZ(); bool open = false;
+          for (u64 c = c0; c < c1; ++c) {
+            if (segBase != (F.chunkSeg[c] & 0x7FFFFFFFu)) throw std::runtime_error("running segment base disagrees with chunkSeg");
             unsigned nEnd[32], endsBefore[32]; Seg tail[32], head[32]; unsigned endMask = 0, total = 0;
             for (int lane = 0; lane < 32; ++lane) {
                 const uint32_t* w = &F.dw[c * 512 + (u64)lane * 16];
-                nEnd[lane] = 0; for (int j = 0; j < 16; ++j) nEnd[lane] += w[j] >> 31;
+                const unsigned Fm = F.endMask[c * 32 + lane];
+                if (Fm >> 16) throw std::runtime_error("end mask has bits above 15");
+                nEnd[lane] = (unsigned)__builtin_popcount(Fm);
                 endsBefore[lane] = total; total += nEnd[lane];
                 if (nEnd[lane]) endMask |= 1u << lane;
-                const uint32_t segFirst = (cs & 0x7FFFFFFFu) + endsBefore[lane];
-                long long acc = 0; int cn = 0; unsigned k = 0; head[lane] = segZ();
-                for (int j = 0; j < 16; ++j) {
-                    const bool lost = (w[j] >> 30) & 1u;
-                    const long long e = ell[w[j] & 0x3FFFFFFFu];
-                    acc += lost ? -e : e; cn += e ? (lost ? -1 : 1) : 0;
-                    if (w[j] >> 31) {
-                        if (k == 0) head[lane] = segOf(acc, cn); else store(segFirst + k, segOf(acc, cn));
-                        ++k; acc = 0; cn = 0;
+                const uint32_t segFirst = segBase + endsBefore[lane];
+                long long P[16]; int Cn[16]; long long acc = 0; int cn = 0;
+                for (int j = 0; j < 16; ++j) {   // running sums, staged in shared memory by the kernel
+                    const long long v = ell[w[j]];
+                    acc += v; cn += (v > 0) - (v < 0);
+                    P[j] = acc; Cn[j] = cn;
+                }
+                head[lane] = segZ();
+                if (Fm) {
+                    const int first = __builtin_ctz(Fm), last = 31 - __builtin_clz(Fm);
+                    head[lane] = segOf(P[first], Cn[first]);
+                    long long pv = P[first]; int pcn = Cn[first]; unsigned k = 1;
+                    for (unsigned m = Fm & (Fm - 1); m; m &= m - 1, ++k) {
+                        const int j = __builtin_ctz(m);
+                        store(segFirst + k, segOf(P[j] - pv, Cn[j] - pcn));
+                        pv = P[j]; pcn = Cn[j];
                     }
+                    acc -= P[last]; cn -= Cn[last];
                 }
                 tail[lane] = segOf(acc, cn);
             }
             Seg incl[32];
             for (int lane = 0; lane < 32; ++lane) incl[lane] = tail[lane];
+            if (!nEnd[0]) incl[0] = segAdd(incl[0], carry);
             for (int dd = 1; dd < 32; dd <<= 1) {   // Hillis-Steele, all lanes read the previous step's values
                 Seg prev[32]; for (int lane = 0; lane < 32; ++lane) prev[lane] = incl[lane];
                 for (int lane = dd; lane < 32; ++lane) {
@@ -141,25 +160,27 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
             }
             for (int lane = 0; lane < 32; ++lane) {
                 if (!nEnd[lane]) continue;
-                Seg f = head[lane];
-                if (lane) f = segAdd(f, incl[lane - 1]);
-                const uint32_t sg = (cs & 0x7FFFFFFFu) + endsBefore[lane];
-                if ((cs >> 31) && !(endMask & ((1u << lane) - 1u))) atomic(sg, f); else store(sg, f);
+                const Seg f = segAdd(head[lane], lane ? incl[lane - 1] : carry);
+                const uint32_t sg = segBase + endsBefore[lane];
+                if (outside && !(endMask & ((1u << lane) - 1u))) atomic(sg, f); else store(sg, f);
             }
-            if (!(F.dw[c * 512 + 511] >> 31)) {
-                const uint32_t sNext = (cs & 0x7FFFFFFFu) + total;
-                if (sNext < F.nSeg) atomic(sNext, incl[31]);
-                else if (incl[31].lo || incl[31].hi || incl[31].cnt) throw std::runtime_error("open run after the last segment");
-            }
+            if (endMask) outside = false;
+            open = !((F.endMask[c * 32 + 31] >> 15) & 1u);
+            carry = open ? incl[31] : segZ();
+            segBase += total;
+          }
+          if (!open) continue;   // (the kernel issues a no-op: its atomic add skips zero values)
+          if (segBase < F.nSeg) atomic(segBase, carry);
+          else if (carry.lo || carry.hi || carry.cnt) throw std::runtime_error("open run after the last segment");
         }
         for (uint32_t sg = 0; sg < F.nSeg; ++sg)
-            if (!isBoundary[sg] && stored[sg] != 1) throw std::runtime_error("a segment was not stored exactly once");
+            if (!atomicked[sg] && stored[sg] != 1) throw std::runtime_error("a segment was not stored exactly once");
         // ---- general deltas + event prefix ----
         std::vector<double> l1p(32768); for (int c = 0; c < 32768; ++c) l1p[c] = std::log1p((double)c);
         const double ln2 = std::log1p(1.0);
         std::vector<Acc5> genRec(F.nGenNodes, accZ()), evPrefix(F.evSlot.size(), accZ());
         for (size_t i = 0; i < F.genSlot.size(); ++i) {
-            const long long e = ell[F.genId[i]];
+            const long long e = ell[2 * (size_t)F.genId[i]];
             if (!e) continue;
             const int p = (int)(short)(F.genPc[i] & 0xFFFF), cc = (int)(short)(F.genPc[i] >> 16);
             const DeltaTerms t = deltaTerms((double)e / 9007199254740992.0, p, cc, p > 0 ? l1p[p] : 0.0, cc > 0 ? l1p[cc] : 0.0);
@@ -179,23 +200,32 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
         SampleScalars S; std::memset(&S, 0, sizeof(S));
         S.readMagnitude = mag; S.logContDenom = denL; S.wcDenom = denW; S.uniqueKept = U1;
         for (uint32_t tile = 0; tile < F.nK2Tiles; ++tile) {
-            const uint32_t a0 = F.nodeBegin + tile * 512, a1 = std::min(a0 + 512u, F.nodeEnd);
+            const uint32_t T = kTileNodesK2;
+            const uint32_t a0 = F.nodeBegin + tile * T, a1 = std::min(a0 + T, F.nodeEnd);
             const uint32_t cb = F.chainOff[tile], ce = F.chainOff[tile + 1];
             std::vector<Seg> chainA(ce - cb);
             Seg run = segZ();
             for (uint32_t j = cb; j < ce; ++j) { run = segAdd(run, recOf(F.chainNodes[j])); chainA[j - cb] = run; }
+            // d' split into carry-free limbs; every node subtracts itself where its subtree ends (shared-memory reductions)
+            std::vector<long long> sA(a1 - a0), sB(a1 - a0); std::vector<int> sC(a1 - a0);
             std::vector<Seg> dp(a1 - a0);
             for (uint32_t w = a0; w < a1; ++w) {
                 Seg v = recOf(w);
                 const uint32_t cs = F.carrySlot[w];
                 if (cs != 0xFFFFFFFFu) { if (cs >= ce - cb) throw std::runtime_error("carry slot outside chain"); v = segAdd(v, chainA[cs]); }
                 dp[w - a0] = v;
+                sA[w - a0] = (long long)(v.lo & 0xFFFFFFFFULL); sB[w - a0] = (long long)((v.lo >> 32) | ((u64)(i64)v.hi << 32)); sC[w - a0] = v.cnt;
+            }
+            for (uint32_t w = a1; w-- > a0;) {   // any order
+                if (F.subEnd[w] >= a1) continue;
+                const Seg& v = dp[w - a0]; const uint32_t li = F.subEnd[w] - a0;
+                sA[li] -= (long long)(v.lo & 0xFFFFFFFFULL); sB[li] -= (long long)((v.lo >> 32) | ((u64)(i64)v.hi << 32)); sC[li] -= v.cnt;
             }
             Seg pre = segZ();
             for (uint32_t w = a0; w < a1; ++w) {
-                Seg dd = dp[w - a0];
-                for (uint32_t c = F.closeOff[w]; c < F.closeOff[w + 1]; ++c) { const uint32_t u = F.closeList[c]; if (u >= a0) dd = segSub(dd, dp[u - a0]); }
-                pre = segAdd(pre, dd);
+                const long long a = sA[w - a0], b = sB[w - a0];
+                const Seg x{(u64)a, (int)(a >> 63), sC[w - a0]}, y{(u64)b << 32, (int)(b >> 32), 0};
+                pre = segAdd(pre, segAdd(x, y));
                 double* m = metrics + (size_t)w * 5;
                 const uint32_t ne = F.nGenNodes ? F.evIdx[w] : 0u;
                 nodeNumerators(pre.lo, pre.hi, pre.cnt, ne ? &evPrefix[ne - 1] : nullptr, ln2, m);

@@ -64,7 +64,7 @@ def test_fixed_point_is_exact_and_order_free(hc):
     assert abs(f.value - math.fsum(x)) <= 2.0 ** -64 * x.size + abs(math.fsum(x)) * 2.0 ** -52
 
 
-def _emulate(hc, idx, th, logv, kept, mag, lsum, shards):
+def _emulate(hc, idx, th, logv, kept, mag, lsum, shards, chunks_per_warp=3):
     import panmap_b200 as pm
     host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l)
     d = host.desc()
@@ -73,7 +73,7 @@ def _emulate(hc, idx, th, logv, kept, mag, lsum, shards):
     covered = np.zeros(N, np.int32)
     for sh in range(shards):
         rc = hc.hc_emulate_scoring(C.byref(d), sh, shards, _p(th), _p(logv), C.c_int64(th.size), C.c_double(kept), C.c_double(mag), C.c_double(lsum),
-                                   _p(metrics), _p(scores), C.byref(wc), C.byref(nb), C.byref(ne))
+                                   _p(metrics), _p(scores), C.byref(wc), C.byref(nb), C.byref(ne), C.c_uint32(chunks_per_warp))
         assert rc == 0, hc.hc_last_error()
         covered[nb.value:ne.value] += 1
     assert (covered == 1).all()
@@ -97,6 +97,9 @@ def test_flatten_and_tile_algorithms_match_oracle(hc, shards):
     assert H.relerr(wc, denW) < 1e-13
     if shards > 1:                                                  # exact arithmetic: sharding cannot change a bit
         m1, s1, _ = _emulate(hc, idx, th, logv, sc["kept"], sc["magnitude"], sc["log_sum"], 1)
+        assert np.array_equal(m, m1) and np.array_equal(s, s1)
+    for per in (1, 2, 1000):                                        # ... and neither can the split of the delta stream over warps
+        m1, s1, _ = _emulate(hc, idx, th, logv, sc["kept"], sc["magnitude"], sc["log_sum"], shards, chunks_per_warp=per)
         assert np.array_equal(m, m1) and np.array_equal(s, s1)
 
 
