@@ -104,7 +104,8 @@ struct pm_workspace {
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0;
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
-    DevBuf<long long> ell; DevBuf<u32> touched; DevBuf<unsigned> countHist; DevBuf<u64> entKey; DevBuf<u32> entCnt;
+    DevBuf<long long> ell; DevBuf<unsigned> countHist; DevBuf<u64> entKey; DevBuf<u32> entCnt, entId;
+    DevBuf<ScanPartial> scanPart; DevBuf<FinPartial> finPart;
     DevBuf<SegRec> segRec, chainA;
     DevBuf<u64> genRec, evPrefix;
     DevBuf<double> scores, metrics, blockMaxAndBfs;
@@ -197,7 +198,8 @@ void refreshView(pm_workspace* W) {
     WorkspaceView& V = W->view;
     V.table = W->table.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
     V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
-    V.acc = W->acc.p; V.ell = W->ell.p; V.touched = W->touched.p; V.touchedCap = (u32)W->touched.n; V.countHist = W->countHist.p; V.entKey = W->entKey.p; V.entCnt = W->entCnt.p;
+    V.acc = W->acc.p; V.ell = W->ell.p; V.countHist = W->countHist.p; V.entKey = W->entKey.p; V.entCnt = W->entCnt.p; V.entId = W->entId.p;
+    V.scanPart = W->scanPart.p; V.finPart = W->finPart.p;
     V.segRec = W->segRec.p; V.chainA = W->chainA.p; V.genRec = W->genRec.p; V.evPrefix = W->evPrefix.p;
     V.scores = W->scores.p; V.metrics = W->wantMetrics ? W->metrics.p : nullptr; V.blockMax = W->blockMaxAndBfs.p;
     V.recRank = W->recRank.p; V.recNode = W->recNode.p; V.recScore = W->recScore.p; V.recCap = W->recCap;
@@ -208,7 +210,7 @@ void ensureTable(pm_workspace* W, u64 wantCap) {
     u64 cap = 1 << 12;
     while (cap < wantCap) cap <<= 1;
     if (cap <= W->tableCap) return;
-    W->table.alloc(cap); W->tableCap = cap; W->entKey.alloc(cap); W->entCnt.alloc(cap);
+    W->table.alloc(cap); W->tableCap = cap; W->entKey.alloc(cap); W->entCnt.alloc(cap); W->entId.alloc(cap);
     refreshView(W);
 }
 
@@ -320,7 +322,7 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
 void stageScore(pm_workspace* W, const pm_place_params& prm) {
     pm_index* I = W->idx;
     const PlaceOpts O = makeOpts(prm, W->wantMetrics);
-    launchFinalize(I->view, W->view, O, I->homo.p, W->lastEntries ? W->lastEntries : W->tableCap / 4, W->st);
+    launchFinalize(I->view, W->view, O, I->homo.p, W->lastEntries ? W->lastEntries : W->tableCap / 4, I->nSM, W->st);
     CK(cudaEventRecord(W->ev[3], W->st));
     launchDeltas(I->view, W->view, I->nSM, W->st);
     launchGeneral(I->view, W->view, W->st);
@@ -509,8 +511,8 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
         W->acc.alloc(1); W->scalars.alloc(1); W->sel.alloc(5);
-        W->ell.alloc(2 * (F.S + 1)); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(long long), W->st));   // [S] is the always-zero slot of the padding words
-        W->touched.alloc(F.S ? F.S : 1);
+        W->ell.alloc(F.S + 2); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(long long), W->st));   // [S] is the always-zero slot of the padding words
+        W->scanPart.alloc(kMaxPartials); W->finPart.alloc(kMaxPartials);
         W->countHist.alloc(kLog1pLut);
         W->segRec.alloc(F.nSeg + 1); CK(cudaMemsetAsync(W->segRec.p, 0, W->segRec.n * sizeof(SegRec), W->st));
         W->chainA.alloc(V.chainTotal ? V.chainTotal : 1);
@@ -585,10 +587,10 @@ int pm_get_node_metrics(pm_workspace* ws, double* out) {
         CK(cudaMemsetAsync(ws->metrics.p, 0, I->F.N * 5 * sizeof(double), ws->st));
         ws->wantMetrics = true; refreshView(ws);
         // ell was reset after the sample: rebuild it from the (still intact) table, then K1 + K2 only
-        CK(cudaMemsetAsync(&ws->acc.p->touchedCount, 0, 2 * sizeof(unsigned), ws->st));   // touchedCount + entCount
+        CK(cudaMemsetAsync(&ws->acc.p->entCount, 0, sizeof(unsigned), ws->st));
         CK(cudaMemsetAsync(ws->acc.p->magSq, 0, 6 * sizeof(u64) + 7 * sizeof(long long), ws->st));
         const PlaceOpts O = makeOpts(ws->lastParams, true);
-        launchFinalize(I->view, ws->view, O, I->homo.p, ws->lastEntries ? ws->lastEntries : ws->tableCap / 4, ws->st);
+        launchFinalize(I->view, ws->view, O, I->homo.p, ws->lastEntries ? ws->lastEntries : ws->tableCap / 4, I->nSM, ws->st);
         launchDeltas(I->view, ws->view, I->nSM, ws->st);
         launchGeneral(I->view, ws->view, ws->st);
         launchPrefixScores(I->view, ws->view, O, ws->st);

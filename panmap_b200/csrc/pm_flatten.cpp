@@ -212,6 +212,14 @@ void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, Flat
         const uint64_t CH = 512;
         F.nDeltaChunks = (F.nFast + CH - 1) / CH;
         F.dw.resize(F.nDeltaChunks * CH, static_cast<uint32_t>(2 * F.S));   // padding gathers the always-zero slot, never ends a segment
+        {   // lane-interleaved storage: logical word 16 l + 4 q + r of a chunk -> stored word 4 (32 q + l) + r
+            std::vector<uint32_t> st(F.dw.size());
+            for (uint64_t c = 0; c < F.nDeltaChunks; ++c)
+                for (uint32_t l = 0; l < 32; ++l)
+                    for (uint32_t q = 0; q < 4; ++q)
+                        for (uint32_t r = 0; r < 4; ++r) st[c * CH + 4 * (32 * q + l) + r] = F.dw[c * CH + 16 * l + 4 * q + r];
+            F.dw.swap(st);
+        }
         F.endMask.assign(F.nDeltaChunks * 32, 0);
         for (uint64_t e : segEnd) F.endMask[e >> 4] |= 1u << (e & 15);
         F.chunkSeg.assign(F.nDeltaChunks + 1, 0);

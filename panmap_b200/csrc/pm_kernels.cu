@@ -11,6 +11,7 @@
 //
 // This is integer/byte streaming work bounded by HBM and issue rate; no tensor cores are involved.
 #include "pm_kernels.cuh"
+#include <algorithm>
 
 namespace pm {
 
@@ -504,62 +505,78 @@ void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* c
     table_export<<<streamGrid(W.tableCap, 2), 256, 0, st>>>(W.table, W.tableCap, W.acc, hash, count, counter, cap);
 }
 
+// Same-address global atomics are serviced one at a time by the L2 (a few ns each), so the passes below never let more than one
+// thread per block touch a shared counter: blocks compact / reduce in shared memory and publish per-block partials.
+//
 // pass 1 (the only pass over the whole table): erase the four homopolymer k-mer hashes (placement.cpp:1708-1718), gather the
 // statistics of the auto min-read-support rule (placement.cpp:931-955) and the pre-filter totals, and compact the occupied
-// slots into a dense (key, count) list -- one warp-aggregated atomic per 128 slots -- so that everything that follows works
-// on U entries instead of the table's capacity.  Four independent 16-byte loads in flight per thread.
+// slots into a dense (key, count) list so that everything that follows works on U entries instead of the table's capacity.
+// A block handles 2048 slots at a time: eight independent 16-byte loads per thread, compaction in shared memory, one global
+// atomic for the block's share of the list, coalesced copy-out.
+constexpr int kScanSlots = 2048;
 __global__ void __launch_bounds__(256) table_scan(WorkspaceView W, const u64* __restrict__ homo) {
+    __shared__ u64 sKey[kScanSlots];
+    __shared__ u32 sCnt[kScanSlots];
+    __shared__ unsigned sN, sBase;
+    __shared__ long long sRed[8][4];
     const u64 h0 = homo[0], h1 = homo[1], h2 = homo[2], h3 = homo[3];
     TableSlot* table = W.table; const u64 cap = W.tableCap; SampleAcc* acc = W.acc;
     long long ms = 0, mc = 0, en = 0, total = 0;
-    const unsigned lane = threadIdx.x & 31u;
-    const u64 warpsTotal = (u64)gridDim.x * 8;
-    for (u64 base = ((u64)blockIdx.x * 8 + (threadIdx.x >> 5)) * 128; base < cap; base += warpsTotal * 128) {
-        uint4 v[4];
+    const unsigned tid = threadIdx.x, lane = tid & 31u;
+    if (tid == 0) sN = 0;
+    __syncthreads();
+    const u64 nBlocks = (cap + kScanSlots - 1) / kScanSlots;
+    for (u64 blk = blockIdx.x; blk < nBlocks; blk += gridDim.x) {
+        const u64 base = blk * kScanSlots;
+        uint4 v[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const u64 i = base + q * 32 + lane; v[q] = i < cap ? ldSlot(table, i) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); }
-        bool occ[4]; unsigned m[4], n = 0;
+        for (int q = 0; q < 8; ++q) { const u64 i = base + q * 256 + tid; v[q] = i < cap ? ldSlot(table, i) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0); }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 8; ++q) {
             const u64 k = slotKey(v[q]);
-            occ[q] = k != kEmptyKey && v[q].z > 0;
-            if (occ[q] && (k == h0 || k == h1 || k == h2 || k == h3)) { table[base + q * 32 + lane].count = 0; occ[q] = false; }
-            if (occ[q]) { const long long c = v[q].z; ++en; total += c; if (c >= 2) { ms += c; ++mc; } }
-            m[q] = __ballot_sync(0xffffffffu, occ[q]);
-            n += __popc(m[q]);
-        }
-        if (n) {
-            unsigned o = 0;
-            if (lane == 0) o = atomicAdd(&acc->entCount, n);
-            o = __shfl_sync(0xffffffffu, o, 0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (occ[q]) { const unsigned d = o + __popc(m[q] & ((1u << lane) - 1u)); W.entKey[d] = slotKey(v[q]); W.entCnt[d] = v[q].z; }
-                o += __popc(m[q]);
+            bool occ = k != kEmptyKey && v[q].z > 0;
+            if (occ && (k == h0 || k == h1 || k == h2 || k == h3)) { table[base + q * 256 + tid].count = 0; occ = false; }
+            if (occ) { const long long c = v[q].z; ++en; total += c; if (c >= 2) { ms += c; ++mc; } }
+            const unsigned m = __ballot_sync(0xffffffffu, occ);
+            if (m) {
+                unsigned o = 0;
+                if (lane == 0) o = atomicAdd(&sN, (unsigned)__popc(m));
+                o = __shfl_sync(0xffffffffu, o, 0) + __popc(m & ((1u << lane) - 1u));
+                if (occ) { sKey[o] = k; sCnt[o] = v[q].z; }
             }
         }
+        __syncthreads();
+        const unsigned n = sN;
+        if (tid == 0 && n) sBase = atomicAdd(&acc->entCount, n);
+        __syncthreads();
+        const unsigned ob = sBase;
+        if (tid == 0) sN = 0;   // every thread has read n; the barrier below orders the reset before the next block's atomics
+        for (unsigned i = tid; i < n; i += 256) { W.entKey[ob + i] = sKey[i]; W.entCnt[ob + i] = sCnt[i]; }
+        __syncthreads();
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {   // the one key that cannot live in the table
+    if (blockIdx.x == 0 && tid == 0 && acc->emptyKeyCount > 0) {   // the one key that cannot live in the table
         const long long c = acc->emptyKeyCount; ++en; total += c; if (c >= 2) { ms += c; ++mc; }
     }
     ms = warpSumLL(ms); mc = warpSumLL(mc); en = warpSumLL(en); total = warpSumLL(total);
-    if (lane == 0) {
-        if (ms) atomicAdd((unsigned long long*)&acc->multiSum, (unsigned long long)ms);
-        if (mc) atomicAdd((unsigned long long*)&acc->multiCount, (unsigned long long)mc);
-        if (en) { atomicAdd((unsigned long long*)&acc->entries, (unsigned long long)en); atomicAdd((unsigned long long*)&acc->unique, (unsigned long long)en); }
-        if (total) atomicAdd((unsigned long long*)&acc->total, (unsigned long long)total);
+    if (lane == 0) { sRed[tid >> 5][0] = ms; sRed[tid >> 5][1] = mc; sRed[tid >> 5][2] = en; sRed[tid >> 5][3] = total; }
+    __syncthreads();
+    if (tid < 4) {
+        long long t = 0;
+        for (int q = 0; q < 8; ++q) t += sRed[q][tid];
+        reinterpret_cast<long long*>(&W.scanPart[blockIdx.x])[tid] = t;
     }
 }
 
-__device__ __forceinline__ long long resolveMinSupport(const SampleAcc* acc, int configured) {
+__device__ __forceinline__ long long resolveMinSupport(long long multiSum, long long multiCount, int configured) {
     if (configured >= 0) return configured;
-    const double est = acc->multiCount > 0 ? (double)(u64)acc->multiSum / (double)(u64)acc->multiCount : 0.0;
+    const double est = multiCount > 0 ? (double)(u64)multiSum / (double)(u64)multiCount : 0.0;
     return est > 3.0 ? 2 : 1;
 }
 
 // pass 2: computeReadSeedMagnitudes (placement.cpp:957-984) + scatter of log1p(count) to the seed-id array, one thread per
 // compacted entry: log1p table, exact sums, count histogram, dictionary probe, scatter -- all independent, so the random
-// accesses of many entries are in flight at once.
+// accesses of many entries are in flight at once.  The seed id found for an entry (or kNone) is written back next to it so
+// that reset_sample can clear exactly the touched ell entries without a separate list.
 constexpr int kHistSmem = 2048;
 struct FinalizeAcc { fx128 mag, lsum; long long kept; u32 maxc; };
 __device__ __forceinline__ u32 finalizeKept(const DevIndexView& I, const WorkspaceView& W, u64 k, u32 c, FinalizeAcc& A, unsigned* sHist) {
@@ -573,56 +590,43 @@ __device__ __forceinline__ u32 finalizeKept(const DevIndexView& I, const Workspa
     while (true) {  // is this seed anywhere in the index?
         const uint4 d = __ldg(reinterpret_cast<const uint4*>(I.dict) + s);
         const u64 dk = (u64)d.x | ((u64)d.y << 32);
-        if (dk == k) {   // l >= ln 2 is an exact multiple of 2^-53; the entry holds +l for a gained seed and -l for a lost one
-            const long long e = __double2ll_rn(l * kEllScale);
-            *reinterpret_cast<longlong2*>(W.ell + 2 * (size_t)d.z) = make_longlong2(e, -e);
-            return d.z;
-        }
+        if (dk == k) { W.ell[d.z] = __double2ll_rn(l * kEllScale); return d.z; }   // l >= ln 2: an exact multiple of 2^-53
         if (dk == kEmptyKey) return kNone;
         s = (s + 1) & I.dictMask;
     }
 }
-// one atomic per warp for the list of touched seed ids (reset_sample clears exactly these after the sample)
-__device__ __forceinline__ void appendTouched(const WorkspaceView& W, u32 id, unsigned activeMask) {
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned m = __ballot_sync(activeMask, id != kNone);
-    if (!m) return;
-    unsigned base = 0;
-    const int leader = __ffs(m) - 1;
-    if ((int)lane == leader) base = atomicAdd(&W.acc->touchedCount, (unsigned)__popc(m));
-    base = __shfl_sync(activeMask, base, leader);
-    if (id != kNone) {
-        const unsigned t = base + __popc(m & ((1u << lane) - 1u));
-        if (t < W.touchedCap) W.touched[t] = id; else W.acc->overflow = 1;
-    }
-}
-__global__ void __launch_bounds__(256) entries_finalize(DevIndexView I, WorkspaceView W, int configuredMinSupport) {
+__global__ void __launch_bounds__(256) entries_finalize(DevIndexView I, WorkspaceView W, int configuredMinSupport, unsigned nScanParts) {
     __shared__ unsigned sHist[kHistSmem];
     __shared__ u64 sRed[8][4];
     __shared__ long long sKept[8];
     __shared__ unsigned sMax[8];
-    for (int i = threadIdx.x; i < kHistSmem; i += blockDim.x) sHist[i] = 0;
+    __shared__ long long sStat[4];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (int i = tid; i < kHistSmem; i += blockDim.x) sHist[i] = 0;
+    if (warp < 4) {   // totals of pass 1: warp q sums field q of the per-block partials
+        long long t = 0;
+        for (unsigned b = lane; b < nScanParts; b += 32) t += reinterpret_cast<const long long*>(&W.scanPart[b])[warp];
+        t = warpSumLL(t);
+        if (lane == 0) sStat[warp] = t;
+    }
     __syncthreads();
     SampleAcc* acc = W.acc;
-    const u32 minSup = (u32)resolveMinSupport(acc, configuredMinSupport);
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && tid == 0) { acc->multiSum = sStat[0]; acc->multiCount = sStat[1]; acc->entries = sStat[2]; acc->unique = sStat[2]; acc->total = sStat[3]; }
+    const u32 minSup = (u32)resolveMinSupport(sStat[0], sStat[1], configuredMinSupport);
     FinalizeAcc A; A.mag = fxZero(); A.lsum = fxZero(); A.kept = 0; A.maxc = 0;
     const unsigned n = acc->entCount;
-    const unsigned nRound = (n + 31u) & ~31u;   // whole warps stay in the loop for the ballot
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nRound; i += gridDim.x * blockDim.x) {
+    for (unsigned i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) {
+        const u32 c = __ldcs(&W.entCnt[i]);
         u32 id = kNone;
-        if (i < n) {
-            const u32 c = __ldcs(&W.entCnt[i]);
-            if (c >= minSup) id = finalizeKept(I, W, __ldcs(&W.entKey[i]), c, A, sHist);
-        }
-        appendTouched(W, id, 0xffffffffu);
+        if (c >= minSup) id = finalizeKept(I, W, __ldcs(&W.entKey[i]), c, A, sHist);
+        W.entId[i] = id;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && acc->emptyKeyCount > 0) {
+    if (blockIdx.x == 0 && tid == 0 && acc->emptyKeyCount > 0) {
         const u32 c = (u32)acc->emptyKeyCount;
         if (c >= minSup) finalizeKept(I, W, kEmptyKey, c, A, sHist);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kHistSmem; i += blockDim.x) if (sHist[i]) atomicAdd(&W.countHist[i], sHist[i]);
+    for (int i = tid; i < kHistSmem; i += blockDim.x) if (sHist[i]) atomicAdd(&W.countHist[i], sHist[i]);
     const fx128 mag = fxWarpSum(A.mag), lsum = fxWarpSum(A.lsum);
     const long long kept = warpSumLL(A.kept);
     unsigned mx = A.maxc;
@@ -630,15 +634,15 @@ __global__ void __launch_bounds__(256) entries_finalize(DevIndexView I, Workspac
     for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     if (lane == 0) { sRed[warp][0] = mag.lo; sRed[warp][1] = (u64)mag.hi; sRed[warp][2] = lsum.lo; sRed[warp][3] = (u64)lsum.hi; sKept[warp] = kept; sMax[warp] = mx; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         fx128 m = fxZero(), l = fxZero(); long long kp = 0; unsigned mm = 0;
         for (int q = 0; q < 8; ++q) {
             fx128 t; t.lo = sRed[q][0]; t.hi = (i64)sRed[q][1]; m = fxAdd(m, t);
             t.lo = sRed[q][2]; t.hi = (i64)sRed[q][3]; l = fxAdd(l, t);
             kp += sKept[q]; mm = max(mm, sMax[q]);
         }
-        if (mm) atomicMax((unsigned long long*)&acc->maxKeptCount, (unsigned long long)mm);
-        if (kp) { fxAtomicAdd(acc->magSq, m); fxAtomicAdd(acc->logSum, l); atomicAdd((unsigned long long*)&acc->kept, (unsigned long long)kp); }
+        FinPartial P; P.mag[0] = m.lo; P.mag[1] = (u64)m.hi; P.lsum[0] = l.lo; P.lsum[1] = (u64)l.hi; P.kept = kp; P.maxc = mm;
+        W.finPart[blockIdx.x] = P;
     }
 }
 
@@ -647,7 +651,7 @@ __global__ void __launch_bounds__(256) root_denominator(DevIndexView I, Workspac
     fx128 s = fxZero();
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < I.rootDCount; i += (u64)gridDim.x * blockDim.x) {
         const int c = (int)__ldg(&I.rootChild[i]);
-        if (c > 0 && W.ell[2 * (size_t)__ldg(&I.rootId[i])] != 0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
+        if (c > 0 && W.ell[__ldg(&I.rootId[i])] != 0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
     }
     s = fxWarpSum(s);
     if ((threadIdx.x & 31) == 0) fxAtomicAdd(W.acc->wcDen, s);
@@ -685,9 +689,36 @@ __device__ __forceinline__ double blockSumF64(double e, double* sRed) {
     return tot;
 }
 
-__global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, WorkspaceView W, int configuredMinSupport) {
+__global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, WorkspaceView W, int configuredMinSupport, unsigned nFinParts) {
     __shared__ double sRed[32];
-    const SampleAcc* a = W.acc;
+    __shared__ u64 sFx[32][4];
+    __shared__ long long sK[32];
+    __shared__ long long sM[32];
+    SampleAcc* a = W.acc;
+    {   // totals of pass 2 from the per-block partials (exact, order independent)
+        fx128 pm = fxZero(), pl = fxZero(); long long pk = 0, px = 0;
+        for (unsigned b = threadIdx.x; b < nFinParts; b += blockDim.x) {
+            const FinPartial P = W.finPart[b];
+            fx128 t; t.lo = P.mag[0]; t.hi = (i64)P.mag[1]; pm = fxAdd(pm, t);
+            t.lo = P.lsum[0]; t.hi = (i64)P.lsum[1]; pl = fxAdd(pl, t);
+            pk += P.kept; px = max(px, P.maxc);
+        }
+        pm = fxWarpSum(pm); pl = fxWarpSum(pl); pk = warpSumLL(pk);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) px = max(px, (long long)shflXorU64((u64)px, d));
+        if ((threadIdx.x & 31) == 0) { const int w = threadIdx.x >> 5; sFx[w][0] = pm.lo; sFx[w][1] = (u64)pm.hi; sFx[w][2] = pl.lo; sFx[w][3] = (u64)pl.hi; sK[w] = pk; sM[w] = px; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            fx128 m = fxZero(), l = fxZero(); long long k = 0, x = 0;
+            for (int w = 0; w < 32; ++w) {
+                fx128 t; t.lo = sFx[w][0]; t.hi = (i64)sFx[w][1]; m = fxAdd(m, t);
+                t.lo = sFx[w][2]; t.hi = (i64)sFx[w][3]; l = fxAdd(l, t);
+                k += sK[w]; x = max(x, sM[w]);
+            }
+            a->magSq[0] = m.lo; a->magSq[1] = (u64)m.hi; a->logSum[0] = l.lo; a->logSum[1] = (u64)l.hi; a->kept = k; a->maxKeptCount = x;
+        }
+        __syncthreads();
+    }
     fx128 m; m.lo = a->magSq[0]; m.hi = (i64)a->magSq[1];
     fx128 l; l.lo = a->logSum[0]; l.hi = (i64)a->logSum[1];
     fx128 w; w.lo = a->wcDen[0]; w.hi = (i64)a->wcDen[1];
@@ -718,7 +749,7 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
     S.logContDenom = logSumExact + dLog;
     S.wcDenom = fxToDouble(w);
     S.uniqueKept = (double)a->kept;
-    S.minSupport = resolveMinSupport(a, configuredMinSupport);
+    S.minSupport = resolveMinSupport(a->multiSum, a->multiCount, configuredMinSupport);
     S.uniqueSeeds = a->unique;
     S.uniqueKeptInt = a->kept;
     S.totalFrequency = a->total;
@@ -728,34 +759,42 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
     *W.scalars = S;
 }
 
-void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, cudaStream_t st) {
+void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st) {
     cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
-    table_scan<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W, homo);
+    const u64 nBlocks = (W.tableCap + kScanSlots - 1) / kScanSlots;
+    const unsigned g1 = (unsigned)std::min<u64>(std::min<u64>(nBlocks ? nBlocks : 1, (u64)nSM * 4), kMaxPartials);
+    table_scan<<<g1, 256, 0, st>>>(W, homo);
     // sized from the previous sample's entry count (the kernel grid-strides, so any grid is correct)
-    u64 g = (expectedEntries + 255) / 256; if (g < 148) g = 148; if (g > 148 * 32) g = 148 * 32;
-    entries_finalize<<<(unsigned)g, 256, 0, st>>>(I, W, O.minReadSupport);
+    u64 g2 = (expectedEntries + 255) / 256; if (g2 < 1) g2 = 1; if (g2 > (u64)nSM * 8) g2 = (u64)nSM * 8; if (g2 > kMaxPartials) g2 = kMaxPartials;
+    entries_finalize<<<(unsigned)g2, 256, 0, st>>>(I, W, O.minReadSupport, g1);
     if (I.hasRoot && I.rootDCount) {
         u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
         root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);
     }
-    finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport);
+    finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport, (unsigned)g2);
 }
 
-// after a sample: clear exactly the ell entries it touched and the segment records that are combined with atomics
+// after a sample: clear exactly the ell entries it set (their ids sit next to the compacted entries) and the segment records
+// that are combined with atomics
 __global__ void __launch_bounds__(256) reset_sample(DevIndexView I, WorkspaceView W) {
-    const unsigned n = W.acc->touchedCount < W.touchedCap ? W.acc->touchedCount : W.touchedCap;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) *reinterpret_cast<longlong2*>(W.ell + 2 * (size_t)W.touched[i]) = make_longlong2(0, 0);
+    const unsigned n = W.acc->entCount;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 id = __ldcs(&W.entId[i]);
+        if (id != kNone) W.ell[id] = 0;
+    }
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nBoundary; i += gridDim.x * blockDim.x)
         *reinterpret_cast<uint4*>(W.segRec + I.boundarySegs[i]) = make_uint4(0u, 0u, 0u, 0u);
 }
-void launchResetSample(DevIndexView I, WorkspaceView W, cudaStream_t st) { reset_sample<<<148, 256, 0, st>>>(I, W); }
+void launchResetSample(DevIndexView I, WorkspaceView W, cudaStream_t st) { reset_sample<<<148 * 4, 256, 0, st>>>(I, W); }
 
 // ------------------------------------------------------------------------------------------------------
 // K1 node_deltas: one pass over the packed delta words (4 B per delta), no block barriers.
 // A warp owns a chunk of 512 consecutive words; lane l owns words [16 l, 16 l + 16): four 16-byte loads, then 16
-// independent gathers of ell[word] (word = 2 * seed id + lost; the entry is +-log1p(read count) as an exact integer, 0 when the
-// seed is not in the reads -- the sign of a lost seed is already in the table).  Node boundaries come as one 16-bit mask per
-// lane (bit j = word j is the last delta of its node), so no offset array is read and no search is needed:
+// independent gathers of ell[seed id] (word = 2 * seed id + lost; the entry is log1p(read count) as an exact integer, 0 when the
+// seed is not in the reads).  The kernel is bound by L1 wavefronts (one per distinct line a gather touches), so (i) the chunk is
+// stored lane-interleaved and read with fully coalesced 16-byte loads, and (ii) the low seed ids -- the root's and other
+// ancestral seeds, which almost half of all deltas refer to -- are served from a shared-memory copy of ell[0 .. kHotIds).
+// Node boundaries come as one 16-bit mask per lane (bit j = word j is the last delta of its node): no offset array, no search.
 //   * a node that begins and ends inside a lane is stored directly (sums of <= 16 terms fit 64 bits);
 //   * a node spread over several lanes is combined with a segmented warp scan (96-bit) and stored by the lane where it ends;
 //   * a node spread over several chunks (listed at flatten time, zeroed by reset_sample) is combined with integer atomics.
@@ -774,14 +813,21 @@ __device__ __forceinline__ void segStore(SegRec* r, u64 lo, int hi, int cnt) {
     *reinterpret_cast<uint4*>(r) = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)cnt);
 }
 
-constexpr int kK1Threads = 128;
-__global__ void __launch_bounds__(kK1Threads, 6) node_deltas(DevIndexView I, WorkspaceView W, u32 chunksPerWarp) {
-    // lane-local running sums after every word, [word][thread]: read back only at the (few) segment ends of the lane
-    __shared__ long long sP[16][kK1Threads];
-    __shared__ int sC[16][kK1Threads];
+constexpr int kK1Threads = 256;
+constexpr int kHotIds = 8192;   // seed ids below this (the root's seeds and other early, ancestral ones) are gathered from shared memory
+__global__ void __launch_bounds__(kK1Threads, 3) node_deltas(DevIndexView I, WorkspaceView W, u32 chunksPerWarp) {
+    extern __shared__ __align__(16) long long sHot[];   // [kHotIds] copy of ell[0 .. kHotIds)
     const long long* __restrict__ ell = W.ell;
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
+    {
+        const u32 nHot = (u32)min((u64)kHotIds, I.nSeeds + 1);
+        const longlong2* src = reinterpret_cast<const longlong2*>(ell);
+        longlong2* dst = reinterpret_cast<longlong2*>(sHot);
+        for (u32 i = tid; i < nHot / 2; i += kK1Threads) dst[i] = __ldg(src + i);
+        if (tid == 0 && (nHot & 1u)) sHot[nHot - 1] = ell[nHot - 1];
+    }
+    __syncthreads();
     // a warp owns a run of consecutive chunks: the open run at the end of a chunk is carried in registers into the next one,
     // so atomics are only needed for a segment that crosses the first or the last chunk boundary of the run
     const u64 c0 = ((u64)blockIdx.x * (kK1Threads >> 5) + (tid >> 5)) * chunksPerWarp;
@@ -794,17 +840,20 @@ __global__ void __launch_bounds__(kK1Threads, 6) node_deltas(DevIndexView I, Wor
     for (u64 c = c0; c < c1; ++c) {
         const unsigned F = __ldg(&I.endMask[c * 32 + lane]);   // bit j: word j of this lane is the last delta of its node
         u32 w[16];
-        {
-            const uint4* p = reinterpret_cast<const uint4*>(I.dw + c * kChunkWords + lane * 16);
+        {   // the chunk is stored lane-interleaved: 16-byte piece q of lane l sits at uint4 index 32 q + l (coalesced)
+            const uint4* p = reinterpret_cast<const uint4*>(I.dw + c * kChunkWords) + lane;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint4 a = __ldg(p + q);
+                const uint4 a = __ldg(p + 32 * q);
                 w[4 * q] = a.x; w[4 * q + 1] = a.y; w[4 * q + 2] = a.z; w[4 * q + 3] = a.w;
             }
         }
-        long long v[16];   // w = 2 * seed id + lost: ell[w] is +log1p(read count) for a gained seed, -log1p for a lost one, 0 if absent
+        long long e[16];   // w = 2 * seed id + lost
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __ldg(&ell[w[j]]);
+        for (int j = 0; j < 16; ++j) {
+            const u32 id = w[j] >> 1;
+            e[j] = id < (u32)kHotIds ? sHot[id] : __ldg(&ell[id]);
+        }
         // segment index of this lane's first segment end: segments ending in earlier chunks + in earlier lanes
         const unsigned nEnd = __popc(F);
         unsigned endsBefore = nEnd;
@@ -814,28 +863,19 @@ __global__ void __launch_bounds__(kK1Threads, 6) node_deltas(DevIndexView I, Wor
         endsBefore -= nEnd;
         const u32 segFirst = segBase + endsBefore;
         const unsigned endMask = __ballot_sync(0xffffffffu, nEnd != 0);
-        // ---- running sums of the 16 words (sums of <= 16 terms fit 64 bits) ----
-        long long acc = 0; int cn = 0;
+        // ---- walk the 16 words: interior segments are stored, the first end is kept for after the scan ----
+        long long acc = 0, headV = 0; int cn = 0, headC = 0; unsigned k = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            acc += v[j];
-            cn += (v[j] > 0) - (v[j] < 0);
-            sP[j][tid] = acc; sC[j][tid] = cn;
-        }
-        // trailing partial of the lane: everything after its last segment end (the whole lane when it has none)
-        long long headV = 0; int headC = 0;
-        if (F) {
-            const int first = __ffs(F) - 1, last = 31 - __clz(F);
-            headV = sP[first][tid]; headC = sC[first][tid];
-            long long pv = headV; int pcn = headC; unsigned k = 1;
-            for (unsigned Fm = F & (F - 1); Fm; Fm &= Fm - 1, ++k) {   // segments that begin and end inside the lane
-                const int j = __ffs(Fm) - 1;
-                const long long pj = sP[j][tid]; const int cj = sC[j][tid];
-                const long long sv = pj - pv;
-                segStore(W.segRec + segFirst + k, (u64)sv, (int)(sv >> 63), cj - pcn);
-                pv = pj; pcn = cj;
+            const int m = -(int)(w[j] & 1u);                      // -1 when the seed is lost, 0 when gained
+            const long long mm = (long long)m;
+            acc += (e[j] ^ mm) - mm;
+            cn += (int)(e[j] >> 32) ? (m | 1) : 0;                // present <=> e >= ln2 * 2^53, i.e. the high word is non-zero
+            if (F & (1u << j)) {
+                if (k == 0) { headV = acc; headC = cn; }
+                else segStore(W.segRec + segFirst + k, (u64)acc, (int)(acc >> 63), cn);
+                ++k; acc = 0; cn = 0;
             }
-            acc -= sP[last][tid]; cn -= sC[last][tid];
         }
         // ---- segmented inclusive scan over the lanes' trailing partials (a lane with a segment end restarts the run) ----
         u64 lo = (u64)acc; int hi = (int)(acc >> 63); int rc = cn;
@@ -873,11 +913,14 @@ __global__ void __launch_bounds__(kK1Threads, 6) node_deltas(DevIndexView I, Wor
 }
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st) {
     if (I.nDeltaChunks == 0) return;
-    const u64 warps = (u64)nSM * 6 * (kK1Threads / 32);   // 6 blocks per SM
-    const u32 per = (u32)((I.nDeltaChunks + warps - 1) / warps);
     const u64 wpb = kK1Threads / 32;
+    const u64 warps = (u64)nSM * 3 * wpb;   // 3 blocks per SM (shared-memory bound)
+    const u32 per = (u32)((I.nDeltaChunks + warps - 1) / warps);
     const u64 grid = ((I.nDeltaChunks + per - 1) / per + wpb - 1) / wpb;
-    node_deltas<<<(unsigned)grid, kK1Threads, 0, st>>>(I, W, per);
+    const size_t sm = (size_t)kHotIds * sizeof(long long);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(node_deltas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr = true; }
+    node_deltas<<<(unsigned)grid, kK1Threads, sm, st>>>(I, W, per);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -917,7 +960,7 @@ __device__ __forceinline__ Acc5 accLoad(const u64* p) {
 }
 __global__ void __launch_bounds__(256) gen_deltas(DevIndexView I, WorkspaceView W) {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nGenDeltas; i += gridDim.x * blockDim.x) {
-        const long long e = __ldg(&W.ell[2 * (size_t)I.genId[i]]);
+        const long long e = __ldg(&W.ell[I.genId[i]]);
         if (!e) continue;
         const u32 pcv = I.genPc[i];
         const int p = (int)(short)(pcv & 0xFFFFu), c = (int)(short)(pcv >> 16);

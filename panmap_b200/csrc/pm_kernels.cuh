@@ -26,10 +26,13 @@ struct __align__(16) DictSlot { u64 key; u32 id; u32 pad; };       // index dict
 struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample)
     u64 magSq[2], logSum[2], wcDen[2];  // fx128 as (lo, hi)
     long long kept, total, unique, multiSum, multiCount, entries, maxKeptCount, overflow, emptyKeyCount;
-    unsigned touchedCount, entCount;
+    unsigned pad0, entCount;
     unsigned recordCount[8];
     unsigned tieCount[8];
 };
+struct ScanPartial { long long multiSum, multiCount, entries, total; };          // one per table_scan block
+struct FinPartial { u64 mag[2], lsum[2]; long long kept; long long maxc; };        // one per entries_finalize block
+constexpr unsigned kMaxPartials = 2048;
 struct Selection {  // outcome of the tolerance chain for one metric
     double best;
     u32 bestNode;
@@ -44,7 +47,8 @@ struct DevIndexView {
     u32 nAnc;
     u64 nLocalDeltas;
     u64 nSeeds;        // distinct seed hashes of the whole index
-    const u32* dw;         // [nDeltaChunks*512] packed fast deltas: 2 * seed id + lost
+    const u32* dw;         // [nDeltaChunks*512] packed fast deltas: 2 * seed id + lost; inside a chunk the 16-byte piece q of lane l
+                           // (logical words 16 l + 4 q ..) is stored at uint4 index 32 q + l
     const u32* endMask;    // [nDeltaChunks*32] per lane (16 words): bit j = word j is the last fast delta of its node
     u64 nDeltaChunks;
     const u32* chunkSeg;   // [nDeltaChunks+1] segments ending before the chunk | bit 31: the chunk starts inside a segment
@@ -82,9 +86,9 @@ struct WorkspaceView {
     TableSlot* table; u64 tableMask; u64 tableCap;
     SampleAcc* acc;
     u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
-    long long* ell;       // [2*(nSeeds+1)] {+l, -l} with l = log1p(read count) * 2^53 of the seed (an exact integer), 0 when absent; slot nSeeds stays 0
-    u32* touched; u32 touchedCap;
-    u64* entKey; u32* entCnt;   // [tableCap] occupied (key, count) pairs compacted by table_scan
+    long long* ell;       // [nSeeds+2] log1p(read count) * 2^53 of the seed id (an exact integer), 0 when absent; slot nSeeds stays 0
+    u64* entKey; u32* entCnt; u32* entId;   // [tableCap] occupied (key, count) pairs compacted by table_scan + the seed id found for them
+    ScanPartial* scanPart; FinPartial* finPart;   // [kMaxPartials] per-block partials of the two finalize passes
     unsigned* countHist;  // [kLog1pLut] multiplicity of every read count among the kept seeds (rounding-drift model)
     SegRec* segRec;       // [nSeg]
     SegRec* chainA;       // [chainTotal] prefix along each K2 tile's ancestor chain
@@ -118,7 +122,7 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
 void launchTableClear(WorkspaceView W, cudaStream_t st);
 void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st);
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st);
-void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, cudaStream_t st);
+void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st);
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st);
 void launchGeneral(DevIndexView I, WorkspaceView W, cudaStream_t st);
 void launchPrefixScores(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st);

@@ -65,7 +65,7 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
         FlatIndex F; flattenIndex(*d, shard, nShards, F);
         *nodeBegin = F.nodeBegin; *nodeEnd = F.nodeEnd;
         // ell by seed id through the dictionary table (as table_finalize does): log1p(count) * 2^53, an exact integer
-        std::vector<long long> ell(2 * (F.S + 1), 0);   // {+l, -l} per seed id
+        std::vector<long long> ell(F.S + 2, 0);
         for (int64_t i = 0; i < U; ++i) {
             if (!(tLog[i] > 0.0)) continue;
             u64 s = mixKey(tHash[i]) & F.dictMask;
@@ -74,7 +74,7 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
                     if (F.dictVals[s] != 0xFFFFFFFFu) {
                         const double sc = tLog[i] * 9007199254740992.0;
                         if (sc != std::floor(sc) || sc >= 9.2e18) throw std::runtime_error("log1p(count) is not a multiple of 2^-53");
-                        ell[2 * (size_t)F.dictVals[s]] = (long long)sc; ell[2 * (size_t)F.dictVals[s] + 1] = -(long long)sc;
+                        ell[F.dictVals[s]] = (long long)sc;
                     }
                     break;
                 }
@@ -86,7 +86,7 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
         fx128 wc = fxZero();
         for (size_t i = 0; i < F.rootId.size(); ++i) {
             const int c = (int)F.rootChild[i];
-            if (c > 0 && ell[2 * (size_t)F.rootId[i]] != 0) wc = fxAdd(wc, fxFromDouble(1.0 / (double)c));
+            if (c > 0 && ell[F.rootId[i]] != 0) wc = fxAdd(wc, fxFromDouble(1.0 / (double)c));
         }
         const double denW = fxToDouble(wc);
         *wcDenOut = denW;
@@ -121,7 +121,8 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
             if (segBase != (F.chunkSeg[c] & 0x7FFFFFFFu)) throw std::runtime_error("running segment base disagrees with chunkSeg");
             unsigned nEnd[32], endsBefore[32]; Seg tail[32], head[32]; unsigned endMask = 0, total = 0;
             for (int lane = 0; lane < 32; ++lane) {
-                const uint32_t* w = &F.dw[c * 512 + (u64)lane * 16];
+                uint32_t w[16];   // lane-interleaved storage: 16-byte piece q of lane l at uint4 index 32 q + l
+                for (int q = 0; q < 4; ++q) for (int r = 0; r < 4; ++r) w[4 * q + r] = F.dw[c * 512 + 4 * (32 * q + lane) + r];
                 const unsigned Fm = F.endMask[c * 32 + lane];
                 if (Fm >> 16) throw std::runtime_error("end mask has bits above 15");
                 nEnd[lane] = (unsigned)__builtin_popcount(Fm);
@@ -130,7 +131,8 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
                 const uint32_t segFirst = segBase + endsBefore[lane];
                 long long P[16]; int Cn[16]; long long acc = 0; int cn = 0;
                 for (int j = 0; j < 16; ++j) {   // running sums, staged in shared memory by the kernel
-                    const long long v = ell[w[j]];
+                    const long long e = ell[w[j] >> 1], mm = -(long long)(w[j] & 1u);
+                    const long long v = (e ^ mm) - mm;
                     acc += v; cn += (v > 0) - (v < 0);
                     P[j] = acc; Cn[j] = cn;
                 }
@@ -180,7 +182,7 @@ int hc_emulate_scoring(const pm_index_desc* d, uint32_t shard, uint32_t nShards,
         const double ln2 = std::log1p(1.0);
         std::vector<Acc5> genRec(F.nGenNodes, accZ()), evPrefix(F.evSlot.size(), accZ());
         for (size_t i = 0; i < F.genSlot.size(); ++i) {
-            const long long e = ell[2 * (size_t)F.genId[i]];
+            const long long e = ell[F.genId[i]];
             if (!e) continue;
             const int p = (int)(short)(F.genPc[i] & 0xFFFF), cc = (int)(short)(F.genPc[i] >> 16);
             const DeltaTerms t = deltaTerms((double)e / 9007199254740992.0, p, cc, p > 0 ? l1p[p] : 0.0, cc > 0 ? l1p[cc] : 0.0);
