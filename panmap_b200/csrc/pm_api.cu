@@ -93,8 +93,8 @@ struct pm_index {
 
 struct pm_workspace {
     pm_index* idx = nullptr;
-    cudaStream_t st = nullptr, stCopy = nullptr;
-    cudaEvent_t ev[9]{}, evCopy[8]{};
+    cudaStream_t st = nullptr, stCopy = nullptr, stIns = nullptr;   // compute, H2D copies, table insertion (overlaps the syncmer kernel)
+    cudaEvent_t ev[9]{}, evCopy[8]{}, evSyn[8]{}, evIns{};
     // inputs
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
@@ -302,9 +302,14 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
         CK(cudaEventRecord(W->evCopy[sl], W->stCopy));
         CK(cudaStreamWaitEvent(W->st, W->evCopy[sl], 0));
         launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st);
-        launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st);
+        launchSyncmersOnly(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st);
+        CK(cudaEventRecord(W->evSyn[sl], W->st));
+        CK(cudaStreamWaitEvent(W->stIns, W->evSyn[sl], 0));   // (the first wait also orders the insertions after acc memset + table_clear)
+        launchSeedsOnly(W->packedOff.p + r0, r1 - r0, P, W->view, W->stIns);
         bfBase += nBlk + 1;
     }
+    CK(cudaEventRecord(W->evIns, W->stIns));
+    CK(cudaStreamWaitEvent(W->st, W->evIns, 0));
     W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false;
 }
 
@@ -316,7 +321,19 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         launchTableClear(W->view, W->st);
     }
     launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st);
-    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st);
+    // slices of reads: the syncmer kernel of slice i+1 (integer-issue bound) overlaps the table insertion of slice i (LSU bound)
+    const u64 n = W->nReads;
+    const int nSlices = n >= (1u << 16) ? 8 : 1;
+    for (int sl = 0; sl < nSlices; ++sl) {
+        const u64 r0 = n * sl / nSlices, r1 = n * (sl + 1) / nSlices;
+        if (r1 == r0) continue;
+        launchSyncmersOnly(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st);
+        CK(cudaEventRecord(W->evSyn[sl], W->st));
+        CK(cudaStreamWaitEvent(W->stIns, W->evSyn[sl], 0));
+        launchSeedsOnly(W->packedOff.p + r0, r1 - r0, P, W->view, W->stIns);
+    }
+    CK(cudaEventRecord(W->evIns, W->stIns));
+    CK(cudaStreamWaitEvent(W->st, W->evIns, 0));
 }
 
 void stageScore(pm_workspace* W, const pm_place_params& prm) {
@@ -506,6 +523,9 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         W->idx = idx;
         CK(cudaStreamCreateWithFlags(&W->st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&W->stCopy, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&W->stIns, cudaStreamNonBlocking));
+        for (auto& e : W->evSyn) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&W->evIns, cudaEventDisableTiming));
         for (auto& e : W->ev) CK(cudaEventCreate(&e));
         for (auto& e : W->evCopy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         const FlatIndex& F = idx->F;
@@ -536,6 +556,9 @@ void pm_workspace_destroy(pm_workspace* ws) {
     cudaSetDevice(ws->idx->device);
     if (ws->st) { cudaStreamSynchronize(ws->st); cudaStreamDestroy(ws->st); }
     if (ws->stCopy) { cudaStreamSynchronize(ws->stCopy); cudaStreamDestroy(ws->stCopy); }
+    if (ws->stIns) { cudaStreamSynchronize(ws->stIns); cudaStreamDestroy(ws->stIns); }
+    for (auto& e : ws->evSyn) if (e) cudaEventDestroy(e);
+    if (ws->evIns) cudaEventDestroy(ws->evIns);
     for (auto& e : ws->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ws->evCopy) if (e) cudaEventDestroy(e);
     delete ws;

@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
 template <int MODE>
 static void launchSeedsFromSyncmers(const u64* synBuf, const unsigned* synCount, const u64* packedOff, const u64* winOff, u64 nReads, int k, int l,
                                     TableSlot* table, u64 mask, SampleAcc* acc, u64* outHash, u64* outCount, cudaStream_t st) {
-    u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
+    u64 g = (nReads + 7) / 8; if (g > 148ull * 4) g = 148ull * 4;   // <= 1024 threads per SM: shares the SMs with the syncmer kernel
     const unsigned grid = (unsigned)(g ? g : 1);
     if (k == 19 && l == 3)
         seeds_from_syncmers<MODE, 19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount);
@@ -417,7 +417,7 @@ static size_t genericSmemBytes(const SeederParams& P) {
 }
 static unsigned seedGrid(u64 nReads) {
     u64 g = (nReads + kSeedThreads - 1) / kSeedThreads;
-    if (g > 148ull * 16) g = 148ull * 16;
+    if (g > 148ull * 8) g = 148ull * 8;   // <= 1024 threads per SM: shares the SMs with seeds_from_syncmers of the previous slice
     return (unsigned)(g ? g : 1);
 }
 template <int K, int S>
@@ -436,10 +436,15 @@ static void launchSyncmers(const uint4* packed, const u64* off, const u64* packe
     syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
                                                                      nullptr, nullptr, nullptr);
 }
-void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
+// The two seeding kernels have complementary bottlenecks (syncmers_*: integer issue; seeds_from_syncmers: L1/LSU wavefronts and
+// L2 atomics), so the host runs them on two streams over slices of the reads: while slice i is counted, slice i+1 is hashed.
+void launchSyncmersOnly(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
+                        const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
     if (nReads == 0) return;
     launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, st);
+}
+void launchSeedsOnly(const u64* packedOff, u64 nReads, const SeederParams& P, WorkspaceView W, cudaStream_t st) {
+    if (nReads == 0) return;
     launchSeedsFromSyncmers<0>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table, W.tableMask, W.acc, nullptr, nullptr, st);
 }
 // mode 1: syncmer (hash, isReverse, pos) lists == seeding::rollingSyncmers(returnAll=false); mode 2: per-read seed lists
@@ -839,6 +844,10 @@ __global__ void __launch_bounds__(kK1Threads, 3) node_deltas(DevIndexView I, Wor
     u64 clo = 0; int chi = 0, ccn = 0;      // open run carried over from the previous chunk (warp-uniform)
     for (u64 c = c0; c < c1; ++c) {
         const unsigned F = __ldg(&I.endMask[c * 32 + lane]);   // bit j: word j of this lane is the last delta of its node
+        if (c + 2 < c1) {   // pull the chunk after next towards L2 while this one is processed (16 lines of words + 1 line of masks)
+            if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(I.dw + (c + 2) * kChunkWords + lane * 32));
+            else if (lane == 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(I.endMask + (c + 2) * 32));
+        }
         u32 w[16];
         {   // the chunk is stored lane-interleaved: 16-byte piece q of lane l sits at uint4 index 32 q + l (coalesced)
             const uint4* p = reinterpret_cast<const uint4*>(I.dw + c * kChunkWords) + lane;
@@ -863,20 +872,38 @@ __global__ void __launch_bounds__(kK1Threads, 3) node_deltas(DevIndexView I, Wor
         endsBefore -= nEnd;
         const u32 segFirst = segBase + endsBefore;
         const unsigned endMask = __ballot_sync(0xffffffffu, nEnd != 0);
-        // ---- walk the 16 words: interior segments are stored, the first end is kept for after the scan ----
-        long long acc = 0, headV = 0; int cn = 0, headC = 0; unsigned k = 0;
+        // ---- walk the 16 words.  The positions of the lane's first and last segment end are known up front, so the running sum
+        //      is simply captured there: head = sum up to the first end, tail = total - sum up to the last end, and for a lane
+        //      with two ends the segment between them is the difference.  Three or more ends in one lane are rare (a re-walk).
+        const int first = F ? __ffs(F) - 1 : 99, last = F ? 31 - __clz(F) : 99;
+        long long acc = 0, headV = 0, lastV = 0; int cn = 0, headC = 0, lastC = 0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int m = -(int)(w[j] & 1u);                      // -1 when the seed is lost, 0 when gained
             const long long mm = (long long)m;
             acc += (e[j] ^ mm) - mm;
             cn += (int)(e[j] >> 32) ? (m | 1) : 0;                // present <=> e >= ln2 * 2^53, i.e. the high word is non-zero
-            if (F & (1u << j)) {
-                if (k == 0) { headV = acc; headC = cn; }
-                else segStore(W.segRec + segFirst + k, (u64)acc, (int)(acc >> 63), cn);
-                ++k; acc = 0; cn = 0;
+            if (j == first) { headV = acc; headC = cn; }
+            if (j == last) { lastV = acc; lastC = cn; }
+        }
+        if (nEnd == 2) { const long long sv = lastV - headV; segStore(W.segRec + segFirst + 1, (u64)sv, (int)(sv >> 63), lastC - headC); }
+        if (__any_sync(0xffffffffu, nEnd > 2)) {
+            if (nEnd > 2) {   // segments that begin and end inside the lane, one by one
+                long long a2 = 0; int c2 = 0; unsigned k = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int m = -(int)(w[j] & 1u);
+                    const long long mm = (long long)m;
+                    a2 += (e[j] ^ mm) - mm;
+                    c2 += (int)(e[j] >> 32) ? (m | 1) : 0;
+                    if (F & (1u << j)) {
+                        if (k) segStore(W.segRec + segFirst + k, (u64)a2, (int)(a2 >> 63), c2);
+                        ++k; a2 = 0; c2 = 0;
+                    }
+                }
             }
         }
+        acc -= lastV; cn -= lastC;   // trailing partial: everything after the last end (the whole lane when it has none)
         // ---- segmented inclusive scan over the lanes' trailing partials (a lane with a segment end restarts the run) ----
         u64 lo = (u64)acc; int hi = (int)(acc >> 63); int rc = cn;
         if (lane == 0 && !nEnd) { const u64 t = lo + clo; hi += chi + (t < lo ? 1 : 0); lo = t; rc += ccn; }

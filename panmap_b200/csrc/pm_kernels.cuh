@@ -114,8 +114,9 @@ struct PlaceOpts {
 // launches (all asynchronous on `st`)
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
                      uint4* packed, cudaStream_t st);
-void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st);
+void launchSyncmersOnly(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
+                        const SeedTables* dTables, WorkspaceView W, cudaStream_t st);
+void launchSeedsOnly(const u64* packedOff, u64 nReads, const SeederParams& P, WorkspaceView W, cudaStream_t st);
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
                     const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
                     unsigned char* outRev, long long* outPos, u64* outCount, cudaStream_t st);
