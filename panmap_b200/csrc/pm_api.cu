@@ -93,8 +93,8 @@ struct pm_index {
 
 struct pm_workspace {
     pm_index* idx = nullptr;
-    cudaStream_t st = nullptr, stCopy = nullptr, stIns = nullptr;   // compute, H2D copies, table insertion (overlaps the syncmer kernel)
-    cudaEvent_t ev[9]{}, evCopy[8]{}, evSyn[8]{}, evIns{};
+    cudaStream_t st = nullptr, stCopy = nullptr;
+    cudaEvent_t ev[9]{}, evCopy[8]{};
     // inputs
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
@@ -104,7 +104,7 @@ struct pm_workspace {
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0;
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
-    DevBuf<long long> ell; DevBuf<unsigned> countHist; DevBuf<u64> entKey; DevBuf<u32> entCnt, entId;
+    DevBuf<long long> ell; cudaTextureObject_t ellTex = 0; DevBuf<unsigned> countHist; DevBuf<u64> entKey; DevBuf<u32> entCnt, entId;
     DevBuf<ScanPartial> scanPart; DevBuf<FinPartial> finPart;
     DevBuf<SegRec> segRec, chainA;
     DevBuf<u64> genRec, evPrefix;
@@ -198,7 +198,7 @@ void refreshView(pm_workspace* W) {
     WorkspaceView& V = W->view;
     V.table = W->table.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
     V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
-    V.acc = W->acc.p; V.ell = W->ell.p; V.countHist = W->countHist.p; V.entKey = W->entKey.p; V.entCnt = W->entCnt.p; V.entId = W->entId.p;
+    V.acc = W->acc.p; V.ell = W->ell.p; V.ellTex = W->ellTex; V.countHist = W->countHist.p; V.entKey = W->entKey.p; V.entCnt = W->entCnt.p; V.entId = W->entId.p;
     V.scanPart = W->scanPart.p; V.finPart = W->finPart.p;
     V.segRec = W->segRec.p; V.chainA = W->chainA.p; V.genRec = W->genRec.p; V.evPrefix = W->evPrefix.p;
     V.scores = W->scores.p; V.metrics = W->wantMetrics ? W->metrics.p : nullptr; V.blockMax = W->blockMaxAndBfs.p;
@@ -302,14 +302,9 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
         CK(cudaEventRecord(W->evCopy[sl], W->stCopy));
         CK(cudaStreamWaitEvent(W->st, W->evCopy[sl], 0));
         launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st);
-        launchSyncmersOnly(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st);
-        CK(cudaEventRecord(W->evSyn[sl], W->st));
-        CK(cudaStreamWaitEvent(W->stIns, W->evSyn[sl], 0));   // (the first wait also orders the insertions after acc memset + table_clear)
-        launchSeedsOnly(W->packedOff.p + r0, r1 - r0, P, W->view, W->stIns);
+        launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st);
         bfBase += nBlk + 1;
     }
-    CK(cudaEventRecord(W->evIns, W->stIns));
-    CK(cudaStreamWaitEvent(W->st, W->evIns, 0));
     W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false;
 }
 
@@ -321,19 +316,7 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         launchTableClear(W->view, W->st);
     }
     launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st);
-    // slices of reads: the syncmer kernel of slice i+1 (integer-issue bound) overlaps the table insertion of slice i (LSU bound)
-    const u64 n = W->nReads;
-    const int nSlices = n >= (1u << 16) ? 8 : 1;
-    for (int sl = 0; sl < nSlices; ++sl) {
-        const u64 r0 = n * sl / nSlices, r1 = n * (sl + 1) / nSlices;
-        if (r1 == r0) continue;
-        launchSyncmersOnly(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st);
-        CK(cudaEventRecord(W->evSyn[sl], W->st));
-        CK(cudaStreamWaitEvent(W->stIns, W->evSyn[sl], 0));
-        launchSeedsOnly(W->packedOff.p + r0, r1 - r0, P, W->view, W->stIns);
-    }
-    CK(cudaEventRecord(W->evIns, W->stIns));
-    CK(cudaStreamWaitEvent(W->st, W->evIns, 0));
+    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st);
 }
 
 void stageScore(pm_workspace* W, const pm_place_params& prm) {
@@ -523,15 +506,19 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         W->idx = idx;
         CK(cudaStreamCreateWithFlags(&W->st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&W->stCopy, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&W->stIns, cudaStreamNonBlocking));
-        for (auto& e : W->evSyn) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&W->evIns, cudaEventDisableTiming));
         for (auto& e : W->ev) CK(cudaEventCreate(&e));
         for (auto& e : W->evCopy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
         W->acc.alloc(1); W->scalars.alloc(1); W->sel.alloc(5);
-        W->ell.alloc(F.S + 2); CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(long long), W->st));   // [S] is the always-zero slot of the padding words
+        W->ell.alloc(F.S + 2);
+        {
+            if (F.S + 2 >= (1ull << 27)) throw Unsupported("more than 2^27 distinct seeds: linear texture limit of the ell table");
+            cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = W->ell.p;
+            rd.res.linear.desc = cudaCreateChannelDesc<int2>(); rd.res.linear.sizeInBytes = (F.S + 2) * sizeof(long long);
+            cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+            CK(cudaCreateTextureObject(&W->ellTex, &rd, &td, nullptr));
+        } CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(long long), W->st));   // [S] is the always-zero slot of the padding words
         W->scanPart.alloc(kMaxPartials); W->finPart.alloc(kMaxPartials);
         W->countHist.alloc(kLog1pLut);
         W->segRec.alloc(F.nSeg + 1); CK(cudaMemsetAsync(W->segRec.p, 0, W->segRec.n * sizeof(SegRec), W->st));
@@ -556,9 +543,7 @@ void pm_workspace_destroy(pm_workspace* ws) {
     cudaSetDevice(ws->idx->device);
     if (ws->st) { cudaStreamSynchronize(ws->st); cudaStreamDestroy(ws->st); }
     if (ws->stCopy) { cudaStreamSynchronize(ws->stCopy); cudaStreamDestroy(ws->stCopy); }
-    if (ws->stIns) { cudaStreamSynchronize(ws->stIns); cudaStreamDestroy(ws->stIns); }
-    for (auto& e : ws->evSyn) if (e) cudaEventDestroy(e);
-    if (ws->evIns) cudaEventDestroy(ws->evIns);
+    if (ws->ellTex) cudaDestroyTextureObject(ws->ellTex);
     for (auto& e : ws->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ws->evCopy) if (e) cudaEventDestroy(e);
     delete ws;

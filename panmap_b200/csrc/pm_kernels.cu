@@ -224,11 +224,15 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
 //   oldest: F[p] == min(window)  <=>  F[p] is the suffix minimum of its block tail (one bit per slot, produced by the
 //           block-end pass) and that suffix minimum is <= the running minimum of the current block
 // so the ring keeps only the in-place suffix minima (2*W words per lane instead of 4*W) plus two W-bit masks.
-template <int K, int S>
+// LF >= 0: the warp that produced the syncmers of its 32 reads goes straight on to build their seeds (k-min-mers of LF syncmers, or
+// the syncmers themselves for LF <= 1) and count them in the table -- placement.cpp:1625-1682 -- while the lists are still in
+// L2.  Warps of an SM are in different phases at any time, so the integer-issue-bound hashing of some overlaps the
+// latency-bound table probes of others.  LF < 0: syncmer lists only.
+template <int K, int S, int LF>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                               const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
                                                               const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
-                                                              unsigned* __restrict__ synCount) {
+                                                              unsigned* __restrict__ synCount, TableSlot* table, u64 tmask, SampleAcc* acc) {
     constexpr int W = K - S + 1;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
@@ -335,6 +339,51 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
             }
         }
         if (valid) synCount[r] = cnt;
+        if (LF >= 0) {
+            __syncwarp();   // the lists written above are read by other lanes of this warp below
+            const int nS = !valid ? 0 : (LF <= 1 ? (int)cnt : ((int)cnt >= LF ? (int)cnt - LF + 1 : 0));
+            int incl = nS;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += o; }
+            const int E = incl - nS;                                   // seeds of the lanes before this one
+            const int T = __shfl_sync(0xffffffffu, incl, 31);          // seeds of the 32 reads
+            const u64 dstBits = reinterpret_cast<u64>(dst);
+            for (int i0 = 0; i0 < T; i0 += 64) {   // seeds are numbered across the 32 reads; two per lane per round, all probes in flight
+                u64 sd[2]; bool has[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int i = i0 + 32 * q + (int)lane;
+                    int lo = 0;                                        // last lane whose first seed number is <= i
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int Em = __shfl_sync(0xffffffffu, E, lo + step);
+                        if (Em <= i) lo += step;
+                    }
+                    const int j = i - __shfl_sync(0xffffffffu, E, lo);
+                    const u64* __restrict__ h = reinterpret_cast<const u64*>(shflU64(dstBits, lo));
+                    has[q] = i < T; sd[q] = 0;
+                    if (has[q]) {
+                        if (LF <= 1) sd[q] = __ldcg(h + j);
+                        else {
+                            u64 fw = 0, rw = 0;
+#pragma unroll
+                            for (int w = 0; w < (LF > 1 ? LF : 1); ++w) {
+                                const u64 x = __ldcg(h + j + w);
+                                fw ^= rol64(x, (unsigned)((K * (LF - 1 - w)) & 63));
+                                rw ^= rol64(x, (unsigned)((K * w) & 63));
+                            }
+                            sd[q] = umin64(fw, rw);
+                            has[q] = fw != rw;
+                        }
+                    }
+                }
+                u64 k0 = 0, k1 = 0, p0 = 0, p1 = 0;
+                if (has[0]) { p0 = mixKey(sd[0]) & tmask; k0 = __ldca(&table[p0].key); }
+                if (has[1]) { p1 = mixKey(sd[1]) & tmask; k1 = __ldca(&table[p1].key); }
+                if (has[0]) { if (k0 == sd[0]) atomicAdd(&table[p0].count, 1u); else tableInsert(table, tmask, sd[0], 1u, acc); }
+                if (has[1]) { if (k1 == sd[1]) atomicAdd(&table[p1].count, 1u); else tableInsert(table, tmask, sd[1], 1u, acc); }
+            }
+        }
     }
 }
 
@@ -402,7 +451,7 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
 template <int MODE>
 static void launchSeedsFromSyncmers(const u64* synBuf, const unsigned* synCount, const u64* packedOff, const u64* winOff, u64 nReads, int k, int l,
                                     TableSlot* table, u64 mask, SampleAcc* acc, u64* outHash, u64* outCount, cudaStream_t st) {
-    u64 g = (nReads + 7) / 8; if (g > 148ull * 4) g = 148ull * 4;   // <= 1024 threads per SM: shares the SMs with the syncmer kernel
+    u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
     const unsigned grid = (unsigned)(g ? g : 1);
     if (k == 19 && l == 3)
         seeds_from_syncmers<MODE, 19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount);
@@ -417,34 +466,36 @@ static size_t genericSmemBytes(const SeederParams& P) {
 }
 static unsigned seedGrid(u64 nReads) {
     u64 g = (nReads + kSeedThreads - 1) / kSeedThreads;
-    if (g > 148ull * 8) g = 148ull * 8;   // <= 1024 threads per SM: shares the SMs with seeds_from_syncmers of the previous slice
+    if (g > 148ull * 16) g = 148ull * 16;
     return (unsigned)(g ? g : 1);
 }
-template <int K, int S>
+template <int K, int S, int LF>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                       u64* synBuf, unsigned* synCount, cudaStream_t st) {
+                       u64* synBuf, unsigned* synCount, TableSlot* table, u64 tmask, SampleAcc* acc, cudaStream_t st) {
     const size_t sm = sizeof(SeedTables) + (size_t)2 * (K - S + 1) * kSeedThreads * sizeof(u64);
-    cudaFuncSetAttribute(syncmers_fast<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    syncmers_fast<K, S><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount);
+    cudaFuncSetAttribute(syncmers_fast<K, S, LF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    syncmers_fast<K, S, LF><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, table, tmask, acc);
 }
 static void launchSyncmers(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
                            u64* synBuf, unsigned* synCount, cudaStream_t st) {
-    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, st);
-    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, st);
+    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8, -1>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, nullptr, 0, nullptr, st);
+    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8, -1>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, nullptr, 0, nullptr, st);
     const size_t sm = genericSmemBytes(P);
     cudaFuncSetAttribute(syncmers_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
                                                                      nullptr, nullptr, nullptr);
 }
-// The two seeding kernels have complementary bottlenecks (syncmers_*: integer issue; seeds_from_syncmers: L1/LSU wavefronts and
-// L2 atomics), so the host runs them on two streams over slices of the reads: while slice i is counted, slice i+1 is hashed.
-void launchSyncmersOnly(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                        const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
+// reads -> count table.  panmap's default parameter sets run as ONE kernel (hash + count fused per warp); anything else as the
+// generic syncmer kernel followed by seeds_from_syncmers.
+void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
+                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
     if (nReads == 0) return;
+    if (!P.open && P.t == 0 && P.s == 8) {
+        if (P.k == 19 && P.l == 3) return launchFast<19, 8, 3>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
+        if (P.k == 15 && P.l == 3) return launchFast<15, 8, 3>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
+        if (P.k == 15 && P.l == 1) return launchFast<15, 8, 1>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
+    }
     launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, st);
-}
-void launchSeedsOnly(const u64* packedOff, u64 nReads, const SeederParams& P, WorkspaceView W, cudaStream_t st) {
-    if (nReads == 0) return;
     launchSeedsFromSyncmers<0>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table, W.tableMask, W.acc, nullptr, nullptr, st);
 }
 // mode 1: syncmer (hash, isReverse, pos) lists == seeding::rollingSyncmers(returnAll=false); mode 2: per-read seed lists
@@ -861,7 +912,8 @@ __global__ void __launch_bounds__(kK1Threads, 3) node_deltas(DevIndexView I, Wor
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const u32 id = w[j] >> 1;
-            e[j] = id < (u32)kHotIds ? sHot[id] : __ldg(&ell[id]);
+            if (id < (u32)kHotIds) e[j] = sHot[id];
+            else { const int2 t = tex1Dfetch<int2>(W.ellTex, (int)id); e[j] = (long long)(((u64)(u32)t.y << 32) | (u32)t.x); }
         }
         // segment index of this lane's first segment end: segments ending in earlier chunks + in earlier lanes
         const unsigned nEnd = __popc(F);

@@ -86,6 +86,7 @@ struct WorkspaceView {
     TableSlot* table; u64 tableMask; u64 tableCap;
     SampleAcc* acc;
     u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
+    cudaTextureObject_t ellTex;   // ell as a linear int2 texture: scattered gathers go through the TEX data path instead of the LSU's
     long long* ell;       // [nSeeds+2] log1p(read count) * 2^53 of the seed id (an exact integer), 0 when absent; slot nSeeds stays 0
     u64* entKey; u32* entCnt; u32* entId;   // [tableCap] occupied (key, count) pairs compacted by table_scan + the seed id found for them
     ScanPartial* scanPart; FinPartial* finPart;   // [kMaxPartials] per-block partials of the two finalize passes
@@ -114,9 +115,8 @@ struct PlaceOpts {
 // launches (all asynchronous on `st`)
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
                      uint4* packed, cudaStream_t st);
-void launchSyncmersOnly(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                        const SeedTables* dTables, WorkspaceView W, cudaStream_t st);
-void launchSeedsOnly(const u64* packedOff, u64 nReads, const SeederParams& P, WorkspaceView W, cudaStream_t st);
+void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
+                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st);
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
                     const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
                     unsigned char* outRev, long long* outPos, u64* outCount, cudaStream_t st);
