@@ -101,7 +101,7 @@ struct pm_workspace {
     u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
     bool residentValid = false;  // the device copy of the reads was laid out by pm_reads_upload (not by the sliced pm_place path)
     // table
-    DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0;
+    DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
     DevBuf<long long> ell; cudaTextureObject_t ellTex = 0; DevBuf<unsigned> countHist; DevBuf<u64> entKey; DevBuf<u32> entCnt, entId;
@@ -196,7 +196,7 @@ int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t 
 
 void refreshView(pm_workspace* W) {
     WorkspaceView& V = W->view;
-    V.table = W->table.p; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
+    V.table = W->table.p; V.tableTex = W->tableTex; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
     V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
     V.acc = W->acc.p; V.ell = W->ell.p; V.ellTex = W->ellTex; V.countHist = W->countHist.p; V.entKey = W->entKey.p; V.entCnt = W->entCnt.p; V.entId = W->entId.p;
     V.scanPart = W->scanPart.p; V.finPart = W->finPart.p;
@@ -210,7 +210,15 @@ void ensureTable(pm_workspace* W, u64 wantCap) {
     u64 cap = 1 << 12;
     while (cap < wantCap) cap <<= 1;
     if (cap <= W->tableCap) return;
+    if (cap > (1ull << 27)) throw std::runtime_error("read seed table would exceed 2^27 slots");
+    if (W->tableTex) { cudaDestroyTextureObject(W->tableTex); W->tableTex = 0; }
     W->table.alloc(cap); W->tableCap = cap; W->entKey.alloc(cap); W->entCnt.alloc(cap); W->entId.alloc(cap);
+    {
+        cudaResourceDesc rd{}; rd.resType = cudaResourceTypeLinear; rd.res.linear.devPtr = W->table.p;
+        rd.res.linear.desc = cudaCreateChannelDesc<uint4>(); rd.res.linear.sizeInBytes = cap * sizeof(TableSlot);
+        cudaTextureDesc td{}; td.readMode = cudaReadModeElementType;
+        CK(cudaCreateTextureObject(&W->tableTex, &rd, &td, nullptr));
+    }
     refreshView(W);
 }
 
@@ -544,6 +552,7 @@ void pm_workspace_destroy(pm_workspace* ws) {
     if (ws->st) { cudaStreamSynchronize(ws->st); cudaStreamDestroy(ws->st); }
     if (ws->stCopy) { cudaStreamSynchronize(ws->stCopy); cudaStreamDestroy(ws->stCopy); }
     if (ws->ellTex) cudaDestroyTextureObject(ws->ellTex);
+    if (ws->tableTex) cudaDestroyTextureObject(ws->tableTex);
     for (auto& e : ws->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ws->evCopy) if (e) cudaEventDestroy(e);
     delete ws;

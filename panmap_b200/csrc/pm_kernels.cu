@@ -12,6 +12,7 @@
 // This is integer/byte streaming work bounded by HBM and issue rate; no tensor cores are involved.
 #include "pm_kernels.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace pm {
 
@@ -236,13 +237,13 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
     constexpr int W = K - S + 1;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
-    u64* rings = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables));
     for (int i = threadIdx.x; i < (int)(sizeof(SeedTables) / 8); i += blockDim.x)
         reinterpret_cast<u64*>(sT)[i] = reinterpret_cast<const u64*>(gT)[i];
     __syncthreads();
     const SeedTables& T = *sT;
-    u64* const rF = rings + threadIdx.x;                       // F / suffix-min ring, slot j at rF[j * kSeedThreads]
-    u64* const rR = rings + (size_t)W * kSeedThreads + threadIdx.x;
+    // F / suffix-min rings of the two strands: every index below is a compile-time constant (the block loop is fully unrolled), so
+    // the rings live in registers and the only shared-memory traffic left is the 8-entry constant tables
+    u64 rF[W], rR[W];
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
     const u64 warpId = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                             bool fA, rA; u64 mf, mr;
                             if (pslot == 0) { mf = preF; mr = preR; fA = firstF == preF; rA = firstR == preR; }
                             else {
-                                const u64 sf = rF[pslot * kSeedThreads], sr = rR[pslot * kSeedThreads];
+                                const u64 sf = rF[pslot], sr = rR[pslot];
                                 mf = umin64(sf, preF); mr = umin64(sr, preR);
                                 fA = ((maskF >> pslot) & 1u) && sf <= preF;
                                 rA = ((maskR >> pslot) & 1u) && sr <= preR;
@@ -322,15 +323,15 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                                 ++cnt;
                             }
                         }
-                        rF[j * kSeedThreads] = fs; rR[j * kSeedThreads] = rs;
+                        rF[j] = fs; rR[j] = rs;
                         if (j == W - 1) {   // block complete: in-place suffix minima + "is its own suffix minimum" masks
                             u64 a = kEmptyKey, bb = kEmptyKey; unsigned mF = 0, mR = 0;
 #pragma unroll
                             for (int q = W - 1; q >= 0; --q) {
-                                const u64 x = rF[q * kSeedThreads], y = rR[q * kSeedThreads];
+                                const u64 x = rF[q], y = rR[q];
                                 a = umin64(a, x); bb = umin64(bb, y);
                                 mF |= (a == x ? 1u : 0u) << q; mR |= (bb == y ? 1u : 0u) << q;
-                                rF[q * kSeedThreads] = a; rR[q * kSeedThreads] = bb;
+                                rF[q] = a; rR[q] = bb;
                             }
                             maskF = mF; maskR = mR;
                         }
@@ -396,7 +397,7 @@ template <int MODE, int KT, int LT>
 __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
                                                            const u64* __restrict__ packedOff, const u64* __restrict__ winOff, u64 nReads,
                                                            int kRt, int lRt, TableSlot* table, u64 mask, SampleAcc* acc,
-                                                           u64* outHash, u64* outCount) {
+                                                           u64* outHash, u64* outCount, cudaTextureObject_t tableTex) {
     const int k = KT > 0 ? KT : kRt, l = KT > 0 ? LT : lRt;
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
@@ -432,8 +433,9 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
             const bool h0 = seedAt(j0 + (int)lane, s0), h1 = seedAt(j0 + 32 + (int)lane, s1);
             if (MODE == 0) {
                 u64 k0 = 0, k1 = 0, p0 = 0, p1 = 0;
-                if (h0) { p0 = mixKey(s0) & mask; k0 = __ldca(&table[p0].key); }
-                if (h1) { p1 = mixKey(s1) & mask; k1 = __ldca(&table[p1].key); }
+                // first probe through the texture path (keys are write-once: a stale EMPTY only sends the seed to the CAS path)
+                if (h0) { p0 = mixKey(s0) & mask; const uint4 t = tex1Dfetch<uint4>(tableTex, (int)p0); k0 = (u64)t.x | ((u64)t.y << 32); }
+                if (h1) { p1 = mixKey(s1) & mask; const uint4 t = tex1Dfetch<uint4>(tableTex, (int)p1); k1 = (u64)t.x | ((u64)t.y << 32); }
                 if (h0) { if (k0 == s0) atomicAdd(&table[p0].count, 1u); else tableInsert(table, mask, s0, 1u, acc); }
                 if (h1) { if (k1 == s1) atomicAdd(&table[p1].count, 1u); else tableInsert(table, mask, s1, 1u, acc); }
             } else {
@@ -450,15 +452,15 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
 }
 template <int MODE>
 static void launchSeedsFromSyncmers(const u64* synBuf, const unsigned* synCount, const u64* packedOff, const u64* winOff, u64 nReads, int k, int l,
-                                    TableSlot* table, u64 mask, SampleAcc* acc, u64* outHash, u64* outCount, cudaStream_t st) {
+                                    TableSlot* table, u64 mask, SampleAcc* acc, u64* outHash, u64* outCount, cudaTextureObject_t tableTex, cudaStream_t st) {
     u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
     const unsigned grid = (unsigned)(g ? g : 1);
     if (k == 19 && l == 3)
-        seeds_from_syncmers<MODE, 19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount);
+        seeds_from_syncmers<MODE, 19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
     else if (k == 15 && l == 3)
-        seeds_from_syncmers<MODE, 15, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount);
+        seeds_from_syncmers<MODE, 15, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
     else
-        seeds_from_syncmers<MODE, 0, 0><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount);
+        seeds_from_syncmers<MODE, 0, 0><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
 }
 
 static size_t genericSmemBytes(const SeederParams& P) {
@@ -472,8 +474,7 @@ static unsigned seedGrid(u64 nReads) {
 template <int K, int S, int LF>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
                        u64* synBuf, unsigned* synCount, TableSlot* table, u64 tmask, SampleAcc* acc, cudaStream_t st) {
-    const size_t sm = sizeof(SeedTables) + (size_t)2 * (K - S + 1) * kSeedThreads * sizeof(u64);
-    cudaFuncSetAttribute(syncmers_fast<K, S, LF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    const size_t sm = sizeof(SeedTables);
     syncmers_fast<K, S, LF><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, table, tmask, acc);
 }
 static void launchSyncmers(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
@@ -490,13 +491,14 @@ static void launchSyncmers(const uint4* packed, const u64* off, const u64* packe
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
     if (nReads == 0) return;
-    if (!P.open && P.t == 0 && P.s == 8) {
+    static const bool fused = [] { const char* e = getenv("PM_SEED_FUSED"); return e ? atoi(e) != 0 : true; }();
+    if (fused && !P.open && P.t == 0 && P.s == 8) {
         if (P.k == 19 && P.l == 3) return launchFast<19, 8, 3>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
         if (P.k == 15 && P.l == 3) return launchFast<15, 8, 3>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
         if (P.k == 15 && P.l == 1) return launchFast<15, 8, 1>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
     }
     launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, st);
-    launchSeedsFromSyncmers<0>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table, W.tableMask, W.acc, nullptr, nullptr, st);
+    launchSeedsFromSyncmers<0>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table, W.tableMask, W.acc, nullptr, nullptr, W.tableTex, st);
 }
 // mode 1: syncmer (hash, isReverse, pos) lists == seeding::rollingSyncmers(returnAll=false); mode 2: per-read seed lists
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
@@ -510,7 +512,7 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
                                                                          outHash, outRev, outPos, outCount);
     } else {
         launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, st);
-        launchSeedsFromSyncmers<2>(synBuf, synCount, packedOff, winOff, nReads, P.k, P.l, nullptr, 0, nullptr, outHash, outCount, st);
+        launchSeedsFromSyncmers<2>(synBuf, synCount, packedOff, winOff, nReads, P.k, P.l, nullptr, 0, nullptr, outHash, outCount, 0, st);
     }
 }
 

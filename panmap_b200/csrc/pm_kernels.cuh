@@ -84,6 +84,7 @@ struct DevIndexView {
 struct WorkspaceView {
     // read table
     TableSlot* table; u64 tableMask; u64 tableCap;
+    cudaTextureObject_t tableTex;   // the table as a linear uint4 texture (first probe of an insertion)
     SampleAcc* acc;
     u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
     cudaTextureObject_t ellTex;   // ell as a linear int2 texture: scattered gathers go through the TEX data path instead of the LSU's
