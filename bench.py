@@ -35,8 +35,11 @@ WORKLOADS = {
     "c3-small": dict(name="synthetic 100k-node tree, 30 kb genome, 100k x 150 bp reads (reduced configs[2], dev only)", n_nodes=100_000,
                      genome=30_000, lam=1.0, n_reads=100_000, read_len=150),
 }
-KERNELS_PER_STEP = 15  # table_clear pack_reads syncmers_fast seeds_from_syncmers table_stats table_finalize root_denominator finish_scalars
-#                        node_deltas prefix_scores bfs_gather bfs_records chain_select collect_ties reset_ell
+KERNELS_PER_STEP = 15  # table_clear pack_reads syncmers_fast count_seeds table_scan entries_finalize root_denominator finish_scalars
+#                        node_deltas prefix_scores bfs_gather bfs_records chain_select collect_ties reset_sample
+#                        (+ gen_deltas, gen_prefix when the index holds deltas with a genome count >= 2; the synthetic one has none)
+# DRAM bytes (read + write) per launch from the ncu --set full capture of this workload (profiles/README.md)
+NCU_TRAFFIC = {"node_deltas": 78.8e6, "syncmers_fast": 0.50e9}
 
 
 def peaks():
@@ -208,13 +211,16 @@ def main():
     sampler = ClockSampler(0)
     sampler.start()
     stage = np.zeros(8)
+    kern = np.zeros(3)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = ws.place_resident(params, full=False)
         stage += np.array(list(r.stage_ms))
+        kern += np.array(ws.last_kernel_ms())
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     stage /= args.steps
+    kern /= args.steps
     dev_ms = float(stage[7])
     value = nodes_reads / (dev_ms * 1e-3)
     res = ws.place_resident(params)  # full result for the record
@@ -240,11 +246,17 @@ def main():
     L.pm_host_free(hp_reads); L.pm_host_free(hp_off)
 
     # ---- roofline ----
+    # dominant kernel of the step = the syncmer kernel (CUDA events of the library around that launch alone); it is bound by the
+    # integer ALU pipe, not by HBM, so its fraction of the HBM roofline is small by construction.  The HBM-bound kernel north_star
+    # names (node_deltas) is reported next to it the same way.
     peak = float(pk["hbm_gbs"])
-    names = ["h2d", "seeding+table insert (pack_reads, seed_reads)", "table finalize", "node_deltas", "prefix_scores", "selection", "d2h"]
-    dom = int(np.argmax(stage[1:6])) + 1
-    dom_bytes = {1: alg["seeding"], 2: 12 * int(res.raw.unique_seeds), 3: alg["delta_kernel"], 4: 40 * S.n_nodes + 40 * S.n_nodes, 5: 40 * S.n_nodes}[dom]
-    ach = dom_bytes / (stage[dom] * 1e-3) / 1e9
+    names = ["h2d", "seeding+table insert (pack_reads, syncmers_fast, count_seeds)", "table finalize", "node_deltas", "prefix_scores", "selection", "d2h"]
+    per_kernel = {"pack_reads": float(kern[0]), "syncmers_fast<19,8>": float(kern[1]), "count_seeds<19,3>": float(kern[2]),
+                  "node_deltas": float(stage[3]), "prefix_scores": float(stage[4])}
+    dom_name = max(per_kernel, key=per_kernel.get)
+    dom_bytes = {"pack_reads": alg["seeding"] * 3 // 2, "syncmers_fast<19,8>": alg["seeding"], "count_seeds<19,3>": 12 * int(res.raw.unique_seeds),
+                 "node_deltas": alg["delta_kernel"], "prefix_scores": 80 * S.n_nodes}[dom_name]
+    ach = dom_bytes / (per_kernel[dom_name] * 1e-3) / 1e9
     sc_ach = alg["delta_kernel"] / (stage[3] * 1e-3) / 1e9
     line = {
         "metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": 1, "steps": args.steps,
@@ -260,11 +272,14 @@ def main():
         "e2e": {"value": e2e_value, "unit": "node*reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
                 "device_ms_per_step": e2e_dev / args.steps},
         "gpu_launches": KERNELS_PER_STEP * args.steps,
-        "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "algorithmic_bytes_per_launch": dom_bytes, "peak_source": pk_src,
-                     "note": "dominant stage of the step by measured time; seeding is issue-bound integer work, not HBM-bound"},
+        "kernel_ms": per_kernel,
+        "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "traffic": NCU_TRAFFIC.get(dom_name.split("<")[0]), "algorithmic_bytes_per_launch": dom_bytes, "ms": per_kernel[dom_name], "peak_source": pk_src,
+                     "note": "dominant kernel of the step by measured time; it is limited by the integer ALU pipe (ncu: pipe_alu 87 %), one byte in per ~130 "
+                             "integer instructions, so the HBM fraction is small by construction -- see roofline_scoring for the HBM-bound kernel north_star names"},
         "roofline_scoring": {"bound": "hbm", "kernel": "node_deltas (the scoring kernel north_star names)", "achieved": sc_ach, "peak": peak, "unit": "GB/s",
-                             "frac": sc_ach / peak, "algorithmic_bytes_per_launch": alg["delta_kernel"], "ms": float(stage[3])},
+                             "frac": sc_ach / peak, "traffic": NCU_TRAFFIC["node_deltas"], "algorithmic_bytes_per_launch": alg["delta_kernel"], "ms": float(stage[3]),
+                             "note": "algorithmic bytes = 12 B/delta + 8 B/node of the reference layout (SURVEY 8d); the kernel itself streams 4 B/delta"},
         "place_stage": {"algorithmic_bytes": alg["total"], "achieved": alg["total"] / (dev_ms * 1e-3) / 1e9, "frac": alg["total"] / (dev_ms * 1e-3) / 1e9 / peak},
         "clocks": clocks,
     }

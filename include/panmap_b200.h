@@ -142,6 +142,9 @@ void pm_host_free(void* p);
 int pm_get_tied(pm_workspace* ws, int metric, uint32_t* out, uint64_t cap);
 int pm_get_node_scores(pm_workspace* ws, double* out /* [n_nodes][5] */);
 int pm_get_node_metrics(pm_workspace* ws, double* out /* [n_nodes][5]: logRawNum, logCosNum, presence, wcNum, logContNum */);
+/* CUDA-event time of the three seeding kernels of the last pm_place_resident call, in ms: 0 pack_reads, 1 syncmers_*,
+ * 2 count_seeds / seeds_from_syncmers (profiling aid for bench.py; the same events bracket nothing else) */
+int pm_last_kernel_ms(pm_workspace* ws, float* out /* [3] */);
 int pm_get_seed_table(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap); /* unsorted; returns n or <0 */
 
 /* ---- seeding::rollingSyncmers (seeding.cpp:47-229) for a batch of sequences, returnAll=false form:

@@ -93,6 +93,7 @@ def lib():
     L.pm_get_tied.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
     L.pm_get_node_scores.argtypes = [C.c_void_p, C.c_void_p]
     L.pm_get_node_metrics.argtypes = [C.c_void_p, C.c_void_p]
+    L.pm_last_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
     L.pm_get_seed_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_rolling_syncmers.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -310,6 +311,12 @@ class Workspace:
         res = PlaceResult()
         _ck(lib().pm_place_resident(self._h, C.byref(params), C.byref(res)))
         return self._finish(res) if full else res
+
+    def last_kernel_ms(self):
+        """CUDA-event times (ms) of pack_reads, syncmers_*, count_seeds of the last place_resident call"""
+        out = (C.c_float * 3)()
+        _ck(lib().pm_last_kernel_ms(self._h, out))
+        return [float(x) for x in out]
 
     def node_scores(self):
         out = np.zeros((self.index.n_nodes, 5), dtype=np.float64)

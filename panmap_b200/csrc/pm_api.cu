@@ -94,7 +94,7 @@ struct pm_index {
 struct pm_workspace {
     pm_index* idx = nullptr;
     cudaStream_t st = nullptr, stCopy = nullptr;
-    cudaEvent_t ev[9]{}, evCopy[8]{};
+    cudaEvent_t ev[9]{}, evCopy[8]{}, evK[4]{};   // evK: around pack_reads / syncmers / count_seeds of the resident path
     // inputs
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
@@ -103,7 +103,11 @@ struct pm_workspace {
     // table
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
-    DevBuf<SampleAcc> acc; DevBuf<SampleScalars> scalars; DevBuf<Selection> sel;
+    // the small per-sample result block lives in ONE device allocation so that it comes back with a single copy:
+    // [SampleAcc | SampleScalars | Selection x 5 | first kTieHead tied nodes of every metric]
+    DevBuf<unsigned char> resultBlob;
+    struct { SampleAcc* p = nullptr; } acc; struct { SampleScalars* p = nullptr; } scalars; struct { Selection* p = nullptr; } sel;
+    u32* tieHead = nullptr;
     DevBuf<long long> ell; cudaTextureObject_t ellTex = 0; DevBuf<unsigned> countHist; DevBuf<u64> entKey; DevBuf<u32> entCnt, entId;
     DevBuf<ScanPartial> scanPart; DevBuf<FinPartial> finPart;
     DevBuf<SegRec> segRec, chainA;
@@ -123,6 +127,8 @@ struct pm_workspace {
 };
 
 namespace {
+
+constexpr size_t kResultBlobBytes = sizeof(SampleAcc) + sizeof(SampleScalars) + 5 * sizeof(Selection) + 5 * kTieHead * sizeof(u32);
 
 void setDevice(int dev) { CK(cudaSetDevice(dev)); }
 
@@ -203,7 +209,7 @@ void refreshView(pm_workspace* W) {
     V.segRec = W->segRec.p; V.chainA = W->chainA.p; V.genRec = W->genRec.p; V.evPrefix = W->evPrefix.p;
     V.scores = W->scores.p; V.metrics = W->wantMetrics ? W->metrics.p : nullptr; V.blockMax = W->blockMaxAndBfs.p;
     V.recRank = W->recRank.p; V.recNode = W->recNode.p; V.recScore = W->recScore.p; V.recCap = W->recCap;
-    V.tieNode = W->tieNode.p; V.tieCap = W->tieCap; V.sel = W->sel.p; V.scalars = W->scalars.p;
+    V.tieNode = W->tieNode.p; V.tieCap = W->tieCap; V.tieHead = W->tieHead; V.sel = W->sel.p; V.scalars = W->scalars.p;
 }
 
 void ensureTable(pm_workspace* W, u64 wantCap) {
@@ -275,12 +281,14 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     const int k = I->F.sp.k;
     if (n && off[0] != 0) throw std::runtime_error("read_offsets[0] must be 0");
     const u64 total = n ? off[n] : 0;
-    const int nSlices = n >= (1u << 16) ? 6 : 1;
+    // slices shrink towards the end: everything after the last copy (its seeding, then scoring and selection) is exposed latency
+    static const double kCut[8] = {0.0, 0.20, 0.40, 0.58, 0.74, 0.86, 0.94, 1.0};
+    const int nSlices = n >= (1u << 16) ? 7 : 1;
     W->nReads = n; W->totalBases = total;
-    W->hPackedOff.ensure(n + 1); W->hBlockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 16);
+    W->hPackedOff.ensure(n + 1); W->hBlockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 32);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
     W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1);
-    W->blockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 16);
+    W->blockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 32);
     if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, (total > (u64)k * n ? total - (u64)(k - 1) * n : 0) / 4));
     refreshView(W);
     const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
@@ -288,7 +296,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     launchTableClear(W->view, W->st);
     u64 chunkAcc = 0, win = 0, bfBase = 0;
     for (int sl = 0; sl < nSlices; ++sl) {
-        const u64 r0 = n * sl / nSlices, r1 = n * (sl + 1) / nSlices;
+        const u64 r0 = nSlices == 1 ? 0 : (u64)((double)n * kCut[sl]), r1 = nSlices == 1 || sl + 1 == nSlices ? n : (u64)((double)n * kCut[sl + 1]);
         if (r1 == r0) continue;
         const u64 gBase = chunkAcc;
         for (u64 i = r0; i < r1; ++i) {
@@ -323,8 +331,11 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
         launchTableClear(W->view, W->st);
     }
+    CK(cudaEventRecord(W->evK[0], W->st));
     launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st);
-    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st);
+    CK(cudaEventRecord(W->evK[1], W->st));
+    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2]);
+    CK(cudaEventRecord(W->evK[3], W->st));
 }
 
 void stageScore(pm_workspace* W, const pm_place_params& prm) {
@@ -342,11 +353,9 @@ void stageScore(pm_workspace* W, const pm_place_params& prm) {
 
 // D2H of the small result block; returns after the stream is idle
 void fetchSmall(pm_workspace* W) {
-    W->hStage.ensure(sizeof(SampleAcc) + sizeof(SampleScalars) + 5 * sizeof(Selection));
+    W->hStage.ensure(kResultBlobBytes);
     unsigned char* h = W->hStage.p;
-    CK(cudaMemcpyAsync(h, W->acc.p, sizeof(SampleAcc), cudaMemcpyDeviceToHost, W->st));
-    CK(cudaMemcpyAsync(h + sizeof(SampleAcc), W->scalars.p, sizeof(SampleScalars), cudaMemcpyDeviceToHost, W->st));
-    CK(cudaMemcpyAsync(h + sizeof(SampleAcc) + sizeof(SampleScalars), W->sel.p, 5 * sizeof(Selection), cudaMemcpyDeviceToHost, W->st));
+    CK(cudaMemcpyAsync(h, W->resultBlob.p, kResultBlobBytes, cudaMemcpyDeviceToHost, W->st));
     CK(cudaStreamSynchronize(W->st));
     std::memcpy(&W->hAcc, h, sizeof(SampleAcc));
     std::memcpy(&W->hScal, h + sizeof(SampleAcc), sizeof(SampleScalars));
@@ -372,16 +381,21 @@ void fillResult(pm_workspace* W, pm_place_result* r, u64 totalReads) {
 
 // tie lists -> host, finalizeTiedIndices semantics (placement.cpp:395-401): sort, unique, best = front
 void fetchTies(pm_workspace* W) {
-    // one pinned staging buffer, one synchronisation
-    size_t tot = 0; unsigned n[5];
-    for (int m = 0; m < 5; ++m) { n[m] = std::min<unsigned>(W->hAcc.tieCount[m], W->tieCap); tot += n[m]; }
+    // short lists (the usual case) came back with the result block; longer ones need one more copy
+    size_t tot = 0; unsigned n[5]; bool big = false;
+    for (int m = 0; m < 5; ++m) { n[m] = std::min<unsigned>(W->hAcc.tieCount[m], W->tieCap); tot += n[m]; big = big || n[m] > (unsigned)kTieHead; }
     W->hTies.ensure(tot + 1);
     size_t o = 0;
-    for (int m = 0; m < 5; ++m) {
-        if (n[m]) CK(cudaMemcpyAsync(W->hTies.p + o, W->tieNode.p + (size_t)m * W->tieCap, n[m] * sizeof(u32), cudaMemcpyDeviceToHost, W->st));
-        o += n[m];
+    if (big) {
+        for (int m = 0; m < 5; ++m) {
+            if (n[m]) CK(cudaMemcpyAsync(W->hTies.p + o, W->tieNode.p + (size_t)m * W->tieCap, n[m] * sizeof(u32), cudaMemcpyDeviceToHost, W->st));
+            o += n[m];
+        }
+        CK(cudaStreamSynchronize(W->st));
+    } else {
+        const u32* head = reinterpret_cast<const u32*>(W->hStage.p + sizeof(SampleAcc) + sizeof(SampleScalars) + 5 * sizeof(Selection));
+        for (int m = 0; m < 5; ++m) { std::memcpy(W->hTies.p + o, head + (size_t)m * kTieHead, n[m] * sizeof(u32)); o += n[m]; }
     }
-    if (tot) CK(cudaStreamSynchronize(W->st));
     o = 0;
     for (int m = 0; m < 5; ++m) {
         std::vector<u32>& t = W->tied[m];
@@ -516,9 +530,15 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         CK(cudaStreamCreateWithFlags(&W->stCopy, cudaStreamNonBlocking));
         for (auto& e : W->ev) CK(cudaEventCreate(&e));
         for (auto& e : W->evCopy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : W->evK) CK(cudaEventCreate(&e));
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
-        W->acc.alloc(1); W->scalars.alloc(1); W->sel.alloc(5);
+        W->resultBlob.alloc(kResultBlobBytes);
+        CK(cudaMemsetAsync(W->resultBlob.p, 0, kResultBlobBytes, W->st));
+        W->acc.p = reinterpret_cast<SampleAcc*>(W->resultBlob.p);
+        W->scalars.p = reinterpret_cast<SampleScalars*>(W->resultBlob.p + sizeof(SampleAcc));
+        W->sel.p = reinterpret_cast<Selection*>(W->resultBlob.p + sizeof(SampleAcc) + sizeof(SampleScalars));
+        W->tieHead = reinterpret_cast<u32*>(W->resultBlob.p + sizeof(SampleAcc) + sizeof(SampleScalars) + 5 * sizeof(Selection));
         W->ell.alloc(F.S + 2);
         {
             if (F.S + 2 >= (1ull << 27)) throw Unsupported("more than 2^27 distinct seeds: linear texture limit of the ell table");
@@ -555,6 +575,7 @@ void pm_workspace_destroy(pm_workspace* ws) {
     if (ws->tableTex) cudaDestroyTextureObject(ws->tableTex);
     for (auto& e : ws->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ws->evCopy) if (e) cudaEventDestroy(e);
+    for (auto& e : ws->evK) if (e) cudaEventDestroy(e);
     delete ws;
 }
 
@@ -926,6 +947,16 @@ int pm_stage_select(pm_workspace* ws, const uint32_t* counts, const uint32_t* co
         std::memset(result, 0, sizeof(*result));
         fillResult(ws, result, total_reads);
         ws->haveResult = true;
+        return PM_OK;
+    });
+}
+
+int pm_last_kernel_ms(pm_workspace* ws, float* out) {
+    if (!ws || !out) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        CK(cudaStreamSynchronize(ws->st));
+        for (int i = 0; i < 3; ++i) { out[i] = 0.f; if (cudaEventElapsedTime(&out[i], ws->evK[i], ws->evK[i + 1]) != cudaSuccess) { cudaGetLastError(); out[i] = 0.f; } }
         return PM_OK;
     });
 }

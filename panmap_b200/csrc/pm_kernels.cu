@@ -225,15 +225,11 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
 //   oldest: F[p] == min(window)  <=>  F[p] is the suffix minimum of its block tail (one bit per slot, produced by the
 //           block-end pass) and that suffix minimum is <= the running minimum of the current block
 // so the ring keeps only the in-place suffix minima (2*W words per lane instead of 4*W) plus two W-bit masks.
-// LF >= 0: the warp that produced the syncmers of its 32 reads goes straight on to build their seeds (k-min-mers of LF syncmers, or
-// the syncmers themselves for LF <= 1) and count them in the table -- placement.cpp:1625-1682 -- while the lists are still in
-// L2.  Warps of an SM are in different phases at any time, so the integer-issue-bound hashing of some overlaps the
-// latency-bound table probes of others.  LF < 0: syncmer lists only.
-template <int K, int S, int LF>
+template <int K, int S>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                               const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
                                                               const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
-                                                              unsigned* __restrict__ synCount, TableSlot* table, u64 tmask, SampleAcc* acc) {
+                                                              unsigned* __restrict__ synCount) {
     constexpr int W = K - S + 1;
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
@@ -340,51 +336,6 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
             }
         }
         if (valid) synCount[r] = cnt;
-        if (LF >= 0) {
-            __syncwarp();   // the lists written above are read by other lanes of this warp below
-            const int nS = !valid ? 0 : (LF <= 1 ? (int)cnt : ((int)cnt >= LF ? (int)cnt - LF + 1 : 0));
-            int incl = nS;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += o; }
-            const int E = incl - nS;                                   // seeds of the lanes before this one
-            const int T = __shfl_sync(0xffffffffu, incl, 31);          // seeds of the 32 reads
-            const u64 dstBits = reinterpret_cast<u64>(dst);
-            for (int i0 = 0; i0 < T; i0 += 64) {   // seeds are numbered across the 32 reads; two per lane per round, all probes in flight
-                u64 sd[2]; bool has[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int i = i0 + 32 * q + (int)lane;
-                    int lo = 0;                                        // last lane whose first seed number is <= i
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const int Em = __shfl_sync(0xffffffffu, E, lo + step);
-                        if (Em <= i) lo += step;
-                    }
-                    const int j = i - __shfl_sync(0xffffffffu, E, lo);
-                    const u64* __restrict__ h = reinterpret_cast<const u64*>(shflU64(dstBits, lo));
-                    has[q] = i < T; sd[q] = 0;
-                    if (has[q]) {
-                        if (LF <= 1) sd[q] = __ldcg(h + j);
-                        else {
-                            u64 fw = 0, rw = 0;
-#pragma unroll
-                            for (int w = 0; w < (LF > 1 ? LF : 1); ++w) {
-                                const u64 x = __ldcg(h + j + w);
-                                fw ^= rol64(x, (unsigned)((K * (LF - 1 - w)) & 63));
-                                rw ^= rol64(x, (unsigned)((K * w) & 63));
-                            }
-                            sd[q] = umin64(fw, rw);
-                            has[q] = fw != rw;
-                        }
-                    }
-                }
-                u64 k0 = 0, k1 = 0, p0 = 0, p1 = 0;
-                if (has[0]) { p0 = mixKey(sd[0]) & tmask; k0 = __ldca(&table[p0].key); }
-                if (has[1]) { p1 = mixKey(sd[1]) & tmask; k1 = __ldca(&table[p1].key); }
-                if (has[0]) { if (k0 == sd[0]) atomicAdd(&table[p0].count, 1u); else tableInsert(table, tmask, sd[0], 1u, acc); }
-                if (has[1]) { if (k1 == sd[1]) atomicAdd(&table[p1].count, 1u); else tableInsert(table, tmask, sd[1], 1u, acc); }
-            }
-        }
     }
 }
 
@@ -450,6 +401,85 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
         if (MODE != 0 && lane == 0) outCount[r] = written;
     }
 }
+// count_seeds: the table-insertion half of seeding for whole samples.  A warp takes 32 reads at a time (lane q holds the list of
+// read r0 + q), numbers their seeds consecutively and works through them 128 at a time, so that every lane has four independent
+// chains (syncmer loads -> seed -> first probe) in flight: the kernel is bound by memory latency, not by bandwidth or issue.
+template <int KT, int LT>
+__global__ void __launch_bounds__(256) count_seeds(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
+                                                   const u64* __restrict__ packedOff, u64 nReads, int kRt, int lRt, TableSlot* table,
+                                                   u64 mask, SampleAcc* acc, cudaTextureObject_t tableTex) {
+    const int k = KT > 0 ? KT : kRt, l = KT > 0 ? LT : lRt;
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 r0 = ((u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; r0 < nReads; r0 += warpsTotal * 32) {
+        const u64 r = r0 + lane;
+        const int n = r < nReads ? (int)__ldg(&synCount[r]) : 0;
+        const u64 listBits = reinterpret_cast<u64>(synBuf + (r < nReads ? __ldg(&packedOff[r]) : 0) * 32);
+        const int nS = l <= 1 ? n : (n >= l ? n - l + 1 : 0);
+        int incl = nS;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += o; }
+        const int E = incl - nS;                                   // seeds of the lanes before this one
+        const int T = __shfl_sync(0xffffffffu, incl, 31);          // seeds of the 32 reads
+        for (int i0 = 0; i0 < T; i0 += 128) {
+            u64 sd[4], slot[4]; bool has[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i0 + 32 * q + (int)lane;
+                int lo = 0;                                        // last lane whose first seed number is <= i
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int Em = __shfl_sync(0xffffffffu, E, lo + step);
+                    if (Em <= i) lo += step;
+                }
+                const int j = i - __shfl_sync(0xffffffffu, E, lo);
+                const u64* __restrict__ h = reinterpret_cast<const u64*>(shflU64(listBits, lo));
+                has[q] = i < T; sd[q] = 0;
+                if (has[q]) {
+                    if (l <= 1) sd[q] = __ldcs(h + j);
+                    else {
+                        u64 fw = 0, rw = 0;
+                        if (KT > 0) {
+#pragma unroll
+                            for (int w = 0; w < (LT > 0 ? LT : 1); ++w) {
+                                const u64 x = __ldg(h + j + w);
+                                fw ^= rol64(x, (unsigned)((KT * (LT - 1 - w)) & 63));
+                                rw ^= rol64(x, (unsigned)((KT * w) & 63));
+                            }
+                        } else {
+                            for (int w = 0; w < l; ++w) {
+                                const u64 x = __ldg(h + j + w);
+                                fw ^= rol64(x, (unsigned)(k * (l - 1 - w)));
+                                rw ^= rol64(x, (unsigned)(k * w));
+                            }
+                        }
+                        sd[q] = umin64(fw, rw);
+                        has[q] = fw != rw;
+                    }
+                }
+                slot[q] = mixKey(sd[q]) & mask;
+            }
+            u64 key[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {   // first probe through the texture path (keys are write-once: a stale EMPTY only sends the seed to the CAS path)
+                key[q] = kEmptyKey;
+                if (has[q]) { const uint4 t = tex1Dfetch<uint4>(tableTex, (int)slot[q]); key[q] = (u64)t.x | ((u64)t.y << 32); }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (has[q]) { if (key[q] == sd[q] && sd[q] != kEmptyKey) atomicAdd(&table[slot[q]].count, 1u); else tableInsert(table, mask, sd[q], 1u, acc); }
+        }
+    }
+}
+static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, TableSlot* table, u64 mask,
+                             SampleAcc* acc, cudaTextureObject_t tableTex, cudaStream_t st) {
+    u64 g = (nReads + 255) / 256; if (g > 148ull * 8) g = 148ull * 8;
+    const unsigned grid = (unsigned)(g ? g : 1);
+    if (k == 19 && l == 3) count_seeds<19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+    else if (k == 15 && l == 3) count_seeds<15, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+    else count_seeds<0, 0><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+}
+
 template <int MODE>
 static void launchSeedsFromSyncmers(const u64* synBuf, const unsigned* synCount, const u64* packedOff, const u64* winOff, u64 nReads, int k, int l,
                                     TableSlot* table, u64 mask, SampleAcc* acc, u64* outHash, u64* outCount, cudaTextureObject_t tableTex, cudaStream_t st) {
@@ -471,34 +501,29 @@ static unsigned seedGrid(u64 nReads) {
     if (g > 148ull * 16) g = 148ull * 16;
     return (unsigned)(g ? g : 1);
 }
-template <int K, int S, int LF>
+template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                       u64* synBuf, unsigned* synCount, TableSlot* table, u64 tmask, SampleAcc* acc, cudaStream_t st) {
-    const size_t sm = sizeof(SeedTables);
-    syncmers_fast<K, S, LF><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, table, tmask, acc);
+                       u64* synBuf, unsigned* synCount, cudaStream_t st) {
+    syncmers_fast<K, S><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables), st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount);
 }
 static void launchSyncmers(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
                            u64* synBuf, unsigned* synCount, cudaStream_t st) {
-    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8, -1>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, nullptr, 0, nullptr, st);
-    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8, -1>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, nullptr, 0, nullptr, st);
+    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, st);
+    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, st);
     const size_t sm = genericSmemBytes(P);
     cudaFuncSetAttribute(syncmers_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
                                                                      nullptr, nullptr, nullptr);
 }
-// reads -> count table.  panmap's default parameter sets run as ONE kernel (hash + count fused per warp); anything else as the
-// generic syncmer kernel followed by seeds_from_syncmers.
+// reads -> count table: syncmer lists per read, then their seeds into the table.  (Running the two as one kernel, or concurrently
+// on two streams, was measured and is slower: both are limited by the same L1/LSU data pipe and the hashing needs every warp an
+// SM can hold.)
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st) {
+                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between) {
     if (nReads == 0) return;
-    static const bool fused = [] { const char* e = getenv("PM_SEED_FUSED"); return e ? atoi(e) != 0 : true; }();
-    if (fused && !P.open && P.t == 0 && P.s == 8) {
-        if (P.k == 19 && P.l == 3) return launchFast<19, 8, 3>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
-        if (P.k == 15 && P.l == 3) return launchFast<15, 8, 3>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
-        if (P.k == 15 && P.l == 1) return launchFast<15, 8, 1>(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, W.table, W.tableMask, W.acc, st);
-    }
     launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, st);
-    launchSeedsFromSyncmers<0>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table, W.tableMask, W.acc, nullptr, nullptr, W.tableTex, st);
+    if (between) cudaEventRecord(between, st);
+    launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, st);
 }
 // mode 1: syncmer (hash, isReverse, pos) lists == seeding::rollingSyncmers(returnAll=false); mode 2: per-read seed lists
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
@@ -1394,6 +1419,7 @@ __global__ void __launch_bounds__(256) collect_ties(DevIndexView I, WorkspaceVie
         if (x >= lo && x > 0.0) {
             const unsigned o = atomicAdd(&W.acc->tieCount[m], 1u);
             if (o < W.tieCap) W.tieNode[(size_t)m * W.tieCap + o] = I.bfsNodes[r]; else W.acc->overflow = 1;
+            if (o < (unsigned)kTieHead) W.tieHead[m * kTieHead + o] = I.bfsNodes[r];
         }
     }
 }

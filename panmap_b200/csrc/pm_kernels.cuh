@@ -10,6 +10,7 @@ constexpr int kChunkWords = 512;    // K1: packed delta words per warp chunk (16
 constexpr int kBfsBlock = 1024;     // selection: BFS positions per block
 constexpr int kLog1pLut = 1 << 16;  // log1p(count) table computed on the host with glibc (bit-identical terms)
 constexpr u32 kNone = 0xFFFFFFFFu;
+constexpr int kTieHead = 64;        // tied nodes per metric that travel with the small result block
 
 // Per-segment (= node with 0<->1 deltas) parent-relative sums written by K1 and read by K2, 16 bytes:
 //   sum = hi * 2^64 + lo, a signed 96-bit integer in units of 2^-53: the exact sum of +-log1p(readCount) over the node's seeds
@@ -102,6 +103,7 @@ struct WorkspaceView {
     // records / ties per metric
     u32* recRank; u32* recNode; double* recScore; u32 recCap;  // [5][recCap]
     u32* tieNode; u32 tieCap;                                  // [5][tieCap]
+    u32* tieHead;                                              // [5][kTieHead] copy of the first entries (inside the result block)
     Selection* sel;       // [5]
     SampleScalars* scalars;
 };
@@ -117,7 +119,7 @@ struct PlaceOpts {
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
                      uint4* packed, cudaStream_t st);
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st);
+                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between = nullptr);
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
                     const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
                     unsigned char* outRev, long long* outPos, u64* outCount, cudaStream_t st);
