@@ -896,9 +896,9 @@ __device__ __forceinline__ void segStore(SegRec* r, u64 lo, int hi, int cnt) {
     *reinterpret_cast<uint4*>(r) = make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)cnt);
 }
 
-constexpr int kK1Threads = 256;
-constexpr int kHotIds = 8192;   // seed ids below this (the root's seeds and other early, ancestral ones) are gathered from shared memory
-__global__ void __launch_bounds__(kK1Threads, 3) node_deltas(DevIndexView I, WorkspaceView W, u32 chunksPerWarp) {
+constexpr int kK1Threads = 768;  // one persistent block per SM: the hot table is filled once per SM
+constexpr int kHotIds = 16384;   // seed ids below this (the root's seeds and other early, ancestral ones) are gathered from shared memory
+__global__ void __launch_bounds__(kK1Threads, 1) node_deltas(DevIndexView I, WorkspaceView W, u32 chunksPerWarp) {
     extern __shared__ __align__(16) long long sHot[];   // [kHotIds] copy of ell[0 .. kHotIds)
     const long long* __restrict__ ell = W.ell;
     const unsigned tid = threadIdx.x, lane = tid & 31u;
@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(kK1Threads, 3) node_deltas(DevIndexView I, Wor
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st) {
     if (I.nDeltaChunks == 0) return;
     const u64 wpb = kK1Threads / 32;
-    const u64 warps = (u64)nSM * 3 * wpb;   // 3 blocks per SM (shared-memory bound)
+    const u64 warps = (u64)nSM * wpb;   // one block per SM
     const u32 per = (u32)((I.nDeltaChunks + warps - 1) / warps);
     const u64 grid = ((I.nDeltaChunks + per - 1) / per + wpb - 1) / wpb;
     const size_t sm = (size_t)kHotIds * sizeof(long long);
