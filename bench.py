@@ -165,7 +165,7 @@ def run_reference_arm(args):
     tot = sum(times)
     value = S.n_nodes * n_s * args.steps / tot
     line = {"impl": "reference", "metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
             "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n_s, "k": 19, "s": 8, "l": 3},
             "cpu_baseline": {"value": value, "unit": "node*reads/s", "cores": threads, "kind": "reference",
