@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                                                               const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
                                                               unsigned* __restrict__ synCount) {
     constexpr int W = K - S + 1;
+    static_assert(K >= 8 && K <= 32 && S >= 8 && S < K, "lagged-word addressing assumes 8 <= s < k <= 32");
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
     for (int i = threadIdx.x; i < (int)(sizeof(SeedTables) / 8); i += blockDim.x)
@@ -255,41 +256,46 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         int maxL = L;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, d));
-        const int validEnd = L - P.trimEnd - K;
-        const int trimStart = P.trimStart;
 
-        u64 fk = 0, rk = 0, fs = 0, rs = 0, hist2 = 0, preF = kEmptyKey, preR = kEmptyKey, firstF = 0, firstR = 0;
-        unsigned histAmb = 0xFFFFFFFFu, maskF = 0, maskR = 0, word = 0, cnt = 0;
+        // The kernel is bound by the integer ALU pipe, so the loop below is written to need as few integer instructions per base
+        // as possible: the bases that leave the k-mer / s-mer windows come from lagged copies of the packed words (one AND + one
+        // shift each, no base history to maintain), every 64-bit minimum doubles as the comparison the syncmer test needs, and
+        // the trim / ambiguity / window-complete conditions are one interval test on the read position.
+        u64 fk = 0, rk = 0, fs = 0, rs = 0, preF = kEmptyKey, preR = kEmptyKey, firstF = 0, firstR = 0;
+        unsigned maskF = 0, maskR = 0, word = 0, cnt = 0;
+        unsigned wh1 = 0xFFFFFFFFu, wh2 = 0xFFFFFFFFu, wh3 = 0xFFFFFFFFu, wh4 = 0xFFFFFFFFu, curFull = 0xFFFFFFFFu;   // earlier words ("ambiguous" before the read)
+        unsigned lagK = 0xFFFFFFFFu, lagS = 0xFFFFFFFFu;
         uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-        int lastAmb = -1;
+        int iLo = P.trimStart + K - 1;           // a window ending at base i is reported iff iLo <= i <= iHi:
+        const int iHi = L - P.trimEnd - 1;       //   complete, inside the trimmed range, no ambiguous base in it (iLo moves past those)
+#pragma unroll
+        for (int q = 0; q < W; ++q) { rF[q] = 0; rR[q] = 0; }
 
-        auto fetch = [&](int i) -> unsigned {   // 4-bit code of base i; i advances by one per call
-            if ((i & 7) == 0) {
+        // base i enters: rolling hashes of the k-mer and s-mer ending at i, both strands (seeding.cpp:147-195)
+        auto fetchRoll = [&](int i) {
+            if ((i & 7) == 0) {   // warp-uniform: next 8-base word, and the lagged words the outgoing bases come from
                 if ((i & 31) == 0) { if (i < L) v = src[i >> 5]; }
-                word = v.x; v.x = v.y; v.y = v.z; v.z = v.w;
+                wh4 = wh3; wh3 = wh2; wh2 = wh1; wh1 = curFull;
+                curFull = v.x; v.x = v.y; v.y = v.z; v.z = v.w;
+                word = curFull;
+                constexpr int KA = K / 8, KB = K % 8, SA = S / 8, SB = S % 8;
+                const unsigned whA[6] = {curFull, wh1, wh2, wh3, wh4, 0xFFFFFFFFu};
+                lagK = KB ? __funnelshift_r(whA[KA + 1], whA[KA], 4 * (8 - KB)) : whA[KA];   // nibble p = base 8n + p - K
+                lagS = SB ? __funnelshift_r(whA[SA + 1], whA[SA], 4 * (8 - SB)) : whA[SA];
             }
-            const unsigned c = word & 0xFu;
-            word >>= 4;
-            return c;
-        };
-        auto roll = [&](int i, unsigned code) {
-            const unsigned oldK = (unsigned)((hist2 >> (2 * (K - 1))) & 3ULL) | (((histAmb >> (K - 1)) & 1u) << 2);
-            const unsigned oldS = (unsigned)((hist2 >> (2 * (S - 1))) & 3ULL) | (((histAmb >> (S - 1)) & 1u) << 2);
-            const unsigned tc = code & 7u;
-            fk = rol1(fk) ^ T.fwdOldK[oldK] ^ T.fwdNew[tc];
-            rk = ror1(rk) ^ T.revOld[oldK] ^ T.revNewK[tc];
-            fs = rol1(fs) ^ T.fwdOldS[oldS] ^ T.fwdNew[tc];
-            rs = ror1(rs) ^ T.revOld[oldS] ^ T.revNewS[tc];
-            hist2 = (hist2 << 2) | (u64)(code & 3u);
-            histAmb = (histAmb << 1) | (code >= 4 ? 1u : 0u);
-            if (code >= 4) lastAmb = i;
+            const unsigned code = word & 0xFu, oldK = lagK & 7u, oldS = lagS & 7u, tc = code & 7u;
+            word >>= 4; lagK >>= 4; lagS >>= 4;
+            if (i < L) {
+                fk = rol1(fk) ^ T.fwdOldK[oldK] ^ T.fwdNew[tc];
+                rk = ror1(rk) ^ T.revOld[oldK] ^ T.revNewK[tc];
+                fs = rol1(fs) ^ T.fwdOldS[oldS] ^ T.fwdNew[tc];
+                rs = ror1(rs) ^ T.revOld[oldS] ^ T.revNewS[tc];
+                if (code >= 4) iLo = max(iLo, i + K);
+            }
         };
         // prologue: the first S-1 bases only feed the rolling hashes
 #pragma unroll 1
-        for (int i = 0; i < S - 1 && i < maxL; ++i) {
-            const unsigned code = fetch(i);
-            if (i < L) roll(i, code);
-        }
+        for (int i = 0; i < S - 1 && i < maxL; ++i) fetchRoll(i);
         // main loop: one block of W s-mers per iteration; s-mer index q = i - (S-1), slot j = q mod W
 #pragma unroll 1
         for (int q0 = 0; q0 + S - 1 < maxL; q0 += W) {
@@ -297,27 +303,24 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
             for (int j = 0; j < W; ++j) {
                 const int i = q0 + j + S - 1;
                 if (i < maxL) {   // warp-uniform
-                    const unsigned code = fetch(i);
+                    fetchRoll(i);
                     if (i < L) {
-                        roll(i, code);
+                        // running minimum of the current block; leF: the newest s-mer attains it
+                        bool leF = true, leR = true;
                         if (j == 0) { preF = fs; preR = rs; firstF = fs; firstR = rs; }
-                        else { preF = umin64(preF, fs); preR = umin64(preR, rs); }
-                        if (q0 + j >= W - 1) {
-                            const int pslot = (j + 1 == W) ? 0 : j + 1;
-                            bool fA, rA; u64 mf, mr;
-                            if (pslot == 0) { mf = preF; mr = preR; fA = firstF == preF; rA = firstR == preR; }
-                            else {
-                                const u64 sf = rF[pslot], sr = rR[pslot];
-                                mf = umin64(sf, preF); mr = umin64(sr, preR);
-                                fA = ((maskF >> pslot) & 1u) && sf <= preF;
-                                rA = ((maskR >> pslot) & 1u) && sr <= preR;
-                            }
-                            const bool fsyn = fA || fs == mf, rsyn = rA || rs == mr;
-                            const int pos = i - K + 1;
-                            if ((i - lastAmb >= K) && (fsyn || rsyn) && (fk != rk) && pos >= trimStart && pos <= validEnd) {
-                                dst[cnt] = umin64(fk, rk);
-                                ++cnt;
-                            }
+                        else { leF = fs <= preF; leR = rs <= preR; preF = leF ? fs : preF; preR = leR ? rs : preR; }
+                        // closed syncmer, t == 0: the OLDEST or the NEWEST s-mer of the window attains the window minimum
+                        const int pslot = (j + 1 == W) ? 0 : j + 1;
+                        bool fsyn, rsyn;
+                        if (pslot == 0) { fsyn = leF || firstF == preF; rsyn = leR || firstR == preR; }
+                        else {
+                            const u64 sf = rF[pslot], sr = rR[pslot];   // suffix minima of the previous block from the oldest s-mer on
+                            fsyn = (leF && fs <= sf) || (((maskF >> pslot) & 1u) && sf <= preF);
+                            rsyn = (leR && rs <= sr) || (((maskR >> pslot) & 1u) && sr <= preR);
+                        }
+                        if ((fsyn || rsyn) && i >= iLo && i <= iHi && fk != rk) {
+                            dst[cnt] = umin64(fk, rk);
+                            ++cnt;
                         }
                         rF[j] = fs; rR[j] = rs;
                         if (j == W - 1) {   // block complete: in-place suffix minima + "is its own suffix minimum" masks
@@ -325,8 +328,9 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
 #pragma unroll
                             for (int q = W - 1; q >= 0; --q) {
                                 const u64 x = rF[q], y = rR[q];
-                                a = umin64(a, x); bb = umin64(bb, y);
-                                mF |= (a == x ? 1u : 0u) << q; mR |= (bb == y ? 1u : 0u) << q;
+                                const bool ia = x <= a, ib = y <= bb;
+                                a = ia ? x : a; bb = ib ? y : bb;
+                                mF |= (ia ? 1u : 0u) << q; mR |= (ib ? 1u : 0u) << q;
                                 rF[q] = a; rR[q] = bb;
                             }
                             maskF = mF; maskR = mR;
