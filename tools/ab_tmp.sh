@@ -1,5 +1,3 @@
 set -u
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.readline()); print(d['ms_per_step'], d['stage_ms'], d['e2e']['ms_per_step'], d['kernel_ms'])"
+ncu --set full --clock-control none --import-source on -k "regex:syncmers_fast" --launch-skip 3 -c 1 -f -o gpurun_out/prof_syn python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+ls -la gpurun_out/prof_syn.ncu-rep
