@@ -71,7 +71,7 @@ typedef struct pm_place_params {
     int32_t trim_start;        /* trimStart */
     int32_t trim_end;          /* trimEnd */
     int32_t min_read_support;  /* minReadSupport: -1 = auto (placement.cpp:931-955) */
-    int32_t dedup_reads;       /* dedupReads (PM_ERR_UNSUPPORTED when non-zero, for now) */
+    int32_t dedup_reads;       /* dedupReads: every distinct read string counts once (placement.cpp:1550-1620) */
     int32_t force_leaf;        /* forceLeaf: only leaves are eligible (placement.cpp:794-795) */
     uint32_t skip_node_index;  /* leave-one-out node, PM_NONE = none (placement.hpp:91) */
     double seed_mask_fraction; /* seedMaskFraction; CLI default 0 (main.cpp:1967) */

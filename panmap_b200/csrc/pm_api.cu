@@ -102,6 +102,7 @@ struct pm_workspace {
     bool residentValid = false;  // the device copy of the reads was laid out by pm_reads_upload (not by the sliced pm_place path)
     // table
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
+    DevBuf<unsigned long long> dedupSlots; u64 dedupMask = 0; DevBuf<unsigned char> dupFlag;   // --dedup only
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     // the small per-sample result block lives in ONE device allocation so that it comes back with a single copy:
     // [SampleAcc | SampleScalars | Selection x 5 | first kTieHead tied nodes of every metric]
@@ -235,7 +236,6 @@ PlaceOpts makeOpts(const pm_place_params& p, bool wantMetrics) {
 
 void checkParams(const pm_place_params* p) {
     if (!p) throw std::runtime_error("null params");
-    if (p->dedup_reads) throw Unsupported("dedup_reads is not implemented on the GPU path yet");
     if (p->seed_mask_fraction > 0.0) throw Unsupported("seed_mask_fraction > 0 is not implemented on the GPU path yet");
     if (p->trim_start < 0 || p->trim_end < 0) throw std::runtime_error("negative trim");
 }
@@ -274,6 +274,19 @@ void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n)
     CK(cudaMemcpyAsync(W->blockFirst.p, W->hBlockFirst.p, ((W->nChunks + 255) / 256 + 1) * sizeof(u32), cudaMemcpyHostToDevice, W->st));
 }
 
+// --dedup: (re)size and clear the read set; returns the flag array (null when the option is off)
+unsigned char* prepareDedup(pm_workspace* W, u64 n, const pm_place_params& prm) {
+    if (!prm.dedup_reads || n == 0) return nullptr;
+    if (n >= 0xFFFFFFFFull) throw std::runtime_error("dedup_reads: more than 2^32 reads");
+    u64 cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+    if (W->dedupSlots.n < cap) W->dedupSlots.alloc(cap);
+    W->dedupMask = cap - 1;
+    W->dupFlag.ensure(n + 1);
+    CK(cudaMemsetAsync(W->dedupSlots.p, 0xFF, cap * sizeof(unsigned long long), W->st));
+    return W->dupFlag.p;
+}
+
 // Host buffers -> table, pipelined: the sample is cut into slices of reads; slice i+1 is copied (copy stream) while slice i is
 // packed, seeded and counted (compute stream).  Host-side chunk offsets of a slice are computed just before its copy.
 void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* off, u64 n, const pm_place_params& prm) {
@@ -294,6 +307,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
     CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
     launchTableClear(W->view, W->st);
+    unsigned char* dup = prepareDedup(W, n, prm);
     u64 chunkAcc = 0, win = 0, bfBase = 0;
     for (int sl = 0; sl < nSlices; ++sl) {
         const u64 r0 = nSlices == 1 ? 0 : (u64)((double)n * kCut[sl]), r1 = nSlices == 1 || sl + 1 == nSlices ? n : (u64)((double)n * kCut[sl + 1]);
@@ -318,7 +332,8 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
         CK(cudaEventRecord(W->evCopy[sl], W->stCopy));
         CK(cudaStreamWaitEvent(W->st, W->evCopy[sl], 0));
         launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st);
-        launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st);
+        if (dup) launchDedup(W->reads.p, W->off.p, r0, r1, W->dedupSlots.p, W->dedupMask, dup, W->st);
+        launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, nullptr, dup ? dup + r0 : nullptr);
         bfBase += nBlk + 1;
     }
     W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false;
@@ -331,10 +346,12 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
         launchTableClear(W->view, W->st);
     }
+    unsigned char* dup = prepareDedup(W, W->nReads, prm);
+    if (dup) launchDedup(W->reads.p, W->off.p, 0, W->nReads, W->dedupSlots.p, W->dedupMask, dup, W->st);
     CK(cudaEventRecord(W->evK[0], W->st));
     launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st);
     CK(cudaEventRecord(W->evK[1], W->st));
-    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2]);
+    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup);
     CK(cudaEventRecord(W->evK[3], W->st));
 }
 

@@ -145,6 +145,51 @@ __device__ __forceinline__ void tableInsert(TableSlot* __restrict__ table, u64 m
 }
 
 // ------------------------------------------------------------------------------------------------------
+// --dedup (placement.cpp:1550-1620 with dedupReads): every distinct read STRING counts once.  One warp per read: position-tagged
+// byte hash, open-addressing set of (31-bit tag, read index) claimed with one 64-bit CAS, and a byte-for-byte comparison against
+// the read that holds a slot with the same tag -- the reference compares the raw strings, so case and the exact ambiguity
+// letters matter and the packed codes cannot be used.  Which copy of a duplicated read survives is irrelevant (same seeds).
+// Slices of a sample insert into the same set one after the other, so the decision is global.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dedup_mark(const char* __restrict__ reads, const u64* __restrict__ off, u64 rBegin, u64 rEnd,
+                                                  unsigned long long* slots, u64 mask, unsigned char* __restrict__ dup) {
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 r = rBegin + (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rEnd; r += warpsTotal) {
+        const u64 b = off[r], L = off[r + 1] - b;
+        u64 h = 0;
+        for (u64 i = lane; i < L; i += 32) h += mixKey((u64)(unsigned char)reads[b + i] + (i << 8) + 0x51ED270B1ULL);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) h += shflXorU64(h, d);
+        h = mixKey(h ^ (L * 0x9E3779B97F4A7C15ULL));
+        const u64 tag = (h >> 33) & 0x7FFFFFFFULL;
+        const unsigned long long mine = (tag << 32) | (r & 0xFFFFFFFFULL);
+        u64 s = h & mask;
+        bool isDup = false;
+        for (u64 probe = 0; probe <= mask; ++probe) {
+            unsigned long long cur = 0;
+            if (lane == 0) cur = atomicCAS(&slots[s], ~0ULL, mine);
+            cur = shflU64(cur, 0);
+            if (cur == ~0ULL) break;   // claimed: first read with this string
+            if ((cur >> 32) == tag) {
+                const u64 o = cur & 0xFFFFFFFFULL;
+                const u64 bo = off[o];
+                bool eq = (off[o + 1] - bo) == L;
+                if (eq) for (u64 i = lane; i < L; i += 32) eq = eq && reads[b + i] == reads[bo + i];
+                if (__all_sync(0xffffffffu, eq)) { isDup = true; break; }
+            }
+            s = (s + 1) & mask;
+        }
+        if (lane == 0) dup[r] = isDup ? 1 : 0;
+    }
+}
+void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsigned long long* slots, u64 mask, unsigned char* dup, cudaStream_t st) {
+    if (rEnd <= rBegin) return;
+    u64 g = (rEnd - rBegin + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
+    dedup_mark<<<(unsigned)g, 256, 0, st>>>(reads, off, rBegin, rEnd, slots, mask, dup);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Seeding = two kernels, mirroring the reference's own split:
 //   syncmers_*          seeding::rollingSyncmers (seeding.cpp:47-229): one lane per read, all lanes of a warp at the same
 //                       read position (lock-step, so the block-end pass of the sliding minimum is convergent); each lane
@@ -162,7 +207,8 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
                                                                  const u64* __restrict__ packedOff, const u64* __restrict__ winOff,
                                                                  u64 nReads, SeederParams P, const SeedTables* __restrict__ gT,
                                                                  u64* __restrict__ synBuf, unsigned* __restrict__ synCount,
-                                                                 u64* outHash, unsigned char* outRev, long long* outPos, u64* outCount) {
+                                                                 u64* outHash, unsigned char* outRev, long long* outPos, u64* outCount,
+                                                                 const unsigned char* __restrict__ dup) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
     u64* rings = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables));
@@ -179,6 +225,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
         const u64 b = valid ? off[r] : 0;
         int L = valid ? (int)(off[r + 1] - b) : 0;
         if (L < P.k) L = 0;  // shorter than k: no windows (seeding.cpp:50)
+        if (dup && valid && dup[r]) L = 0;   // --dedup: a byte-identical read was seen before (placement.cpp:1550-1620)
         const u64 pOff = valid ? packedOff[r] : 0;
         const int nCh = (L + 31) >> 5;
         int maxL = L;
@@ -229,7 +276,7 @@ template <int K, int S>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                               const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
                                                               const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
-                                                              unsigned* __restrict__ synCount) {
+                                                              unsigned* __restrict__ synCount, const unsigned char* __restrict__ dup) {
     constexpr int W = K - S + 1;
     static_assert(K >= 8 && K <= 32 && S >= 8 && S < K, "lagged-word addressing assumes 8 <= s < k <= 32");
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -250,6 +297,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         const u64 b = valid ? off[r] : 0;
         int L = valid ? (int)(off[r + 1] - b) : 0;
         if (L < K) L = 0;
+        if (dup && valid && dup[r]) L = 0;   // --dedup: a byte-identical read was seen before
         const u64 pOff = valid ? packedOff[r] : 0;
         const uint4* __restrict__ src = packed + pOff;
         u64* __restrict__ dst = synBuf + pOff * 32;
@@ -507,25 +555,25 @@ static unsigned seedGrid(u64 nReads) {
 }
 template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                       u64* synBuf, unsigned* synCount, cudaStream_t st) {
-    syncmers_fast<K, S><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables), st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount);
+                       u64* synBuf, unsigned* synCount, const unsigned char* dup, cudaStream_t st) {
+    syncmers_fast<K, S><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables), st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup);
 }
 static void launchSyncmers(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                           u64* synBuf, unsigned* synCount, cudaStream_t st) {
-    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, st);
-    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, st);
+                           u64* synBuf, unsigned* synCount, const unsigned char* dup, cudaStream_t st) {
+    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, st);
+    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, st);
     const size_t sm = genericSmemBytes(P);
     cudaFuncSetAttribute(syncmers_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
-                                                                     nullptr, nullptr, nullptr);
+                                                                     nullptr, nullptr, nullptr, dup);
 }
 // reads -> count table: syncmer lists per read, then their seeds into the table.  (Running the two as one kernel, or concurrently
 // on two streams, was measured and is slower: both are limited by the same L1/LSU data pipe and the hashing needs every warp an
 // SM can hold.)
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between) {
+                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between, const unsigned char* dup) {
     if (nReads == 0) return;
-    launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, st);
+    launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, dup, st);
     if (between) cudaEventRecord(between, st);
     launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, st);
 }
@@ -538,9 +586,9 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
         const size_t sm = genericSmemBytes(P);
         cudaFuncSetAttribute(syncmers_generic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         syncmers_generic<1><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr, nullptr,
-                                                                         outHash, outRev, outPos, outCount);
+                                                                         outHash, outRev, outPos, outCount, nullptr);
     } else {
-        launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, st);
+        launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, nullptr, st);
         launchSeedsFromSyncmers<2>(synBuf, synCount, packedOff, winOff, nReads, P.k, P.l, nullptr, 0, nullptr, outHash, outCount, 0, st);
     }
 }

@@ -119,7 +119,10 @@ struct PlaceOpts {
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
                      uint4* packed, cudaStream_t st);
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between = nullptr);
+                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between = nullptr,
+                     const unsigned char* dup = nullptr);
+// --dedup: dup[r] = 1 when a byte-identical read holds the set already; reads [rBegin, rEnd) of the sample, `off` = all offsets
+void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsigned long long* slots, u64 mask, unsigned char* dup, cudaStream_t st);
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
                     const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
                     unsigned char* outRev, long long* outPos, u64* outCount, cudaStream_t st);

@@ -48,7 +48,7 @@ def _place_and_check(idx, reads, params=None, **okw):
     assert res.raw.total_read_seed_frequency == exp["total_frequency"]
     assert res.raw.min_read_support == exp["min_support"]
     th, tc = ws.seed_table()
-    eh, ec = cpu.seed_table(buf, off, idx.k, idx.s, idx.t, idx.l, idx.open, okw.get("trim_start", 0), okw.get("trim_end", 0))
+    eh, ec = cpu.seed_table(buf, off, idx.k, idx.s, idx.t, idx.l, idx.open, okw.get("trim_start", 0), okw.get("trim_end", 0), okw.get("dedup", False))
     keep = tc > 0
     assert np.array_equal(th[keep], eh) and np.array_equal(tc[keep], ec)
     # f64
@@ -70,6 +70,20 @@ def test_place_synthetic_index_with_table_only_reads():
     idx, _, _ = H.synthetic_index(700, rng)
     reads = H.random_reads(rng, 500)
     _place_and_check(idx, reads)
+
+
+def test_place_dedup_counts_every_distinct_read_string_once():
+    """--dedup (placement.cpp:1550-1620): byte-identical reads count once; reads that differ only in case or in the ambiguity
+    letter are different strings for the reference and must both count.  Small and sliced (>= 65536 reads) paths."""
+    rng = np.random.default_rng(8)
+    idx, _, _ = H.synthetic_index(400, rng)
+    base = H.random_reads(rng, 300)
+    reads = base + base[:120] + [r.lower() for r in base[:40]] + [base[7]] * 9 + [b"", b"", b"ACGTN" * 9, b"ACGTR" * 9, b"ACGTN" * 9]
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    _place_and_check(idx, reads, pm.PlaceParams(dedup_reads=1), dedup=True)
+    big = [base[i % 300] for i in range(70000)] + H.random_reads(rng, 500)
+    _place_and_check(idx, big, pm.PlaceParams(dedup_reads=1), dedup=True)
 
 
 def test_place_empty_and_short_reads():
