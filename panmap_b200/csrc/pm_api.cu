@@ -213,6 +213,11 @@ void refreshView(pm_workspace* W) {
     V.tieNode = W->tieNode.p; V.tieCap = W->tieCap; V.tieHead = W->tieHead; V.sel = W->sel.p; V.scalars = W->scalars.p;
 }
 
+// table capacity is kept between 2x and 4x the unique seeds of the previous sample (tighter fits were measured: the insertions
+// lose what the table passes gain)
+static u64 fitLo() { return 4; }
+static u64 fitHi() { return 8; }
+
 void ensureTable(pm_workspace* W, u64 wantCap) {
     u64 cap = 1 << 12;
     while (cap < wantCap) cap <<= 1;
@@ -439,10 +444,10 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaEventRecord(W->ev[0], W->st));
         if (W->tableCap == 0 && inputsResident) ensureTable(W, std::max<u64>(1 << 16, W->totalWindows / 4));
-        else if (W->lastEntries && W->tableCap > (1u << 16) && W->tableCap > 4 * W->lastEntries) {
+        else if (W->lastEntries && W->tableCap > (1u << 16) && W->tableCap > fitHi() * W->lastEntries / 2) {
             // the previous sample filled under a quarter of the slots: every pass over the table is cheaper with a tighter one
             u64 cap = 1 << 16;
-            while (cap < 2 * W->lastEntries) cap <<= 1;
+            while (cap < fitLo() * W->lastEntries / 2) cap <<= 1;
             if (cap < W->tableCap) { W->tableCap = cap; }   // keep the allocation, use a prefix
         }
         refreshView(W);

@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(256) count_seeds(const u64* __restrict__ synBu
                         if (KT > 0) {
 #pragma unroll
                             for (int w = 0; w < (LT > 0 ? LT : 1); ++w) {
-                                const u64 x = __ldg(h + j + w);
+                                const u64 x = __ldcs(h + j + w);   // streaming: the lists must not push the table out of L2
                                 fw ^= rol64(x, (unsigned)((KT * (LT - 1 - w)) & 63));
                                 rw ^= rol64(x, (unsigned)((KT * w) & 63));
                             }
