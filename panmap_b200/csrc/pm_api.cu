@@ -94,7 +94,7 @@ struct pm_index {
 struct pm_workspace {
     pm_index* idx = nullptr;
     cudaStream_t st = nullptr, stCopy = nullptr;
-    cudaEvent_t ev[9]{}, evCopy[8]{}, evK[4]{};   // evK: around pack_reads / syncmers / count_seeds of the resident path
+    cudaEvent_t ev[9]{}, evCopy[12]{}, evK[4]{};   // evK: around pack_reads / syncmers / count_seeds of the resident path
     // inputs
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
@@ -299,9 +299,11 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     const int k = I->F.sp.k;
     if (n && off[0] != 0) throw std::runtime_error("read_offsets[0] must be 0");
     const u64 total = n ? off[n] : 0;
-    // slices shrink towards the end: everything after the last copy (its seeding, then scoring and selection) is exposed latency
-    static const double kCut[8] = {0.0, 0.20, 0.40, 0.58, 0.74, 0.86, 0.94, 1.0};
-    const int nSlices = n >= (1u << 16) ? 7 : 1;
+    // Slice schedule: the host prepares the chunk offsets of slice i while slice i-1 is on the wire, so the first slice is tiny
+    // (its preparation is the only one nothing overlaps) and slices grow by at most 2x; they shrink again towards the end because
+    // everything after the last copy (its seeding, then scoring and selection) is exposed latency.
+    static const double kCut[11] = {0.0, 0.03, 0.09, 0.21, 0.40, 0.58, 0.73, 0.84, 0.91, 0.96, 1.0};
+    const int nSlices = n >= (1u << 16) ? 10 : 1;
     W->nReads = n; W->totalBases = total;
     W->hPackedOff.ensure(n + 1); W->hBlockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 32);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
