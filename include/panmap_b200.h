@@ -48,7 +48,7 @@ typedef struct pm_workspace pm_workspace;   /* per-sample state: stream, read ta
 typedef struct pm_seed_params {
     int32_t k, s, t, l;
     int32_t open; /* 0 = closed syncmers */
-    int32_t hpc;  /* homopolymer-compressed index: reads must be compressed by the caller (seeding.cpp:286-306) */
+    int32_t hpc;  /* homopolymer-compressed index: pm_place* collapses the reads on the device (placement.cpp:1145-1165, seeding.cpp:286-306) */
 } pm_seed_params;
 
 /* Flat view of the per-node seed-delta index (index_lite.capnp LiteIndex: seedChangeHashes /

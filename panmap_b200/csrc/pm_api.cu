@@ -103,6 +103,7 @@ struct pm_workspace {
     // table
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
     DevBuf<unsigned long long> dedupSlots; u64 dedupMask = 0; DevBuf<unsigned char> dupFlag;   // --dedup only
+    DevBuf<u64> endOff;                                                                        // hpc indexes only
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     // the small per-sample result block lives in ONE device allocation so that it comes back with a single copy:
     // [SampleAcc | SampleScalars | Selection x 5 | first kTieHead tied nodes of every metric]
@@ -315,6 +316,8 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
     launchTableClear(W->view, W->st);
     unsigned char* dup = prepareDedup(W, n, prm);
+    const bool hpc = I->F.sp.hpc != 0;
+    if (hpc) W->endOff.ensure(n + 1);
     u64 chunkAcc = 0, win = 0, bfBase = 0;
     for (int sl = 0; sl < nSlices; ++sl) {
         const u64 r0 = nSlices == 1 ? 0 : (u64)((double)n * kCut[sl]), r1 = nSlices == 1 || sl + 1 == nSlices ? n : (u64)((double)n * kCut[sl + 1]);
@@ -338,9 +341,11 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
         CK(cudaMemcpyAsync(W->blockFirst.p + bfBase, W->hBlockFirst.p + bfBase, (nBlk + 1) * sizeof(u32), cudaMemcpyHostToDevice, W->stCopy));
         CK(cudaEventRecord(W->evCopy[sl], W->stCopy));
         CK(cudaStreamWaitEvent(W->st, W->evCopy[sl], 0));
-        launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st);
-        if (dup) launchDedup(W->reads.p, W->off.p, r0, r1, W->dedupSlots.p, W->dedupMask, dup, W->st);
-        launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, nullptr, dup ? dup + r0 : nullptr);
+        if (hpc) launchHpcCompress(W->reads.p, W->off.p + r0, r1 - r0, W->endOff.p + r0, W->st);
+        launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st, hpc ? W->endOff.p + r0 : nullptr);
+        if (dup) launchDedup(W->reads.p, W->off.p, r0, r1, W->dedupSlots.p, W->dedupMask, dup, W->st, hpc ? W->endOff.p : nullptr);
+        launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, nullptr, dup ? dup + r0 : nullptr,
+                        hpc ? W->endOff.p + r0 : nullptr);
         bfBase += nBlk + 1;
     }
     W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false;
@@ -354,11 +359,17 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         launchTableClear(W->view, W->st);
     }
     unsigned char* dup = prepareDedup(W, W->nReads, prm);
-    if (dup) launchDedup(W->reads.p, W->off.p, 0, W->nReads, W->dedupSlots.p, W->dedupMask, dup, W->st);
+    const u64* endOff = nullptr;
+    if (I->F.sp.hpc) {   // in place and idempotent: resident reads may be placed many times
+        W->endOff.ensure(W->nReads + 1);
+        launchHpcCompress(W->reads.p, W->off.p, W->nReads, W->endOff.p, W->st);
+        endOff = W->endOff.p;
+    }
+    if (dup) launchDedup(W->reads.p, W->off.p, 0, W->nReads, W->dedupSlots.p, W->dedupMask, dup, W->st, endOff);
     CK(cudaEventRecord(W->evK[0], W->st));
-    launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st);
+    launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st, endOff);
     CK(cudaEventRecord(W->evK[1], W->st));
-    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup);
+    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup, endOff);
     CK(cudaEventRecord(W->evK[3], W->st));
 }
 

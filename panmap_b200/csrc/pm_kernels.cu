@@ -57,9 +57,10 @@ __device__ __forceinline__ long long warpSumLL(long long v) {
 // segments, so the lines are shared through L1) and realigned with funnel shifts; base -> code via a shared 256-byte table.
 __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads, const u64* __restrict__ off,
                                                   const u64* __restrict__ packedOff, const u32* __restrict__ blockFirst, u64 nReads,
-                                                  u64 gBase, u64 nChunks, uint4* __restrict__ packed) {
+                                                  u64 gBase, u64 nChunks, uint4* __restrict__ packed, const u64* __restrict__ endOff) {
     __shared__ u64 sPO[258];
     __shared__ u64 sOff[258];
+    __shared__ u64 sEnd[258];
     __shared__ unsigned char sLut[256];
     __shared__ u64 sFirst;
     const u64 g0 = gBase + (u64)blockIdx.x * 256;   // gBase: first chunk of the read slice this launch covers
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads
         const u64 r = rFirst + i;
         sPO[i] = r <= nReads ? __ldg(&packedOff[r]) : ~0ULL;
         sOff[i] = r <= nReads ? __ldg(&off[r]) : 0;
+        if (endOff) sEnd[i] = r < nReads ? __ldg(&endOff[r]) : 0;   // homopolymer-compressed reads end before the next one begins
     }
     __syncthreads();
     const u64 g = g0 + threadIdx.x;
@@ -88,11 +90,11 @@ __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads
             const u64 mid = (glo + ghi) >> 1;
             if (__ldg(&packedOff[mid]) <= g) glo = mid; else ghi = mid;
         }
-        c = g - __ldg(&packedOff[glo]); src = __ldg(&off[glo]) + 32 * c; e = __ldg(&off[glo + 1]);
+        c = g - __ldg(&packedOff[glo]); src = __ldg(&off[glo]) + 32 * c; e = endOff ? __ldg(&endOff[glo]) : __ldg(&off[glo + 1]);
     } else {
-        c = g - sPO[lo]; src = sOff[lo] + 32 * c; e = sOff[lo + 1];
+        c = g - sPO[lo]; src = sOff[lo] + 32 * c; e = endOff ? sEnd[lo] : sOff[lo + 1];
     }
-    const int n = (int)((e - src) < 32 ? (e - src) : 32);
+    const int n = e <= src ? 0 : (int)((e - src) < 32 ? (e - src) : 32);
     const unsigned* __restrict__ wsrc = reinterpret_cast<const unsigned*>(reads + (src & ~3ULL));
     const unsigned sh = (unsigned)(src & 3ULL) * 8u;
     unsigned x[9];
@@ -118,10 +120,45 @@ __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads
 }
 
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
-                     uint4* packed, cudaStream_t st) {
+                     uint4* packed, cudaStream_t st, const u64* endOff) {
     if (nChunks == 0) return;
     const unsigned grid = (unsigned)((nChunks + 255) / 256);
-    pack_reads<<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed);
+    pack_reads<<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, endOff);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Homopolymer compression of the reads when the index was built with --hpc (placement.cpp:1145-1165, seeding::hpcCompress,
+// seeding.cpp:286-306): a base is dropped when it equals its predecessor ignoring case.  One warp per read, in place inside the
+// read's own byte range (the write position never overtakes the read position); endOff[r] = one past the last kept byte.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hpc_compress(char* __restrict__ reads, const u64* __restrict__ off, u64 nReads, u64* __restrict__ endOff) {
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nReads; r += warpsTotal) {
+        const u64 b = off[r], L = off[r + 1] - b;
+        u64 written = 0;
+        int prevUp = -1;   // upper-cased last byte of the previous window
+        for (u64 i0 = 0; i0 < L; i0 += 32) {
+            const u64 i = i0 + lane;
+            const int c = i < L ? (int)(unsigned char)reads[b + i] : -2;
+            const int up = (c >= 'a' && c <= 'z') ? c - 32 : c;
+            int before = __shfl_up_sync(0xffffffffu, up, 1);
+            if (lane == 0) before = prevUp;
+            const bool keep = i < L && up != before;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();
+            if (keep) reads[b + written + __popc(m & ((1u << lane) - 1u))] = (char)c;
+            __syncwarp();
+            written += __popc(m);
+            prevUp = __shfl_sync(0xffffffffu, up, 31);
+        }
+        if (lane == 0) endOff[r] = b + written;
+    }
+}
+void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st) {
+    if (nReads == 0) return;
+    u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
+    hpc_compress<<<(unsigned)g, 256, 0, st>>>(reads, off, nReads, endOff);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -152,11 +189,12 @@ __device__ __forceinline__ void tableInsert(TableSlot* __restrict__ table, u64 m
 // Slices of a sample insert into the same set one after the other, so the decision is global.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dedup_mark(const char* __restrict__ reads, const u64* __restrict__ off, u64 rBegin, u64 rEnd,
-                                                  unsigned long long* slots, u64 mask, unsigned char* __restrict__ dup) {
+                                                  unsigned long long* slots, u64 mask, unsigned char* __restrict__ dup,
+                                                  const u64* __restrict__ endOff) {
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
     for (u64 r = rBegin + (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rEnd; r += warpsTotal) {
-        const u64 b = off[r], L = off[r + 1] - b;
+        const u64 b = off[r], L = (endOff ? endOff[r] : off[r + 1]) - b;
         u64 h = 0;
         for (u64 i = lane; i < L; i += 32) h += mixKey((u64)(unsigned char)reads[b + i] + (i << 8) + 0x51ED270B1ULL);
 #pragma unroll
@@ -174,7 +212,7 @@ __global__ void __launch_bounds__(256) dedup_mark(const char* __restrict__ reads
             if ((cur >> 32) == tag) {
                 const u64 o = cur & 0xFFFFFFFFULL;
                 const u64 bo = off[o];
-                bool eq = (off[o + 1] - bo) == L;
+                bool eq = ((endOff ? endOff[o] : off[o + 1]) - bo) == L;
                 if (eq) for (u64 i = lane; i < L; i += 32) eq = eq && reads[b + i] == reads[bo + i];
                 if (__all_sync(0xffffffffu, eq)) { isDup = true; break; }
             }
@@ -183,10 +221,11 @@ __global__ void __launch_bounds__(256) dedup_mark(const char* __restrict__ reads
         if (lane == 0) dup[r] = isDup ? 1 : 0;
     }
 }
-void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsigned long long* slots, u64 mask, unsigned char* dup, cudaStream_t st) {
+void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsigned long long* slots, u64 mask, unsigned char* dup, cudaStream_t st,
+                 const u64* endOff) {
     if (rEnd <= rBegin) return;
     u64 g = (rEnd - rBegin + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
-    dedup_mark<<<(unsigned)g, 256, 0, st>>>(reads, off, rBegin, rEnd, slots, mask, dup);
+    dedup_mark<<<(unsigned)g, 256, 0, st>>>(reads, off, rBegin, rEnd, slots, mask, dup, endOff);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -208,7 +247,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
                                                                  u64 nReads, SeederParams P, const SeedTables* __restrict__ gT,
                                                                  u64* __restrict__ synBuf, unsigned* __restrict__ synCount,
                                                                  u64* outHash, unsigned char* outRev, long long* outPos, u64* outCount,
-                                                                 const unsigned char* __restrict__ dup) {
+                                                                 const unsigned char* __restrict__ dup, const u64* __restrict__ endOff) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
     u64* rings = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables));
@@ -223,7 +262,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
         const u64 r = r0 + lane;
         const bool valid = r < nReads;
         const u64 b = valid ? off[r] : 0;
-        int L = valid ? (int)(off[r + 1] - b) : 0;
+        int L = valid ? (int)((endOff ? endOff[r] : off[r + 1]) - b) : 0;
         if (L < P.k) L = 0;  // shorter than k: no windows (seeding.cpp:50)
         if (dup && valid && dup[r]) L = 0;   // --dedup: a byte-identical read was seen before (placement.cpp:1550-1620)
         const u64 pOff = valid ? packedOff[r] : 0;
@@ -276,7 +315,8 @@ template <int K, int S>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                               const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
                                                               const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
-                                                              unsigned* __restrict__ synCount, const unsigned char* __restrict__ dup) {
+                                                              unsigned* __restrict__ synCount, const unsigned char* __restrict__ dup,
+                                                              const u64* __restrict__ endOff) {
     constexpr int W = K - S + 1;
     static_assert(K >= 8 && K <= 32 && S >= 8 && S < K, "lagged-word addressing assumes 8 <= s < k <= 32");
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -295,7 +335,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         const u64 r = r0 + lane;
         const bool valid = r < nReads;
         const u64 b = valid ? off[r] : 0;
-        int L = valid ? (int)(off[r + 1] - b) : 0;
+        int L = valid ? (int)((endOff ? endOff[r] : off[r + 1]) - b) : 0;
         if (L < K) L = 0;
         if (dup && valid && dup[r]) L = 0;   // --dedup: a byte-identical read was seen before
         const u64 pOff = valid ? packedOff[r] : 0;
@@ -555,25 +595,26 @@ static unsigned seedGrid(u64 nReads) {
 }
 template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                       u64* synBuf, unsigned* synCount, const unsigned char* dup, cudaStream_t st) {
-    syncmers_fast<K, S><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables), st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup);
+                       u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, cudaStream_t st) {
+    syncmers_fast<K, S><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables), st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff);
 }
 static void launchSyncmers(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                           u64* synBuf, unsigned* synCount, const unsigned char* dup, cudaStream_t st) {
-    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, st);
-    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, st);
+                           u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, cudaStream_t st) {
+    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, st);
+    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, st);
     const size_t sm = genericSmemBytes(P);
     cudaFuncSetAttribute(syncmers_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
-                                                                     nullptr, nullptr, nullptr, dup);
+                                                                     nullptr, nullptr, nullptr, dup, endOff);
 }
 // reads -> count table: syncmer lists per read, then their seeds into the table.  (Running the two as one kernel, or concurrently
 // on two streams, was measured and is slower: both are limited by the same L1/LSU data pipe and the hashing needs every warp an
 // SM can hold.)
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
-                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between, const unsigned char* dup) {
+                     const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between, const unsigned char* dup,
+                     const u64* endOff) {
     if (nReads == 0) return;
-    launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, dup, st);
+    launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, dup, endOff, st);
     if (between) cudaEventRecord(between, st);
     launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, st);
 }
@@ -586,9 +627,9 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
         const size_t sm = genericSmemBytes(P);
         cudaFuncSetAttribute(syncmers_generic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         syncmers_generic<1><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr, nullptr,
-                                                                         outHash, outRev, outPos, outCount, nullptr);
+                                                                         outHash, outRev, outPos, outCount, nullptr, nullptr);
     } else {
-        launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, nullptr, st);
+        launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, nullptr, nullptr, st);
         launchSeedsFromSyncmers<2>(synBuf, synCount, packedOff, winOff, nReads, P.k, P.l, nullptr, 0, nullptr, outHash, outCount, 0, st);
     }
 }

@@ -116,13 +116,16 @@ struct PlaceOpts {
 };
 
 // launches (all asynchronous on `st`)
+// endOff (optional, everywhere below): end of read r when it is shorter than off[r+1] - off[r] (homopolymer-compressed in place)
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
-                     uint4* packed, cudaStream_t st);
+                     uint4* packed, cudaStream_t st, const u64* endOff = nullptr);
+void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st);
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between = nullptr,
-                     const unsigned char* dup = nullptr);
+                     const unsigned char* dup = nullptr, const u64* endOff = nullptr);
 // --dedup: dup[r] = 1 when a byte-identical read holds the set already; reads [rBegin, rEnd) of the sample, `off` = all offsets
-void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsigned long long* slots, u64 mask, unsigned char* dup, cudaStream_t st);
+void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsigned long long* slots, u64 mask, unsigned char* dup, cudaStream_t st,
+                 const u64* endOff = nullptr);
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
                     const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
                     unsigned char* outRev, long long* outPos, u64* outCount, cudaStream_t st);

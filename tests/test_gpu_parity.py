@@ -86,6 +86,47 @@ def test_place_dedup_counts_every_distinct_read_string_once():
     _place_and_check(idx, big, pm.PlaceParams(dedup_reads=1), dedup=True)
 
 
+def _hpc(seq):
+    """seeding::hpcCompress (seeding.cpp:286-306): drop a base that equals its predecessor ignoring case"""
+    out = bytearray()
+    for i, c in enumerate(seq):
+        if i == 0 or bytes([c]).upper() != bytes([seq[i - 1]]).upper():
+            out.append(c)
+    return bytes(out)
+
+
+def test_place_hpc_index_compresses_reads_on_the_device():
+    """index built with --hpc (placement.cpp:1145-1165): the reads are homopolymer-compressed before seeding; also with --dedup,
+    which then compares the compressed strings"""
+    rng = np.random.default_rng(12)
+    idx, _, _ = H.synthetic_index(300, rng)
+    raw = []
+    for r in H.random_reads(rng, 400, lo=20, hi=200):
+        a = bytearray()
+        for c in r:                      # stretch runs so that compression changes most reads
+            a += bytes([c]) * int(rng.choice([1, 1, 1, 2, 3, 5]))
+        raw.append(bytes(a))
+    raw += [b"", b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", b"aAcCgGtTnN" * 12, raw[3], raw[3].lower()]
+    comp = [_hpc(r) for r in raw]
+    for dedup in (0, 1):
+        buf, off = pm.pack_reads(raw)
+        host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open, hpc=1)
+        ws = pm.Workspace(pm.Index(host))
+        res = ws.place(buf, off, pm.PlaceParams(dedup_reads=dedup))
+        cbuf, coff = pm.pack_reads(comp)
+        exp = cpu.place(cbuf, coff, idx, want_scores=True, dedup=bool(dedup))
+        assert res.raw.unique_seeds == exp["unique_seeds"] and res.raw.read_unique_seed_count == exp["kept"]
+        assert res.raw.total_read_seed_frequency == exp["total_frequency"]
+        th, tc = ws.seed_table()
+        eh, ec = cpu.seed_table(cbuf, coff, idx.k, idx.s, idx.t, idx.l, idx.open, 0, 0, bool(dedup))
+        assert np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec)
+        assert H.relerr(ws.node_scores(), exp["scores"]).max() < RTOL
+        for m, name in enumerate(pm.METRICS):
+            assert res.best_index[name] == exp["best_index"][m] and np.array_equal(res.tied[name], exp["tied"][m])
+        res2 = ws.place(buf, off, pm.PlaceParams(dedup_reads=dedup))      # in-place compression is idempotent across calls
+        assert res2.raw.unique_seeds == res.raw.unique_seeds and res2.best_index == res.best_index
+
+
 def test_place_empty_and_short_reads():
     rng = np.random.default_rng(6)
     idx, _, _ = H.synthetic_index(50, rng)
