@@ -139,3 +139,12 @@ def place(reads, offsets, idx, trim_start=0, trim_end=0, dedup=False, min_read_s
     return dict(best_score=best, best_index=bidx, tied=[tied[m, :tcount[m]].copy() for m in range(5)], scores=scores,
                 unique_seeds=int(stats[0]), min_support=int(stats[1]), kept=int(stats[2]), magnitude=stats[3], log_sum=stats[4],
                 wc_denominator=stats[5], total_frequency=int(stats[6]))
+
+
+def hpc_compress(seq):
+    """seeding::hpcCompress (seeding.cpp:286-306): a base is dropped when it equals its predecessor ignoring case (std::toupper)."""
+    out = bytearray()
+    for i, c in enumerate(seq):
+        if i == 0 or bytes([c]).upper() != bytes([seq[i - 1]]).upper():
+            out.append(c)
+    return bytes(out)

@@ -149,6 +149,7 @@ def write_index(path, idx):
     o = np.ascontiguousarray(idx.offsets, np.uint64); pi = np.ascontiguousarray(idx.parent_index, np.uint32)
     f = lib().ref_write_index
     f.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64] + [C.c_int] * 5
-    rc = f(os.fsencode(path), _p(h), _p(p), _p(c), _p(o), _p(pi), pi.size, h.size, idx.k, idx.s, idx.t, idx.l, int(idx.open))
+    rc = f(os.fsencode(path), _p(h), _p(p), _p(c), _p(o), _p(pi), pi.size, h.size, idx.k, idx.s, idx.t, idx.l,
+           int(idx.open) | (int(getattr(idx, "hpc", 0)) << 1))
     if rc != 0:
         raise RuntimeError(lib().ref_last_error().decode())

@@ -230,11 +230,12 @@ int64_t ref_select_chain(const uint32_t* order, const double* score, int64_t n, 
 // flat arrays -> a real uncompressed .idx (LiteIndex capnp message + PMI1 header, as IndexBuilder::writeIndex lays it out),
 // so the reference's placeLite can consume synthetic indexes byte-for-byte identical to what the GPU path is given
 int ref_write_index(const char* path, const uint64_t* hash, const int16_t* par, const int16_t* chi, const uint64_t* off,
-                    const uint32_t* parent, uint64_t N, uint64_t D, int k, int s, int t, int l, int open) {
+                    const uint32_t* parent, uint64_t N, uint64_t D, int k, int s, int t, int l, int openAndHpc) {
+    const int open = openAndHpc & 1; const bool hpc = (openAndHpc >> 1) & 1;   // bit 1: index built with --hpc
     try {
         capnp::MallocMessageBuilder msg;
         auto idx = msg.initRoot<LiteIndex>();
-        idx.setK(k); idx.setS(s); idx.setT(t); idx.setL(l); idx.setOpen(open != 0); idx.setHpc(false);
+        idx.setK(k); idx.setS(s); idx.setT(t); idx.setL(l); idx.setOpen(open != 0); idx.setHpc(hpc);
         idx.setFormatVersion(panmapUtils::INDEX_FORMAT_VERSION);
         auto tree = idx.initLiteTree();
         auto nodes = tree.initLiteNodes(static_cast<unsigned>(N));
@@ -254,7 +255,7 @@ int ref_write_index(const char* path, const uint64_t* hash, const int16_t* par, 
         auto O = idx.initNodeChangeOffsets(static_cast<unsigned>(N + 1));
         for (uint64_t i = 0; i <= N; ++i) O.set(i, off[i]);
         kj::Array<capnp::word> flat = capnp::messageToFlatArray(msg);
-        index_single_mode::IndexParamsHeader ph; ph.k = k; ph.s = s; ph.t = t; ph.l = l; ph.hpc = false; ph.open = open != 0; ph.uncompressed = true;
+        index_single_mode::IndexParamsHeader ph; ph.k = k; ph.s = s; ph.t = t; ph.l = l; ph.hpc = hpc; ph.open = open != 0; ph.uncompressed = true;
         const auto header = index_single_mode::encodeIndexHeader(ph);
         std::ofstream out(path, std::ios::binary | std::ios::trunc);
         out.write(reinterpret_cast<const char*>(header.data()), header.size());

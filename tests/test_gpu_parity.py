@@ -86,15 +86,6 @@ def test_place_dedup_counts_every_distinct_read_string_once():
     _place_and_check(idx, big, pm.PlaceParams(dedup_reads=1), dedup=True)
 
 
-def _hpc(seq):
-    """seeding::hpcCompress (seeding.cpp:286-306): drop a base that equals its predecessor ignoring case"""
-    out = bytearray()
-    for i, c in enumerate(seq):
-        if i == 0 or bytes([c]).upper() != bytes([seq[i - 1]]).upper():
-            out.append(c)
-    return bytes(out)
-
-
 def test_place_hpc_index_compresses_reads_on_the_device():
     """index built with --hpc (placement.cpp:1145-1165): the reads are homopolymer-compressed before seeding; also with --dedup,
     which then compares the compressed strings"""
@@ -107,7 +98,7 @@ def test_place_hpc_index_compresses_reads_on_the_device():
             a += bytes([c]) * int(rng.choice([1, 1, 1, 2, 3, 5]))
         raw.append(bytes(a))
     raw += [b"", b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", b"aAcCgGtTnN" * 12, raw[3], raw[3].lower()]
-    comp = [_hpc(r) for r in raw]
+    comp = [cpu.hpc_compress(r) for r in raw]
     for dedup in (0, 1):
         buf, off = pm.pack_reads(raw)
         host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open, hpc=1)
@@ -306,3 +297,43 @@ def test_batch_mode_concurrent_workspaces_share_one_index():
             assert out[j].best_index[name] == serial[j].best_index[name] == exp["best_index"][m]
             assert out[j].best_score[name] == serial[j].best_score[name]
             assert np.array_equal(out[j].tied[name], exp["tied"][m])
+
+
+def test_full_size_sample_matches_oracle_and_is_shard_and_call_invariant():
+    """BASELINE configs[2] at full size (1M-node tree, 15.6M deltas, 1M x 150 bp reads; the workload bench.py times): the whole
+    result against the CPU oracle -- integers, table, best nodes and tie lists bit-exact, all 5M scores to 1e-12 -- plus the
+    size-independent properties: a node without deltas scores exactly like its parent, the truth leaf is the placement, a second
+    call and a 3-shard index give bit-identical scores."""
+    from tools.synth import synth
+    S = synth.generate(1_000_000, 30_000, 1.0, 1_000_000, read_len=150, seed=0)
+    host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
+    index = pm.Index(host)
+    ws = pm.Workspace(index)
+    res = ws.place(S.reads, S.read_offsets)
+    sc = ws.node_scores()
+    exp = cpu.place(S.reads, S.read_offsets, S, want_scores=True)
+    assert res.raw.unique_seeds == exp["unique_seeds"] and res.raw.read_unique_seed_count == exp["kept"]
+    assert res.raw.total_read_seed_frequency == exp["total_frequency"] and res.raw.min_read_support == exp["min_support"]
+    assert H.relerr(sc, exp["scores"]).max() < RTOL
+    for m, name in enumerate(pm.METRICS):
+        assert res.best_index[name] == exp["best_index"][m], name
+        assert np.array_equal(res.tied[name], exp["tied"][m]), name
+        assert H.relerr(res.best_score[name], exp["best_score"][m]).max() < RTOL
+    assert S.truth in res.tied["log_raw"] and S.truth in res.tied["log_containment"]
+    # exact prefix: nodes without deltas repeat their parent's scores bit for bit
+    nd = np.diff(S.offsets.astype(np.int64))
+    z = np.nonzero(nd[1:] == 0)[0] + 1
+    assert z.size > 1000 and np.array_equal(sc[z], sc[S.parent_index[z]])
+    # determinism across calls (atomics order must not matter) and across shardings of the index
+    ws.place(S.reads, S.read_offsets)
+    assert np.array_equal(ws.node_scores(), sc)
+    del ws, index
+    got = np.zeros_like(sc)
+    for sh in range(3):
+        ix = pm.Index(host, shard=sh, n_shards=3)
+        w2 = pm.Workspace(ix)
+        w2.place(S.reads, S.read_offsets)
+        b, e = ix.shard_range()
+        got[b:e] = w2.node_scores()[b:e]
+        del w2, ix
+    assert np.array_equal(got, sc)

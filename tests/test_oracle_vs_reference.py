@@ -75,3 +75,51 @@ def test_place_matches_reference_on_synthetic_genome_index():
         assert H.relerr(o["best_score"], r["best_score"]).max() < 1e-12
         eh, ec = cpu.seed_table(S.reads, S.read_offsets, k, s, 0, l)
         assert np.array_equal(eh, r["table_hash"]) and np.array_equal(ec, r["table_count"])
+
+
+def _fastq(path, reads):
+    with open(path, "wb") as f:
+        for i, r in enumerate(reads):
+            f.write(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)))
+
+
+def test_dedup_trim_force_leaf_and_hpc_match_reference_placeLite():
+    """non-default options of the path against the reference's own placeLite: --dedup (placement.cpp:1550-1620), trims, --force-leaf,
+    and an index flagged hpc (reads are homopolymer-compressed first, placement.cpp:1145-1165)"""
+    from tools.synth import synth
+    rng = np.random.default_rng(21)
+    S = synth.generate(1200, 6000, 1.5, 3000, k=19, s=8, l=3, seed=5)
+    off = S.read_offsets.astype(np.int64); buf = S.reads.tobytes()
+    reads = [buf[off[i]:off[i + 1]] for i in range(3000)]
+    reads = reads + reads[:700] + [r.lower() for r in reads[:50]]            # duplicates, and case variants that are NOT duplicates
+    reads = [reads[i] for i in rng.permutation(len(reads))]
+    stretched = [b"".join(bytes([c]) * int(rng.choice([1, 1, 2, 3])) for c in r) for r in reads[:1500]]
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "s.idx"); ref.write_index(p, S)
+        fq = os.path.join(td, "r.fastq"); _fastq(fq, reads)
+        R = ref.RefIndex(p)
+        import panmap_b200 as pm
+        rb, ro = pm.pack_reads(reads)
+        for kw, okw in [(dict(dedup=True), dict(dedup=True)), (dict(trim_start=6, trim_end=11), dict(trim_start=6, trim_end=11)),
+                        (dict(force_leaf=True, dedup=True), dict(force_leaf=True, dedup=True))]:
+            r = R.place(fq, **kw)
+            o = cpu.place(rb, ro, S, **okw)
+            assert np.array_equal(o["best_index"], r["best_index"]), kw
+            assert all(np.array_equal(o["tied"][m], r["tied"][m]) for m in range(5)), kw
+            assert o["kept"] == r["kept"] and o["unique_seeds"] == r["unique_seeds"] and o["total_frequency"] == r["total_frequency"], kw
+            assert H.relerr(o["best_score"], r["best_score"]).max() < 1e-12
+        R.close()
+        S.hpc = 1
+        ph = os.path.join(td, "h.idx"); ref.write_index(ph, S)
+        S.hpc = 0
+        fqh = os.path.join(td, "h.fastq"); _fastq(fqh, stretched)
+        R = ref.RefIndex(ph)
+        r = R.place(fqh)
+        R.close()
+        cb, co = pm.pack_reads([cpu.hpc_compress(x) for x in stretched])
+        o = cpu.place(cb, co, S)
+        assert np.array_equal(o["best_index"], r["best_index"])
+        assert all(np.array_equal(o["tied"][m], r["tied"][m]) for m in range(5))
+        assert o["kept"] == r["kept"] and o["unique_seeds"] == r["unique_seeds"] and o["total_frequency"] == r["total_frequency"]
+        eh, ec = cpu.seed_table(cb, co, 19, 8, 0, 3)
+        assert np.array_equal(eh, r["table_hash"]) and np.array_equal(ec, r["table_count"])
