@@ -1117,8 +1117,7 @@ void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st) {
     const u32 per = (u32)((I.nDeltaChunks + warps - 1) / warps);
     const u64 grid = ((I.nDeltaChunks + per - 1) / per + wpb - 1) / wpb;
     const size_t sm = (size_t)kHotIds * sizeof(long long);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(node_deltas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); attr = true; }
+    cudaFuncSetAttribute(node_deltas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   // per device: set on every launch (cheap)
     node_deltas<<<(unsigned)grid, kK1Threads, sm, st>>>(I, W, per);
 }
 

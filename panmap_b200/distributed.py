@@ -97,6 +97,8 @@ def place_sharded(ws, reads, offsets, total_reads, params, device=None, group=No
     Returns the same Placement on every rank (== the single-GPU result)."""
     from .api import METRICS
     import os, time
+    if getattr(params, "dedup_reads", 0):
+        raise ValueError("dedup_reads needs the whole sample on one GPU: duplicates across the per-rank read shards would go unseen")
     trace = os.environ.get("PM_TRACE")
     tt = [time.perf_counter()]
     def mark():
