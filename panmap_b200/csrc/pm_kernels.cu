@@ -1256,7 +1256,7 @@ __device__ __forceinline__ Seg3 blockInclusiveScan(Seg3 v, SegRec* sWarp) {
 constexpr int kChainSmem = 256;   // ancestor chains up to this length are kept in shared memory
 constexpr int kK2Per = kTileNodesK2 / 256;
 
-__global__ void __launch_bounds__(256) prefix_scores(DevIndexView I, WorkspaceView W, PlaceOpts O) {
+__global__ void __launch_bounds__(256, 4) prefix_scores(DevIndexView I, WorkspaceView W, PlaceOpts O) {
     __shared__ long long sA[kTileNodesK2];   // diff, low limb: sum of the low 32-bit pieces
     __shared__ long long sB[kTileNodesK2];   // diff, upper limb: sum of (value >> 32)
     __shared__ int sC[kTileNodesK2];         // diff, count
@@ -1340,24 +1340,36 @@ __global__ void __launch_bounds__(256) prefix_scores(DevIndexView I, WorkspaceVi
     const Seg3 incl = blockInclusiveScan(mine, sWarp);
     Seg3 run = s3Sub(incl, mine);
     const SampleScalars S = *W.scalars;
+    double out[kK2Per * 5];   // the thread's 4 nodes are 160 contiguous bytes of the score array
 #pragma unroll
     for (int q = 0; q < kK2Per; ++q) {
         const u32 w = w0 + q;
+#pragma unroll
+        for (int m = 0; m < 5; ++m) out[5 * q + m] = 0.0;
         if (w < a1) {
             run = s3Add(run, d[q]);
             double num[5];
             const u32 ne = I.nGenNodes ? __ldg(&I.evIdx[w]) : 0u;
             if (ne) { const Acc5 g = accLoad(W.evPrefix + (size_t)(ne - 1) * kGenWords); nodeNumerators(run.lo, run.hi, run.cnt, &g, I.ln2, num); }
             else nodeNumerators(run.lo, run.hi, run.cnt, nullptr, I.ln2, num);
-            double sc[5];
-            nodeScores(num[0], num[1], num[2], num[3], num[4], I.gMag[w], S, sc);
-            double* o = W.scores + (size_t)w * 5;
-            o[0] = sc[0]; o[1] = sc[1]; o[2] = sc[2]; o[3] = sc[3]; o[4] = sc[4];
+            nodeScores(num[0], num[1], num[2], num[3], num[4], I.gMag[w], S, out + 5 * q);
             if (W.metrics) {
                 double* m = W.metrics + (size_t)w * 5;
                 m[0] = num[0]; m[1] = num[1]; m[2] = num[2]; m[3] = num[3]; m[4] = num[4];
             }
         }
+    }
+    double* o = W.scores + (size_t)w0 * 5;
+    if (w0 + kK2Per <= a1 && (w0 & 1u) == 0) {   // 16-byte aligned: ten 16-byte stores instead of twenty 8-byte ones
+#pragma unroll
+        for (int i = 0; i < kK2Per * 5 / 2; ++i) reinterpret_cast<double2*>(o)[i] = make_double2(out[2 * i], out[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < kK2Per; ++q)
+            if (w0 + q < a1) {
+#pragma unroll
+                for (int m = 0; m < 5; ++m) o[5 * q + m] = out[5 * q + m];
+            }
     }
 }
 void launchPrefixScores(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st) {
