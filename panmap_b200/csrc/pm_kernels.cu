@@ -55,12 +55,13 @@ __device__ __forceinline__ long long warpSumLL(long long v) {
 // chunk/byte offsets of the <= 257 reads it can touch in shared memory, and every thread then locates its read there.
 // Source bytes are fetched as nine aligned 32-bit words per thread (neighbouring threads read neighbouring 32-byte
 // segments, so the lines are shared through L1) and realigned with funnel shifts; base -> code via a shared 256-byte table.
+template <bool HAS_END>   // HAS_END: reads were homopolymer-compressed in place, endOff[r] is where read r now ends
 __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads, const u64* __restrict__ off,
                                                   const u64* __restrict__ packedOff, const u32* __restrict__ blockFirst, u64 nReads,
                                                   u64 gBase, u64 nChunks, uint4* __restrict__ packed, const u64* __restrict__ endOff) {
     __shared__ u64 sPO[258];
     __shared__ u64 sOff[258];
-    __shared__ u64 sEnd[258];
+    __shared__ u64 sEnd[HAS_END ? 258 : 1];
     __shared__ unsigned char sLut[256];
     __shared__ u64 sFirst;
     const u64 g0 = gBase + (u64)blockIdx.x * 256;   // gBase: first chunk of the read slice this launch covers
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads
         const u64 r = rFirst + i;
         sPO[i] = r <= nReads ? __ldg(&packedOff[r]) : ~0ULL;
         sOff[i] = r <= nReads ? __ldg(&off[r]) : 0;
-        if (endOff) sEnd[i] = r < nReads ? __ldg(&endOff[r]) : 0;   // homopolymer-compressed reads end before the next one begins
+        if (HAS_END) sEnd[i] = r < nReads ? __ldg(&endOff[r]) : 0;   // homopolymer-compressed reads end before the next one begins
     }
     __syncthreads();
     const u64 g = g0 + threadIdx.x;
@@ -90,11 +91,11 @@ __global__ void __launch_bounds__(256) pack_reads(const char* __restrict__ reads
             const u64 mid = (glo + ghi) >> 1;
             if (__ldg(&packedOff[mid]) <= g) glo = mid; else ghi = mid;
         }
-        c = g - __ldg(&packedOff[glo]); src = __ldg(&off[glo]) + 32 * c; e = endOff ? __ldg(&endOff[glo]) : __ldg(&off[glo + 1]);
+        c = g - __ldg(&packedOff[glo]); src = __ldg(&off[glo]) + 32 * c; e = HAS_END ? __ldg(&endOff[glo]) : __ldg(&off[glo + 1]);
     } else {
-        c = g - sPO[lo]; src = sOff[lo] + 32 * c; e = endOff ? sEnd[lo] : sOff[lo + 1];
+        c = g - sPO[lo]; src = sOff[lo] + 32 * c; e = HAS_END ? sEnd[lo] : sOff[lo + 1];
     }
-    const int n = e <= src ? 0 : (int)((e - src) < 32 ? (e - src) : 32);
+    const int n = (HAS_END && e <= src) ? 0 : (int)((e - src) < 32 ? (e - src) : 32);
     const unsigned* __restrict__ wsrc = reinterpret_cast<const unsigned*>(reads + (src & ~3ULL));
     const unsigned sh = (unsigned)(src & 3ULL) * 8u;
     unsigned x[9];
@@ -123,7 +124,8 @@ void launchPackReads(const char* reads, const u64* off, const u64* packedOff, co
                      uint4* packed, cudaStream_t st, const u64* endOff) {
     if (nChunks == 0) return;
     const unsigned grid = (unsigned)((nChunks + 255) / 256);
-    pack_reads<<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, endOff);
+    if (endOff) pack_reads<true><<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, endOff);
+    else pack_reads<false><<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------------
