@@ -40,7 +40,7 @@ KERNELS_PER_STEP = 15  # table_clear pack_reads syncmers_fast count_seeds table_
 #                        node_deltas prefix_scores bfs_gather bfs_records chain_select collect_ties reset_sample
 #                        (+ gen_deltas, gen_prefix when the index holds deltas with a genome count >= 2; the synthetic one has none)
 # DRAM bytes (read + write) per launch from the ncu --set full capture of this workload (profiles/README.md)
-NCU_TRAFFIC = {"node_deltas": 78.8e6, "syncmers_fast": 0.50e9}
+NCU_TRAFFIC = {"node_deltas": 77.6e6, "syncmers_fast": 0.47e9, "count_seeds": 0.57e9, "prefix_scores": 70e6, "pack_reads": 0.22e9}
 
 
 def peaks():
