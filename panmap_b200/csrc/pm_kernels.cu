@@ -498,10 +498,37 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
 // count_seeds: the table-insertion half of seeding for whole samples.  A warp takes 32 reads at a time (lane q holds the list of
 // read r0 + q), numbers their seeds consecutively and works through them 128 at a time, so that every lane has four independent
 // chains (syncmer loads -> seed -> first probe) in flight: the kernel is bound by memory latency, not by bandwidth or issue.
-template <int KT, int LT>
-__global__ void __launch_bounds__(256) count_seeds(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
+// AGG (whole samples in one launch): one 1024-thread block per SM keeps an open-addressing table of (seed, count) in shared memory
+// (kAggSlots entries, 64-bit CAS to claim a key, 32-bit atomic add to count) and flushes it into the global table at the end.
+// At sequencing depth most seed instances repeat a few thousand genome seeds, and the kernel is bound by L2 request rate (probe +
+// red.add per instance, the hot keys concentrated on few slices): those instances now stay on the SM.  Seeds that find their
+// probe window taken go to the global table directly, so the result is the same multiset of (seed, count) either way.
+constexpr int kAggSlots = 16384;
+__device__ __forceinline__ bool aggAdd(u64* __restrict__ sKey, u32* __restrict__ sCnt, u64 s, u64 m) {
+    u32 i = (u32)(m >> 40) & (kAggSlots - 1);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        u64 kk = sKey[i];
+        if (kk == kEmptyKey) {
+            kk = atomicCAS(reinterpret_cast<unsigned long long*>(&sKey[i]), (unsigned long long)kEmptyKey, (unsigned long long)s);
+            if (kk == kEmptyKey) kk = s;
+        }
+        if (kk == s) { atomicAdd(&sCnt[i], 1u); return true; }
+        i = (i + 1) & (kAggSlots - 1);
+    }
+    return false;
+}
+template <int KT, int LT, bool AGG>
+__global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
                                                    const u64* __restrict__ packedOff, u64 nReads, int kRt, int lRt, TableSlot* table,
                                                    u64 mask, SampleAcc* acc, cudaTextureObject_t tableTex) {
+    extern __shared__ __align__(16) unsigned char aggRaw[];
+    u64* sKey = reinterpret_cast<u64*>(aggRaw);
+    u32* sCnt = reinterpret_cast<u32*>(aggRaw + (size_t)kAggSlots * sizeof(u64));
+    if (AGG) {
+        for (int i = threadIdx.x; i < kAggSlots; i += blockDim.x) { sKey[i] = kEmptyKey; sCnt[i] = 0; }
+        __syncthreads();
+    }
     const int k = KT > 0 ? KT : kRt, l = KT > 0 ? LT : lRt;
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
@@ -551,7 +578,9 @@ __global__ void __launch_bounds__(256) count_seeds(const u64* __restrict__ synBu
                         has[q] = fw != rw;
                     }
                 }
-                slot[q] = mixKey(sd[q]) & mask;
+                const u64 m = mixKey(sd[q]);
+                slot[q] = m & mask;
+                if (AGG && has[q] && sd[q] != kEmptyKey && aggAdd(sKey, sCnt, sd[q], m)) has[q] = false;   // counted on the SM
             }
             u64 key[4];
 #pragma unroll
@@ -564,14 +593,37 @@ __global__ void __launch_bounds__(256) count_seeds(const u64* __restrict__ synBu
                 if (has[q]) { if (key[q] == sd[q] && sd[q] != kEmptyKey) atomicAdd(&table[slot[q]].count, 1u); else tableInsert(table, mask, sd[q], 1u, acc); }
         }
     }
+    if (AGG) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kAggSlots; i += blockDim.x) {
+            const u32 c = sCnt[i];
+            if (c) tableInsert(table, mask, sKey[i], c, acc);
+        }
+    }
 }
 static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, TableSlot* table, u64 mask,
                              SampleAcc* acc, cudaTextureObject_t tableTex, cudaStream_t st) {
+    static const int aggMode = getenv("PM_COUNT_AGG") ? atoi(getenv("PM_COUNT_AGG")) : 1;
+    if (aggMode && nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
+        const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
+        const unsigned grid = 148;
+        if (k == 19 && l == 3) {
+            cudaFuncSetAttribute(count_seeds<19, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            count_seeds<19, 3, true><<<grid, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+        } else if (k == 15 && l == 3) {
+            cudaFuncSetAttribute(count_seeds<15, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            count_seeds<15, 3, true><<<grid, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+        } else {
+            cudaFuncSetAttribute(count_seeds<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            count_seeds<0, 0, true><<<grid, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+        }
+        return;
+    }
     u64 g = (nReads + 255) / 256; if (g > 148ull * 8) g = 148ull * 8;
     const unsigned grid = (unsigned)(g ? g : 1);
-    if (k == 19 && l == 3) count_seeds<19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
-    else if (k == 15 && l == 3) count_seeds<15, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
-    else count_seeds<0, 0><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+    if (k == 19 && l == 3) count_seeds<19, 3, false><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+    else if (k == 15 && l == 3) count_seeds<15, 3, false><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+    else count_seeds<0, 0, false><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
 }
 
 template <int MODE>
