@@ -316,6 +316,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
     launchTableClear(W->view, W->st);
     unsigned char* dup = prepareDedup(W, n, prm);
+    const bool ascii = seedTableReadsAscii(P);   // the default parameter sets hash straight from the bytes: no pack_reads pass
     const bool hpc = I->F.sp.hpc != 0;
     if (hpc) W->endOff.ensure(n + 1);
     u64 chunkAcc = 0, win = 0, bfBase = 0;
@@ -342,10 +343,10 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
         CK(cudaEventRecord(W->evCopy[sl], W->stCopy));
         CK(cudaStreamWaitEvent(W->st, W->evCopy[sl], 0));
         if (hpc) launchHpcCompress(W->reads.p, W->off.p + r0, r1 - r0, W->endOff.p + r0, W->st);
-        launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st, hpc ? W->endOff.p + r0 : nullptr);
+        if (!ascii) launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st, hpc ? W->endOff.p + r0 : nullptr);
         if (dup) launchDedup(W->reads.p, W->off.p, r0, r1, W->dedupSlots.p, W->dedupMask, dup, W->st, hpc ? W->endOff.p : nullptr);
         launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, nullptr, dup ? dup + r0 : nullptr,
-                        hpc ? W->endOff.p + r0 : nullptr);
+                        hpc ? W->endOff.p + r0 : nullptr, ascii ? W->reads.p : nullptr);
         bfBase += nBlk + 1;
     }
     W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false;
@@ -366,10 +367,11 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         endOff = W->endOff.p;
     }
     if (dup) launchDedup(W->reads.p, W->off.p, 0, W->nReads, W->dedupSlots.p, W->dedupMask, dup, W->st, endOff);
+    const bool ascii = seedTableReadsAscii(P);
     CK(cudaEventRecord(W->evK[0], W->st));
-    launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st, endOff);
+    if (!ascii) launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st, endOff);
     CK(cudaEventRecord(W->evK[1], W->st));
-    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup, endOff);
+    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup, endOff, ascii ? W->reads.p : nullptr);
     CK(cudaEventRecord(W->evK[3], W->st));
 }
 

@@ -313,18 +313,22 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
 //   oldest: F[p] == min(window)  <=>  F[p] is the suffix minimum of its block tail (one bit per slot, produced by the
 //           block-end pass) and that suffix minimum is <= the running minimum of the current block
 // so the ring keeps only the in-place suffix minima (2*W words per lane instead of 4*W) plus two W-bit masks.
-template <int K, int S>
+// ASCII: the kernel reads the bases themselves (`reads`, one byte per base) and turns 8 of them at a time into the 4-bit codes
+// through a 256-byte table in shared memory -- no pack_reads pass and no packed copy of the sample; !ASCII: 4-bit codes from `packed`.
+template <int K, int S, bool ASCII>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                               const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
                                                               const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
                                                               unsigned* __restrict__ synCount, const unsigned char* __restrict__ dup,
-                                                              const u64* __restrict__ endOff) {
+                                                              const u64* __restrict__ endOff, const char* __restrict__ reads) {
     constexpr int W = K - S + 1;
     static_assert(K >= 8 && K <= 32 && S >= 8 && S < K, "lagged-word addressing assumes 8 <= s < k <= 32");
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
+    unsigned char* sLut = smemRaw + sizeof(SeedTables);
     for (int i = threadIdx.x; i < (int)(sizeof(SeedTables) / 8); i += blockDim.x)
         reinterpret_cast<u64*>(sT)[i] = reinterpret_cast<const u64*>(gT)[i];
+    if (ASCII) for (int i = threadIdx.x; i < 256; i += blockDim.x) sLut[i] = (unsigned char)baseCode((unsigned char)i);
     __syncthreads();
     const SeedTables& T = *sT;
     // F / suffix-min rings of the two strands: every index below is a compile-time constant (the block loop is fully unrolled), so
@@ -342,6 +346,8 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         if (dup && valid && dup[r]) L = 0;   // --dedup: a byte-identical read was seen before
         const u64 pOff = valid ? packedOff[r] : 0;
         const uint4* __restrict__ src = packed + pOff;
+        const char* rbase = ASCII ? reads + (b & ~3ULL) : nullptr;   // 4-byte aligned base of the read, rshift = its misalignment
+        const unsigned rshift = (unsigned)(b & 3ULL);
         u64* __restrict__ dst = synBuf + pOff * 32;
         int maxL = L;
 #pragma unroll
@@ -364,9 +370,27 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         // base i enters: rolling hashes of the k-mer and s-mer ending at i, both strands (seeding.cpp:147-195)
         auto fetchRoll = [&](int i) {
             if ((i & 7) == 0) {   // warp-uniform: next 8-base word, and the lagged words the outgoing bases come from
-                if ((i & 31) == 0) { if (i < L) v = src[i >> 5]; }
                 wh4 = wh3; wh3 = wh2; wh2 = wh1; wh1 = curFull;
-                curFull = v.x; v.x = v.y; v.y = v.z; v.z = v.w;
+                if (ASCII) {
+                    if (i < L) {   // 8 bytes from an arbitrary byte address: three aligned words, two funnel shifts, eight table look-ups
+                        const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + ((rshift + (unsigned)i) & ~3u));
+                        const unsigned sh = ((rshift + (unsigned)i) & 3u) * 8u;
+                        const unsigned x0 = __ldg(wp), x1 = __ldg(wp + 1), x2 = __ldg(wp + 2);
+                        const unsigned b0 = __funnelshift_r(x0, x1, sh), b1 = __funnelshift_r(x1, x2, sh);
+                        unsigned cw = sLut[b1 >> 24];
+                        cw = cw * 16u + sLut[(b1 >> 16) & 0xFFu];
+                        cw = cw * 16u + sLut[(b1 >> 8) & 0xFFu];
+                        cw = cw * 16u + sLut[b1 & 0xFFu];
+                        cw = cw * 16u + sLut[b0 >> 24];
+                        cw = cw * 16u + sLut[(b0 >> 16) & 0xFFu];
+                        cw = cw * 16u + sLut[(b0 >> 8) & 0xFFu];
+                        cw = cw * 16u + sLut[b0 & 0xFFu];
+                        curFull = cw;
+                    }
+                } else {
+                    if ((i & 31) == 0) { if (i < L) v = src[i >> 5]; }
+                    curFull = v.x; v.x = v.y; v.y = v.z; v.z = v.w;
+                }
                 word = curFull;
                 constexpr int KA = K / 8, KB = K % 8, SA = S / 8, SB = S % 8;
                 const unsigned whA[6] = {curFull, wh1, wh2, wh3, wh4, 0xFFFFFFFFu};
@@ -649,13 +673,18 @@ static unsigned seedGrid(u64 nReads) {
 }
 template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                       u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, cudaStream_t st) {
-    syncmers_fast<K, S><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables), st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff);
+                       u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
+    if (reads)
+        syncmers_fast<K, S, true><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables) + 256, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+    else
+        syncmers_fast<K, S, false><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables), st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
 }
+// true when launchSeedTable hashes these parameters straight from the ASCII reads (no pack_reads needed beforehand)
+bool seedTableReadsAscii(const SeederParams& P) { return !P.open && P.t == 0 && P.s == 8 && (P.k == 19 || P.k == 15); }
 static void launchSyncmers(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                           u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, cudaStream_t st) {
-    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, st);
-    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, st);
+                           u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, cudaStream_t st, const char* reads = nullptr) {
+    if (!P.open && P.t == 0 && P.k == 19 && P.s == 8) return launchFast<19, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads, st);
+    if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads, st);
     const size_t sm = genericSmemBytes(P);
     cudaFuncSetAttribute(syncmers_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
@@ -666,9 +695,9 @@ static void launchSyncmers(const uint4* packed, const u64* off, const u64* packe
 // SM can hold.)
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between, const unsigned char* dup,
-                     const u64* endOff) {
+                     const u64* endOff, const char* reads) {
     if (nReads == 0) return;
-    launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, dup, endOff, st);
+    launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, dup, endOff, st, reads);
     if (between) cudaEventRecord(between, st);
     launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, st);
 }

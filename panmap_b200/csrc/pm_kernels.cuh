@@ -122,7 +122,9 @@ void launchPackReads(const char* reads, const u64* off, const u64* packedOff, co
 void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st);
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between = nullptr,
-                     const unsigned char* dup = nullptr, const u64* endOff = nullptr);
+                     const unsigned char* dup = nullptr, const u64* endOff = nullptr, const char* reads = nullptr);
+// true when launchSeedTable can hash these parameters straight from the ASCII reads (pass `reads`, skip pack_reads)
+bool seedTableReadsAscii(const SeederParams& P);
 // --dedup: dup[r] = 1 when a byte-identical read holds the set already; reads [rBegin, rEnd) of the sample, `off` = all offsets
 void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsigned long long* slots, u64 mask, unsigned char* dup, cudaStream_t st,
                  const u64* endOff = nullptr);
