@@ -252,10 +252,12 @@ def main():
     # names (node_deltas) is reported next to it the same way.
     peak = float(pk["hbm_gbs"])
     names = ["h2d", "seeding+table insert (syncmers_fast, count_seeds)", "table finalize", "node_deltas", "prefix_scores", "selection", "d2h"]
-    per_kernel = {"pack_reads (unused: the bases are hashed straight from the ASCII reads)": float(kern[0]), "syncmers_fast<19,8>": float(kern[1]), "count_seeds<19,3>": float(kern[2]),
+    per_kernel = {"pack_reads": float(kern[0]), "syncmers_fast<19,8>": float(kern[1]), "count_seeds<19,3>": float(kern[2]),
                   "node_deltas": float(stage[3]), "prefix_scores": float(stage[4])}
+    if per_kernel["pack_reads"] < 0.01:   # the default parameter sets hash straight from the ASCII reads: no pack_reads launch
+        del per_kernel["pack_reads"]
     dom_name = max(per_kernel, key=per_kernel.get)
-    dom_bytes = {"pack_reads (unused: the bases are hashed straight from the ASCII reads)": alg["seeding"] * 3 // 2, "syncmers_fast<19,8>": alg["seeding"], "count_seeds<19,3>": 12 * int(res.raw.unique_seeds),
+    dom_bytes = {"pack_reads": alg["seeding"] * 3 // 2, "syncmers_fast<19,8>": alg["seeding"], "count_seeds<19,3>": 12 * int(res.raw.unique_seeds),
                  "node_deltas": alg["delta_kernel"], "prefix_scores": 80 * S.n_nodes}[dom_name]
     ach = dom_bytes / (per_kernel[dom_name] * 1e-3) / 1e9
     sc_ach = alg["delta_kernel"] / (stage[3] * 1e-3) / 1e9
