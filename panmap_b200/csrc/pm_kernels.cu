@@ -627,8 +627,7 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds(const u64* __res
 }
 static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, TableSlot* table, u64 mask,
                              SampleAcc* acc, cudaTextureObject_t tableTex, cudaStream_t st) {
-    static const int aggMode = getenv("PM_COUNT_AGG") ? atoi(getenv("PM_COUNT_AGG")) : 1;
-    if (aggMode && nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
+    if (nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
         const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
         const unsigned grid = 148;
         if (k == 19 && l == 3) {
