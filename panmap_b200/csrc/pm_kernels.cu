@@ -602,10 +602,15 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds(const u64* __res
                         has[q] = fw != rw;
                     }
                 }
-                const u64 m = mixKey(sd[q]);
-                slot[q] = m & mask;
-                if (AGG && has[q] && sd[q] != kEmptyKey && aggAdd(sKey, sCnt, sd[q], m)) has[q] = false;   // counted on the SM
+                slot[q] = mixKey(sd[q]);
             }
+            if (AGG) {   // after ALL list loads of the round were issued: atomics are ordering points for the compiler
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (has[q] && sd[q] != kEmptyKey && aggAdd(sKey, sCnt, sd[q], slot[q])) has[q] = false;   // counted on the SM
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) slot[q] &= mask;
             u64 key[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {   // first probe through the texture path (keys are write-once: a stale EMPTY only sends the seed to the CAS path)
