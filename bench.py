@@ -242,7 +242,7 @@ def main():
         e2e_dev += r2.stage_ms[7]
     e2e_wall = time.perf_counter() - t0
     e2e_value = nodes_reads * args.steps / e2e_wall
-    h2d = nbytes + 16 * (w["n_reads"] + 1)           # reads + offsets + packed-chunk offsets
+    h2d = nbytes + 8 * (w["n_reads"] + 1)            # reads + offsets (the chunk offsets are rebuilt on the device)
     d2h = 432 + 4 * int(sum(res.raw.tied_count))     # accumulators/scalars/selection block + tie lists
     L.pm_host_free(hp_reads); L.pm_host_free(hp_off)
 
@@ -358,7 +358,7 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
     dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     L.pm_host_free(hp_reads); L.pm_host_free(hp_off)
     e2e = {"value": world * nodes_reads / (float(e2e_ms.item()) / args.steps * 1e-3), "unit": "node*reads/s",
-           "h2d_bytes_per_step": world * (nbytes + 16 * (n + 1)), "d2h_bytes_per_step": world * 452, "ms_per_step": float(e2e_ms.item()) / args.steps}
+           "h2d_bytes_per_step": world * (nbytes + 8 * (n + 1)), "d2h_bytes_per_step": world * 452, "ms_per_step": float(e2e_ms.item()) / args.steps}
     del ws, index
 
     # ---- single sample, node range sharded over the ranks (strong scaling; reported, not the headline) ----

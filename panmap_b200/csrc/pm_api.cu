@@ -104,6 +104,7 @@ struct pm_workspace {
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
     DevBuf<unsigned long long> dedupSlots; u64 dedupMask = 0; DevBuf<unsigned char> dupFlag;   // --dedup only
     DevBuf<u64> endOff;                                                                        // hpc indexes only
+    DevBuf<u64> tileSum;                                                                       // scratch of the device-side chunk offsets
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
     // the small per-sample result block lives in ONE device allocation so that it comes back with a single copy:
     // [SampleAcc | SampleScalars | Selection x 5 | first kTieHead tied nodes of every metric]
@@ -319,6 +320,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     const bool ascii = seedTableReadsAscii(P);   // the default parameter sets hash straight from the bytes: no pack_reads pass
     const bool hpc = I->F.sp.hpc != 0;
     if (hpc) W->endOff.ensure(n + 1);
+    if (ascii) W->tileSum.ensure(n / 4096 + 2);
     u64 chunkAcc = 0, win = 0, bfBase = 0;
     for (int sl = 0; sl < nSlices; ++sl) {
         const u64 r0 = nSlices == 1 ? 0 : (u64)((double)n * kCut[sl]), r1 = nSlices == 1 || sl + 1 == nSlices ? n : (u64)((double)n * kCut[sl + 1]);
@@ -328,20 +330,23 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
             if (off[i + 1] < off[i]) throw std::runtime_error("read offsets not monotone");
             const u64 L = off[i + 1] - off[i];
             if (L > 0x7FFFFFF0ull) throw std::runtime_error("read longer than 2^31 bases");
-            W->hPackedOff.p[i] = chunkAcc;
+            if (!ascii) W->hPackedOff.p[i] = chunkAcc;
             chunkAcc += (L + 31) >> 5;
             if (L >= (u64)k) win += L - (u64)k + 1;
         }
-        W->hPackedOff.p[r1] = chunkAcc;
         const u64 nCh = chunkAcc - gBase, nBlk = (nCh + 255) / 256;
-        packBlockFirst(W->hPackedOff.p + r0, r1 - r0, nCh, W->hBlockFirst.p + bfBase);
         const u64 b0 = off[r0], b1 = off[r1];
         if (b1 > b0) CK(cudaMemcpyAsync(W->reads.p + b0, reads + b0, b1 - b0, cudaMemcpyHostToDevice, W->stCopy));
         CK(cudaMemcpyAsync(W->off.p + r0, off + r0, (r1 - r0 + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->stCopy));
-        CK(cudaMemcpyAsync(W->packedOff.p + r0, W->hPackedOff.p + r0, (r1 - r0 + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->stCopy));
-        CK(cudaMemcpyAsync(W->blockFirst.p + bfBase, W->hBlockFirst.p + bfBase, (nBlk + 1) * sizeof(u32), cudaMemcpyHostToDevice, W->stCopy));
+        if (!ascii) {   // pack_reads needs the chunk offsets and its block table; otherwise the offsets are rebuilt on the device
+            W->hPackedOff.p[r1] = chunkAcc;
+            packBlockFirst(W->hPackedOff.p + r0, r1 - r0, nCh, W->hBlockFirst.p + bfBase);
+            CK(cudaMemcpyAsync(W->packedOff.p + r0, W->hPackedOff.p + r0, (r1 - r0 + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->stCopy));
+            CK(cudaMemcpyAsync(W->blockFirst.p + bfBase, W->hBlockFirst.p + bfBase, (nBlk + 1) * sizeof(u32), cudaMemcpyHostToDevice, W->stCopy));
+        }
         CK(cudaEventRecord(W->evCopy[sl], W->stCopy));
         CK(cudaStreamWaitEvent(W->st, W->evCopy[sl], 0));
+        if (ascii) launchChunkOffsets(W->off.p + r0, r1 - r0, gBase, W->tileSum.p, W->packedOff.p + r0, W->st);
         if (hpc) launchHpcCompress(W->reads.p, W->off.p + r0, r1 - r0, W->endOff.p + r0, W->st);
         if (!ascii) launchPackReads(W->reads.p, W->off.p + r0, W->packedOff.p + r0, W->blockFirst.p + bfBase, r1 - r0, gBase, nCh, W->packed.p, W->st, hpc ? W->endOff.p + r0 : nullptr);
         if (dup) launchDedup(W->reads.p, W->off.p, r0, r1, W->dedupSlots.p, W->dedupMask, dup, W->st, hpc ? W->endOff.p : nullptr);

@@ -128,6 +128,57 @@ void launchPackReads(const char* reads, const u64* off, const u64* packedOff, co
     else pack_reads<false><<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, nullptr);
 }
 
+// Chunk offsets of a slice of reads on the device: packedOff[i] = gBase + sum_{j<i} ceil(len_j / 32), i = 0..n (n+1 entries), so
+// that they need not cross PCIe (8 bytes per read).  Two small launches: per-tile sums (4096 reads per block), then every block
+// adds the sums of the tiles before it to an in-tile exclusive scan.
+constexpr int kOffTile = 4096;
+__device__ __forceinline__ u64 blockSumU64(u64 v, u64* sRed) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += shflXorU64(v, d);
+    if ((threadIdx.x & 31) == 0) sRed[threadIdx.x >> 5] = v;
+    __syncthreads();
+    u64 t = 0;
+    for (int w = 0; w < 32; ++w) t += sRed[w];
+    __syncthreads();
+    return t;
+}
+__global__ void __launch_bounds__(1024) chunk_tile_sums(const u64* __restrict__ off, u64 n, u64* __restrict__ tileSum) {
+    __shared__ u64 sRed[32];
+    const u64 base = (u64)blockIdx.x * kOffTile + 4ull * threadIdx.x;
+    u64 v = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) if (base + q < n) v += (off[base + q + 1] - off[base + q] + 31) >> 5;
+    v = blockSumU64(v, sRed);
+    if (threadIdx.x == 0) tileSum[blockIdx.x] = v;
+}
+__global__ void __launch_bounds__(1024) chunk_offsets_tiled(const u64* __restrict__ off, u64 n, u64 gBase, const u64* __restrict__ tileSum,
+                                                            u64* __restrict__ packedOff) {
+    __shared__ u64 sRed[32];
+    __shared__ u64 sWarp[32];
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    u64 pre = 0;
+    for (unsigned b = tid; b < blockIdx.x; b += 1024) pre += tileSum[b];
+    pre = blockSumU64(pre, sRed) + gBase;
+    const u64 base = (u64)blockIdx.x * kOffTile + 4ull * tid;
+    u64 c[4], tot = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { c[q] = base + q < n ? (off[base + q + 1] - off[base + q] + 31) >> 5 : 0; tot += c[q]; }
+    u64 incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const u64 o = shflUpU64(incl, d); if (lane >= (unsigned)d) incl += o; }
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    for (unsigned w = 0; w < warp; ++w) pre += sWarp[w];
+    u64 run = pre + incl - tot;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { if (base + q <= n) packedOff[base + q] = run; run += c[q]; }   // entry n = the slice total
+}
+void launchChunkOffsets(const u64* off, u64 n, u64 gBase, u64* tileSum, u64* packedOff, cudaStream_t st) {
+    const unsigned tiles = (unsigned)(n / kOffTile + 1);   // +1: the tile that holds entry n
+    chunk_tile_sums<<<tiles, 1024, 0, st>>>(off, n, tileSum);
+    chunk_offsets_tiled<<<tiles, 1024, 0, st>>>(off, n, gBase, tileSum, packedOff);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Homopolymer compression of the reads when the index was built with --hpc (placement.cpp:1145-1165, seeding::hpcCompress,
 // seeding.cpp:286-306): a base is dropped when it equals its predecessor ignoring case.  One warp per read, in place inside the

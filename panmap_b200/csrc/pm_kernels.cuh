@@ -120,6 +120,7 @@ struct PlaceOpts {
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
                      uint4* packed, cudaStream_t st, const u64* endOff = nullptr);
 void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st);
+void launchChunkOffsets(const u64* off, u64 n, u64 gBase, u64* tileSum /* [n/4096 + 1] scratch */, u64* packedOff, cudaStream_t st);
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between = nullptr,
                      const unsigned char* dup = nullptr, const u64* endOff = nullptr, const char* reads = nullptr);
