@@ -681,28 +681,99 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds(const u64* __res
         }
     }
 }
-static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, TableSlot* table, u64 mask,
-                             SampleAcc* acc, cudaTextureObject_t tableTex, cudaStream_t st) {
+// count_seeds_lane: the same counting with one LANE per read (as in the syncmer kernel): a lane walks its own list, keeps the last
+// LT-1 syncmers in registers and loads one new syncmer per seed -- no search for "which read does seed i belong to", a third of the
+// loads and a quarter of the instructions of the flat numbering above.  Four seeds per lane are formed before anything is probed.
+template <int KT, int LT, bool AGG>
+__global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds_lane(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
+                                                   const u64* __restrict__ packedOff, u64 nReads, TableSlot* table,
+                                                   u64 mask, SampleAcc* acc, cudaTextureObject_t tableTex) {
+    static_assert(LT == 1 || LT == 3, "lane-per-read counting is specialised for l = 1 and l = 3");
+    extern __shared__ __align__(16) unsigned char aggRaw[];
+    u64* sKey = reinterpret_cast<u64*>(aggRaw);
+    u32* sCnt = reinterpret_cast<u32*>(aggRaw + (size_t)kAggSlots * sizeof(u64));
+    if (AGG) {
+        for (int i = threadIdx.x; i < kAggSlots; i += blockDim.x) { sKey[i] = kEmptyKey; sCnt[i] = 0; }
+        __syncthreads();
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 r0 = ((u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; r0 < nReads; r0 += warpsTotal * 32) {
+        const u64 r = r0 + lane;
+        const int n = r < nReads ? (int)__ldg(&synCount[r]) : 0;
+        const u64* __restrict__ h = synBuf + (r < nReads ? __ldg(&packedOff[r]) : 0) * 32;
+        const int nS = LT <= 1 ? n : (n >= LT ? n - LT + 1 : 0);
+        int maxS = nS;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) maxS = max(maxS, __shfl_xor_sync(0xffffffffu, maxS, d));
+        u64 h0 = 0, h1 = 0;   // the two syncmers before the next one to load (l = 3)
+        if (LT == 3 && nS > 0) { h0 = __ldg(h); h1 = __ldg(h + 1); }
+        for (int j0 = 0; j0 < maxS; j0 += 4) {
+            u64 x[4], sd[4], slot[4]; bool has[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { has[q] = j0 + q < nS; x[q] = has[q] ? __ldg(h + j0 + q + (LT - 1)) : 0; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (LT == 1) sd[q] = x[q];
+                else {
+                    const u64 fw = rol64(h0, (unsigned)((KT * 2) & 63)) ^ rol64(h1, (unsigned)(KT & 63)) ^ x[q];
+                    const u64 rw = h0 ^ rol64(h1, (unsigned)(KT & 63)) ^ rol64(x[q], (unsigned)((KT * 2) & 63));
+                    sd[q] = umin64(fw, rw);
+                    has[q] = has[q] && fw != rw;
+                    h0 = h1; h1 = x[q];
+                }
+                slot[q] = mixKey(sd[q]);
+            }
+            if (AGG) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (has[q] && sd[q] != kEmptyKey && aggAdd(sKey, sCnt, sd[q], slot[q])) has[q] = false;   // counted on the SM
+            }
+            u64 key[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                slot[q] &= mask; key[q] = kEmptyKey;
+                if (has[q]) { const uint4 t = tex1Dfetch<uint4>(tableTex, (int)slot[q]); key[q] = (u64)t.x | ((u64)t.y << 32); }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (has[q]) { if (key[q] == sd[q] && sd[q] != kEmptyKey) atomicAdd(&table[slot[q]].count, 1u); else tableInsert(table, mask, sd[q], 1u, acc); }
+        }
+    }
+    if (AGG) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kAggSlots; i += blockDim.x) {
+            const u32 c = sCnt[i];
+            if (c) tableInsert(table, mask, sKey[i], c, acc);
+        }
+    }
+}
+template <int KT, int LT>
+static void launchCountLane(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, TableSlot* table, u64 mask, SampleAcc* acc,
+                            cudaTextureObject_t tableTex, cudaStream_t st) {
     if (nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
         const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
-        const unsigned grid = 148;
-        if (k == 19 && l == 3) {
-            cudaFuncSetAttribute(count_seeds<19, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            count_seeds<19, 3, true><<<grid, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
-        } else if (k == 15 && l == 3) {
-            cudaFuncSetAttribute(count_seeds<15, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            count_seeds<15, 3, true><<<grid, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
-        } else {
-            cudaFuncSetAttribute(count_seeds<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-            count_seeds<0, 0, true><<<grid, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
-        }
+        cudaFuncSetAttribute(count_seeds_lane<KT, LT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        count_seeds_lane<KT, LT, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
+    } else {
+        u64 g = (nReads + 255) / 256; if (g > 148ull * 8) g = 148ull * 8;
+        count_seeds_lane<KT, LT, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
+    }
+}
+static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, TableSlot* table, u64 mask,
+                             SampleAcc* acc, cudaTextureObject_t tableTex, cudaStream_t st) {
+    // panmap's parameter sets (l = 3 with k = 19 / 15, and l <= 1) use the lane-per-read kernel; any other (k, l) the flat one below
+    if (k == 19 && l == 3) return launchCountLane<19, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
+    if (k == 15 && l == 3) return launchCountLane<15, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
+    if (l <= 1) return launchCountLane<0, 1>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
+    if (nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
+        const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
+        cudaFuncSetAttribute(count_seeds<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        count_seeds<0, 0, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
         return;
     }
     u64 g = (nReads + 255) / 256; if (g > 148ull * 8) g = 148ull * 8;
-    const unsigned grid = (unsigned)(g ? g : 1);
-    if (k == 19 && l == 3) count_seeds<19, 3, false><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
-    else if (k == 15 && l == 3) count_seeds<15, 3, false><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
-    else count_seeds<0, 0, false><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+    count_seeds<0, 0, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
 }
 
 template <int MODE>

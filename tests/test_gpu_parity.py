@@ -72,6 +72,16 @@ def test_place_synthetic_index_with_table_only_reads():
     _place_and_check(idx, reads)
 
 
+@pytest.mark.parametrize("k,s,t,l,op", [(21, 10, 1, 2, True), (15, 8, 0, 1, False), (31, 8, 0, 5, False), (15, 8, 0, 3, False), (12, 5, 2, 0, False)])
+def test_place_other_seeding_parameters(k, s, t, l, op):
+    """parameter sets besides panmap's default: the generic syncmer kernel + pack_reads + the flat counting kernel (any k <= 32, s, t,
+    open/closed, l), and the specialised k=15 kernels"""
+    rng = np.random.default_rng(100 + k + l)
+    idx, _, _ = H.synthetic_index(300, rng, k=k, s=s, t=t, l=l)
+    idx.open = int(op)
+    _place_and_check(idx, H.random_reads(rng, 300, lo=10, hi=220))
+
+
 def test_place_dedup_counts_every_distinct_read_string_once():
     """--dedup (placement.cpp:1550-1620): byte-identical reads count once; reads that differ only in case or in the ambiguity
     letter are different strings for the reference and must both count.  Small and sliced (>= 65536 reads) paths."""
