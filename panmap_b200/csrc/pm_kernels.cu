@@ -735,16 +735,56 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds_lane(const u64* 
                 slot[q] &= mask; key[q] = kEmptyKey;
                 if (has[q]) { const uint4 t = tex1Dfetch<uint4>(tableTex, (int)slot[q]); key[q] = (u64)t.x | ((u64)t.y << 32); }
             }
+            // new keys claim their slot with a CAS whose result takes a round trip to L2: issue the CASes of all four seeds before
+            // looking at any result (one exposed latency per round instead of up to four); true collisions go the general way
+            bool claim[4], slow[4]; unsigned long long was[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                claim[q] = slow[q] = false;
+                if (has[q]) {
+                    if (sd[q] == kEmptyKey) slow[q] = true;
+                    else if (key[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u);
+                    else if (key[q] == kEmptyKey) claim[q] = true;
+                    else slow[q] = true;
+                }
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (has[q]) { if (key[q] == sd[q] && sd[q] != kEmptyKey) atomicAdd(&table[slot[q]].count, 1u); else tableInsert(table, mask, sd[q], 1u, acc); }
+                if (claim[q]) was[q] = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot[q]].key), (unsigned long long)kEmptyKey, (unsigned long long)sd[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (claim[q]) { if (was[q] == kEmptyKey || was[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u); else slow[q] = true; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (slow[q]) tableInsert(table, mask, sd[q], 1u, acc);
         }
     }
-    if (AGG) {
+    if (AGG) {   // flush: the block's (seed, count) pairs into the global table, four claims in flight per thread
         __syncthreads();
-        for (int i = threadIdx.x; i < kAggSlots; i += blockDim.x) {
-            const u32 c = sCnt[i];
-            if (c) tableInsert(table, mask, sKey[i], c, acc);
+        for (int i0 = threadIdx.x * 4; i0 < kAggSlots; i0 += blockDim.x * 4) {
+            u64 k4[4], sl[4], seen[4]; u32 c4[4]; unsigned long long was[4]; bool claim[4], slow[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { k4[q] = sKey[i0 + q]; c4[q] = sCnt[i0 + q]; sl[q] = mixKey(k4[q]) & mask; seen[q] = kEmptyKey; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (c4[q]) seen[q] = __ldcg(&table[sl[q]].key);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                claim[q] = slow[q] = false;
+                if (c4[q]) {
+                    if (seen[q] == k4[q]) atomicAdd(&table[sl[q]].count, c4[q]);
+                    else if (seen[q] == kEmptyKey) claim[q] = true;
+                    else slow[q] = true;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (claim[q]) was[q] = atomicCAS(reinterpret_cast<unsigned long long*>(&table[sl[q]].key), (unsigned long long)kEmptyKey, (unsigned long long)k4[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (claim[q]) { if (was[q] == kEmptyKey || was[q] == k4[q]) atomicAdd(&table[sl[q]].count, c4[q]); else slow[q] = true; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (slow[q]) tableInsert(table, mask, k4[q], c4[q], acc);
         }
     }
 }
