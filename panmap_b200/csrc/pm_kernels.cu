@@ -1190,7 +1190,7 @@ void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* hom
     const unsigned g1 = (unsigned)std::min<u64>(std::min<u64>(nBlocks ? nBlocks : 1, (u64)nSM * 4), kMaxPartials);
     table_scan<<<g1, 256, 0, st>>>(W, homo);
     // sized from the previous sample's entry count (the kernel grid-strides, so any grid is correct)
-    u64 g2 = (expectedEntries + 255) / 256; if (g2 < 1) g2 = 1; if (g2 > (u64)nSM * 8) g2 = (u64)nSM * 8; if (g2 > kMaxPartials) g2 = kMaxPartials;
+    u64 g2 = (expectedEntries + 255) / 256; if (g2 < 1) g2 = 1; if (g2 > (u64)nSM * 4) g2 = (u64)nSM * 4; if (g2 > kMaxPartials) g2 = kMaxPartials;
     entries_finalize<<<(unsigned)g2, 256, 0, st>>>(I, W, O.minReadSupport, g1);
     if (I.hasRoot && I.rootDCount) {
         u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
