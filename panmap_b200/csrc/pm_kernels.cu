@@ -377,9 +377,16 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
     unsigned char* sLut = smemRaw + sizeof(SeedTables);
+    // (outgoing base, incoming base) pair tables: one look-up and one XOR per rolling hash instead of two and two
+    u64* sPair = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables) + 256);   // [4][8][8]: fk, rk, fs, rs
     for (int i = threadIdx.x; i < (int)(sizeof(SeedTables) / 8); i += blockDim.x)
         reinterpret_cast<u64*>(sT)[i] = reinterpret_cast<const u64*>(gT)[i];
-    if (ASCII) for (int i = threadIdx.x; i < 256; i += blockDim.x) sLut[i] = (unsigned char)baseCode((unsigned char)i);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sLut[i] = (unsigned char)baseCode((unsigned char)i);
+        const int tb = i >> 6, o = (i >> 3) & 7, nw = i & 7;
+        sPair[i] = tb == 0 ? gT->fwdOldK[o] ^ gT->fwdNew[nw] : tb == 1 ? gT->revOld[o] ^ gT->revNewK[nw]
+                 : tb == 2 ? gT->fwdOldS[o] ^ gT->fwdNew[nw] : gT->revOld[o] ^ gT->revNewS[nw];
+    }
     __syncthreads();
     const SeedTables& T = *sT;
     // F / suffix-min rings of the two strands: every index below is a compile-time constant (the block loop is fully unrolled), so
@@ -451,10 +458,11 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
             const unsigned code = word & 0xFu, oldK = lagK & 7u, oldS = lagS & 7u, tc = code & 7u;
             word >>= 4; lagK >>= 4; lagS >>= 4;
             if (i < L) {
-                fk = rol1(fk) ^ T.fwdOldK[oldK] ^ T.fwdNew[tc];
-                rk = ror1(rk) ^ T.revOld[oldK] ^ T.revNewK[tc];
-                fs = rol1(fs) ^ T.fwdOldS[oldS] ^ T.fwdNew[tc];
-                rs = ror1(rs) ^ T.revOld[oldS] ^ T.revNewS[tc];
+                const unsigned pk = oldK * 8u + tc, ps = oldS * 8u + tc;
+                fk = rol1(fk) ^ sPair[pk];
+                rk = ror1(rk) ^ sPair[64 + pk];
+                fs = rol1(fs) ^ sPair[128 + ps];
+                rs = ror1(rs) ^ sPair[192 + ps];
                 if (code >= 4) iLo = max(iLo, i + K);
             }
         };
@@ -841,9 +849,9 @@ template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
                        u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
     if (reads)
-        syncmers_fast<K, S, true><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables) + 256, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+        syncmers_fast<K, S, true><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables) + 256 + 2048, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
     else
-        syncmers_fast<K, S, false><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables), st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
+        syncmers_fast<K, S, false><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables) + 256 + 2048, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
 }
 // true when launchSeedTable hashes these parameters straight from the ASCII reads (no pack_reads needed beforehand)
 bool seedTableReadsAscii(const SeederParams& P) { return !P.open && P.t == 0 && P.s == 8 && (P.k == 19 || P.k == 15); }
