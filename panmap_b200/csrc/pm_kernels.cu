@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
 // so the ring keeps only the in-place suffix minima (2*W words per lane instead of 4*W) plus two W-bit masks.
 // ASCII: the kernel reads the bases themselves (`reads`, one byte per base) and turns 8 of them at a time into the 4-bit codes
 // through a 256-byte table in shared memory -- no pack_reads pass and no packed copy of the sample; !ASCII: 4-bit codes from `packed`.
-template <int K, int S, bool ASCII>
+// NOTRIM: trimEnd == 0 (the default), so "window inside the trimmed range" is implied by i < L and costs nothing
+template <int K, int S, bool ASCII, bool NOTRIM>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                               const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
                                                               const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
@@ -491,15 +492,17 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                             fsyn = (leF && fs <= sf) || (((maskF >> pslot) & 1u) && sf <= preF);
                             rsyn = (leR && rs <= sr) || (((maskR >> pslot) & 1u) && sr <= preR);
                         }
-                        if ((fsyn || rsyn) && i >= iLo && i <= iHi && fk != rk) {
+                        if ((fsyn || rsyn) && i >= iLo && (NOTRIM || i <= iHi) && fk != rk) {
                             dst[cnt] = umin64(fk, rk);
                             ++cnt;
                         }
                         rF[j] = fs; rR[j] = rs;
                         if (j == W - 1) {   // block complete: in-place suffix minima + "is its own suffix minimum" masks
-                            u64 a = kEmptyKey, bb = kEmptyKey; unsigned mF = 0, mR = 0;
+                            // the newest s-mer (slot W-1, = fs / rs) is its own suffix minimum; slot 0 is never looked up (a window that
+                            // starts there is the block itself)
+                            u64 a = fs, bb = rs; unsigned mF = 1u << (W - 1), mR = 1u << (W - 1);
 #pragma unroll
-                            for (int q = W - 1; q >= 0; --q) {
+                            for (int q = W - 2; q >= 1; --q) {
                                 const u64 x = rF[q], y = rR[q];
                                 const bool ia = x <= a, ib = y <= bb;
                                 a = ia ? x : a; bb = ib ? y : bb;
@@ -848,10 +851,13 @@ static unsigned seedGrid(u64 nReads) {
 template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
                        u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
-    if (reads)
-        syncmers_fast<K, S, true><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables) + 256 + 2048, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+    const size_t sm = sizeof(SeedTables) + 256 + 2048;
+    if (reads && P.trimEnd == 0)
+        syncmers_fast<K, S, true, true><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+    else if (reads)
+        syncmers_fast<K, S, true, false><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
     else
-        syncmers_fast<K, S, false><<<seedGrid(nReads), kSeedThreads, sizeof(SeedTables) + 256 + 2048, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
+        syncmers_fast<K, S, false, false><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
 }
 // true when launchSeedTable hashes these parameters straight from the ASCII reads (no pack_reads needed beforehand)
 bool seedTableReadsAscii(const SeederParams& P) { return !P.open && P.t == 0 && P.s == 8 && (P.k == 19 || P.k == 15); }
