@@ -74,7 +74,7 @@ typedef struct pm_place_params {
     int32_t dedup_reads;       /* dedupReads: every distinct read string counts once (placement.cpp:1550-1620) */
     int32_t force_leaf;        /* forceLeaf: only leaves are eligible (placement.cpp:794-795) */
     uint32_t skip_node_index;  /* leave-one-out node, PM_NONE = none (placement.hpp:91) */
-    double seed_mask_fraction; /* seedMaskFraction; CLI default 0 (main.cpp:1967) */
+    double seed_mask_fraction; /* seedMaskFraction (placement.cpp:1748-1799); CLI default 0 (main.cpp:1967); ties at the cut: smaller hash first */
     int32_t want_node_scores;  /* keep the [n_nodes][5] f64 score matrix for pm_get_node_scores */
     int32_t reserved;
 } pm_place_params;

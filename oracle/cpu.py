@@ -78,6 +78,14 @@ def seed_table(reads, offsets, k, s, t, l, open=False, trim_start=0, trim_end=0,
     return h, c
 
 
+def mask_top_seeds(hash_, count, frac):
+    """orc_mask_top_seeds (placement.cpp:1748-1799): the table without its floor(frac * U) most frequent seeds, sorted by hash;
+    ties at the cut go by ascending hash (unspecified in the reference)."""
+    h = np.array(hash_, np.uint64); c = np.array(count, np.int64)
+    n = lib().orc_mask_top_seeds(_p(h), _p(c), C.c_int64(h.size), C.c_double(frac))
+    return h[:n].copy(), c[:n].copy()
+
+
 def resolve_min_read_support(counts, configured=-1):
     counts = np.ascontiguousarray(counts, np.int64)
     return int(lib().orc_resolve_min_read_support(_p(counts), C.c_int64(counts.size), configured))

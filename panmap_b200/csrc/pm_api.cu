@@ -119,6 +119,7 @@ struct pm_workspace {
     DevBuf<u32> recRank, recNode; DevBuf<double> recScore; u32 recCap = 0;
     DevBuf<u32> tieNode; u32 tieCap = 0; DevBuf<u32> selCounts;
     DevBuf<u64> expHash; DevBuf<long long> expCount; DevBuf<unsigned> expCounter;
+    DevBuf<unsigned long long> maskScratch;   // --seed-mask-fraction only
     // host staging (pinned)
     PinBuf<unsigned char> hStage; PinBuf<u32> hTies; PinBuf<unsigned char> hRec;
     // results of the last sample
@@ -243,7 +244,6 @@ PlaceOpts makeOpts(const pm_place_params& p, bool wantMetrics) {
 
 void checkParams(const pm_place_params* p) {
     if (!p) throw std::runtime_error("null params");
-    if (p->seed_mask_fraction > 0.0) throw Unsupported("seed_mask_fraction > 0 is not implemented on the GPU path yet");
     if (p->trim_start < 0 || p->trim_end < 0) throw std::runtime_error("negative trim");
 }
 
@@ -383,7 +383,9 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
 void stageScore(pm_workspace* W, const pm_place_params& prm) {
     pm_index* I = W->idx;
     const PlaceOpts O = makeOpts(prm, W->wantMetrics);
-    launchFinalize(I->view, W->view, O, I->homo.p, W->lastEntries ? W->lastEntries : W->tableCap / 4, I->nSM, W->st);
+    if (prm.seed_mask_fraction > 0.0) W->maskScratch.ensure(2);
+    launchFinalize(I->view, W->view, O, I->homo.p, W->lastEntries ? W->lastEntries : W->tableCap / 4, I->nSM, W->st, prm.seed_mask_fraction,
+                   W->maskScratch.p);
     CK(cudaEventRecord(W->ev[3], W->st));
     launchDeltas(I->view, W->view, I->nSM, W->st);
     launchGeneral(I->view, W->view, W->st);

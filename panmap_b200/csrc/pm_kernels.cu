@@ -13,6 +13,7 @@
 #include "pm_kernels.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 namespace pm {
 
@@ -1006,6 +1007,99 @@ __global__ void __launch_bounds__(256) table_scan(WorkspaceView W, const u64* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// --seed-mask-fraction (placement.cpp:1748-1799; off by default): drop the floor(frac * U) most frequent seeds before the
+// min-support rule and the magnitudes see the table.  The reference sorts by count only, so which seeds go at a tied cut is
+// unspecified there; like the oracle this path takes the smaller hashes first.  The cut (count c*, hash h*) is found by
+// bisection with one counting pass over the compacted entries per step, driven from the host -- a handful of tiny launches
+// on an optional path, nothing on the default one.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_count(WorkspaceView W, u32 cThr, u64 hThr, unsigned long long* __restrict__ out) {
+    unsigned long long above = 0, tied = 0;   // entries with count > cThr; with count == cThr and key <= hThr
+    const unsigned n = W.acc->entCount;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 c = W.entCnt[i];
+        if (c > cThr) ++above;
+        else if (c == cThr && c > 0 && W.entKey[i] <= hThr) ++tied;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && W.acc->emptyKeyCount > 0) {   // the key that lives outside the table (largest hash)
+        const unsigned long long c = (unsigned long long)W.acc->emptyKeyCount;
+        if (c > cThr) ++above; else if (c == cThr && kEmptyKey <= hThr) ++tied;
+    }
+    above = (unsigned long long)warpSumLL((long long)above); tied = (unsigned long long)warpSumLL((long long)tied);
+    if ((threadIdx.x & 31u) == 0) { if (above) atomicAdd(out, above); if (tied) atomicAdd(out + 1, tied); }
+}
+__global__ void __launch_bounds__(256) mask_apply(WorkspaceView W, u32 cThr, u64 hThr, unsigned partIdx) {
+    long long ms = 0, mc = 0, en = 0, total = 0;   // what the masked seeds had contributed to pass 1's statistics
+    const unsigned n = W.acc->entCount;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 c = W.entCnt[i];
+        if (c == 0) continue;
+        const u64 k = W.entKey[i];
+        if (!(c > cThr || (c == cThr && k <= hThr))) continue;
+        W.entCnt[i] = 0;   // pass 2 skips it
+        u64 slot = mixKey(k) & W.tableMask;
+        while (W.table[slot].key != k) slot = (slot + 1) & W.tableMask;   // present by construction
+        W.table[slot].count = 0;   // like the homopolymer seeds: gone for the exported table too
+        --en; total -= c; if (c >= 2) { ms -= c; --mc; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && W.acc->emptyKeyCount > 0) {
+        const long long c = W.acc->emptyKeyCount;
+        if ((unsigned long long)c > cThr || ((unsigned long long)c == cThr && kEmptyKey <= hThr)) {
+            W.acc->emptyKeyCount = 0; --en; total -= c; if (c >= 2) { ms -= c; --mc; }
+        }
+    }
+    ms = warpSumLL(ms); mc = warpSumLL(mc); en = warpSumLL(en); total = warpSumLL(total);
+    if ((threadIdx.x & 31u) == 0 && en) {
+        unsigned long long* p = reinterpret_cast<unsigned long long*>(&W.scanPart[partIdx]);   // zeroed by the host; two's complement adds
+        atomicAdd(p + 0, (unsigned long long)ms); atomicAdd(p + 1, (unsigned long long)mc);
+        atomicAdd(p + 2, (unsigned long long)en); atomicAdd(p + 3, (unsigned long long)total);
+    }
+}
+// synchronous; returns the number of masked seeds.  scratch: two device words
+static u64 maskTopSeeds(WorkspaceView W, double frac, unsigned nScanParts, unsigned long long* scratch, cudaStream_t st) {
+    std::vector<ScanPartial> parts(nScanParts);
+    cudaMemcpyAsync(parts.data(), W.scanPart, nScanParts * sizeof(ScanPartial), cudaMemcpyDeviceToHost, st);
+    cudaMemsetAsync(&W.scanPart[nScanParts], 0, sizeof(ScanPartial), st);
+    cudaStreamSynchronize(st);
+    u64 U = 0;
+    for (const ScanPartial& sp : parts) U += (u64)sp.entries;
+    const u64 numToMask = (u64)(size_t)(frac * (double)U);   // placement.cpp:1775
+    const u64 drop = std::min(numToMask, U);
+    if (drop == 0) return 0;
+    const unsigned grid = streamGrid(U, 4);
+    auto query = [&](u32 c, u64 h, u64& above, u64& tied) {
+        unsigned long long r[2];
+        cudaMemsetAsync(scratch, 0, sizeof(r), st);
+        mask_count<<<grid, 256, 0, st>>>(W, c, h, scratch);
+        cudaMemcpyAsync(r, scratch, sizeof(r), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        above = r[0]; tied = r[1];
+    };
+    // c* = count of the drop-th most frequent seed: the smallest c with #(count > c) < drop
+    u64 lo = 1, hi = 0xFFFFFFFFull, above = 0, tied = 0;
+    while (lo < hi) {
+        const u64 mid = lo + (hi - lo) / 2;
+        query((u32)mid, 0, above, tied);
+        if (above < drop) hi = mid; else lo = mid + 1;
+    }
+    const u32 cStar = (u32)lo;
+    query(cStar, ~0ull, above, tied);
+    const u64 need = drop - above;   // of the seeds with count c*, the `need` smallest hashes go
+    u64 hStar = ~0ull;
+    if (tied > need) {
+        u64 hl = 0, hh = ~0ull;
+        while (hl < hh) {   // smallest h with #(count == c*, key <= h) >= need
+            const u64 mid = hl + (hh - hl) / 2;
+            u64 a2, t2; query(cStar, mid, a2, t2);
+            if (t2 >= need) hh = mid; else hl = mid + 1;
+        }
+        hStar = hl;
+    }
+    mask_apply<<<grid, 256, 0, st>>>(W, cStar, hStar, nScanParts);
+    return drop;
+}
+
 __device__ __forceinline__ long long resolveMinSupport(long long multiSum, long long multiCount, int configured) {
     if (configured >= 0) return configured;
     const double est = multiCount > 0 ? (double)(u64)multiSum / (double)(u64)multiCount : 0.0;
@@ -1057,7 +1151,7 @@ __global__ void __launch_bounds__(256) entries_finalize(DevIndexView I, Workspac
     for (unsigned i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) {
         const u32 c = __ldcs(&W.entCnt[i]);
         u32 id = kNone;
-        if (c >= minSup) id = finalizeKept(I, W, __ldcs(&W.entKey[i]), c, A, sHist);
+        if (c >= minSup && c != 0) id = finalizeKept(I, W, __ldcs(&W.entKey[i]), c, A, sHist);   // c == 0: masked
         W.entId[i] = id;
     }
     if (blockIdx.x == 0 && tid == 0 && acc->emptyKeyCount > 0) {
@@ -1198,11 +1292,13 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
     *W.scalars = S;
 }
 
-void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st) {
+void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st,
+                    double seedMaskFraction, unsigned long long* maskScratch) {
     cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
     const u64 nBlocks = (W.tableCap + kScanSlots - 1) / kScanSlots;
-    const unsigned g1 = (unsigned)std::min<u64>(std::min<u64>(nBlocks ? nBlocks : 1, (u64)nSM * 4), kMaxPartials);
+    unsigned g1 = (unsigned)std::min<u64>(std::min<u64>(nBlocks ? nBlocks : 1, (u64)nSM * 4), kMaxPartials - 1);
     table_scan<<<g1, 256, 0, st>>>(W, homo);
+    if (seedMaskFraction > 0.0) { maskTopSeeds(W, seedMaskFraction, g1, maskScratch, st); ++g1; }   // + one partial of corrections
     // sized from the previous sample's entry count (the kernel grid-strides, so any grid is correct)
     u64 g2 = (expectedEntries + 255) / 256; if (g2 < 1) g2 = 1; if (g2 > (u64)nSM * 4) g2 = (u64)nSM * 4; if (g2 > kMaxPartials) g2 = kMaxPartials;
     entries_finalize<<<(unsigned)g2, 256, 0, st>>>(I, W, O.minReadSupport, g1);

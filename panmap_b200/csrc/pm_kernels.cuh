@@ -135,7 +135,9 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
 void launchTableClear(WorkspaceView W, cudaStream_t st);
 void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st);
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st);
-void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st);
+// seedMaskFraction > 0 (off by default): synchronises the stream a few dozen times to find the cut; maskScratch = two device words
+void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st,
+                    double seedMaskFraction = 0.0, unsigned long long* maskScratch = nullptr);
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st);
 void launchGeneral(DevIndexView I, WorkspaceView W, cudaStream_t st);
 void launchPrefixScores(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st);

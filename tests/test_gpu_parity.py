@@ -49,6 +49,8 @@ def _place_and_check(idx, reads, params=None, **okw):
     assert res.raw.min_read_support == exp["min_support"]
     th, tc = ws.seed_table()
     eh, ec = cpu.seed_table(buf, off, idx.k, idx.s, idx.t, idx.l, idx.open, okw.get("trim_start", 0), okw.get("trim_end", 0), okw.get("dedup", False))
+    if okw.get("seed_mask_fraction", 0) > 0:
+        eh, ec = cpu.mask_top_seeds(eh, ec, okw["seed_mask_fraction"])
     keep = tc > 0
     assert np.array_equal(th[keep], eh) and np.array_equal(tc[keep], ec)
     # f64
@@ -94,6 +96,24 @@ def test_place_dedup_counts_every_distinct_read_string_once():
     _place_and_check(idx, reads, pm.PlaceParams(dedup_reads=1), dedup=True)
     big = [base[i % 300] for i in range(70000)] + H.random_reads(rng, 500)
     _place_and_check(idx, big, pm.PlaceParams(dedup_reads=1), dedup=True)
+
+
+@pytest.mark.parametrize("frac", [0.0004, 0.013, 0.2, 0.77, 1.0])
+def test_place_seed_mask_fraction_drops_the_most_frequent_seeds(frac):
+    """--seed-mask-fraction (placement.cpp:1748-1799): the floor(frac * U) most frequent seeds leave the table before the min-support
+    rule and the magnitudes; ties at the cut go by ascending hash like the oracle (the reference leaves them unspecified).  Duplicated
+    reads give a wide spread of counts, so the cut lands inside groups of equal counts as well as between them."""
+    rng = np.random.default_rng(31)
+    idx, _, _ = H.synthetic_index(500, rng)
+    base = H.random_reads(rng, 600)
+    reads = base + base[:300] * 2 + base[:80] * 5 + base[:9] * 40
+    res, exp, ws, _ = _place_and_check(idx, reads, pm.PlaceParams(seed_mask_fraction=frac), seed_mask_fraction=frac)
+    full = cpu.place(*pm.pack_reads(reads), idx)
+    assert exp["unique_seeds"] == full["unique_seeds"] - int(frac * full["unique_seeds"])
+    # the debug re-run of the scoring stages must not mask a second time
+    assert H.relerr(ws.node_scores(), exp["scores"]).max() < RTOL
+    ws.node_metrics()
+    assert ws.place(*pm.pack_reads(reads), pm.PlaceParams(seed_mask_fraction=frac)).raw.unique_seeds == exp["unique_seeds"]
 
 
 def test_place_hpc_index_compresses_reads_on_the_device():

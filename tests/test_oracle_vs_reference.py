@@ -123,3 +123,37 @@ def test_dedup_trim_force_leaf_and_hpc_match_reference_placeLite():
         assert o["kept"] == r["kept"] and o["unique_seeds"] == r["unique_seeds"] and o["total_frequency"] == r["total_frequency"]
         eh, ec = cpu.seed_table(cb, co, 19, 8, 0, 3)
         assert np.array_equal(eh, r["table_hash"]) and np.array_equal(ec, r["table_count"])
+
+
+def test_seed_mask_fraction_matches_reference_placeLite_at_a_tie_free_cut():
+    """--seed-mask-fraction (placement.cpp:1748-1799): the reference sorts by count only, so the masked set is only defined when
+    the cut does not fall inside a group of equal counts; fractions are chosen so that it does not, and then everything must match"""
+    from tools.synth import synth
+    import panmap_b200 as pm
+    S = synth.generate(900, 5000, 1.5, 4000, k=19, s=8, l=3, seed=9)
+    off = S.read_offsets.astype(np.int64); buf = S.reads.tobytes()
+    reads = [buf[off[i]:off[i + 1]] for i in range(4000)]
+    rb, ro = pm.pack_reads(reads)
+    eh, ec = cpu.seed_table(rb, ro, 19, 8, 0, 3)
+    U = eh.size
+    desc = np.sort(ec)[::-1]
+    cuts = [int(m) for m in np.nonzero(desc[:-1] > desc[1:])[0] + 1]          # M seeds masked <=> desc[M-1] > desc[M]
+    assert len(cuts) >= 3
+    picks = [cuts[0], cuts[len(cuts) // 2], cuts[-1]]
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "s.idx"); ref.write_index(p, S)
+        fq = os.path.join(td, "r.fastq"); _fastq(fq, reads)
+        R = ref.RefIndex(p)
+        for M in picks:
+            frac = (M + 0.5) / U
+            assert int(frac * U) == M
+            r = R.place(fq, seed_mask_fraction=frac)
+            o = cpu.place(rb, ro, S, seed_mask_fraction=frac)
+            assert o["unique_seeds"] == r["unique_seeds"] == U - M
+            assert o["kept"] == r["kept"] and o["total_frequency"] == r["total_frequency"], M
+            assert np.array_equal(o["best_index"], r["best_index"]), M
+            assert all(np.array_equal(o["tied"][m], r["tied"][m]) for m in range(5)), M
+            assert H.relerr(o["best_score"], r["best_score"]).max() < 1e-12
+            mh, mc = cpu.mask_top_seeds(eh, ec, frac)
+            assert np.array_equal(mh, r["table_hash"]) and np.array_equal(mc, r["table_count"]), M
+        R.close()
