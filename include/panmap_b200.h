@@ -76,7 +76,7 @@ typedef struct pm_place_params {
     uint32_t skip_node_index;  /* leave-one-out node, PM_NONE = none (placement.hpp:91) */
     double seed_mask_fraction; /* seedMaskFraction (placement.cpp:1748-1799); CLI default 0 (main.cpp:1967); ties at the cut: smaller hash first */
     int32_t want_node_scores;  /* keep the [n_nodes][5] f64 score matrix for pm_get_node_scores */
-    int32_t reserved;
+    int32_t min_seed_quality;  /* minSeedQuality (placement.hpp:37): min average Phred over a seed's k bases; 0 = off; needs pm_place_quality */
 } pm_place_params;
 
 /* == the scalar part of placement::PlacementResult (placement.hpp:157-235) */
@@ -130,6 +130,12 @@ void pm_workspace_destroy(pm_workspace* ws);
  *      Buffers are HOST memory; the call uploads them, runs every stage on the GPU and returns the result. */
 int pm_place(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads,
              const pm_place_params* params, pm_place_result* result);
+/* The same with per-base qualities for --min-seed-quality (placement.cpp:1179-1240, 1388-1533): quals has one Phred+33 byte per base at the
+ * reads' offsets (a FASTQ record's quality line; for records without one the reference substitutes 'I', placement.cpp:211).
+ * With params->min_seed_quality <= 0 the qualities are ignored and this is pm_place.  On this path the reference does not deduplicate
+ * reads, so dedup_reads has no effect.  pm_place with min_seed_quality > 0 returns PM_ERR_INVALID. */
+int pm_place_quality(pm_workspace* ws, const char* reads, const char* quals, const uint64_t* read_offsets, uint64_t n_reads,
+                     const pm_place_params* params, pm_place_result* result);
 /* "inputs already resident in HBM": pm_reads_upload copies + lays out the reads once (untimed by callers that
  * measure device throughput), pm_place_resident then runs every stage on them; may be called repeatedly. */
 int pm_reads_upload(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads);

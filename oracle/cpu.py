@@ -25,6 +25,7 @@ def lib():
         L.orc_rolling_syncmers.restype = C.c_int64
         L.orc_read_seeds.restype = C.c_int64
         L.orc_seed_table.restype = C.c_int64
+        L.orc_seed_table_quality.restype = C.c_int64
         L.orc_mask_top_seeds.restype = C.c_int64
         L.orc_resolve_min_read_support.restype = C.c_int64
         L.orc_select_chain.restype = C.c_int64
@@ -67,11 +68,18 @@ def read_seeds(seq, k, s, t, l, open=False, trim_start=0, trim_end=0):
     return out[:n]
 
 
-def seed_table(reads, offsets, k, s, t, l, open=False, trim_start=0, trim_end=0, dedup=False):
+def seed_table(reads, offsets, k, s, t, l, open=False, trim_start=0, trim_end=0, dedup=False, quals=None, min_seed_quality=0):
+    """quals + min_seed_quality > 0: the --min-seed-quality construction (placement.cpp:1179-1240, 1388-1533), which ignores dedup"""
     reads = np.ascontiguousarray(reads, np.uint8); offsets = np.ascontiguousarray(offsets, np.uint64)
     ph, pc = C.c_void_p(), C.c_void_p()
-    U = lib().orc_seed_table(_p(reads), _p(offsets), C.c_uint64(offsets.size - 1), k, s, t, l, int(bool(open)), trim_start, trim_end,
-                             int(bool(dedup)), C.byref(ph), C.byref(pc))
+    if quals is not None and min_seed_quality > 0:
+        quals = np.ascontiguousarray(quals, np.uint8)
+        assert quals.size == reads.size
+        U = lib().orc_seed_table_quality(_p(reads), _p(quals), _p(offsets), C.c_uint64(offsets.size - 1), k, s, t, l, int(bool(open)),
+                                         trim_start, trim_end, int(min_seed_quality), C.byref(ph), C.byref(pc))
+    else:
+        U = lib().orc_seed_table(_p(reads), _p(offsets), C.c_uint64(offsets.size - 1), k, s, t, l, int(bool(open)), trim_start, trim_end,
+                                 int(bool(dedup)), C.byref(ph), C.byref(pc))
     h = np.ctypeslib.as_array(C.cast(ph, C.POINTER(C.c_uint64)), shape=(max(U, 1),))[:U].copy()
     c = np.ctypeslib.as_array(C.cast(pc, C.POINTER(C.c_int64)), shape=(max(U, 1),))[:U].copy()
     lib().orc_free(ph); lib().orc_free(pc)
@@ -131,7 +139,7 @@ def select_chain(order, score):
 
 
 def place(reads, offsets, idx, trim_start=0, trim_end=0, dedup=False, min_read_support=-1, seed_mask_fraction=0.0,
-          force_leaf=False, skip_node=0xFFFFFFFF, want_scores=False):
+          force_leaf=False, skip_node=0xFFFFFFFF, want_scores=False, quals=None, min_seed_quality=0):
     """orc_place: the compute part of placeLite on the CPU. idx has hash/parent/child/offsets/parent_index + k,s,t,l,open."""
     reads = np.ascontiguousarray(reads, np.uint8); offsets = np.ascontiguousarray(offsets, np.uint64)
     N = idx.parent_index.size
@@ -140,10 +148,14 @@ def place(reads, offsets, idx, trim_start=0, trim_end=0, dedup=False, min_read_s
     tied = np.zeros((5, cap), np.uint32)
     scores = np.zeros((max(N, 1), 5), np.float64) if want_scores else None
     stats = np.zeros(7, np.float64)
-    lib().orc_place(_p(reads), _p(offsets), C.c_uint64(offsets.size - 1), _p(idx.hash), _p(idx.parent), _p(idx.child), _p(idx.offsets),
-                    _p(idx.parent_index), C.c_uint64(N), idx.k, idx.s, idx.t, idx.l, int(idx.open), trim_start, trim_end, int(bool(dedup)),
-                    min_read_support, C.c_double(seed_mask_fraction), int(bool(force_leaf)), C.c_uint32(skip_node), _p(best), _p(bidx),
-                    _p(tcount), _p(tied), C.c_int64(cap), _p(scores) if scores is not None else None, _p(stats))
+    if quals is not None:
+        quals = np.ascontiguousarray(quals, np.uint8)
+        assert quals.size == reads.size
+    lib().orc_place_q(_p(reads), _p(quals) if quals is not None else None, _p(offsets), C.c_uint64(offsets.size - 1), _p(idx.hash),
+                      _p(idx.parent), _p(idx.child), _p(idx.offsets), _p(idx.parent_index), C.c_uint64(N), idx.k, idx.s, idx.t, idx.l,
+                      int(idx.open), trim_start, trim_end, int(bool(dedup)), min_read_support, C.c_double(seed_mask_fraction),
+                      int(bool(force_leaf)), C.c_uint32(skip_node), int(min_seed_quality), _p(best), _p(bidx),
+                      _p(tcount), _p(tied), C.c_int64(cap), _p(scores) if scores is not None else None, _p(stats))
     return dict(best_score=best, best_index=bidx, tied=[tied[m, :tcount[m]].copy() for m in range(5)], scores=scores,
                 unique_seeds=int(stats[0]), min_support=int(stats[1]), kept=int(stats[2]), magnitude=stats[3], log_sum=stats[4],
                 wc_denominator=stats[5], total_frequency=int(stats[6]))

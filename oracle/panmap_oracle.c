@@ -170,6 +170,57 @@ static int cmp_u64(const void* a, const void* b) {
     return x < y ? -1 : x > y;
 }
 
+/* ---- placement.cpp:79-88 avgPhredQuality: mean of (signed char) qual - 33 over the k-mer span; 0.0 when the span
+ * does not fit the quality string ---- */
+double orc_avg_phred(const char* qual, i64 qlen, i64 startPos, int k) {
+    if (qlen == 0 || startPos < 0 || startPos + k > qlen) return 0.0;
+    i64 sum = 0;
+    for (int i = 0; i < k; i++) sum += (int)qual[startPos + i] - 33;
+    return (double)sum / k;
+}
+
+/* ---- placement.cpp:1179-1240 (l==0) and :1388-1533 (l>=1) with --min-seed-quality > 0: seeds of ONE read ------
+ * A syncmer "passes" when its start lies in [trimStart, len-trimEnd-k] and the average Phred quality over its k
+ * bases is >= minQ.  l<=1: every passing syncmer is a seed.  l>1: k-min-mers over windows of l CONSECUTIVE syncmers of
+ * the unrestricted list, kept only when all l of them pass (unlike the default path, which closes the list up after the
+ * trim filter); needs >= l syncmers in the read (:1428).  Reads are never deduplicated on this path. */
+i64 orc_read_seeds_quality(const char* seq, const char* qual, i64 len, int k, int s, int t, int l, int open, int trimStart,
+                           int trimEnd, int minQ, u64* out, i64 cap) {
+    if (len < k) return 0;
+    const i64 maxw = len - k + 1;
+    u64* h = (u64*)malloc(sizeof(u64) * (size_t)maxw);
+    uint8_t* b1 = (uint8_t*)malloc((size_t)maxw);
+    uint8_t* b2 = (uint8_t*)malloc((size_t)maxw);
+    i64* ps = (i64*)malloc(sizeof(i64) * (size_t)maxw);
+    uint8_t* pass = (uint8_t*)malloc((size_t)maxw);
+    const i64 m = orc_rolling_syncmers(seq, len, k, s, open, t, 0, h, b1, b2, ps, maxw);
+    const int validStart = trimStart;
+    const int validEnd = (int)len - trimEnd - k;
+    for (i64 j = 0; j < m; j++) {
+        const int sp = (int)ps[j];
+        pass[j] = (uint8_t)(sp >= validStart && sp <= validEnd && !(orc_avg_phred(qual, len, ps[j], k) < (double)minQ));
+    }
+    i64 n = 0;
+    if (l <= 1) {
+        for (i64 j = 0; j < m; j++) if (pass[j]) { if (n < cap) out[n] = h[j]; n++; }
+    } else if (m >= l) {
+        for (i64 j = 0; j + l <= m; j++) {
+            int ok = 1;
+            for (int w = 0; w < l; w++) ok &= pass[j + w];
+            if (!ok) continue;
+            u64 fw = 0, rw = 0;
+            for (int w = 0; w < l; w++) {
+                fw ^= orc_rol(h[j + w], (u64)k * (u64)(l - 1 - w));
+                rw ^= orc_rol(h[j + w], (u64)k * (u64)w);
+            }
+            if (fw != rw) { if (n < cap) out[n] = fw < rw ? fw : rw; n++; }
+        }
+    }
+    free(h); free(b1); free(b2); free(ps); free(pass);
+    return n;
+}
+
+
 /* ---- placement.cpp:1550-1722 : reads -> seedFreqInReads (hash -> count), sorted by hash -----------------
  * reads = concatenated bytes, off[n_reads+1].  Counting every read occurrence equals the reference's
  * dedup-then-multiply (:1550-1620); with dedup!=0 each distinct sequence counts once (:1619).
@@ -186,6 +237,26 @@ static int cmp_read(const void* a, const void* b, void* ctx) {
     return li < lj ? -1 : li > lj;
 }
 void orc_free(void* p) { free(p); }
+
+/* seed instances -> (hash, count) sorted by hash, minus the four homopolymer k-mer hashes (:1708-1718); frees inst */
+static i64 table_from_instances(u64* inst, u64 nInst, int k, u64** outHash, i64** outCount) {
+    qsort(inst, (size_t)nInst, sizeof(u64), cmp_u64);
+    u64 homo[4];
+    orc_homopolymer_hashes(k, homo);
+    u64* H = (u64*)malloc(sizeof(u64) * (size_t)(nInst ? nInst : 1));
+    i64* C = (i64*)malloc(sizeof(i64) * (size_t)(nInst ? nInst : 1));
+    i64 U = 0;
+    for (u64 i = 0; i < nInst;) {
+        u64 j = i;
+        while (j < nInst && inst[j] == inst[i]) j++;
+        const u64 hsh = inst[i];
+        if (hsh != homo[0] && hsh != homo[1] && hsh != homo[2] && hsh != homo[3]) { H[U] = hsh; C[U] = (i64)(j - i); U++; }
+        i = j;
+    }
+    free(inst);
+    *outHash = H; *outCount = C;
+    return U;
+}
 
 i64 orc_seed_table(const char* reads, const u64* off, u64 n_reads, int k, int s, int t, int l, int open,
                    int trimStart, int trimEnd, int dedup, u64** outHash, i64** outCount) {
@@ -210,22 +281,20 @@ i64 orc_seed_table(const char* reads, const u64* off, u64 n_reads, int k, int s,
         }
         free(order);
     }
-    qsort(inst, (size_t)nInst, sizeof(u64), cmp_u64);
-    u64 homo[4];
-    orc_homopolymer_hashes(k, homo);
-    u64* H = (u64*)malloc(sizeof(u64) * (size_t)(nInst ? nInst : 1));
-    i64* C = (i64*)malloc(sizeof(i64) * (size_t)(nInst ? nInst : 1));
-    i64 U = 0;
-    for (u64 i = 0; i < nInst;) {
-        u64 j = i;
-        while (j < nInst && inst[j] == inst[i]) j++;
-        const u64 hsh = inst[i];
-        if (hsh != homo[0] && hsh != homo[1] && hsh != homo[2] && hsh != homo[3]) { H[U] = hsh; C[U] = (i64)(j - i); U++; }
-        i = j;
-    }
-    free(inst);
-    *outHash = H; *outCount = C;
-    return U;
+    return table_from_instances(inst, nInst, k, outHash, outCount);
+}
+
+/* same with --min-seed-quality > 0 (quals: one byte per base, same offsets as the reads) */
+i64 orc_seed_table_quality(const char* reads, const char* quals, const u64* off, u64 n_reads, int k, int s, int t, int l, int open,
+                           int trimStart, int trimEnd, int minQ, u64** outHash, i64** outCount) {
+    u64 capInst = 0;
+    for (u64 i = 0; i < n_reads; i++) { const u64 L = off[i + 1] - off[i]; if (L >= (u64)k) capInst += L - (u64)k + 1; }
+    u64* inst = (u64*)malloc(sizeof(u64) * (size_t)(capInst ? capInst : 1));
+    u64 nInst = 0;
+    for (u64 i = 0; i < n_reads; i++)
+        nInst += (u64)orc_read_seeds_quality(reads + off[i], quals + off[i], (i64)(off[i + 1] - off[i]), k, s, t, l, open, trimStart, trimEnd,
+                                             minQ, inst + nInst, (i64)(capInst - nInst));
+    return table_from_instances(inst, nInst, k, outHash, outCount);
 }
 
 /* ---- placement.cpp:1748-1799 : mask the top floor(frac*U) seeds by count --------------------------------
@@ -402,13 +471,15 @@ i64 orc_select_chain(const u32* order, const double* score, i64 n, double* bestS
  * leave-one-out index (ORC_NONE = none).  tied: [5][tiedCap]; nodeScores (may be NULL): [N][5].
  * stats: [0]=U (unique seeds after homopolymer/mask) [1]=minSupport [2]=U' [3]=logReadMagnitude
  *        [4]=logContDenom [5]=wcDenom [6]=totalReadSeedFrequency */
-int orc_place(const char* reads, const u64* readOff, u64 n_reads,
-              const u64* dHash, const int16_t* dParent, const int16_t* dChild, const u64* off, const u32* parentIdx, u64 N,
-              int k, int s, int t, int l, int open, int trimStart, int trimEnd, int dedup, int minReadSupport,
-              double seedMaskFraction, int forceLeaf, u32 skipNode,
-              double* bestScore, u32* bestIdx, i64* tiedCount, u32* tied, i64 tiedCap, double* nodeScores, double* stats) {
+int orc_place_q(const char* reads, const char* quals, const u64* readOff, u64 n_reads,
+                const u64* dHash, const int16_t* dParent, const int16_t* dChild, const u64* off, const u32* parentIdx, u64 N,
+                int k, int s, int t, int l, int open, int trimStart, int trimEnd, int dedup, int minReadSupport,
+                double seedMaskFraction, int forceLeaf, u32 skipNode, int minSeedQuality,
+                double* bestScore, u32* bestIdx, i64* tiedCount, u32* tied, i64 tiedCap, double* nodeScores, double* stats) {
     u64* H; i64* C;
-    i64 U = orc_seed_table(reads, readOff, n_reads, k, s, t, l, open, trimStart, trimEnd, dedup, &H, &C);
+    i64 U = (minSeedQuality > 0 && quals)   /* placement.cpp:1179,1388: the quality path replaces the seed construction (and ignores dedup) */
+                ? orc_seed_table_quality(reads, quals, readOff, n_reads, k, s, t, l, open, trimStart, trimEnd, minSeedQuality, &H, &C)
+                : orc_seed_table(reads, readOff, n_reads, k, s, t, l, open, trimStart, trimEnd, dedup, &H, &C);
     if (n_reads > 0) U = orc_mask_top_seeds(H, C, U, seedMaskFraction);
     const i64 ms = orc_resolve_min_read_support(C, U, minReadSupport);
     double* logv = (double*)malloc(sizeof(double) * (size_t)(U ? U : 1));
@@ -437,4 +508,13 @@ int orc_place(const char* reads, const u64* readOff, u64 n_reads,
     free(H); free(C); free(logv); free(metrics); if (!nodeScores) free(scores);
     free(order); free(hasChild); free(eo); free(es);
     return 0;
+}
+
+int orc_place(const char* reads, const u64* readOff, u64 n_reads,
+              const u64* dHash, const int16_t* dParent, const int16_t* dChild, const u64* off, const u32* parentIdx, u64 N,
+              int k, int s, int t, int l, int open, int trimStart, int trimEnd, int dedup, int minReadSupport,
+              double seedMaskFraction, int forceLeaf, u32 skipNode,
+              double* bestScore, u32* bestIdx, i64* tiedCount, u32* tied, i64 tiedCap, double* nodeScores, double* stats) {
+    return orc_place_q(reads, NULL, readOff, n_reads, dHash, dParent, dChild, off, parentIdx, N, k, s, t, l, open, trimStart, trimEnd, dedup,
+                       minReadSupport, seedMaskFraction, forceLeaf, skipNode, 0, bestScore, bestIdx, tiedCount, tied, tiedCap, nodeScores, stats);
 }

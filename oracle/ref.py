@@ -103,11 +103,13 @@ class RefIndex:
             self.h = None
 
     def place(self, r1, r2="", out_tsv="/dev/null", threads=1, min_read_support=-1, seed_mask_fraction=0.0, trim_start=0, trim_end=0,
-              dedup=False, force_leaf=False):
+              dedup=False, force_leaf=False, min_seed_quality=0):
         """the reference placement::placeLite with CLI-default options"""
         o = PlaceOut()
+        lib().ref_set_min_seed_quality(int(min_seed_quality))
         k = lib().ref_place(self.h, os.fsencode(r1), os.fsencode(r2), os.fsencode(out_tsv), threads, min_read_support,
                             seed_mask_fraction, trim_start, trim_end, int(dedup), int(force_leaf), 0, C.byref(o))
+        lib().ref_set_min_seed_quality(0)
         if not k:
             raise RuntimeError(lib().ref_last_error().decode())
         tied = []

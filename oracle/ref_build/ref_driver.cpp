@@ -114,6 +114,8 @@ struct RefPlaceOut {
 };
 
 // reference placement::placeLite with CLI-default params; tied index lists / seed table fetched afterwards
+int g_minSeedQuality = 0;   // --min-seed-quality of the next ref_place calls (0 = off, the CLI default)
+void ref_set_min_seed_quality(int q) { g_minSeedQuality = q; }
 struct RefPlaceKeep { placement::PlacementResult res; };
 void* ref_place(void* h, const char* r1, const char* r2, const char* outTsv, int threads, int minReadSupport,
                 double seedMaskFraction, int trimStart, int trimEnd, int dedup, int forceLeaf, int storeDiag,
@@ -127,6 +129,7 @@ void* ref_place(void* h, const char* r1, const char* r2, const char* outTsv, int
         tp.minReadSupport = minReadSupport;
         tp.trimStart = trimStart; tp.trimEnd = trimEnd; tp.dedupReads = dedup != 0; tp.forceLeaf = forceLeaf != 0;
         tp.store_diagnostics = storeDiag != 0;
+        tp.minSeedQuality = g_minSeedQuality;
         std::string o = outTsv ? outTsv : "";
         auto t0 = std::chrono::steady_clock::now();
         placement::placeLite(K->res, &L->tree, *L->rd, r1 ? r1 : "", r2 ? r2 : "", o, tp, nullptr);

@@ -40,7 +40,7 @@ class PlaceParams(C.Structure):
     """== placement::TraversalParams (placement.hpp:28-54), hot-path subset; defaults are the CLI defaults."""
     _fields_ = [("trim_start", C.c_int32), ("trim_end", C.c_int32), ("min_read_support", C.c_int32), ("dedup_reads", C.c_int32),
                 ("force_leaf", C.c_int32), ("skip_node_index", C.c_uint32), ("seed_mask_fraction", C.c_double),
-                ("want_node_scores", C.c_int32), ("reserved", C.c_int32)]
+                ("want_node_scores", C.c_int32), ("min_seed_quality", C.c_int32)]
 
     def __init__(self, **kw):
         super().__init__()
@@ -88,6 +88,7 @@ def lib():
     L.pm_workspace_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.pm_workspace_destroy.argtypes = [C.c_void_p]
     L.pm_place.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_place_quality.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
     L.pm_reads_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_place_resident.argtypes = [C.c_void_p, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
     L.pm_get_tied.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
@@ -293,6 +294,17 @@ class Workspace:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         res = PlaceResult()
         _ck(lib().pm_place(self._h, _ptr(reads), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params), C.byref(res)))
+        return self._finish(res)
+
+    def place_quality(self, reads, quals, offsets, params):
+        """--min-seed-quality: quals = one Phred+33 byte per base at the reads' offsets (pm_place_quality)"""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8); quals = np.ascontiguousarray(quals, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if quals.size != reads.size:
+            raise ValueError("quals must have one byte per base")
+        res = PlaceResult()
+        _ck(lib().pm_place_quality(self._h, _ptr(reads), _ptr(quals), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params),
+                                   C.byref(res)))
         return self._finish(res)
 
     def place_raw(self, reads_ptr, offsets_ptr, n_reads, params):

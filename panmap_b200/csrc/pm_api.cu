@@ -120,6 +120,7 @@ struct pm_workspace {
     DevBuf<u32> tieNode; u32 tieCap = 0; DevBuf<u32> selCounts;
     DevBuf<u64> expHash; DevBuf<long long> expCount; DevBuf<unsigned> expCounter;
     DevBuf<unsigned long long> maskScratch;   // --seed-mask-fraction only
+    DevBuf<char> quals; DevBuf<unsigned char> synPass; bool useQuals = false;   // --min-seed-quality only (pm_place_quality)
     // host staging (pinned)
     PinBuf<unsigned char> hStage; PinBuf<u32> hTies; PinBuf<unsigned char> hRec;
     // results of the last sample
@@ -364,19 +365,27 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
         launchTableClear(W->view, W->st);
     }
-    unsigned char* dup = prepareDedup(W, W->nReads, prm);
+    const bool quality = W->useQuals && prm.min_seed_quality > 0;   // the reference's quality path never deduplicates (placement.cpp:1388)
+    unsigned char* dup = quality ? nullptr : prepareDedup(W, W->nReads, prm);
     const u64* endOff = nullptr;
     if (I->F.sp.hpc) {   // in place and idempotent: resident reads may be placed many times
         W->endOff.ensure(W->nReads + 1);
-        launchHpcCompress(W->reads.p, W->off.p, W->nReads, W->endOff.p, W->st);
+        launchHpcCompress(W->reads.p, W->off.p, W->nReads, W->endOff.p, W->st, quality ? W->quals.p : nullptr);
         endOff = W->endOff.p;
     }
     if (dup) launchDedup(W->reads.p, W->off.p, 0, W->nReads, W->dedupSlots.p, W->dedupMask, dup, W->st, endOff);
-    const bool ascii = seedTableReadsAscii(P);
+    const bool ascii = seedTableReadsAscii(P) && !quality;
     CK(cudaEventRecord(W->evK[0], W->st));
     if (!ascii) launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st, endOff);
     CK(cudaEventRecord(W->evK[1], W->st));
-    launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup, endOff, ascii ? W->reads.p : nullptr);
+    if (quality) {
+        W->synPass.ensure(W->nChunks * 32 + 32);
+        launchSeedTableQuality(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, endOff, W->quals.p,
+                               prm.min_seed_quality, W->synPass.p);
+        CK(cudaEventRecord(W->evK[2], W->st));
+    } else {
+        launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup, endOff, ascii ? W->reads.p : nullptr);
+    }
     CK(cudaEventRecord(W->evK[3], W->st));
 }
 
@@ -459,6 +468,7 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
     pm_index* I = W->idx;
     setDevice(I->device);
     checkParams(prm);
+    if (prm->min_seed_quality > 0 && !W->useQuals) throw std::runtime_error("min_seed_quality > 0 needs the base qualities: call pm_place_quality");
     if (!res) throw std::runtime_error("null result");
     std::memset(res, 0, sizeof(*res));
     W->wantMetrics = false;
@@ -627,6 +637,22 @@ int pm_place(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, 
              pm_place_result* result) {
     if (!ws || !read_offsets || (!reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");
     return guarded([&]() -> int { return runPlace(ws, params, result, false, reads, read_offsets, n_reads); });
+}
+int pm_place_quality(pm_workspace* ws, const char* reads, const char* quals, const uint64_t* read_offsets, uint64_t n_reads,
+                     const pm_place_params* params, pm_place_result* result) {
+    if (!params || params->min_seed_quality <= 0) return pm_place(ws, reads, read_offsets, n_reads, params, result);
+    if (!ws || !read_offsets || ((!reads || !quals) && n_reads)) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        uploadReads(ws, reads, read_offsets, n_reads);   // an optional mode: plain upload, then the resident stages
+        const u64 total = n_reads ? read_offsets[n_reads] : 0;
+        ws->quals.ensure(total + 64);
+        if (total) CK(cudaMemcpyAsync(ws->quals.p, quals, total, cudaMemcpyHostToDevice, ws->st));
+        ws->residentValid = false;   // hpc indexes compress reads and qualities in place: not reusable by pm_place_resident
+        ws->useQuals = true;
+        struct Reset { pm_workspace* w; ~Reset() { w->useQuals = false; } } reset{ws};
+        return runPlace(ws, params, result, true, nullptr, nullptr, 0);
+    });
 }
 int pm_reads_upload(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads) {
     if (!ws || !read_offsets || (!reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");

@@ -185,7 +185,9 @@ void launchChunkOffsets(const u64* off, u64 n, u64 gBase, u64* tileSum, u64* pac
 // seeding.cpp:286-306): a base is dropped when it equals its predecessor ignoring case.  One warp per read, in place inside the
 // read's own byte range (the write position never overtakes the read position); endOff[r] = one past the last kept byte.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) hpc_compress(char* __restrict__ reads, const u64* __restrict__ off, u64 nReads, u64* __restrict__ endOff) {
+// quals (optional, --min-seed-quality): the quality of the first base of every run moves along with it (placement.cpp:1147-1159)
+__global__ void __launch_bounds__(256) hpc_compress(char* __restrict__ reads, const u64* __restrict__ off, u64 nReads, u64* __restrict__ endOff,
+                                                    char* __restrict__ quals) {
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
     for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nReads; r += warpsTotal) {
@@ -195,13 +197,14 @@ __global__ void __launch_bounds__(256) hpc_compress(char* __restrict__ reads, co
         for (u64 i0 = 0; i0 < L; i0 += 32) {
             const u64 i = i0 + lane;
             const int c = i < L ? (int)(unsigned char)reads[b + i] : -2;
+            const char qc = (quals && i < L) ? quals[b + i] : 0;
             const int up = (c >= 'a' && c <= 'z') ? c - 32 : c;
             int before = __shfl_up_sync(0xffffffffu, up, 1);
             if (lane == 0) before = prevUp;
             const bool keep = i < L && up != before;
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             __syncwarp();
-            if (keep) reads[b + written + __popc(m & ((1u << lane) - 1u))] = (char)c;
+            if (keep) { const u64 o = b + written + __popc(m & ((1u << lane) - 1u)); reads[o] = (char)c; if (quals) quals[o] = qc; }
             __syncwarp();
             written += __popc(m);
             prevUp = __shfl_sync(0xffffffffu, up, 31);
@@ -209,10 +212,10 @@ __global__ void __launch_bounds__(256) hpc_compress(char* __restrict__ reads, co
         if (lane == 0) endOff[r] = b + written;
     }
 }
-void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st) {
+void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st, char* quals) {
     if (nReads == 0) return;
     u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
-    hpc_compress<<<(unsigned)g, 256, 0, st>>>(reads, off, nReads, endOff);
+    hpc_compress<<<(unsigned)g, 256, 0, st>>>(reads, off, nReads, endOff, quals);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -295,13 +298,17 @@ void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsign
 constexpr int kSeedThreads = 128;
 
 // generic (any k <= 32, s, t, open/closed).  MODE 0: hashes -> synBuf (+ count); MODE 1: (hash, isReverse, pos) lists.
+// MODE 3 (--min-seed-quality, placement.cpp:1179-1240 / 1388-1533): EVERY syncmer goes to synBuf, and outRev[same index] says whether
+// it "passes": start inside the trimmed range and average Phred quality over its k bases >= minQ.  (int)(signed char)q - 33 summed
+// over k bases and compared with minQ * k is the reference's `double(sum) / k < minQ` exactly (|sum / k - minQ| >= 1/k when unequal).
 template <int MODE>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                                  const u64* __restrict__ packedOff, const u64* __restrict__ winOff,
                                                                  u64 nReads, SeederParams P, const SeedTables* __restrict__ gT,
                                                                  u64* __restrict__ synBuf, unsigned* __restrict__ synCount,
                                                                  u64* outHash, unsigned char* outRev, long long* outPos, u64* outCount,
-                                                                 const unsigned char* __restrict__ dup, const u64* __restrict__ endOff) {
+                                                                 const unsigned char* __restrict__ dup, const u64* __restrict__ endOff,
+                                                                 const char* __restrict__ quals, int minQualSum) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
     u64* rings = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables));
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
         ReadSeederT<kSeedThreads> sd;
         sd.reset(rings + threadIdx.x, P.w);
         unsigned cnt = 0;
-        const u64 obase = MODE == 0 ? pOff * 32 : (valid ? winOff[r] : 0);
+        const u64 obase = (MODE == 0 || MODE == 3) ? pOff * 32 : (valid ? winOff[r] : 0);
 #pragma unroll 1
         for (int c = 0; c < nChMax; ++c) {
             uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -347,13 +354,20 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
                         if (sd.pushBase(i, code, T, P, h, rev)) {
                             const int pos = i - P.k + 1;
                             if (MODE == 1) { outHash[obase + cnt] = h; outRev[obase + cnt] = rev ? 1 : 0; outPos[obase + cnt] = pos; ++cnt; }
+                            else if (MODE == 3) {
+                                int qs = 0;
+                                for (int q = 0; q < P.k; ++q) qs += (int)(signed char)quals[b + pos + q] - 33;
+                                synBuf[obase + cnt] = h;
+                                outRev[obase + cnt] = (pos >= P.trimStart && pos <= validEnd && qs >= minQualSum) ? 1 : 0;
+                                ++cnt;
+                            }
                             else if (pos >= P.trimStart && pos <= validEnd) { synBuf[obase + cnt] = h; ++cnt; }
                         }
                     }
                 }
             }
         }
-        if (valid) { if (MODE == 0) synCount[r] = cnt; else outCount[r] = cnt; }
+        if (valid) { if (MODE == 0 || MODE == 3) synCount[r] = cnt; else outCount[r] = cnt; }
     }
 }
 
@@ -529,7 +543,9 @@ template <int MODE, int KT, int LT>
 __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
                                                            const u64* __restrict__ packedOff, const u64* __restrict__ winOff, u64 nReads,
                                                            int kRt, int lRt, TableSlot* table, u64 mask, SampleAcc* acc,
-                                                           u64* outHash, u64* outCount, cudaTextureObject_t tableTex) {
+                                                           u64* outHash, u64* outCount, cudaTextureObject_t tableTex,
+                                                           const unsigned char* __restrict__ pass = nullptr) {
+    // pass (--min-seed-quality only, same indexing as synBuf): a window counts only when all of its syncmers pass
     const int k = KT > 0 ? KT : kRt, l = KT > 0 ? LT : lRt;
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
@@ -538,8 +554,10 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
         const u64* __restrict__ h = synBuf + packedOff[r] * 32;
         const int nSeeds = l <= 1 ? n : (n >= l ? n - l + 1 : 0);
         u64 written = 0;
+        const unsigned char* __restrict__ pp = pass ? pass + packedOff[r] * 32 : nullptr;
         auto seedAt = [&](int j, u64& seed) -> bool {
             if (j >= nSeeds) return false;
+            if (pp) { for (int w = 0; w < (l <= 1 ? 1 : l); ++w) if (!pp[j + w]) return false; }
             if (l <= 1) { seed = h[j]; return true; }
             u64 fw = 0, rw = 0;
             if (KT > 0) {
@@ -869,7 +887,7 @@ static void launchSyncmers(const uint4* packed, const u64* off, const u64* packe
     const size_t sm = genericSmemBytes(P);
     cudaFuncSetAttribute(syncmers_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
-                                                                     nullptr, nullptr, nullptr, dup, endOff);
+                                                                     nullptr, nullptr, nullptr, dup, endOff, nullptr, 0);
 }
 // reads -> count table: syncmer lists per read, then their seeds into the table.  (Running the two as one kernel, or concurrently
 // on two streams, was measured and is slower: both are limited by the same L1/LSU data pipe and the hashing needs every warp an
@@ -882,6 +900,20 @@ void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, 
     if (between) cudaEventRecord(between, st);
     launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, st);
 }
+// --min-seed-quality > 0 (off by default): the generic kernels with per-syncmer pass flags; quals has one byte per base at the reads'
+// offsets (compressed in lockstep for hpc indexes), synPass one byte per synBuf entry
+void launchSeedTableQuality(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
+                            const SeedTables* dTables, WorkspaceView W, cudaStream_t st, const u64* endOff, const char* quals,
+                            int minSeedQuality, unsigned char* synPass) {
+    if (nReads == 0) return;
+    const size_t sm = genericSmemBytes(P);
+    cudaFuncSetAttribute(syncmers_generic<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    syncmers_generic<3><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dTables, W.synBuf, W.synCount,
+                                                                     nullptr, synPass, nullptr, nullptr, nullptr, endOff, quals, minSeedQuality * P.k);
+    u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
+    seeds_from_syncmers<0, 0, 0><<<(unsigned)(g ? g : 1), 256, 0, st>>>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table,
+                                                                         W.tableMask, W.acc, nullptr, nullptr, W.tableTex, synPass);
+}
 // mode 1: syncmer (hash, isReverse, pos) lists == seeding::rollingSyncmers(returnAll=false); mode 2: per-read seed lists
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
                     const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
@@ -891,7 +923,7 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
         const size_t sm = genericSmemBytes(P);
         cudaFuncSetAttribute(syncmers_generic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         syncmers_generic<1><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr, nullptr,
-                                                                         outHash, outRev, outPos, outCount, nullptr, nullptr);
+                                                                         outHash, outRev, outPos, outCount, nullptr, nullptr, nullptr, 0);
     } else {
         launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, nullptr, nullptr, st);
         launchSeedsFromSyncmers<2>(synBuf, synCount, packedOff, winOff, nReads, P.k, P.l, nullptr, 0, nullptr, outHash, outCount, 0, st);

@@ -119,11 +119,15 @@ struct PlaceOpts {
 // endOff (optional, everywhere below): end of read r when it is shorter than off[r+1] - off[r] (homopolymer-compressed in place)
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,
                      uint4* packed, cudaStream_t st, const u64* endOff = nullptr);
-void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st);
+void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st, char* quals = nullptr);
 void launchChunkOffsets(const u64* off, u64 n, u64 gBase, u64* tileSum /* [n/4096 + 1] scratch */, u64* packedOff, cudaStream_t st);
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between = nullptr,
                      const unsigned char* dup = nullptr, const u64* endOff = nullptr, const char* reads = nullptr);
+// --min-seed-quality > 0: needs the packed reads; quals = one byte per base at the reads' offsets, synPass = one byte per synBuf entry
+void launchSeedTableQuality(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
+                            const SeedTables* dTables, WorkspaceView W, cudaStream_t st, const u64* endOff, const char* quals,
+                            int minSeedQuality, unsigned char* synPass);
 // true when launchSeedTable can hash these parameters straight from the ASCII reads (pass `reads`, skip pack_reads)
 bool seedTableReadsAscii(const SeederParams& P);
 // --dedup: dup[r] = 1 when a byte-identical read holds the set already; reads [rBegin, rEnd) of the sample, `off` = all offsets

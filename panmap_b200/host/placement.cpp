@@ -15,7 +15,8 @@
 namespace {
 
 // kseq semantics (FASTA and FASTQ, multi-line sequences, gz or plain through zlib's transparent gzread)
-void readFastx(const std::string& path, std::vector<std::string>& out) {
+// quals (optional): the quality string of every record, 'I' * length when the record has none (extractFullFastqData, placement.cpp:199-238)
+void readFastx(const std::string& path, std::vector<std::string>& out, std::vector<std::string>* quals = nullptr) {
     gzFile f = gzopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("Failed to open FASTQ file: " + path);  // mgsr.hpp:175
     gzbuffer(f, 1 << 20);
@@ -37,12 +38,14 @@ void readFastx(const std::string& path, std::vector<std::string>& out) {
         p = lineEnd(p) + 1;  // header line
         std::string seq;
         while (p < N && data[p] != '>' && data[p] != '@' && data[p] != '+') { const size_t e = lineEnd(p); appendLine(seq, p, e); p = e + 1; }
+        std::string qual;
         if (p < N && data[p] == '+') {
             p = lineEnd(p) + 1;
-            size_t got = 0;
-            while (p < N && got < seq.size()) { const size_t e = lineEnd(p); std::string q; appendLine(q, p, e); got += q.size(); p = e + 1; }
+            while (p < N && qual.size() < seq.size()) { const size_t e = lineEnd(p); appendLine(qual, p, e); p = e + 1; }
             while (p < N && data[p] != '>' && data[p] != '@') p = lineEnd(p) + 1;
+            if (quals && qual.size() != seq.size()) break;   // kseq_read returns -2 (truncated quality): the reference's loop ends here
         }
+        if (quals) quals->push_back(qual.empty() ? std::string(seq.size(), 'I') : std::move(qual));
         out.push_back(std::move(seq));
     }
 }
@@ -51,36 +54,45 @@ void readFastx(const std::string& path, std::vector<std::string>& out) {
 
 namespace placement {
 
-void extractReadSequences(const std::string& readPath1, const std::string& readPath2, std::string& bases, std::vector<uint64_t>& offsets) {
-    std::vector<std::string> r;
-    readFastx(readPath1, r);
+void extractReadSequences(const std::string& readPath1, const std::string& readPath2, std::string& bases, std::vector<uint64_t>& offsets,
+                          std::string* quals) {
+    std::vector<std::string> r, q;
+    readFastx(readPath1, r, quals ? &q : nullptr);
     if (!readPath2.empty()) {
         const size_t fwd = r.size();
-        readFastx(readPath2, r);
+        readFastx(readPath2, r, quals ? &q : nullptr);
         if (r.size() != fwd * 2) throw std::runtime_error("File " + readPath2 + " does not contain the same number of reads as " + readPath1);
-        std::vector<std::string> canvas(r.size());  // seeding::perfect_shuffle (seeding.hpp:33-43)
-        for (size_t i = 0; i < fwd; ++i) { canvas[2 * i] = std::move(r[i]); canvas[2 * i + 1] = std::move(r[i + fwd]); }
-        r.swap(canvas);
+        auto shuffle = [&](std::vector<std::string>& v) {   // seeding::perfect_shuffle (seeding.hpp:33-43)
+            std::vector<std::string> canvas(v.size());
+            for (size_t i = 0; i < fwd; ++i) { canvas[2 * i] = std::move(v[i]); canvas[2 * i + 1] = std::move(v[i + fwd]); }
+            v.swap(canvas);
+        };
+        shuffle(r);
+        if (quals) shuffle(q);
     }
     offsets.assign(r.size() + 1, 0);
     size_t tot = 0;
     for (size_t i = 0; i < r.size(); ++i) { tot += r[i].size(); offsets[i + 1] = tot; }
     bases.clear(); bases.reserve(tot);
     for (auto& s : r) bases += s;
+    if (quals) { quals->clear(); quals->reserve(tot); for (auto& s : q) *quals += s; }
 }
 
 void placeLite(PlacementResult& result, DeviceIndex& index, const std::string& reads1, const std::string& reads2, std::string& outputPath,
                const TraversalParams& params) {
     if (!index.index || !index.workspace) throw std::runtime_error("placeLite: device index not initialised");
-    if (params.minSeedQuality > 0) throw std::runtime_error("--min-seed-quality is not implemented on the GPU path yet");
-    std::string bases; std::vector<uint64_t> off(1, 0);
-    if (!reads1.empty()) extractReadSequences(reads1, reads2, bases, off);
+    std::string bases, quals; std::vector<uint64_t> off(1, 0);
+    const bool quality = params.minSeedQuality > 0;   // placement.cpp:1131-1137: the quality strings are loaded only then
+    if (!reads1.empty()) extractReadSequences(reads1, reads2, bases, off, quality ? &quals : nullptr);
     pm_place_params p{};
     p.trim_start = params.trimStart; p.trim_end = params.trimEnd; p.min_read_support = params.minReadSupport;
     p.dedup_reads = params.dedupReads ? 1 : 0; p.force_leaf = params.forceLeaf ? 1 : 0; p.skip_node_index = PM_NONE;
     p.seed_mask_fraction = params.seedMaskFraction; p.want_node_scores = params.store_diagnostics ? 1 : 0;
+    p.min_seed_quality = quality && off.size() > 1 ? params.minSeedQuality : 0;   // no reads: `!allReadQualities.empty()` fails, default path
     pm_place_result r{};
-    if (pm_place(index.workspace, bases.data(), off.data(), off.size() - 1, &p, &r) != PM_OK) throw std::runtime_error(pm_last_error());
+    const int rc = p.min_seed_quality > 0 ? pm_place_quality(index.workspace, bases.data(), quals.data(), off.data(), off.size() - 1, &p, &r)
+                                          : pm_place(index.workspace, bases.data(), off.data(), off.size() - 1, &p, &r);
+    if (rc != PM_OK) throw std::runtime_error(pm_last_error());
     double* sc[5] = {&result.bestLogRawScore, &result.bestLogCosineScore, &result.bestContainmentScore, &result.bestWeightedContainmentScore,
                      &result.bestLogContainmentScore};
     uint32_t* ix[5] = {&result.bestLogRawNodeIndex, &result.bestLogCosineNodeIndex, &result.bestContainmentNodeIndex,
@@ -167,6 +179,7 @@ extern "C" int pm_place_files(pm_index* idx, pm_workspace* ws, const char* const
         placement::TraversalParams tp;
         tp.seedMaskFraction = prm ? prm->seed_mask_fraction : 0.0; tp.trimStart = prm ? prm->trim_start : 0; tp.trimEnd = prm ? prm->trim_end : 0;
         tp.minReadSupport = prm ? prm->min_read_support : -1; tp.forceLeaf = prm && prm->force_leaf; tp.dedupReads = prm && prm->dedup_reads;
+        tp.minSeedQuality = prm ? prm->min_seed_quality : 0;
         placement::PlacementResult R;
         std::string out = out_tsv ? out_tsv : "";
         placement::placeLite(R, D, reads1 ? reads1 : "", reads2 ? reads2 : "", out, tp);

@@ -53,6 +53,8 @@ void placeLite(PlacementResult& result, DeviceIndex& index, const std::string& r
 
 // extractReadSequences (placement.cpp:164-197): sequences of reads1 then reads2, pairs interleaved; throws on pair-count
 // mismatch (the reference prints the message and exit(1)s)
-void extractReadSequences(const std::string& readPath1, const std::string& readPath2, std::string& bases, std::vector<uint64_t>& offsets);
+// quals (optional) == extractFullFastqData (placement.cpp:199-238): the quality bytes at the same offsets, 'I' for records without
+void extractReadSequences(const std::string& readPath1, const std::string& readPath2, std::string& bases, std::vector<uint64_t>& offsets,
+                          std::string* quals = nullptr);
 
 }  // namespace placement

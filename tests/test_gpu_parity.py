@@ -116,6 +116,99 @@ def test_place_seed_mask_fraction_drops_the_most_frequent_seeds(frac):
     assert ws.place(*pm.pack_reads(reads), pm.PlaceParams(seed_mask_fraction=frac)).raw.unique_seeds == exp["unique_seeds"]
 
 
+def _quality_strings(rng, reads):
+    """blocks of good and bad base qualities so that k-mer windows straddle the threshold"""
+    out = []
+    for r in reads:
+        q = np.repeat(rng.choice([2, 12, 19, 20, 21, 30, 40], size=len(r) // 7 + 1), 7)[:len(r)] + rng.integers(0, 3, len(r))
+        out.append(bytes((q + 33).astype(np.uint8)))
+    return out
+
+
+@pytest.mark.parametrize("k,s,t,l,op", [(19, 8, 0, 3, False), (19, 8, 0, 1, False), (15, 8, 0, 0, False), (21, 10, 1, 2, True)])
+def test_place_min_seed_quality_filters_syncmers_by_average_phred(k, s, t, l, op, tmp_path):
+    """--min-seed-quality (placement.cpp:1179-1240, 1388-1533): only syncmers whose k bases average >= Q (and start inside the trimmed
+    range) count, k-min-mers need l consecutive passing syncmers, dedup is ignored; also through the C++ shim from a FASTQ file"""
+    rng = np.random.default_rng(60 + k + l)
+    idx, _, _ = H.synthetic_index(300, rng, k=k, s=s, t=t, l=l)
+    idx.open = int(op)
+    reads = H.random_reads(rng, 400, lo=10, hi=220)
+    reads = reads + reads[:50] + [b"", b"ACGT", bytes([200, 65, 67]) * 30]
+    quals = _quality_strings(rng, reads)
+    quals[-1] = bytes([250, 33, 126]) * 30          # bytes >= 128 are negative for the reference's (signed) char
+    buf, off = pm.pack_reads(reads)
+    qbuf, _ = pm.pack_reads(quals)
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open)
+    ws = pm.Workspace(pm.Index(host))
+    plain = cpu.seed_table(buf, off, k, s, t, l, op)[1].sum()
+    for kw in [dict(min_seed_quality=20), dict(min_seed_quality=13, trim_start=5, trim_end=9), dict(min_seed_quality=31, dedup_reads=1)]:
+        res = ws.place_quality(buf, qbuf, off, pm.PlaceParams(**kw))
+        okw = dict(trim_start=kw.get("trim_start", 0), trim_end=kw.get("trim_end", 0), min_seed_quality=kw["min_seed_quality"])
+        exp = cpu.place(buf, off, idx, want_scores=True, quals=qbuf, **okw)
+        assert res.raw.unique_seeds == exp["unique_seeds"] and res.raw.read_unique_seed_count == exp["kept"]
+        assert res.raw.total_read_seed_frequency == exp["total_frequency"] and res.raw.min_read_support == exp["min_support"]
+        th, tc = ws.seed_table()
+        eh, ec = cpu.seed_table(buf, off, k, s, t, l, op, quals=qbuf, **okw)
+        assert np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec)
+        assert 0 < ec.sum() < plain
+        assert H.relerr(ws.node_scores(), exp["scores"]).max() < RTOL
+        for m, name in enumerate(pm.METRICS):
+            assert res.best_index[name] == exp["best_index"][m] and np.array_equal(res.tied[name], exp["tied"][m]), name
+    # min_seed_quality without qualities must fail loudly, and 0 must ignore them
+    with pytest.raises(pm.PanmapError):
+        ws.place(buf, off, pm.PlaceParams(min_seed_quality=20))
+    assert ws.place_quality(buf, qbuf, off, pm.PlaceParams()).raw.total_read_seed_frequency == plain
+    # files through the shim: FASTQ with these qualities, and a FASTA (the reference substitutes 'I' = Q40)
+    keep = [i for i, r in enumerate(reads) if r and max(r) < 128]
+    fq = tmp_path / "r.fastq"
+    with open(fq, "wb") as f:
+        for i in keep:
+            f.write(b"@r%d\n%s\n+\n%s\n" % (i, reads[i], quals[i].replace(bytes([250]), b"!")))
+    fbuf, foff = pm.pack_reads([reads[i] for i in keep]); fq_q, _ = pm.pack_reads([quals[i].replace(bytes([250]), b"!") for i in keep])
+    r1 = pm.place_files(ws, str(fq), "", str(tmp_path / "o.tsv"), pm.PlaceParams(min_seed_quality=20))
+    e1 = cpu.place(fbuf, foff, idx, quals=fq_q, min_seed_quality=20)
+    assert r1.read_unique_seed_count == e1["kept"] and r1.total_read_seed_frequency == e1["total_frequency"]
+    assert list(r1.best_index) == list(e1["best_index"])
+    fa = tmp_path / "r.fa"
+    with open(fa, "wb") as f:
+        for i in keep:
+            f.write(b">r%d\n%s\n" % (i, reads[i]))
+    r2 = pm.place_files(ws, str(fa), "", str(tmp_path / "o2.tsv"), pm.PlaceParams(min_seed_quality=40))
+    e2 = cpu.place(fbuf, foff, idx, quals=np.full(fbuf.size, ord("I"), np.uint8), min_seed_quality=40)
+    assert r2.total_read_seed_frequency == e2["total_frequency"] > 0 and list(r2.best_index) == list(e2["best_index"])
+
+
+def test_place_min_seed_quality_on_an_hpc_index_compresses_qualities_in_lockstep():
+    """hpc index + --min-seed-quality (placement.cpp:1147-1159): the quality of the first base of every run stays with it"""
+    rng = np.random.default_rng(77)
+    idx, _, _ = H.synthetic_index(300, rng)
+    raw = []
+    for r in H.random_reads(rng, 300, lo=20, hi=200):
+        a = bytearray()
+        for c in r:
+            a += bytes([c]) * int(rng.choice([1, 1, 1, 2, 3, 5]))
+        raw.append(bytes(a))
+    raw += [b"", b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA", b"aAcCgGtTnN" * 12]
+    quals = _quality_strings(rng, raw)
+    comp, cq = [], []
+    for r, q in zip(raw, quals):
+        keep = [i for i in range(len(r)) if i == 0 or bytes([r[i]]).upper() != bytes([r[i - 1]]).upper()]
+        comp.append(bytes(r[i] for i in keep)); cq.append(bytes(q[i] for i in keep))
+    assert comp == [cpu.hpc_compress(r) for r in raw]
+    buf, off = pm.pack_reads(raw); qbuf, _ = pm.pack_reads(quals)
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open, hpc=1)
+    ws = pm.Workspace(pm.Index(host))
+    res = ws.place_quality(buf, qbuf, off, pm.PlaceParams(min_seed_quality=18))
+    cbuf, coff = pm.pack_reads(comp); cqb, _ = pm.pack_reads(cq)
+    exp = cpu.place(cbuf, coff, idx, want_scores=True, quals=cqb, min_seed_quality=18)
+    assert res.raw.unique_seeds == exp["unique_seeds"] and res.raw.read_unique_seed_count == exp["kept"]
+    assert res.raw.total_read_seed_frequency == exp["total_frequency"] > 0
+    th, tc = ws.seed_table()
+    eh, ec = cpu.seed_table(cbuf, coff, idx.k, idx.s, idx.t, idx.l, quals=cqb, min_seed_quality=18)
+    assert np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec)
+    assert H.relerr(ws.node_scores(), exp["scores"]).max() < RTOL
+
+
 def test_place_hpc_index_compresses_reads_on_the_device():
     """index built with --hpc (placement.cpp:1145-1165): the reads are homopolymer-compressed before seeding; also with --dedup,
     which then compares the compressed strings"""

@@ -157,3 +157,48 @@ def test_seed_mask_fraction_matches_reference_placeLite_at_a_tie_free_cut():
             mh, mc = cpu.mask_top_seeds(eh, ec, frac)
             assert np.array_equal(mh, r["table_hash"]) and np.array_equal(mc, r["table_count"]), M
         R.close()
+
+
+def _fastq_q(path, reads, quals):
+    with open(path, "wb") as f:
+        for i, (r, q) in enumerate(zip(reads, quals)):
+            f.write(b"@r%d\n%s\n+\n%s\n" % (i, r, q))
+
+
+@pytest.mark.parametrize("l", [3, 1, 0])
+def test_min_seed_quality_path_matches_reference_placeLite(l):
+    """--min-seed-quality > 0 (placement.cpp:1179-1240 for l == 0, :1388-1533 for l >= 1): syncmers whose k bases average below the
+    threshold (or start in a trimmed flank) drop out, k-min-mers need l consecutive passing syncmers, reads are not deduplicated"""
+    from tools.synth import synth
+    import panmap_b200 as pm
+    rng = np.random.default_rng(40 + l)
+    S = synth.generate(700, 5000, 1.5, 2500, k=19, s=8, l=max(l, 1), seed=11)
+    S.l = l
+    off = S.read_offsets.astype(np.int64); buf = S.reads.tobytes()
+    reads = [buf[off[i]:off[i + 1]] for i in range(2500)]
+    reads = reads + reads[:300] + [b"", b"ACGT", b"ACGTNACGTTGCATGCATGCATGCAACGGTCA" * 3]
+    quals = []
+    for r in reads:                       # blocks of good and bad quality so that windows straddle the threshold
+        q = np.repeat(rng.choice([2, 12, 19, 20, 21, 30, 40], size=len(r) // 7 + 1), 7)[:len(r)] + rng.integers(0, 3, len(r))
+        quals.append(bytes((q + 33).astype(np.uint8)))
+    rb, ro = pm.pack_reads(reads)
+    qb, _ = pm.pack_reads(quals)
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "s.idx"); ref.write_index(p, S)
+        fq = os.path.join(td, "r.fastq"); _fastq_q(fq, reads, quals)
+        R = ref.RefIndex(p)
+        for kw in [dict(min_seed_quality=20), dict(min_seed_quality=13, trim_start=5, trim_end=9), dict(min_seed_quality=31, dedup=True)]:
+            r = R.place(fq, **kw)
+            o = cpu.place(rb, ro, S, quals=qb, **kw)
+            assert o["unique_seeds"] == r["unique_seeds"] and o["unique_seeds"] > 0, kw
+            assert o["kept"] == r["kept"] and o["total_frequency"] == r["total_frequency"], kw
+            assert np.array_equal(o["best_index"], r["best_index"]), kw
+            assert all(np.array_equal(o["tied"][m], r["tied"][m]) for m in range(5)), kw
+            assert H.relerr(o["best_score"], r["best_score"]).max() < 1e-12
+            eh, ec = cpu.seed_table(rb, ro, 19, 8, 0, l, quals=qb, min_seed_quality=kw["min_seed_quality"],
+                                    trim_start=kw.get("trim_start", 0), trim_end=kw.get("trim_end", 0))
+            assert np.array_equal(eh, r["table_hash"]) and np.array_equal(ec, r["table_count"]), kw
+        # the filter must have removed something, or the test proves nothing
+        fh, fc = cpu.seed_table(rb, ro, 19, 8, 0, l)
+        assert fc.sum() > ec.sum()
+        R.close()
