@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
 // ASCII: the kernel reads the bases themselves (`reads`, one byte per base) and turns 8 of them at a time into the 4-bit codes
 // through a 256-byte table in shared memory -- no pack_reads pass and no packed copy of the sample; !ASCII: 4-bit codes from `packed`.
 // NOTRIM: trimEnd == 0 (the default), so "window inside the trimmed range" is implied by i < L and costs nothing
+constexpr int kPairStride = 96;   // >= 12 * 7 + 8 entries, a multiple of 16 so that every table starts on the same bank
 template <int K, int S, bool ASCII, bool NOTRIM>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                               const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
@@ -394,14 +395,16 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
     unsigned char* sLut = smemRaw + sizeof(SeedTables);
     // (outgoing base, incoming base) pair tables: one look-up and one XOR per rolling hash instead of two and two
-    u64* sPair = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables) + 256);   // [4][8][8]: fk, rk, fs, rs
+    // [4][kPairStride]: fk, rk, fs, rs; entry (o, nw) at 12 o + nw: the sixteen ACGT x ACGT pairs land in sixteen different
+    // bank pairs (12 o mod 16 = 0, 12, 8, 4), so a warp's 64-bit look-ups are conflict-free unless ambiguous bases are involved
+    u64* sPair = reinterpret_cast<u64*>(smemRaw + sizeof(SeedTables) + 256);
     for (int i = threadIdx.x; i < (int)(sizeof(SeedTables) / 8); i += blockDim.x)
         reinterpret_cast<u64*>(sT)[i] = reinterpret_cast<const u64*>(gT)[i];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         sLut[i] = (unsigned char)baseCode((unsigned char)i);
         const int tb = i >> 6, o = (i >> 3) & 7, nw = i & 7;
-        sPair[i] = tb == 0 ? gT->fwdOldK[o] ^ gT->fwdNew[nw] : tb == 1 ? gT->revOld[o] ^ gT->revNewK[nw]
-                 : tb == 2 ? gT->fwdOldS[o] ^ gT->fwdNew[nw] : gT->revOld[o] ^ gT->revNewS[nw];
+        sPair[tb * kPairStride + o * 12 + nw] = tb == 0 ? gT->fwdOldK[o] ^ gT->fwdNew[nw] : tb == 1 ? gT->revOld[o] ^ gT->revNewK[nw]
+                                              : tb == 2 ? gT->fwdOldS[o] ^ gT->fwdNew[nw] : gT->revOld[o] ^ gT->revNewS[nw];
     }
     __syncthreads();
     const SeedTables& T = *sT;
@@ -474,11 +477,11 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
             const unsigned code = word & 0xFu, oldK = lagK & 7u, oldS = lagS & 7u, tc = code & 7u;
             word >>= 4; lagK >>= 4; lagS >>= 4;
             if (i < L) {
-                const unsigned pk = oldK * 8u + tc, ps = oldS * 8u + tc;
+                const unsigned pk = oldK * 12u + tc, ps = oldS * 12u + tc;
                 fk = rol1(fk) ^ sPair[pk];
-                rk = ror1(rk) ^ sPair[64 + pk];
-                fs = rol1(fs) ^ sPair[128 + ps];
-                rs = ror1(rs) ^ sPair[192 + ps];
+                rk = ror1(rk) ^ sPair[kPairStride + pk];
+                fs = rol1(fs) ^ sPair[2 * kPairStride + ps];
+                rs = ror1(rs) ^ sPair[3 * kPairStride + ps];
                 if (code >= 4) iLo = max(iLo, i + K);
             }
         };
@@ -870,7 +873,7 @@ static unsigned seedGrid(u64 nReads) {
 template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
                        u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
-    const size_t sm = sizeof(SeedTables) + 256 + 2048;
+    const size_t sm = sizeof(SeedTables) + 256 + 4 * kPairStride * sizeof(u64);
     if (reads && P.trimEnd == 0)
         syncmers_fast<K, S, true, true><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
     else if (reads)

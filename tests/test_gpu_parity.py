@@ -322,6 +322,47 @@ def test_sharded_scoring_is_identical_to_single_shard():
             assert np.array_equal(scores, full)
 
 
+def test_reference_unit_test_cases_on_the_gpu():
+    """the hand-derived cases of the reference's own unit tests, through the staged ABI (one-node index holding the seed changes, read
+    table imported as (hash, count) pairs): test_placement.cpp:100-180 (computeChildMetrics) and :243-295 (min support, magnitudes)"""
+    def run(changes, th, tc, min_support=-1):
+        idx = H.FlatIdx([c[0] for c in changes], [c[1] for c in changes], [c[2] for c in changes], [0, len(changes)], [0], 15, 8, 0, 1)
+        host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, 15, 8, 0, 1, 0)
+        ws = pm.Workspace(pm.Index(host))
+        p = pm.PlaceParams(min_read_support=min_support)
+        buf, off = pm.pack_reads([b"ACGT"])                   # shorter than k: an empty table to import into
+        ws.stage_seed(buf, off, p)
+        ws.stage_table_import(np.array(th, np.uint64), np.array(tc, np.int64))
+        ws.stage_score(p)
+        r = ws.stage_select(ws.stage_records(), 1)
+        return ws.node_scores()[0], r
+    Hh, X = 0xAAAA, 0xBBBB
+    # r=3, g=2: logRaw = (l/2)/l, logCosine 1, containment 1, logContainment 1; weighted = (1/2) / (root's own 1/2)
+    s, r = run([(Hh, 0, 2)], [Hh], [3])
+    assert np.allclose(s, [0.5, 1.0, 1.0, 1.0, 1.0], rtol=1e-12) and r.best_index["log_raw"] == 0
+    assert r.raw.min_read_support == 1 and r.raw.read_unique_seed_count == 1 and r.raw.total_read_seed_frequency == 3
+    assert abs(r.raw.read_magnitude - np.log1p(3.0)) < 1e-15
+    s, r = run([(X, 0, 5)], [Hh], [3])                      # a genome seed that no read has
+    assert np.all(s == 0.0)
+    s, r = run([(Hh, 2, 2)], [Hh], [3])                     # unchanged count: no contribution
+    assert np.all(s == 0.0)
+    H1, H2 = 0x1111, 0x2222                                 # test_placement.cpp:144-180
+    s, r = run([(H1, 0, 2), (H2, 0, 2)], [H1, H2], [3, 3])
+    assert np.allclose(s, [1 / np.sqrt(2), 1.0, 1.0, 1.0, 1.0], rtol=1e-12)
+    s, r = run([(H1, 0, 2)], [H1, H2], [3, 3])
+    assert np.allclose(s, [0.5 / np.sqrt(2), 1 / np.sqrt(2), 0.5, 1.0, 0.5], rtol=1e-12)
+    # test_placement.cpp:243-295
+    for counts, cfg, want in [([5, 4, 3], -1, 2), ([2, 1, 1], -1, 1), ([1], -1, 1), ([5], 7, 7)]:
+        _, r = run([(Hh, 0, 1)], [0x10 + i for i in range(len(counts))], counts, cfg)
+        assert r.raw.min_read_support == want, counts
+    _, r = run([(Hh, 0, 1)], [0x10, 0x11, 0x12], [5, 3, 1], 2)
+    la, lb = np.log1p(5.0), np.log1p(3.0)
+    assert r.raw.read_unique_seed_count == 2 and r.raw.total_read_seed_frequency == 9
+    assert np.isclose(r.raw.log_containment_denominator, la + lb, rtol=1e-14) and np.isclose(r.raw.read_magnitude, np.sqrt(la * la + lb * lb), rtol=1e-14)
+    _, r = run([(Hh, 0, 1)], [0x10, 0x11, 0x12], [5, 3, 1], 1)
+    assert r.raw.read_unique_seed_count == 3
+
+
 def test_many_empty_reads_between_real_ones():
     """runs of zero-length reads (more than a pack block can index locally) must not disturb the chunk -> read mapping"""
     rng = np.random.default_rng(21)
