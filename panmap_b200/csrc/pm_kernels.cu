@@ -1074,8 +1074,8 @@ __global__ void __launch_bounds__(256) mask_apply(WorkspaceView W, u32 cThr, u64
         if (!(c > cThr || (c == cThr && k <= hThr))) continue;
         W.entCnt[i] = 0;   // pass 2 skips it
         u64 slot = mixKey(k) & W.tableMask;
-        while (W.table[slot].key != k) slot = (slot + 1) & W.tableMask;   // present by construction
-        W.table[slot].count = 0;   // like the homopolymer seeds: gone for the exported table too
+        for (int probe = 0; probe < 8192 && W.table[slot].key != k; ++probe) slot = (slot + 1) & W.tableMask;   // present by construction
+        if (W.table[slot].key == k) W.table[slot].count = 0;   // like the homopolymer seeds: gone for the exported table too
         --en; total -= c; if (c >= 2) { ms -= c; --mc; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && W.acc->emptyKeyCount > 0) {
