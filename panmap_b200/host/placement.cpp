@@ -2,6 +2,10 @@
 #include "placement.hpp"
 #include "seeding.hpp"
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -11,12 +15,21 @@
 #include <iomanip>
 #include <cstdlib>
 #include <stdexcept>
+#include <thread>
 
 namespace {
 
+// reads of one file in the layout the C ABI takes: read i = data[off[i], off[i+1])
+struct FlatReads {
+    std::string data; std::vector<uint64_t> off;
+    FlatReads() : off(1, 0) {}
+    size_t size() const { return off.size() - 1; }
+    void push(const std::string& s) { data += s; off.push_back(data.size()); }
+};
+
 // kseq semantics (FASTA and FASTQ, multi-line sequences, gz or plain through zlib's transparent gzread)
 // quals (optional): the quality string of every record, 'I' * length when the record has none (extractFullFastqData, placement.cpp:199-238)
-void readFastx(const std::string& path, std::vector<std::string>& out, std::vector<std::string>* quals = nullptr) {
+void readFastxSerial(const std::string& path, FlatReads& out, FlatReads* quals) {
     gzFile f = gzopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("Failed to open FASTQ file: " + path);  // mgsr.hpp:175
     gzbuffer(f, 1 << 20);
@@ -34,20 +47,132 @@ void readFastx(const std::string& path, std::vector<std::string>& out, std::vect
         for (size_t i = b; i < e; ++i) { const char ch = data[i]; if (ch != '\r' && ch != ' ' && ch != '\t') dst.push_back(ch); }
     };
     while (p < N && data[p] != '>' && data[p] != '@') p = lineEnd(p) + 1;
+    std::string seq, qual;
     while (p < N) {
         p = lineEnd(p) + 1;  // header line
-        std::string seq;
+        seq.clear(); qual.clear();
         while (p < N && data[p] != '>' && data[p] != '@' && data[p] != '+') { const size_t e = lineEnd(p); appendLine(seq, p, e); p = e + 1; }
-        std::string qual;
         if (p < N && data[p] == '+') {
             p = lineEnd(p) + 1;
             while (p < N && qual.size() < seq.size()) { const size_t e = lineEnd(p); appendLine(qual, p, e); p = e + 1; }
             while (p < N && data[p] != '>' && data[p] != '@') p = lineEnd(p) + 1;
             if (quals && qual.size() != seq.size()) break;   // kseq_read returns -2 (truncated quality): the reference's loop ends here
         }
-        if (quals) quals->push_back(qual.empty() ? std::string(seq.size(), 'I') : std::move(qual));
-        out.push_back(std::move(seq));
+        if (quals) quals->push(qual.empty() ? std::string(seq.size(), 'I') : qual);
+        out.push(seq);
     }
+}
+
+// Uncompressed strict four-line FASTQ (what parallelFastqSeqs, placement.cpp:96-162, takes): the file is mapped, cut at record starts
+// into one range per thread, and parsed twice -- first for the record count and base total of every range, then, the prefix sums known,
+// every thread copies its sequences (and qualities) to their final place in the flat buffers.  No per-read strings, no merge.
+// Returns false for gzip / FASTA / anything that is not four lines per record: the serial parser above takes those.
+struct MappedFile {
+    const char* d = nullptr; size_t size = 0; int fd = -1;
+    explicit MappedFile(const std::string& path) {
+        fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return;
+        struct stat st;
+        if (::fstat(fd, &st) != 0 || st.st_size <= 0) return;
+        void* m = ::mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) return;
+        d = static_cast<const char*>(m); size = static_cast<size_t>(st.st_size);
+    }
+    ~MappedFile() { if (d) ::munmap(const_cast<char*>(d), size); if (fd >= 0) ::close(fd); }
+};
+inline size_t fqEol(const char* d, size_t size, size_t p) {
+    const void* nl = p < size ? std::memchr(d + p, '\n', size - p) : nullptr;
+    return nl ? static_cast<size_t>(static_cast<const char*>(nl) - d) : size;
+}
+// first record start at or after `from`: a line that begins with '@', whose third line begins with '+' and whose second and fourth
+// lines have the same length (this rules out a '@' that opens a quality line)
+size_t fqRecordStart(const char* d, size_t size, size_t from) {
+    size_t o = from;
+    while (o > 0 && o < size && d[o - 1] != '\n') ++o;
+    while (o < size) {
+        if (d[o] == '@') {
+            const size_t s0 = fqEol(d, size, o) + 1;
+            if (s0 <= size) {
+                const size_t s1 = fqEol(d, size, s0), p0 = s1 + 1;
+                if (p0 < size && d[p0] == '+') {
+                    const size_t q0 = fqEol(d, size, p0) + 1, q1 = fqEol(d, size, q0);
+                    if (s1 - s0 == q1 - q0) return o;
+                }
+            }
+        }
+        o = fqEol(d, size, o) + 1;
+    }
+    return size;
+}
+bool readFastqParallel(const std::string& path, FlatReads& out, FlatReads* quals) {
+    MappedFile mf(path);
+    if (!mf.d || mf.size < 4) return false;
+    const char* d = mf.d; const size_t size = mf.size;
+    if ((static_cast<unsigned char>(d[0]) == 0x1f && static_cast<unsigned char>(d[1]) == 0x8b) || d[0] != '@') return false;
+    size_t nT = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    if (size < (1u << 20)) nT = 1;
+    std::vector<size_t> bounds(nT + 1, size);
+    bounds[0] = 0;
+    for (size_t i = 1; i < nT; ++i) bounds[i] = std::max(bounds[i - 1], fqRecordStart(d, size, (size / nT) * i));
+    struct Range { std::vector<uint64_t> seqAt, qualAt; std::vector<uint32_t> len; uint64_t bases = 0; bool bad = false; };
+    std::vector<Range> R(nT);
+    auto scan = [&](size_t t) {
+        Range& r = R[t];
+        size_t o = bounds[t];
+        const size_t end = bounds[t + 1];
+        while (o < end) {
+            if (d[o] != '@') {   // only blank lines may follow the last record
+                for (size_t i = o; i < end; ++i) if (d[i] != '\n' && d[i] != '\r') { r.bad = true; break; }
+                break;
+            }
+            const size_t s0 = fqEol(d, size, o) + 1;
+            if (s0 > size) { r.bad = true; break; }
+            size_t s1 = fqEol(d, size, s0);
+            const size_t p0 = s1 + 1;
+            if (p0 >= size || d[p0] != '+') { r.bad = true; break; }
+            const size_t q0 = fqEol(d, size, p0) + 1;
+            size_t q1 = fqEol(d, size, q0);
+            o = q1 + 1;
+            if (s1 > s0 && d[s1 - 1] == '\r') --s1;   // \r\n files
+            if (q1 > q0 && q0 <= size && d[q1 - 1] == '\r') --q1;
+            const size_t L = s1 - s0;
+            if (q0 > size || q1 - q0 != L || L > 0xFFFFFFFFull) { r.bad = true; break; }
+            for (size_t i = s0; i < s1; ++i) if (d[i] == ' ' || d[i] == '\t') { r.bad = true; break; }   // kseq would drop these
+            if (r.bad) break;
+            r.seqAt.push_back(s0); r.len.push_back(static_cast<uint32_t>(L)); r.bases += L;
+            if (quals) r.qualAt.push_back(q0);
+        }
+    };
+    auto runAll = [&](auto&& fn) {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nT; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto& x : th) x.join();
+    };
+    runAll(scan);
+    uint64_t nReads = 0, nBases = 0;
+    std::vector<uint64_t> firstRead(nT), firstBase(nT);
+    for (size_t t = 0; t < nT; ++t) { if (R[t].bad) return false; firstRead[t] = nReads; firstBase[t] = nBases; nReads += R[t].len.size(); nBases += R[t].bases; }
+    out.data.resize(nBases); out.off.assign(nReads + 1, 0);
+    if (quals) { quals->data.resize(nBases); quals->off.assign(nReads + 1, 0); }
+    auto fill = [&](size_t t) {
+        const Range& r = R[t];
+        uint64_t b = firstBase[t];
+        for (size_t i = 0; i < r.len.size(); ++i) {
+            out.off[firstRead[t] + i] = b;
+            std::memcpy(&out.data[b], d + r.seqAt[i], r.len[i]);
+            if (quals) std::memcpy(&quals->data[b], d + r.qualAt[i], r.len[i]);
+            b += r.len[i];
+        }
+    };
+    runAll(fill);
+    out.off[nReads] = nBases;
+    if (quals) quals->off = out.off;
+    return true;
+}
+
+void readFastx(const std::string& path, FlatReads& out, FlatReads* quals) {
+    if (!readFastqParallel(path, out, quals)) { out = FlatReads(); if (quals) *quals = FlatReads(); readFastxSerial(path, out, quals); }
 }
 
 }  // namespace
@@ -56,26 +181,32 @@ namespace placement {
 
 void extractReadSequences(const std::string& readPath1, const std::string& readPath2, std::string& bases, std::vector<uint64_t>& offsets,
                           std::string* quals) {
-    std::vector<std::string> r, q;
-    readFastx(readPath1, r, quals ? &q : nullptr);
-    if (!readPath2.empty()) {
-        const size_t fwd = r.size();
-        readFastx(readPath2, r, quals ? &q : nullptr);
-        if (r.size() != fwd * 2) throw std::runtime_error("File " + readPath2 + " does not contain the same number of reads as " + readPath1);
-        auto shuffle = [&](std::vector<std::string>& v) {   // seeding::perfect_shuffle (seeding.hpp:33-43)
-            std::vector<std::string> canvas(v.size());
-            for (size_t i = 0; i < fwd; ++i) { canvas[2 * i] = std::move(v[i]); canvas[2 * i + 1] = std::move(v[i + fwd]); }
-            v.swap(canvas);
-        };
-        shuffle(r);
-        if (quals) shuffle(q);
+    FlatReads a, qa;
+    readFastx(readPath1, a, quals ? &qa : nullptr);
+    if (readPath2.empty()) {
+        bases = std::move(a.data); offsets = std::move(a.off);
+        if (quals) *quals = std::move(qa.data);
+        return;
     }
-    offsets.assign(r.size() + 1, 0);
-    size_t tot = 0;
-    for (size_t i = 0; i < r.size(); ++i) { tot += r[i].size(); offsets[i + 1] = tot; }
-    bases.clear(); bases.reserve(tot);
-    for (auto& s : r) bases += s;
-    if (quals) { quals->clear(); quals->reserve(tot); for (auto& s : q) *quals += s; }
+    FlatReads b, qb;
+    readFastx(readPath2, b, quals ? &qb : nullptr);
+    if (b.size() != a.size()) throw std::runtime_error("File " + readPath2 + " does not contain the same number of reads as " + readPath1);
+    // seeding::perfect_shuffle (seeding.hpp:33-43): pair i becomes reads 2i, 2i+1; their places follow from the two offset arrays
+    const size_t n = a.size();
+    offsets.assign(2 * n + 1, 0);
+    bases.resize(a.data.size() + b.data.size());
+    if (quals) quals->resize(bases.size());
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t o0 = a.off[i] + b.off[i], o1 = a.off[i + 1] + b.off[i];
+        offsets[2 * i] = o0; offsets[2 * i + 1] = o1;
+        std::memcpy(&bases[o0], &a.data[a.off[i]], a.off[i + 1] - a.off[i]);
+        std::memcpy(&bases[o1], &b.data[b.off[i]], b.off[i + 1] - b.off[i]);
+        if (quals) {
+            std::memcpy(&(*quals)[o0], &qa.data[a.off[i]], a.off[i + 1] - a.off[i]);
+            std::memcpy(&(*quals)[o1], &qb.data[b.off[i]], b.off[i + 1] - b.off[i]);
+        }
+    }
+    offsets[2 * n] = bases.size();
 }
 
 void placeLite(PlacementResult& result, DeviceIndex& index, const std::string& reads1, const std::string& reads2, std::string& outputPath,

@@ -97,3 +97,48 @@ def test_fastx_ingest_small_cases(tmp_path):
     q.write_text(">s1\nAC\r\nGT\n>s2\n\n>s3\nTT")
     b, o = pm.read_fastx(str(q))
     assert bytes(b) == b"ACGTTT" and list(o) == [0, 4, 4, 6]
+
+
+def test_fastq_parallel_ingest_equals_the_serial_parser(tmp_path):
+    """plain strict four-line FASTQ goes through the multi-threaded flat parser (the reference's parallelFastqSeqs fast path,
+    placement.cpp:96-162); the same records gzipped go through the serial kseq-style parser: both must give the same reads, in file
+    order, also for paired files, \\r\\n line ends, '@' opening a quality line, an empty read and a missing final newline"""
+    import gzip
+    rng = np.random.default_rng(3)
+    reads = H.random_reads(rng, 12000, lo=1, hi=250) + [b"", b"ACGT"]
+    quals = []
+    for r in reads:
+        q = (rng.integers(0, 41, len(r)) + 33).astype(np.uint8)
+        if len(r):
+            q[0] = ord("@")                                # a quality line that looks like a header
+        quals.append(q.tobytes())
+    def records(rs, qs, eol=b"\n", last_eol=True):
+        out = b"".join(b"@r%d some text" % i + eol + r + eol + b"+" + eol + q + eol for i, (r, q) in enumerate(zip(rs, qs)))
+        return out if last_eol else out[:-len(eol)]
+    eb, eo = pm.pack_reads(reads)
+    for name, blob in [("a.fq", records(reads, quals)), ("b.fq", records(reads, quals, b"\r\n")), ("c.fq", records(reads, quals, last_eol=False))]:
+        p = tmp_path / name
+        p.write_bytes(blob)
+        assert len(blob) > (1 << 20)                       # large enough for more than one parser thread
+        b, o = pm.read_fastx(str(p))
+        assert np.array_equal(o, eo) and np.array_equal(b, eb), name
+        g = tmp_path / (name + ".gz")
+        with gzip.open(g, "wb", compresslevel=1) as f:
+            f.write(blob)
+        b2, o2 = pm.read_fastx(str(g))
+        assert np.array_equal(o2, eo) and np.array_equal(b2, eb), name
+    # pairs: R1 plain (parallel parser), R2 gzipped (serial parser), interleaved
+    r2 = [r[::-1] for r in reads]
+    (tmp_path / "r2.fq").write_bytes(records(r2, quals))
+    with gzip.open(tmp_path / "r2.fq.gz", "wb", compresslevel=1) as f:
+        f.write(records(r2, quals))
+    inter = [x for pair in zip(reads, r2) for x in pair]
+    ib, io = pm.pack_reads(inter)
+    for second in ("r2.fq", "r2.fq.gz"):
+        b, o = pm.read_fastx(str(tmp_path / "a.fq"), str(tmp_path / second))
+        assert np.array_equal(o, io) and np.array_equal(b, ib), second
+    # not four lines per record: the serial parser takes over
+    m = tmp_path / "m.fq"
+    m.write_bytes(b"@x\nAC\nGT\n+\nIIII\n" * 3)
+    b, o = pm.read_fastx(str(m))
+    assert bytes(b) == b"ACGT" * 3 and list(o) == [0, 4, 8, 12]
