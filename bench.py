@@ -39,8 +39,8 @@ WORKLOADS = {
 KERNELS_PER_STEP = 14  # table_clear syncmers_fast count_seeds table_scan entries_finalize root_denominator finish_scalars
 #                        node_deltas prefix_scores bfs_gather bfs_records chain_select collect_ties reset_sample
 #                        (+ gen_deltas, gen_prefix when the index holds deltas with a genome count >= 2; the synthetic one has none)
-# DRAM bytes (read + write) per launch from the ncu --set full capture of this workload (profiles/README.md)
-NCU_TRAFFIC = {"node_deltas": 77.6e6, "syncmers_fast": 0.47e9, "count_seeds": 0.57e9, "prefix_scores": 70e6, "pack_reads": 0.22e9}
+# DRAM bytes (read + write) per launch from the ncu --set full captures of this workload (profiles/ncu_r01x_summary.txt, ncu_r01w_summary.txt)
+NCU_TRAFFIC = {"node_deltas": 78.4e6, "syncmers_fast": 0.563e9, "count_seeds": 0.57e9, "prefix_scores": 70e6, "pack_reads": 0.22e9}
 
 
 def peaks():
@@ -278,7 +278,7 @@ def main():
         "kernel_ms": per_kernel,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": NCU_TRAFFIC.get(dom_name.split("<")[0]), "algorithmic_bytes_per_launch": dom_bytes, "ms": per_kernel[dom_name], "peak_source": pk_src,
-                     "note": "dominant kernel of the step by measured time; it is limited by the integer ALU pipe (ncu: pipe_alu 87 %), one byte in per ~130 "
+                     "note": "dominant kernel of the step by measured time; it is limited by the integer ALU pipe (ncu: pipe_alu 84-88 %), one byte in per ~120 "
                              "integer instructions, so the HBM fraction is small by construction -- see roofline_scoring for the HBM-bound kernel north_star names"},
         "roofline_scoring": {"bound": "hbm", "kernel": "node_deltas (the scoring kernel north_star names)", "achieved": sc_ach, "peak": peak, "unit": "GB/s",
                              "frac": sc_ach / peak, "traffic": NCU_TRAFFIC["node_deltas"], "algorithmic_bytes_per_launch": alg["delta_kernel"], "ms": float(stage[3]),
