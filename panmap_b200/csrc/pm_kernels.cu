@@ -13,6 +13,7 @@
 #include "pm_kernels.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 namespace pm {
@@ -426,9 +427,9 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         const char* rbase = ASCII ? reads + (b & ~3ULL) : nullptr;   // 4-byte aligned base of the read, rshift = its misalignment
         const unsigned rshift = (unsigned)(b & 3ULL);
         u64* __restrict__ dst = synBuf + pOff * 32;
-        int maxL = L;
+        int maxL = L, minL = L;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, d));
+        for (int d = 16; d > 0; d >>= 1) { maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, d)); minL = min(minL, __shfl_xor_sync(0xffffffffu, minL, d)); }
 
         // The kernel is bound by the integer ALU pipe, so the loop below is written to need as few integer instructions per base
         // as possible: the bases that leave the k-mer / s-mer windows come from lagged copies of the packed words (one AND + one
@@ -445,11 +446,13 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         for (int q = 0; q < W; ++q) { rF[q] = 0; rR[q] = 0; }
 
         // base i enters: rolling hashes of the k-mer and s-mer ending at i, both strands (seeding.cpp:147-195)
-        auto fetchRoll = [&](int i) {
+        // FULL (compile time): base i lies inside every lane's read, so the `i < L` / `i < maxL` tests are dropped
+        auto fetchRoll = [&](int i, auto full) {
+            constexpr bool FULL = decltype(full)::value;
             if ((i & 7) == 0) {   // warp-uniform: next 8-base word, and the lagged words the outgoing bases come from
                 wh4 = wh3; wh3 = wh2; wh2 = wh1; wh1 = curFull;
                 if (ASCII) {
-                    if (i < L) {   // 8 bytes from an arbitrary byte address: three aligned words, two funnel shifts, eight table look-ups
+                    if (FULL || i < L) {   // 8 bytes from an arbitrary byte address: three aligned words, two funnel shifts, eight table look-ups
                         const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + ((rshift + (unsigned)i) & ~3u));
                         const unsigned sh = ((rshift + (unsigned)i) & 3u) * 8u;
                         const unsigned x0 = __ldg(wp), x1 = __ldg(wp + 1), x2 = __ldg(wp + 2);
@@ -465,7 +468,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                         curFull = cw;
                     }
                 } else {
-                    if ((i & 31) == 0) { if (i < L) v = src[i >> 5]; }
+                    if ((i & 31) == 0) { if (FULL || i < L) v = src[i >> 5]; }
                     curFull = v.x; v.x = v.y; v.y = v.z; v.z = v.w;
                 }
                 word = curFull;
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
             }
             const unsigned code = word & 0xFu, oldK = lagK & 7u, oldS = lagS & 7u, tc = code & 7u;
             word >>= 4; lagK >>= 4; lagS >>= 4;
-            if (i < L) {
+            if (FULL || i < L) {
                 const unsigned pk = oldK * 12u + tc, ps = oldS * 12u + tc;
                 fk = rol1(fk) ^ sPair[pk];
                 rk = ror1(rk) ^ sPair[kPairStride + pk];
@@ -487,16 +490,16 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         };
         // prologue: the first S-1 bases only feed the rolling hashes
 #pragma unroll 1
-        for (int i = 0; i < S - 1 && i < maxL; ++i) fetchRoll(i);
-        // main loop: one block of W s-mers per iteration; s-mer index q = i - (S-1), slot j = q mod W
-#pragma unroll 1
-        for (int q0 = 0; q0 + S - 1 < maxL; q0 += W) {
+        for (int i = 0; i < S - 1 && i < maxL; ++i) fetchRoll(i, std::false_type{});
+        // one block of W s-mers; s-mer index q = i - (S-1), slot j = q mod W
+        auto block = [&](int q0, auto full) {
+            constexpr bool FULL = decltype(full)::value;
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 const int i = q0 + j + S - 1;
-                if (i < maxL) {   // warp-uniform
-                    fetchRoll(i);
-                    if (i < L) {
+                if (FULL || i < maxL) {   // warp-uniform
+                    fetchRoll(i, full);
+                    if (FULL || i < L) {
                         // running minimum of the current block; leF: the newest s-mer attains it
                         bool leF = true, leR = true;
                         if (j == 0) { preF = fs; preR = rs; firstF = fs; firstR = rs; }
@@ -532,6 +535,12 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                     }
                 }
             }
+        };
+        // main loop: blocks that lie inside every lane's read take the copy without the per-base length tests
+#pragma unroll 1
+        for (int q0 = 0; q0 + S - 1 < maxL; q0 += W) {
+            if (q0 + W + S - 1 <= minL) block(q0, std::true_type{});
+            else block(q0, std::false_type{});
         }
         if (valid) synCount[r] = cnt;
     }
