@@ -383,6 +383,13 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_generic(const uint4* __
 // ASCII: the kernel reads the bases themselves (`reads`, one byte per base) and turns 8 of them at a time into the 4-bit codes
 // through a 256-byte table in shared memory -- no pack_reads pass and no packed copy of the sample; !ASCII: 4-bit codes from `packed`.
 // NOTRIM: trimEnd == 0 (the default), so "window inside the trimmed range" is implied by i < L and costs nothing
+// (mask & bit) != 0 through an opaque AND: the front end otherwise rewrites it as (mask >> p) & 1 == 1, three ALU instructions
+// where ptxas has one LOP3 with a predicate result
+__device__ __forceinline__ bool maskBit(unsigned mask, unsigned bit) {
+    unsigned t;
+    asm("and.b32 %0, %1, %2;" : "=r"(t) : "r"(mask), "r"(bit));
+    return t != 0u;
+}
 constexpr int kPairStride = 96;   // >= 12 * 7 + 8 entries, a multiple of 16 so that every table starts on the same bank
 template <int K, int S, bool ASCII, bool NOTRIM>
 __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __restrict__ packed, const u64* __restrict__ off,
@@ -510,8 +517,9 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                         if (pslot == 0) { fsyn = leF || firstF == preF; rsyn = leR || firstR == preR; }
                         else {
                             const u64 sf = rF[pslot], sr = rR[pslot];   // suffix minima of the previous block from the oldest s-mer on
-                            fsyn = (leF && fs <= sf) || (((maskF >> pslot) & 1u) && sf <= preF);
-                            rsyn = (leR && rs <= sr) || (((maskR >> pslot) & 1u) && sr <= preR);
+                            // (mask & constant) != 0 is one LOP3 with a predicate result; (mask >> pslot) & 1 compiled to three instructions
+                            fsyn = (leF && fs <= sf) || (maskBit(maskF, 1u << pslot) && sf <= preF);
+                            rsyn = (leR && rs <= sr) || (maskBit(maskR, 1u << pslot) && sr <= preR);
                         }
                         if ((fsyn || rsyn) && i >= iLo && (NOTRIM || i <= iHi) && fk != rk) {
                             dst[cnt] = umin64(fk, rk);
@@ -527,7 +535,8 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                                 const u64 x = rF[q], y = rR[q];
                                 const bool ia = x <= a, ib = y <= bb;
                                 a = ia ? x : a; bb = ib ? y : bb;
-                                mF |= (ia ? 1u : 0u) << q; mR |= (ib ? 1u : 0u) << q;
+                                if (ia) mF |= 1u << q;
+                                if (ib) mR |= 1u << q;
                                 rF[q] = a; rR[q] = bb;
                             }
                             maskF = mF; maskR = mR;
