@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
                                                               unsigned* __restrict__ synCount, const unsigned char* __restrict__ dup,
                                                               const u64* __restrict__ endOff, const char* __restrict__ reads) {
     constexpr int W = K - S + 1;
-    static_assert(K >= 8 && K <= 32 && S >= 8 && S < K, "lagged-word addressing assumes 8 <= s < k <= 32");
+    static_assert(K >= 8 && K <= 20 && S >= 8 && S < K && (K - S + 1) % 4 == 0, "word history holds 20 bases; the block length must be a multiple of 4");
     extern __shared__ __align__(16) unsigned char smemRaw[];
     SeedTables* sT = reinterpret_cast<SeedTables*>(smemRaw);
     unsigned char* sLut = smemRaw + sizeof(SeedTables);
@@ -443,61 +443,66 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
         // shift each, no base history to maintain), every 64-bit minimum doubles as the comparison the syncmer test needs, and
         // the trim / ambiguity / window-complete conditions are one interval test on the read position.
         u64 fk = 0, rk = 0, fs = 0, rs = 0, preF = kEmptyKey, preR = kEmptyKey, firstF = 0, firstR = 0;
-        unsigned maskF = 0, maskR = 0, word = 0, cnt = 0;
-        unsigned wh1 = 0xFFFFFFFFu, wh2 = 0xFFFFFFFFu, wh3 = 0xFFFFFFFFu, wh4 = 0xFFFFFFFFu, curFull = 0xFFFFFFFFu;   // earlier words ("ambiguous" before the read)
-        unsigned lagK = 0xFFFFFFFFu, lagS = 0xFFFFFFFFu;
+        unsigned maskF = 0, maskR = 0, cnt = 0;
+        // the bases travel as one code byte each, four to a word: cur = bases 4n .. 4n+3, hN = the word N words back ("ambiguous"
+        // before the read); combK / combS hold 12 * outgoing + incoming for the four positions of the current word
+        unsigned cur = 0x04040404u, h1 = 0x04040404u, h2 = 0x04040404u, h3 = 0x04040404u, h4 = 0x04040404u, h5 = 0x04040404u;
+        unsigned combK = 0, combS = 0;
         uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
         int iLo = P.trimStart + K - 1;           // a window ending at base i is reported iff iLo <= i <= iHi:
         const int iHi = L - P.trimEnd - 1;       //   complete, inside the trimmed range, no ambiguous base in it (iLo moves past those)
 #pragma unroll
         for (int q = 0; q < W; ++q) { rF[q] = 0; rR[q] = 0; }
 
-        // base i enters: rolling hashes of the k-mer and s-mer ending at i, both strands (seeding.cpp:147-195)
-        // FULL (compile time): base i lies inside every lane's read, so the `i < L` / `i < maxL` tests are dropped
-        auto fetchRoll = [&](int i, auto full) {
+        // base i enters: rolling hashes of the k-mer and s-mer ending at i, both strands (seeding.cpp:147-195).  ph = i & 3 is a
+        // compile-time constant inside the unrolled block (W is a multiple of 4), so the word bookkeeping below is resolved statically
+        // and every per-base index is ONE byte permute: with 4-bit codes the three shift+mask pairs per base were 6 of ~55 ALU-pipe
+        // instructions.  FULL (compile time): base i lies inside every lane's read, so the `i < L` / `i < maxL` tests are dropped
+        auto fetchRoll = [&](int i, int ph, auto full) {
             constexpr bool FULL = decltype(full)::value;
-            if ((i & 7) == 0) {   // warp-uniform: next 8-base word, and the lagged words the outgoing bases come from
-                wh4 = wh3; wh3 = wh2; wh2 = wh1; wh1 = curFull;
+            if (ph == 0) {   // next four bases
+                h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = cur;
                 if (ASCII) {
-                    if (FULL || i < L) {   // 8 bytes from an arbitrary byte address: three aligned words, two funnel shifts, eight table look-ups
-                        const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + ((rshift + (unsigned)i) & ~3u));
-                        const unsigned sh = ((rshift + (unsigned)i) & 3u) * 8u;
-                        const unsigned x0 = __ldg(wp), x1 = __ldg(wp + 1), x2 = __ldg(wp + 2);
-                        const unsigned b0 = __funnelshift_r(x0, x1, sh), b1 = __funnelshift_r(x1, x2, sh);
-                        unsigned cw = sLut[b1 >> 24];
-                        cw = cw * 16u + sLut[(b1 >> 16) & 0xFFu];
-                        cw = cw * 16u + sLut[(b1 >> 8) & 0xFFu];
-                        cw = cw * 16u + sLut[b1 & 0xFFu];
-                        cw = cw * 16u + sLut[b0 >> 24];
-                        cw = cw * 16u + sLut[(b0 >> 16) & 0xFFu];
-                        cw = cw * 16u + sLut[(b0 >> 8) & 0xFFu];
-                        cw = cw * 16u + sLut[b0 & 0xFFu];
-                        curFull = cw;
+                    if (FULL || i < L) {   // 4 bytes from an arbitrary byte address: two aligned words, one funnel shift, four table look-ups
+                        const unsigned a = rshift + (unsigned)i;
+                        const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + (a & ~3u));
+                        const unsigned x0 = __ldg(wp), x1 = __ldg(wp + 1);
+                        const unsigned bts = __funnelshift_r(x0, x1, (a & 3u) * 8u);
+                        unsigned cw = sLut[bts >> 24];
+                        cw = cw * 256u + sLut[(bts >> 16) & 0xFFu];
+                        cw = cw * 256u + sLut[(bts >> 8) & 0xFFu];
+                        cw = cw * 256u + sLut[bts & 0xFFu];
+                        cur = cw;
                     }
-                } else {
+                } else {   // 4-bit codes from `packed` (list utilities): spread four nibbles to bytes
                     if ((i & 31) == 0) { if (FULL || i < L) v = src[i >> 5]; }
-                    curFull = v.x; v.x = v.y; v.y = v.z; v.z = v.w;
+                    const int wsel = (i >> 3) & 3;
+                    const unsigned w32 = wsel == 0 ? v.x : wsel == 1 ? v.y : wsel == 2 ? v.z : v.w;
+                    const unsigned n16 = (w32 >> (16 * ((i >> 2) & 1))) & 0xFFFFu;
+                    cur = (((n16 & 0xF000u) << 12) | ((n16 & 0x0F00u) << 8) | ((n16 & 0x00F0u) << 4) | (n16 & 0x000Fu)) & 0x07070707u;
                 }
-                word = curFull;
-                constexpr int KA = K / 8, KB = K % 8, SA = S / 8, SB = S % 8;
-                const unsigned whA[6] = {curFull, wh1, wh2, wh3, wh4, 0xFFFFFFFFu};
-                lagK = KB ? __funnelshift_r(whA[KA + 1], whA[KA], 4 * (8 - KB)) : whA[KA];   // nibble p = base 8n + p - K
-                lagS = SB ? __funnelshift_r(whA[SA + 1], whA[SA], 4 * (8 - SB)) : whA[SA];
+                constexpr int KA = K / 4, KB = K % 4, SA = S / 4, SB = S % 4;
+                const unsigned hist[7] = {cur, h1, h2, h3, h4, h5, 0x04040404u};
+                // byte j of the lag word = base 4n + j - K: four consecutive bytes of (hist[KA+1], hist[KA]) starting at byte 4 - KB
+                constexpr unsigned selK = (4 - KB) | ((5 - KB) << 4) | ((6 - KB) << 8) | ((7 - KB) << 12);
+                constexpr unsigned selS = (4 - SB) | ((5 - SB) << 4) | ((6 - SB) << 8) | ((7 - SB) << 12);
+                const unsigned lagK = KB ? __byte_perm(hist[KA + 1], hist[KA], selK) : hist[KA];
+                const unsigned lagS = SB ? __byte_perm(hist[SA + 1], hist[SA], selS) : hist[SA];
+                combK = lagK * 12u + cur;   // bytewise: codes are <= 7, 12 * 7 + 7 < 256
+                combS = lagS * 12u + cur;
             }
-            const unsigned code = word & 0xFu, oldK = lagK & 7u, oldS = lagS & 7u, tc = code & 7u;
-            word >>= 4; lagK >>= 4; lagS >>= 4;
             if (FULL || i < L) {
-                const unsigned pk = oldK * 12u + tc, ps = oldS * 12u + tc;
+                const unsigned pk = __byte_perm(combK, 0u, 0x4440u + (unsigned)ph), ps = __byte_perm(combS, 0u, 0x4440u + (unsigned)ph);
                 fk = rol1(fk) ^ sPair[pk];
                 rk = ror1(rk) ^ sPair[kPairStride + pk];
                 fs = rol1(fs) ^ sPair[2 * kPairStride + ps];
                 rs = ror1(rs) ^ sPair[3 * kPairStride + ps];
-                if (code >= 4) iLo = max(iLo, i + K);
+                if (cur & (0x04u << (8 * ph))) iLo = max(iLo, i + K);   // codes >= 4 are ambiguous
             }
         };
         // prologue: the first S-1 bases only feed the rolling hashes
 #pragma unroll 1
-        for (int i = 0; i < S - 1 && i < maxL; ++i) fetchRoll(i, std::false_type{});
+        for (int i = 0; i < S - 1 && i < maxL; ++i) fetchRoll(i, i & 3, std::false_type{});
         // one block of W s-mers; s-mer index q = i - (S-1), slot j = q mod W
         auto block = [&](int q0, auto full) {
             constexpr bool FULL = decltype(full)::value;
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
             for (int j = 0; j < W; ++j) {
                 const int i = q0 + j + S - 1;
                 if (FULL || i < maxL) {   // warp-uniform
-                    fetchRoll(i, full);
+                    fetchRoll(i, (j + S - 1) & 3, full);   // q0 is a multiple of W, W of 4
                     if (FULL || i < L) {
                         // running minimum of the current block; leF: the newest s-mer attains it
                         bool leF = true, leR = true;
