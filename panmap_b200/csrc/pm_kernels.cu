@@ -638,7 +638,7 @@ constexpr int kAggSlots = 16384;
 __device__ __forceinline__ bool aggAdd(u64* __restrict__ sKey, u32* __restrict__ sCnt, u64 s, u64 m) {
     u32 i = (u32)(m >> 40) & (kAggSlots - 1);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < 2; ++p) {   // two slots: junk (error) seeds fill the table early and every further probe is issued for a few lanes only (4: 442 us, 2: 410 us, 1: 401 us but a quarter of the hot keys would lose their slot)
         u64 kk = sKey[i];
         if (kk == kEmptyKey) {
             kk = atomicCAS(reinterpret_cast<unsigned long long*>(&sKey[i]), (unsigned long long)kEmptyKey, (unsigned long long)s);
