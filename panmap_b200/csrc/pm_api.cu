@@ -100,6 +100,7 @@ struct pm_workspace {
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
     u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
     bool residentValid = false;  // the device copy of the reads was laid out by pm_reads_upload (not by the sliced pm_place path)
+    bool hpcDone = false;        // hpc indexes: the resident reads (and qualities) were compressed in place already, endOff is valid
     // table
     DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
     DevBuf<unsigned long long> dedupSlots; u64 dedupMask = 0; DevBuf<unsigned char> dupFlag;   // --dedup only
@@ -222,11 +223,13 @@ void refreshView(pm_workspace* W) {
 static u64 fitLo() { return 4; }
 static u64 fitHi() { return 8; }
 
+// grows the table in use to at least wantCap slots (never shrinks it); a prefix of a larger allocation is reused as it is
 void ensureTable(pm_workspace* W, u64 wantCap) {
     u64 cap = 1 << 12;
     while (cap < wantCap) cap <<= 1;
     if (cap <= W->tableCap) return;
     if (cap > (1ull << 27)) throw std::runtime_error("read seed table would exceed 2^27 slots");
+    if (cap <= W->table.n) { W->tableCap = cap; refreshView(W); return; }   // the allocation (and its texture) already covers it
     if (W->tableTex) { cudaDestroyTextureObject(W->tableTex); W->tableTex = 0; }
     W->table.alloc(cap); W->tableCap = cap; W->entKey.alloc(cap); W->entCnt.alloc(cap); W->entId.alloc(cap);
     {
@@ -271,7 +274,7 @@ void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n)
     const u64 base0 = n ? off[0] : 0;
     const u64 total = n ? off[n] - base0 : 0;
     hostPackedOffsets(W, off, n, I->F.sp.k);
-    W->nReads = n; W->totalBases = total;
+    W->nReads = n; W->totalBases = total; W->hpcDone = false;
     W->synBuf.ensure(W->nChunks * 32 + 32); W->synCount.ensure(n + 1);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1); W->packed.ensure(W->nChunks + 1);
     if (base0 != 0) throw std::runtime_error("read_offsets[0] must be 0");
@@ -355,7 +358,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
                         hpc ? W->endOff.p + r0 : nullptr, ascii ? W->reads.p : nullptr);
         bfBase += nBlk + 1;
     }
-    W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false;
+    W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false; W->hpcDone = false;
 }
 
 void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
@@ -368,9 +371,14 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
     const bool quality = W->useQuals && prm.min_seed_quality > 0;   // the reference's quality path never deduplicates (placement.cpp:1388)
     unsigned char* dup = quality ? nullptr : prepareDedup(W, W->nReads, prm);
     const u64* endOff = nullptr;
-    if (I->F.sp.hpc) {   // in place and idempotent: resident reads may be placed many times
-        W->endOff.ensure(W->nReads + 1);
-        launchHpcCompress(W->reads.p, W->off.p, W->nReads, W->endOff.p, W->st, quality ? W->quals.p : nullptr);
+    if (I->F.sp.hpc) {
+        // in place, and NOT idempotent (a second pass would compress the compressed prefix together with the stale tail): once per
+        // upload; repeated pm_place_resident calls and table-growth retries reuse the compressed bytes and endOff
+        if (!W->hpcDone) {
+            W->endOff.ensure(W->nReads + 1);
+            launchHpcCompress(W->reads.p, W->off.p, W->nReads, W->endOff.p, W->st, W->useQuals ? W->quals.p : nullptr);
+            W->hpcDone = true;
+        }
         endOff = W->endOff.p;
     }
     if (dup) launchDedup(W->reads.p, W->off.p, 0, W->nReads, W->dedupSlots.p, W->dedupMask, dup, W->st, endOff);
@@ -476,7 +484,8 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaEventRecord(W->ev[0], W->st));
         if (W->tableCap == 0 && inputsResident) ensureTable(W, std::max<u64>(1 << 16, W->totalWindows / 4));
-        else if (W->lastEntries && W->tableCap > (1u << 16) && W->tableCap > fitHi() * W->lastEntries / 2) {
+        else if (attempt == 0 && W->lastEntries && W->tableCap > (1u << 16) && W->tableCap > fitHi() * W->lastEntries / 2) {
+            // (first attempt only: a retry has just grown the table for THIS sample and lastEntries still describes the previous one)
             // the previous sample filled under a quarter of the slots: every pass over the table is cheaper with a tighter one
             u64 cap = 1 << 16;
             while (cap < fitLo() * W->lastEntries / 2) cap <<= 1;
@@ -498,7 +507,9 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
             // grow and redo: the table (or a list) was too small for this sample
             CK(cudaStreamSynchronize(W->st));
             if (W->hAcc.overflow && !tableTight && attempt >= 2) throw std::runtime_error("internal capacity exceeded");
-            ensureTable(W, W->tableCap * 4);
+            // a tight table knows its entry count: size for it directly; an overflowed one only knows "more"
+            ensureTable(W, std::max<u64>(W->tableCap * 4, W->hAcc.overflow ? 0 : fitLo() * (u64)W->hAcc.entries / 2));
+            W->lastEntries = 0;
             continue;
         }
         fetchTies(W);

@@ -26,7 +26,11 @@ struct Msg {
         if (seg >= segStart.size() || w >= segWords[seg]) throw std::runtime_error("index: pointer out of range");
         uint64_t v; std::memcpy(&v, base + segStart[seg] + 8 * w, 8); return v;
     }
-    const uint8_t* at(uint32_t seg, size_t w) const { return base + segStart[seg] + 8 * w; }
+    // checked view of `bytes` bytes that start at word w of segment seg (every list body goes through here)
+    const uint8_t* span(uint32_t seg, size_t w, uint64_t bytes) const {
+        if (seg >= segStart.size() || w > segWords[seg] || bytes > 8ull * (segWords[seg] - w)) throw std::runtime_error("index: list extends past its segment (truncated or corrupt file)");
+        return base + segStart[seg] + 8 * w;
+    }
 };
 struct Ref { int kind = 0; uint32_t seg = 0; size_t off = 0; uint32_t dataWords = 0, ptrWords = 0, elemSize = 0; uint64_t count = 0; };
 
@@ -140,9 +144,15 @@ void readIdxFile(const std::string& path, HostIndex& out) {
     const uint64_t N = nodes.kind == 2 ? nodes.count : 0;
     if (offs.count < N + 1)
         throw std::runtime_error("Struct-of-arrays format offsets size mismatch: " + std::to_string(offs.count) + " vs " + std::to_string(N + 1));
+    if (offs.elemSize != 5) throw std::runtime_error("index: nodeChangeOffsets is not a list of 64-bit words");
     out.nodeOffsets.resize(N + 1);
-    std::memcpy(out.nodeOffsets.data(), m.at(offs.seg, offs.off), 8 * (N + 1));
+    std::memcpy(out.nodeOffsets.data(), m.span(offs.seg, offs.off, 8 * (N + 1)), 8 * (N + 1));
     const uint64_t D = out.nodeOffsets[N];
+    {   // D sizes the allocations below: it cannot exceed what the seed-change lists hold
+        uint64_t have = 0;
+        for (uint64_t sgi = 0; sgi < hashes.count; ++sgi) { const Ref inner = resolve(m, hashes.seg, hashes.off + sgi); if (inner.kind == 2) have += inner.count; }
+        if (D > have) throw std::runtime_error("index: nodeChangeOffsets names more seed changes than the file holds");
+    }
     out.hash.resize(D); out.parentCount.resize(D); out.childCount.resize(D);
     auto gatherSegs = [&](const Ref& outer, void* dst, size_t elemBytes, unsigned wantCode) {
         uint64_t done = 0;
@@ -151,7 +161,7 @@ void readIdxFile(const std::string& path, HostIndex& out) {
             if (inner.kind != 2) continue;
             if (inner.elemSize != wantCode) throw std::runtime_error("index: unexpected list element size");
             const uint64_t n = inner.count < D - done ? inner.count : D - done;
-            std::memcpy(static_cast<uint8_t*>(dst) + done * elemBytes, m.at(inner.seg, inner.off), n * elemBytes);
+            std::memcpy(static_cast<uint8_t*>(dst) + done * elemBytes, m.span(inner.seg, inner.off, n * elemBytes), n * elemBytes);
             done += n;
         }
         if (done != D) throw std::runtime_error("index: seed-change arrays shorter than nodeChangeOffsets says");
@@ -166,7 +176,7 @@ void readIdxFile(const std::string& path, HostIndex& out) {
         out.parentIndex[i] = nodes.dataWords ? static_cast<uint32_t>(m.word(nodes.seg, eo) & 0xffffffffu) : 0;
         Ref e; e.kind = 1; e.seg = nodes.seg; e.off = eo; e.dataWords = nodes.dataWords; e.ptrWords = nodes.ptrWords;
         const Ref id = ptrOf(m, e, 0);
-        if (id.kind == 2 && id.count > 0) out.nodeIds[i].assign(reinterpret_cast<const char*>(m.at(id.seg, id.off)), id.count - 1);
+        if (id.kind == 2 && id.elemSize == 2 && id.count > 0) out.nodeIds[i].assign(reinterpret_cast<const char*>(m.span(id.seg, id.off, id.count)), id.count - 1);
         if (i > 0 && out.parentIndex[i] >= i) throw std::runtime_error("index: nodes are not in DFS pre-order (parentIndex >= index)");
     }
     out.raw.clear(); out.raw.shrink_to_fit();

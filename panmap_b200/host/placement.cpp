@@ -43,8 +43,9 @@ void readFastxSerial(const std::string& path, FlatReads& out, FlatReads* quals) 
     size_t p = 0;
     const size_t N = data.size();
     auto lineEnd = [&](size_t q) { while (q < N && data[q] != '\n') ++q; return q; };
-    auto appendLine = [&](std::string& dst, size_t b, size_t e) {
-        for (size_t i = b; i < e; ++i) { const char ch = data[i]; if (ch != '\r' && ch != ' ' && ch != '\t') dst.push_back(ch); }
+    auto appendLine = [&](std::string& dst, size_t b, size_t e) {   // ks_getuntil(KS_SEP_LINE): the line without its end, a trailing CR dropped
+        if (e > b && data[e - 1] == '\r') --e;
+        dst.append(data, b, e - b);
     };
     while (p < N && data[p] != '>' && data[p] != '@') p = lineEnd(p) + 1;
     std::string seq, qual;
@@ -56,7 +57,7 @@ void readFastxSerial(const std::string& path, FlatReads& out, FlatReads* quals) 
             p = lineEnd(p) + 1;
             while (p < N && qual.size() < seq.size()) { const size_t e = lineEnd(p); appendLine(qual, p, e); p = e + 1; }
             while (p < N && data[p] != '>' && data[p] != '@') p = lineEnd(p) + 1;
-            if (quals && qual.size() != seq.size()) break;   // kseq_read returns -2 (truncated quality): the reference's loop ends here
+            if (qual.size() != seq.size()) break;   // kseq_read returns -2 (truncated quality): `while (kseq_read(seq) >= 0)` ends here, with or without quals
         }
         if (quals) quals->push(qual.empty() ? std::string(seq.size(), 'I') : qual);
         out.push(seq);
@@ -84,31 +85,29 @@ inline size_t fqEol(const char* d, size_t size, size_t p) {
     const void* nl = p < size ? std::memchr(d + p, '\n', size - p) : nullptr;
     return nl ? static_cast<size_t>(static_cast<const char*>(nl) - d) : size;
 }
-// first record start at or after `from`: a line that begins with '@', whose third line begins with '+' and whose second and fourth
-// lines have the same length (this rules out a '@' that opens a quality line)
+// Where does the first whole record begin at or after byte `from`?  One pass over the newlines keeps the starts of the last four
+// lines in a small ring; as soon as four consecutive lines look like (header '@...', bases, '+...', qualities of the same length as the
+// bases) the first of them is the answer.  The equal-length test is what tells a header from a quality line that happens to begin with '@'.
 size_t fqRecordStart(const char* d, size_t size, size_t from) {
-    size_t o = from;
-    while (o > 0 && o < size && d[o - 1] != '\n') ++o;
-    while (o < size) {
-        if (d[o] == '@') {
-            const size_t s0 = fqEol(d, size, o) + 1;
-            if (s0 <= size) {
-                const size_t s1 = fqEol(d, size, s0), p0 = s1 + 1;
-                if (p0 < size && d[p0] == '+') {
-                    const size_t q0 = fqEol(d, size, p0) + 1, q1 = fqEol(d, size, q0);
-                    if (s1 - s0 == q1 - q0) return o;
-                }
-            }
-        }
-        o = fqEol(d, size, o) + 1;
+    size_t pos = from;
+    if (pos > 0 && pos < size && d[pos - 1] != '\n') pos = fqEol(d, size, pos) + 1;   // move to the next line boundary
+    size_t start[4], len[4];   // ring over the last four lines
+    int have = 0;
+    while (pos < size) {
+        const size_t e = fqEol(d, size, pos);
+        if (have == 4) { for (int i = 0; i < 3; ++i) { start[i] = start[i + 1]; len[i] = len[i + 1]; } have = 3; }
+        start[have] = pos; len[have] = e - pos; ++have;
+        if (have == 4 && d[start[0]] == '@' && len[2] > 0 && d[start[2]] == '+' && len[1] == len[3]) return start[0];
+        pos = e + 1;
     }
+    // fewer than four lines left after the candidate: a last record whose quality line ends the file without a newline was handled above
     return size;
 }
 bool readFastqParallel(const std::string& path, FlatReads& out, FlatReads* quals) {
     MappedFile mf(path);
     if (!mf.d || mf.size < 4) return false;
     const char* d = mf.d; const size_t size = mf.size;
-    if ((static_cast<unsigned char>(d[0]) == 0x1f && static_cast<unsigned char>(d[1]) == 0x8b) || d[0] != '@') return false;
+    if (d[0] != '@') return false;   // gzip streams (1f 8b), FASTA ('>') and anything else: the serial parser takes them
     size_t nT = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
     if (size < (1u << 20)) nT = 1;
     std::vector<size_t> bounds(nT + 1, size);

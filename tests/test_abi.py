@@ -142,3 +142,52 @@ def test_fastq_parallel_ingest_equals_the_serial_parser(tmp_path):
     m.write_bytes(b"@x\nAC\nGT\n+\nIIII\n" * 3)
     b, o = pm.read_fastx(str(m))
     assert bytes(b) == b"ACGT" * 3 and list(o) == [0, 4, 8, 12]
+
+
+def test_idx_reader_rejects_truncated_and_corrupt_files(tmp_path):
+    """every list body of the schema-less Cap'n Proto walk is bounds-checked: a file cut short, or one whose list headers name more
+    elements than its segments hold, must come back as a clean PM_ERR_INVALID (the reference's capnp reader throws), never a crash"""
+    raw = open(os.path.join(H.GOLDEN, "tiny.idx"), "rb").read()
+    good = pm.HostIndex.read(os.path.join(H.GOLDEN, "tiny.idx"))
+    n_ok = 0
+    for cut in list(range(40, len(raw), max(1, len(raw) // 97))) + [len(raw) - 8, len(raw) - 1]:
+        p = tmp_path / "cut.idx"
+        p.write_bytes(raw[:cut])
+        try:
+            hi = pm.HostIndex.read(str(p))
+            # a cut inside trailing padding may still parse: then it must parse to the same index
+            assert np.array_equal(hi.hash, good.hash) and np.array_equal(hi.offsets, good.offsets)
+            n_ok += 1
+        except pm.PanmapError as e:
+            assert e.code == -1, (cut, e)
+    assert n_ok <= 3
+    # corrupt list headers: blow up the element count of every list pointer in turn
+    import struct
+    words = (len(raw) - 32) // 8
+    hits = 0
+    for w in range(2, words):
+        v, = struct.unpack_from("<Q", raw, 32 + 8 * w)
+        if (v & 3) != 1 or (v >> 35) == 0 or (v >> 35) > 1 << 20:   # list pointers with a plausible element count
+            continue
+        bad = bytearray(raw)
+        struct.pack_into("<Q", bad, 32 + 8 * w, (v & ((1 << 35) - 1)) | ((1 << 27) << 35))
+        p = tmp_path / "bad.idx"
+        p.write_bytes(bytes(bad))
+        try:
+            pm.HostIndex.read(str(p))
+        except pm.PanmapError as e:
+            assert e.code == -1
+            hits += 1
+    assert hits >= 3
+
+
+def test_fastx_serial_parser_keeps_kseq_corner_cases(tmp_path):
+    """kseq keeps blanks inside a sequence line (only the line end and a trailing CR go) and `while (kseq_read(seq) >= 0)` stops at a
+    record whose quality string is shorter than its sequence, whether or not the qualities were asked for (placement.cpp:164-176)"""
+    p = tmp_path / "t.fq"
+    p.write_text("@a\nAC GT\n+\nIIIII\n@b\nACGT\n+\nII\n")         # record b: quality cut short by the end of the file
+    b, o = pm.read_fastx(str(p))
+    assert bytes(b) == b"AC GT" and list(o) == [0, 5]
+    p.write_text("@a\nACGT\n+\nII\n@c\nGG\n+\nII\n")               # kseq reads "II" + "@c" as a's four quality bytes, then finds no header
+    b, o = pm.read_fastx(str(p))
+    assert bytes(b) == b"ACGT" and list(o) == [0, 4]

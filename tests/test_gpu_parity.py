@@ -241,6 +241,77 @@ def test_place_hpc_index_compresses_reads_on_the_device():
         assert res2.raw.unique_seeds == res.raw.unique_seeds and res2.best_index == res.best_index
 
 
+def test_hpc_index_resident_reads_are_compressed_once_per_upload():
+    """hpc_compress works in place and is NOT idempotent: repeated pm_place_resident calls (and table-growth retries) on the same
+    upload must reuse the compressed bytes, with and without qualities"""
+    rng = np.random.default_rng(21)
+    idx, _, _ = H.synthetic_index(200, rng)
+    raw = []
+    for r in H.random_reads(rng, 500, lo=20, hi=200):
+        a = bytearray()
+        for c in r:
+            a += bytes([c]) * int(rng.choice([1, 1, 2, 2, 3]))
+        raw.append(bytes(a))
+    comp = [cpu.hpc_compress(r) for r in raw]
+    buf, off = pm.pack_reads(raw)
+    cbuf, coff = pm.pack_reads(comp)
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open, hpc=1)
+    ws = pm.Workspace(pm.Index(host))
+    exp = cpu.place(cbuf, coff, idx, want_scores=True)
+    eh, ec = cpu.seed_table(cbuf, coff, idx.k, idx.s, idx.t, idx.l, idx.open, 0, 0, False)
+    ws.upload(buf, off)
+    for _ in range(3):
+        res = ws.place_resident()
+        assert res.raw.unique_seeds == exp["unique_seeds"] and res.raw.total_read_seed_frequency == exp["total_frequency"]
+        th, tc = ws.seed_table()
+        assert np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec)
+        assert H.relerr(ws.node_scores(), exp["scores"]).max() < RTOL
+
+
+def test_workspace_grows_its_table_for_a_much_larger_sample_and_shrinks_back():
+    """the count table is fitted to the previous sample: a sample with >10x the unique seeds must trigger the grow-and-redo path and
+    succeed (not shrink back on the retry), in either order, also on an hpc index where the retry must not compress twice"""
+    rng = np.random.default_rng(22)
+    idx, _, _ = H.synthetic_index(300, rng)
+    small = H.random_reads(rng, 40)
+    big = H.random_reads(rng, 9000, lo=100, hi=200)        # ~9000 * 40 unique random seeds >> 2^16 slots
+    for hpc in (0, 1):
+        host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open, hpc=hpc)
+        ws = pm.Workspace(pm.Index(host))
+        for reads in (small, big, small, big, big, small):
+            rr = [cpu.hpc_compress(r) for r in reads] if hpc else reads
+            buf, off = pm.pack_reads(reads)
+            res = ws.place(buf, off)
+            eh, ec = cpu.seed_table(*pm.pack_reads(rr), idx.k, idx.s, idx.t, idx.l, idx.open, 0, 0, False)
+            assert res.raw.unique_seeds == eh.size, (hpc, len(reads))
+            th, tc = ws.seed_table()
+            assert np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec)
+        # the same through the resident path (retries re-run the seeding stage on the uploaded reads)
+        ws2 = pm.Workspace(ws.index)
+        for reads in (small, big):
+            rr = [cpu.hpc_compress(r) for r in reads] if hpc else reads
+            ws2.upload(*pm.pack_reads(reads))
+            res = ws2.place_resident()
+            eh, ec = cpu.seed_table(*pm.pack_reads(rr), idx.k, idx.s, idx.t, idx.l, idx.open, 0, 0, False)
+            th, tc = ws2.seed_table()
+            assert res.raw.unique_seeds == eh.size and np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec)
+
+
+@pytest.mark.parametrize("l", [1, 0])
+def test_homopolymer_kmers_are_erased_from_the_read_table(l):
+    """placement.cpp:41-76, 1708-1722: the canonical hashes of the four homopolymer k-mers leave the table before anything is counted;
+    at l <= 1 seeds ARE syncmer hashes, so poly-A/C/G/T reads put exactly those keys into the table"""
+    rng = np.random.default_rng(23 + l)
+    idx, _, _ = H.synthetic_index(200, rng, k=19, s=8, t=0, l=l)
+    reads = H.random_reads(rng, 200) + [b"A" * 70, b"C" * 45, b"G" * 19, b"T" * 150, b"a" * 33, b"ACGT" * 10 + b"A" * 40 + b"CCGT" * 9] * 3
+    res, exp, ws, _ = _place_and_check(idx, reads)
+    homo = cpu.seed_table(*pm.pack_reads([b"A" * 19, b"C" * 19]), 19, 8, 0, l, 0, 0, 0, False)
+    assert homo[0].size == 0                               # the oracle's table has them erased ...
+    th, tc = ws.seed_table()
+    raw = set(int(x) for x in cpu.read_seeds(b"A" * 19, 19, 8, 0, l, False, 0, 0)) | set(int(x) for x in cpu.read_seeds(b"C" * 19, 19, 8, 0, l, False, 0, 0))
+    assert len(raw) == 2 and not (raw & set(int(x) for x in th[tc > 0]))     # ... and so has the device table (the keys were inserted, then zeroed)
+
+
 def test_place_empty_and_short_reads():
     rng = np.random.default_rng(6)
     idx, _, _ = H.synthetic_index(50, rng)
