@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 1
+#define PM_ABI_VERSION 2
 #define PM_NONE 0xFFFFFFFFu /* "no node" (reference: UINT32_MAX, placement.hpp:159) */
 #define PM_NUM_METRICS 5    /* log_raw, log_cosine, containment, weighted_containment, log_containment */
 
@@ -43,6 +43,7 @@ typedef enum pm_status {
 typedef struct pm_host_index pm_host_index; /* a parsed .idx on the host */
 typedef struct pm_index pm_index;           /* flattened index resident in HBM on one device */
 typedef struct pm_workspace pm_workspace;   /* per-sample state: stream, read table, scores */
+typedef struct pm_comm pm_comm;             /* one rank of a group of GPUs that place ONE sample together */
 
 /* Seeding parameters; authoritative source is the index (placement.cpp:1094-1101). */
 typedef struct pm_seed_params {
@@ -191,6 +192,37 @@ int pm_stage_records_export_all(pm_workspace* ws, uint32_t* counts /* [5] */, ui
 int pm_stage_select(pm_workspace* ws, const uint32_t* counts /* [5] */, const uint32_t* const* bfs_rank /* [5] */,
                     const uint32_t* const* node /* [5] */, const double* const* score /* [5] */, uint64_t total_reads,
                     pm_place_result* result);
+
+/* ---- ONE sample over several GPUs (BASELINE configs[2]: node range sharded over 1/2/4/8 GPUs; the reference's own parallel form is
+ *      the level-parallel traversal + per-thread seed maps merged at the end, placement.cpp:742-913, 922-929).
+ *      Rank r holds shard r of the node range (pm_index_create_shard(desc, device, r, n)) and seeds its own slice of the reads; the seed
+ *      table is hash-partitioned over the ranks (all-to-all), finalized where it lives, and the per-seed log counts every shard's delta
+ *      kernel needs come back with one all-gather; prefix-maximum records and tie heads take one small all-gather each.  Everything is
+ *      enqueued on the workspace stream with fixed-capacity buffers and in-band counts: the host waits once, for the result.
+ *      Results are bit-identical to pm_place on one GPU.  dedup_reads, seed_mask_fraction and min_seed_quality need the whole sample
+ *      in one place and return PM_ERR_UNSUPPORTED here.
+ *      Two transports:
+ *        pm_comm_create_nccl   one process per GPU; NCCL (libnccl.so.2, resolved at run time) on the workspace stream.  The 128-byte id
+ *                              comes from pm_comm_unique_id on rank 0 and reaches the other ranks through the caller (MPI, torchrun, a file).
+ *        pm_comm_create_local  one process, one host thread driving n workspaces (any mix of devices, also all on one): peer copies
+ *                              ordered by events.  This is the form panmap itself (a single process) would call. ---- */
+#define PM_COMM_ID_BYTES 128
+int pm_comm_unique_id(void* id_out /* PM_COMM_ID_BYTES */);
+int pm_comm_create_nccl(pm_workspace* ws, const void* id, int rank, int n_ranks, pm_comm** out);
+int pm_comm_create_local(pm_workspace* const* ws /* [n_ranks] */, int n_ranks, pm_comm** out /* [n_ranks] */);
+void pm_comm_destroy(pm_comm* c);
+/* NCCL transport: every rank calls with its slice of the reads (HOST buffers, offsets start at 0); every rank receives the same result.
+ * _resident: the slice was laid out by pm_reads_upload on the communicator's workspace. */
+int pm_place_sharded(pm_comm* c, const char* reads, const uint64_t* read_offsets, uint64_t n_reads_local, const pm_place_params* params,
+                     pm_place_result* result);
+int pm_place_sharded_resident(pm_comm* c, const pm_place_params* params, pm_place_result* result);
+/* local transport: the whole sample in, cut into n contiguous slices of reads internally; the result (and pm_get_tied) is available on every
+ * rank's workspace, `result` receives rank 0's. _resident: slice r was laid out by pm_reads_upload on workspace r. */
+int pm_place_multi(pm_comm* const* comms, int n_ranks, const char* reads, const uint64_t* read_offsets, uint64_t n_reads,
+                   const pm_place_params* params, pm_place_result* result);
+int pm_place_multi_resident(pm_comm* const* comms, int n_ranks, const pm_place_params* params, pm_place_result* result);
+/* bytes this rank sent / received through the transport for the last sample (collective payloads, capacities not fill levels) */
+int pm_comm_last_traffic(pm_comm* c, uint64_t* bytes_sent, uint64_t* bytes_received);
 
 /* placement::placeLite through the C++ host shim (panmap_b200/host/placement.hpp): FASTA/FASTQ(.gz) files in, result + <out_tsv> out.
  * node_ids = LiteNode ids by DFS index (for the TSV); err receives the exception text on failure. */

@@ -115,6 +115,15 @@ def lib():
     L.pm_stage_records_size.argtypes = [C.c_void_p, C.c_int]
     L.pm_stage_records_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_stage_select.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceResult)]
+    L.pm_comm_unique_id.argtypes = [C.c_void_p]
+    L.pm_comm_create_nccl.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.pm_comm_create_local.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+    L.pm_comm_destroy.argtypes = [C.c_void_p]
+    L.pm_place_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_place_sharded_resident.argtypes = [C.c_void_p, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_place_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_place_multi_resident.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_comm_last_traffic.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.pm_read_fastx.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64]
     L.pm_free.argtypes = [C.c_void_p]
     L.pm_place_files.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(PlaceParams),
@@ -423,6 +432,94 @@ class Workspace:
         res = PlaceResult()
         _ck(lib().pm_stage_select(self._h, _ptr(counts), pr, pn, ps, total_reads, C.byref(res)))
         return self._finish(res)
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """the 128-byte id rank 0 creates and hands to the other ranks (ncclGetUniqueId behind pm_comm_unique_id)"""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _ck(lib().pm_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """One rank of a group of GPUs that place ONE sample together (pm_comm): the workspace sits on shard `rank` of the node range."""
+
+    def __init__(self, handle, workspace, rank, n_ranks):
+        self._h, self.ws, self.rank, self.n_ranks = handle, workspace, rank, n_ranks
+
+    @classmethod
+    def nccl(cls, workspace, unique_id, rank, n_ranks):
+        """one process per GPU; NCCL on the workspace stream"""
+        h = C.c_void_p()
+        _ck(lib().pm_comm_create_nccl(workspace._h, unique_id, rank, n_ranks, C.byref(h)))
+        return cls(h, workspace, rank, n_ranks)
+
+    @classmethod
+    def local(cls, workspaces):
+        """one process, one host thread, n workspaces (any devices): returns the n communicators in rank order"""
+        n = len(workspaces)
+        hs = (C.c_void_p * n)(*[w._h for w in workspaces])
+        out = (C.c_void_p * n)()
+        _ck(lib().pm_comm_create_local(hs, n, out))
+        return [cls(C.c_void_p(out[r]), workspaces[r], r, n) for r in range(n)]
+
+    def close(self):
+        if self._h:
+            lib().pm_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def place_sharded(self, reads, offsets, params=None, full=True):
+        """NCCL transport: this rank's slice of the reads (offsets start at 0); every rank gets the same Placement"""
+        params = params or PlaceParams()
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        res = PlaceResult()
+        _ck(lib().pm_place_sharded(self._h, _ptr(reads), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params), C.byref(res)))
+        return self.ws._finish(res) if full else res
+
+    def place_sharded_raw(self, reads_ptr, offsets_ptr, n_reads, params):
+        res = PlaceResult()
+        _ck(lib().pm_place_sharded(self._h, reads_ptr, offsets_ptr, n_reads, C.byref(params), C.byref(res)))
+        return res
+
+    def place_sharded_resident(self, params=None, full=True):
+        params = params or PlaceParams()
+        res = PlaceResult()
+        _ck(lib().pm_place_sharded_resident(self._h, C.byref(params), C.byref(res)))
+        return self.ws._finish(res) if full else res
+
+    def last_traffic(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _ck(lib().pm_comm_last_traffic(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def place_multi(comms, reads, offsets, params=None):
+    """local transport: the whole sample in, sliced over the ranks; returns rank 0's Placement (all ranks hold the same)"""
+    params = params or PlaceParams()
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    hs = (C.c_void_p * len(comms))(*[c._h for c in comms])
+    res = PlaceResult()
+    _ck(lib().pm_place_multi(hs, len(comms), _ptr(reads), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params), C.byref(res)))
+    return comms[0].ws._finish(res)
+
+
+def place_multi_resident(comms, params=None, full=True):
+    params = params or PlaceParams()
+    hs = (C.c_void_p * len(comms))(*[c._h for c in comms])
+    res = PlaceResult()
+    _ck(lib().pm_place_multi_resident(hs, len(comms), C.byref(params), C.byref(res)))
+    return comms[0].ws._finish(res) if full else res
 
 
 def rolling_syncmers(seqs, k, s, open=False, t=0, device=0):

@@ -1,8 +1,7 @@
 // pm_api.cu -- the C ABI (include/panmap_b200.h): index upload, per-sample workspaces, the placement pipeline.
 // All compute runs in the kernels of pm_kernels.cu; the host code here only prepares launches, moves the
 // inputs/outputs and assembles the result structure.  There is no CPU compute fallback.
-#include "pm_host.h"
-#include "pm_kernels.cuh"
+#include "pm_internal.h"
 
 #include <algorithm>
 #include <cmath>
@@ -14,131 +13,23 @@
 #include <vector>
 
 using namespace pm;
+using namespace pm::host;
 
-namespace {
+namespace pm {
+namespace host {
 
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
-
-struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
-    } while (0)
-
-template <class F>
-int guarded(F&& f) {
-    try { return f(); }
-    catch (const CudaError& e) { return fail(PM_ERR_CUDA, e.what()); }
-    catch (const IoError& e) { return fail(PM_ERR_IO, e.what()); }
-    catch (const Unsupported& e) { return fail(PM_ERR_UNSUPPORTED, e.what()); }
-    catch (const std::bad_alloc&) { return fail(PM_ERR_CAPACITY, "out of host memory"); }
-    catch (const std::exception& e) { return fail(PM_ERR_INVALID, e.what()); }
-}
-
-template <class T>
-struct DevBuf {
-    T* p = nullptr; size_t n = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
-    void alloc(size_t count) {
-        if (p) { cudaFree(p); p = nullptr; }
-        n = count;
-        if (count) CK(cudaMalloc(&p, count * sizeof(T)));
-    }
-    void ensure(size_t count) { if (count > n) alloc(count + count / 8); }
-    void upload(const std::vector<T>& v, cudaStream_t st = 0) {
-        alloc(v.size());
-        if (!v.empty()) { CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st)); CK(cudaStreamSynchronize(st)); }
-    }
-};
-template <class T>
-struct PinBuf {
-    T* p = nullptr; size_t n = 0;
-    ~PinBuf() { if (p) cudaFreeHost(p); }
-    void ensure(size_t count) {
-        if (count <= n) return;
-        if (p) { cudaFreeHost(p); p = nullptr; }
-        n = count + count / 8;
-        CK(cudaMallocHost(&p, n * sizeof(T)));
-    }
-};
-
 int deviceCountNoThrow() {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
-}  // namespace
-
-struct pm_host_index { HostIndex h; };
-
-struct pm_index {
-    int device = 0; int nSM = 148;
-    FlatIndex F;  // host copy of the small arrays (tree) is kept for result assembly; big vectors are released
-    DevBuf<u32> dw, endMask, chunkSeg, nodeSeg, boundarySegs, genSlot, genId, genPc, evSlot, evIdx, rootId, rootChild;
-    DevBuf<u32> parent, subEnd, carrySlot, chainOff, chainNodes, bfsNodes, bfsRanks;
-    DevBuf<u64> dictHash, homo;
-    DevBuf<DictSlot> dict;
-    DevBuf<double> gMag, log1pLut, log1pSmall;
-    DevBuf<unsigned char> isLeaf;
-    DevBuf<SeedTables> seedTables;
-    DevIndexView view{};
-    std::vector<double> gMagSqHost; std::vector<int64_t> gUniqueHost;
-};
-
-struct pm_workspace {
-    pm_index* idx = nullptr;
-    cudaStream_t st = nullptr, stCopy = nullptr;
-    cudaEvent_t ev[9]{}, evCopy[12]{}, evK[4]{};   // evK: around pack_reads / syncmers / count_seeds of the resident path
-    // inputs
-    DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
-    PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
-    u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
-    bool residentValid = false;  // the device copy of the reads was laid out by pm_reads_upload (not by the sliced pm_place path)
-    bool hpcDone = false;        // hpc indexes: the resident reads (and qualities) were compressed in place already, endOff is valid
-    // table
-    DevBuf<TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
-    DevBuf<unsigned long long> dedupSlots; u64 dedupMask = 0; DevBuf<unsigned char> dupFlag;   // --dedup only
-    DevBuf<u64> endOff;                                                                        // hpc indexes only
-    DevBuf<u64> tileSum;                                                                       // scratch of the device-side chunk offsets
-    DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
-    // the small per-sample result block lives in ONE device allocation so that it comes back with a single copy:
-    // [SampleAcc | SampleScalars | Selection x 5 | first kTieHead tied nodes of every metric]
-    DevBuf<unsigned char> resultBlob;
-    struct { SampleAcc* p = nullptr; } acc; struct { SampleScalars* p = nullptr; } scalars; struct { Selection* p = nullptr; } sel;
-    u32* tieHead = nullptr;
-    DevBuf<long long> ell; cudaTextureObject_t ellTex = 0; DevBuf<unsigned> countHist; DevBuf<u64> entKey; DevBuf<u32> entCnt, entId;
-    DevBuf<ScanPartial> scanPart; DevBuf<FinPartial> finPart;
-    DevBuf<SegRec> segRec, chainA;
-    DevBuf<u64> genRec, evPrefix;
-    DevBuf<double> scores, metrics, blockMaxAndBfs;
-    DevBuf<u32> recRank, recNode; DevBuf<double> recScore; u32 recCap = 0;
-    DevBuf<u32> tieNode; u32 tieCap = 0; DevBuf<u32> selCounts;
-    DevBuf<u64> expHash; DevBuf<long long> expCount; DevBuf<unsigned> expCounter;
-    DevBuf<unsigned long long> maskScratch;   // --seed-mask-fraction only
-    DevBuf<char> quals; DevBuf<unsigned char> synPass; bool useQuals = false;   // --min-seed-quality only (pm_place_quality)
-    // host staging (pinned)
-    PinBuf<unsigned char> hStage; PinBuf<u32> hTies; PinBuf<unsigned char> hRec;
-    // results of the last sample
-    bool haveResult = false; bool wantMetrics = false;
-    pm_place_params lastParams{};
-    Selection hSel[5]{}; SampleAcc hAcc{}; SampleScalars hScal{};
-    std::vector<u32> tied[5];
-    WorkspaceView view{};
-};
-
-namespace {
-
-constexpr size_t kResultBlobBytes = sizeof(SampleAcc) + sizeof(SampleScalars) + 5 * sizeof(Selection) + 5 * kTieHead * sizeof(u32);
 
 void setDevice(int dev) { CK(cudaSetDevice(dev)); }
 
-void buildViews(pm_index* I) {
+static void buildViews(pm_index* I) {
     FlatIndex& F = I->F;
     DevIndexView& V = I->view;
     V.nNodes = F.N; V.nodeBegin = F.nodeBegin; V.nodeEnd = F.nodeEnd; V.nLocal = F.nLocal; V.nAnc = F.nAnc;
@@ -159,7 +50,7 @@ void buildViews(pm_index* I) {
     V.ln2 = std::log1p(1.0);
 }
 
-int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t nShards, pm_index** out) {
+static int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t nShards, pm_index** out) {
     if (!desc || !out) return fail(PM_ERR_INVALID, "null argument");
     *out = nullptr;
     if (deviceCountNoThrow() <= device || device < 0)
@@ -252,7 +143,7 @@ void checkParams(const pm_place_params* p) {
 }
 
 // host side: chunk offsets of the packed layout (ceil(len/32) 16-byte chunks per read)
-void hostPackedOffsets(pm_workspace* W, const uint64_t* off, u64 n, int k) {
+static void hostPackedOffsets(pm_workspace* W, const uint64_t* off, u64 n, int k) {
     W->hPackedOff.ensure(n + 1);
     u64 acc = 0, win = 0;
     for (u64 i = 0; i < n; ++i) {
@@ -286,7 +177,7 @@ void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n)
 }
 
 // --dedup: (re)size and clear the read set; returns the flag array (null when the option is off)
-unsigned char* prepareDedup(pm_workspace* W, u64 n, const pm_place_params& prm) {
+static unsigned char* prepareDedup(pm_workspace* W, u64 n, const pm_place_params& prm) {
     if (!prm.dedup_reads || n == 0) return nullptr;
     if (n >= 0xFFFFFFFFull) throw std::runtime_error("dedup_reads: more than 2^32 reads");
     u64 cap = 1024;
@@ -403,6 +294,11 @@ void stageScore(pm_workspace* W, const pm_place_params& prm) {
     if (prm.seed_mask_fraction > 0.0) W->maskScratch.ensure(2);
     launchFinalize(I->view, W->view, O, I->homo.p, W->lastEntries ? W->lastEntries : W->tableCap / 4, I->nSM, W->st, prm.seed_mask_fraction,
                    W->maskScratch.p);
+    stageDeltasScoresRecords(W, prm);
+}
+void stageDeltasScoresRecords(pm_workspace* W, const pm_place_params& prm) {
+    pm_index* I = W->idx;
+    const PlaceOpts O = makeOpts(prm, W->wantMetrics);
     CK(cudaEventRecord(W->ev[3], W->st));
     launchDeltas(I->view, W->view, I->nSM, W->st);
     launchGeneral(I->view, W->view, W->st);
@@ -412,15 +308,21 @@ void stageScore(pm_workspace* W, const pm_place_params& prm) {
     launchRecords(I->view, W->view, O, W->st);
 }
 
-// D2H of the small result block; returns after the stream is idle
-void fetchSmall(pm_workspace* W) {
+// D2H of the small result block: enqueue the copy, and (after the stream went idle) unpack it
+void enqueueSmall(pm_workspace* W) {
     W->hStage.ensure(kResultBlobBytes);
-    unsigned char* h = W->hStage.p;
-    CK(cudaMemcpyAsync(h, W->resultBlob.p, kResultBlobBytes, cudaMemcpyDeviceToHost, W->st));
-    CK(cudaStreamSynchronize(W->st));
+    CK(cudaMemcpyAsync(W->hStage.p, W->resultBlob.p, kResultBlobBytes, cudaMemcpyDeviceToHost, W->st));
+}
+void parseSmall(pm_workspace* W) {
+    const unsigned char* h = W->hStage.p;
     std::memcpy(&W->hAcc, h, sizeof(SampleAcc));
     std::memcpy(&W->hScal, h + sizeof(SampleAcc), sizeof(SampleScalars));
     std::memcpy(W->hSel, h + sizeof(SampleAcc) + sizeof(SampleScalars), 5 * sizeof(Selection));
+}
+void fetchSmall(pm_workspace* W) {
+    enqueueSmall(W);
+    CK(cudaStreamSynchronize(W->st));
+    parseSmall(W);
 }
 
 void fillResult(pm_workspace* W, pm_place_result* r, u64 totalReads) {
@@ -441,7 +343,21 @@ void fillResult(pm_workspace* W, pm_place_result* r, u64 totalReads) {
 }
 
 // tie lists -> host, finalizeTiedIndices semantics (placement.cpp:395-401): sort, unique, best = front
-void fetchTies(pm_workspace* W) {
+void finishTies(pm_workspace* W, const u32* lists, const unsigned* n) {
+    size_t o = 0;
+    for (int m = 0; m < 5; ++m) {
+        std::vector<u32>& t = W->tied[m];
+        t.assign(lists + o, lists + o + n[m]);
+        o += n[m];
+        const Selection& s = W->hSel[m];
+        // the reference pushes bestNodeIndex (possibly UINT32_MAX before any improvement) next to every tie, and
+        // an improvement leaves [node] in the list
+        if (s.bestNode != kNone || !t.empty()) t.push_back(s.bestNode);
+        std::sort(t.begin(), t.end());
+        t.erase(std::unique(t.begin(), t.end()), t.end());
+    }
+}
+static void fetchTies(pm_workspace* W) {
     // short lists (the usual case) came back with the result block; longer ones need one more copy
     size_t tot = 0; unsigned n[5]; bool big = false;
     for (int m = 0; m < 5; ++m) { n[m] = std::min<unsigned>(W->hAcc.tieCount[m], W->tieCap); tot += n[m]; big = big || n[m] > (unsigned)kTieHead; }
@@ -457,21 +373,15 @@ void fetchTies(pm_workspace* W) {
         const u32* head = reinterpret_cast<const u32*>(W->hStage.p + sizeof(SampleAcc) + sizeof(SampleScalars) + 5 * sizeof(Selection));
         for (int m = 0; m < 5; ++m) { std::memcpy(W->hTies.p + o, head + (size_t)m * kTieHead, n[m] * sizeof(u32)); o += n[m]; }
     }
-    o = 0;
-    for (int m = 0; m < 5; ++m) {
-        std::vector<u32>& t = W->tied[m];
-        t.assign(W->hTies.p + o, W->hTies.p + o + n[m]);
-        o += n[m];
-        const Selection& s = W->hSel[m];
-        // the reference pushes bestNodeIndex (possibly UINT32_MAX before any improvement) next to every tie, and
-        // an improvement leaves [node] in the list
-        if (s.bestNode != kNone || !t.empty()) t.push_back(s.bestNode);
-        std::sort(t.begin(), t.end());
-        t.erase(std::unique(t.begin(), t.end()), t.end());
-    }
+    finishTies(W, W->hTies.p, n);
+}
+void recordStageTimes(pm_workspace* W, pm_place_result* res) {
+    float ms = 0;
+    for (int i = 0; i < 7; ++i) { ms = 0; if (cudaEventElapsedTime(&ms, W->ev[i], W->ev[i + 1]) != cudaSuccess) cudaGetLastError(); res->stage_ms[i] = ms; }
+    ms = 0; if (cudaEventElapsedTime(&ms, W->ev[0], W->ev[7]) != cudaSuccess) cudaGetLastError(); res->stage_ms[7] = ms;
 }
 
-int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, bool inputsResident, const char* reads,
+static int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, bool inputsResident, const char* reads,
              const uint64_t* off, u64 n) {
     pm_index* I = W->idx;
     setDevice(I->device);
@@ -517,17 +427,15 @@ int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, 
         CK(cudaEventRecord(W->ev[7], W->st));
         CK(cudaStreamSynchronize(W->st));
         fillResult(W, res, W->nReads);
-        float ms = 0;
-        const int a[7] = {0, 1, 2, 3, 4, 5, 6}, b[7] = {1, 2, 3, 4, 5, 6, 7};
-        for (int i = 0; i < 7; ++i) { cudaEventElapsedTime(&ms, W->ev[a[i]], W->ev[b[i]]); res->stage_ms[i] = ms; }
-        cudaEventElapsedTime(&ms, W->ev[0], W->ev[7]); res->stage_ms[7] = ms;
+        recordStageTimes(W, res);
         W->haveResult = true;
         return PM_OK;
     }
     throw std::runtime_error("read seed table kept overflowing");
 }
 
-}  // namespace
+}  // namespace host
+}  // namespace pm
 
 // =====================================================================================================
 extern "C" {

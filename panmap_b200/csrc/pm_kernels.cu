@@ -10,45 +10,13 @@
 //   bfs_* / chain / ties   selection with the reference's order-dependent tolerance chain (placement.cpp:355-401)
 //
 // This is integer/byte streaming work bounded by HBM and issue rate; no tensor cores are involved.
-#include "pm_kernels.cuh"
+#include "pm_device.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 #include <vector>
 
 namespace pm {
-
-// ------------------------------------------------------------------------------------------------------
-// small helpers
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 shflU64(u64 v, int srcLane) {
-    return __shfl_sync(0xffffffffu, v, srcLane);
-}
-__device__ __forceinline__ u64 shflUpU64(u64 v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
-__device__ __forceinline__ u64 shflXorU64(u64 v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
-__device__ __forceinline__ double shflXorF64(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
-
-__device__ __forceinline__ void fxAtomicAdd(u64* acc /* lo, hi */, fx128 v) {
-    // exact 128-bit accumulation with two 64-bit atomics: the number of carries out of the low word does not
-    // depend on the order of the additions, so the result is deterministic.
-    const u64 old = atomicAdd(reinterpret_cast<unsigned long long*>(&acc[0]), v.lo);
-    const u64 carry = (old + v.lo < old) ? 1ULL : 0ULL;
-    const u64 hiAdd = (u64)v.hi + carry;
-    if (hiAdd) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[1]), hiAdd);
-}
-__device__ __forceinline__ fx128 fxWarpSum(fx128 v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        fx128 o; o.lo = shflXorU64(v.lo, d); o.hi = (i64)shflXorU64((u64)v.hi, d);
-        v = fxAdd(v, o);
-    }
-    return v;
-}
-__device__ __forceinline__ long long warpSumLL(long long v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += (long long)shflXorU64((u64)v, d);
-    return v;
-}
 
 // ------------------------------------------------------------------------------------------------------
 // pack_reads
@@ -217,26 +185,6 @@ void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cud
     if (nReads == 0) return;
     u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
     hpc_compress<<<(unsigned)g, 256, 0, st>>>(reads, off, nReads, endOff, quals);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// count table insert (open addressing, linear probing; keys are 64-bit seed hashes)
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tableInsert(TableSlot* __restrict__ table, u64 mask, u64 h, u32 add, SampleAcc* acc) {
-    if (h == kEmptyKey) { atomicAdd((unsigned long long*)&acc->emptyKeyCount, (unsigned long long)add); return; }
-    u64 slot = mixKey(h) & mask;
-    for (int probe = 0; probe < 8192; ++probe) {
-        // keys are write-once (EMPTY -> key), so a possibly stale L1 copy is safe: a stale EMPTY is resolved by the CAS, a cached
-        // non-EMPTY key is final.  Hot seeds therefore hit L1 and only the count update travels to L2.
-        u64 cur = __ldca(&table[slot].key);
-        if (cur == kEmptyKey) {
-            cur = atomicCAS((unsigned long long*)&table[slot].key, (unsigned long long)kEmptyKey, (unsigned long long)h);
-            if (cur == kEmptyKey) cur = h;
-        }
-        if (cur == h) { atomicAdd(&table[slot].count, add); return; }
-        slot = (slot + 1) & mask;
-    }
-    acc->overflow = 1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -964,11 +912,6 @@ __global__ void __launch_bounds__(256) table_clear(TableSlot* table, u64 cap) {
     uint4* t = reinterpret_cast<uint4*>(table);
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) t[i] = e;
 }
-static unsigned streamGrid(u64 n, unsigned perThread) {
-    u64 g = (n + 256ull * perThread - 1) / (256ull * perThread);
-    if (g > 148 * 16) g = 148 * 16;
-    return (unsigned)(g ? g : 1);
-}
 void launchTableClear(WorkspaceView W, cudaStream_t st) { table_clear<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W.table, W.tableCap); }
 
 __global__ void __launch_bounds__(256) table_import(TableSlot* table, u64 mask, SampleAcc* acc, const u64* __restrict__ hash,
@@ -980,9 +923,6 @@ void launchTableImport(WorkspaceView W, const u64* hash, const long long* count,
     if (!n) return;
     table_import<<<streamGrid(n, 1), 256, 0, st>>>(W.table, W.tableMask, W.acc, hash, count, n);
 }
-
-__device__ __forceinline__ uint4 ldSlot(const TableSlot* t, u64 i) { return __ldcs(reinterpret_cast<const uint4*>(t) + i); }
-__device__ __forceinline__ u64 slotKey(const uint4& v) { return (u64)v.x | ((u64)v.y << 32); }
 
 __global__ void __launch_bounds__(256) table_export(const TableSlot* __restrict__ table, u64 cap, const SampleAcc* acc, u64* outHash,
                                                     long long* outCount, unsigned* counter, u64 outCap) {
@@ -1158,39 +1098,13 @@ static u64 maskTopSeeds(WorkspaceView W, double frac, unsigned nScanParts, unsig
     return drop;
 }
 
-__device__ __forceinline__ long long resolveMinSupport(long long multiSum, long long multiCount, int configured) {
-    if (configured >= 0) return configured;
-    const double est = multiCount > 0 ? (double)(u64)multiSum / (double)(u64)multiCount : 0.0;
-    return est > 3.0 ? 2 : 1;
-}
-
 // pass 2: computeReadSeedMagnitudes (placement.cpp:957-984) + scatter of log1p(count) to the seed-id array, one thread per
 // compacted entry: log1p table, exact sums, count histogram, dictionary probe, scatter -- all independent, so the random
 // accesses of many entries are in flight at once.  The seed id found for an entry (or kNone) is written back next to it so
 // that reset_sample can clear exactly the touched ell entries without a separate list.
-constexpr int kHistSmem = 2048;
-struct FinalizeAcc { fx128 mag, lsum; long long kept; u32 maxc; };
-__device__ __forceinline__ u32 finalizeKept(const DevIndexView& I, const WorkspaceView& W, u64 k, u32 c, FinalizeAcc& A, unsigned* sHist) {
-    const double l = c < (u32)kLog1pLut ? __ldg(&I.log1pLut[c]) : log1p((double)c);
-    ++A.kept; A.maxc = max(A.maxc, c);
-    if (c < (u32)kLog1pLut) { if (c < (u32)kHistSmem) atomicAdd(&sHist[c], 1u); else atomicAdd(&W.countHist[c], 1u); }
-    A.mag = fxAdd(A.mag, fxFromDouble(l * l));
-    A.lsum = fxAdd(A.lsum, fxFromDouble(l));
-    if (k == kEmptyKey) return kNone;
-    u64 s = mixKey(k) & I.dictMask;
-    while (true) {  // is this seed anywhere in the index?
-        const uint4 d = __ldg(reinterpret_cast<const uint4*>(I.dict) + s);
-        const u64 dk = (u64)d.x | ((u64)d.y << 32);
-        if (dk == k) { W.ell[d.z] = __double2ll_rn(l * kEllScale); return d.z; }   // l >= ln 2: an exact multiple of 2^-53
-        if (dk == kEmptyKey) return kNone;
-        s = (s + 1) & I.dictMask;
-    }
-}
 __global__ void __launch_bounds__(256) entries_finalize(DevIndexView I, WorkspaceView W, int configuredMinSupport, unsigned nScanParts) {
     __shared__ unsigned sHist[kHistSmem];
-    __shared__ u64 sRed[8][4];
-    __shared__ long long sKept[8];
-    __shared__ unsigned sMax[8];
+    __shared__ FinalizeShared sFin;
     __shared__ long long sStat[4];
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     for (int i = tid; i < kHistSmem; i += blockDim.x) sHist[i] = 0;
@@ -1209,32 +1123,18 @@ __global__ void __launch_bounds__(256) entries_finalize(DevIndexView I, Workspac
     for (unsigned i = blockIdx.x * blockDim.x + tid; i < n; i += gridDim.x * blockDim.x) {
         const u32 c = __ldcs(&W.entCnt[i]);
         u32 id = kNone;
-        if (c >= minSup && c != 0) id = finalizeKept(I, W, __ldcs(&W.entKey[i]), c, A, sHist);   // c == 0: masked
+        if (c >= minSup && c != 0) {   // c == 0: masked
+            const double l = finalizeSums(I, W, c, A, sHist);
+            id = dictLookup(I, __ldcs(&W.entKey[i]));
+            if (id != kNone) W.ell[id] = __double2ll_rn(l * kEllScale);   // l >= ln 2: an exact multiple of 2^-53
+        }
         W.entId[i] = id;
     }
     if (blockIdx.x == 0 && tid == 0 && acc->emptyKeyCount > 0) {
         const u32 c = (u32)acc->emptyKeyCount;
-        if (c >= minSup) finalizeKept(I, W, kEmptyKey, c, A, sHist);
+        if (c >= minSup) finalizeSums(I, W, c, A, sHist);
     }
-    __syncthreads();
-    for (int i = tid; i < kHistSmem; i += blockDim.x) if (sHist[i]) atomicAdd(&W.countHist[i], sHist[i]);
-    const fx128 mag = fxWarpSum(A.mag), lsum = fxWarpSum(A.lsum);
-    const long long kept = warpSumLL(A.kept);
-    unsigned mx = A.maxc;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if (lane == 0) { sRed[warp][0] = mag.lo; sRed[warp][1] = (u64)mag.hi; sRed[warp][2] = lsum.lo; sRed[warp][3] = (u64)lsum.hi; sKept[warp] = kept; sMax[warp] = mx; }
-    __syncthreads();
-    if (tid == 0) {
-        fx128 m = fxZero(), l = fxZero(); long long kp = 0; unsigned mm = 0;
-        for (int q = 0; q < 8; ++q) {
-            fx128 t; t.lo = sRed[q][0]; t.hi = (i64)sRed[q][1]; m = fxAdd(m, t);
-            t.lo = sRed[q][2]; t.hi = (i64)sRed[q][3]; l = fxAdd(l, t);
-            kp += sKept[q]; mm = max(mm, sMax[q]);
-        }
-        FinPartial P; P.mag[0] = m.lo; P.mag[1] = (u64)m.hi; P.lsum[0] = l.lo; P.lsum[1] = (u64)l.hi; P.kept = kp; P.maxc = mm;
-        W.finPart[blockIdx.x] = P;
-    }
+    finalizeBlockEpilogue(W, A, sHist, &sFin);
 }
 
 // weighted-containment denominator over the ROOT's deltas (placement.cpp:1863-1876)
@@ -1306,6 +1206,14 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
                 t.lo = sFx[w][2]; t.hi = (i64)sFx[w][3]; l = fxAdd(l, t);
                 k += sK[w]; x = max(x, sM[w]);
             }
+            // sharded samples: seeds with read count 1 that the index does not hold arrive as a count (SampleAcc::n1NotIndex): each of them
+            // adds exactly what finalizeSums adds for c == 1 (their histogram share was entered by gathered_finalize)
+            const long long n1 = a->n1NotIndex;
+            if (n1 > 0 && resolveMinSupport(a->multiSum, a->multiCount, configuredMinSupport) <= 1) {
+                const double l1 = I.log1pLut[1];
+                m = fxAdd(m, fxMulU64(fxFromDouble(l1 * l1), (u64)n1)); l = fxAdd(l, fxMulU64(fxFromDouble(l1), (u64)n1));
+                k += n1; x = max(x, 1LL);
+            }
             a->magSq[0] = m.lo; a->magSq[1] = (u64)m.hi; a->logSum[0] = l.lo; a->logSum[1] = (u64)l.hi; a->kept = k; a->maxKeptCount = x;
         }
         __syncthreads();
@@ -1350,21 +1258,29 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
     *W.scalars = S;
 }
 
-void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st,
-                    double seedMaskFraction, unsigned long long* maskScratch) {
+void launchTableScan(WorkspaceView W, const u64* homo, int nSM, unsigned* nPartsOut, cudaStream_t st) {
     cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
     const u64 nBlocks = (W.tableCap + kScanSlots - 1) / kScanSlots;
-    unsigned g1 = (unsigned)std::min<u64>(std::min<u64>(nBlocks ? nBlocks : 1, (u64)nSM * 4), kMaxPartials - 1);
+    const unsigned g1 = (unsigned)std::min<u64>(std::min<u64>(nBlocks ? nBlocks : 1, (u64)nSM * 4), kMaxPartials - 1);
     table_scan<<<g1, 256, 0, st>>>(W, homo);
-    if (seedMaskFraction > 0.0) { maskTopSeeds(W, seedMaskFraction, g1, maskScratch, st); ++g1; }   // + one partial of corrections
-    // sized from the previous sample's entry count (the kernel grid-strides, so any grid is correct)
-    u64 g2 = (expectedEntries + 255) / 256; if (g2 < 1) g2 = 1; if (g2 > (u64)nSM * 4) g2 = (u64)nSM * 4; if (g2 > kMaxPartials) g2 = kMaxPartials;
-    entries_finalize<<<(unsigned)g2, 256, 0, st>>>(I, W, O.minReadSupport, g1);
+    *nPartsOut = g1;
+}
+void launchRootAndScalars(DevIndexView I, WorkspaceView W, PlaceOpts O, unsigned nFinParts, cudaStream_t st) {
     if (I.hasRoot && I.rootDCount) {
         u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
         root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);
     }
-    finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport, (unsigned)g2);
+    finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport, nFinParts);
+}
+void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st,
+                    double seedMaskFraction, unsigned long long* maskScratch) {
+    unsigned g1 = 0;
+    launchTableScan(W, homo, nSM, &g1, st);
+    if (seedMaskFraction > 0.0) { maskTopSeeds(W, seedMaskFraction, g1, maskScratch, st); ++g1; }   // + one partial of corrections
+    // sized from the previous sample's entry count (the kernel grid-strides, so any grid is correct)
+    u64 g2 = (expectedEntries + 255) / 256; if (g2 < 1) g2 = 1; if (g2 > (u64)nSM * 4) g2 = (u64)nSM * 4; if (g2 > kMaxPartials) g2 = kMaxPartials;
+    entries_finalize<<<(unsigned)g2, 256, 0, st>>>(I, W, O.minReadSupport, g1);
+    launchRootAndScalars(I, W, O, (unsigned)g2, st);
 }
 
 // after a sample: clear exactly the ell entries it set (their ids sit next to the compacted entries) and the segment records
@@ -1878,7 +1794,7 @@ __global__ void __launch_bounds__(256) bfs_records(DevIndexView I, WorkspaceView
                 W.recRank[(size_t)m * W.recCap + o] = I.bfsRanks[r];
                 W.recNode[(size_t)m * W.recCap + o] = I.bfsNodes[r];
                 W.recScore[(size_t)m * W.recCap + o] = x[q];
-            } else W.acc->overflow = 1;
+            } else raiseFlag(W.acc, kOvfTable);
         }
         run = fmax(run, x[q]);
     }
@@ -1939,7 +1855,7 @@ __global__ void __launch_bounds__(256) collect_ties(DevIndexView I, WorkspaceVie
         const double x = bfsScores[(size_t)m * I.nShardNodes + r];
         if (x >= lo && x > 0.0) {
             const unsigned o = atomicAdd(&W.acc->tieCount[m], 1u);
-            if (o < W.tieCap) W.tieNode[(size_t)m * W.tieCap + o] = I.bfsNodes[r]; else W.acc->overflow = 1;
+            if (o < W.tieCap) W.tieNode[(size_t)m * W.tieCap + o] = I.bfsNodes[r]; else raiseFlag(W.acc, kOvfTable);
             if (o < (unsigned)kTieHead) W.tieHead[m * kTieHead + o] = I.bfsNodes[r];
         }
     }

@@ -30,7 +30,11 @@ struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample
     unsigned pad0, entCount;
     unsigned recordCount[8];
     unsigned tieCount[8];
+    long long n1NotIndex;   // sharded samples: kept seeds with read count 1 that the index does not hold (they travel as a count, not as entries)
+    long long totalReads;   // sharded samples: reads of all ranks
 };
+// bits of SampleAcc::overflow (any non-zero value makes the host grow what was too small and redo the sample)
+constexpr long long kOvfTable = 1, kOvfPair = 2, kOvfGather = 4, kOvfRecords = 8;
 struct ScanPartial { long long multiSum, multiCount, entries, total; };          // one per table_scan block
 struct FinPartial { u64 mag[2], lsum[2]; long long kept; long long maxc; };        // one per entries_finalize block
 constexpr unsigned kMaxPartials = 2048;
@@ -108,6 +112,29 @@ struct WorkspaceView {
     SampleScalars* scalars;
 };
 
+// ---- one sample over several GPUs: fixed-capacity exchange buffers with in-band counts (no host round trip between stages) ----
+// seed partition exchange (all-to-all): per destination rank one segment of 1 + capPair 16-byte slots; slot 0 is the header
+struct __align__(16) XHeader { u32 count; u32 flags; u32 pad[2]; };
+struct __align__(16) XEntry { u64 key; u32 count; u32 pad; };
+// finalized partition entries (all-gather): header + capG pairs (read count, seed id or kNone)
+struct __align__(16) GHeader {
+    u32 nEntries; u32 flags;            // flags: SampleAcc::overflow of the sending rank at that point
+    u64 n1NotIndex;                     // seeds with count 1 that are not in the index (sent as a count only)
+    long long multiSum, multiCount;     // auto min-support statistics of the partition (placement.cpp:931-955)
+    long long unique, total;            // seeds / seed instances of the partition (after homopolymer removal)
+    u64 nReads;                         // reads this rank seeded
+    u32 maxPairCount; u32 localEntries; // sizing feedback: largest per-destination export count, unique seeds of the local table
+};
+static_assert(sizeof(GHeader) == 64, "GHeader is eight uint2 slots");
+constexpr u32 kGHeaderSlots = sizeof(GHeader) / sizeof(uint2);
+// local prefix-maximum records (all-gather): header (2 slots) + [5][recX] records of 16 bytes; recX is a run-time capacity
+struct __align__(16) RHeader { u32 count[5]; u32 flags; u32 pad[2]; };
+struct __align__(16) RRecord { double score; u32 rank; u32 node; };
+// tie heads (all-gather): counts, flags, sizing feedback for the next sample, then [5][kTieHead] node ids
+struct __align__(16) THeader { u32 tieCount[5]; u32 flags; u32 maxPairCount, localEntries, gEntries, partEntries; u32 pad[6]; };
+static_assert(sizeof(THeader) == 64, "THeader is sixteen words");
+constexpr u32 kTWords = sizeof(THeader) / 4 + 5 * kTieHead;   // 32-bit words per rank
+
 struct PlaceOpts {
     int minReadSupport;
     int forceLeaf;
@@ -149,5 +176,24 @@ void launchRecords(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st
 void launchChain(WorkspaceView W, const u32* recCountOverride, cudaStream_t st);
 void launchTies(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st);
 void launchResetSample(DevIndexView I, WorkspaceView W, cudaStream_t st);
+
+// ---- sharded samples (pm_shard_kernels.cu) ----
+// local table -> per-owner segments of xSend ([nRanks][1 + capPair] slots, headers zeroed by the launch)
+void launchPartitionExport(WorkspaceView W, u32 nRanks, u32 capPair, uint4* xSend, u32* exportInfo /* device, [2]: max per-destination count, total */, cudaStream_t st);
+// received segments -> this rank's partition table (cleared by the caller)
+void launchPartitionImport(WorkspaceView W, const uint4* xRecv, u32 nRanks, u32 capPair, cudaStream_t st);
+// after table_scan on the partition: dictionary look-up of every entry, header + (count, id) pairs into gSend ([kGHeaderSlots + capG] uint2)
+void launchPartitionFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, int nSM, uint2* gSend, u32 capG, u64 nLocalReads,
+                             const u32* maxPairCount, u32 localEntriesHint, cudaStream_t st);
+// all ranks' gathered lists -> ell, exact magnitude sums, histogram, scalars (replaces entries_finalize + finish_scalars of the one-GPU path)
+void launchGatheredFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const uint2* gRecv, u32 nRanks, u32 capG, int nSM, cudaStream_t st);
+void launchRecordsPack(WorkspaceView W, uint4* rSend, u32 recX, cudaStream_t st);
+void launchChainGathered(WorkspaceView W, const uint4* rRecv, u32 nRanks, u32 recX, cudaStream_t st);
+void launchTiesPack(WorkspaceView W, u32* tSend, const uint2* gSend, const u32* exportInfo /* [2] from launchPartitionExport */, cudaStream_t st);
+void launchTiesFullPack(WorkspaceView W, u32* out /* [5][capT] */, u32 capT, cudaStream_t st);
+void launchResetGathered(DevIndexView I, WorkspaceView W, const uint2* gRecv, u32 nRanks, u32 capG, cudaStream_t st);
+// pieces of launchFinalize the sharded path runs on their own
+void launchTableScan(WorkspaceView W, const u64* homo, int nSM, unsigned* nPartsOut, cudaStream_t st);
+void launchRootAndScalars(DevIndexView I, WorkspaceView W, PlaceOpts O, unsigned nFinParts, cudaStream_t st);
 
 }  // namespace pm

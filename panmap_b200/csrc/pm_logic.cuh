@@ -202,6 +202,14 @@ PM_HD fx128 fxNeg(fx128 a) {
     fx128 r; r.lo = ~a.lo + 1ULL; r.hi = (i64)(~(u64)a.hi + (r.lo == 0 ? 1ULL : 0ULL)); return r;
 }
 PM_HD fx128 fxSub(fx128 a, fx128 b) { return fxAdd(a, fxNeg(b)); }
+PM_HD fx128 fxMulU64(fx128 a, u64 n) {   // a >= 0 times a count (the product must stay below 2^126)
+#if defined(__CUDA_ARCH__)
+    const u64 carry = __umul64hi(a.lo, n);
+#else
+    const u64 carry = (u64)(((unsigned __int128)a.lo * n) >> 64);
+#endif
+    fx128 r; r.lo = a.lo * n; r.hi = (i64)((u64)a.hi * n + carry); return r;
+}
 PM_HD fx128 fxFromInt(i64 v) { fx128 r; r.lo = 0; r.hi = v; return r; }
 PM_HD u64 dblBits(double x) {
 #if defined(__CUDA_ARCH__)
@@ -332,5 +340,8 @@ PM_HD void nodeScores(double raw, double cosn, double pres, double wc, double co
 
 // table slot hash (keys are already hashes, but their low bits come from XORs of rotations: mix once)
 PM_HD u64 mixKey(u64 h) { h ^= h >> 32; h *= 0x9E3779B97F4A7C15ULL; h ^= h >> 29; return h; }
+
+// sharded samples: owner rank of a seed = the high bits of its mixed hash scaled to [0, nRanks) (table slots use the low bits)
+PM_HD u32 seedOwner(u64 h, u32 nRanks) { return (u32)(((mixKey(h) >> 32) * (u64)nRanks) >> 32); }
 
 }  // namespace pm

@@ -37,6 +37,18 @@ int64_t hc_seed(const char* seq, int64_t len, int k, int s, int t, int l, int op
     return n;
 }
 
+// owner rank of every seed of a sharded sample (pm_logic.cuh seedOwner, the function partition_export uses on the device)
+void hc_seed_owner(const uint64_t* h, int64_t n, uint32_t nRanks, uint32_t* out) { for (int64_t i = 0; i < n; ++i) out[i] = seedOwner(h[i], nRanks); }
+// exact magnitude sums the way gathered_finalize + finish_scalars form them (minus the rounding-drift term): per-entry fixed-point terms
+// of the listed counts plus n1 times the count-1 term; out: sum log1p^2, sum log1p
+void hc_gathered_sums(const uint32_t* cnt, int64_t n, uint64_t n1, double* out) {
+    fx128 m = fxZero(), l = fxZero();
+    for (int64_t i = 0; i < n; ++i) { const double x = std::log1p((double)cnt[i]); m = fxAdd(m, fxFromDouble(x * x)); l = fxAdd(l, fxFromDouble(x)); }
+    const double l1 = std::log1p(1.0);
+    m = fxAdd(m, fxMulU64(fxFromDouble(l1 * l1), n1)); l = fxAdd(l, fxMulU64(fxFromDouble(l1), n1));
+    out[0] = fxToDouble(m); out[1] = fxToDouble(l);
+}
+
 double hc_fx_roundtrip(double x) { return fxToDouble(fxFromDouble(x)); }
 // exact sum of doubles through the fixed-point accumulator, in the given order and in reverse: both must agree
 int hc_fx_sum(const double* x, int64_t n, double* fwd, double* rev) {
