@@ -10,9 +10,9 @@ delta kernel -> exact tree prefix + scores -> tolerance-chain selection -> 5 bes
   roofline: dominant kernel of the step (by measured time) + the scoring kernel north_star names, algorithmic bytes/launch
   cpu_baseline / --impl reference: the reference's own placeLite (oracle/_ref, compiled unmodified) on the host cores
 
-N > 1 (torchrun): batch mode -- every rank holds the index and places its own sample per step, no collective (weak scaling);
-the single-sample node-sharded protocol (reads sharded for seeding, tables / records / ties all-gathered over NCCL) is timed
-as well and reported under "single_sample_node_sharded".
+N > 1 (torchrun): ONE sample over the N GPUs (BASELINE configs[2]: node range sharded, reads sliced for seeding, seed table
+hash-partitioned; pm_comm over NCCL) -- strong scaling, this is `value`; the sample-sharded batch mode (one replica and one sample per GPU,
+no collective) is timed as well and reported under "batch_mode".
 """
 import argparse
 import ctypes as C
@@ -36,11 +36,6 @@ WORKLOADS = {
     "c3-small": dict(name="synthetic 100k-node tree, 30 kb genome, 100k x 150 bp reads (reduced configs[2], dev only)", n_nodes=100_000,
                      genome=30_000, lam=1.0, n_reads=100_000, read_len=150),
 }
-KERNELS_PER_STEP = 14  # table_clear syncmers_fast count_seeds table_scan entries_finalize root_denominator finish_scalars
-#                        node_deltas prefix_scores bfs_gather bfs_records chain_select collect_ties reset_sample
-#                        (+ gen_deltas, gen_prefix when the index holds deltas with a genome count >= 2; the synthetic one has none)
-# DRAM bytes (read + write) per launch from the ncu --set full captures of this workload (profiles/ncu_r01x_summary.txt, ncu_r01w_summary.txt)
-NCU_TRAFFIC = {"node_deltas": 78.4e6, "syncmers_fast": 0.563e9, "count_seeds": 0.57e9, "prefix_scores": 70e6, "pack_reads": 0.22e9}
 
 
 def peaks():
@@ -114,28 +109,53 @@ def algorithmic_bytes(S):
     return dict(seeding=bases, scoring=score, delta_kernel=12 * D + 8 * (N + 1), total=bases + score)
 
 
+def write_fastq(S, n_reads, path):
+    """FASTQ of the first n_reads reads of the synthetic sample (four lines per record, constant qualities)"""
+    if os.path.exists(path):
+        return path
+    off = S.read_offsets
+    buf = S.reads.tobytes()
+    with open(path, "wb") as f:
+        chunk = []
+        for i in range(n_reads):
+            s = buf[int(off[i]):int(off[i + 1])]
+            chunk.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
+            if len(chunk) >= 20000:
+                f.write(b"".join(chunk)); chunk = []
+        f.write(b"".join(chunk))
+    return path
+
+
 def reference_step(S, n_reads, threads, tmpdir, cache={}):
-    """the reference's placeLite on the synthetic index (written as a real uncompressed .idx) + a FASTQ of the first n_reads"""
+    """the reference's own placeLite (oracle/_ref: unmodified sources) on the synthetic index (written as a real uncompressed .idx) and a
+    FASTQ of the first n_reads reads.  Returns (seconds of the whole call, result incl. the reference's own stage timers)."""
     from oracle import ref
     if "idx" not in cache:
         p = os.path.join(tmpdir, "synth.idx")
         ref.write_index(p, S)
         cache["idx"] = ref.RefIndex(p)
-    fq = os.path.join(tmpdir, f"reads_{n_reads}.fastq")
-    if not os.path.exists(fq):
-        off = S.read_offsets
-        buf = S.reads.tobytes()
-        with open(fq, "wb") as f:
-            chunk = []
-            for i in range(n_reads):
-                s = buf[int(off[i]):int(off[i + 1])]
-                chunk.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * len(s)))
-                if len(chunk) >= 20000:
-                    f.write(b"".join(chunk)); chunk = []
-            f.write(b"".join(chunk))
+    fq = write_fastq(S, n_reads, os.path.join(tmpdir, f"reads_{n_reads}.fastq"))
     t = time.perf_counter()
-    r = cache["idx"].place(fq, "", out_tsv=os.path.join(tmpdir, "ref.tsv"), threads=threads)
+    r = cache["idx"].place(fq, "", out_tsv=os.path.join(tmpdir, "ref.tsv"), threads=threads, stage_timers=True)
     return time.perf_counter() - t, r
+
+
+def reference_spans(dt, r):
+    """the reference's place stage split by its own timers (placement.cpp:1128,1691,1701,1929): FASTQ parse = read processing minus seed
+    extraction; buffers -> result = the whole call minus that parse (what the GPU arm's `e2e` spans: reads in host memory -> placement)"""
+    st = r["stage_ms"]
+    parse = max(st["read_processing"] - max(st["seeding"], 0.0) - max(st["dedup"], 0.0), 0.0)
+    return {"file_to_result_ms": 1e3 * dt, "fastq_parse_ms": parse, "seeding_ms": st["seeding"], "tree_traversal_ms": st["traversal"],
+            "buffers_to_result_ms": 1e3 * dt - parse}
+
+
+def same_placement(a_idx, a_tied, a_score, b_idx, b_tied, b_score, rtol=1e-12):
+    """best node, tie list and best score of every metric agree"""
+    ok = True
+    for m in range(5):
+        ok = ok and int(a_idx[m]) == int(b_idx[m]) and np.array_equal(np.asarray(a_tied[m], np.uint32), np.asarray(b_tied[m], np.uint32))
+        ok = ok and abs(float(a_score[m]) - float(b_score[m])) <= rtol * max(abs(float(b_score[m])), 1e-9)
+    return bool(ok)
 
 
 def run_reference_arm(args):
@@ -158,21 +178,45 @@ def run_reference_arm(args):
         n_s = int(min(w["n_reads"], max(20000, (budget - fixed) / per_read)))
         for _ in range(args.warmup):
             reference_step(S, n_s, threads, td)
-        times = []
+        spans = []
         for _ in range(args.steps):
             dt, r = reference_step(S, n_s, threads, td)
-            times.append(dt)
-    tot = sum(times)
-    value = S.n_nodes * n_s * args.steps / tot
+            spans.append(reference_spans(dt, r))
+    mean = {k: float(np.mean([x[k] for x in spans])) for k in spans[0]}
+    # headline of this arm = the same span as the GPU arm's e2e: reads in host memory -> placement on the host (the parse is reported beside it)
+    ms = mean["buffers_to_result_ms"]
+    value = S.n_nodes * n_s / (ms * 1e-3)
     line = {"impl": "reference", "metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
             "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n_s, "k": 19, "s": 8, "l": 3},
+            "spans": mean,
+            "span_note": "value / ms_per_step / e2e = buffers_to_result (the whole placeLite call minus its FASTQ parse, by the reference's own stage timers): "
+                         "the span the GPU arm's e2e covers.  file_to_result_ms is the whole call (parse of the FASTQ file + TSV write included).",
+            "placed": {m: int(r["best_index"][i]) for i, m in enumerate(("log_raw", "log_cosine", "containment", "weighted_containment", "log_containment"))},
+            "tied_counts": [int(len(t)) for t in r["tied"]], "best_scores": [float(x) for x in r["best_score"]],
             "cpu_baseline": {"value": value, "unit": "node*reads/s", "cores": threads, "kind": "reference",
                              "sample": f"reference placeLite (oracle/_ref, unmodified sources, std-container/oneTBB stand-ins) on the full {S.n_nodes}-node index "
-                                       f"with the first {n_s} of {w['n_reads']} reads per step"},
+                                       f"with the first {n_s} of {w['n_reads']} reads per step, {threads} host threads"},
             "e2e": {"value": value, "unit": "node*reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def ncu_traffic():
+    """DRAM bytes (read + write) per launch of the hot kernels, from the committed ncu --set full capture of the CURRENT round
+    (profiles/ncu_traffic.json, written by tools/ncu_summary.py --json); None when there is no such file"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return {}, None
+    d = json.load(open(p))
+    return d.get("kernels", {}), d.get("capture")
+
+
+def pinned_copy(L, arr):
+    n = int(arr.nbytes)
+    p = L.pm_host_alloc(n + 64)
+    C.memmove(p, arr.ctypes.data, n)
+    return p
 
 
 def main():
@@ -183,6 +227,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=os.environ.get("PM_BENCH_WORKLOAD", "c3"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-file-span", action="store_true", help="skip the FASTQ file -> result measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -213,12 +258,14 @@ def main():
     sampler.start()
     stage = np.zeros(8)
     kern = np.zeros(3)
+    launches0 = pm.launch_count()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         r = ws.place_resident(params, full=False)
         stage += np.array(list(r.stage_ms))
         kern += np.array(ws.last_kernel_ms())
     wall = time.perf_counter() - t0
+    launches = pm.launch_count() - launches0
     clocks = sampler.stop()
     stage /= args.steps
     kern /= args.steps
@@ -229,10 +276,8 @@ def main():
     # ---- e2e: host (pinned) buffers through the C ABI ----
     L = pm.lib()
     nbytes = int(S.read_offsets[-1])
-    hp_reads = L.pm_host_alloc(nbytes + 64)
-    hp_off = L.pm_host_alloc(8 * (w["n_reads"] + 1))
-    C.memmove(hp_reads, S.reads.ctypes.data, nbytes)
-    C.memmove(hp_off, S.read_offsets.ctypes.data, 8 * (w["n_reads"] + 1))
+    hp_reads = pinned_copy(L, S.reads)
+    hp_off = pinned_copy(L, S.read_offsets)
     for _ in range(3):
         ws.place_raw(hp_reads, hp_off, w["n_reads"], params)
     t0 = time.perf_counter()
@@ -245,12 +290,14 @@ def main():
     h2d = nbytes + 8 * (w["n_reads"] + 1)            # reads + offsets (the chunk offsets are rebuilt on the device)
     d2h = 432 + 4 * int(sum(res.raw.tied_count))     # accumulators/scalars/selection block + tie lists
     L.pm_host_free(hp_reads); L.pm_host_free(hp_off)
+    spans = {"buffers_to_result_ms": 1e3 * e2e_wall / args.steps}
 
     # ---- roofline ----
     # dominant kernel of the step = the syncmer kernel (CUDA events of the library around that launch alone); it is bound by the
     # integer ALU pipe, not by HBM, so its fraction of the HBM roofline is small by construction.  The HBM-bound kernel north_star
     # names (node_deltas) is reported next to it the same way.
     peak = float(pk["hbm_gbs"])
+    traffic, capture = ncu_traffic()
     names = ["h2d", "seeding+table insert (syncmers_fast, count_seeds)", "table finalize", "node_deltas", "prefix_scores", "selection", "d2h"]
     per_kernel = {"pack_reads": float(kern[0]), "syncmers_fast<19,8>": float(kern[1]), "count_seeds<19,3>": float(kern[2]),
                   "node_deltas": float(stage[3]), "prefix_scores": float(stage[4])}
@@ -266,50 +313,74 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64+f64", "data": "synthetic",
         "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": w["n_reads"], "read_bases": nbytes, "k": S.k, "s": S.s,
-                   "l": S.l, "l2": "per-step working set (reads 150 MB + packed 75 MB + count table + delta arrays) exceeds the 126 MB L2; no explicit flush",
+                   "l": S.l, "l2": "per-step working set (reads 150 MB + syncmer lists 320 MB + count table + delta arrays) exceeds the 126 MB L2; no explicit flush",
                    "truth_node": int(S.truth), "placed": {m: int(res.best_index[m]) for m in pm.METRICS},
                    "unique_seeds": int(res.raw.unique_seeds), "kept_seeds": int(res.raw.read_unique_seed_count),
                    "min_read_support": int(res.raw.min_read_support), "index_distinct_seeds": int(index.num_distinct_seeds)},
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "stage_ms": {n: float(stage[i]) for i, n in enumerate(names)},
         "e2e": {"value": e2e_value, "unit": "node*reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
-                "device_ms_per_step": e2e_dev / args.steps},
-        "gpu_launches": KERNELS_PER_STEP * args.steps,
+                "device_ms_per_step": e2e_dev / args.steps, "span": "buffers_to_result: ASCII reads + offsets in pinned host memory -> best nodes + tie lists on the host"},
+        "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "kernel_ms": per_kernel,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": NCU_TRAFFIC.get(dom_name.split("<")[0]), "algorithmic_bytes_per_launch": dom_bytes, "ms": per_kernel[dom_name], "peak_source": pk_src,
+                     "traffic": traffic.get(dom_name.split("<")[0]), "traffic_capture": capture, "algorithmic_bytes_per_launch": dom_bytes, "ms": per_kernel[dom_name],
+                     "peak_source": pk_src,
                      "note": "dominant kernel of the step by measured time; it is limited by the integer ALU pipe (ncu: pipe_alu 84-88 %), one byte in per ~120 "
                              "integer instructions, so the HBM fraction is small by construction -- see roofline_scoring for the HBM-bound kernel north_star names"},
         "roofline_scoring": {"bound": "hbm", "kernel": "node_deltas (the scoring kernel north_star names)", "achieved": sc_ach, "peak": peak, "unit": "GB/s",
-                             "frac": sc_ach / peak, "traffic": NCU_TRAFFIC["node_deltas"], "algorithmic_bytes_per_launch": alg["delta_kernel"], "ms": float(stage[3]),
+                             "frac": sc_ach / peak, "traffic": traffic.get("node_deltas"), "algorithmic_bytes_per_launch": alg["delta_kernel"], "ms": float(stage[3]),
                              "note": "algorithmic bytes = 12 B/delta + 8 B/node of the reference layout (SURVEY 8d); the kernel itself streams 4 B/delta"},
         "place_stage": {"algorithmic_bytes": alg["total"], "achieved": alg["total"] / (dev_ms * 1e-3) / 1e9, "frac": alg["total"] / (dev_ms * 1e-3) / 1e9 / peak},
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
-        try:
-            from oracle import ref
-            if ref.available():
-                with tempfile.TemporaryDirectory() as td:
+    with tempfile.TemporaryDirectory() as td:
+        if not args.no_file_span:
+            # the other span: FASTQ FILE -> result through the C++ shim (multi-threaded flat parser + the same pm_place), same file the reference arm parses
+            try:
+                fq = write_fastq(S, w["n_reads"], os.path.join(td, "reads_all.fastq"))
+                pm.place_files(ws, fq, "", os.path.join(td, "gpu.tsv"), params)
+                t0 = time.perf_counter()
+                k3 = max(2, min(args.steps, 5))
+                for _ in range(k3):
+                    rf = pm.place_files(ws, fq, "", os.path.join(td, "gpu.tsv"), params)
+                spans["file_to_result_ms"] = 1e3 * (time.perf_counter() - t0) / k3
+                spans["file_bytes"] = os.path.getsize(fq)
+                spans["file_result_same_as_buffers"] = bool(all(int(rf.best_index[i]) == int(res.best_index[m]) for i, m in enumerate(pm.METRICS)))
+            except Exception as e:  # reported, never fatal
+                spans["file_to_result_error"] = str(e)
+        line["spans"] = spans
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+                if ref.available():
                     threads = os.cpu_count() or 1
                     n_s = min(w["n_reads"], 200_000)
                     dt, rr = reference_step(S, n_s, threads, td)
-                    line["cpu_baseline"] = {"value": S.n_nodes * n_s / dt, "unit": "node*reads/s", "cores": threads, "kind": "reference", "seconds": dt,
-                                            "sample": f"reference placeLite (oracle/_ref: unmodified reference sources, std-container + std::thread oneTBB stand-ins) on the full "
-                                                      f"{S.n_nodes}-node index with the first {n_s} of {w['n_reads']} reads, FASTQ parse included",
-                                            "agrees_with_gpu": bool(all(int(rr["best_index"][m]) == int(res.best_index[n]) for m, n in enumerate(pm.METRICS)) if n_s == w["n_reads"] else True)}
-            else:
-                line["cpu_baseline"] = {"value": None, "unit": "node*reads/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
-        except Exception as e:  # the baseline is reported, never fatal
-            line["cpu_baseline"] = {"value": None, "unit": "node*reads/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+                    sp = reference_spans(dt, rr)
+                    # the GPU on the very same sample: agreement is checked, not assumed
+                    sub_off = np.ascontiguousarray(S.read_offsets[:n_s + 1])
+                    g = ws.place(S.reads[:int(sub_off[-1])], sub_off, params)
+                    agree = same_placement([g.best_index[m] for m in pm.METRICS], [g.tied[m] for m in pm.METRICS], [g.best_score[m] for m in pm.METRICS],
+                                           rr["best_index"], rr["tied"], rr["best_score"])
+                    line["cpu_baseline"] = {"value": S.n_nodes * n_s / (sp["buffers_to_result_ms"] * 1e-3), "unit": "node*reads/s", "cores": threads, "kind": "reference",
+                                            "seconds": dt, "spans": sp,
+                                            "sample": f"first {n_s} of {w['n_reads']} reads on the full {S.n_nodes}-node index, ONE call: reference placeLite (oracle/_ref: unmodified "
+                                                      f"reference sources, std-container + std::thread oneTBB stand-ins), {threads} host threads; value = its buffers_to_result span "
+                                                      f"(whole call minus its FASTQ parse); the --impl reference arm runs more reads per step",
+                                            "gpu_same_sample": {"best_nodes_tie_lists_scores_agree": agree, "gpu_ms": float(g.stage_ms[7])}}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "node*reads/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+            except Exception as e:  # the baseline is reported, never fatal
+                line["cpu_baseline"] = {"value": None, "unit": "node*reads/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
     print(json.dumps(line))
 
 
 def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local):
-    """N > 1: batch mode (north_star: "a multi-sample batch mode shards samples instead"; reference runBatchPlacement,
-    main.cpp:1464-1666): every rank holds the whole index and places its own sample, no data-path collective -> weak scaling.
-    The single-sample node-sharded protocol (panmap_b200/distributed.py: reads sharded for seeding, tables / records / ties
-    all-gathered over NCCL) is timed after it and reported under "single_sample_node_sharded"."""
+    """N > 1: ONE sample over the N GPUs (BASELINE configs[2]): node range sharded, reads sliced for seeding, seed table hash-partitioned
+    (pm_comm over NCCL, panmap_b200/csrc/pm_multi.cu) -> strong scaling; this is `value`.  The sample-sharded batch mode (one replica and
+    one sample per GPU per step, no collective; reference runBatchPlacement, main.cpp:1464-1666) is timed after it and reported under
+    "batch_mode"."""
     import torch
     import torch.distributed as dist
     from panmap_b200 import distributed as pmd
@@ -318,87 +389,107 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
     dev = torch.device("cuda", local)
     n = w["n_reads"]
     nodes_reads = S.n_nodes * n
+    L = pm.lib()
+    steps, warm = args.steps, max(args.warmup, 3)
 
-    # ---- batch mode: one replica per GPU, every rank places its own copy of the sample ----
-    index = pm.Index(host, device=local)
+    def maxf(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- one sample over N GPUs ----
+    index = pm.Index(host, device=local, shard=rank, n_shards=world)
     ws = pm.Workspace(index)
-    ws.upload(S.reads, S.read_offsets)
-    for _ in range(max(args.warmup, 3)):
-        ws.place_resident(params, full=False)
+    comm = pmd.make_comm(ws)
+    reads, off = pmd.slice_reads(S.reads, S.read_offsets, rank, world)
+    ws.upload(reads, off)
+    for _ in range(warm):
+        comm.place_sharded_resident(params, full=False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    stage = np.zeros(8)
     dist.barrier(); torch.cuda.synchronize()
-    dev_ms = 0.0
+    launches0 = pm.launch_count()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        r = ws.place_resident(params, full=False)     # returns after the result is on the host (stream synchronised)
-        dev_ms += r.stage_ms[7]
-    wall = time.perf_counter() - t0
-    torch.cuda.synchronize(); dist.barrier()
+    for _ in range(steps):
+        r = comm.place_sharded_resident(params, full=False)   # returns after the result is on the host (library stream synchronised)
+        stage += np.array(list(r.stage_ms))
+    torch.cuda.synchronize()
+    wall_local = time.perf_counter() - t0
+    launches = pm.launch_count() - launches0
+    dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
-    res = ws.place_resident(params)
-    t = torch.tensor([dev_ms, wall * 1e3], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    per = float(t[0].item()) / args.steps            # CUDA-event time of a step, max over ranks
-    ok = torch.tensor([1 if all(int(res.best_index[m]) >= 0 for m in pm.METRICS) else 0], device=dev)
-    placed = {m: int(res.best_index[m]) for m in pm.METRICS}
-    # e2e: host (pinned) buffers through the C ABI on every rank
-    L = pm.lib()
-    nbytes = int(S.read_offsets[-1])
-    hp_reads = L.pm_host_alloc(nbytes + 64); hp_off = L.pm_host_alloc(8 * (n + 1))
-    C.memmove(hp_reads, S.reads.ctypes.data, nbytes); C.memmove(hp_off, S.read_offsets.ctypes.data, 8 * (n + 1))
+    stage /= steps
+    per = maxf(float(stage[7]))                                # CUDA-event time of a step on the library stream, max over ranks
+    wall = maxf(wall_local * 1e3 / steps)
+    res = comm.place_sharded_resident(params)
+    sent, recv = comm.last_traffic()
+    stage_max = [maxf(float(x)) for x in stage]
+    # e2e: every rank's slice in pinned host memory -> result on every rank
+    hp_reads = pinned_copy(L, reads); hp_off = pinned_copy(L, off)
     for _ in range(3):
-        ws.place_raw(hp_reads, hp_off, n, params)
+        comm.place_sharded_raw(hp_reads, hp_off, off.size - 1, params)
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ws.place_raw(hp_reads, hp_off, n, params)
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
-    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    for _ in range(steps):
+        comm.place_sharded_raw(hp_reads, hp_off, off.size - 1, params)
+    e2e_ms = maxf((time.perf_counter() - t0) * 1e3 / steps)
     L.pm_host_free(hp_reads); L.pm_host_free(hp_off)
-    e2e = {"value": world * nodes_reads / (float(e2e_ms.item()) / args.steps * 1e-3), "unit": "node*reads/s",
-           "h2d_bytes_per_step": world * (nbytes + 8 * (n + 1)), "d2h_bytes_per_step": world * 452, "ms_per_step": float(e2e_ms.item()) / args.steps}
+    h2d_local = int(reads.nbytes) + 8 * int(off.size)
+    t = torch.tensor([h2d_local, launches], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    h2d_all, launches_all = int(t[0].item()), int(t[1].item())
+    sharded_placed = {m: int(res.best_index[m]) for m in pm.METRICS}
+    sharded_tied = [np.asarray(res.tied[m]) for m in pm.METRICS]
+    sharded_score = [float(res.best_score[m]) for m in pm.METRICS]
+    comm.close()
     del ws, index
 
-    # ---- single sample, node range sharded over the ranks (strong scaling; reported, not the headline) ----
-    sharded = None
+    # ---- batch mode: one replica per GPU, every rank places its own copy of the sample (weak scaling, no collective) ----
+    batch = None
     try:
-        index = pm.Index(host, device=local, shard=rank, n_shards=world)
+        index = pm.Index(host, device=local)
         ws = pm.Workspace(index)
-        lo, hi = (n * rank) // world, (n * (rank + 1)) // world
-        off = S.read_offsets[lo:hi + 1] - S.read_offsets[lo]
-        reads = S.reads[int(S.read_offsets[lo]):int(S.read_offsets[hi])]
-        ws.upload(reads, off)
+        ws.upload(S.reads, S.read_offsets)
         for _ in range(3):
-            r2 = pmd.place_sharded(ws, reads, off, n, params, device=dev, resident=True)
+            ws.place_resident(params, full=False)
         dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        k2 = max(3, min(args.steps, 10))
+        k2 = max(3, min(steps, 10))
+        dev_ms = 0.0
         for _ in range(k2):
-            r2 = pmd.place_sharded(ws, reads, off, n, params, device=dev, resident=True)
+            dev_ms += ws.place_resident(params, full=False).stage_ms[7]
         torch.cuda.synchronize(); dist.barrier()
-        ms2 = torch.tensor([(time.perf_counter() - t0) * 1e3 / k2], device=dev, dtype=torch.float64)
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        sharded = {"ms_per_step": float(ms2.item()), "value": nodes_reads / (float(ms2.item()) * 1e-3), "scaling": "strong",
-                   "same_placement_as_batch": bool(all(int(r2.best_index[m]) == placed[m] for m in pm.METRICS)),
-                   "parallelism": f"node range sharded over {world} GPUs (delta-balanced DFS ranges), reads sharded for seeding, count tables / records / ties all-gathered (NCCL)"}
+        bper = maxf(dev_ms / k2)
+        one = ws.place_resident(params)
+        same = same_placement([one.best_index[m] for m in pm.METRICS], [one.tied[m] for m in pm.METRICS], [one.best_score[m] for m in pm.METRICS],
+                              [sharded_placed[m] for m in pm.METRICS], sharded_tied, sharded_score, rtol=0.0)
+        same = maxf(0.0 if same else 1.0) == 0.0
+        batch = {"ms_per_step": bper, "value": world * nodes_reads / (bper * 1e-3), "scaling": "weak", "samples_per_step": world,
+                 "parallelism": f"{world} replicas of the index, one sample per GPU per step, no collective (BASELINE configs[4] mode on configs[2] shapes)"}
     except Exception as e:  # reported, never fatal
-        sharded = {"error": str(e)}
+        batch = {"error": str(e)}; same = None
     if rank == 0:
-        value = world * nodes_reads / (per * 1e-3)
-        line = {"metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64+f64",
+        value = nodes_reads / (per * 1e-3)
+        names = ["setup", "table setup", "seeding of the read slice + partition export", "exchange + partition finalize + all-gather + gathered finalize",
+                 "node_deltas (own node range)", "prefix_scores", "records all-gather + chain + ties + ties all-gather", "d2h + reset"]
+        line = {"metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": world, "steps": steps,
+                "warmup": warm, "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64+f64",
                 "data": "synthetic",
-                "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n, "samples_per_step": world, "k": S.k, "s": S.s, "l": S.l,
-                           "parallelism": f"batch mode: {world} replicas of the index, one sample per GPU per step, no collective (sample-sharded, BASELINE configs[4] mode on configs[2] shapes)",
-                           "l2": "working set exceeds L2; no explicit flush", "placed": placed, "truth_node": int(S.truth)},
-                "wall_ms_per_step": float(t[1].item()) / args.steps,
-                "e2e": e2e,
-                "gpu_launches": KERNELS_PER_STEP * args.steps * world,
-                "roofline": {"bound": "hbm", "kernel": "whole place stage (all replicas)", "achieved": world * alg["total"] / (per * 1e-3) / 1e9, "peak": float(pk["hbm_gbs"]) * world,
-                             "unit": "GB/s", "frac": alg["total"] / (per * 1e-3) / 1e9 / float(pk["hbm_gbs"]), "traffic": None, "peak_source": pk_src},
-                "single_sample_node_sharded": sharded,
+                "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n, "samples_per_step": 1, "k": S.k, "s": S.s, "l": S.l,
+                           "parallelism": f"one sample over {world} GPUs: node range sharded (delta-balanced DFS ranges + ancestors), reads sliced for seeding, seed table "
+                                          f"hash-partitioned (NCCL all-to-all), finalized (count, seed id) pairs / records / tie heads by fixed-capacity all-gathers, one D2H",
+                           "l2": "working set exceeds L2; no explicit flush", "placed": sharded_placed, "truth_node": int(S.truth)},
+                "wall_ms_per_step": wall,
+                "stage_ms": {nm: stage_max[i] for i, nm in enumerate(names[:7])},
+                "e2e": {"value": nodes_reads / (e2e_ms * 1e-3), "unit": "node*reads/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": world * (432 + 4 * 336 * world),
+                        "ms_per_step": e2e_ms, "span": "buffers_to_result: every rank's read slice in pinned host memory -> best nodes + tie lists on every rank"},
+                "gpu_launches": launches_all, "gpu_launches_per_step": launches_all / steps,
+                "collective_bytes_per_step_rank0": {"sent": int(sent), "received": int(recv)},
+                "same_result_as_one_gpu": same,
+                "roofline": {"bound": "hbm", "kernel": "whole place stage (one sample, all ranks)", "achieved": alg["total"] / (per * 1e-3) / 1e9, "peak": float(pk["hbm_gbs"]) * world,
+                             "unit": "GB/s", "frac": alg["total"] / (per * 1e-3) / 1e9 / (float(pk["hbm_gbs"]) * world), "traffic": None, "peak_source": pk_src},
+                "batch_mode": batch,
                 "clocks": clocks}
         print(json.dumps(line))
     dist.destroy_process_group()

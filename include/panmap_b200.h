@@ -101,6 +101,8 @@ const char* pm_last_error(void);
 int pm_abi_version(void);
 /* number of usable CUDA devices (0 when none; never fails) */
 int pm_device_count(void);
+/* kernels this library has launched in this process so far (every launch site counts itself; memsets and copies are not kernels) */
+uint64_t pm_launch_count(void);
 
 /* ---- .idx container (index_single_mode.cpp:1561-1636, main.cpp:193-236): 32-byte "PMI1" header + raw
  *      Cap'n Proto LiteIndex message, raw or as independent zstd frames (libzstd.so.1 is loaded at run time when needed). ---- */

@@ -103,9 +103,11 @@ class RefIndex:
             self.h = None
 
     def place(self, r1, r2="", out_tsv="/dev/null", threads=1, min_read_support=-1, seed_mask_fraction=0.0, trim_start=0, trim_end=0,
-              dedup=False, force_leaf=False, min_seed_quality=0):
-        """the reference placement::placeLite with CLI-default options"""
+              dedup=False, force_leaf=False, min_seed_quality=0, stage_timers=False):
+        """the reference placement::placeLite with CLI-default options.  stage_timers: also return the reference's own stage times
+        (its debug log lines, captured by the driver): stage_ms = dict(read_processing, seeding, dedup, traversal, total)"""
         o = PlaceOut()
+        lib().ref_set_stage_timers(int(bool(stage_timers)))
         lib().ref_set_min_seed_quality(int(min_seed_quality))
         k = lib().ref_place(self.h, os.fsencode(r1), os.fsencode(r2), os.fsencode(out_tsv), threads, min_read_support,
                             seed_mask_fraction, trim_start, trim_end, int(dedup), int(force_leaf), 0, C.byref(o))
@@ -122,9 +124,15 @@ class RefIndex:
         h, c = h[:o.unique_seeds], c[:o.unique_seeds]
         order = np.argsort(h, kind="stable")
         lib().ref_place_free(k)
-        return dict(best_score=np.array(o.best_score), best_index=np.array(o.best_index), tied=tied, total_reads=o.total_reads,
-                    kept=o.read_unique_seed_count, total_frequency=o.total_read_seed_frequency, magnitude=o.read_magnitude,
-                    unique_seeds=o.unique_seeds, seconds=o.seconds, table_hash=h[order], table_count=c[order])
+        out = dict(best_score=np.array(o.best_score), best_index=np.array(o.best_index), tied=tied, total_reads=o.total_reads,
+                   kept=o.read_unique_seed_count, total_frequency=o.total_read_seed_frequency, magnitude=o.read_magnitude,
+                   unique_seeds=o.unique_seeds, seconds=o.seconds, table_hash=h[order], table_count=c[order])
+        if stage_timers:
+            ms = (C.c_double * 5)()
+            lib().ref_last_stage_ms(ms)
+            lib().ref_set_stage_timers(0)
+            out["stage_ms"] = dict(zip(("read_processing", "seeding", "dedup", "traversal", "total"), [float(x) for x in ms]))
+        return out
 
     def node_metrics(self, table_hash, table_count, min_read_support=-1):
         N = self.n_nodes

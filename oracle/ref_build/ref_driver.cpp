@@ -16,6 +16,9 @@
 
 #include <chrono>
 #include <cstring>
+#include <iostream>
+#include <sstream>
+#include <cstring>
 #include <fstream>
 #include <memory>
 #include <queue>
@@ -114,6 +117,19 @@ struct RefPlaceOut {
 };
 
 // reference placement::placeLite with CLI-default params; tied index lists / seed table fetched afterwards
+// Stage timers of the reference itself: placeLite logs "Total read processing", "K-minimizer extraction" / "Seed extraction", "Read
+// deduplication" and "Tree traversal" in ms through output::debug / output::info (placement.cpp:1275,1376,1691,1701,1929), which write
+// to std::cerr when verbose.  With the timers on, ref_place turns verbose on, captures std::cerr for the duration of the call and
+// parses those lines; nothing in the reference is modified.
+int g_stageTimers = 0;
+double g_stageMs[5] = {0, 0, 0, 0, 0};   // read processing (parse + dedup + seeding), seeding alone, dedup, tree traversal, whole call
+void ref_set_stage_timers(int on) { g_stageTimers = on; }
+void ref_last_stage_ms(double* out) { for (int i = 0; i < 5; ++i) out[i] = g_stageMs[i]; }
+static double grabMs(const std::string& log, const char* key) {
+    const size_t p = log.find(key);
+    if (p == std::string::npos) return -1.0;
+    return std::atof(log.c_str() + p + std::strlen(key));
+}
 int g_minSeedQuality = 0;   // --min-seed-quality of the next ref_place calls (0 = off, the CLI default)
 void ref_set_min_seed_quality(int q) { g_minSeedQuality = q; }
 struct RefPlaceKeep { placement::PlacementResult res; };
@@ -131,9 +147,23 @@ void* ref_place(void* h, const char* r1, const char* r2, const char* outTsv, int
         tp.store_diagnostics = storeDiag != 0;
         tp.minSeedQuality = g_minSeedQuality;
         std::string o = outTsv ? outTsv : "";
+        std::ostringstream captured;
+        std::streambuf* oldBuf = nullptr;
+        const bool wasVerbose = output::config().verbose, wasPlain = output::config().plain, wasQuiet = output::config().quiet;
+        if (g_stageTimers) { output::config().verbose = true; output::config().plain = true; output::config().quiet = false; oldBuf = std::cerr.rdbuf(captured.rdbuf()); }
         auto t0 = std::chrono::steady_clock::now();
-        placement::placeLite(K->res, &L->tree, *L->rd, r1 ? r1 : "", r2 ? r2 : "", o, tp, nullptr);
+        try { placement::placeLite(K->res, &L->tree, *L->rd, r1 ? r1 : "", r2 ? r2 : "", o, tp, nullptr); }
+        catch (...) { if (oldBuf) std::cerr.rdbuf(oldBuf); output::config().verbose = wasVerbose; output::config().plain = wasPlain; output::config().quiet = wasQuiet; throw; }
         auto t1 = std::chrono::steady_clock::now();
+        if (g_stageTimers) {
+            std::cerr.rdbuf(oldBuf); output::config().verbose = wasVerbose; output::config().plain = wasPlain; output::config().quiet = wasQuiet;
+            const std::string log = captured.str();
+            g_stageMs[0] = grabMs(log, "Total read processing: ");
+            g_stageMs[1] = std::max(grabMs(log, "K-minimizer extraction: "), grabMs(log, "Seed extraction: "));
+            g_stageMs[2] = grabMs(log, "Read deduplication: ");
+            g_stageMs[3] = grabMs(log, "Tree traversal: ");
+            g_stageMs[4] = 1e3 * std::chrono::duration<double>(t1 - t0).count();
+        }
         auto& R = K->res;
         const double sc[5] = {R.bestLogRawScore, R.bestLogCosineScore, R.bestContainmentScore,
                               R.bestWeightedContainmentScore, R.bestLogContainmentScore};

@@ -71,6 +71,7 @@ def lib():
         raise PanmapError(-2, f"{p} is missing: run __graft_entry__.build() (there is no CPU fallback)")
     L = C.CDLL(p)
     L.pm_last_error.restype = C.c_char_p
+    L.pm_launch_count.restype = C.c_uint64
     L.pm_host_index_node_id.restype = C.c_char_p
     L.pm_host_index_node_id.argtypes = [C.c_void_p, C.c_uint64]
     L.pm_host_index_read.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
@@ -139,6 +140,11 @@ def _ck(rc):
     if rc < 0:
         raise PanmapError(rc, lib().pm_last_error().decode(errors="replace"))
     return rc
+
+
+def launch_count():
+    """kernel launches of the library in this process so far"""
+    return int(lib().pm_launch_count())
 
 
 def device_count():

@@ -4,6 +4,7 @@
 #include "pm_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -18,6 +19,10 @@ using namespace pm::host;
 namespace pm {
 namespace host {
 
+static std::atomic<unsigned long long> g_launches{0};
+}  // namespace host
+void noteLaunch() { host::g_launches.fetch_add(1, std::memory_order_relaxed); }
+namespace host {
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int deviceCountNoThrow() {
@@ -443,6 +448,7 @@ extern "C" {
 const char* pm_last_error(void) { return g_err.c_str(); }
 int pm_abi_version(void) { return PM_ABI_VERSION; }
 int pm_device_count(void) { return deviceCountNoThrow(); }
+uint64_t pm_launch_count(void) { return pm::host::g_launches.load(std::memory_order_relaxed); }
 
 int pm_host_index_read(const char* path, pm_host_index** out) {
     if (!path || !out) return fail(PM_ERR_INVALID, "null argument");

@@ -94,8 +94,8 @@ void launchPackReads(const char* reads, const u64* off, const u64* packedOff, co
                      uint4* packed, cudaStream_t st, const u64* endOff) {
     if (nChunks == 0) return;
     const unsigned grid = (unsigned)((nChunks + 255) / 256);
-    if (endOff) pack_reads<true><<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, endOff);
-    else pack_reads<false><<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, nullptr);
+    if (endOff) noteLaunch(), pack_reads<true><<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, endOff);
+    else noteLaunch(), pack_reads<false><<<grid, 256, 0, st>>>(reads, off, packedOff, blockFirst, nReads, gBase, nChunks, packed, nullptr);
 }
 
 // Chunk offsets of a slice of reads on the device: packedOff[i] = gBase + sum_{j<i} ceil(len_j / 32), i = 0..n (n+1 entries), so
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(1024) chunk_offsets_tiled(const u64* __restric
 }
 void launchChunkOffsets(const u64* off, u64 n, u64 gBase, u64* tileSum, u64* packedOff, cudaStream_t st) {
     const unsigned tiles = (unsigned)(n / kOffTile + 1);   // +1: the tile that holds entry n
-    chunk_tile_sums<<<tiles, 1024, 0, st>>>(off, n, tileSum);
-    chunk_offsets_tiled<<<tiles, 1024, 0, st>>>(off, n, gBase, tileSum, packedOff);
+    noteLaunch(), chunk_tile_sums<<<tiles, 1024, 0, st>>>(off, n, tileSum);
+    noteLaunch(), chunk_offsets_tiled<<<tiles, 1024, 0, st>>>(off, n, gBase, tileSum, packedOff);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) hpc_compress(char* __restrict__ reads, co
 void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cudaStream_t st, char* quals) {
     if (nReads == 0) return;
     u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
-    hpc_compress<<<(unsigned)g, 256, 0, st>>>(reads, off, nReads, endOff, quals);
+    noteLaunch(), hpc_compress<<<(unsigned)g, 256, 0, st>>>(reads, off, nReads, endOff, quals);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -231,7 +231,7 @@ void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsign
                  const u64* endOff) {
     if (rEnd <= rBegin) return;
     u64 g = (rEnd - rBegin + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
-    dedup_mark<<<(unsigned)g, 256, 0, st>>>(reads, off, rBegin, rEnd, slots, mask, dup, endOff);
+    noteLaunch(), dedup_mark<<<(unsigned)g, 256, 0, st>>>(reads, off, rBegin, rEnd, slots, mask, dup, endOff);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -798,10 +798,10 @@ static void launchCountLane(const u64* synBuf, const unsigned* synCount, const u
     if (nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
         const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
         cudaFuncSetAttribute(count_seeds_lane<KT, LT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        count_seeds_lane<KT, LT, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
+        noteLaunch(), count_seeds_lane<KT, LT, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
     } else {
         u64 g = (nReads + 255) / 256; if (g > 148ull * 8) g = 148ull * 8;
-        count_seeds_lane<KT, LT, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
+        noteLaunch(), count_seeds_lane<KT, LT, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
     }
 }
 static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, TableSlot* table, u64 mask,
@@ -813,11 +813,11 @@ static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const 
     if (nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
         const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
         cudaFuncSetAttribute(count_seeds<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        count_seeds<0, 0, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+        noteLaunch(), count_seeds<0, 0, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
         return;
     }
     u64 g = (nReads + 255) / 256; if (g > 148ull * 8) g = 148ull * 8;
-    count_seeds<0, 0, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
+    noteLaunch(), count_seeds<0, 0, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);
 }
 
 template <int MODE>
@@ -826,11 +826,11 @@ static void launchSeedsFromSyncmers(const u64* synBuf, const unsigned* synCount,
     u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
     const unsigned grid = (unsigned)(g ? g : 1);
     if (k == 19 && l == 3)
-        seeds_from_syncmers<MODE, 19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
+        noteLaunch(), seeds_from_syncmers<MODE, 19, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
     else if (k == 15 && l == 3)
-        seeds_from_syncmers<MODE, 15, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
+        noteLaunch(), seeds_from_syncmers<MODE, 15, 3><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
     else
-        seeds_from_syncmers<MODE, 0, 0><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
+        noteLaunch(), seeds_from_syncmers<MODE, 0, 0><<<grid, 256, 0, st>>>(synBuf, synCount, packedOff, winOff, nReads, k, l, table, mask, acc, outHash, outCount, tableTex);
 }
 
 static size_t genericSmemBytes(const SeederParams& P) {
@@ -846,11 +846,11 @@ static void launchFast(const uint4* packed, const u64* off, const u64* packedOff
                        u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
     const size_t sm = sizeof(SeedTables) + 256 + 4 * kPairStride * sizeof(u64);
     if (reads && P.trimEnd == 0)
-        syncmers_fast<K, S, true, true><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+        noteLaunch(), syncmers_fast<K, S, true, true><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
     else if (reads)
-        syncmers_fast<K, S, true, false><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+        noteLaunch(), syncmers_fast<K, S, true, false><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
     else
-        syncmers_fast<K, S, false, false><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
+        noteLaunch(), syncmers_fast<K, S, false, false><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
 }
 // true when launchSeedTable hashes these parameters straight from the ASCII reads (no pack_reads needed beforehand)
 bool seedTableReadsAscii(const SeederParams& P) { return !P.open && P.t == 0 && P.s == 8 && (P.k == 19 || P.k == 15); }
@@ -860,7 +860,7 @@ static void launchSyncmers(const uint4* packed, const u64* off, const u64* packe
     if (!P.open && P.t == 0 && P.k == 15 && P.s == 8) return launchFast<15, 8>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads, st);
     const size_t sm = genericSmemBytes(P);
     cudaFuncSetAttribute(syncmers_generic<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
+    noteLaunch(), syncmers_generic<0><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dT, synBuf, synCount, nullptr,
                                                                      nullptr, nullptr, nullptr, dup, endOff, nullptr, 0);
 }
 // reads -> count table: syncmer lists per read, then their seeds into the table.  (Running the two as one kernel, or concurrently
@@ -882,10 +882,10 @@ void launchSeedTableQuality(const uint4* packed, const u64* off, const u64* pack
     if (nReads == 0) return;
     const size_t sm = genericSmemBytes(P);
     cudaFuncSetAttribute(syncmers_generic<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    syncmers_generic<3><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dTables, W.synBuf, W.synCount,
+    noteLaunch(), syncmers_generic<3><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nullptr, nReads, P, dTables, W.synBuf, W.synCount,
                                                                      nullptr, synPass, nullptr, nullptr, nullptr, endOff, quals, minSeedQuality * P.k);
     u64 g = (nReads + 7) / 8; if (g > 148ull * 8) g = 148ull * 8;
-    seeds_from_syncmers<0, 0, 0><<<(unsigned)(g ? g : 1), 256, 0, st>>>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table,
+    noteLaunch(), seeds_from_syncmers<0, 0, 0><<<(unsigned)(g ? g : 1), 256, 0, st>>>(W.synBuf, W.synCount, packedOff, nullptr, nReads, P.k, P.l, W.table,
                                                                          W.tableMask, W.acc, nullptr, nullptr, W.tableTex, synPass);
 }
 // mode 1: syncmer (hash, isReverse, pos) lists == seeding::rollingSyncmers(returnAll=false); mode 2: per-read seed lists
@@ -896,7 +896,7 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
     if (mode == 1) {
         const size_t sm = genericSmemBytes(P);
         cudaFuncSetAttribute(syncmers_generic<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        syncmers_generic<1><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr, nullptr,
+        noteLaunch(), syncmers_generic<1><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, winOff, nReads, P, dTables, nullptr, nullptr,
                                                                          outHash, outRev, outPos, outCount, nullptr, nullptr, nullptr, 0);
     } else {
         launchSyncmers(packed, off, packedOff, nReads, P, dTables, synBuf, synCount, nullptr, nullptr, st);
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(256) table_clear(TableSlot* table, u64 cap) {
     uint4* t = reinterpret_cast<uint4*>(table);
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) t[i] = e;
 }
-void launchTableClear(WorkspaceView W, cudaStream_t st) { table_clear<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W.table, W.tableCap); }
+void launchTableClear(WorkspaceView W, cudaStream_t st) { noteLaunch(), table_clear<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W.table, W.tableCap); }
 
 __global__ void __launch_bounds__(256) table_import(TableSlot* table, u64 mask, SampleAcc* acc, const u64* __restrict__ hash,
                                                     const long long* __restrict__ count, u64 n) {
@@ -921,7 +921,7 @@ __global__ void __launch_bounds__(256) table_import(TableSlot* table, u64 mask, 
 }
 void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st) {
     if (!n) return;
-    table_import<<<streamGrid(n, 1), 256, 0, st>>>(W.table, W.tableMask, W.acc, hash, count, n);
+    noteLaunch(), table_import<<<streamGrid(n, 1), 256, 0, st>>>(W.table, W.tableMask, W.acc, hash, count, n);
 }
 
 __global__ void __launch_bounds__(256) table_export(const TableSlot* __restrict__ table, u64 cap, const SampleAcc* acc, u64* outHash,
@@ -940,7 +940,7 @@ __global__ void __launch_bounds__(256) table_export(const TableSlot* __restrict_
     }
 }
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st) {
-    table_export<<<streamGrid(W.tableCap, 2), 256, 0, st>>>(W.table, W.tableCap, W.acc, hash, count, counter, cap);
+    noteLaunch(), table_export<<<streamGrid(W.tableCap, 2), 256, 0, st>>>(W.table, W.tableCap, W.acc, hash, count, counter, cap);
 }
 
 // Same-address global atomics are serviced one at a time by the L2 (a few ns each), so the passes below never let more than one
@@ -1069,7 +1069,7 @@ static u64 maskTopSeeds(WorkspaceView W, double frac, unsigned nScanParts, unsig
     auto query = [&](u32 c, u64 h, u64& above, u64& tied) {
         unsigned long long r[2];
         cudaMemsetAsync(scratch, 0, sizeof(r), st);
-        mask_count<<<grid, 256, 0, st>>>(W, c, h, scratch);
+        noteLaunch(), mask_count<<<grid, 256, 0, st>>>(W, c, h, scratch);
         cudaMemcpyAsync(r, scratch, sizeof(r), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
         above = r[0]; tied = r[1];
@@ -1094,7 +1094,7 @@ static u64 maskTopSeeds(WorkspaceView W, double frac, unsigned nScanParts, unsig
         }
         hStar = hl;
     }
-    mask_apply<<<grid, 256, 0, st>>>(W, cStar, hStar, nScanParts);
+    noteLaunch(), mask_apply<<<grid, 256, 0, st>>>(W, cStar, hStar, nScanParts);
     return drop;
 }
 
@@ -1262,15 +1262,15 @@ void launchTableScan(WorkspaceView W, const u64* homo, int nSM, unsigned* nParts
     cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
     const u64 nBlocks = (W.tableCap + kScanSlots - 1) / kScanSlots;
     const unsigned g1 = (unsigned)std::min<u64>(std::min<u64>(nBlocks ? nBlocks : 1, (u64)nSM * 4), kMaxPartials - 1);
-    table_scan<<<g1, 256, 0, st>>>(W, homo);
+    noteLaunch(), table_scan<<<g1, 256, 0, st>>>(W, homo);
     *nPartsOut = g1;
 }
 void launchRootAndScalars(DevIndexView I, WorkspaceView W, PlaceOpts O, unsigned nFinParts, cudaStream_t st) {
     if (I.hasRoot && I.rootDCount) {
         u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
-        root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);
+        noteLaunch(), root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);
     }
-    finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport, nFinParts);
+    noteLaunch(), finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport, nFinParts);
 }
 void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st,
                     double seedMaskFraction, unsigned long long* maskScratch) {
@@ -1279,7 +1279,7 @@ void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* hom
     if (seedMaskFraction > 0.0) { maskTopSeeds(W, seedMaskFraction, g1, maskScratch, st); ++g1; }   // + one partial of corrections
     // sized from the previous sample's entry count (the kernel grid-strides, so any grid is correct)
     u64 g2 = (expectedEntries + 255) / 256; if (g2 < 1) g2 = 1; if (g2 > (u64)nSM * 4) g2 = (u64)nSM * 4; if (g2 > kMaxPartials) g2 = kMaxPartials;
-    entries_finalize<<<(unsigned)g2, 256, 0, st>>>(I, W, O.minReadSupport, g1);
+    noteLaunch(), entries_finalize<<<(unsigned)g2, 256, 0, st>>>(I, W, O.minReadSupport, g1);
     launchRootAndScalars(I, W, O, (unsigned)g2, st);
 }
 
@@ -1294,7 +1294,7 @@ __global__ void __launch_bounds__(256) reset_sample(DevIndexView I, WorkspaceVie
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < I.nBoundary; i += gridDim.x * blockDim.x)
         *reinterpret_cast<uint4*>(W.segRec + I.boundarySegs[i]) = make_uint4(0u, 0u, 0u, 0u);
 }
-void launchResetSample(DevIndexView I, WorkspaceView W, cudaStream_t st) { reset_sample<<<148 * 4, 256, 0, st>>>(I, W); }
+void launchResetSample(DevIndexView I, WorkspaceView W, cudaStream_t st) { noteLaunch(), reset_sample<<<148 * 4, 256, 0, st>>>(I, W); }
 
 // ------------------------------------------------------------------------------------------------------
 // K1 node_deltas: one pass over the packed delta words (4 B per delta), no block barriers.
@@ -1451,7 +1451,7 @@ void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st) {
     const u64 grid = ((I.nDeltaChunks + per - 1) / per + wpb - 1) / wpb;
     const size_t sm = (size_t)kHotIds * sizeof(long long);
     cudaFuncSetAttribute(node_deltas, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);   // per device: set on every launch (cheap)
-    node_deltas<<<(unsigned)grid, kK1Threads, sm, st>>>(I, W, per);
+    noteLaunch(), node_deltas<<<(unsigned)grid, kK1Threads, sm, st>>>(I, W, per);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1534,8 +1534,8 @@ void launchGeneral(DevIndexView I, WorkspaceView W, cudaStream_t st) {
     if (I.nGenNodes == 0) return;
     cudaMemsetAsync(W.genRec, 0, (size_t)I.nGenNodes * kGenWords * sizeof(u64), st);
     unsigned g = (I.nGenDeltas + 255) / 256; if (g > 148 * 8) g = 148 * 8;
-    gen_deltas<<<g, 256, 0, st>>>(I, W);
-    gen_prefix<<<1, 256, 0, st>>>(I, W);
+    noteLaunch(), gen_deltas<<<g, 256, 0, st>>>(I, W);
+    noteLaunch(), gen_prefix<<<1, 256, 0, st>>>(I, W);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1707,7 +1707,7 @@ __global__ void __launch_bounds__(256, 4) prefix_scores(DevIndexView I, Workspac
 }
 void launchPrefixScores(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st) {
     if (I.nK2Tiles == 0) return;
-    prefix_scores<<<I.nK2Tiles, 256, 0, st>>>(I, W, O);
+    noteLaunch(), prefix_scores<<<I.nK2Tiles, 256, 0, st>>>(I, W, O);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1839,7 +1839,7 @@ __global__ void __launch_bounds__(256) chain_select(WorkspaceView W, const u32* 
         W.sel[m] = s;
     }
 }
-void launchChain(WorkspaceView W, const u32* recCountOverride, cudaStream_t st) { chain_select<<<5, 256, 0, st>>>(W, recCountOverride); }
+void launchChain(WorkspaceView W, const u32* recCountOverride, cudaStream_t st) { noteLaunch(), chain_select<<<5, 256, 0, st>>>(W, recCountOverride); }
 
 __global__ void __launch_bounds__(256) collect_ties(DevIndexView I, WorkspaceView W, const double* __restrict__ bfsScores) {
     const int m = blockIdx.y;
@@ -1867,12 +1867,12 @@ static double* bfsScoresOf(const DevIndexView& I, const WorkspaceView& W) { retu
 void launchRecords(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st) {
     if (I.nBfsBlocks == 0) return;
     double* bs = bfsScoresOf(I, W);
-    bfs_gather<<<I.nBfsBlocks, 256, 0, st>>>(I, W, O, bs);
-    bfs_records<<<dim3(I.nBfsBlocks, 5), 256, 0, st>>>(I, W, bs);
+    noteLaunch(), bfs_gather<<<I.nBfsBlocks, 256, 0, st>>>(I, W, O, bs);
+    noteLaunch(), bfs_records<<<dim3(I.nBfsBlocks, 5), 256, 0, st>>>(I, W, bs);
 }
 void launchTies(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st) {
     if (I.nBfsBlocks == 0) return;
-    collect_ties<<<dim3(I.nBfsBlocks, 5), 256, 0, st>>>(I, W, bfsScoresOf(I, W));
+    noteLaunch(), collect_ties<<<dim3(I.nBfsBlocks, 5), 256, 0, st>>>(I, W, bfsScoresOf(I, W));
 }
 
 }  // namespace pm

@@ -142,6 +142,9 @@ struct PlaceOpts {
     int wantMetrics;
 };
 
+// every kernel launch of the library passes through here (pm_launch_count() reports the total: the bench's "gpu_launches")
+void noteLaunch();
+
 // launches (all asynchronous on `st`)
 // endOff (optional, everywhere below): end of read r when it is shorter than off[r+1] - off[r] (homopolymer-compressed in place)
 void launchPackReads(const char* reads, const u64* off, const u64* packedOff, const u32* blockFirst, u64 nReads, u64 gBase, u64 nChunks,

@@ -93,8 +93,8 @@ void launchPartitionExport(WorkspaceView W, u32 nRanks, u32 capPair, uint4* xSen
     for (u32 p = 0; p < nRanks; ++p) cudaMemsetAsync(xSend + (size_t)p * ((size_t)capPair + 1), 0, sizeof(uint4), st);
     const u64 nTiles = (W.tableCap + kExpSlots - 1) / kExpSlots;
     const unsigned grid = (unsigned)std::min<u64>(nTiles ? nTiles : 1, 148ull * 4);
-    partition_export<<<grid, 256, 0, st>>>(W, nRanks, capPair, xSend, maxPairCount);
-    partition_export_finish<<<1, 32, 0, st>>>(W, nRanks, capPair, xSend, maxPairCount);
+    noteLaunch(), partition_export<<<grid, 256, 0, st>>>(W, nRanks, capPair, xSend, maxPairCount);
+    noteLaunch(), partition_export_finish<<<1, 32, 0, st>>>(W, nRanks, capPair, xSend, maxPairCount);
 }
 
 // received segments -> the partition table
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) partition_import(WorkspaceView W, const u
     }
 }
 void launchPartitionImport(WorkspaceView W, const uint4* xRecv, u32 nRanks, u32 capPair, cudaStream_t st) {
-    partition_import<<<streamGrid((u64)nRanks * capPair, 2), 256, 0, st>>>(W, xRecv, nRanks, capPair);
+    noteLaunch(), partition_import<<<streamGrid((u64)nRanks * capPair, 2), 256, 0, st>>>(W, xRecv, nRanks, capPair);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -198,8 +198,8 @@ void launchPartitionFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const
     unsigned nParts = 0;
     launchTableScan(W, homo, nSM, &nParts, st);
     cudaMemsetAsync(gSend, 0, sizeof(GHeader), st);
-    partition_finalize<<<(unsigned)nSM * 2, 256, 0, st>>>(I, W, O.minReadSupport, nParts, gSend, capG, nLocalReads, maxPairCount, localEntriesHint);
-    partition_finalize_finish<<<1, 32, 0, st>>>(W, gSend, capG);
+    noteLaunch(), partition_finalize<<<(unsigned)nSM * 2, 256, 0, st>>>(I, W, O.minReadSupport, nParts, gSend, capG, nLocalReads, maxPairCount, localEntriesHint);
+    noteLaunch(), partition_finalize_finish<<<1, 32, 0, st>>>(W, gSend, capG);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) gathered_finalize(DevIndexView I, Workspa
 }
 void launchGatheredFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const uint2* gRecv, u32 nRanks, u32 capG, int nSM, cudaStream_t st) {
     u64 g = ((u64)nRanks * capG + 255) / 256; if (g < 1) g = 1; if (g > (u64)nSM * 4) g = (u64)nSM * 4; if (g > kMaxPartials) g = kMaxPartials;
-    gathered_finalize<<<(unsigned)g, 256, 0, st>>>(I, W, O.minReadSupport, gRecv, nRanks, capG);
+    noteLaunch(), gathered_finalize<<<(unsigned)g, 256, 0, st>>>(I, W, O.minReadSupport, gRecv, nRanks, capG);
     launchRootAndScalars(I, W, O, (unsigned)g, st);
 }
 // after the sample: clear exactly the ell entries it set, and the segment records that are combined with atomics
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(256) reset_gathered(DevIndexView I, WorkspaceV
         *reinterpret_cast<uint4*>(W.segRec + I.boundarySegs[i]) = make_uint4(0u, 0u, 0u, 0u);
 }
 void launchResetGathered(DevIndexView I, WorkspaceView W, const uint2* gRecv, u32 nRanks, u32 capG, cudaStream_t st) {
-    reset_gathered<<<148 * 4, 256, 0, st>>>(I, W, gRecv, nRanks, capG);
+    noteLaunch(), reset_gathered<<<148 * 4, 256, 0, st>>>(I, W, gRecv, nRanks, capG);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -297,8 +297,8 @@ __global__ void records_pack_finish(WorkspaceView W, uint4* rSend) {
     if (threadIdx.x == 0 && blockIdx.x == 0) reinterpret_cast<RHeader*>(rSend)->flags = (u32)W.acc->overflow;
 }
 void launchRecordsPack(WorkspaceView W, uint4* rSend, u32 recX, cudaStream_t st) {
-    records_pack<<<5, 128, 0, st>>>(W, rSend, recX);
-    records_pack_finish<<<1, 32, 0, st>>>(W, rSend);
+    noteLaunch(), records_pack<<<5, 128, 0, st>>>(W, rSend, recX);
+    noteLaunch(), records_pack_finish<<<1, 32, 0, st>>>(W, rSend);
 }
 
 // the tolerance chain (placement.cpp:355-371) over the records of all ranks; block m = metric m.  Records of a rank are in no
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) chain_gathered(WorkspaceView W, const uin
         W.sel[m] = s;
     }
 }
-void launchChainGathered(WorkspaceView W, const uint4* rRecv, u32 nRanks, u32 recX, cudaStream_t st) { chain_gathered<<<5, 256, 0, st>>>(W, rRecv, nRanks, recX); }
+void launchChainGathered(WorkspaceView W, const uint4* rRecv, u32 nRanks, u32 recX, cudaStream_t st) { noteLaunch(), chain_gathered<<<5, 256, 0, st>>>(W, rRecv, nRanks, recX); }
 
 __global__ void __launch_bounds__(64) ties_pack(WorkspaceView W, u32* __restrict__ tSend, const uint2* __restrict__ gSend, const u32* __restrict__ exportInfo) {
     THeader* hdr = reinterpret_cast<THeader*>(tSend);
@@ -368,13 +368,13 @@ __global__ void __launch_bounds__(64) ties_pack(WorkspaceView W, u32* __restrict
         for (unsigned i = threadIdx.x; i < n; i += blockDim.x) heads[m * kTieHead + i] = W.tieHead[m * kTieHead + i];
     }
 }
-void launchTiesPack(WorkspaceView W, u32* tSend, const uint2* gSend, const u32* exportInfo, cudaStream_t st) { ties_pack<<<1, 64, 0, st>>>(W, tSend, gSend, exportInfo); }
+void launchTiesPack(WorkspaceView W, u32* tSend, const uint2* gSend, const u32* exportInfo, cudaStream_t st) { noteLaunch(), ties_pack<<<1, 64, 0, st>>>(W, tSend, gSend, exportInfo); }
 // full local tie lists into a [5][capT] block (slow path: some rank has more than kTieHead ties)
 __global__ void __launch_bounds__(256) ties_full_pack(WorkspaceView W, u32* __restrict__ out, u32 capT) {
     const int m = blockIdx.y;
     const unsigned n = min(min(W.acc->tieCount[m], W.tieCap), capT);
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[(size_t)m * capT + i] = W.tieNode[(size_t)m * W.tieCap + i];
 }
-void launchTiesFullPack(WorkspaceView W, u32* out, u32 capT, cudaStream_t st) { ties_full_pack<<<dim3(64, 5), 256, 0, st>>>(W, out, capT); }
+void launchTiesFullPack(WorkspaceView W, u32* out, u32 capT, cudaStream_t st) { noteLaunch(), ties_full_pack<<<dim3(64, 5), 256, 0, st>>>(W, out, capT); }
 
 }  // namespace pm

@@ -31,7 +31,7 @@ def _check(comms, res, exp, n_nodes):
     assert H.relerr(res.raw.read_magnitude, exp["magnitude"]).max() < RTOL
     assert H.relerr(res.raw.log_containment_denominator, exp["log_sum"]).max() < RTOL
     assert H.relerr(res.raw.weighted_containment_denominator, exp["wc_denominator"]).max() < RTOL
-    if "scores" in exp:
+    if exp.get("scores") is not None:
         sc = np.zeros((n_nodes, 5))
         covered = 0
         for c in comms:                                   # every rank holds the scores of its own node range
