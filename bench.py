@@ -289,8 +289,25 @@ def main():
     e2e_value = nodes_reads * args.steps / e2e_wall
     h2d = nbytes + 8 * (w["n_reads"] + 1)            # reads + offsets (the chunk offsets are rebuilt on the device)
     d2h = 432 + 4 * int(sum(res.raw.tied_count))     # accumulators/scalars/selection block + tie lists
-    L.pm_host_free(hp_reads); L.pm_host_free(hp_off)
-    spans = {"buffers_to_result_ms": 1e3 * e2e_wall / args.steps}
+    # the same with the reads as 4-bit codes in pinned memory (what the packing FASTQ parser of the host shim emits): half the PCIe bytes
+    t0 = time.perf_counter()
+    packed = pm.host_pack_reads(S.reads, S.read_offsets)
+    pack_ms = 1e3 * (time.perf_counter() - t0)
+    hp_packed = pinned_copy(L, packed)
+    for _ in range(3):
+        ws.place_packed_raw(hp_packed, hp_off, w["n_reads"], params)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r3 = ws.place_packed_raw(hp_packed, hp_off, w["n_reads"], params)
+    e2ep_wall = time.perf_counter() - t0
+    rp = ws.place_packed(packed, S.read_offsets, params)
+    e2e_packed = {"value": nodes_reads * args.steps / e2ep_wall, "unit": "node*reads/s", "ms_per_step": 1e3 * e2ep_wall / args.steps,
+                  "h2d_bytes_per_step": int(packed.nbytes) + 8 * (w["n_reads"] + 1), "d2h_bytes_per_step": d2h,
+                  "host_pack_ms_not_in_span": pack_ms,
+                  "same_result_as_ascii": bool(all(rp.best_index[m] == res.best_index[m] and rp.best_score[m] == res.best_score[m] and np.array_equal(rp.tied[m], res.tied[m]) for m in pm.METRICS)),
+                  "span": "buffers_to_result with the reads as 4-bit codes (pm_place_packed): 16-byte chunks of 32 bases in pinned host memory -> result"}
+    L.pm_host_free(hp_reads); L.pm_host_free(hp_off); L.pm_host_free(hp_packed)
+    spans = {"buffers_to_result_ms": 1e3 * e2e_wall / args.steps, "packed_buffers_to_result_ms": 1e3 * e2ep_wall / args.steps}
 
     # ---- roofline ----
     # dominant kernel of the step = the syncmer kernel (CUDA events of the library around that launch alone); it is bound by the
@@ -321,6 +338,7 @@ def main():
         "stage_ms": {n: float(stage[i]) for i, n in enumerate(names)},
         "e2e": {"value": e2e_value, "unit": "node*reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall / args.steps,
                 "device_ms_per_step": e2e_dev / args.steps, "span": "buffers_to_result: ASCII reads + offsets in pinned host memory -> best nodes + tie lists on the host"},
+        "e2e_packed": e2e_packed,
         "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "kernel_ms": per_kernel,
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -435,7 +453,16 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
     for _ in range(steps):
         comm.place_sharded_raw(hp_reads, hp_off, off.size - 1, params)
     e2e_ms = maxf((time.perf_counter() - t0) * 1e3 / steps)
-    L.pm_host_free(hp_reads); L.pm_host_free(hp_off)
+    packed = pm.host_pack_reads(reads, off)
+    hp_packed = pinned_copy(L, packed)
+    for _ in range(3):
+        comm.place_sharded_packed_raw(hp_packed, hp_off, off.size - 1, params)
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        comm.place_sharded_packed_raw(hp_packed, hp_off, off.size - 1, params)
+    e2ep_ms = maxf((time.perf_counter() - t0) * 1e3 / steps)
+    L.pm_host_free(hp_reads); L.pm_host_free(hp_off); L.pm_host_free(hp_packed)
     h2d_local = int(reads.nbytes) + 8 * int(off.size)
     t = torch.tensor([h2d_local, launches], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -484,6 +511,8 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
                 "stage_ms": {nm: stage_max[i] for i, nm in enumerate(names[:7])},
                 "e2e": {"value": nodes_reads / (e2e_ms * 1e-3), "unit": "node*reads/s", "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": world * (432 + 4 * 336 * world),
                         "ms_per_step": e2e_ms, "span": "buffers_to_result: every rank's read slice in pinned host memory -> best nodes + tie lists on every rank"},
+                "e2e_packed": {"value": nodes_reads / (e2ep_ms * 1e-3), "unit": "node*reads/s", "ms_per_step": e2ep_ms,
+                               "span": "the same with every rank's slice as 4-bit codes (pm_place_sharded_packed)"},
                 "gpu_launches": launches_all, "gpu_launches_per_step": launches_all / steps,
                 "collective_bytes_per_step_rank0": {"sent": int(sent), "received": int(recv)},
                 "same_result_as_one_gpu": same,

@@ -133,6 +133,18 @@ void pm_workspace_destroy(pm_workspace* ws);
  *      Buffers are HOST memory; the call uploads them, runs every stage on the GPU and returns the result. */
 int pm_place(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads,
              const pm_place_params* params, pm_place_result* result);
+/* The same for reads that already are 4-bit base codes (what a FASTQ parser can emit directly: panmap_b200/host/placement.cpp does, and
+ * pm_pack_reads converts ASCII on the host): half the bytes cross PCIe and the device never sees ASCII.
+ *   code: A 0, C 1, G 2, T 3 (either case), anything else 4 (ambiguous: seeding.hpp:86-112 gives every other byte hash 0)
+ *   layout: 16-byte chunks of 32 bases, base j of a chunk in bits [4j, 4j+4) of the chunk read as a little-endian 128-bit word; slots past
+ *   the end of a read hold 4; every read starts on a chunk boundary: read r occupies chunks [c_r, c_r + ceil(len_r / 32)), c_r = sum of the
+ *   chunk counts before it.  read_offsets are the BASE offsets as for pm_place (lengths = differences).  `packed` must be 16-byte aligned.
+ * Needs the raw strings and therefore returns PM_ERR_UNSUPPORTED: dedup_reads, hpc indexes, min_seed_quality. */
+int pm_place_packed(pm_workspace* ws, const void* packed, const uint64_t* read_offsets, uint64_t n_reads, const pm_place_params* params,
+                    pm_place_result* result);
+/* ASCII -> the layout above on the host with up to `threads` threads (0 = all cores); packed_out holds pm_packed_chunks() * 16 bytes */
+uint64_t pm_packed_chunks(const uint64_t* read_offsets, uint64_t n_reads);
+int pm_pack_reads(const char* reads, const uint64_t* read_offsets, uint64_t n_reads, void* packed_out, int threads);
 /* The same with per-base qualities for --min-seed-quality (placement.cpp:1179-1240, 1388-1533): quals has one Phred+33 byte per base at the
  * reads' offsets (a FASTQ record's quality line; for records without one the reference substitutes 'I', placement.cpp:211).
  * With params->min_seed_quality <= 0 the qualities are ignored and this is pm_place.  On this path the reference does not deduplicate
@@ -218,6 +230,9 @@ void pm_comm_destroy(pm_comm* c);
 int pm_place_sharded(pm_comm* c, const char* reads, const uint64_t* read_offsets, uint64_t n_reads_local, const pm_place_params* params,
                      pm_place_result* result);
 int pm_place_sharded_resident(pm_comm* c, const pm_place_params* params, pm_place_result* result);
+/* the rank's slice as 4-bit codes (layout and restrictions of pm_place_packed) */
+int pm_place_sharded_packed(pm_comm* c, const void* packed, const uint64_t* read_offsets, uint64_t n_reads_local, const pm_place_params* params,
+                            pm_place_result* result);
 /* local transport: the whole sample in, cut into n contiguous slices of reads internally; the result (and pm_get_tied) is available on every
  * rank's workspace, `result` receives rank 0's. _resident: slice r was laid out by pm_reads_upload on workspace r. */
 int pm_place_multi(pm_comm* const* comms, int n_ranks, const char* reads, const uint64_t* read_offsets, uint64_t n_reads,

@@ -89,6 +89,10 @@ def lib():
     L.pm_workspace_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.pm_workspace_destroy.argtypes = [C.c_void_p]
     L.pm_place.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_place_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_packed_chunks.restype = C.c_uint64
+    L.pm_packed_chunks.argtypes = [C.c_void_p, C.c_uint64]
+    L.pm_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
     L.pm_place_quality.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
     L.pm_reads_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_place_resident.argtypes = [C.c_void_p, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
@@ -121,6 +125,7 @@ def lib():
     L.pm_comm_create_local.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
     L.pm_comm_destroy.argtypes = [C.c_void_p]
     L.pm_place_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
+    L.pm_place_sharded_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
     L.pm_place_sharded_resident.argtypes = [C.c_void_p, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
     L.pm_place_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
     L.pm_place_multi_resident.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
@@ -159,6 +164,19 @@ def pack_reads(reads):
         off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
     buf = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, dtype=np.uint8)
     return buf, off
+
+
+def host_pack_reads(reads, offsets, threads=0):
+    """ASCII reads -> the 4-bit layout of pm_place_packed (pm_pack_reads on the host); returns a 16-byte aligned uint8 array"""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = offsets.size - 1
+    chunks = int(lib().pm_packed_chunks(offsets.ctypes.data_as(C.c_void_p), n))
+    raw = np.zeros(chunks * 16 + 16, dtype=np.uint8)
+    shift = (-raw.ctypes.data) % 16
+    out = raw[shift:shift + chunks * 16]
+    _ck(lib().pm_pack_reads(reads.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), n, out.ctypes.data_as(C.c_void_p), threads))
+    return out
 
 
 def _ptr(a):
@@ -321,6 +339,21 @@ class Workspace:
         _ck(lib().pm_place_quality(self._h, _ptr(reads), _ptr(quals), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params),
                                    C.byref(res)))
         return self._finish(res)
+
+    def place_packed(self, packed, offsets, params=None):
+        """reads as 4-bit codes (host_pack_reads / a packing parser): uint8 array of 16-byte chunks, 16-byte aligned"""
+        params = params or PlaceParams()
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        if packed.ctypes.data % 16:
+            raise ValueError("packed reads must be 16-byte aligned")
+        res = PlaceResult()
+        _ck(lib().pm_place_packed(self._h, packed.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1, C.byref(params), C.byref(res)))
+        return self._finish(res)
+
+    def place_packed_raw(self, packed_ptr, offsets_ptr, n_reads, params):
+        res = PlaceResult()
+        _ck(lib().pm_place_packed(self._h, packed_ptr, offsets_ptr, n_reads, C.byref(params), C.byref(res)))
+        return res
 
     def place_raw(self, reads_ptr, offsets_ptr, n_reads, params):
         """host pointers (e.g. pinned buffers); returns the PlaceResult struct only"""
@@ -495,6 +528,11 @@ class Comm:
     def place_sharded_raw(self, reads_ptr, offsets_ptr, n_reads, params):
         res = PlaceResult()
         _ck(lib().pm_place_sharded(self._h, reads_ptr, offsets_ptr, n_reads, C.byref(params), C.byref(res)))
+        return res
+
+    def place_sharded_packed_raw(self, packed_ptr, offsets_ptr, n_reads, params):
+        res = PlaceResult()
+        _ck(lib().pm_place_sharded_packed(self._h, packed_ptr, offsets_ptr, n_reads, C.byref(params), C.byref(res)))
         return res
 
     def place_sharded_resident(self, params=None, full=True):

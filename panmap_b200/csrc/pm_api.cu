@@ -33,6 +33,17 @@ int deviceCountNoThrow() {
 
 
 void setDevice(int dev) { CK(cudaSetDevice(dev)); }
+static std::mutex g_wsMutex;
+static std::vector<const pm_workspace*> g_wsLive;
+bool workspaceAlive(const pm_workspace* W) {
+    std::lock_guard<std::mutex> lk(g_wsMutex);
+    return std::find(g_wsLive.begin(), g_wsLive.end(), W) != g_wsLive.end();
+}
+static void workspaceRegister(const pm_workspace* W, bool add) {
+    std::lock_guard<std::mutex> lk(g_wsMutex);
+    if (add) g_wsLive.push_back(W);
+    else g_wsLive.erase(std::remove(g_wsLive.begin(), g_wsLive.end(), W), g_wsLive.end());
+}
 
 static void buildViews(pm_index* I) {
     FlatIndex& F = I->F;
@@ -257,6 +268,49 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false; W->hpcDone = false;
 }
 
+// The same pipeline for reads that arrive as 4-bit codes (pm_place_packed): half the bytes on the wire, and the syncmer kernel takes the
+// codes as they are -- no ASCII on the device at all.  hPacked: 16-byte chunks of 32 bases, read r at chunk sum_{j<r} ceil(len_j / 32).
+void uploadAndSeedPipelinedPacked(pm_workspace* W, const uint4* hPacked, const uint64_t* off, u64 n, const pm_place_params& prm) {
+    pm_index* I = W->idx;
+    const int k = I->F.sp.k;
+    if (n && off[0] != 0) throw std::runtime_error("read_offsets[0] must be 0");
+    if (I->F.sp.hpc) throw Unsupported("packed reads on an hpc index: homopolymer compression works on the ASCII reads (use pm_place)");
+    if (prm.dedup_reads) throw Unsupported("dedup_reads compares the raw read strings, which 4-bit codes do not preserve (use pm_place)");
+    const u64 total = n ? off[n] : 0;
+    static const double kCut[11] = {0.0, 0.03, 0.09, 0.21, 0.40, 0.58, 0.73, 0.84, 0.91, 0.96, 1.0};
+    const int nSlices = n >= (1u << 16) ? 10 : 1;
+    W->nReads = n; W->totalBases = total;
+    W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
+    W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1);
+    W->tileSum.ensure(n / 4096 + 2);
+    if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, (total > (u64)k * n ? total - (u64)(k - 1) * n : 0) / 4));
+    refreshView(W);
+    const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
+    CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
+    launchTableClear(W->view, W->st);
+    u64 chunkAcc = 0, win = 0;
+    for (int sl = 0; sl < nSlices; ++sl) {
+        const u64 r0 = nSlices == 1 ? 0 : (u64)((double)n * kCut[sl]), r1 = nSlices == 1 || sl + 1 == nSlices ? n : (u64)((double)n * kCut[sl + 1]);
+        if (r1 == r0) continue;
+        const u64 gBase = chunkAcc;
+        for (u64 i = r0; i < r1; ++i) {
+            if (off[i + 1] < off[i]) throw std::runtime_error("read offsets not monotone");
+            const u64 L = off[i + 1] - off[i];
+            if (L > 0x7FFFFFF0ull) throw std::runtime_error("read longer than 2^31 bases");
+            chunkAcc += (L + 31) >> 5;
+            if (L >= (u64)k) win += L - (u64)k + 1;
+        }
+        const u64 nCh = chunkAcc - gBase;
+        if (nCh) CK(cudaMemcpyAsync(W->packed.p + gBase, hPacked + gBase, nCh * sizeof(uint4), cudaMemcpyHostToDevice, W->stCopy));
+        CK(cudaMemcpyAsync(W->off.p + r0, off + r0, (r1 - r0 + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->stCopy));
+        CK(cudaEventRecord(W->evCopy[sl], W->stCopy));
+        CK(cudaStreamWaitEvent(W->st, W->evCopy[sl], 0));
+        launchChunkOffsets(W->off.p + r0, r1 - r0, gBase, W->tileSum.p, W->packedOff.p + r0, W->st);
+        launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, nullptr, nullptr, nullptr, nullptr);
+    }
+    W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false; W->hpcDone = false;
+}
+
 void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
     pm_index* I = W->idx;
     const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
@@ -387,7 +441,7 @@ void recordStageTimes(pm_workspace* W, pm_place_result* res) {
 }
 
 static int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result* res, bool inputsResident, const char* reads,
-             const uint64_t* off, u64 n) {
+             const uint64_t* off, u64 n, const uint4* packedHost = nullptr) {
     pm_index* I = W->idx;
     setDevice(I->device);
     checkParams(prm);
@@ -409,6 +463,7 @@ static int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result
         refreshView(W);
         CK(cudaEventRecord(W->ev[1], W->st));
         if (inputsResident) stageSeed(W, true, *prm);
+        else if (packedHost) uploadAndSeedPipelinedPacked(W, packedHost, off, n, *prm);
         else uploadAndSeedPipelined(W, reads, off, n, *prm);   // H2D of the slices overlaps pack + seeding of earlier slices
         CK(cudaEventRecord(W->ev[2], W->st));
         stageScore(W, *prm);
@@ -504,7 +559,7 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
     return guarded([&]() -> int {
         setDevice(idx->device);
         std::unique_ptr<pm_workspace> W(new pm_workspace());
-        W->idx = idx;
+        W->idx = idx; W->device = idx->device;
         CK(cudaStreamCreateWithFlags(&W->st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&W->stCopy, cudaStreamNonBlocking));
         for (auto& e : W->ev) CK(cudaEventCreate(&e));
@@ -541,13 +596,15 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
         CK(cudaStreamSynchronize(W->st));
         refreshView(W.get());
+        workspaceRegister(W.get(), true);
         *out = W.release();
         return PM_OK;
     });
 }
 void pm_workspace_destroy(pm_workspace* ws) {
     if (!ws) return;
-    cudaSetDevice(ws->idx->device);
+    workspaceRegister(ws, false);
+    cudaSetDevice(ws->device);
     if (ws->st) { cudaStreamSynchronize(ws->st); cudaStreamDestroy(ws->st); }
     if (ws->stCopy) { cudaStreamSynchronize(ws->stCopy); cudaStreamDestroy(ws->stCopy); }
     if (ws->ellTex) cudaDestroyTextureObject(ws->ellTex);
@@ -562,6 +619,13 @@ int pm_place(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, 
              pm_place_result* result) {
     if (!ws || !read_offsets || (!reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");
     return guarded([&]() -> int { return runPlace(ws, params, result, false, reads, read_offsets, n_reads); });
+}
+int pm_place_packed(pm_workspace* ws, const void* packed, const uint64_t* read_offsets, uint64_t n_reads, const pm_place_params* params,
+                    pm_place_result* result) {
+    if (!ws || !read_offsets || (!packed && n_reads)) return fail(PM_ERR_INVALID, "null argument");
+    if ((reinterpret_cast<uintptr_t>(packed) & 15u) != 0) return fail(PM_ERR_INVALID, "packed reads must be 16-byte aligned");
+    if (params && params->min_seed_quality > 0) return fail(PM_ERR_UNSUPPORTED, "min_seed_quality needs the ASCII reads and qualities: pm_place_quality");
+    return guarded([&]() -> int { return runPlace(ws, params, result, false, nullptr, read_offsets, n_reads, static_cast<const uint4*>(packed)); });
 }
 int pm_place_quality(pm_workspace* ws, const char* reads, const char* quals, const uint64_t* read_offsets, uint64_t n_reads,
                      const pm_place_params* params, pm_place_result* result) {

@@ -87,6 +87,7 @@ struct pm_index {
 
 struct pm_workspace {
     pm_index* idx = nullptr;
+    int device = 0;   // == idx->device (kept here: a binding's garbage collector may destroy the index handle first)
     cudaStream_t st = nullptr, stCopy = nullptr;
     cudaEvent_t ev[9]{}, evCopy[12]{}, evK[4]{};   // evK: around pack_reads / syncmers / count_seeds of the resident path
     // inputs
@@ -133,12 +134,14 @@ namespace host {
 constexpr size_t kResultBlobBytes = sizeof(SampleAcc) + sizeof(SampleScalars) + 5 * sizeof(Selection) + 5 * kTieHead * sizeof(u32);
 
 void setDevice(int dev);
+bool workspaceAlive(const pm_workspace* W);   // false once pm_workspace_destroy ran (communicators outlive their workspace in GC'd bindings)
 void refreshView(pm_workspace* W);
 void ensureTable(pm_workspace* W, u64 wantCap);   // grows the table in use to at least wantCap slots (never shrinks it)
 PlaceOpts makeOpts(const pm_place_params& p, bool wantMetrics);
 void checkParams(const pm_place_params* p);
 void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n);
 void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* off, u64 n, const pm_place_params& prm);
+void uploadAndSeedPipelinedPacked(pm_workspace* W, const uint4* hPacked, const uint64_t* off, u64 n, const pm_place_params& prm);
 void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm);
 void stageScore(pm_workspace* W, const pm_place_params& prm);         // finalize + the three stages below
 void stageDeltasScoresRecords(pm_workspace* W, const pm_place_params& prm);   // node_deltas, prefix_scores, local prefix-maximum records

@@ -849,6 +849,8 @@ static void launchFast(const uint4* packed, const u64* off, const u64* packedOff
         noteLaunch(), syncmers_fast<K, S, true, true><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
     else if (reads)
         noteLaunch(), syncmers_fast<K, S, true, false><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+    else if (P.trimEnd == 0)   // 4-bit codes (pm_place_packed and the list utilities)
+        noteLaunch(), syncmers_fast<K, S, false, true><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
     else
         noteLaunch(), syncmers_fast<K, S, false, false><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, nullptr);
 }

@@ -69,7 +69,7 @@ NcclApi& ncclApi() {
 struct LocalGroup { std::vector<pm_comm*> members; };
 
 struct pm_comm {
-    int rank = 0, n = 1;
+    int rank = 0, n = 1, device = 0;
     pm_workspace* ws = nullptr;
     ncclComm_t nccl = nullptr;                 // NCCL transport
     std::shared_ptr<LocalGroup> grp;           // in-process transport
@@ -87,7 +87,7 @@ struct pm_comm {
     u64 nLocalReads = 0, localBases = 0;
     u64 sent = 0, received = 0;
     // per-call inputs
-    const char* hReads = nullptr; const uint64_t* hOff = nullptr; bool resident = false;
+    const char* hReads = nullptr; const uint4* hPacked = nullptr; const uint64_t* hOff = nullptr; bool resident = false;
 };
 
 namespace {
@@ -185,6 +185,7 @@ void phase0(pm_comm* c, const pm_place_params& prm) {
     refreshView(W);
     CK(cudaEventRecord(W->ev[1], W->st));
     if (c->resident) stageSeed(W, true, prm);
+    else if (c->hPacked) uploadAndSeedPipelinedPacked(W, c->hPacked, c->hOff, c->nLocalReads, prm);
     else uploadAndSeedPipelined(W, c->hReads, c->hOff, c->nLocalReads, prm);
     launchPartitionExport(W->view, (u32)c->n, c->capPair, c->xSend.p, c->exportInfo.p, W->st);
     CK(cudaEventRecord(W->ev[2], W->st));
@@ -238,6 +239,7 @@ void fitTable(pm_comm* c) {
 
 void runSharded(std::vector<pm_comm*>& cs, const pm_place_params* prm, pm_place_result* res0) {
     checkParams(prm);
+    for (pm_comm* c : cs) if (!workspaceAlive(c->ws)) throw std::runtime_error("communicator's workspace was destroyed");
     if (prm->dedup_reads) throw Unsupported("dedup_reads needs the whole sample on one GPU (duplicates across the ranks' read slices would go unseen): use pm_place");
     if (prm->seed_mask_fraction > 0.0) throw Unsupported("seed_mask_fraction needs the whole seed table on one GPU: use pm_place");
     if (prm->min_seed_quality > 0) throw Unsupported("min_seed_quality is not available for sharded samples: use pm_place_quality");
@@ -376,7 +378,7 @@ int pm_comm_create_nccl(pm_workspace* ws, const void* id, int rank, int n_ranks,
     return guarded([&]() -> int {
         setDevice(ws->idx->device);
         std::unique_ptr<pm_comm> c(new pm_comm());
-        c->rank = rank; c->n = n_ranks; c->ws = ws;
+        c->rank = rank; c->n = n_ranks; c->ws = ws; c->device = ws->device;
         ncclUniqueId uid; std::memcpy(&uid, id, sizeof(uid));
         NK(ncclApi().CommInitRank(&c->nccl, n_ranks, uid, rank));
         *out = c.release();
@@ -393,7 +395,7 @@ int pm_comm_create_local(pm_workspace* const* ws, int n_ranks, pm_comm** out) {
         for (int r = 0; r < n_ranks; ++r) {
             setDevice(ws[r]->idx->device);
             std::unique_ptr<pm_comm> c(new pm_comm());
-            c->rank = r; c->n = n_ranks; c->ws = ws[r]; c->grp = grp;
+            c->rank = r; c->n = n_ranks; c->ws = ws[r]; c->grp = grp; c->device = ws[r]->device;
             for (auto& e : c->ready) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             cs.push_back(std::move(c));
         }
@@ -412,8 +414,9 @@ int pm_comm_create_local(pm_workspace* const* ws, int n_ranks, pm_comm** out) {
 
 void pm_comm_destroy(pm_comm* c) {
     if (!c) return;
-    cudaSetDevice(c->ws->idx->device);
-    cudaStreamSynchronize(c->ws->st);
+    cudaSetDevice(c->device);
+    if (workspaceAlive(c->ws)) cudaStreamSynchronize(c->ws->st);   // a binding's garbage collector may have destroyed the workspace first
+    else cudaDeviceSynchronize();
     if (c->nccl) { try { ncclApi().CommDestroy(c->nccl); } catch (...) {} }
     for (auto& e : c->ready) if (e) cudaEventDestroy(e);
     if (c->grp) for (auto& m : c->grp->members) if (m == c) m = nullptr;
@@ -425,7 +428,20 @@ int pm_place_sharded(pm_comm* c, const char* reads, const uint64_t* read_offsets
     if (!c || !read_offsets || (!reads && n_reads_local) || !result) return fail(PM_ERR_INVALID, "null argument");
     if (!c->nccl) return fail(PM_ERR_INVALID, "pm_place_sharded needs an NCCL communicator (in-process groups: pm_place_multi)");
     return guarded([&]() -> int {
-        c->hReads = reads; c->hOff = read_offsets; c->nLocalReads = n_reads_local; c->localBases = n_reads_local ? read_offsets[n_reads_local] : 0; c->resident = false;
+        c->hReads = reads; c->hPacked = nullptr; c->hOff = read_offsets; c->nLocalReads = n_reads_local; c->localBases = n_reads_local ? read_offsets[n_reads_local] : 0; c->resident = false;
+        std::vector<pm_comm*> cs{c};
+        runSharded(cs, params, result);
+        return PM_OK;
+    });
+}
+int pm_place_sharded_packed(pm_comm* c, const void* packed, const uint64_t* read_offsets, uint64_t n_reads_local, const pm_place_params* params,
+                            pm_place_result* result) {
+    if (!c || !read_offsets || (!packed && n_reads_local) || !result) return fail(PM_ERR_INVALID, "null argument");
+    if (!c->nccl) return fail(PM_ERR_INVALID, "pm_place_sharded_packed needs an NCCL communicator");
+    if ((reinterpret_cast<uintptr_t>(packed) & 15u) != 0) return fail(PM_ERR_INVALID, "packed reads must be 16-byte aligned");
+    return guarded([&]() -> int {
+        c->hReads = nullptr; c->hPacked = static_cast<const uint4*>(packed); c->hOff = read_offsets; c->nLocalReads = n_reads_local;
+        c->localBases = n_reads_local ? read_offsets[n_reads_local] : 0; c->resident = false;
         std::vector<pm_comm*> cs{c};
         runSharded(cs, params, result);
         return PM_OK;
@@ -434,6 +450,7 @@ int pm_place_sharded(pm_comm* c, const char* reads, const uint64_t* read_offsets
 int pm_place_sharded_resident(pm_comm* c, const pm_place_params* params, pm_place_result* result) {
     if (!c || !result) return fail(PM_ERR_INVALID, "null argument");
     if (!c->nccl) return fail(PM_ERR_INVALID, "pm_place_sharded_resident needs an NCCL communicator (in-process groups: pm_place_multi_resident)");
+    if (!workspaceAlive(c->ws)) return fail(PM_ERR_INVALID, "communicator's workspace was destroyed");
     if (!c->ws->residentValid) return fail(PM_ERR_INVALID, "pm_place_sharded_resident: call pm_reads_upload first");
     return guarded([&]() -> int {
         c->nLocalReads = c->ws->nReads; c->localBases = c->ws->totalBases; c->resident = true;
@@ -455,7 +472,7 @@ int pm_place_multi(pm_comm* const* comms, int n_ranks, const char* reads, const 
             const uint64_t lo = n_reads * (uint64_t)r / (uint64_t)n_ranks, hi = n_reads * (uint64_t)(r + 1) / (uint64_t)n_ranks;
             offs[r].resize(hi - lo + 1);
             for (uint64_t i = lo; i <= hi; ++i) offs[r][i - lo] = read_offsets[i] - read_offsets[lo];
-            cs[r]->hReads = reads + read_offsets[lo]; cs[r]->hOff = offs[r].data(); cs[r]->nLocalReads = hi - lo;
+            cs[r]->hReads = reads + read_offsets[lo]; cs[r]->hPacked = nullptr; cs[r]->hOff = offs[r].data(); cs[r]->nLocalReads = hi - lo;
             cs[r]->localBases = read_offsets[hi] - read_offsets[lo]; cs[r]->resident = false;
         }
         runSharded(cs, params, result);
@@ -468,6 +485,7 @@ int pm_place_multi_resident(pm_comm* const* comms, int n_ranks, const pm_place_p
         checkGroup(comms, n_ranks);
         std::vector<pm_comm*> cs(comms, comms + n_ranks);
         for (pm_comm* c : cs) {
+            if (!workspaceAlive(c->ws)) throw std::runtime_error("communicator's workspace was destroyed");
             if (!c->ws->residentValid) throw std::runtime_error("pm_place_multi_resident: call pm_reads_upload on every rank's workspace first");
             c->nLocalReads = c->ws->nReads; c->localBases = c->ws->totalBases; c->resident = true;
         }

@@ -283,6 +283,59 @@ std::vector<std::tuple<size_t, bool, bool, int64_t>> rollingSyncmers(std::string
 }
 }  // namespace seeding
 
+// ---- ASCII -> 4-bit codes on the host (the layout pm_place_packed takes, see include/panmap_b200.h) ----
+namespace {
+struct PackLut {
+    uint8_t lo[256];
+    PackLut() { for (int c = 0; c < 256; ++c) { uint8_t v = 4; switch (c) { case 'A': case 'a': v = 0; break; case 'C': case 'c': v = 1; break; case 'G': case 'g': v = 2; break; case 'T': case 't': v = 3; break; default: break; } lo[c] = v; } }
+};
+const PackLut kPackLut;
+// one read: len bases -> ceil(len / 32) chunks at dst (slots past the end hold 4)
+inline void packOneRead(const unsigned char* src, uint64_t len, unsigned char* dst) {
+    const uint64_t pairs = len / 2;
+    for (uint64_t b = 0; b < pairs; ++b) dst[b] = static_cast<unsigned char>(kPackLut.lo[src[2 * b]] | (kPackLut.lo[src[2 * b + 1]] << 4));
+    uint64_t b = pairs;
+    const uint64_t bytes = ((len + 31) / 32) * 16;
+    if (len & 1) { dst[b] = static_cast<unsigned char>(kPackLut.lo[src[len - 1]] | 0x40); ++b; }
+    for (; b < bytes; ++b) dst[b] = 0x44;
+}
+}  // namespace
+
+extern "C" uint64_t pm_packed_chunks(const uint64_t* read_offsets, uint64_t n_reads) {
+    uint64_t c = 0;
+    if (!read_offsets) return 0;
+    for (uint64_t i = 0; i < n_reads; ++i) c += (read_offsets[i + 1] - read_offsets[i] + 31) >> 5;
+    return c;
+}
+extern "C" int pm_pack_reads(const char* reads, const uint64_t* read_offsets, uint64_t n_reads, void* packed_out, int threads) {
+    if (!read_offsets || (!reads && n_reads) || (!packed_out && n_reads)) return PM_ERR_INVALID;
+    size_t nT = threads > 0 ? static_cast<size_t>(threads) : std::max(1u, std::thread::hardware_concurrency());
+    if (n_reads < 4096) nT = 1;
+    nT = std::min<size_t>(nT, 64);
+    // thread t takes reads [n t / nT, n (t+1) / nT); its first chunk is the chunk count of everything before
+    std::vector<uint64_t> firstChunk(nT + 1, 0);
+    for (size_t t = 0; t < nT; ++t) {
+        const uint64_t r0 = n_reads * t / nT, r1 = n_reads * (t + 1) / nT;
+        uint64_t c = 0;
+        for (uint64_t i = r0; i < r1; ++i) c += (read_offsets[i + 1] - read_offsets[i] + 31) >> 5;
+        firstChunk[t + 1] = firstChunk[t] + c;
+    }
+    auto work = [&](size_t t) {
+        const uint64_t r0 = n_reads * t / nT, r1 = n_reads * (t + 1) / nT;
+        unsigned char* dst = static_cast<unsigned char*>(packed_out) + firstChunk[t] * 16;
+        for (uint64_t i = r0; i < r1; ++i) {
+            const uint64_t len = read_offsets[i + 1] - read_offsets[i];
+            packOneRead(reinterpret_cast<const unsigned char*>(reads) + read_offsets[i], len, dst);
+            dst += ((len + 31) >> 5) * 16;
+        }
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nT; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    return PM_OK;
+}
+
 // file ingest alone (no GPU): bases + offsets of reads1 (+ reads2 interleaved); buffers are malloc'd, free with pm_free
 extern "C" int pm_read_fastx(const char* reads1, const char* reads2, char** bases, uint64_t** offsets, uint64_t* n_reads, char* err, uint64_t err_cap) {
     try {

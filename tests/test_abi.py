@@ -191,3 +191,28 @@ def test_fastx_serial_parser_keeps_kseq_corner_cases(tmp_path):
     p.write_text("@a\nACGT\n+\nII\n@c\nGG\n+\nII\n")               # kseq reads "II" + "@c" as a's four quality bytes, then finds no header
     b, o = pm.read_fastx(str(p))
     assert bytes(b) == b"ACGT" and list(o) == [0, 4]
+
+
+def test_host_packer_writes_the_4bit_layout_of_pm_place_packed():
+    """pm_pack_reads (multi-threaded above 4096 reads): A/C/G/T in either case -> 0..3, everything else 4, 32 bases per 16-byte chunk with
+    base j in bits [4j, 4j+4), slots past a read's end = 4, every read on a chunk boundary"""
+    rng = np.random.default_rng(17)
+    reads = H.random_reads(rng, 9000, lo=0, hi=170, p_n=0.03, p_lower=0.05) + [b"", b"ACGTRYKM-*acgtn", b"T" * 32, b"G" * 33, b"C" * 31]
+    buf, off = pm.pack_reads(reads)
+    pk = pm.host_pack_reads(buf, off)
+    assert pk.ctypes.data % 16 == 0
+    lut = np.full(256, 4, np.uint8)
+    for ch, v in zip(b"ACGTacgt", [0, 1, 2, 3, 0, 1, 2, 3]):
+        lut[ch] = v
+    lens = np.diff(off).astype(np.int64)
+    chunks = (lens + 31) // 32
+    assert pk.size == int(chunks.sum()) * 16 == int(pm.lib().pm_packed_chunks(off.ctypes.data, len(reads))) * 16
+    nib = np.empty(pk.size * 2, np.uint8)
+    nib[0::2] = pk & 15; nib[1::2] = pk >> 4
+    exp = np.full(nib.size, 4, np.uint8)
+    starts = np.concatenate([[0], np.cumsum(chunks)[:-1]]) * 32
+    for r in range(len(reads)):
+        exp[starts[r]:starts[r] + lens[r]] = lut[buf[int(off[r]):int(off[r + 1])]]
+    assert np.array_equal(nib, exp)
+    one = pm.host_pack_reads(buf, off, threads=1)
+    assert np.array_equal(one, pk)

@@ -312,6 +312,34 @@ def test_homopolymer_kmers_are_erased_from_the_read_table(l):
     assert len(raw) == 2 and not (raw & set(int(x) for x in th[tc > 0]))     # ... and so has the device table (the keys were inserted, then zeroed)
 
 
+@pytest.mark.parametrize("k,s,t,l,op,ts,te", [(19, 8, 0, 3, False, 0, 0), (19, 8, 0, 3, False, 6, 9), (15, 8, 0, 1, False, 0, 0), (21, 10, 1, 2, True, 0, 0)])
+def test_place_packed_reads_equal_ascii_reads(k, s, t, l, op, ts, te):
+    """pm_place_packed: the reads arrive as 4-bit codes (half the PCIe bytes, no ASCII on the device); same table, scores and placement as
+    pm_place on the ASCII bytes, for the specialised and the generic syncmer kernels, small (one slice) and sliced (>= 65536 reads) samples"""
+    rng = np.random.default_rng(300 + k + l + ts)
+    idx, _, _ = H.synthetic_index(300, rng, k=k, s=s, t=t, l=l)
+    idx.open = int(op)
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, k, s, t, l, int(op))
+    ws = pm.Workspace(pm.Index(host))
+    prm = pm.PlaceParams(trim_start=ts, trim_end=te)
+    base = H.random_reads(rng, 500, lo=0, hi=260, p_n=0.02, p_lower=0.05)
+    for reads in (base, [base[i % 500] for i in range(70000)]):
+        buf, off = pm.pack_reads(reads)
+        a = ws.place(buf, off, prm)
+        ta = ws.seed_table()
+        b = ws.place_packed(pm.host_pack_reads(buf, off), off, prm)
+        tb = ws.seed_table()
+        assert np.array_equal(ta[0], tb[0]) and np.array_equal(ta[1], tb[1])
+        assert a.raw.unique_seeds == b.raw.unique_seeds and a.raw.read_magnitude == b.raw.read_magnitude
+        assert all(a.best_index[m] == b.best_index[m] and a.best_score[m] == b.best_score[m] and np.array_equal(a.tied[m], b.tied[m]) for m in pm.METRICS)
+    exp = cpu.place(*pm.pack_reads(base), idx, trim_start=ts, trim_end=te)
+    got = ws.place_packed(pm.host_pack_reads(*pm.pack_reads(base)), pm.pack_reads(base)[1], prm)
+    assert got.raw.unique_seeds == exp["unique_seeds"] and all(got.best_index[n] == exp["best_index"][m] for m, n in enumerate(pm.METRICS))
+    with pytest.raises(pm.PanmapError) as e:
+        ws.place_packed(pm.host_pack_reads(*pm.pack_reads(base)), pm.pack_reads(base)[1], pm.PlaceParams(dedup_reads=1))
+    assert e.value.code == -5
+
+
 def test_place_empty_and_short_reads():
     rng = np.random.default_rng(6)
     idx, _, _ = H.synthetic_index(50, rng)
