@@ -35,6 +35,18 @@ WORKLOADS = {
                lam=1.0, n_reads=1_000_000, read_len=150),
     "c3-small": dict(name="synthetic 100k-node tree, 30 kb genome, 100k x 150 bp reads (reduced configs[2], dev only)", n_nodes=100_000,
                      genome=30_000, lam=1.0, n_reads=100_000, read_len=150),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case, real data (index built by the reference's IndexBuilder, oracle/_ref/data)
+    "c1": dict(name="sars_20000_twilight_dipper.panman + isolate_R1/R2.fastq.gz, single sample (BASELINE configs[0])", real=True),
+    # BASELINE.json configs[3]
+    "c4": dict(name="synthetic bacterial-scale tree: 100k nodes, 5 Mb genome, 10M x 150 bp reads (BASELINE configs[3])", n_nodes=100_000,
+               genome=5_000_000, lam=50.0, n_reads=10_000_000, read_len=150),
+    "c4-small": dict(name="synthetic 20k nodes, 1 Mb genome, 1M x 150 bp reads (reduced configs[3], dev only)", n_nodes=20_000,
+                     genome=1_000_000, lam=50.0, n_reads=1_000_000, read_len=150),
+    # BASELINE.json configs[4]: sample-sharded batch; the index has config 1's shape (40k nodes, 30 kb genome, ~60 seed deltas per node)
+    "c5": dict(name="batch placement of 1,024 synthetic samples (100k x 133 bp reads each, random leaves) against a sars_20000-shaped index (BASELINE configs[4])",
+               n_nodes=40_000, genome=30_000, lam=3.3, n_reads=100_000, read_len=133, batch=1024),
+    "c5-small": dict(name="batch of 64 synthetic samples against a sars_20000-shaped index (reduced configs[4], dev only)",
+                     n_nodes=40_000, genome=30_000, lam=3.3, n_reads=100_000, read_len=133, batch=64),
 }
 
 
@@ -92,11 +104,34 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(name, seed=0):
+class RealSample:
+    """config 1: the reference-built sars_20000 index (.idx read by the product's own reader) + the isolate reads (the host shim's parser)"""
+
+    def __init__(self):
+        import panmap_b200 as pm
+        from tests import helpers as H
+        for p in (H.SARS_IDX, H.ISOLATE_R1, H.ISOLATE_R2):
+            if not os.path.exists(p):
+                raise SystemExit(f"workload c1 needs {p} (staged by __graft_entry__.build() from the reference's bundled data)")
+        self.host = pm.HostIndex.read(H.SARS_IDX)
+        h = self.host
+        self.hash, self.parent, self.child, self.offsets, self.parent_index = h.hash, h.parent, h.child, h.offsets, h.parent_index
+        self.k, self.s, self.t, self.l, self.open = h.k, h.s, h.t, h.l, h.open
+        self.n_nodes, self.n_deltas = h.n_nodes, h.n_deltas
+        self.reads, self.read_offsets = pm.read_fastx(H.ISOLATE_R1, H.ISOLATE_R2)
+        self.truth = -1
+        self.idx_path, self.fastq = H.SARS_IDX, (H.ISOLATE_R1, H.ISOLATE_R2)
+
+
+def make_workload(name, seed=0, n_reads=None):
     from tools.synth import synth
-    w = WORKLOADS[name]
+    w = dict(WORKLOADS[name])
     t = time.time()
-    S = synth.generate(w["n_nodes"], w["genome"], w["lam"], w["n_reads"], read_len=w["read_len"], seed=seed)
+    if w.get("real"):
+        S = RealSample()
+        w["n_reads"] = int(S.read_offsets.size - 1)
+    else:
+        S = synth.generate(w["n_nodes"], w["genome"], w["lam"], n_reads or w["n_reads"], read_len=w["read_len"], seed=seed)
     S.gen_seconds = time.time() - t
     return S, w
 
@@ -131,12 +166,18 @@ def reference_step(S, n_reads, threads, tmpdir, cache={}):
     FASTQ of the first n_reads reads.  Returns (seconds of the whole call, result incl. the reference's own stage timers)."""
     from oracle import ref
     if "idx" not in cache:
-        p = os.path.join(tmpdir, "synth.idx")
-        ref.write_index(p, S)
-        cache["idx"] = ref.RefIndex(p)
-    fq = write_fastq(S, n_reads, os.path.join(tmpdir, f"reads_{n_reads}.fastq"))
+        if hasattr(S, "idx_path"):
+            cache["idx"] = ref.RefIndex(S.idx_path)
+        else:
+            p = os.path.join(tmpdir, "synth.idx")
+            ref.write_index(p, S)
+            cache["idx"] = ref.RefIndex(p)
+    if hasattr(S, "fastq"):     # real sample: the files themselves (gzip inflate is part of the reference's read processing)
+        fq, fq2 = S.fastq
+    else:
+        fq, fq2 = write_fastq(S, n_reads, os.path.join(tmpdir, f"reads_{n_reads}.fastq")), ""
     t = time.perf_counter()
-    r = cache["idx"].place(fq, "", out_tsv=os.path.join(tmpdir, "ref.tsv"), threads=threads, stage_timers=True)
+    r = cache["idx"].place(fq, fq2, out_tsv=os.path.join(tmpdir, "ref.tsv"), threads=threads, stage_timers=True)
     return time.perf_counter() - t, r
 
 
@@ -169,13 +210,18 @@ def run_reference_arm(args):
     S, w = make_workload(args.workload)
     threads = os.cpu_count() or 1
     with tempfile.TemporaryDirectory() as td:
-        # bounded sample: full index, reads subsampled so that K+W steps end within a few minutes
-        t_small, _ = reference_step(S, min(20000, w["n_reads"]), threads, td)
-        t_mid, _ = reference_step(S, min(60000, w["n_reads"]), threads, td)
-        per_read = max((t_mid - t_small) / 40000.0, 1e-7)
-        fixed = max(t_small - 20000 * per_read, 0.05)
-        budget = 150.0 / max(args.steps + args.warmup, 1)
-        n_s = int(min(w["n_reads"], max(20000, (budget - fixed) / per_read)))
+        if w.get("real") or w.get("batch"):
+            # one real sample / one sample of the batch per step (the whole sample: ~0.5 s per step)
+            n_s = w["n_reads"]
+            reference_step(S, n_s, threads, td)
+        else:
+            # bounded sample: full index, reads subsampled so that K+W steps end within a few minutes
+            t_small, _ = reference_step(S, min(20000, w["n_reads"]), threads, td)
+            t_mid, _ = reference_step(S, min(60000, w["n_reads"]), threads, td)
+            per_read = max((t_mid - t_small) / 40000.0, 1e-7)
+            fixed = max(t_small - 20000 * per_read, 0.05)
+            budget = 150.0 / max(args.steps + args.warmup, 1)
+            n_s = int(min(w["n_reads"], max(20000, (budget - fixed) / per_read)))
         for _ in range(args.warmup):
             reference_step(S, n_s, threads, td)
         spans = []
@@ -189,7 +235,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak",
             "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
-            "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n_s, "k": 19, "s": 8, "l": 3},
+            "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": n_s, "k": int(S.k), "s": int(S.s), "l": int(S.l)},
             "spans": mean,
             "span_note": "value / ms_per_step / e2e = buffers_to_result (the whole placeLite call minus its FASTQ parse, by the reference's own stage timers): "
                          "the span the GPU arm's e2e covers.  file_to_result_ms is the whole call (parse of the FASTQ file + TSV write included).",
@@ -239,7 +285,9 @@ def main():
     if pm.device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: the placement path has no CPU fallback")
     S, w = make_workload(args.workload)
-    host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
+    if WORKLOADS[args.workload].get("batch"):
+        return run_batch(args, pm, world, rank, local)
+    host = getattr(S, "host", None) or pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
     params = pm.PlaceParams()
     alg = algorithmic_bytes(S)
     pk, pk_src = peaks()
@@ -309,6 +357,24 @@ def main():
     L.pm_host_free(hp_reads); L.pm_host_free(hp_off); L.pm_host_free(hp_packed)
     spans = {"buffers_to_result_ms": 1e3 * e2e_wall / args.steps, "packed_buffers_to_result_ms": 1e3 * e2ep_wall / args.steps}
 
+    # between-iteration cache state (timing rule): large samples exceed L2 by themselves; small ones get an explicit flush measurement beside the hot one
+    ws_bytes = nbytes + 8 * nbytes // 3 + 12 * S.n_deltas // 3 + 80 * S.n_nodes
+    l2_note = (f"per-step working set ~{ws_bytes / 1e6:.0f} MB (reads + syncmer lists + count table + delta words + scores) exceeds the 126 MB L2; no explicit flush"
+               if ws_bytes > 200e6 else
+               f"per-step working set ~{ws_bytes / 1e6:.0f} MB fits the 126 MB L2: `value` is the hot-cache number a batch of samples sees; see cold_cache for the L2-flushed one")
+    cold = None
+    if ws_bytes <= 200e6:
+        try:
+            import torch
+            junk = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+            cms = 0.0
+            for _ in range(args.steps):
+                junk.fill_(1); torch.cuda.synchronize()
+                cms += ws.place_resident(params, full=False).stage_ms[7]
+            cold = {"ms_per_step": cms / args.steps, "flush": "256 MB written to HBM between steps"}
+            del junk
+        except Exception as e:
+            cold = {"error": str(e)}
     # ---- roofline ----
     # dominant kernel of the step = the syncmer kernel (CUDA events of the library around that launch alone); it is bound by the
     # integer ALU pipe, not by HBM, so its fraction of the HBM roofline is small by construction.  The HBM-bound kernel north_star
@@ -330,7 +396,7 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64+f64", "data": "synthetic",
         "config": {"workload": w["name"], "n_nodes": S.n_nodes, "n_deltas": S.n_deltas, "n_reads": w["n_reads"], "read_bases": nbytes, "k": S.k, "s": S.s,
-                   "l": S.l, "l2": "per-step working set (reads 150 MB + syncmer lists 320 MB + count table + delta arrays) exceeds the 126 MB L2; no explicit flush",
+                   "l": S.l, "l2": l2_note,
                    "truth_node": int(S.truth), "placed": {m: int(res.best_index[m]) for m in pm.METRICS},
                    "unique_seeds": int(res.raw.unique_seeds), "kept_seeds": int(res.raw.read_unique_seed_count),
                    "min_read_support": int(res.raw.min_read_support), "index_distinct_seeds": int(index.num_distinct_seeds)},
@@ -352,18 +418,20 @@ def main():
         "place_stage": {"algorithmic_bytes": alg["total"], "achieved": alg["total"] / (dev_ms * 1e-3) / 1e9, "frac": alg["total"] / (dev_ms * 1e-3) / 1e9 / peak},
         "clocks": clocks,
     }
+    if cold is not None:
+        line["cold_cache"] = cold
     with tempfile.TemporaryDirectory() as td:
         if not args.no_file_span:
             # the other span: FASTQ FILE -> result through the C++ shim (multi-threaded flat parser + the same pm_place), same file the reference arm parses
             try:
-                fq = write_fastq(S, w["n_reads"], os.path.join(td, "reads_all.fastq"))
-                pm.place_files(ws, fq, "", os.path.join(td, "gpu.tsv"), params)
+                fq, fq2 = S.fastq if hasattr(S, "fastq") else (write_fastq(S, w["n_reads"], os.path.join(td, "reads_all.fastq")), "")
+                pm.place_files(ws, fq, fq2, os.path.join(td, "gpu.tsv"), params)
                 t0 = time.perf_counter()
                 k3 = max(2, min(args.steps, 5))
                 for _ in range(k3):
-                    rf = pm.place_files(ws, fq, "", os.path.join(td, "gpu.tsv"), params)
+                    rf = pm.place_files(ws, fq, fq2, os.path.join(td, "gpu.tsv"), params)
                 spans["file_to_result_ms"] = 1e3 * (time.perf_counter() - t0) / k3
-                spans["file_bytes"] = os.path.getsize(fq)
+                spans["file_bytes"] = os.path.getsize(fq) + (os.path.getsize(fq2) if fq2 else 0)
                 spans["file_result_same_as_buffers"] = bool(all(int(rf.best_index[i]) == int(res.best_index[m]) for i, m in enumerate(pm.METRICS)))
             except Exception as e:  # reported, never fatal
                 spans["file_to_result_error"] = str(e)
@@ -374,6 +442,7 @@ def main():
                 if ref.available():
                     threads = os.cpu_count() or 1
                     n_s = min(w["n_reads"], 200_000)
+                    reference_step(S, n_s, threads, td)          # first call maps the index (seedChangesLoaded): not part of the place stage
                     dt, rr = reference_step(S, n_s, threads, td)
                     sp = reference_spans(dt, rr)
                     # the GPU on the very same sample: agreement is checked, not assumed
@@ -392,6 +461,159 @@ def main():
             except Exception as e:  # the baseline is reported, never fatal
                 line["cpu_baseline"] = {"value": None, "unit": "node*reads/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
     print(json.dumps(line))
+
+
+def batch_samples(w, rank, world, limit=None):
+    """this rank's share of the batch: groups of 64 samples, every group from its own random leaf of the same synthetic tree (same seed ->
+    same tree and index in every call; the leaf is chosen by truth_frac).  Returns (index arrays of the first call, list of (reads, offsets, truth))."""
+    from tools.synth import synth
+    B = w["batch"]
+    per_rank = B // world if limit is None else min(limit, B // world)
+    group = 64
+    out, first = [], None
+    for g in range((per_rank + group - 1) // group):
+        k = min(group, per_rank - g * group)
+        frac = ((rank * 131 + g * 17 + 7) % 97) / 97.0 * 0.9 + 0.05
+        S = synth.generate(w["n_nodes"], w["genome"], w["lam"], k * w["n_reads"], read_len=w["read_len"], seed=0, truth_frac=frac)
+        if first is None:
+            first = S
+        n = w["n_reads"]
+        for j in range(k):
+            lo, hi = int(S.read_offsets[j * n]), int(S.read_offsets[(j + 1) * n])
+            out.append((S.reads[lo:hi], np.ascontiguousarray(S.read_offsets[j * n:(j + 1) * n + 1] - np.uint64(lo)), int(S.truth)))
+    return first, out
+
+
+def run_batch(args, pm, world, rank, local):
+    """BASELINE configs[4]: many samples against one index, sample-sharded over the GPUs (reference runBatchPlacement, main.cpp:1464-1666: TBB
+    workers call placeLite concurrently on one LiteTree).  Every rank holds the index and its share of the samples; `threads` host threads per
+    GPU each drive their own workspace (own stream) and pull samples from a shared queue.  No collective on the data path -> weak scaling.
+    value: samples resident in a device pool (device-to-device hand-over per sample inside the timed region); e2e: samples in pinned host memory."""
+    import threading as th
+    import torch
+    w = dict(WORKLOADS[args.workload])
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl")
+    dev = torch.device("cuda", local)
+    S0, samples = batch_samples(w, rank, world)
+    host = pm.HostIndex(S0.hash, S0.parent, S0.child, S0.offsets, S0.parent_index, S0.k, S0.s, S0.t, S0.l)
+    index = pm.Index(host, device=local)
+    n_threads = int(os.environ.get("PM_BATCH_THREADS", "4"))
+    wss = [pm.Workspace(index) for _ in range(n_threads)]
+    params = pm.PlaceParams()
+    L = pm.lib()
+    # device pool: every sample's bytes and offsets in HBM
+    d_reads = [torch.from_numpy(r).to(dev) for r, _, _ in samples]
+    d_offs = [torch.from_numpy(o.view(np.int64)).to(dev) for _, o, _ in samples]
+    torch.cuda.synchronize()
+    n_s = len(samples)
+    placed = np.full(n_s, -1, np.int64)
+
+    def pass_over(fn):
+        nxt = [0]; lock = th.Lock()
+        def work(t):
+            while True:
+                with lock:
+                    i = nxt[0]; nxt[0] += 1
+                if i >= n_s:
+                    return
+                placed[i] = fn(wss[t], i)
+        ts = [th.Thread(target=work, args=(t,)) for t in range(n_threads)]
+        for x in ts: x.start()
+        for x in ts: x.join()
+
+    def resident(ws, i):
+        ws.upload_device(d_reads[i].data_ptr(), d_offs[i].data_ptr(), samples[i][1])
+        return int(ws.place_resident(params, full=False).best_index[0])
+    hp = [(pinned_copy(L, r), pinned_copy(L, o)) for r, o, _ in samples[:min(n_s, 128)]]
+    def from_host(ws, i):
+        j = i % len(hp)
+        return int(ws.place_raw(hp[j][0], hp[j][1], samples[j][1].size - 1, params).best_index[0])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    def maxf(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+    def sumf(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.SUM); return float(t.item())
+
+    steps, warm = max(1, args.steps // 4), max(1, args.warmup // 3)      # a step = one pass over the rank's whole share of the batch
+    for _ in range(warm):
+        pass_over(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = pm.launch_count(); t0 = time.perf_counter()
+    for _ in range(steps):
+        pass_over(resident)
+    torch.cuda.synchronize()
+    dt = maxf(time.perf_counter() - t0); launches = sumf(pm.launch_count() - l0)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    on_truth = sumf(float(sum(1 for i in range(n_s) if placed[i] == samples[i][2])))
+    pass_over(from_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pass_over(from_host)
+    torch.cuda.synchronize()
+    dte = maxf(time.perf_counter() - t0)
+    for a, b in hp:
+        L.pm_host_free(a); L.pm_host_free(b)
+    total_samples = sumf(float(n_s))
+    if rank == 0:
+        nr = S0.n_nodes * w["n_reads"]
+        bases = int(sum(int(o[-1]) for _, o, _ in samples[:1])) 
+        pk, pk_src = peaks()
+        alg = bases + 12 * S0.n_deltas + 8 * (S0.n_nodes + 1) + 4 * S0.n_nodes + 40 * S0.n_nodes
+        ms_sample = 1e3 * dt / (steps * n_s)
+        line = {"metric": "placement nodes x reads scored per second", "value": total_samples * steps * nr / dt, "unit": "node*reads/s", "n_gpus": world,
+                "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64+f64",
+                "data": "synthetic",
+                "config": {"workload": w["name"], "n_nodes": S0.n_nodes, "n_deltas": S0.n_deltas, "samples": int(total_samples), "samples_per_gpu": n_s,
+                           "reads_per_sample": w["n_reads"], "read_len": w["read_len"], "k": S0.k, "s": S0.s, "l": S0.l, "host_threads_per_gpu": n_threads,
+                           "parallelism": f"sample-sharded over {world} GPU(s), {n_threads} workspaces (streams) per GPU on one shared index, no collective",
+                           "l2": "a pass touches every sample of the rank's share once (>= 1.7 GB per 128 samples): nothing of a sample survives in L2 until its next turn"},
+                "samples_per_second": total_samples * steps / dt, "ms_per_sample_per_gpu": ms_sample,
+                "placed_on_truth_leaf": int(on_truth), "placed_total": int(total_samples),
+                "e2e": {"value": total_samples * steps * nr / dte, "unit": "node*reads/s", "samples_per_second": total_samples * steps / dte,
+                        "h2d_bytes_per_step": int(total_samples) * (bases + 8 * (w["n_reads"] + 1)), "d2h_bytes_per_step": int(total_samples) * 452,
+                        "ms_per_step": 1e3 * dte / steps, "span": "buffers_to_result per sample: reads + offsets in pinned host memory -> best nodes + tie lists"},
+                "gpu_launches": int(launches), "gpu_launches_per_sample": launches / (steps * total_samples),
+                "roofline": {"bound": "hbm", "kernel": "whole place stage of one sample (latency regime: ~45 MB algorithmic per sample)", "achieved": alg / (ms_sample * 1e-3) / 1e9,
+                             "peak": float(pk["hbm_gbs"]), "unit": "GB/s", "frac": alg / (ms_sample * 1e-3) / 1e9 / float(pk["hbm_gbs"]), "traffic": None, "peak_source": pk_src},
+                "clocks": clocks}
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+                if ref.available():
+                    with tempfile.TemporaryDirectory() as td:
+                        class One:   # one sample of the batch for the reference arm
+                            pass
+                        o = One(); o.__dict__.update(S0.__dict__); o.reads, o.read_offsets = samples[0][0], samples[0][1]
+                        threads = os.cpu_count() or 1
+                        reference_step(o, w["n_reads"], threads, td)
+                        dtr, rr = reference_step(o, w["n_reads"], threads, td)
+                        sp = reference_spans(dtr, rr)
+                        g = wss[0].place(samples[0][0], samples[0][1], params)
+                        line["cpu_baseline"] = {"value": nr / (sp["buffers_to_result_ms"] * 1e-3), "unit": "node*reads/s", "cores": threads, "kind": "reference", "spans": sp,
+                                                "sample": f"ONE sample of the batch ({w['n_reads']} reads) through the reference placeLite with {threads} host threads; value = its buffers_to_result span",
+                                                "gpu_same_sample": {"best_nodes_tie_lists_scores_agree": same_placement([g.best_index[m] for m in pm.METRICS], [g.tied[m] for m in pm.METRICS],
+                                                                    [g.best_score[m] for m in pm.METRICS], rr["best_index"], rr["tied"], rr["best_score"])}}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": "node*reads/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local):

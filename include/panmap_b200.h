@@ -155,6 +155,9 @@ int pm_place_quality(pm_workspace* ws, const char* reads, const char* quals, con
  * measure device throughput), pm_place_resident then runs every stage on them; may be called repeatedly. */
 int pm_reads_upload(pm_workspace* ws, const char* reads, const uint64_t* read_offsets, uint64_t n_reads);
 int pm_place_resident(pm_workspace* ws, const pm_place_params* params, pm_place_result* result);
+/* the same layout step for a sample that already sits in HBM (e.g. one of many samples a batch caller keeps in a device pool): d_reads /
+ * d_read_offsets are DEVICE pointers, h_read_offsets the same offsets on the host (sizing); device-to-device copies, enqueued without waiting */
+int pm_reads_upload_device(pm_workspace* ws, const char* d_reads, const uint64_t* d_read_offsets, const uint64_t* h_read_offsets, uint64_t n_reads);
 /* page-locked host buffers for callers that want the H2D copies of pm_place to run at full PCIe speed */
 void* pm_host_alloc(uint64_t bytes);
 void pm_host_free(void* p);

@@ -95,6 +95,7 @@ def lib():
     L.pm_pack_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
     L.pm_place_quality.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
     L.pm_reads_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_reads_upload_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_place_resident.argtypes = [C.c_void_p, C.POINTER(PlaceParams), C.POINTER(PlaceResult)]
     L.pm_get_tied.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
     L.pm_get_node_scores.argtypes = [C.c_void_p, C.c_void_p]
@@ -365,6 +366,11 @@ class Workspace:
         reads = np.ascontiguousarray(reads, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         _ck(lib().pm_reads_upload(self._h, _ptr(reads), offsets.ctypes.data_as(C.c_void_p), offsets.size - 1))
+
+    def upload_device(self, d_reads_ptr, d_offsets_ptr, h_offsets):
+        """sample already in HBM (device pointers) -> this workspace; h_offsets: the same offsets as a host array"""
+        h_offsets = np.ascontiguousarray(h_offsets, dtype=np.uint64)
+        _ck(lib().pm_reads_upload_device(self._h, d_reads_ptr, d_offsets_ptr, h_offsets.ctypes.data_as(C.c_void_p), h_offsets.size - 1))
 
     def place_resident(self, params=None, full=True):
         params = params or PlaceParams()

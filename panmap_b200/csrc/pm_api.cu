@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
+#include <initializer_list>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -176,7 +178,8 @@ static void hostPackedOffsets(pm_workspace* W, const uint64_t* off, u64 n, int k
     packBlockFirst(W->hPackedOff.p, n, acc, W->hBlockFirst.p);
 }
 
-void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n) {
+// fromDevice: `reads` and `dOff` already live in HBM (a caller-side pool of samples): device-to-device copies, no host wait
+void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n, bool fromDevice, const uint64_t* dOff) {
     pm_index* I = W->idx;
     const u64 base0 = n ? off[0] : 0;
     const u64 total = n ? off[n] - base0 : 0;
@@ -185,8 +188,9 @@ void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n)
     W->synBuf.ensure(W->nChunks * 32 + 32); W->synCount.ensure(n + 1);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1); W->packed.ensure(W->nChunks + 1);
     if (base0 != 0) throw std::runtime_error("read_offsets[0] must be 0");
-    if (total) CK(cudaMemcpyAsync(W->reads.p, reads, total, cudaMemcpyHostToDevice, W->st));
-    CK(cudaMemcpyAsync(W->off.p, off, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->st));
+    if (total) CK(cudaMemcpyAsync(W->reads.p, reads, total, fromDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, W->st));
+    if (fromDevice) CK(cudaMemcpyAsync(W->off.p, dOff, (n + 1) * sizeof(u64), cudaMemcpyDeviceToDevice, W->st));
+    else CK(cudaMemcpyAsync(W->off.p, off, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->st));
     CK(cudaMemcpyAsync(W->packedOff.p, W->hPackedOff.p, (n + 1) * sizeof(u64), cudaMemcpyHostToDevice, W->st));
     W->blockFirst.ensure((W->nChunks + 255) / 256 + 1);
     CK(cudaMemcpyAsync(W->blockFirst.p, W->hBlockFirst.p, ((W->nChunks + 255) / 256 + 1) * sizeof(u32), cudaMemcpyHostToDevice, W->st));
@@ -207,6 +211,21 @@ static unsigned char* prepareDedup(pm_workspace* W, u64 n, const pm_place_params
 
 // Host buffers -> table, pipelined: the sample is cut into slices of reads; slice i+1 is copied (copy stream) while slice i is
 // packed, seeded and counted (compute stream).  Host-side chunk offsets of a slice are computed just before its copy.
+// slice schedule of the host-buffer pipelines: cumulative fractions of the reads (tuning override: PM_SLICES_ASCII / PM_SLICES_PACKED =
+// comma-separated cumulative cut points ending in 1)
+struct SliceSchedule { int n; double cut[33]; };
+static SliceSchedule scheduleFromEnv(const char* var, std::initializer_list<double> dflt) {
+    SliceSchedule s{0, {0.0}};
+    std::vector<double> v(dflt);
+    if (const char* e = std::getenv(var)) {
+        std::vector<double> u; const char* p = e;
+        while (*p) { char* q; const double x = std::strtod(p, &q); if (q == p) break; u.push_back(x); p = (*q == ',') ? q + 1 : q; }
+        if (!u.empty() && u.size() <= 32 && u.back() == 1.0 && std::is_sorted(u.begin(), u.end()) && u.front() > 0.0) v = u;
+    }
+    s.n = (int)v.size();
+    for (int i = 0; i < s.n; ++i) s.cut[i + 1] = v[i];
+    return s;
+}
 void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* off, u64 n, const pm_place_params& prm) {
     pm_index* I = W->idx;
     const int k = I->F.sp.k;
@@ -215,8 +234,9 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     // Slice schedule: the host prepares the chunk offsets of slice i while slice i-1 is on the wire, so the first slice is tiny
     // (its preparation is the only one nothing overlaps) and slices grow by at most 2x; they shrink again towards the end because
     // everything after the last copy (its seeding, then scoring and selection) is exposed latency.
-    static const double kCut[11] = {0.0, 0.03, 0.09, 0.21, 0.40, 0.58, 0.73, 0.84, 0.91, 0.96, 1.0};
-    const int nSlices = n >= (1u << 16) ? 10 : 1;
+    static const SliceSchedule sched = scheduleFromEnv("PM_SLICES_ASCII", {0.03, 0.09, 0.21, 0.40, 0.58, 0.73, 0.84, 0.91, 0.96, 1.0});
+    const double* kCut = sched.cut;
+    const int nSlices = n >= (1u << 16) ? sched.n : 1;
     W->nReads = n; W->totalBases = total;
     W->hPackedOff.ensure(n + 1); W->hBlockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 32);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
@@ -277,8 +297,9 @@ void uploadAndSeedPipelinedPacked(pm_workspace* W, const uint4* hPacked, const u
     if (I->F.sp.hpc) throw Unsupported("packed reads on an hpc index: homopolymer compression works on the ASCII reads (use pm_place)");
     if (prm.dedup_reads) throw Unsupported("dedup_reads compares the raw read strings, which 4-bit codes do not preserve (use pm_place)");
     const u64 total = n ? off[n] : 0;
-    static const double kCut[11] = {0.0, 0.03, 0.09, 0.21, 0.40, 0.58, 0.73, 0.84, 0.91, 0.96, 1.0};
-    const int nSlices = n >= (1u << 16) ? 10 : 1;
+    static const SliceSchedule sched = scheduleFromEnv("PM_SLICES_PACKED", {0.03, 0.09, 0.21, 0.40, 0.58, 0.73, 0.84, 0.91, 0.96, 1.0});
+    const double* kCut = sched.cut;
+    const int nSlices = n >= (1u << 16) ? sched.n : 1;
     W->nReads = n; W->totalBases = total;
     W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
     W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1);
@@ -372,7 +393,8 @@ void enqueueSmall(pm_workspace* W) {
     W->hStage.ensure(kResultBlobBytes);
     CK(cudaMemcpyAsync(W->hStage.p, W->resultBlob.p, kResultBlobBytes, cudaMemcpyDeviceToHost, W->st));
 }
-void parseSmall(pm_workspace* W) {
+void parseSmall(pm_workspace* W) {   // runs right after a stream synchronisation
+    W->uploadPending = false;
     const unsigned char* h = W->hStage.p;
     std::memcpy(&W->hAcc, h, sizeof(SampleAcc));
     std::memcpy(&W->hScal, h + sizeof(SampleAcc), sizeof(SampleScalars));
@@ -563,7 +585,7 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         CK(cudaStreamCreateWithFlags(&W->st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&W->stCopy, cudaStreamNonBlocking));
         for (auto& e : W->ev) CK(cudaEventCreate(&e));
-        for (auto& e : W->evCopy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : W->evCopy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));   // one per slice of the host-buffer pipeline
         for (auto& e : W->evK) CK(cudaEventCreate(&e));
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
@@ -650,6 +672,16 @@ int pm_reads_upload(pm_workspace* ws, const char* reads, const uint64_t* read_of
         uploadReads(ws, reads, read_offsets, n_reads);
         CK(cudaStreamSynchronize(ws->st));
         ws->residentValid = true;
+        return PM_OK;
+    });
+}
+int pm_reads_upload_device(pm_workspace* ws, const char* d_reads, const uint64_t* d_read_offsets, const uint64_t* h_read_offsets, uint64_t n_reads) {
+    if (!ws || !h_read_offsets || !d_read_offsets || (!d_reads && n_reads)) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->idx->device);
+        if (ws->uploadPending) CK(cudaStreamSynchronize(ws->st));   // the pinned staging arrays of the previous upload may still be in flight
+        uploadReads(ws, d_reads, h_read_offsets, n_reads, true, d_read_offsets);   // stream-ordered: no host wait
+        ws->residentValid = true; ws->uploadPending = true;
         return PM_OK;
     });
 }

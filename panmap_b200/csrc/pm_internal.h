@@ -89,12 +89,13 @@ struct pm_workspace {
     pm_index* idx = nullptr;
     int device = 0;   // == idx->device (kept here: a binding's garbage collector may destroy the index handle first)
     cudaStream_t st = nullptr, stCopy = nullptr;
-    cudaEvent_t ev[9]{}, evCopy[12]{}, evK[4]{};   // evK: around pack_reads / syncmers / count_seeds of the resident path
+    cudaEvent_t ev[9]{}, evCopy[33]{}, evK[4]{};   // evK: around pack_reads / syncmers / count_seeds of the resident path
     // inputs
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
     u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
     bool residentValid = false;  // the device copy of the reads was laid out by pm_reads_upload (not by the sliced pm_place path)
+    bool uploadPending = false;  // pm_reads_upload_device enqueued copies from the pinned staging arrays and did not wait
     bool hpcDone = false;        // hpc indexes: the resident reads (and qualities) were compressed in place already, endOff is valid
     // table
     DevBuf<pm::TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
@@ -139,7 +140,7 @@ void refreshView(pm_workspace* W);
 void ensureTable(pm_workspace* W, u64 wantCap);   // grows the table in use to at least wantCap slots (never shrinks it)
 PlaceOpts makeOpts(const pm_place_params& p, bool wantMetrics);
 void checkParams(const pm_place_params* p);
-void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n);
+void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n, bool fromDevice = false, const uint64_t* dOff = nullptr);
 void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* off, u64 n, const pm_place_params& prm);
 void uploadAndSeedPipelinedPacked(pm_workspace* W, const uint4* hPacked, const uint64_t* off, u64 n, const pm_place_params& prm);
 void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm);

@@ -583,6 +583,11 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
 // red.add per instance, the hot keys concentrated on few slices): those instances now stay on the SM.  Seeds that find their
 // probe window taken go to the global table directly, so the result is the same multiset of (seed, count) either way.
 constexpr int kAggSlots = 16384;
+// below this many reads per launch the flush of 148 shared-memory tables costs more than the pre-aggregation saves (tuning override: PM_AGG_MIN_READS)
+static u64 aggMinReads() {
+    static const u64 v = [] { const char* e = std::getenv("PM_AGG_MIN_READS"); return e ? (u64)std::strtoull(e, nullptr, 10) : (u64)(1u << 18); }();
+    return v;
+}
 __device__ __forceinline__ bool aggAdd(u64* __restrict__ sKey, u32* __restrict__ sCnt, u64 s, u64 m) {
     u32 i = (u32)(m >> 40) & (kAggSlots - 1);
 #pragma unroll
@@ -795,7 +800,7 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds_lane(const u64* 
 template <int KT, int LT>
 static void launchCountLane(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, TableSlot* table, u64 mask, SampleAcc* acc,
                             cudaTextureObject_t tableTex, cudaStream_t st) {
-    if (nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
+    if (nReads >= aggMinReads()) {   // whole samples and the per-rank slices of sharded ones: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
         const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
         cudaFuncSetAttribute(count_seeds_lane<KT, LT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         noteLaunch(), count_seeds_lane<KT, LT, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
@@ -810,7 +815,7 @@ static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const 
     if (k == 19 && l == 3) return launchCountLane<19, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
     if (k == 15 && l == 3) return launchCountLane<15, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
     if (l <= 1) return launchCountLane<0, 1>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
-    if (nReads >= (1u << 19)) {   // whole samples: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
+    if (nReads >= aggMinReads()) {   // whole samples and the per-rank slices of sharded ones: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
         const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
         cudaFuncSetAttribute(count_seeds<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         noteLaunch(), count_seeds<0, 0, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, k, l, table, mask, acc, tableTex);

@@ -82,6 +82,7 @@ struct pm_comm {
     DevBuf<u32> exportInfo;                    // [2] largest per-destination export count, local unique seeds
     DevBuf<u64> agree; PinBuf<u64> hAgree;     // sizing agreement before the first sample
     u32 capPair = 0, capG = 0, recX = 128;
+    u64 localCap = 0, partCap = 0;             // table slots in use while seeding the slice / while holding the partition (one allocation)
     PinBuf<u32> hT;
     cudaEvent_t ready[5]{};
     u64 nLocalReads = 0, localBases = 0;
@@ -181,7 +182,9 @@ void phase0(pm_comm* c, const pm_place_params& prm) {
     pm_workspace* W = c->ws;
     setDevice(W->idx->device);
     CK(cudaEventRecord(W->ev[0], W->st));
-    if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, c->localBases / 4));
+    if (c->localCap == 0) { c->localCap = 1 << 16; while (c->localCap < c->localBases / 4) c->localCap <<= 1; c->partCap = c->localCap; }
+    ensureTable(W, std::max(c->localCap, c->partCap));   // the allocation covers both phases; each uses its own prefix
+    W->tableCap = c->localCap;
     refreshView(W);
     CK(cudaEventRecord(W->ev[1], W->st));
     if (c->resident) stageSeed(W, true, prm);
@@ -193,6 +196,8 @@ void phase0(pm_comm* c, const pm_place_params& prm) {
 void phase1(pm_comm* c, const pm_place_params& prm) {
     pm_workspace* W = c->ws; pm_index* I = W->idx;
     setDevice(I->device);
+    W->tableCap = c->partCap;
+    refreshView(W);
     launchTableClear(W->view, W->st);
     launchPartitionImport(W->view, c->xRecv.p, (u32)c->n, c->capPair, W->st);
     launchPartitionFinalize(I->view, W->view, makeOpts(prm, false), I->homo.p, I->nSM, c->gSend.p, c->capG, c->nLocalReads, c->exportInfo.p, 0, W->st);
@@ -223,18 +228,16 @@ void phase4(pm_comm* c) {
 
 const THeader* tHdr(const pm_comm* c, int q) { return reinterpret_cast<const THeader*>(c->hT.p + (size_t)q * kTWords); }
 
-// table capacity for the next sample: the local table and the partition table share one buffer
+// table capacities for the next sample: 2-4x the entries each phase saw (the local table while seeding, the partition afterwards)
+u64 fitCap(u64 cap, u64 entries) {
+    if (entries * 10 > cap * 7 || (cap > (1u << 16) && cap > 4 * entries)) { cap = 1 << 16; while (cap < 2 * entries) cap <<= 1; }
+    return cap;
+}
 void fitTable(pm_comm* c) {
-    pm_workspace* W = c->ws;
     const THeader* h = tHdr(c, c->rank);
-    const u64 want = std::max<u64>(h->localEntries, h->partEntries);
-    W->lastEntries = want;
-    if (want * 10 > W->tableCap * 7) ensureTable(W, 2 * want);
-    else if (W->tableCap > (1u << 16) && W->tableCap > 4 * want) {
-        u64 cap = 1 << 16;
-        while (cap < 2 * want) cap <<= 1;
-        if (cap < W->tableCap) { W->tableCap = cap; refreshView(W); }
-    }
+    c->localCap = fitCap(c->localCap, h->localEntries);
+    c->partCap = fitCap(c->partCap, h->partEntries);
+    c->ws->lastEntries = std::max<u64>(h->localEntries, h->partEntries);
 }
 
 void runSharded(std::vector<pm_comm*>& cs, const pm_place_params* prm, pm_place_result* res0) {
@@ -282,7 +285,7 @@ void runSharded(std::vector<pm_comm*>& cs, const pm_place_params* prm, pm_place_
                 // a pair overflow starves the partitions: the gather counts of this attempt are too small to size from
                 if (flags & kOvfGather) c->capG = std::max<u32>(c->capG * 2, wantG);
                 if (flags & kOvfRecords) c->recX *= 4;
-                if (flags & kOvfTable) { ensureTable(c->ws, c->ws->tableCap * 4); c->ws->lastEntries = 0; }
+                if (flags & kOvfTable) { c->localCap *= 4; c->partCap *= 4; }
             }
             continue;
         }

@@ -249,6 +249,7 @@ void placeLite(PlacementResult& result, DeviceIndex& index, const std::string& r
     result.reads1Path = reads1; result.reads2Path = reads2;
     result.readUniqueSeedCount = r.read_unique_seed_count; result.totalReadSeedFrequency = r.total_read_seed_frequency;
     result.readMagnitude = r.read_magnitude;
+    result.raw = r;
     // <prefix>.placement.tsv (placement.cpp:1952-1985)
     std::ofstream out(outputPath);
     if (out.is_open()) {
@@ -366,13 +367,7 @@ extern "C" int pm_place_files(pm_index* idx, pm_workspace* ws, const char* const
         placement::PlacementResult R;
         std::string out = out_tsv ? out_tsv : "";
         placement::placeLite(R, D, reads1 ? reads1 : "", reads2 ? reads2 : "", out, tp);
-        if (res_out) {
-            const double sc[5] = {R.bestLogRawScore, R.bestLogCosineScore, R.bestContainmentScore, R.bestWeightedContainmentScore, R.bestLogContainmentScore};
-            const uint32_t ix[5] = {R.bestLogRawNodeIndex, R.bestLogCosineNodeIndex, R.bestContainmentNodeIndex, R.bestWeightedContainmentNodeIndex, R.bestLogContainmentNodeIndex};
-            for (int m = 0; m < 5; ++m) { res_out->best_score[m] = sc[m]; res_out->best_index[m] = ix[m]; }
-            res_out->total_reads = static_cast<uint64_t>(R.totalReadsProcessed); res_out->read_unique_seed_count = R.readUniqueSeedCount;
-            res_out->total_read_seed_frequency = R.totalReadSeedFrequency; res_out->read_magnitude = R.readMagnitude;
-        }
+        if (res_out) *res_out = R.raw;   // the whole C-ABI result of the sample: scores, best nodes, tie counts (pm_get_tied has the lists), statistics
         return PM_OK;
     } catch (const std::exception& e) {
         if (err && err_cap) { std::strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }

@@ -39,6 +39,7 @@ struct PlacementResult {  // placement.hpp:157-235
     size_t readUniqueSeedCount = 0;
     int64_t totalReadSeedFrequency = 0;
     double readMagnitude = 0.0;
+    pm_place_result raw{};                        // everything the C ABI returned for this sample (tie counts, seed statistics, stage times)
 };
 
 // the device index + what LiteTree::resolveNodeId needs (panmap_utils.hpp:113-118)

@@ -21,8 +21,31 @@ namespace {
 struct Gen {
     int k, s, t, l, open;
     std::string g;
-    std::map<int, u64> syn;                 // start position -> canonical syncmer hash of the current genome
-    std::unordered_map<u64, int> counts;    // seed hash -> multiplicity in the current genome
+    // syncmers of the current genome by start position (flat: the bacterial-scale workload keeps 1.5 M of them and touches them 10^8 times)
+    std::vector<u64> synHash; std::vector<uint8_t> synHas;
+    int nextSyn(int pos) const { const int G = (int)synHas.size(); while (pos < G && !synHas[pos]) ++pos; return pos < G ? pos : -1; }   // first syncmer at >= pos
+    int prevSyn(int pos) const { while (pos >= 0 && !synHas[pos]) --pos; return pos; }                                                  // last syncmer at <= pos
+    // seed hash -> multiplicity in the current genome: open addressing, no deletion (a count may return to 0 and stay)
+    struct Counts {
+        std::vector<u64> key; std::vector<int> val; std::vector<uint8_t> used; size_t n = 0, mask = 0;
+        void init(size_t cap) { size_t c = 1024; while (c < cap) c <<= 1; key.assign(c, 0); val.assign(c, 0); used.assign(c, 0); mask = c - 1; n = 0; }
+        size_t slot(u64 h) const { size_t i = (size_t)mixKey(h) & mask; while (used[i] && key[i] != h) i = (i + 1) & mask; return i; }
+        int get(u64 h) const { const size_t i = slot(h); return used[i] ? val[i] : 0; }
+        void set(u64 h, int v) {
+            size_t i = slot(h);
+            if (!used[i]) {
+                if ((n + 1) * 10 > (mask + 1) * 6) { grow(); i = slot(h); }
+                used[i] = 1; key[i] = h; ++n;
+            }
+            val[i] = v;
+        }
+        void grow() {
+            std::vector<u64> k2; std::vector<int> v2; std::vector<uint8_t> u2;
+            k2.swap(key); v2.swap(val); u2.swap(used);
+            init((mask + 1) * 2);
+            for (size_t j = 0; j < k2.size(); ++j) if (u2[j]) { const size_t i = slot(k2[j]); used[i] = 1; key[i] = k2[j]; val[i] = v2[j]; ++n; }
+        }
+    } counts;
     SeedTables T; SeederParams P; std::vector<u64> ring;
 
     void init(int k_, int s_, int t_, int l_, int open_) {
@@ -75,6 +98,7 @@ int synth_generate(uint64_t nNodes, uint64_t genomeLen, double lambda, uint64_t 
     std::mt19937_64 rg(seed + 42), rt(seed + 43), rm(seed + 44), rr(seed + 45);
     Gen G; G.init(k, s, t, l, open);
     G.g.resize(genomeLen);
+    G.synHash.assign(genomeLen, 0); G.synHas.assign(genomeLen, 0); G.counts.init(genomeLen);
     const char B[4] = {'A', 'C', 'G', 'T'};
     for (auto& c : G.g) c = B[rg() & 3];
     O.parent.assign(nNodes, 0); O.off.assign(nNodes + 1, 0);
@@ -85,9 +109,9 @@ int synth_generate(uint64_t nNodes, uint64_t genomeLen, double lambda, uint64_t 
     const uint64_t truthTarget = (uint64_t)(truthFrac * (double)(nNodes - 1));
     std::string truthGenome; bool truthFixed = false; uint32_t truthCand = 0;
 
-    auto applyCounts = [&](Undo& u, std::vector<u64>& minus, std::vector<u64>& plus, std::unordered_map<u64, int>& net) {
-        for (u64 h : minus) net[h] -= 1;
-        for (u64 h : plus) net[h] += 1;
+    auto applyCounts = [&](Undo& u, std::vector<u64>& minus, std::vector<u64>& plus, std::vector<std::pair<u64, int>>& net) {
+        for (u64 h : minus) net.push_back({h, -1});
+        for (u64 h : plus) net.push_back({h, 1});
         (void)u;
     };
 
@@ -101,23 +125,23 @@ int synth_generate(uint64_t nNodes, uint64_t genomeLen, double lambda, uint64_t 
             if (!truthFixed && truthCand == v - 1 && v - 1 >= truthTarget && p != v - 1) { truthFixed = true; O.truth = (uint32_t)(v - 1); }
             while (!stack.empty() && stack.back().node != p) {  // backtrack: undo everything below p
                 Undo& u = stack.back();
-                for (auto it = u.countOld.rbegin(); it != u.countOld.rend(); ++it) { if (it->second) G.counts[it->first] = it->second; else G.counts.erase(it->first); }
-                for (int pos : u.synAdded) G.syn.erase(pos);
-                for (auto& pr : u.synRemoved) G.syn[pr.first] = pr.second;
+                for (auto it = u.countOld.rbegin(); it != u.countOld.rend(); ++it) G.counts.set(it->first, it->second);
+                for (int pos : u.synAdded) G.synHas[pos] = 0;
+                for (auto& pr : u.synRemoved) { G.synHas[pr.first] = 1; G.synHash[pr.first] = pr.second; }
                 for (auto it = u.bases.rbegin(); it != u.bases.rend(); ++it) G.g[it->first] = it->second;
                 stack.pop_back();
             }
             O.parent[v] = p;
         }
         stack.push_back(Undo()); Undo& U = stack.back(); U.node = (uint32_t)v;
-        std::unordered_map<u64, int> net;
+        std::vector<std::pair<u64, int>> net;   // (seed, +-1) of this node; summed per seed below
         if (v == 0) {
             // root: all seeds of the genome from the empty genome
             G.syncmersIn(0, (int)genomeLen - k, tmpSyn);
             newH.clear();
-            for (auto& pr : tmpSyn) { G.syn[pr.first] = pr.second; newH.push_back(pr.second); }
+            for (auto& pr : tmpSyn) { G.synHas[pr.first] = 1; G.synHash[pr.first] = pr.second; newH.push_back(pr.second); }
             newSeeds.clear(); G.seedsOf(newH, newSeeds);
-            for (u64 h : newSeeds) net[h] += 1;
+            for (u64 h : newSeeds) net.push_back({h, 1});
         } else {
             int nm = lambda > 0 ? pois(rm) : 0;
             std::vector<int> posv;
@@ -141,10 +165,10 @@ int synth_generate(uint64_t nNodes, uint64_t genomeLen, double lambda, uint64_t 
             std::vector<Seg> segs;
             for (auto& r : rng) {
                 Seg sg{r.first, r.second, r.first, r.second};
-                auto it = G.syn.lower_bound(r.first);
-                for (int i = 0; i < fl && it != G.syn.begin(); ++i) { --it; sg.lo = it->first; }
-                it = G.syn.upper_bound(r.second);
-                for (int i = 0; i < fl && it != G.syn.end(); ++i) { sg.hi = it->first; ++it; }
+                int q = r.first;
+                for (int i = 0; i < fl; ++i) { q = G.prevSyn(q - 1); if (q < 0) break; sg.lo = q; }
+                q = r.second;
+                for (int i = 0; i < fl; ++i) { q = G.nextSyn(q + 1); if (q < 0) break; sg.hi = q; }
                 if (!segs.empty() && sg.lo <= segs.back().hi) {
                     // overlapping neighbourhoods: merge into one segment (windows between them cancel in the net diff)
                     segs.back().hi = std::max(segs.back().hi, sg.hi); segs.back().b = sg.b;
@@ -154,27 +178,31 @@ int synth_generate(uint64_t nNodes, uint64_t genomeLen, double lambda, uint64_t 
             for (auto& sg : segs) {
                 oldH.clear(); newH.clear();
                 std::vector<std::pair<int, u64>> oldIn;
-                for (auto it = G.syn.lower_bound(sg.lo); it != G.syn.end() && it->first <= sg.hi; ++it) { oldH.push_back(it->second); if (it->first >= sg.a && it->first <= sg.b) oldIn.push_back(*it); }
+                for (int q = G.nextSyn(sg.lo); q >= 0 && q <= sg.hi; q = G.nextSyn(q + 1)) { oldH.push_back(G.synHash[q]); if (q >= sg.a && q <= sg.b) oldIn.push_back({q, G.synHash[q]}); }
                 // recompute the syncmers of every window in [a,b] on the mutated genome
                 G.syncmersIn(sg.a, sg.b, tmpSyn);
-                for (auto& pr : oldIn) { G.syn.erase(pr.first); U.synRemoved.push_back(pr); }
-                for (auto& pr : tmpSyn) { G.syn[pr.first] = pr.second; U.synAdded.push_back(pr.first); }
-                for (auto it = G.syn.lower_bound(sg.lo); it != G.syn.end() && it->first <= sg.hi; ++it) newH.push_back(it->second);
+                for (auto& pr : oldIn) { G.synHas[pr.first] = 0; U.synRemoved.push_back(pr); }
+                for (auto& pr : tmpSyn) { G.synHas[pr.first] = 1; G.synHash[pr.first] = pr.second; U.synAdded.push_back(pr.first); }
+                for (int q = G.nextSyn(sg.lo); q >= 0 && q <= sg.hi; q = G.nextSyn(q + 1)) newH.push_back(G.synHash[q]);
                 oldSeeds.clear(); newSeeds.clear();
                 G.seedsOf(oldH, oldSeeds); G.seedsOf(newH, newSeeds);
                 applyCounts(U, oldSeeds, newSeeds, net);
             }
         }
         // ---- emit this node's deltas (sorted by hash) ----
+        std::sort(net.begin(), net.end());
         std::vector<std::pair<u64, int>> ch;
-        for (auto& kv : net) if (kv.second != 0) ch.push_back({kv.first, kv.second});
-        std::sort(ch.begin(), ch.end());
+        for (size_t i = 0; i < net.size();) {
+            size_t j = i; int d = 0;
+            while (j < net.size() && net[j].first == net[i].first) { d += net[j].second; ++j; }
+            if (d != 0) ch.push_back({net[i].first, d});
+            i = j;
+        }
         for (auto& c : ch) {
-            auto it = G.counts.find(c.first);
-            const int oldc = it == G.counts.end() ? 0 : it->second;
+            const int oldc = G.counts.get(c.first);
             const int newc = oldc + c.second;
             U.countOld.push_back({c.first, oldc});
-            if (newc) G.counts[c.first] = newc; else G.counts.erase(c.first);
+            G.counts.set(c.first, newc);
             O.hash.push_back(c.first); O.par.push_back((int16_t)std::min(oldc, 32767)); O.chi.push_back((int16_t)std::min(newc, 32767));
         }
         O.off[v + 1] = O.hash.size();
