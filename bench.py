@@ -367,6 +367,7 @@ def main():
         try:
             import torch
             junk = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+            ws.upload(S.reads, S.read_offsets)
             cms = 0.0
             for _ in range(args.steps):
                 junk.fill_(1); torch.cuda.synchronize()

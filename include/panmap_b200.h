@@ -171,6 +171,10 @@ int pm_get_node_metrics(pm_workspace* ws, double* out /* [n_nodes][5]: logRawNum
 int pm_last_kernel_ms(pm_workspace* ws, float* out /* [3] */);
 int pm_get_seed_table(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap); /* unsorted; returns n or <0 */
 
+/* ---- seeding::hashSeq (seeding.hpp:123, seeding.cpp:20-30) for a batch of k-mers: forward and reverse-complement hash of each sequence;
+ *      PM_ERR_INVALID ("Kmer contains non canonical base") when a sequence holds anything but ACGT/acgt, like the reference's exception ---- */
+int pm_hash_seq(int device, const char* seqs, const uint64_t* seq_offsets, uint64_t n_seqs, uint64_t* out_fwd, uint64_t* out_rev);
+
 /* ---- seeding::rollingSyncmers (seeding.cpp:47-229) for a batch of sequences, returnAll=false form:
  *      per sequence i the syncmers are written at out_*[win_offsets[i] ...] where
  *      win_offsets[i] = sum_{j<i} max(0, len_j - k + 1); out_count[i] = number of syncmers of sequence i. ---- */

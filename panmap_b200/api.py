@@ -102,6 +102,7 @@ def lib():
     L.pm_get_node_metrics.argtypes = [C.c_void_p, C.c_void_p]
     L.pm_last_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
     L.pm_get_seed_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.pm_hash_seq.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.pm_rolling_syncmers.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.pm_read_seeds.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(SeedParams), C.c_int, C.c_int,
@@ -570,6 +571,14 @@ def place_multi_resident(comms, params=None, full=True):
     res = PlaceResult()
     _ck(lib().pm_place_multi_resident(hs, len(comms), C.byref(params), C.byref(res)))
     return comms[0].ws._finish(res) if full else res
+
+
+def hash_seq(seqs, device=0):
+    """GPU seeding::hashSeq for a batch of k-mers -> (forward[], reverse[]) uint64 arrays; raises on non-ACGT like the reference"""
+    buf, off = pack_reads(seqs)
+    f = np.zeros(len(seqs), np.uint64); r = np.zeros(len(seqs), np.uint64)
+    _ck(lib().pm_hash_seq(device, _ptr(buf), off.ctypes.data_as(C.c_void_p), len(seqs), f.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p)))
+    return f, r
 
 
 def rolling_syncmers(seqs, k, s, open=False, t=0, device=0):

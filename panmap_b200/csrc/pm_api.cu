@@ -214,6 +214,9 @@ static unsigned char* prepareDedup(pm_workspace* W, u64 n, const pm_place_params
 // slice schedule of the host-buffer pipelines: cumulative fractions of the reads (tuning override: PM_SLICES_ASCII / PM_SLICES_PACKED =
 // comma-separated cumulative cut points ending in 1)
 struct SliceSchedule { int n; double cut[33]; };
+// below ~1 ms of PCIe time the per-slice launches cost more than the overlap returns (PM_SLICE_MIN_BYTES overrides, read per call: tests use it
+// to drive small samples through the sliced path)
+static u64 sliceMinBytes() { const char* e = std::getenv("PM_SLICE_MIN_BYTES"); return e ? (u64)std::strtoull(e, nullptr, 10) : (48ull << 20); }
 static SliceSchedule scheduleFromEnv(const char* var, std::initializer_list<double> dflt) {
     SliceSchedule s{0, {0.0}};
     std::vector<double> v(dflt);
@@ -236,7 +239,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     // everything after the last copy (its seeding, then scoring and selection) is exposed latency.
     static const SliceSchedule sched = scheduleFromEnv("PM_SLICES_ASCII", {0.03, 0.09, 0.21, 0.40, 0.58, 0.73, 0.84, 0.91, 0.96, 1.0});
     const double* kCut = sched.cut;
-    const int nSlices = n >= (1u << 16) ? sched.n : 1;
+    const int nSlices = total >= sliceMinBytes() ? sched.n : 1;   // small samples: one copy, one set of launches
     W->nReads = n; W->totalBases = total;
     W->hPackedOff.ensure(n + 1); W->hBlockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 32);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
@@ -299,7 +302,7 @@ void uploadAndSeedPipelinedPacked(pm_workspace* W, const uint4* hPacked, const u
     const u64 total = n ? off[n] : 0;
     static const SliceSchedule sched = scheduleFromEnv("PM_SLICES_PACKED", {0.03, 0.09, 0.21, 0.40, 0.58, 0.73, 0.84, 0.91, 0.96, 1.0});
     const double* kCut = sched.cut;
-    const int nSlices = n >= (1u << 16) ? sched.n : 1;
+    const int nSlices = total >= sliceMinBytes() ? sched.n : 1;
     W->nReads = n; W->totalBases = total;
     W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
     W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1);
@@ -800,6 +803,29 @@ static int seedListImpl(int device, const char* seqs, const uint64_t* off, uint6
         if (n) CK(cudaMemcpyAsync(outCount, dCount.p, n * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         cudaStreamDestroy(st);
+        return PM_OK;
+    });
+}
+// seeding::hashSeq for a batch (seeding.cpp:20-30); a sequence with a non-ACGT base makes the call fail like the reference's std::invalid_argument
+int pm_hash_seq(int device, const char* seqs, const uint64_t* seq_offsets, uint64_t n_seqs, uint64_t* out_fwd, uint64_t* out_rev) {
+    if (!seq_offsets || (!seqs && n_seqs) || !out_fwd || !out_rev) return fail(PM_ERR_INVALID, "null argument");
+    if (deviceCountNoThrow() <= device || device < 0) return fail(PM_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");
+    return guarded([&]() -> int {
+        setDevice(device);
+        const u64 total = n_seqs ? seq_offsets[n_seqs] : 0;
+        DevBuf<char> dS; DevBuf<u64> dO, dF, dR; DevBuf<unsigned char> dB;
+        dS.alloc(total + 1); dO.alloc(n_seqs + 1); dF.alloc(n_seqs + 1); dR.alloc(n_seqs + 1); dB.alloc(n_seqs + 1);
+        if (total) CK(cudaMemcpy(dS.p, seqs, total, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dO.p, seq_offsets, (n_seqs + 1) * 8, cudaMemcpyHostToDevice));
+        launchHashSeq(dS.p, dO.p, n_seqs, dF.p, dR.p, dB.p, 0);
+        CK(cudaGetLastError());
+        std::vector<unsigned char> bad(n_seqs + 1);
+        if (n_seqs) {
+            CK(cudaMemcpy(out_fwd, dF.p, n_seqs * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(out_rev, dR.p, n_seqs * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(bad.data(), dB.p, n_seqs, cudaMemcpyDeviceToHost));
+        }
+        for (u64 i = 0; i < n_seqs; ++i) if (bad[i]) throw std::invalid_argument("Kmer contains non canonical base");
         return PM_OK;
     });
 }

@@ -809,8 +809,19 @@ static void launchCountLane(const u64* synBuf, const unsigned* synCount, const u
         noteLaunch(), count_seeds_lane<KT, LT, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
     }
 }
+template <int MODE>
+static void launchSeedsFromSyncmers(const u64* synBuf, const unsigned* synCount, const u64* packedOff, const u64* winOff, u64 nReads, int k, int l,
+                                    TableSlot* table, u64 mask, SampleAcc* acc, u64* outHash, u64* outCount, cudaTextureObject_t tableTex, cudaStream_t st);
+// launches below this many reads (slices of the host-buffer pipeline, per-rank slices of sharded samples) give the lane-per-read kernels at most
+// one group of 32 reads per resident warp: a single wave of long dependent chains.  There the warp-per-read kernel (lanes over the seeds of
+// one read, every chain one probe long) is faster.  Tuning override: PM_COUNT_WARP_BELOW
+static u64 countWarpBelow() {
+    static const u64 v = [] { const char* e = std::getenv("PM_COUNT_WARP_BELOW"); return e ? (u64)std::strtoull(e, nullptr, 10) : (u64)200000; }();   // measured: 125 k reads 90 vs 107 us, 250 k equal, 500 k+ slower
+    return v;
+}
 static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, TableSlot* table, u64 mask,
                              SampleAcc* acc, cudaTextureObject_t tableTex, cudaStream_t st) {
+    if (nReads < countWarpBelow()) return launchSeedsFromSyncmers<0>(synBuf, synCount, packedOff, nullptr, nReads, k, l, table, mask, acc, nullptr, nullptr, tableTex, st);
     // panmap's parameter sets (l = 3 with k = 19 / 15, and l <= 1) use the lane-per-read kernel; any other (k, l) the flat one below
     if (k == 19 && l == 3) return launchCountLane<19, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
     if (k == 15 && l == 3) return launchCountLane<15, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);

@@ -195,6 +195,7 @@ void launchChainGathered(WorkspaceView W, const uint4* rRecv, u32 nRanks, u32 re
 void launchTiesPack(WorkspaceView W, u32* tSend, const uint2* gSend, const u32* exportInfo /* [2] from launchPartitionExport */, cudaStream_t st);
 void launchTiesFullPack(WorkspaceView W, u32* out /* [5][capT] */, u32 capT, cudaStream_t st);
 void launchResetGathered(DevIndexView I, WorkspaceView W, const uint2* gRecv, u32 nRanks, u32 capG, cudaStream_t st);
+void launchHashSeq(const char* seqs, const u64* off, u64 n, u64* fwd, u64* rev, unsigned char* status, cudaStream_t st);
 // pieces of launchFinalize the sharded path runs on their own
 void launchTableScan(WorkspaceView W, const u64* homo, int nSM, unsigned* nPartsOut, cudaStream_t st);
 void launchRootAndScalars(DevIndexView I, WorkspaceView W, PlaceOpts O, unsigned nFinParts, cudaStream_t st);

@@ -377,4 +377,27 @@ __global__ void __launch_bounds__(256) ties_full_pack(WorkspaceView W, u32* __re
 }
 void launchTiesFullPack(WorkspaceView W, u32* out, u32 capT, cudaStream_t st) { noteLaunch(), ties_full_pack<<<dim3(64, 5), 256, 0, st>>>(W, out, capT); }
 
+
+// ------------------------------------------------------------------------------------------------------
+// seeding::hashSeq (seeding.cpp:20-30) for a batch of k-mers: f = XOR_i rol(c(b_i), k-1-i), r = XOR_i rol(c(comp b_{k-1-i}), k-1-i),
+// rotations taken modulo 64 like the reference's rol.  One thread per sequence; status 1 = "Kmer contains non canonical base".
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hash_seq(const char* __restrict__ seqs, const u64* __restrict__ off, u64 n, u64* __restrict__ fwd, u64* __restrict__ rev,
+                                                unsigned char* __restrict__ status) {
+    for (u64 q = (u64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (u64)gridDim.x * blockDim.x) {
+        const u64 b = off[q], k = off[q + 1] - b;
+        u64 f = 0, r = 0; bool bad = false;
+        for (u64 i = 0; i < k; ++i) {
+            const unsigned ci = baseCode((unsigned char)seqs[b + i]), cj = baseCode((unsigned char)seqs[b + k - 1 - i]);
+            bad = bad || ci >= 4;
+            f ^= rol64(codeHash(ci), (unsigned)((k - i - 1) & 63));
+            r ^= rol64(cj < 4 ? codeHash(3 - cj) : 0ULL, (unsigned)((k - i - 1) & 63));
+        }
+        fwd[q] = f; rev[q] = r; status[q] = bad ? 1 : 0;
+    }
+}
+void launchHashSeq(const char* seqs, const u64* off, u64 n, u64* fwd, u64* rev, unsigned char* status, cudaStream_t st) {
+    if (n) noteLaunch(), hash_seq<<<streamGrid(n, 1), 256, 0, st>>>(seqs, off, n, fwd, rev, status);
+}
+
 }  // namespace pm

@@ -95,7 +95,11 @@ def test_place_dedup_counts_every_distinct_read_string_once():
     reads = [reads[i] for i in order]
     _place_and_check(idx, reads, pm.PlaceParams(dedup_reads=1), dedup=True)
     big = [base[i % 300] for i in range(70000)] + H.random_reads(rng, 500)
-    _place_and_check(idx, big, pm.PlaceParams(dedup_reads=1), dedup=True)
+    os.environ["PM_SLICE_MIN_BYTES"] = "1000000"          # the sliced host-buffer pipeline (normally samples >= 48 MB): the read set spans slices
+    try:
+        _place_and_check(idx, big, pm.PlaceParams(dedup_reads=1), dedup=True)
+    finally:
+        del os.environ["PM_SLICE_MIN_BYTES"]
 
 
 @pytest.mark.parametrize("frac", [0.0004, 0.013, 0.2, 0.77, 1.0])
@@ -325,10 +329,15 @@ def test_place_packed_reads_equal_ascii_reads(k, s, t, l, op, ts, te):
     base = H.random_reads(rng, 500, lo=0, hi=260, p_n=0.02, p_lower=0.05)
     for reads in (base, [base[i % 500] for i in range(70000)]):
         buf, off = pm.pack_reads(reads)
-        a = ws.place(buf, off, prm)
-        ta = ws.seed_table()
-        b = ws.place_packed(pm.host_pack_reads(buf, off), off, prm)
-        tb = ws.seed_table()
+        if len(reads) > 500:
+            os.environ["PM_SLICE_MIN_BYTES"] = "1000000"  # the sliced pipeline (normally samples >= 48 MB)
+        try:
+            a = ws.place(buf, off, prm)
+            ta = ws.seed_table()
+            b = ws.place_packed(pm.host_pack_reads(buf, off), off, prm)
+            tb = ws.seed_table()
+        finally:
+            os.environ.pop("PM_SLICE_MIN_BYTES", None)
         assert np.array_equal(ta[0], tb[0]) and np.array_equal(ta[1], tb[1])
         assert a.raw.unique_seeds == b.raw.unique_seeds and a.raw.read_magnitude == b.raw.read_magnitude
         assert all(a.best_index[m] == b.best_index[m] and a.best_score[m] == b.best_score[m] and np.array_equal(a.tied[m], b.tied[m]) for m in pm.METRICS)
@@ -600,3 +609,16 @@ def test_full_size_sample_matches_oracle_and_is_shard_and_call_invariant():
         got[b:e] = w2.node_scores()[b:e]
         del w2, ix
     assert np.array_equal(got, sc)
+
+
+def test_hash_seq_matches_oracle_and_rejects_non_acgt():
+    """seeding::hashSeq (seeding.cpp:20-30) on the GPU for a batch of k-mers of every length 1..40 (rotations wrap at 64 like the reference's)"""
+    rng = np.random.default_rng(77)
+    seqs = [bytes(rng.choice(np.frombuffer(b"ACGTacgt", np.uint8), size=n)) for n in list(range(1, 41)) * 3] + [b"A" * 70, b"ACGT" * 33]
+    f, r = pm.hash_seq(seqs)
+    for s, a, b in zip(seqs, f, r):
+        assert (int(a), int(b)) == cpu.hash_seq(s), s
+    with pytest.raises(pm.PanmapError, match="non canonical base"):
+        pm.hash_seq([b"ACGT", b"ACNT"])
+    f, r = pm.hash_seq([])
+    assert f.size == 0
