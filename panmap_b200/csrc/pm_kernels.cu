@@ -1173,20 +1173,6 @@ __global__ void __launch_bounds__(256) root_denominator(DevIndexView I, Workspac
 // read counts: while the running sum is in binade [2^e, 2^(e+1)) every addition of x is rounded to a multiple of
 // u = 2^(e-52), i.e. contributes rint(x/u)*u - x, and a fraction (hi-lo)/T of the additions happens in that binade.
 // Adding it to the exact fixed-point sum reproduces the reference's value to ~1e-14 relative.
-constexpr int kBinades = 10;  // each lower binade carries 1/4 of the drift of the one above it
-struct Binades { double fr[kBinades], u[kBinades], iu[kBinades]; };
-__device__ __forceinline__ void makeBinades(double T, Binades& B) {
-    const int eTop = (int)((dblBits(T) >> 52) & 0x7FF) - 1023;
-#pragma unroll
-    for (int j = 0; j < kBinades; ++j) {   // share of the additions that land in each binade, its ulp and 1/ulp
-        const int ex = eTop - j;
-        const double lo = j == kBinades - 1 ? 0.0 : bitsDbl((u64)(ex + 1023) << 52);
-        const double hi = fmin(T, bitsDbl((u64)(ex + 1024) << 52));
-        B.fr[j] = (hi - lo) / T;
-        B.u[j] = bitsDbl((u64)(ex - 52 + 1023) << 52);
-        B.iu[j] = bitsDbl((u64)(52 - ex + 1023) << 52);
-    }
-}
 __device__ __forceinline__ double blockSumF64(double e, double* sRed) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) e += shflXorF64(e, d);
@@ -1248,14 +1234,8 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
         for (int c = threadIdx.x; c <= cMax; c += blockDim.x) {
             const unsigned mult = W.countHist[c];
             if (!mult) continue;
-            const double x = I.log1pLut[c], x2 = x * x;
-            double am = 0.0, al = 0.0;
-#pragma unroll
-            for (int j = 0; j < kBinades; ++j) {
-                am += BM.fr[j] * (rint(x2 * BM.iu[j]) * BM.u[j] - x2);
-                al += BL.fr[j] * (rint(x * BL.iu[j]) * BL.u[j] - x);
-            }
-            eMag += am * (double)mult; eLog += al * (double)mult;
+            const double x = I.log1pLut[c];
+            eMag += driftOf(BM, x * x) * (double)mult; eLog += driftOf(BL, x) * (double)mult;
         }
     }
     const double dMag = blockSumF64(eMag, sRed);

@@ -10,6 +10,7 @@
 //   placement.cpp:242-345     per-delta contributions of computeChildMetrics
 //   placement.hpp:120-149     the five score getters
 #pragma once
+#include <math.h>
 #include <stddef.h>
 #include <stdint.h>
 
@@ -270,6 +271,29 @@ PM_HD double fxToDouble(fx128 a) {  // round-to-nearest-even of the exact value
     const u64 bits = ((u64)(e2 + 52 + 1023) << 52) | (mant & 0xFFFFFFFFFFFFFULL);
     const double d = bitsDbl(bits);
     return neg ? -d : d;
+}
+
+// ---- expected rounding drift of a sequential f64 sum (finish_scalars; see the comment there) ----------
+// While the running sum is in binade [2^e, 2^(e+1)) every addition of x is rounded to a multiple of u = 2^(e-52), i.e. contributes
+// rint(x/u)*u - x, and (for addends in random order) a share (hi-lo)/T of the additions happens in that binade.
+constexpr int kBinades = 10;  // each lower binade carries 1/4 of the drift of the one above it
+struct Binades { double fr[kBinades], u[kBinades], iu[kBinades]; };
+PM_HD void makeBinades(double T, Binades& B) {   // T = the exact total
+    const int eTop = (int)((dblBits(T) >> 52) & 0x7FF) - 1023;
+    for (int j = 0; j < kBinades; ++j) {   // share of the additions that land in each binade, its ulp and 1/ulp
+        const int ex = eTop - j;
+        const double lo = j == kBinades - 1 ? 0.0 : bitsDbl((u64)(ex + 1023) << 52);
+        const double top = bitsDbl((u64)(ex + 1024) << 52);
+        const double hi = T < top ? T : top;
+        B.fr[j] = (hi - lo) / T;
+        B.u[j] = bitsDbl((u64)(ex - 52 + 1023) << 52);
+        B.iu[j] = bitsDbl((u64)(52 - ex + 1023) << 52);
+    }
+}
+PM_HD double driftOf(const Binades& B, double x) {   // expected drift contributed by ONE addition of x
+    double a = 0.0;
+    for (int j = 0; j < kBinades; ++j) a += B.fr[j] * (rint(x * B.iu[j]) * B.u[j] - x);
+    return a;
 }
 
 // ---- per-node numerators from the two accumulator families --------------------------------------------

@@ -49,6 +49,26 @@ void hc_gathered_sums(const uint32_t* cnt, int64_t n, uint64_t n1, double* out) 
     out[0] = fxToDouble(m); out[1] = fxToDouble(l);
 }
 
+// the device's read-magnitude scalars on the host: exact fixed-point sums of log1p(count) and its square over the kept counts plus the
+// expected sequential-summation drift from the count histogram (finish_scalars); out: sum log1p^2, sum log1p -- both WITH the drift term
+void hc_magnitude_model(const uint32_t* cnt, int64_t n, double* out) {
+    fx128 m = fxZero(), l = fxZero();
+    std::vector<uint32_t> sorted(cnt, cnt + n);
+    std::sort(sorted.begin(), sorted.end());
+    for (int64_t i = 0; i < n; ++i) { const double x = std::log1p((double)cnt[i]); m = fxAdd(m, fxFromDouble(x * x)); l = fxAdd(l, fxFromDouble(x)); }
+    const double M = fxToDouble(m), L = fxToDouble(l);
+    double dM = 0.0, dL = 0.0;
+    if (M > 0.0 && L > 0.0) {
+        Binades BM, BL; makeBinades(M, BM); makeBinades(L, BL);
+        for (int64_t i = 0; i < n;) {
+            int64_t j = i; while (j < n && sorted[j] == sorted[i]) ++j;
+            if (sorted[i] < 65536u) { const double x = std::log1p((double)sorted[i]); dM += driftOf(BM, x * x) * (double)(j - i); dL += driftOf(BL, x) * (double)(j - i); }
+            i = j;
+        }
+    }
+    out[0] = M + dM; out[1] = L + dL;
+}
+
 double hc_fx_roundtrip(double x) { return fxToDouble(fxFromDouble(x)); }
 // exact sum of doubles through the fixed-point accumulator, in the given order and in reverse: both must agree
 int hc_fx_sum(const double* x, int64_t n, double* fwd, double* rev) {
