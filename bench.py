@@ -721,8 +721,8 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
         batch = {"error": str(e)}; same = None
     if rank == 0:
         value = nodes_reads / (per * 1e-3)
-        names = ["setup", "table setup", "seeding of the read slice + partition export", "exchange + partition finalize + all-gather + gathered finalize",
-                 "node_deltas (own node range)", "prefix_scores", "records all-gather + chain + ties + ties all-gather", "d2h + reset"]
+        names = ["table setup", "seeding of the read slice + partition export", "all-to-all + partition import/finalize + pairs all-gather + gathered finalize",
+                 "node_deltas (own node range)", "prefix_scores", "records + records all-gather + chain + ties", "tie heads all-gather + d2h + reset"]
         line = {"metric": "placement nodes x reads scored per second", "value": value, "unit": "node*reads/s", "n_gpus": world, "steps": steps,
                 "warmup": warm, "ms_per_step": per, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64+f64",
                 "data": "synthetic",
