@@ -100,8 +100,8 @@ static int createIndex(const pm_index_desc* desc, int device, uint32_t shard, ui
             I->log1pLut.upload(lut); I->log1pSmall.upload(small);
             std::vector<u64> homo(F.homo, F.homo + 4);
             I->homo.upload(homo);
-            std::vector<SeedTables> st(1);
-            buildSeedTables(st[0], F.sp.k, F.sp.s);
+            std::vector<SeedTables> st(kSeedTableElems);   // + the s = 8 rank table behind element 0 (syncmers_rank)
+            buildSeedTableImage(st.data(), F.sp.k, F.sp.s);
             I->seedTables.upload(st);
         }
         I->gMagSqHost = F.gMagSq; I->gUniqueHost = F.gUnique;
@@ -785,8 +785,8 @@ static int seedListImpl(int device, const char* seqs, const uint64_t* off, uint6
         CK(cudaMemcpyAsync(dOff.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dPOff.p, pOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(dWOff.p, wOff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-        std::vector<SeedTables> T(1); buildSeedTables(T[0], sp->k, sp->s);
-        dT.alloc(1); CK(cudaMemcpyAsync(dT.p, T.data(), sizeof(SeedTables), cudaMemcpyHostToDevice, st));
+        std::vector<SeedTables> T(kSeedTableElems); buildSeedTableImage(T.data(), sp->k, sp->s);
+        dT.alloc(kSeedTableElems); CK(cudaMemcpyAsync(dT.p, T.data(), kSeedTableElems * sizeof(SeedTables), cudaMemcpyHostToDevice, st));
         const SeederParams P = makeSeederParams(sp->k, sp->s, sp->t, sp->l, sp->open, trimStart, trimEnd);
         std::vector<u32> bf((ch + 255) / 256 + 1);
         packBlockFirst(pOff.data(), n, ch, bf.data());

@@ -508,6 +508,164 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
     }
 }
 
+// ---- syncmers_rank: the s = 8 closed-syncmer kernel on hash RANKS (pm_logic.cuh "closed syncmers with s = 8 by RANK") -------------
+// Same output as syncmers_fast<K, 8>, about half the integer work per base: the two rolling s-mer hashes and their 64-bit sliding
+// minima are replaced by two look-ups in a 128 KB rank table in shared memory (brought in by one TMA bulk copy per block while the
+// warps set up their reads) and a sliding minimum over both strands' ranks at once (one VIMNMX.U16x2 per comparison, which also
+// returns the two per-strand "<=" predicates).  The rolling k-mer hashes -- the values that are reported -- are unchanged.
+// One persistent block per SM (the table takes 128 of its 227 KB of shared memory).
+constexpr int kRankThreads = 512;
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int K, bool ASCII, bool NOTRIM>
+__global__ void __launch_bounds__(kRankThreads, 1) syncmers_rank(const uint4* __restrict__ packed, const u64* __restrict__ off,
+                                                                 const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
+                                                                 const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
+                                                                 unsigned* __restrict__ synCount, const unsigned char* __restrict__ dup,
+                                                                 const u64* __restrict__ endOff, const char* __restrict__ reads) {
+    constexpr int S = kRankS, W = K - S + 1;
+    static_assert(K >= 12 && K <= 20 && W % 4 == 0 && W <= 12, "word history holds 20 bases; the block length must be a multiple of 4");
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    unsigned char* sRank = smemRaw;                                              // u16[65536]
+    u64* sPair = reinterpret_cast<u64*>(smemRaw + kRankEntries * 2);             // [2][kPairStride]: fk, rk (outgoing, incoming) pair tables
+    unsigned char* sLut = smemRaw + kRankEntries * 2 + 2 * kPairStride * 8;      // ASCII -> base code
+    __shared__ __align__(8) unsigned long long sBar;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&sBar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sLut[i] = (unsigned char)baseCode((unsigned char)i);
+        if (i < 128) {
+            const int tb = i >> 6, o = (i >> 3) & 7, nw = i & 7;
+            sPair[tb * kPairStride + o * 12 + nw] = tb == 0 ? gT->fwdOldK[o] ^ gT->fwdNew[nw] : gT->revOld[o] ^ gT->revNewK[nw];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {   // the rank table sits right behind the SeedTables (pm_api.cu: seedTableBlob): four 32 KB bulk copies, one barrier
+        const unsigned bar = smemAddr(&sBar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kRankEntries * 2u) : "memory");
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(gT + 1);
+#pragma unroll
+        for (unsigned c = 0; c < 4; ++c)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(sRank + c * 32768u)),
+                         "l"(src + c * 32768u), "r"(32768u), "r"(bar)
+                         : "memory");
+    }
+    bool tableReady = false;
+    RankWindow<W> win;
+    const unsigned lane = threadIdx.x & 31u;
+    const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    const u64 warpId = (u64)(threadIdx.x >> 5) * gridDim.x + blockIdx.x;   // consecutive groups of 32 reads go to different SMs
+    for (u64 r0 = warpId * 32; r0 < nReads; r0 += warpsTotal * 32) {
+        const u64 r = r0 + lane;
+        const bool valid = r < nReads;
+        const u64 b = valid ? off[r] : 0;
+        int L = valid ? (int)((endOff ? endOff[r] : off[r + 1]) - b) : 0;
+        if (L < K) L = 0;
+        if (dup && valid && dup[r]) L = 0;   // --dedup: a byte-identical read was seen before
+        const u64 pOff = valid ? packedOff[r] : 0;
+        const uint4* __restrict__ src = packed + pOff;
+        const char* rbase = ASCII ? reads + (b & ~3ULL) : nullptr;   // 4-byte aligned base of the read, rshift = its misalignment
+        const unsigned rshift = (unsigned)(b & 3ULL);
+        u64* __restrict__ dst = synBuf + pOff * 32;
+        int maxL = L, minL = L;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, d)); minL = min(minL, __shfl_xor_sync(0xffffffffu, minL, d)); }
+        if (!tableReady) {   // first group of the warp: everything above overlapped the bulk copy
+            unsigned ok;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smemAddr(&sBar)) : "memory");
+            } while (!ok);
+            tableReady = true;
+        }
+
+        u64 fk = 0, rk = 0;
+        unsigned HF = 0, HR = 0, cnt = 0;
+        // the bases travel as one code byte each, four to a word: cur = bases 4n .. 4n+3, hN = the word N words back ("ambiguous"
+        // before the read); combK holds 12 * outgoing + incoming for the four positions of the current word
+        unsigned cur = 0x04040404u, h1 = 0x04040404u, h2 = 0x04040404u, h3 = 0x04040404u, h4 = 0x04040404u, h5 = 0x04040404u;
+        unsigned combK = 0;
+        bool ambWord = false;
+        uint4 v4 = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        int iLo = P.trimStart + K - 1;           // a window ending at base i is reported iff iLo <= i <= iHi:
+        const int iHi = L - P.trimEnd - 1;       //   complete, inside the trimmed range, no ambiguous base in it (iLo moves past those)
+        win.reset();
+
+        // base i enters: the k-mer's rolling hashes on both strands (seeding.cpp:147-195) and, once per word, the 2-bit histories the
+        // s-mer ranks are looked up with.  ph = i & 3 is a compile-time constant inside the unrolled block.
+        auto fetchRoll = [&](int i, int ph, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+            if (ph == 0) {   // next four bases
+                h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = cur;
+                if (ASCII) {
+                    if (FULL || i < L) {   // 4 bytes from an arbitrary byte address: two aligned words, one funnel shift, four table look-ups
+                        const unsigned a = rshift + (unsigned)i;
+                        const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + (a & ~3u));
+                        const unsigned x0 = __ldg(wp), x1 = __ldg(wp + 1);
+                        const unsigned bts = __funnelshift_r(x0, x1, (a & 3u) * 8u);
+                        unsigned cw = sLut[bts >> 24];
+                        cw = cw * 256u + sLut[(bts >> 16) & 0xFFu];
+                        cw = cw * 256u + sLut[(bts >> 8) & 0xFFu];
+                        cw = cw * 256u + sLut[bts & 0xFFu];
+                        cur = cw;
+                    }
+                } else {   // 4-bit codes from `packed`: spread four nibbles to bytes
+                    if ((i & 31) == 0) { if (FULL || i < L) v4 = src[i >> 5]; }
+                    const int wsel = (i >> 3) & 3;
+                    const unsigned w32 = wsel == 0 ? v4.x : wsel == 1 ? v4.y : wsel == 2 ? v4.z : v4.w;
+                    const unsigned n16 = (w32 >> (16 * ((i >> 2) & 1))) & 0xFFFFu;
+                    cur = (((n16 & 0xF000u) << 12) | ((n16 & 0x0F00u) << 8) | ((n16 & 0x00F0u) << 4) | (n16 & 0x000Fu)) & 0x07070707u;
+                }
+                constexpr int KA = K / 4, KB = K % 4;
+                const unsigned hist[7] = {cur, h1, h2, h3, h4, h5, 0x04040404u};
+                // byte j of the lag word = base 4n + j - K: four consecutive bytes of (hist[KA+1], hist[KA]) starting at byte 4 - KB
+                constexpr unsigned selK = (4 - KB) | ((5 - KB) << 4) | ((6 - KB) << 8) | ((7 - KB) << 12);
+                const unsigned lagK = KB ? __byte_perm(hist[KA + 1], hist[KA], selK) : hist[KA];
+                combK = lagK * 12u + cur;   // bytewise: codes are <= 7, 12 * 7 + 7 < 256
+                rankPushWord(cur, HF, HR);
+                ambWord = (cur & 0x04040404u) != 0u;   // rare: the per-base test below hangs off this one predicate
+            }
+            if (FULL || i < L) {
+                const unsigned pk = __byte_perm(combK, 0u, 0x4440u + (unsigned)ph);
+                fk = rol1(fk) ^ sPair[pk];
+                rk = ror1(rk) ^ sPair[kPairStride + pk];
+                if (ambWord) { if (cur & (0x04u << (8 * ph))) iLo = max(iLo, i + K); }   // codes >= 4 are ambiguous
+            }
+        };
+        // prologue: the first S-1 bases only feed the rolling hashes and the histories
+#pragma unroll 1
+        for (int i = 0; i < S - 1 && i < maxL; ++i) fetchRoll(i, i & 3, std::false_type{});
+        // one block of W s-mers; s-mer index q = i - (S-1), slot j = q mod W
+        auto block = [&](int q0, auto full) {
+            constexpr bool FULL = decltype(full)::value;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const int i = q0 + j + S - 1;
+                if (FULL || i < maxL) {   // warp-uniform
+                    const int ph = (j + S - 1) & 3;   // q0 is a multiple of W, W of 4
+                    fetchRoll(i, ph, full);
+                    if (FULL || i < L) {
+                        const unsigned rf = *reinterpret_cast<const unsigned short*>(sRank + rankAddrF(HF, ph));
+                        const unsigned rr = *reinterpret_cast<const unsigned short*>(sRank + rankAddrR(HR, ph));
+                        const bool syn = win.step(j, __byte_perm(rf, rr, 0x5410u));
+                        if (syn && i >= iLo && (NOTRIM || i <= iHi) && fk != rk) {
+                            dst[cnt] = umin64(fk, rk);
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        };
+        // main loop: blocks that lie inside every lane's read take the copy without the per-base length tests
+#pragma unroll 1
+        for (int q0 = 0; q0 + S - 1 < maxL; q0 += W) {
+            if (q0 + W + S - 1 <= minL) block(q0, std::true_type{});
+            else block(q0, std::false_type{});
+        }
+        if (valid) synCount[r] = cnt;
+    }
+}
+
 // placement.cpp:1625-1682: one warp per read; lane j builds the k-min-mer of syncmers j..j+l-1 in closed form
 //   Fw = XOR_w rol(h[j+w], k*(l-1-w)),  Rw = XOR_w rol(h[j+w], k*w),  seed = min(Fw,Rw) unless Fw == Rw     (l > 1)
 //   seed = h[j]                                                                                                 (l <= 1)
@@ -857,9 +1015,33 @@ static unsigned seedGrid(u64 nReads) {
     if (g > 148ull * 16) g = 148ull * 16;
     return (unsigned)(g ? g : 1);
 }
+// launches with at least this many reads take syncmers_rank (its blocks each bring the 128 KB rank table in: not worth it for small slices).
+// Tuning override: PM_RANK_MIN_READS (0 = always, huge = never)
+static u64 rankMinReads() {
+    static const u64 v = [] { const char* e = std::getenv("PM_RANK_MIN_READS"); return e ? (u64)std::strtoull(e, nullptr, 10) : (u64)20000; }();
+    return v;
+}
+template <int K>
+static void launchRank(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
+                       u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
+    const size_t sm = (size_t)kRankEntries * 2 + 2 * kPairStride * sizeof(u64) + 256;
+    u64 g = (nReads + kRankThreads - 1) / kRankThreads; if (g > 148) g = 148;
+    const unsigned grid = (unsigned)(g ? g : 1);
+#define PM_RANK_LAUNCH(A, N)                                                                                                        \
+    do {                                                                                                                            \
+        cudaFuncSetAttribute(syncmers_rank<K, A, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                         \
+        noteLaunch(), syncmers_rank<K, A, N><<<grid, kRankThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads); \
+    } while (0)
+    if (reads && P.trimEnd == 0) PM_RANK_LAUNCH(true, true);
+    else if (reads) PM_RANK_LAUNCH(true, false);
+    else if (P.trimEnd == 0) PM_RANK_LAUNCH(false, true);
+    else PM_RANK_LAUNCH(false, false);
+#undef PM_RANK_LAUNCH
+}
 template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
                        u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
+    if (S == kRankS && nReads >= rankMinReads()) return launchRank<K>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads, st);
     const size_t sm = sizeof(SeedTables) + 256 + 4 * kPairStride * sizeof(u64);
     if (reads && P.trimEnd == 0)
         noteLaunch(), syncmers_fast<K, S, true, true><<<seedGrid(nReads), kSeedThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);

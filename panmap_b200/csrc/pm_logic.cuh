@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define PM_HD __host__ __device__ __forceinline__
@@ -72,6 +73,9 @@ inline void buildSeedTables(SeedTables& T, int k, int s) {
         T.revOld[c] = ror64(r, 1);
     }
 }
+
+// device image of the tables: element 0 = the SeedTables, the elements behind it hold the s = 8 rank table (syncmers_rank; zeros for s != 8)
+constexpr size_t kSeedTableElems = 1 + ((size_t)(1u << 16) * 2 + sizeof(SeedTables) - 1) / sizeof(SeedTables);
 
 struct SeederParams {
     int k, s, t, l, open;
@@ -188,6 +192,102 @@ struct ReadSeederT {
     }
 };
 PM_HD int seederRingWords(int k, int s, int l) { return 4 * (k - s + 1) + (l > 1 ? l : 1); }
+
+// ---- closed syncmers with s = 8 by RANK (syncmers_rank kernel; seeding.cpp:147-226) --------------------------------------------
+// Whether a k-mer is a closed syncmer depends only on the ORDER of its s-mer hashes (does the oldest or the newest of the k-s+1 s-mers
+// attain the window minimum), never on their values.  For s = 8 there are 4^8 = 65,536 s-mers without an ambiguous base, so the order is
+// a table: rank[idx] = dense rank of the forward hash of the 8-mer idx (first base in the two top bits) among all 8-mer hashes -- equal
+// hashes get equal ranks, so every <= / == the reference evaluates on 64-bit hashes gives the same answer on 16-bit ranks.  The reverse
+// strand needs no second table: the reverse hash of an s-mer IS the forward hash of its reverse complement (XOR_i rol(c(comp b_i), i)),
+// so its rank is rank[index of the reverse complement].  s-mers that contain an ambiguous base have no rank; every k-mer window that
+// holds one is rejected anyway (seeding.cpp: the window must be free of ambiguous bases), and a window's test only looks at its own s-mers.
+// Both strands' ranks travel in one 32-bit word (forward low, reverse high): one 16x2 minimum instruction (VIMNMX.U16x2 on sm_90+,
+// which also returns the two "a <= b" predicates) serves both strands.
+constexpr int kRankS = 8;
+constexpr unsigned kRankEntries = 1u << (2 * kRankS);
+inline void buildSmerRanks(uint16_t* rank) {   // host, once per index: 65,536 hashes, sort, dense rank
+    struct E { u64 h; unsigned idx; };
+    E* e = new E[kRankEntries];
+    for (unsigned idx = 0; idx < kRankEntries; ++idx) {
+        u64 h = 0;
+        for (int i = 0; i < kRankS; ++i) h ^= rol64(codeHash((idx >> (2 * (kRankS - 1 - i))) & 3u), (unsigned)(kRankS - 1 - i));
+        e[idx].h = h; e[idx].idx = idx;
+    }
+    // plain shell sort keeps this header free of <algorithm>; 65,536 entries once per index
+    for (unsigned gap = kRankEntries / 2; gap > 0; gap /= 2)
+        for (unsigned i = gap; i < kRankEntries; ++i) {
+            const E x = e[i]; unsigned j = i;
+            for (; j >= gap && e[j - gap].h > x.h; j -= gap) e[j] = e[j - gap];
+            e[j] = x;
+        }
+    unsigned r = 0;
+    for (unsigned i = 0; i < kRankEntries; ++i) { if (i && e[i].h != e[i - 1].h) ++r; rank[e[i].idx] = (uint16_t)r; }
+    delete[] e;
+}
+inline void buildSeedTableImage(SeedTables* img, int k, int s) {   // img[kSeedTableElems]
+    memset(img, 0, kSeedTableElems * sizeof(SeedTables));
+    buildSeedTables(img[0], k, s);
+    if (s == kRankS) buildSmerRanks(reinterpret_cast<uint16_t*>(img + 1));
+}
+// cur holds four base codes, one per byte (byte j = base 4n + j; codes >= 4 are ambiguous and enter as code & 3).  HF collects the last
+// 16 bases as 2-bit codes, newest in the low bits; HR their complements, newest in the HIGH bits.  One multiply gathers the four 2-bit
+// fields of a word into its top byte (the partial products land on disjoint bits), one byte permute shifts it into the history.
+PM_HD unsigned bytePerm(unsigned a, unsigned b, unsigned sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const u64 v = ((u64)b << 32) | a; unsigned r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+    return r;
+#endif
+}
+PM_HD void rankPushWord(unsigned cur, unsigned& HF, unsigned& HR) {
+    const unsigned x = cur & 0x03030303u;
+    HF = bytePerm(HF, x * 0x40100401u, 0x2107u);                    // HF << 8 | (c0 c1 c2 c3)
+    HR = bytePerm(HR, (x ^ 0x03030303u) * 0x01041040u, 0x7321u);    // HR >> 8 | (c3' c2' c1' c0') << 24
+}
+// byte offsets into the u16 rank table of the s-mer that ENDS at base ph (0..3) of the newest word
+PM_HD unsigned rankAddrF(unsigned HF, int ph) { return (ph == 3 ? HF << 1 : HF >> (5 - 2 * ph)) & 0x1FFFEu; }
+PM_HD unsigned rankAddrR(unsigned HR, int ph) { return (HR >> (9 + 2 * ph)) & 0x1FFFEu; }
+PM_HD unsigned minU16x2(unsigned a, unsigned b) {
+#if defined(__CUDA_ARCH__)
+    return __vminu2(a, b);
+#else
+    const unsigned lo = (a & 0xFFFFu) < (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu), hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+#endif
+}
+PM_HD unsigned minU16x2Le(unsigned a, unsigned b, bool& leHi, bool& leLo) {   // per-half minimum and "a <= b"
+#if defined(__CUDA_ARCH__)
+    return __vibmin_u16x2(a, b, &leHi, &leLo);
+#else
+    leHi = (a >> 16) <= (b >> 16); leLo = (a & 0xFFFFu) <= (b & 0xFFFFu);
+    return minU16x2(a, b);
+#endif
+}
+// Sliding minimum over the last W s-mers in blocks of W (van Herk / Gil-Werman): raw[] = the packed ranks of the current block so far
+// (slots > j still hold the previous block's), suf[q] = minimum of the previous block's slots q..W-1, pre = minimum of the current block.
+// step(j, v): s-mer v lands in slot j; true when the window of W s-mers ending here has its minimum at the oldest or the newest s-mer, on
+// either strand.  j must be a compile-time constant after unrolling so that raw / suf stay in registers.
+template <int W>
+struct RankWindow {
+    unsigned raw[W], suf[W], pre;
+    PM_HD void reset() { for (int q = 0; q < W; ++q) { raw[q] = 0; suf[q] = 0; } pre = 0; }
+    PM_HD bool step(int j, unsigned v) {
+        const int pslot = (j + 1 == W) ? 0 : j + 1;                 // slot of the oldest s-mer of the window
+        const unsigned t = j == 0 ? suf[1] : (pslot == 0 ? pre : minU16x2(pre, suf[pslot]));   // everything but the newest
+        bool nh, nl, oh, ol;
+        const unsigned m = minU16x2Le(v, t, nh, nl);                // newest <= rest: it attains the minimum
+        (void)minU16x2Le(raw[pslot], m, oh, ol);                    // oldest <= minimum: it attains it (slot 0: this block's first)
+        pre = j == 0 ? v : minU16x2(pre, v);
+        raw[j] = v;
+        if (j == W - 1) {
+            unsigned a = v; suf[W - 1] = a;
+            for (int q = W - 2; q >= 1; --q) { a = minU16x2(raw[q], a); suf[q] = a; }
+        }
+        return nh || nl || oh || ol;
+    }
+};
 
 // ---- exact accumulation: signed 128-bit fixed point, 64 fractional bits --------------------------------
 // Every f64 quantity that is summed across nodes (tree prefix) or across table slots (read magnitudes) is first

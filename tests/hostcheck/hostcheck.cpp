@@ -37,6 +37,59 @@ int64_t hc_seed(const char* seq, int64_t len, int k, int s, int t, int l, int op
     return n;
 }
 
+}  // extern "C"
+// the syncmers_rank kernel's decision logic on the host (pm_logic.cuh: rank table, 2-bit histories, 16x2 sliding minimum), with the
+// k-mer hashes taken from their definition: (hash, pos) of every closed syncmer, t = 0, s = 8
+template <int K>
+static int64_t seedRankT(const char* seq, int64_t len, int trimS, int trimE, const uint16_t* rank, uint64_t* outHash, int64_t* outPos, int64_t cap) {
+    constexpr int S = kRankS, W = K - S + 1;
+    if (len < K) return 0;
+    RankWindow<W> win; win.reset();
+    unsigned HF = 0, HR = 0, cur = 0;
+    int iLo = trimS + K - 1; const int iHi = (int)len - trimE - 1;
+    int64_t n = 0;
+    auto codeAt = [&](int64_t i) -> unsigned { return i < len ? baseCode((unsigned char)seq[i]) : 4u; };
+    for (int i = 0; i < (int)len; ++i) {
+        const int ph = i & 3;
+        if (ph == 0) {
+            cur = codeAt(i) | (codeAt(i + 1) << 8) | (codeAt(i + 2) << 16) | (codeAt(i + 3) << 24);
+            rankPushWord(cur, HF, HR);
+        }
+        if ((cur & 0x04040404u) && (cur & (4u << (8 * ph)))) iLo = std::max(iLo, i + K);   // an ambiguous base closes every window that holds it
+        if (i < S - 1) continue;
+        const unsigned rf = rank[rankAddrF(HF, ph) >> 1], rr = rank[rankAddrR(HR, ph) >> 1];
+        const int j = (i - (S - 1)) % W;
+        bool syn = false;
+        // step() wants a constant slot after unrolling on the device; here a switch stands in for the unrolled loop
+        switch (j) {
+#define PM_CASE(J) case J: if (J < W) syn = win.step(J < W ? J : 0, rf | (rr << 16)); break;
+            PM_CASE(0) PM_CASE(1) PM_CASE(2) PM_CASE(3) PM_CASE(4) PM_CASE(5) PM_CASE(6) PM_CASE(7) PM_CASE(8) PM_CASE(9) PM_CASE(10) PM_CASE(11)
+#undef PM_CASE
+        }
+        if (!syn || i < iLo || i > iHi) continue;
+        u64 fk = 0, rk = 0;
+        for (int q = 0; q < K; ++q) {
+            const unsigned c = baseCode((unsigned char)seq[i - K + 1 + q]);
+            fk ^= rol64(codeHash(c), (unsigned)(K - 1 - q));
+            rk ^= rol64(c < 4 ? codeHash(3 - c) : 0ULL, (unsigned)q);
+        }
+        if (fk == rk) continue;
+        if (n < cap) { outHash[n] = umin64(fk, rk); outPos[n] = i - K + 1; }
+        ++n;
+    }
+    return n;
+}
+extern "C" {
+int64_t hc_seed_rank(const char* seq, int64_t len, int k, int trimS, int trimE, uint64_t* outHash, int64_t* outPos, int64_t cap) {
+    static std::vector<uint16_t> rank;
+    if (rank.empty()) { rank.resize(kRankEntries); buildSmerRanks(rank.data()); }
+    if (k == 19) return seedRankT<19>(seq, len, trimS, trimE, rank.data(), outHash, outPos, cap);
+    if (k == 15) return seedRankT<15>(seq, len, trimS, trimE, rank.data(), outHash, outPos, cap);
+    return -1;
+}
+// number of distinct ranks (65,536 unless two 8-mers share a hash)
+uint32_t hc_rank_distinct() { std::vector<uint16_t> r(kRankEntries); buildSmerRanks(r.data()); uint32_t mx = 0; for (auto v : r) mx = std::max<uint32_t>(mx, v); return mx + 1; }
+
 // owner rank of every seed of a sharded sample (pm_logic.cuh seedOwner, the function partition_export uses on the device)
 void hc_seed_owner(const uint64_t* h, int64_t n, uint32_t nRanks, uint32_t* out) { for (int64_t i = 0; i < n; ++i) out[i] = seedOwner(h[i], nRanks); }
 // exact magnitude sums the way gathered_finalize + finish_scalars form them (minus the rounding-drift term): per-entry fixed-point terms

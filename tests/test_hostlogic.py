@@ -52,6 +52,27 @@ def test_read_seeder_matches_oracle(hc):
         assert np.array_equal(cpu.read_seeds(seq, k, s, t, l, op, ts, te), hc_seed(hc, seq, k, s, t, l, op, ts, te, 2)[0]), (k, s, t, l, op, ts, te)
 
 
+def test_rank_based_closed_syncmers_equal_the_oracle(hc):
+    """syncmers_rank decides "closed syncmer" on 16-bit RANKS of the s-mer hashes (s = 8: a 65,536-entry table, the reverse strand through
+    the index of the reverse complement) with both strands in one 16x2 word.  Same syncmers as the oracle's 64-bit rolling hashes
+    (seeding.cpp:147-226) for k = 19 / 15, ambiguous bases, lower case, trims, reads shorter than k."""
+    assert hc.hc_rank_distinct() == 65536          # no two 8-mers share a hash: ranks are a permutation
+    hc.hc_seed_rank.restype = C.c_int64
+    rng = np.random.default_rng(5)
+    for it in range(1200):
+        k = int(rng.choice([19, 15])); ts = int(rng.choice([0, 0, 4, 11])); te = int(rng.choice([0, 0, 6, 25]))
+        seq = H.random_reads(rng, 1, lo=1, hi=400, p_n=float(rng.choice([0.0, 0.02, 0.2])), p_lower=0.02)[0]
+        if it % 7 == 0:                               # low-complexity reads: many equal s-mers inside a window (ties on the minimum)
+            unit = H.random_reads(rng, 1, lo=1, hi=6, p_n=0.0, p_lower=0.0)[0]
+            seq = (unit * 200)[: len(seq) + 40]
+        a = cpu.rolling_syncmers(seq, k, 8, False, 0, False)
+        keep = (a[3] >= ts) & (a[3] <= len(seq) - te - k)
+        cap = max(len(seq), 1)
+        h = np.zeros(cap, np.uint64); p = np.zeros(cap, np.int64)
+        n = hc.hc_seed_rank(seq, C.c_int64(len(seq)), k, ts, te, _p(h), _p(p), C.c_int64(cap))
+        assert n == int(keep.sum()) and np.array_equal(h[:n], a[0][keep]) and np.array_equal(p[:n], a[3][keep]), (it, k, ts, te, seq[:60])
+
+
 def test_fixed_point_is_exact_and_order_free(hc):
     rng = np.random.default_rng(1)
     for x in [0.0, 1.0, -1.0, 2.0 ** -30, 3.5e11, -7.25e-5, np.log1p(3.0), 1e-19]:
