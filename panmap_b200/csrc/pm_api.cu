@@ -118,7 +118,7 @@ static int createIndex(const pm_index_desc* desc, int device, uint32_t shard, ui
 void refreshView(pm_workspace* W) {
     WorkspaceView& V = W->view;
     V.table = W->table.p; V.tableTex = W->tableTex; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
-    V.synBuf = W->synBuf.p; V.synCount = W->synCount.p;
+    V.synBuf = W->synBuf.p; V.synCount = W->synCount.p; V.missQ = W->missQ.p; V.missCap = W->missQ.n;
     V.acc = W->acc.p; V.ell = W->ell.p; V.ellTex = W->ellTex; V.countHist = W->countHist.p; V.entKey = W->entKey.p; V.entCnt = W->entCnt.p; V.entId = W->entId.p;
     V.scanPart = W->scanPart.p; V.finPart = W->finPart.p;
     V.segRec = W->segRec.p; V.chainA = W->chainA.p; V.genRec = W->genRec.p; V.evPrefix = W->evPrefix.p;
@@ -185,7 +185,7 @@ void uploadReads(pm_workspace* W, const char* reads, const uint64_t* off, u64 n,
     const u64 total = n ? off[n] - base0 : 0;
     hostPackedOffsets(W, off, n, I->F.sp.k);
     W->nReads = n; W->totalBases = total; W->hpcDone = false;
-    W->synBuf.ensure(W->nChunks * 32 + 32); W->synCount.ensure(n + 1);
+    W->synBuf.ensure(W->nChunks * 32 + 32); W->synCount.ensure(n + 1); W->missQ.ensure(W->nChunks * 8 + 65536);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1); W->packed.ensure(W->nChunks + 1);
     if (base0 != 0) throw std::runtime_error("read_offsets[0] must be 0");
     if (total) CK(cudaMemcpyAsync(W->reads.p, reads, total, fromDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, W->st));
@@ -243,7 +243,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     W->nReads = n; W->totalBases = total;
     W->hPackedOff.ensure(n + 1); W->hBlockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 32);
     W->reads.ensure(total + 64); W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
-    W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1);
+    W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1); W->missQ.ensure((total / 32 + n + 16) * 8 + 65536);
     W->blockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 32);
     if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, (total > (u64)k * n ? total - (u64)(k - 1) * n : 0) / 4));
     refreshView(W);
@@ -305,7 +305,7 @@ void uploadAndSeedPipelinedPacked(pm_workspace* W, const uint4* hPacked, const u
     const int nSlices = total >= sliceMinBytes() ? sched.n : 1;
     W->nReads = n; W->totalBases = total;
     W->off.ensure(n + 1); W->packedOff.ensure(n + 1);
-    W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1);
+    W->packed.ensure(total / 32 + n + 16); W->synBuf.ensure((total / 32 + n + 16) * 32); W->synCount.ensure(n + 1); W->missQ.ensure((total / 32 + n + 16) * 8 + 65536);
     W->tileSum.ensure(n / 4096 + 2);
     if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, (total > (u64)k * n ? total - (u64)(k - 1) * n : 0) / 4));
     refreshView(W);

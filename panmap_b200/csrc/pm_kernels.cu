@@ -514,10 +514,9 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
 // warps set up their reads) and a sliding minimum over both strands' ranks at once (one VIMNMX.U16x2 per comparison, which also
 // returns the two per-strand "<=" predicates).  The rolling k-mer hashes -- the values that are reported -- are unchanged.
 // One persistent block per SM (the table takes 128 of its 227 KB of shared memory).
-constexpr int kRankThreads = 512;
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-template <int K, bool ASCII, bool NOTRIM>
-__global__ void __launch_bounds__(kRankThreads, 1) syncmers_rank(const uint4* __restrict__ packed, const u64* __restrict__ off,
+template <int K, bool ASCII, bool NOTRIM, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) syncmers_rank(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                                  const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
                                                                  const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
                                                                  unsigned* __restrict__ synCount, const unsigned char* __restrict__ dup,
@@ -591,60 +590,70 @@ __global__ void __launch_bounds__(kRankThreads, 1) syncmers_rank(const uint4* __
         const int iHi = L - P.trimEnd - 1;       //   complete, inside the trimmed range, no ambiguous base in it (iLo moves past those)
         win.reset();
 
-        // base i enters: the k-mer's rolling hashes on both strands (seeding.cpp:147-195) and, once per word, the 2-bit histories the
-        // s-mer ranks are looked up with.  ph = i & 3 is a compile-time constant inside the unrolled block.
-        auto fetchRoll = [&](int i, int ph, auto full) {
-            constexpr bool FULL = decltype(full)::value;
-            if (ph == 0) {   // next four bases
-                h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = cur;
-                if (ASCII) {
-                    if (FULL || i < L) {   // 4 bytes from an arbitrary byte address: two aligned words, one funnel shift, four table look-ups
-                        const unsigned a = rshift + (unsigned)i;
-                        const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + (a & ~3u));
-                        const unsigned x0 = __ldg(wp), x1 = __ldg(wp + 1);
-                        const unsigned bts = __funnelshift_r(x0, x1, (a & 3u) * 8u);
-                        unsigned cw = sLut[bts >> 24];
-                        cw = cw * 256u + sLut[(bts >> 16) & 0xFFu];
-                        cw = cw * 256u + sLut[(bts >> 8) & 0xFFu];
-                        cw = cw * 256u + sLut[bts & 0xFFu];
-                        cur = cw;
-                    }
-                } else {   // 4-bit codes from `packed`: spread four nibbles to bytes
-                    if ((i & 31) == 0) { if (FULL || i < L) v4 = src[i >> 5]; }
-                    const int wsel = (i >> 3) & 3;
-                    const unsigned w32 = wsel == 0 ? v4.x : wsel == 1 ? v4.y : wsel == 2 ? v4.z : v4.w;
-                    const unsigned n16 = (w32 >> (16 * ((i >> 2) & 1))) & 0xFFFFu;
-                    cur = (((n16 & 0xF000u) << 12) | ((n16 & 0x0F00u) << 8) | ((n16 & 0x00F0u) << 4) | (n16 & 0x000Fu)) & 0x07070707u;
-                }
-                constexpr int KA = K / 4, KB = K % 4;
-                const unsigned hist[7] = {cur, h1, h2, h3, h4, h5, 0x04040404u};
-                // byte j of the lag word = base 4n + j - K: four consecutive bytes of (hist[KA+1], hist[KA]) starting at byte 4 - KB
-                constexpr unsigned selK = (4 - KB) | ((5 - KB) << 4) | ((6 - KB) << 8) | ((7 - KB) << 12);
-                const unsigned lagK = KB ? __byte_perm(hist[KA + 1], hist[KA], selK) : hist[KA];
-                combK = lagK * 12u + cur;   // bytewise: codes are <= 7, 12 * 7 + 7 < 256
-                rankPushWord(cur, HF, HR);
-                ambWord = (cur & 0x04040404u) != 0u;   // rare: the per-base test below hangs off this one predicate
+        // the next four bases (i .. i+3, i a multiple of 4) as one code byte each
+        auto loadWord = [&](int i) -> unsigned {
+            if (ASCII) {   // 4 bytes from an arbitrary byte address: two aligned words, one funnel shift, four table look-ups
+                const unsigned a = rshift + (unsigned)i;
+                const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + (a & ~3u));
+                const unsigned x0 = __ldg(wp), x1 = __ldg(wp + 1);
+                const unsigned bts = __funnelshift_r(x0, x1, (a & 3u) * 8u);
+                unsigned cw = sLut[bts >> 24];
+                cw = cw * 256u + sLut[(bts >> 16) & 0xFFu];
+                cw = cw * 256u + sLut[(bts >> 8) & 0xFFu];
+                cw = cw * 256u + sLut[bts & 0xFFu];
+                return cw;
             }
-            if (FULL || i < L) {
-                const unsigned pk = __byte_perm(combK, 0u, 0x4440u + (unsigned)ph);
-                fk = rol1(fk) ^ sPair[pk];
-                rk = ror1(rk) ^ sPair[kPairStride + pk];
-                if (ambWord) { if (cur & (0x04u << (8 * ph))) iLo = max(iLo, i + K); }   // codes >= 4 are ambiguous
-            }
+            // 4-bit codes from `packed`: spread four nibbles to bytes
+            if ((i & 31) == 0) v4 = src[i >> 5];
+            const int wsel = (i >> 3) & 3;
+            const unsigned w32 = wsel == 0 ? v4.x : wsel == 1 ? v4.y : wsel == 2 ? v4.z : v4.w;
+            const unsigned n16 = (w32 >> (16 * ((i >> 2) & 1))) & 0xFFFFu;
+            return (((n16 & 0xF000u) << 12) | ((n16 & 0x0F00u) << 8) | ((n16 & 0x00F0u) << 4) | (n16 & 0x000Fu)) & 0x07070707u;
+        };
+        // word cw becomes the current one: word history for the k-mer's outgoing bases, 2-bit histories for the s-mer ranks
+        auto pushWord = [&](unsigned cw, auto clean) {
+            constexpr bool CLEAN = decltype(clean)::value;
+            h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = cur; cur = cw;
+            constexpr int KA = K / 4, KB = K % 4;
+            const unsigned hist[7] = {cur, h1, h2, h3, h4, h5, 0x04040404u};
+            // byte j of the lag word = base 4n + j - K: four consecutive bytes of (hist[KA+1], hist[KA]) starting at byte 4 - KB
+            constexpr unsigned selK = (4 - KB) | ((5 - KB) << 4) | ((6 - KB) << 8) | ((7 - KB) << 12);
+            const unsigned lagK = KB ? __byte_perm(hist[KA + 1], hist[KA], selK) : hist[KA];
+            combK = lagK * 12u + cur;   // bytewise: codes are <= 7, 12 * 7 + 7 < 256
+            rankPushWord(cur, HF, HR);
+            if (!CLEAN) ambWord = (cur & 0x04040404u) != 0u;
+        };
+        // base i (phase ph of the current word) enters the k-mer's rolling hashes on both strands (seeding.cpp:147-195)
+        auto roll = [&](int i, int ph, auto clean) {
+            constexpr bool CLEAN = decltype(clean)::value;
+            const unsigned pk = __byte_perm(combK, 0u, 0x4440u + (unsigned)ph);
+            fk = rol1(fk) ^ sPair[pk];
+            rk = ror1(rk) ^ sPair[kPairStride + pk];
+            if (!CLEAN) { if (ambWord) { if (cur & (0x04u << (8 * ph))) iLo = max(iLo, i + K); } }   // codes >= 4 are ambiguous
         };
         // prologue: the first S-1 bases only feed the rolling hashes and the histories
 #pragma unroll 1
-        for (int i = 0; i < S - 1 && i < maxL; ++i) fetchRoll(i, i & 3, std::false_type{});
-        // one block of W s-mers; s-mer index q = i - (S-1), slot j = q mod W
-        auto block = [&](int q0, auto full) {
+        for (int i = 0; i < S - 1 && i < maxL; ++i) {
+            if ((i & 3) == 0) { unsigned cw = cur; if (i < L) cw = loadWord(i); pushWord(cw, std::false_type{}); }
+            if (i < L) roll(i, i & 3, std::false_type{});
+        }
+        // one block of W s-mers; s-mer index q = i - (S-1), slot j = q mod W.  FULL: the block lies inside every lane's read (no length
+        // tests) and its words were loaded up front (pre); CLEAN: none of them -- nor the word the block starts in -- has an ambiguous base
+        auto block = [&](int q0, auto full, auto clean, const unsigned* pre) {
             constexpr bool FULL = decltype(full)::value;
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 const int i = q0 + j + S - 1;
                 if (FULL || i < maxL) {   // warp-uniform
                     const int ph = (j + S - 1) & 3;   // q0 is a multiple of W, W of 4
-                    fetchRoll(i, ph, full);
+                    if (ph == 0) {
+                        unsigned cw = cur;
+                        if (FULL) cw = pre[(j - 1) / 4];
+                        else if (i < L) cw = loadWord(i);
+                        pushWord(cw, clean);
+                    }
                     if (FULL || i < L) {
+                        roll(i, ph, clean);
                         const unsigned rf = *reinterpret_cast<const unsigned short*>(sRank + rankAddrF(HF, ph));
                         const unsigned rr = *reinterpret_cast<const unsigned short*>(sRank + rankAddrR(HR, ph));
                         const bool syn = win.step(j, __byte_perm(rf, rr, 0x5410u));
@@ -656,11 +665,17 @@ __global__ void __launch_bounds__(kRankThreads, 1) syncmers_rank(const uint4* __
                 }
             }
         };
-        // main loop: blocks that lie inside every lane's read take the copy without the per-base length tests
+        // main loop: blocks that lie inside every lane's read take the copies without the per-base length tests
 #pragma unroll 1
         for (int q0 = 0; q0 + S - 1 < maxL; q0 += W) {
-            if (q0 + W + S - 1 <= minL) block(q0, std::true_type{});
-            else block(q0, std::false_type{});
+            if (q0 + W + S - 1 <= minL) {
+                unsigned pre[W / 4];
+                bool amb = ambWord;
+#pragma unroll
+                for (int t = 0; t < W / 4; ++t) { pre[t] = loadWord(q0 + S + 4 * t); amb = amb || (pre[t] & 0x04040404u) != 0u; }
+                if (!__any_sync(0xffffffffu, amb)) block(q0, std::true_type{}, std::true_type{}, pre);
+                else block(q0, std::true_type{}, std::false_type{}, pre);
+            } else block(q0, std::false_type{}, std::false_type{}, nullptr);
         }
         if (valid) synCount[r] = cnt;
     }
@@ -851,19 +866,38 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds(const u64* __res
 // count_seeds_lane: the same counting with one LANE per read (as in the syncmer kernel): a lane walks its own list, keeps the last
 // LT-1 syncmers in registers and loads one new syncmer per seed -- no search for "which read does seed i belong to", a third of the
 // loads and a quarter of the instructions of the flat numbering above.  Four seeds per lane are formed before anything is probed.
-template <int KT, int LT, bool AGG>
-__global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds_lane(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
+// QUEUE (whole samples): seeds that miss the block's shared-memory table are not walked through the global table here -- a few lanes
+// at a time, every one a dependent chain of L2 round trips that the whole warp waits for -- but appended to a miss queue in global
+// memory (per-warp staging in shared memory, one reservation per ~100 entries); count_misses then inserts them with every lane busy.
+constexpr int kWarpQueue = 128;   // staged misses per warp
+template <int KT, int LT, bool AGG, bool QUEUE>
+__global__ void __launch_bounds__(AGG ? 1024 : 256, 1) count_seeds_lane(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
                                                    const u64* __restrict__ packedOff, u64 nReads, TableSlot* table,
-                                                   u64 mask, SampleAcc* acc, cudaTextureObject_t tableTex) {
+                                                   u64 mask, SampleAcc* acc, cudaTextureObject_t tableTex, u64* __restrict__ missQ, u64 missCap) {
     static_assert(LT == 1 || LT == 3, "lane-per-read counting is specialised for l = 1 and l = 3");
+    static_assert(AGG || !QUEUE, "the miss queue belongs to the pre-aggregating variant");
     extern __shared__ __align__(16) unsigned char aggRaw[];
     u64* sKey = reinterpret_cast<u64*>(aggRaw);
     u32* sCnt = reinterpret_cast<u32*>(aggRaw + (size_t)kAggSlots * sizeof(u64));
+    u64* wq = reinterpret_cast<u64*>(aggRaw + (size_t)kAggSlots * (sizeof(u64) + sizeof(u32))) + (size_t)(threadIdx.x >> 5) * kWarpQueue;
+    unsigned wcnt = 0;   // warp-uniform
     if (AGG) {
         for (int i = threadIdx.x; i < kAggSlots; i += blockDim.x) { sKey[i] = kEmptyKey; sCnt[i] = 0; }
         __syncthreads();
     }
     const unsigned lane = threadIdx.x & 31u;
+    auto flushQueue = [&]() {   // whole warp
+        __syncwarp();
+        unsigned base32 = 0;
+        if (lane == 0) base32 = atomicAdd(&acc->missCount, wcnt);
+        const u64 base = __shfl_sync(0xffffffffu, base32, 0);
+        for (unsigned i = lane; i < wcnt; i += 32) {
+            if (base + i < missCap) missQ[base + i] = wq[i];
+            else tableInsert(table, mask, wq[i], 1u, acc);   // queue full: the direct way (count_misses stops at missCap)
+        }
+        __syncwarp();
+        wcnt = 0;
+    };
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
     for (u64 r0 = ((u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; r0 < nReads; r0 += warpsTotal * 32) {
         const u64 r = r0 + lane;
@@ -875,12 +909,18 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds_lane(const u64* 
         for (int d = 16; d > 0; d >>= 1) maxS = max(maxS, __shfl_xor_sync(0xffffffffu, maxS, d));
         u64 h0 = 0, h1 = 0;   // the two syncmers before the next one to load (l = 3)
         if (LT == 3 && nS > 0) { h0 = __ldg(h); h1 = __ldg(h + 1); }
-        for (int j0 = 0; j0 < maxS; j0 += 4) {
-            u64 x[4], sd[4], slot[4]; bool has[4];
+        constexpr int R = QUEUE ? 8 : 4;   // seeds per lane and round: without the global walk there are registers for eight loads in flight
+        for (int j0 = 0; j0 < maxS; j0 += R) {
+            u64 x[R], sd[R], slot[R]; bool has[R];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { has[q] = j0 + q < nS; x[q] = has[q] ? __ldg(h + j0 + q + (LT - 1)) : 0; }
+            for (int q = 0; q < R; q += 2) {   // 16 bytes at a time (lists start on 256-byte boundaries, j0 + LT - 1 is even): every sector is fetched once
+                has[q] = j0 + q < nS; has[q + 1] = j0 + q + 1 < nS;
+                uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                if (has[q]) t = __ldg(reinterpret_cast<const uint4*>(h + j0 + q + (LT - 1)));   // the second half may lie past the list's end: unused then
+                x[q] = (u64)t.x | ((u64)t.y << 32); x[q + 1] = (u64)t.z | ((u64)t.w << 32);
+            }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < R; ++q) {
                 if (LT == 1) sd[q] = x[q];
                 else {
                     const u64 fw = rol64(h0, (unsigned)((KT * 2) & 63)) ^ rol64(h1, (unsigned)(KT & 63)) ^ x[q];
@@ -893,20 +933,32 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds_lane(const u64* 
             }
             if (AGG) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
+                for (int q = 0; q < R; ++q)
                     if (has[q] && sd[q] != kEmptyKey && aggAdd(sKey, sCnt, sd[q], slot[q])) has[q] = false;   // counted on the SM
             }
-            u64 key[4];
+            if (QUEUE) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+                for (int q = 0; q < R; ++q) {
+                    const unsigned m = __ballot_sync(0xffffffffu, has[q]);
+                    if (m) {
+                        if (wcnt + (unsigned)__popc(m) > (unsigned)kWarpQueue) flushQueue();
+                        if (has[q]) wq[wcnt + (unsigned)__popc(m & ((1u << lane) - 1u))] = sd[q];
+                        wcnt += (unsigned)__popc(m);
+                    }
+                }
+                continue;
+            }
+            u64 key[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
                 slot[q] &= mask; key[q] = kEmptyKey;
                 if (has[q]) { const uint4 t = tex1Dfetch<uint4>(tableTex, (int)slot[q]); key[q] = (u64)t.x | ((u64)t.y << 32); }
             }
             // new keys claim their slot with a CAS whose result takes a round trip to L2: issue the CASes of all four seeds before
             // looking at any result (one exposed latency per round instead of up to four); true collisions go the general way
-            bool claim[4], slow[4]; unsigned long long was[4];
+            bool claim[R], slow[R]; unsigned long long was[R];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < R; ++q) {
                 claim[q] = slow[q] = false;
                 if (has[q]) {
                     if (sd[q] == kEmptyKey) slow[q] = true;
@@ -916,16 +968,17 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds_lane(const u64* 
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < R; ++q)
                 if (claim[q]) was[q] = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot[q]].key), (unsigned long long)kEmptyKey, (unsigned long long)sd[q]);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < R; ++q)
                 if (claim[q]) { if (was[q] == kEmptyKey || was[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u); else slow[q] = true; }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < R; ++q)
                 if (slow[q]) tableInsert(table, mask, sd[q], 1u, acc);
         }
     }
+    if (QUEUE) { if (wcnt) flushQueue(); }
     if (AGG) {   // flush: the block's (seed, count) pairs into the global table, four claims in flight per thread
         __syncthreads();
         for (int i0 = threadIdx.x * 4; i0 < kAggSlots; i0 += blockDim.x * 4) {
@@ -955,16 +1008,66 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256) count_seeds_lane(const u64* 
         }
     }
 }
+// the miss queue of count_seeds_lane<.., QUEUE> into the global table: one seed per thread and turn, four turns in flight
+__global__ void __launch_bounds__(256) count_misses(const u64* __restrict__ missQ, u64 missCap, TableSlot* table, u64 mask, SampleAcc* acc,
+                                                    cudaTextureObject_t tableTex) {
+    const u64 n = min((u64)acc->missCount, missCap);
+    const u64 T = (u64)gridDim.x * blockDim.x;
+    for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * T) {
+        u64 sd[4], slot[4], key[4]; bool has[4], claim[4], slow[4]; unsigned long long was[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const u64 i = i0 + (u64)q * T; has[q] = i < n; sd[q] = has[q] ? __ldcs(missQ + i) : 0; slot[q] = mixKey(sd[q]) & mask; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            key[q] = kEmptyKey;
+            if (has[q]) { const uint4 t = tex1Dfetch<uint4>(tableTex, (int)slot[q]); key[q] = (u64)t.x | ((u64)t.y << 32); }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            claim[q] = slow[q] = false;
+            if (has[q]) {
+                if (sd[q] == kEmptyKey) slow[q] = true;
+                else if (key[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u);
+                else if (key[q] == kEmptyKey) claim[q] = true;
+                else slow[q] = true;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (claim[q]) was[q] = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot[q]].key), (unsigned long long)kEmptyKey, (unsigned long long)sd[q]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (claim[q]) { if (was[q] == kEmptyKey || was[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u); else slow[q] = true; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (slow[q]) tableInsert(table, mask, sd[q], 1u, acc);
+    }
+}
+// Measured on the 1M x 150 bp sample (r02f): count_seeds_lane without the global walk 328 us + count_misses 136-158 us = 475 us against
+// 393 us with the walk inside -- the walk was not the bottleneck (list loads + shared-memory probes are), and on its own the queue pass
+// pays the 11.5 M L2 round trips that the fused kernel hides.  Kept as an experiment switch: PM_MISS_QUEUE=1
+static bool useMissQueue() {
+    static const bool v = [] { const char* e = std::getenv("PM_MISS_QUEUE"); return e ? std::atoi(e) != 0 : false; }();
+    return v;
+}
 template <int KT, int LT>
 static void launchCountLane(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, TableSlot* table, u64 mask, SampleAcc* acc,
-                            cudaTextureObject_t tableTex, cudaStream_t st) {
+                            cudaTextureObject_t tableTex, u64* missQ, u64 missCap, cudaStream_t st) {
     if (nReads >= aggMinReads()) {   // whole samples and the per-rank slices of sharded ones: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
         const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
-        cudaFuncSetAttribute(count_seeds_lane<KT, LT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        noteLaunch(), count_seeds_lane<KT, LT, true><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
+        if (missQ && missCap && useMissQueue()) {
+            const size_t smq = sm + (size_t)32 * kWarpQueue * sizeof(u64);
+            cudaMemsetAsync(&acc->missCount, 0, sizeof(acc->missCount), st);
+            cudaFuncSetAttribute(count_seeds_lane<KT, LT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq);
+            noteLaunch(), count_seeds_lane<KT, LT, true, true><<<148, 1024, smq, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, missQ, missCap);
+            noteLaunch(), count_misses<<<148 * 8, 256, 0, st>>>(missQ, missCap, table, mask, acc, tableTex);
+            return;
+        }
+        cudaFuncSetAttribute(count_seeds_lane<KT, LT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        noteLaunch(), count_seeds_lane<KT, LT, true, false><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, nullptr, 0);
     } else {
         u64 g = (nReads + 255) / 256; if (g > 148ull * 8) g = 148ull * 8;
-        noteLaunch(), count_seeds_lane<KT, LT, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex);
+        noteLaunch(), count_seeds_lane<KT, LT, false, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, nullptr, 0);
     }
 }
 template <int MODE>
@@ -978,12 +1081,12 @@ static u64 countWarpBelow() {
     return v;
 }
 static void launchCountSeeds(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, TableSlot* table, u64 mask,
-                             SampleAcc* acc, cudaTextureObject_t tableTex, cudaStream_t st) {
+                             SampleAcc* acc, cudaTextureObject_t tableTex, u64* missQ, u64 missCap, cudaStream_t st) {
     if (nReads < countWarpBelow()) return launchSeedsFromSyncmers<0>(synBuf, synCount, packedOff, nullptr, nReads, k, l, table, mask, acc, nullptr, nullptr, tableTex, st);
     // panmap's parameter sets (l = 3 with k = 19 / 15, and l <= 1) use the lane-per-read kernel; any other (k, l) the flat one below
-    if (k == 19 && l == 3) return launchCountLane<19, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
-    if (k == 15 && l == 3) return launchCountLane<15, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
-    if (l <= 1) return launchCountLane<0, 1>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, st);
+    if (k == 19 && l == 3) return launchCountLane<19, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, missQ, missCap, st);
+    if (k == 15 && l == 3) return launchCountLane<15, 3>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, missQ, missCap, st);
+    if (l <= 1) return launchCountLane<0, 1>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, missQ, missCap, st);
     if (nReads >= aggMinReads()) {   // whole samples and the per-rank slices of sharded ones: per-SM pre-aggregation (a block must see enough reads for its table to pay off)
         const size_t sm = (size_t)kAggSlots * (sizeof(u64) + sizeof(u32));
         cudaFuncSetAttribute(count_seeds<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -1021,22 +1124,32 @@ static u64 rankMinReads() {
     static const u64 v = [] { const char* e = std::getenv("PM_RANK_MIN_READS"); return e ? (u64)std::strtoull(e, nullptr, 10) : (u64)20000; }();
     return v;
 }
-template <int K>
-static void launchRank(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
-                       u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
+static int rankThreads() {   // tuning override: PM_RANK_THREADS (512 or 768)
+    static const int v = [] { const char* e = std::getenv("PM_RANK_THREADS"); return e ? std::atoi(e) : 512; }();
+    return v;
+}
+template <int K, int THREADS>
+static void launchRankT(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
+                        u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
     const size_t sm = (size_t)kRankEntries * 2 + 2 * kPairStride * sizeof(u64) + 256;
-    u64 g = (nReads + kRankThreads - 1) / kRankThreads; if (g > 148) g = 148;
+    u64 g = (nReads + THREADS - 1) / THREADS; if (g > 148) g = 148;
     const unsigned grid = (unsigned)(g ? g : 1);
 #define PM_RANK_LAUNCH(A, N)                                                                                                        \
     do {                                                                                                                            \
-        cudaFuncSetAttribute(syncmers_rank<K, A, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                         \
-        noteLaunch(), syncmers_rank<K, A, N><<<grid, kRankThreads, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads); \
+        cudaFuncSetAttribute(syncmers_rank<K, A, N, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                \
+        noteLaunch(), syncmers_rank<K, A, N, THREADS><<<grid, THREADS, sm, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads); \
     } while (0)
     if (reads && P.trimEnd == 0) PM_RANK_LAUNCH(true, true);
     else if (reads) PM_RANK_LAUNCH(true, false);
     else if (P.trimEnd == 0) PM_RANK_LAUNCH(false, true);
     else PM_RANK_LAUNCH(false, false);
 #undef PM_RANK_LAUNCH
+}
+template <int K>
+static void launchRank(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
+                       u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
+    if (rankThreads() == 768) return launchRankT<K, 768>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads, st);
+    return launchRankT<K, 512>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads, st);
 }
 template <int K, int S>
 static void launchFast(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
@@ -1072,7 +1185,7 @@ void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, 
     if (nReads == 0) return;
     launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, dup, endOff, st, reads);
     if (between) cudaEventRecord(between, st);
-    launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, st);
+    launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, W.missQ, W.missCap, st);
 }
 // --min-seed-quality > 0 (off by default): the generic kernels with per-syncmer pass flags; quals has one byte per base at the reads'
 // offsets (compressed in lockstep for hpc indexes), synPass one byte per synBuf entry

@@ -27,7 +27,7 @@ struct __align__(16) DictSlot { u64 key; u32 id; u32 pad; };       // index dict
 struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample)
     u64 magSq[2], logSum[2], wcDen[2];  // fx128 as (lo, hi)
     long long kept, total, unique, multiSum, multiCount, entries, maxKeptCount, overflow, emptyKeyCount;
-    unsigned pad0, entCount;
+    unsigned missCount, entCount;   // missCount: entries of the miss queue (count_seeds_lane -> count_misses)
     unsigned recordCount[8];
     unsigned tieCount[8];
     long long n1NotIndex;   // sharded samples: kept seeds with read count 1 that the index does not hold (they travel as a count, not as entries)
@@ -92,6 +92,7 @@ struct WorkspaceView {
     cudaTextureObject_t tableTex;   // the table as a linear uint4 texture (first probe of an insertion)
     SampleAcc* acc;
     u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
+    u64* missQ; u64 missCap;          // seeds that missed the per-SM tables of count_seeds_lane, waiting for count_misses
     cudaTextureObject_t ellTex;   // ell as a linear int2 texture: scattered gathers go through the TEX data path instead of the LSU's
     long long* ell;       // [nSeeds+2] log1p(read count) * 2^53 of the seed id (an exact integer), 0 when absent; slot nSeeds stays 0
     u64* entKey; u32* entCnt; u32* entId;   // [tableCap] occupied (key, count) pairs compacted by table_scan + the seed id found for them
