@@ -73,6 +73,77 @@ static inline unsigned streamGrid(u64 n, unsigned perThread) {
     return (unsigned)(g ? g : 1);
 }
 
+// true in exactly one block of the grid: the one whose threads get here last (everything the other blocks wrote before is visible to it).
+// *ctr must be zero before the launch and is zero again afterwards; sFlag: one word of shared memory.
+__device__ __forceinline__ bool lastBlockDone(unsigned* ctr, unsigned* sFlag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const bool last = atomicAdd(ctr, 1u) == gridDim.x * gridDim.y - 1u;
+        if (last) *ctr = 0u;
+        *sFlag = last ? 1u : 0u;
+    }
+    __syncthreads();
+    const bool r = *sFlag != 0u;
+    if (r) __threadfence();
+    return r;
+}
+
+// ---- tolerance chain over a set of prefix-maximum records (placement.cpp:355-371), one 256-thread block per metric ----------------
+// Records are unordered: every step picks the lowest-rank record after the last event that beats best + tol.  The valid records are
+// first staged in shared memory (a handful per metric in practice), so a step costs shared-memory latency instead of an L2 round trip
+// per record; more than kChainCap records are walked where they lie.
+constexpr int kChainCap = 1536;
+struct ChainShared {
+    unsigned long long sMin[8]; unsigned long long sPick; unsigned sN;
+    u32 rank[kChainCap]; u32 node[kChainCap]; double score[kChainCap];
+};
+template <class RecAt>   // recAt(idx, rank, score, node) -> record idx exists
+__device__ __forceinline__ Selection chainReplay(ChainShared& S, unsigned total, RecAt recAt) {
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) S.sN = 0;
+    __syncthreads();
+    for (unsigned idx = tid; idx < total; idx += 256) {
+        u32 rk, nd; double sc;
+        if (!recAt(idx, rk, sc, nd)) continue;
+        const unsigned o = atomicAdd(&S.sN, 1u);
+        if (o < (unsigned)kChainCap) { S.rank[o] = rk; S.node[o] = nd; S.score[o] = sc; }
+    }
+    __syncthreads();
+    const unsigned n = S.sN;
+    const bool staged = n <= (unsigned)kChainCap;
+    const unsigned span = staged ? n : total;
+    double best = 0.0; u32 bestNode = kNone; long long lastRank = -1;
+    while (true) {
+        const double thr = best + fmax(best * 0.0001, 1e-9);
+        unsigned long long pick = ~0ULL;
+        for (unsigned i = tid; i < span; i += 256) {
+            u32 rk, nd; double sc;
+            if (staged) { rk = S.rank[i]; sc = S.score[i]; }
+            else if (!recAt(i, rk, sc, nd)) continue;
+            if ((long long)rk > lastRank && sc > thr) {
+                const unsigned long long key = ((unsigned long long)rk << 32) | i;
+                pick = key < pick ? key : pick;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = shflXorU64(pick, d); pick = o < pick ? o : pick; }
+        if ((tid & 31) == 0) S.sMin[tid >> 5] = pick;
+        __syncthreads();
+        if (tid == 0) { unsigned long long v = S.sMin[0]; for (int w = 1; w < 8; ++w) v = S.sMin[w] < v ? S.sMin[w] : v; S.sPick = v; }
+        __syncthreads();
+        const unsigned long long p = S.sPick;
+        __syncthreads();
+        if (p == ~0ULL) break;
+        const unsigned i = (unsigned)(p & 0xFFFFFFFFu);
+        if (staged) { best = S.score[i]; bestNode = S.node[i]; }
+        else { u32 rk; recAt(i, rk, best, bestNode); }
+        lastRank = (long long)(p >> 32);
+    }
+    Selection s; s.best = best; s.bestNode = bestNode; s.lastRank = lastRank < 0 ? kNone : (u32)lastRank;
+    return s;
+}
+
 // ---- computeReadSeedMagnitudes pieces shared by entries_finalize (one GPU) and gathered_finalize (one sample over several GPUs) ----
 constexpr int kHistSmem = 2048;
 struct FinalizeAcc { fx128 mag, lsum; long long kept; u32 maxc; };

@@ -696,6 +696,56 @@ __global__ void __launch_bounds__(256) seeds_from_syncmers(const u64* __restrict
     const int k = KT > 0 ? KT : kRt, l = KT > 0 ? LT : lRt;
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
+    if (MODE == 0) {
+        // counting: a warp works on TWO reads at a time, two seeds per lane and read, so that four independent chains (list loads ->
+        // seed -> first probe -> update) are in flight per lane: the kernel is a sequence of L2 round trips per read otherwise
+        auto seedOf = [&](const u64* __restrict__ h, const unsigned char* __restrict__ pp, int nSeeds, int j, u64& seed) -> bool {
+            if (j >= nSeeds) return false;
+            if (pp) { for (int w = 0; w < (l <= 1 ? 1 : l); ++w) if (!pp[j + w]) return false; }
+            if (l <= 1) { seed = h[j]; return true; }
+            u64 fw = 0, rw = 0;
+            if (KT > 0) {
+#pragma unroll
+                for (int w = 0; w < (LT > 0 ? LT : 1); ++w) {
+                    const u64 x = h[j + w];
+                    fw ^= rol64(x, (unsigned)((KT * (LT - 1 - w)) & 63));
+                    rw ^= rol64(x, (unsigned)((KT * w) & 63));
+                }
+            } else {
+                for (int w = 0; w < l; ++w) {
+                    const u64 x = h[j + w];
+                    fw ^= rol64(x, (unsigned)(k * (l - 1 - w)));
+                    rw ^= rol64(x, (unsigned)(k * w));
+                }
+            }
+            seed = umin64(fw, rw);
+            return fw != rw;
+        };
+        for (u64 rA = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rA < nReads; rA += 2 * warpsTotal) {
+            const u64 rB = rA + warpsTotal;
+            const bool isB = rB < nReads;
+            const int nA = (int)__ldg(&synCount[rA]), nB = isB ? (int)__ldg(&synCount[rB]) : 0;
+            const u64 oA = __ldg(&packedOff[rA]) * 32, oB = isB ? __ldg(&packedOff[rB]) * 32 : 0;
+            const u64* __restrict__ hA = synBuf + oA; const u64* __restrict__ hB = synBuf + oB;
+            const unsigned char* __restrict__ pA = pass ? pass + oA : nullptr; const unsigned char* __restrict__ pB = pass ? pass + oB : nullptr;
+            const int sA = l <= 1 ? nA : (nA >= l ? nA - l + 1 : 0), sB = l <= 1 ? nB : (nB >= l ? nB - l + 1 : 0);
+            for (int j0 = 0; j0 < max(sA, sB); j0 += 64) {
+                u64 sd[4] = {0, 0, 0, 0}, ps[4], ky[4]; bool has[4];
+                has[0] = seedOf(hA, pA, sA, j0 + (int)lane, sd[0]); has[1] = seedOf(hB, pB, sB, j0 + (int)lane, sd[1]);
+                has[2] = seedOf(hA, pA, sA, j0 + 32 + (int)lane, sd[2]); has[3] = seedOf(hB, pB, sB, j0 + 32 + (int)lane, sd[3]);
+                // first probe through the texture path (keys are write-once: a stale EMPTY only sends the seed to the CAS path)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    ps[q] = mixKey(sd[q]) & mask; ky[q] = 0;
+                    if (has[q]) { const uint4 t = tex1Dfetch<uint4>(tableTex, (int)ps[q]); ky[q] = (u64)t.x | ((u64)t.y << 32); }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (has[q]) { if (ky[q] == sd[q] && sd[q] != kEmptyKey) atomicAdd(&table[ps[q]].count, 1u); else tableInsert(table, mask, sd[q], 1u, acc); }
+            }
+        }
+        return;
+    }
     for (u64 r = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nReads; r += warpsTotal) {
         const int n = (int)synCount[r];
         const u64* __restrict__ h = synBuf + packedOff[r] * 32;
@@ -1450,21 +1500,10 @@ __global__ void __launch_bounds__(256) entries_finalize(DevIndexView I, Workspac
     finalizeBlockEpilogue(W, A, sHist, &sFin);
 }
 
-// weighted-containment denominator over the ROOT's deltas (placement.cpp:1863-1876)
-__global__ void __launch_bounds__(256) root_denominator(DevIndexView I, WorkspaceView W) {
-    fx128 s = fxZero();
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < I.rootDCount; i += (u64)gridDim.x * blockDim.x) {
-        const int c = (int)__ldg(&I.rootChild[i]);
-        if (c > 0 && W.ell[__ldg(&I.rootId[i])] != 0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
-    }
-    s = fxWarpSum(s);
-    if ((threadIdx.x & 31) == 0) fxAtomicAdd(W.acc->wcDen, s);
-}
-
 // The reference adds the U' values log1p(count) (and their squares) one by one into an f64 (placement.cpp:967-977).
 // That sequential sum drifts from the exact sum by O(U' * 2^-53) -- 1.7e-12 relative on the sars_20000 sample, more than the
 // 1e-12 parity tolerance, and nearly independent of the (unspecified, hash-map) order because the addends repeat.
-// sequentialDrift() returns the expectation of that drift over random orders, in closed form from the histogram of
+// driftOf() (pm_logic.cuh) returns the expectation of that drift over random orders, in closed form from the histogram of
 // read counts: while the running sum is in binade [2^e, 2^(e+1)) every addition of x is rounded to a multiple of
 // u = 2^(e-52), i.e. contributes rint(x/u)*u - x, and a fraction (hi-lo)/T of the additions happens in that binade.
 // Adding it to the exact fixed-point sum reproduces the reference's value to ~1e-14 relative.
@@ -1479,15 +1518,35 @@ __device__ __forceinline__ double blockSumF64(double e, double* sRed) {
     return tot;
 }
 
-__global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, WorkspaceView W, int configuredMinSupport, unsigned nFinParts) {
-    __shared__ double sRed[32];
-    __shared__ u64 sFx[32][4];
-    __shared__ long long sK[32];
-    __shared__ long long sM[32];
+// root_and_scalars: (i) the weighted-containment denominator over the ROOT's deltas (placement.cpp:1863-1876), all blocks;
+// (ii) in the block that finishes last: totals of the finalize pass from its per-block partials, the drift terms, the sample's scalars
+// (computeReadSeedMagnitudes, placement.cpp:957-984).  One launch instead of two, and nothing of (ii) goes through global memory twice.
+__global__ void __launch_bounds__(256) root_and_scalars(DevIndexView I, WorkspaceView W, int configuredMinSupport, unsigned nFinParts) {
+    __shared__ double sRed[8];
+    __shared__ u64 sFx[8][4];
+    __shared__ long long sK[8], sM[8];
+    __shared__ u64 sTot[4];
+    __shared__ long long sKept, sMaxc;
+    __shared__ unsigned sLast;
     SampleAcc* a = W.acc;
-    {   // totals of pass 2 from the per-block partials (exact, order independent)
+    const unsigned tid = threadIdx.x;
+    if (I.hasRoot && I.rootDCount) {
+        fx128 s = fxZero();
+        for (u64 i = (u64)blockIdx.x * blockDim.x + tid; i < I.rootDCount; i += (u64)gridDim.x * blockDim.x) {
+            const int c = (int)__ldg(&I.rootChild[i]);
+            if (c > 0 && W.ell[__ldg(&I.rootId[i])] != 0) s = fxAdd(s, fxFromDouble(1.0 / (double)c));
+        }
+        s = fxWarpSum(s);
+        if ((tid & 31) == 0 && (s.lo | (u64)s.hi)) fxAtomicAdd(a->wcDen, s);
+    }
+    __syncthreads();
+    if (tid == 0) { __threadfence(); sLast = (atomicAdd(&a->finDone, 1u) == gridDim.x - 1u) ? 1u : 0u; }
+    __syncthreads();
+    if (!sLast) return;
+    __threadfence();
+    {   // totals of the finalize pass from the per-block partials (exact, order independent)
         fx128 pm = fxZero(), pl = fxZero(); long long pk = 0, px = 0;
-        for (unsigned b = threadIdx.x; b < nFinParts; b += blockDim.x) {
+        for (unsigned b = tid; b < nFinParts; b += blockDim.x) {
             const FinPartial P = W.finPart[b];
             fx128 t; t.lo = P.mag[0]; t.hi = (i64)P.mag[1]; pm = fxAdd(pm, t);
             t.lo = P.lsum[0]; t.hi = (i64)P.lsum[1]; pl = fxAdd(pl, t);
@@ -1496,11 +1555,11 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
         pm = fxWarpSum(pm); pl = fxWarpSum(pl); pk = warpSumLL(pk);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) px = max(px, (long long)shflXorU64((u64)px, d));
-        if ((threadIdx.x & 31) == 0) { const int w = threadIdx.x >> 5; sFx[w][0] = pm.lo; sFx[w][1] = (u64)pm.hi; sFx[w][2] = pl.lo; sFx[w][3] = (u64)pl.hi; sK[w] = pk; sM[w] = px; }
+        if ((tid & 31) == 0) { const int w = tid >> 5; sFx[w][0] = pm.lo; sFx[w][1] = (u64)pm.hi; sFx[w][2] = pl.lo; sFx[w][3] = (u64)pl.hi; sK[w] = pk; sM[w] = px; }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             fx128 m = fxZero(), l = fxZero(); long long k = 0, x = 0;
-            for (int w = 0; w < 32; ++w) {
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
                 fx128 t; t.lo = sFx[w][0]; t.hi = (i64)sFx[w][1]; m = fxAdd(m, t);
                 t.lo = sFx[w][2]; t.hi = (i64)sFx[w][3]; l = fxAdd(l, t);
                 k += sK[w]; x = max(x, sM[w]);
@@ -1514,41 +1573,45 @@ __global__ void __launch_bounds__(1024) finish_scalars(DevIndexView I, Workspace
                 k += n1; x = max(x, 1LL);
             }
             a->magSq[0] = m.lo; a->magSq[1] = (u64)m.hi; a->logSum[0] = l.lo; a->logSum[1] = (u64)l.hi; a->kept = k; a->maxKeptCount = x;
+            sTot[0] = m.lo; sTot[1] = (u64)m.hi; sTot[2] = l.lo; sTot[3] = (u64)l.hi; sKept = k; sMaxc = x;
         }
         __syncthreads();
     }
-    fx128 m; m.lo = a->magSq[0]; m.hi = (i64)a->magSq[1];
-    fx128 l; l.lo = a->logSum[0]; l.hi = (i64)a->logSum[1];
-    fx128 w; w.lo = a->wcDen[0]; w.hi = (i64)a->wcDen[1];
+    fx128 m; m.lo = sTot[0]; m.hi = (i64)sTot[1];
+    fx128 l; l.lo = sTot[2]; l.hi = (i64)sTot[3];
     const double magSqExact = fxToDouble(m), logSumExact = fxToDouble(l);
     double eMag = 0.0, eLog = 0.0;
     if (logSumExact > 0.0 && magSqExact > 0.0) {
         Binades BM, BL;
         makeBinades(magSqExact, BM); makeBinades(logSumExact, BL);
-        const int cMax = (int)min((long long)kLog1pLut - 1, a->maxKeptCount);
-        for (int c = threadIdx.x; c <= cMax; c += blockDim.x) {
-            const unsigned mult = W.countHist[c];
-            if (!mult) continue;
-            const double x = I.log1pLut[c];
-            eMag += driftOf(BM, x * x) * (double)mult; eLog += driftOf(BL, x) * (double)mult;
+        const int cMax = (int)min((long long)kLog1pLut - 1, sMaxc);
+        for (int c0 = tid; c0 <= cMax; c0 += 4 * (int)blockDim.x) {   // four bins per turn: their loads are in flight together
+            unsigned mult[4]; double x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int c = c0 + q * (int)blockDim.x; mult[q] = c <= cMax ? __ldcg(&W.countHist[c]) : 0u; x[q] = c <= cMax ? __ldg(&I.log1pLut[c]) : 0.0; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (mult[q]) { eMag += driftOf(BM, x[q] * x[q]) * (double)mult[q]; eLog += driftOf(BL, x[q]) * (double)mult[q]; }
         }
     }
     const double dMag = blockSumF64(eMag, sRed);
     const double dLog = blockSumF64(eLog, sRed);
-    if (threadIdx.x != 0) return;
+    if (tid != 0) return;
+    fx128 w; w.lo = __ldcg(&a->wcDen[0]); w.hi = (i64)__ldcg(&a->wcDen[1]);
     SampleScalars S;
     S.readMagnitude = sqrt(magSqExact + dMag);
     S.logContDenom = logSumExact + dLog;
     S.wcDenom = fxToDouble(w);
-    S.uniqueKept = (double)a->kept;
+    S.uniqueKept = (double)sKept;
     S.minSupport = resolveMinSupport(a->multiSum, a->multiCount, configuredMinSupport);
     S.uniqueSeeds = a->unique;
-    S.uniqueKeptInt = a->kept;
+    S.uniqueKeptInt = sKept;
     S.totalFrequency = a->total;
     S.multiSum = a->multiSum; S.multiCount = a->multiCount;
     S.tableEntries = a->entries;
     S.overflow = a->overflow;
     *W.scalars = S;
+    a->finDone = 0;   // ready for the next pass over the same accumulators (staged scoring may run again without a new sample)
 }
 
 void launchTableScan(WorkspaceView W, const u64* homo, int nSM, unsigned* nPartsOut, cudaStream_t st) {
@@ -1559,11 +1622,9 @@ void launchTableScan(WorkspaceView W, const u64* homo, int nSM, unsigned* nParts
     *nPartsOut = g1;
 }
 void launchRootAndScalars(DevIndexView I, WorkspaceView W, PlaceOpts O, unsigned nFinParts, cudaStream_t st) {
-    if (I.hasRoot && I.rootDCount) {
-        u64 gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8;
-        noteLaunch(), root_denominator<<<(unsigned)gr, 256, 0, st>>>(I, W);
-    }
-    noteLaunch(), finish_scalars<<<1, 1024, 0, st>>>(I, W, O.minReadSupport, nFinParts);
+    u64 gr = 1;
+    if (I.hasRoot && I.rootDCount) { gr = ((u64)I.rootDCount + 255) / 256; if (gr > 148 * 8) gr = 148 * 8; }
+    noteLaunch(), root_and_scalars<<<(unsigned)gr, 256, 0, st>>>(I, W, O.minReadSupport, nFinParts);
 }
 void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st,
                     double seedMaskFraction, unsigned long long* maskScratch) {
@@ -2096,41 +2157,15 @@ __global__ void __launch_bounds__(256) bfs_records(DevIndexView I, WorkspaceView
 // tolerance chain over the records of one metric (block m).  Records are unordered: every step finds the
 // lowest-rank record after the last event that beats best + tol.
 __global__ void __launch_bounds__(256) chain_select(WorkspaceView W, const u32* __restrict__ countOverride) {
-    __shared__ unsigned long long sMin[8];
-    __shared__ unsigned long long sPick;
+    __shared__ ChainShared S;
     const int m = blockIdx.x;
     unsigned n = countOverride ? countOverride[m] : W.acc->recordCount[m];
     if (n > W.recCap) n = W.recCap;
     const u32* rk = W.recRank + (size_t)m * W.recCap;
     const u32* nd = W.recNode + (size_t)m * W.recCap;
     const double* sc = W.recScore + (size_t)m * W.recCap;
-    double best = 0.0; u32 bestNode = kNone; long long lastRank = -1;
-    while (true) {
-        const double tol = fmax(best * 0.0001, 1e-9);
-        const double thr = best + tol;
-        unsigned long long pick = ~0ULL;
-        for (unsigned i = threadIdx.x; i < n; i += 256) {
-            if ((long long)rk[i] > lastRank && sc[i] > thr) {
-                const unsigned long long key = ((unsigned long long)rk[i] << 32) | i;
-                pick = key < pick ? key : pick;
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = shflXorU64(pick, d); pick = o < pick ? o : pick; }
-        if ((threadIdx.x & 31) == 0) sMin[threadIdx.x >> 5] = pick;
-        __syncthreads();
-        if (threadIdx.x == 0) { unsigned long long v = sMin[0]; for (int w = 1; w < 8; ++w) v = sMin[w] < v ? sMin[w] : v; sPick = v; }
-        __syncthreads();
-        const unsigned long long p = sPick;
-        __syncthreads();
-        if (p == ~0ULL) break;
-        const unsigned i = (unsigned)(p & 0xFFFFFFFFu);
-        best = sc[i]; bestNode = nd[i]; lastRank = (long long)(p >> 32);
-    }
-    if (threadIdx.x == 0) {
-        Selection s; s.best = best; s.bestNode = bestNode; s.lastRank = lastRank < 0 ? kNone : (u32)lastRank;
-        W.sel[m] = s;
-    }
+    const Selection s = chainReplay(S, n, [&](unsigned i, u32& r, double& x, u32& v) { r = rk[i]; x = sc[i]; v = nd[i]; return true; });
+    if (threadIdx.x == 0) W.sel[m] = s;
 }
 void launchChain(WorkspaceView W, const u32* recCountOverride, cudaStream_t st) { noteLaunch(), chain_select<<<5, 256, 0, st>>>(W, recCountOverride); }
 

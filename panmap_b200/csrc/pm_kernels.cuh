@@ -32,6 +32,7 @@ struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample
     unsigned tieCount[8];
     long long n1NotIndex;   // sharded samples: kept seeds with read count 1 that the index does not hold (they travel as a count, not as entries)
     long long totalReads;   // sharded samples: reads of all ranks
+    unsigned finDone, pad1; // root_and_scalars: blocks that finished the root pass (the last one computes the scalars)
 };
 // bits of SampleAcc::overflow (any non-zero value makes the host grow what was too small and redo the sample)
 constexpr long long kOvfTable = 1, kOvfPair = 2, kOvfGather = 4, kOvfRecords = 8;

@@ -74,27 +74,29 @@ __global__ void __launch_bounds__(256) partition_export(WorkspaceView W, u32 nRa
         const unsigned o = atomicAdd(reinterpret_cast<u32*>(xSend), 1u);
         if (o < capPair) xSend[1 + o] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, (u32)min((long long)0xFFFFFFFFLL, W.acc->emptyKeyCount), 0u);
     }
-}
-// after the export: largest per-destination count (sizing feedback) and the overflow flag; also clears emptyKeyCount, whose
-// share now sits in rank 0's segment
-__global__ void partition_export_finish(WorkspaceView W, u32 nRanks, u32 capPair, uint4* xSend, u32* maxPair) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // after the export (the block that finishes last): largest per-destination count (sizing feedback) and the overflow flag; also
+    // clears emptyKeyCount, whose share now sits in rank 0's segment
+    __shared__ unsigned sLast;
+    if (!lastBlockDone(&W.acc->finDone, &sLast) || tid != 0) return;
     u32 mx = 0, sum = 0;
     for (u32 p = 0; p < nRanks; ++p) {
-        XHeader* h = reinterpret_cast<XHeader*>(xSend + (size_t)p * ((size_t)capPair + 1));
-        mx = max(mx, h->count); sum += h->count;
-        h->flags = (u32)W.acc->overflow;
+        XHeader* h = reinterpret_cast<XHeader*>(xSend + (size_t)p * segStride);
+        const u32 c = __ldcg(&h->count);
+        mx = max(mx, c); sum += c;
     }
     maxPair[0] = mx; maxPair[1] = sum;   // sizing feedback: largest per-destination count, unique seeds of the local table
     if (mx > capPair) raiseFlag(W.acc, kOvfPair);
+    __threadfence();
+    const u32 fl = (u32)atomicOr(reinterpret_cast<unsigned long long*>(&W.acc->overflow), 0ULL);
+    for (u32 p = 0; p < nRanks; ++p) reinterpret_cast<XHeader*>(xSend + (size_t)p * segStride)->flags = fl;
     W.acc->emptyKeyCount = 0;
 }
 void launchPartitionExport(WorkspaceView W, u32 nRanks, u32 capPair, uint4* xSend, u32* maxPairCount, cudaStream_t st) {
-    for (u32 p = 0; p < nRanks; ++p) cudaMemsetAsync(xSend + (size_t)p * ((size_t)capPair + 1), 0, sizeof(uint4), st);
+    // the nRanks segment headers (16 bytes at the start of every segment) with one strided memset
+    cudaMemset2DAsync(xSend, ((size_t)capPair + 1) * sizeof(uint4), 0, sizeof(uint4), nRanks, st);
     const u64 nTiles = (W.tableCap + kExpSlots - 1) / kExpSlots;
     const unsigned grid = (unsigned)std::min<u64>(nTiles ? nTiles : 1, 148ull * 4);
     noteLaunch(), partition_export<<<grid, 256, 0, st>>>(W, nRanks, capPair, xSend, maxPairCount);
-    noteLaunch(), partition_export_finish<<<1, 32, 0, st>>>(W, nRanks, capPair, xSend, maxPairCount);
 }
 
 // received segments -> the partition table
@@ -185,13 +187,12 @@ __global__ void __launch_bounds__(256) partition_finalize(DevIndexView I, Worksp
     if (lane == 0 && ones) atomicAdd(&sOne, ones);
     __syncthreads();
     if (tid == 0 && sOne) atomicAdd(reinterpret_cast<unsigned long long*>(&hdr->n1NotIndex), sOne);
-}
-// the flags go last (they must include what this very kernel sequence raised)
-__global__ void partition_finalize_finish(WorkspaceView W, uint2* gSend, u32 capG) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    GHeader* hdr = reinterpret_cast<GHeader*>(gSend);
-    if (hdr->nEntries > capG) raiseFlag(W.acc, kOvfGather);
-    hdr->flags = (u32)W.acc->overflow;
+    // the flags go last (they must include what this very kernel raised): the block that finishes last
+    __shared__ unsigned sLast;
+    if (!lastBlockDone(&acc->finDone, &sLast) || tid != 0) return;
+    if (__ldcg(&hdr->nEntries) > capG) raiseFlag(acc, kOvfGather);
+    __threadfence();
+    hdr->flags = (u32)atomicOr(reinterpret_cast<unsigned long long*>(&acc->overflow), 0ULL);
 }
 void launchPartitionFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, int nSM, uint2* gSend, u32 capG, u64 nLocalReads,
                              const u32* maxPairCount, u32 localEntriesHint, cudaStream_t st) {
@@ -199,7 +200,6 @@ void launchPartitionFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const
     launchTableScan(W, homo, nSM, &nParts, st);
     cudaMemsetAsync(gSend, 0, sizeof(GHeader), st);
     noteLaunch(), partition_finalize<<<(unsigned)nSM * 2, 256, 0, st>>>(I, W, O.minReadSupport, nParts, gSend, capG, nLocalReads, maxPairCount, localEntriesHint);
-    noteLaunch(), partition_finalize_finish<<<1, 32, 0, st>>>(W, gSend, capG);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -292,20 +292,18 @@ __global__ void __launch_bounds__(128) records_pack(WorkspaceView W, uint4* __re
         RRecord r; r.score = W.recScore[(size_t)m * W.recCap + i]; r.rank = W.recRank[(size_t)m * W.recCap + i]; r.node = W.recNode[(size_t)m * W.recCap + i];
         rec[(size_t)m * recX + i] = r;
     }
-}
-__global__ void records_pack_finish(WorkspaceView W, uint4* rSend) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) reinterpret_cast<RHeader*>(rSend)->flags = (u32)W.acc->overflow;
+    __shared__ unsigned sLast;   // the flags go last: they include what the five blocks raised
+    if (!lastBlockDone(&W.acc->finDone, &sLast) || threadIdx.x != 0) return;
+    hdr->flags = (u32)atomicOr(reinterpret_cast<unsigned long long*>(&W.acc->overflow), 0ULL);
 }
 void launchRecordsPack(WorkspaceView W, uint4* rSend, u32 recX, cudaStream_t st) {
     noteLaunch(), records_pack<<<5, 128, 0, st>>>(W, rSend, recX);
-    noteLaunch(), records_pack_finish<<<1, 32, 0, st>>>(W, rSend);
 }
 
 // the tolerance chain (placement.cpp:355-371) over the records of all ranks; block m = metric m.  Records of a rank are in no
 // particular order: every step picks the lowest-rank record after the last event that beats best + tol.
 __global__ void __launch_bounds__(256) chain_gathered(WorkspaceView W, const uint4* __restrict__ rRecv, u32 nRanks, u32 recX) {
-    __shared__ unsigned long long sMin[8];
-    __shared__ unsigned long long sPick;
+    __shared__ ChainShared S;
     __shared__ u32 sCount[kMaxRanks];
     const int m = blockIdx.x;
     const size_t rSlots = 2 + (size_t)5 * recX;
@@ -317,39 +315,13 @@ __global__ void __launch_bounds__(256) chain_gathered(WorkspaceView W, const uin
         if (m == 0 && fl) raiseFlag(W.acc, fl);
     }
     __syncthreads();
-    const unsigned total = nRanks * recX;
-    auto recAt = [&](unsigned idx) -> const RRecord* {
-        return reinterpret_cast<const RRecord*>(rRecv + (size_t)(idx / recX) * rSlots + 2) + (size_t)m * recX + (idx % recX);
-    };
-    double best = 0.0; u32 bestNode = kNone; long long lastRank = -1;
-    while (true) {
-        const double tol = fmax(best * 0.0001, 1e-9);
-        const double thr = best + tol;
-        unsigned long long pick = ~0ULL;
-        for (unsigned idx = threadIdx.x; idx < total; idx += 256) {
-            if ((idx % recX) >= sCount[idx / recX]) continue;
-            const RRecord* r = recAt(idx);
-            if ((long long)r->rank > lastRank && r->score > thr) {
-                const unsigned long long key = ((unsigned long long)r->rank << 32) | idx;
-                pick = key < pick ? key : pick;
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = shflXorU64(pick, d); pick = o < pick ? o : pick; }
-        if ((threadIdx.x & 31) == 0) sMin[threadIdx.x >> 5] = pick;
-        __syncthreads();
-        if (threadIdx.x == 0) { unsigned long long v = sMin[0]; for (int w = 1; w < 8; ++w) v = sMin[w] < v ? sMin[w] : v; sPick = v; }
-        __syncthreads();
-        const unsigned long long p = sPick;
-        __syncthreads();
-        if (p == ~0ULL) break;
-        const RRecord* r = recAt((unsigned)(p & 0xFFFFFFFFu));
-        best = r->score; bestNode = r->node; lastRank = (long long)(p >> 32);
-    }
-    if (threadIdx.x == 0) {
-        Selection s; s.best = best; s.bestNode = bestNode; s.lastRank = lastRank < 0 ? kNone : (u32)lastRank;
-        W.sel[m] = s;
-    }
+    const Selection s = chainReplay(S, nRanks * recX, [&](unsigned idx, u32& r, double& x, u32& v) {
+        if ((idx % recX) >= sCount[idx / recX]) return false;
+        const RRecord* rec = reinterpret_cast<const RRecord*>(rRecv + (size_t)(idx / recX) * rSlots + 2) + (size_t)m * recX + (idx % recX);
+        r = rec->rank; x = rec->score; v = rec->node;
+        return true;
+    });
+    if (threadIdx.x == 0) W.sel[m] = s;
 }
 void launchChainGathered(WorkspaceView W, const uint4* rRecv, u32 nRanks, u32 recX, cudaStream_t st) { noteLaunch(), chain_gathered<<<5, 256, 0, st>>>(W, rRecv, nRanks, recX); }
 

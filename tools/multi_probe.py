@@ -1,0 +1,32 @@
+#!/usr/bin/env python3
+"""One C3-shaped sample placed by N in-process ranks that all sit on device 0 (local transport): every kernel of the sharded data plane
+at its per-rank size, for an ncu launch list (times are per rank; the ranks run one after the other on the one GPU).
+usage: tools/multi_probe.py <n_ranks> [steps]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+import bench  # noqa: E402
+import panmap_b200 as pm  # noqa: E402
+from panmap_b200 import distributed as pmd  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]); steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    S, w = bench.make_workload("c3")
+    host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
+    wss = [pm.Workspace(pm.Index(host, device=0, shard=r, n_shards=n)) for r in range(n)]
+    comms = pm.Comm.local(wss)
+    for r in range(n):
+        reads, off = pmd.slice_reads(S.reads, S.read_offsets, r, n)
+        wss[r].upload(reads, off)
+    params = pm.PlaceParams()
+    for _ in range(steps):
+        res = pm.place_multi_resident(comms, params, full=False)
+    print("stage_ms", [round(x, 4) for x in res.stage_ms])
+
+
+if __name__ == "__main__":
+    main()
