@@ -642,6 +642,7 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
     index = pm.Index(host, device=local, shard=rank, n_shards=world)
     ws = pm.Workspace(index)
     comm = pmd.make_comm(ws)
+    transport = [""]
     reads, off = pmd.slice_reads(S.reads, S.read_offsets, rank, world)
     ws.upload(reads, off)
     for _ in range(warm):
@@ -666,6 +667,7 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
     wall = maxf(wall_local * 1e3 / steps)
     res = comm.place_sharded_resident(params)
     sent, recv = comm.last_traffic()
+    transport[0] = comm.transport()
     stage_max = [maxf(float(x)) for x in stage]
     # e2e: every rank's slice in pinned host memory -> result on every rank
     hp_reads = pinned_copy(L, reads); hp_off = pinned_copy(L, off)
@@ -737,7 +739,7 @@ def run_multi(args, pm, S, w, host, params, alg, pk, pk_src, world, rank, local)
                 "e2e_packed": {"value": nodes_reads / (e2ep_ms * 1e-3), "unit": "node*reads/s", "ms_per_step": e2ep_ms,
                                "span": "the same with every rank's slice as 4-bit codes (pm_place_sharded_packed)"},
                 "gpu_launches": launches_all, "gpu_launches_per_step": launches_all / steps,
-                "collective_bytes_per_step_rank0": {"sent": int(sent), "received": int(recv)},
+                "collective_bytes_per_step_rank0": {"sent": int(sent), "received": int(recv)}, "transport": transport[0],
                 "same_result_as_one_gpu": same,
                 "roofline": {"bound": "hbm", "kernel": "whole place stage (one sample, all ranks)", "achieved": alg["total"] / (per * 1e-3) / 1e9, "peak": float(pk["hbm_gbs"]) * world,
                              "unit": "GB/s", "frac": alg["total"] / (per * 1e-3) / 1e9 / (float(pk["hbm_gbs"]) * world), "traffic": None, "peak_source": pk_src},

@@ -247,6 +247,10 @@ int pm_place_multi(pm_comm* const* comms, int n_ranks, const char* reads, const 
 int pm_place_multi_resident(pm_comm* const* comms, int n_ranks, const pm_place_params* params, pm_place_result* result);
 /* bytes this rank sent / received through the transport for the last sample (collective payloads, capacities not fill levels) */
 int pm_comm_last_traffic(pm_comm* c, uint64_t* bytes_sent, uint64_t* bytes_received);
+/* how the exchanges of this communicator travel: "local" (in-process copies), "nccl", or "nccl bootstrap + peer-memory exchanges"
+ * (every rank's receive buffers mapped into the others through CUDA IPC; the payloads are stored over NVLink, NCCL only bootstraps).
+ * Decided at the first sample; PM_PEER_EXCHANGE=0 keeps NCCL. */
+const char* pm_comm_transport(pm_comm* c);
 
 /* placement::placeLite through the C++ host shim (panmap_b200/host/placement.hpp): FASTA/FASTQ(.gz) files in, result + <out_tsv> out.
  * node_ids = LiteNode ids by DFS index (for the TSV); err receives the exception text on failure. */

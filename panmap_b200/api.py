@@ -512,6 +512,10 @@ class Comm:
         _ck(lib().pm_comm_create_local(hs, n, out))
         return [cls(C.c_void_p(out[r]), workspaces[r], r, n) for r in range(n)]
 
+    def transport(self):
+        lib().pm_comm_transport.restype = C.c_char_p
+        return lib().pm_comm_transport(self._h).decode()
+
     def close(self):
         if self._h:
             lib().pm_comm_destroy(self._h)

@@ -36,6 +36,7 @@ struct SampleAcc {  // device-side accumulators of one sample (zeroed per sample
 };
 // bits of SampleAcc::overflow (any non-zero value makes the host grow what was too small and redo the sample)
 constexpr long long kOvfTable = 1, kOvfPair = 2, kOvfGather = 4, kOvfRecords = 8;
+constexpr long long kOvfPeer = 16;   // not a capacity: a peer's data did not arrive in time (peer-memory transport); never retried
 struct ScanPartial { long long multiSum, multiCount, entries, total; };          // one per table_scan block
 struct FinPartial { u64 mag[2], lsum[2]; long long kept; long long maxc; };        // one per entries_finalize block
 constexpr unsigned kMaxPartials = 2048;
@@ -196,6 +197,23 @@ void launchRecordsPack(WorkspaceView W, uint4* rSend, u32 recX, cudaStream_t st)
 void launchChainGathered(WorkspaceView W, const uint4* rRecv, u32 nRanks, u32 recX, cudaStream_t st);
 void launchTiesPack(WorkspaceView W, u32* tSend, const uint2* gSend, const u32* exportInfo /* [2] from launchPartitionExport */, cudaStream_t st);
 void launchTiesFullPack(WorkspaceView W, u32* out /* [5][capT] */, u32 capT, cudaStream_t st);
+// ---- peer-memory transport of the exchanges (one process per GPU, every rank's receive buffers mapped into every other rank) ----
+// push_segments stores this rank's payload straight into the peers' receive buffers over NVLink and then raises, in every peer,
+// the flag word (exchange, this rank) to `epoch`; wait_flags spins (bounded) until the flags of all ranks carry `epoch`.
+constexpr int kPeerMax = 32;
+struct PushArgs {
+    const unsigned char* src;      // send buffer
+    size_t srcStride;              // all-to-all: the segment for rank q starts at src + q * srcStride; all-gather: 0
+    unsigned char* dst[kPeerMax];  // receive buffer of rank q as mapped here (own rank: the local one)
+    size_t dstOffset;              // where this rank's segment starts inside a receive buffer
+    size_t segBytes;               // capacity of a segment
+    u32* flag[kPeerMax];           // flag word (exchange, this rank) inside rank q's flag block
+    u32 kind;                      // 0 seed segments (XHeader), 1 pairs (GHeader), 2 / 3 fixed size
+    u32 capEntries;                // kind 0: capPair, kind 1: capG
+    u32 n, epoch;
+};
+void launchPushSegments(const PushArgs& A, WorkspaceView W, cudaStream_t st);
+void launchWaitFlags(const u32* flags /* [n] of one exchange */, u32 n, u32 epoch, WorkspaceView W, cudaStream_t st);
 void launchResetGathered(DevIndexView I, WorkspaceView W, const uint2* gRecv, u32 nRanks, u32 capG, cudaStream_t st);
 void launchHashSeq(const char* seqs, const u64* off, u64 n, u64* fwd, u64* rev, unsigned char* status, cudaStream_t st);
 // pieces of launchFinalize the sharded path runs on their own

@@ -12,8 +12,12 @@
 //   P4  ONE device-to-host copy, reset
 // Nothing between P0 and P4 waits for the host: capacities are fixed per sample, fill counts travel in band, an overflow anywhere
 // reaches every rank with X3 and all ranks then redo the sample with the sizes the counts ask for.
-// Transports: NCCL on the workspace stream (one process per GPU; libnccl.so.2 resolved with dlopen so that the library loads on
-// machines without it), or in-process peer copies ordered by events (one host thread drives all ranks).
+// Transports.  One process per GPU: the ranks meet through NCCL (libnccl.so.2 resolved with dlopen so that the library loads on machines
+// without it), which carries the bootstrap -- sizing agreement and the CUDA IPC handles of every rank's receive buffers -- and, when the
+// buffers cannot be mapped, the exchanges themselves.  Once mapped, X0..X3 are plain 16-byte stores into the peers' buffers over NVLink
+// plus one flag word per peer (push_segments / wait_flags, pm_shard_kernels.cu): these payloads are a few megabytes at most, and four
+// NCCL collectives cost ~35-50 us each at 8 ranks where a store-and-flag exchange costs a launch.  PM_PEER_EXCHANGE=0 keeps NCCL.
+// One process, one host thread driving all ranks (tests, single-box tools): peer copies ordered by events.
 #include "pm_internal.h"
 
 #include <dlfcn.h>
@@ -87,6 +91,16 @@ struct pm_comm {
     cudaEvent_t ready[5]{};
     u64 nLocalReads = 0, localBases = 0;
     u64 sent = 0, received = 0;
+    // peer-memory transport (NCCL communicators whose ranks could map each other's receive buffers)
+    bool peerOn = false, peerOff = false;      // peerOff: tried and not available (or switched off): stay with NCCL
+    void* peerPtr[5][kPeerMax]{};              // [xRecv, gRecv, rRecv, tRecv, flags][rank]: that buffer of that rank as mapped in this process
+    void* peerOpened[5][kPeerMax]{};           // what cudaIpcOpenMemHandle returned, to be closed again
+    void* peerOpenedBase[5][kPeerMax]{};       // base of the opened allocation behind peerPtr (shared when two buffers sit in one allocation)
+    void* mappedLocal[5]{};                    // the local buffers the mapping was made for (a reallocation invalidates it)
+    DevBuf<u32> flags;                         // [4][kPeerMax]: flags[k][q] = epoch of the last exchange k whose payload from rank q is complete
+    DevBuf<unsigned char> ipcStage; PinBuf<unsigned char> hIpc;
+    u32 epoch = 0;
+    const char* transport = "local";
     // per-call inputs
     const char* hReads = nullptr; const uint4* hPacked = nullptr; const uint64_t* hOff = nullptr; bool resident = false;
 };
@@ -120,6 +134,23 @@ Xfer xferOf(pm_comm* c, int k, u32 capT) {
 }
 
 void exchange(std::vector<pm_comm*>& cs, int k, u32 capT = 0) {
+    if (cs[0]->nccl && cs[0]->peerOn && k <= 3) {
+        pm_comm* c = cs[0];
+        const Xfer x = xferOf(c, k, capT);
+        PushArgs A{};
+        A.src = static_cast<const unsigned char*>(x.send);
+        A.srcStride = k == 0 ? x.bytes : 0;
+        A.dstOffset = (size_t)c->rank * x.bytes; A.segBytes = x.bytes;
+        A.kind = (u32)k; A.capEntries = k == 0 ? c->capPair : c->capG; A.n = (u32)c->n; A.epoch = c->epoch;
+        for (int q = 0; q < c->n; ++q) {
+            A.dst[q] = static_cast<unsigned char*>(c->peerPtr[k][q]);
+            A.flag[q] = static_cast<u32*>(c->peerPtr[4][q]) + (size_t)k * kPeerMax + c->rank;
+        }
+        launchPushSegments(A, c->ws->view, c->ws->st);
+        launchWaitFlags(c->flags.p + (size_t)k * kPeerMax, (u32)c->n, c->epoch, c->ws->view, c->ws->st);
+        c->sent += x.bytes * (size_t)(c->n - 1); c->received += x.bytes * (size_t)(c->n - 1);   // capacity; only the filled part travels
+        return;
+    }
     if (cs[0]->nccl) {
         pm_comm* c = cs[0];
         NcclApi& N = ncclApi();
@@ -176,6 +207,93 @@ u64 agreeMax(std::vector<pm_comm*>& cs, u64 (*value)(pm_comm*)) {
         for (pm_comm* c : cs) mx = std::max(mx, value(c));
     }
     return mx;
+}
+
+// Maps every rank's receive buffers (and flag block) into this process.  Collective: all ranks call it at the same points (the
+// capacities that trigger it are agreed values) and all of them end up with the same answer -- a rank that cannot map makes everybody
+// stay with NCCL.
+bool peerExchangeWanted() {
+    static const bool v = [] { const char* e = std::getenv("PM_PEER_EXCHANGE"); return e ? std::atoi(e) != 0 : true; }();
+    return v;
+}
+void unmapPeers(pm_comm* c) {
+    for (int b = 0; b < 5; ++b)
+        for (int q = 0; q < kPeerMax; ++q) {
+            if (c->peerOpened[b][q]) { cudaIpcCloseMemHandle(c->peerOpened[b][q]); c->peerOpened[b][q] = nullptr; }
+            c->peerPtr[b][q] = nullptr; c->peerOpenedBase[b][q] = nullptr;
+        }
+    c->peerOn = false;
+}
+void mapPeers(pm_comm* c) {
+    if (!c->nccl || c->peerOff || c->n < 2) return;
+    void* mine[5] = {c->xRecv.p, c->gRecv.p, c->rRecv.p, c->tRecv.p, c->flags.p};
+    // the buffers only move when they grow, and they grow by the same rule from the same agreed capacities on every rank
+    if (c->peerOn && std::memcmp(mine, c->mappedLocal, sizeof(mine)) == 0) return;
+    if (!peerExchangeWanted()) { c->peerOff = true; return; }
+    cudaStream_t st = c->ws->st;
+    CK(cudaStreamSynchronize(st));   // nobody may still be writing into buffers that are about to be unmapped
+    unmapPeers(c);
+    if (!c->flags.p) { c->flags.alloc((size_t)4 * kPeerMax); CK(cudaMemsetAsync(c->flags.p, 0, (size_t)4 * kPeerMax * sizeof(u32), st)); }
+    mine[4] = c->flags.p;
+    constexpr size_t kHd = sizeof(cudaIpcMemHandle_t) + 8;        // handle of the allocation + offset of the buffer inside it
+    constexpr size_t kRec = 5 * kHd + 8;                           // five of those + "I can map" word
+    const size_t n = (size_t)c->n;
+    c->ipcStage.ensure((n + 1) * kRec); c->hIpc.ensure((n + 1) * kRec);
+    unsigned char* h = c->hIpc.p;
+    std::memset(h, 0, kRec);
+    bool ok = true;
+    // cudaMalloc may carve small buffers out of a larger allocation; an IPC handle always names the whole allocation
+    typedef int (*AddrRangeFn)(unsigned long long*, size_t*, unsigned long long);
+    AddrRangeFn addrRange = nullptr;
+    {
+        void* fn = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) addrRange = reinterpret_cast<AddrRangeFn>(fn);
+        else { cudaGetLastError(); ok = false; }
+    }
+    for (int b = 0; b < 5 && ok; ++b) {
+        cudaIpcMemHandle_t hd;
+        unsigned long long base = 0; size_t size = 0;
+        if (addrRange(&base, &size, (unsigned long long)(uintptr_t)mine[b]) != 0) { ok = false; break; }
+        if (cudaIpcGetMemHandle(&hd, reinterpret_cast<void*>((uintptr_t)base)) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        const u64 offset = (u64)((uintptr_t)mine[b] - (uintptr_t)base);
+        std::memcpy(h + (size_t)b * kHd, &hd, sizeof(hd));
+        std::memcpy(h + (size_t)b * kHd + sizeof(hd), &offset, 8);
+    }
+    auto gather = [&]() {   // record 0 of the host block -> records 1..n of everybody
+        CK(cudaMemcpyAsync(c->ipcStage.p, h, kRec, cudaMemcpyHostToDevice, st));
+        NK(ncclApi().AllGather(c->ipcStage.p, c->ipcStage.p + kRec, kRec, ncclChar, c->nccl, st));
+        CK(cudaMemcpyAsync(h + kRec, c->ipcStage.p + kRec, n * kRec, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    };
+    h[5 * kHd] = ok ? 1 : 0;
+    gather();
+    for (size_t q = 0; q < n; ++q) ok = ok && h[(1 + q) * kRec + 5 * kHd] == 1;
+    if (ok) {
+        for (size_t q = 0; q < n && ok; ++q)
+            for (int b = 0; b < 5 && ok; ++b) {
+                if ((int)q == c->rank) { c->peerPtr[b][q] = mine[b]; continue; }
+                cudaIpcMemHandle_t hd; u64 offset = 0;
+                std::memcpy(&hd, h + (1 + q) * kRec + (size_t)b * kHd, sizeof(hd));
+                std::memcpy(&offset, h + (1 + q) * kRec + (size_t)b * kHd + sizeof(hd), 8);
+                // two buffers of a rank may live in one allocation: an allocation can be opened only once per process
+                void* ptr = nullptr;
+                for (int pb = 0; pb < b && !ptr; ++pb)
+                    if (std::memcmp(h + (1 + q) * kRec + (size_t)pb * kHd, &hd, sizeof(hd)) == 0) ptr = c->peerOpenedBase[pb][q];
+                if (!ptr) {
+                    if (cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+                    c->peerOpened[b][q] = ptr;
+                }
+                c->peerOpenedBase[b][q] = ptr;
+                c->peerPtr[b][q] = static_cast<unsigned char*>(ptr) + offset;
+            }
+    }
+    // second round: did everybody manage to open everything?
+    h[5 * kHd] = ok ? 1 : 0;
+    gather();
+    for (size_t q = 0; q < n; ++q) ok = ok && h[(1 + q) * kRec + 5 * kHd] == 1;
+    if (!ok) { unmapPeers(c); c->peerOff = true; c->transport = "nccl"; return; }
+    c->peerOn = true; c->transport = "nccl bootstrap + peer-memory exchanges";
+    std::memcpy(c->mappedLocal, mine, sizeof(mine));
 }
 
 void phase0(pm_comm* c, const pm_place_params& prm) {
@@ -258,6 +376,7 @@ void runSharded(std::vector<pm_comm*>& cs, const pm_place_params* prm, pm_place_
     }
     for (int attempt = 0; attempt < 6; ++attempt) {
         for (pm_comm* c : cs) { c->capG = (c->capG + 1u) & ~1u; setDevice(c->ws->idx->device); ensureBuffers(c); }   // even: per-rank segments stay 16-byte aligned
+        for (pm_comm* c : cs) { mapPeers(c); ++c->epoch; }
         for (pm_comm* c : cs) phase0(c, *prm);
         exchange(cs, 0);
         for (pm_comm* c : cs) phase1(c, *prm);
@@ -277,6 +396,8 @@ void runSharded(std::vector<pm_comm*>& cs, const pm_place_params* prm, pm_place_
             for (int m = 0; m < 5; ++m) maxTie = std::max(maxTie, h->tieCount[m]);
         }
         const u32 wantPair = maxPair + maxPair / 4 + 1024, wantG = maxG + maxG / 4 + 1024;
+        for (pm_comm* c : cs) flags |= (u32)c->ws->hAcc.overflow & (u32)kOvfPeer;   // the last exchange itself may have timed out
+        if (flags & (u32)kOvfPeer) throw std::runtime_error("sharded placement: a rank's data did not arrive (peer-memory exchange timed out)");
         if (flags) {
             if (attempt == 5) break;
             for (pm_comm* c : cs) {
@@ -381,7 +502,7 @@ int pm_comm_create_nccl(pm_workspace* ws, const void* id, int rank, int n_ranks,
     return guarded([&]() -> int {
         setDevice(ws->idx->device);
         std::unique_ptr<pm_comm> c(new pm_comm());
-        c->rank = rank; c->n = n_ranks; c->ws = ws; c->device = ws->device;
+        c->rank = rank; c->n = n_ranks; c->ws = ws; c->device = ws->device; c->transport = "nccl";
         ncclUniqueId uid; std::memcpy(&uid, id, sizeof(uid));
         NK(ncclApi().CommInitRank(&c->nccl, n_ranks, uid, rank));
         *out = c.release();
@@ -420,6 +541,7 @@ void pm_comm_destroy(pm_comm* c) {
     cudaSetDevice(c->device);
     if (workspaceAlive(c->ws)) cudaStreamSynchronize(c->ws->st);   // a binding's garbage collector may have destroyed the workspace first
     else cudaDeviceSynchronize();
+    unmapPeers(c);
     if (c->nccl) { try { ncclApi().CommDestroy(c->nccl); } catch (...) {} }
     for (auto& e : c->ready) if (e) cudaEventDestroy(e);
     if (c->grp) for (auto& m : c->grp->members) if (m == c) m = nullptr;
@@ -496,6 +618,8 @@ int pm_place_multi_resident(pm_comm* const* comms, int n_ranks, const pm_place_p
         return PM_OK;
     });
 }
+
+const char* pm_comm_transport(pm_comm* c) { return c ? c->transport : ""; }
 
 int pm_comm_last_traffic(pm_comm* c, uint64_t* bytes_sent, uint64_t* bytes_received) {
     if (!c) return fail(PM_ERR_INVALID, "null argument");

@@ -368,6 +368,50 @@ __global__ void __launch_bounds__(256) hash_seq(const char* __restrict__ seqs, c
         fwd[q] = f; rev[q] = r; status[q] = bad ? 1 : 0;
     }
 }
+// ------------------------------------------------------------------------------------------------------
+// peer-memory exchanges (pm_multi.cu): the collectives of this path move a few megabytes at most and are bound by launch and
+// protocol latency, so every rank simply WRITES its payload into the peers' buffers -- 16-byte stores over NVLink -- and raises one
+// flag word per peer when the last block is through.  Only the filled part of a segment travels (its header says how much).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) push_segments(PushArgs A, WorkspaceView W) {
+    __shared__ unsigned sLast;
+    const u32 perPeer = gridDim.x / A.n;                 // blocks per destination
+    const u32 q = blockIdx.x / perPeer, part = blockIdx.x % perPeer;
+    if (q < A.n) {
+        const unsigned char* src = A.src + (size_t)q * A.srcStride;
+        size_t bytes = A.segBytes;
+        if (A.kind == 0) bytes = ((size_t)min(reinterpret_cast<const XHeader*>(src)->count, A.capEntries) + 1) * sizeof(uint4);
+        else if (A.kind == 1) bytes = (((size_t)min(reinterpret_cast<const GHeader*>(src)->nEntries, A.capEntries) + kGHeaderSlots) * sizeof(uint2) + 15) & ~(size_t)15;
+        if (bytes > A.segBytes) bytes = A.segBytes;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(A.dst[q] + A.dstOffset);
+        const size_t n16 = bytes / 16;
+        for (size_t i = (size_t)part * 256 + threadIdx.x; i < n16; i += (size_t)perPeer * 256) d4[i] = s4[i];
+    }
+    __threadfence_system();                              // this thread's remote stores are out before the block reports in
+    if (!lastBlockDone(&W.acc->finDone, &sLast)) return;
+    __threadfence_system();
+    if (threadIdx.x < A.n) *reinterpret_cast<volatile u32*>(A.flag[threadIdx.x]) = A.epoch;
+}
+void launchPushSegments(const PushArgs& A, WorkspaceView W, cudaStream_t st) {
+    const size_t per = (A.segBytes / 16 + 256 * 8 - 1) / (256 * 8);           // ~8 stores per thread
+    const unsigned perPeer = (unsigned)std::min<size_t>(std::max<size_t>(per, 1), 64);
+    noteLaunch(), push_segments<<<perPeer * A.n, 256, 0, st>>>(A, W);
+}
+// bounded wait (about half a minute of polling): a rank that never delivers must not hang the GPU; the sample then fails with kOvfPeer
+__global__ void wait_flags(const u32* __restrict__ flags, u32 n, u32 epoch, WorkspaceView W) {
+    if (threadIdx.x < n) {
+        const volatile u32* f = flags + threadIdx.x;
+        const long long t0 = clock64();
+        while (*f != epoch) {
+            __nanosleep(200);
+            if (clock64() - t0 > 60000000000LL) { raiseFlag(W.acc, kOvfPeer); break; }
+        }
+    }
+    __threadfence_system();
+}
+void launchWaitFlags(const u32* flags, u32 n, u32 epoch, WorkspaceView W, cudaStream_t st) { noteLaunch(), wait_flags<<<1, 32, 0, st>>>(flags, n, epoch, W); }
+
 void launchHashSeq(const char* seqs, const u64* off, u64 n, u64* fwd, u64* rev, unsigned char* status, cudaStream_t st) {
     if (n) noteLaunch(), hash_seq<<<streamGrid(n, 1), 256, 0, st>>>(seqs, off, n, fwd, rev, status);
 }

@@ -2,7 +2,9 @@
 torch.distributed (gloo), then pm_place_sharded on every rank -- seeding of the rank's read slice, all-to-all of the seed partitions,
 all-gathers of the finalized pairs / records / tie heads, all enqueued by the library on its own stream.  Every rank must return the
 oracle's placement (integers, best nodes and tie lists bit-exact, scores to 1e-12), from host buffers and from resident reads,
-also right after a much smaller sample (capacities regrown in lock-step on all ranks)."""
+also right after a much smaller sample (capacities regrown in lock-step on all ranks).  Both transports of the exchanges are run:
+NCCL collectives, and the peer-memory one (every rank's receive buffers mapped into the others through CUDA IPC, payloads stored over
+NVLink, NCCL only as the bootstrap), which must actually be the one in use when it is asked for."""
 import os
 import socket
 
@@ -14,8 +16,9 @@ import panmap_b200 as pm
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, peer):
     try:
+        os.environ["PM_PEER_EXCHANGE"] = peer
         import torch.distributed as dist
         from oracle import cpu
         from panmap_b200 import distributed as pmd
@@ -50,15 +53,18 @@ def _worker(rank, world, port, q):
                 ok = ok and H.relerr(res.best_score[name], exp["best_score"][m]).max() < 1e-12
         sent, recv = comm.last_traffic()
         ok = ok and sent > 0 and recv > 0
+        tr = comm.transport()
+        ok = ok and (("peer-memory" in tr) if peer == "1" else tr == "nccl")
         comm.close()
-        q.put((rank, bool(ok), ""))
+        q.put((rank, bool(ok), "" if ok else f"transport={tr}"))
         dist.destroy_process_group()
     except Exception as e:  # surface the failure in the parent
         import traceback
         q.put((rank, False, traceback.format_exc()))
 
 
-def test_nccl_sharded_sample_matches_oracle_on_every_rank():
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_nccl_sharded_sample_matches_oracle_on_every_rank(peer):
     world = pm.device_count()
     if world < 2:
         pytest.skip("needs at least two CUDA devices")
@@ -67,7 +73,7 @@ def test_nccl_sharded_sample_matches_oracle_on_every_rank():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q, peer)) for r in range(world)]
     for p in ps:
         p.start()
     out = [q.get(timeout=600) for _ in ps]
