@@ -58,50 +58,68 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)"""
+    """SM clock + clock-event (throttle) reasons DURING the timed region (B200_PROFILING.md's clocks line).  The timed regions here are tens of
+    milliseconds, so the samples come from NVML inside a thread (one query is ~0.1 ms; a sample every millisecond) rather than from an
+    `nvidia-smi -lms 100` child, which cannot deliver a single line in that time; nvidia-smi stays as the fallback when NVML is unusable."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+               ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, gpu=0):
-        self.gpu = gpu
-        self.rows = []
-        self.proc = None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip().isdigit()]
+        self.gpu = int(ids[gpu]) if gpu < len(ids) else gpu
+        self.sm, self.mask, self.mx = [], 0, None
+        self.stop_flag = threading.Event()
+        self.th = None
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        while True:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            if self.stop_flag.wait(0.001):
+                return
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.source = None
+            self.th = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _smi_once(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+            self.sm.append(float(f[0])); self.mx = float(f[1])
+            for (n, bit), v in zip(self.REASONS[:4], f[2:6]):
+                if v.lower().startswith("active"):
+                    self.mask |= bit
+            self.source = "nvidia-smi (one query right after the timed region, GPU still clocked up)"
+        except Exception:
+            pass
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        if self.th is not None:
+            self.stop_flag.set()
+            self.th.join(timeout=2)
+        if not self.sm:
+            self._smi_once()
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        reasons = sorted(n for n, bit in self.REASONS if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": reasons, "samples": len(self.sm), "source": self.source}
 
 
 class RealSample:
@@ -382,13 +400,17 @@ def main():
     # names (node_deltas) is reported next to it the same way.
     peak = float(pk["hbm_gbs"])
     traffic, capture = ncu_traffic()
-    names = ["h2d", "seeding+table insert (syncmers_fast, count_seeds)", "table finalize", "node_deltas", "prefix_scores", "selection", "d2h"]
-    per_kernel = {"pack_reads": float(kern[0]), "syncmers_fast<19,8>": float(kern[1]), "count_seeds<19,3>": float(kern[2]),
+    # kernel names as the library picks them (pm_kernels.cu launchSyncmers / launchCount): s = 8 and >= 20 k reads -> syncmers_rank, else
+    # syncmers_fast; whole samples count with one lane per read
+    syn_name = (f"syncmers_rank<{S.k}>" if int(S.s) == 8 and w["n_reads"] >= 20000 else f"syncmers_fast<{S.k},{S.s}>")
+    cnt_name = f"count_seeds_lane<{S.k},{S.l}>" if w["n_reads"] >= 200000 else f"seeds_from_syncmers / count_seeds<{S.k},{S.l}>"
+    names = ["h2d", f"seeding+table insert ({syn_name.split('<')[0]}, {cnt_name.split('<')[0]})", "table finalize", "node_deltas", "prefix_scores", "selection", "d2h"]
+    per_kernel = {"pack_reads": float(kern[0]), syn_name: float(kern[1]), cnt_name: float(kern[2]),
                   "node_deltas": float(stage[3]), "prefix_scores": float(stage[4])}
     if per_kernel["pack_reads"] < 0.01:   # the default parameter sets hash straight from the ASCII reads: no pack_reads launch
         del per_kernel["pack_reads"]
     dom_name = max(per_kernel, key=per_kernel.get)
-    dom_bytes = {"pack_reads": alg["seeding"] * 3 // 2, "syncmers_fast<19,8>": alg["seeding"], "count_seeds<19,3>": 12 * int(res.raw.unique_seeds),
+    dom_bytes = {"pack_reads": alg["seeding"] * 3 // 2, syn_name: alg["seeding"], cnt_name: 12 * int(res.raw.unique_seeds),
                  "node_deltas": alg["delta_kernel"], "prefix_scores": 80 * S.n_nodes}[dom_name]
     ach = dom_bytes / (per_kernel[dom_name] * 1e-3) / 1e9
     sc_ach = alg["delta_kernel"] / (stage[3] * 1e-3) / 1e9
@@ -411,8 +433,9 @@ def main():
         "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": traffic.get(dom_name.split("<")[0]), "traffic_capture": capture, "algorithmic_bytes_per_launch": dom_bytes, "ms": per_kernel[dom_name],
                      "peak_source": pk_src,
-                     "note": "dominant kernel of the step by measured time; it is limited by the integer ALU pipe (ncu: pipe_alu 84-88 %), one byte in per ~120 "
-                             "integer instructions, so the HBM fraction is small by construction -- see roofline_scoring for the HBM-bound kernel north_star names"},
+                     "note": "dominant kernel of the step by measured time; it is limited by the integer ALU and L1 data pipes (ncu r02e: pipe_alu 68 %, l1 data "
+                             "pipe 77 %, issue 54 %), one base in per ~58 thread instructions, so the HBM fraction is small by construction -- see roofline_scoring for the "
+                             "HBM-bound kernel north_star names"},
         "roofline_scoring": {"bound": "hbm", "kernel": "node_deltas (the scoring kernel north_star names)", "achieved": sc_ach, "peak": peak, "unit": "GB/s",
                              "frac": sc_ach / peak, "traffic": traffic.get("node_deltas"), "algorithmic_bytes_per_launch": alg["delta_kernel"], "ms": float(stage[3]),
                              "note": "algorithmic bytes = 12 B/delta + 8 B/node of the reference layout (SURVEY 8d); the kernel itself streams 4 B/delta"},

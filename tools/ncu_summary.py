@@ -13,6 +13,28 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__t_bytes.sum", "smsp__average_warp_latency_per_inst_issued.ratio"]
 
 
+def traffic_json(paths, dest):
+    """profiles/ncu_traffic.json: dram__bytes_read + dram__bytes_write per launch (mean over the captured launches) of every kernel in the
+    given --set full captures; bench.py reads it for roofline.traffic"""
+    import json
+    import os
+    acc = {}
+    for path in paths:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units = rows[0], rows[1]
+        ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            name = r[ki].split("(")[0].replace("void ", "").split("<")[0].strip()
+            b = float(r[ri]) * scale[units[ri]] + float(r[wi]) * scale[units[wi]]
+            acc.setdefault(name, []).append(b)
+    d = {"capture": ", ".join(os.path.basename(p) for p in paths), "unit": "bytes per launch (dram read + write, ncu --set full)",
+         "kernels": {k: sum(v) / len(v) for k, v in acc.items()}}
+    json.dump(d, open(dest, "w"), indent=1)
+    print(json.dumps(d))
+
+
 def main(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -30,4 +52,7 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if sys.argv[1] == "--json":      # tools/ncu_summary.py --json profiles/ncu_traffic.json a.ncu-rep [b.ncu-rep ...]
+        traffic_json(sys.argv[3:], sys.argv[2])
+    else:
+        main(sys.argv[1])
