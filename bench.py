@@ -460,6 +460,23 @@ def main():
             except Exception as e:  # reported, never fatal
                 spans["file_to_result_error"] = str(e)
         line["spans"] = spans
+        if not args.no_file_span:
+            # opening the index (not part of a placement): .idx -> parse + flatten + upload, against the cached flattened image
+            try:
+                ip = getattr(S, "idx_path", None)
+                if ip is None:
+                    ip = os.path.join(td, "bench.idx")
+                    host.write(ip)
+                else:
+                    import shutil
+                    ip2 = os.path.join(td, "bench.idx"); shutil.copyfile(ip, ip2); ip = ip2
+                t0 = time.perf_counter(); i1 = pm.Index.open_cached(ip); t1 = time.perf_counter(); i2 = pm.Index.open_cached(ip); t2 = time.perf_counter()
+                line["index_open"] = {"idx_bytes": os.path.getsize(ip), "image_bytes": os.path.getsize(ip + ".pmflat"),
+                                      "parse_flatten_write_image_upload_ms": 1e3 * (t1 - t0), "cached_image_upload_ms": 1e3 * (t2 - t1),
+                                      "first_was_miss": i1.cache_hit is False, "second_was_hit": i2.cache_hit is True}
+                del i1, i2
+            except Exception as e:  # reported, never fatal
+                line["index_open"] = {"error": str(e)}
         if not args.no_cpu_baseline:
             try:
                 from oracle import ref

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 2
+#define PM_ABI_VERSION 3
 #define PM_NONE 0xFFFFFFFFu /* "no node" (reference: UINT32_MAX, placement.hpp:159) */
 #define PM_NUM_METRICS 5    /* log_raw, log_cosine, containment, weighted_containment, log_containment */
 
@@ -110,12 +110,35 @@ int pm_host_index_read(const char* path, pm_host_index** out);
 void pm_host_index_free(pm_host_index* h);
 int pm_host_index_desc(const pm_host_index* h, pm_index_desc* out); /* pointers stay owned by h */
 const char* pm_host_index_node_id(const pm_host_index* h, uint64_t node); /* LiteNode.id */
+/* What a LiteIndex holds besides the seed deltas; placement reads none of it except the ids, other stages do (mgsr.cpp:436-471), so a
+ * read -> write round trip carries it through.  Every pointer may be NULL. */
+typedef struct pm_index_extras {
+    const char* const* node_ids;        /* [n_nodes] LiteNode.id; "node_<i>" when NULL */
+    const uint8_t* identical_to_parent; /* [n_nodes] LiteNode.identicalToParent */
+    const uint32_t* block_ranges;       /* [2 * n_blocks] LiteTree.blockRanges as (rangeBeg, rangeEnd) */
+    uint64_t n_blocks;
+    const double* substitution_matrix;  /* [16] LiteIndex.substitutionMatrix */
+} pm_index_extras;
+int pm_host_index_extras(const pm_host_index* h, pm_index_extras* out); /* pointers stay owned by h */
+/* IndexBuilder::writeIndex (index_single_mode.cpp:1593-1636): PMI1 header + LiteIndex message (formatVersion 4), uncompressed when
+ * zstd_level < 0, else independent 64 MB zstd frames at that level.  The file is readable by the reference's IndexReader
+ * (main.cpp:193-236) and by pm_host_index_read.  One Cap'n Proto segment: PM_ERR_UNSUPPORTED beyond 4 GB of message. */
+int pm_host_index_write(const char* path, const pm_index_desc* desc, const pm_index_extras* extras, int zstd_level, uint64_t* bytes_out);
 
 /* ---- device index (replaces LiteTree::initialize + the SoA hookup, placement.cpp:1021-1092).
  *      node_begin/node_end select a shard of whole tiles for multi-GPU runs (0,0 = all nodes). ---- */
 int pm_index_create(const pm_index_desc* desc, int device, pm_index** out);
 int pm_index_create_shard(const pm_index_desc* desc, int device, uint32_t shard, uint32_t n_shards, pm_index** out);
 void pm_index_destroy(pm_index* idx);
+/* Cached image of the flattened index: the arrays pm_index_create derives from a LiteIndex (packed delta words, segment masks, seed
+ * dictionary, tile chains, BFS order), stored next to the .idx so that later runs skip the parse and the flattening.  Same rule as the
+ * reference's own index cache (cachedIndexUsable, main.cpp:371-396): an image is used only if it was made from exactly this file
+ * (size, mtime, PMI1 header with the seeding parameters) for this shard; anything else re-flattens and rewrites it.
+ * image_path NULL = idx_path + ".pmflat" (+ ".<shard>of<n>" for shards); *cache_hit reports which way it went. */
+int pm_index_open_cached(const char* idx_path, const char* image_path, int device, uint32_t shard, uint32_t n_shards, pm_index** out, int* cache_hit);
+int pm_index_image_write(const pm_index_desc* desc, const char* const* node_ids, uint32_t shard, uint32_t n_shards, const char* image_path, uint64_t* bytes_out);
+int pm_index_create_from_image(const char* image_path, int device, pm_index** out); /* no source check: the caller vouches for the image */
+const char* pm_index_node_id(const pm_index* idx, uint64_t node); /* ids travel with indexes opened from a file or an image; "" otherwise */
 uint64_t pm_index_num_nodes(const pm_index* idx);
 uint64_t pm_index_num_deltas(const pm_index* idx);
 uint64_t pm_index_num_distinct_seeds(const pm_index* idx);

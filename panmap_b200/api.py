@@ -50,6 +50,12 @@ class PlaceParams(C.Structure):
             setattr(self, k, v)
 
 
+class IndexExtras(C.Structure):
+    """== pm_index_extras: what a LiteIndex holds besides the seed deltas (ids, identicalToParent, blockRanges, substitutionMatrix)"""
+    _fields_ = [("node_ids", C.POINTER(C.c_char_p)), ("identical_to_parent", C.c_void_p), ("block_ranges", C.c_void_p), ("n_blocks", C.c_uint64),
+                ("substitution_matrix", C.c_void_p)]
+
+
 class PlaceResult(C.Structure):
     _fields_ = [("best_score", C.c_double * 5), ("best_index", C.c_uint32 * 5), ("tied_count", C.c_uint64 * 5),
                 ("total_reads", C.c_uint64), ("unique_seeds", C.c_uint64), ("read_unique_seed_count", C.c_uint64),
@@ -77,6 +83,13 @@ def lib():
     L.pm_host_index_read.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
     L.pm_host_index_free.argtypes = [C.c_void_p]
     L.pm_host_index_desc.argtypes = [C.c_void_p, C.POINTER(IndexDesc)]
+    L.pm_host_index_extras.argtypes = [C.c_void_p, C.POINTER(IndexExtras)]
+    L.pm_host_index_write.argtypes = [C.c_char_p, C.POINTER(IndexDesc), C.POINTER(IndexExtras), C.c_int, C.POINTER(C.c_uint64)]
+    L.pm_index_open_cached.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    L.pm_index_image_write.argtypes = [C.POINTER(IndexDesc), C.POINTER(C.c_char_p), C.c_uint32, C.c_uint32, C.c_char_p, C.POINTER(C.c_uint64)]
+    L.pm_index_create_from_image.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.pm_index_node_id.restype = C.c_char_p
+    L.pm_index_node_id.argtypes = [C.c_void_p, C.c_uint64]
     L.pm_index_create.argtypes = [C.POINTER(IndexDesc), C.c_int, C.POINTER(C.c_void_p)]
     L.pm_index_create_shard.argtypes = [C.POINTER(IndexDesc), C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]
     L.pm_index_destroy.argtypes = [C.c_void_p]
@@ -198,6 +211,29 @@ class HostIndex:
         self.node_ids = node_ids
         self.n_nodes = int(self.parent_index.size)
         self.n_deltas = int(self.hash.size)
+        self.identical_to_parent = None     # u8[n_nodes]
+        self.block_ranges = None            # u32[n_blocks, 2]
+        self.substitution_matrix = None     # f64[16]
+
+    def write(self, path, zstd_level=-1):
+        """IndexBuilder::writeIndex (index_single_mode.cpp:1593-1636): PMI1 header + LiteIndex message; zstd_level < 0 = uncompressed.
+        Returns the file size."""
+        d = self.desc()
+        x = IndexExtras()
+        keep = []
+        if self.node_ids is not None:
+            ids = (C.c_char_p * self.n_nodes)(*[i.encode() for i in self.node_ids])
+            keep.append(ids)
+            x.node_ids = C.cast(ids, C.POINTER(C.c_char_p))
+        if self.identical_to_parent is not None:
+            a = np.ascontiguousarray(self.identical_to_parent, np.uint8); keep.append(a); x.identical_to_parent = _ptr(a)
+        if self.block_ranges is not None and len(self.block_ranges):
+            a = np.ascontiguousarray(self.block_ranges, np.uint32).reshape(-1); keep.append(a); x.block_ranges = _ptr(a); x.n_blocks = a.size // 2
+        if self.substitution_matrix is not None:
+            a = np.ascontiguousarray(self.substitution_matrix, np.float64).reshape(-1); keep.append(a); x.substitution_matrix = _ptr(a)
+        n = C.c_uint64()
+        _ck(lib().pm_host_index_write(os.fsencode(path), C.byref(d), C.byref(x), int(zstd_level), C.byref(n)))
+        return n.value
 
     @classmethod
     def read(cls, path):
@@ -214,9 +250,18 @@ class HostIndex:
                     return np.zeros(0, dtype=dt)
                 return np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,)).copy()
             ids = [L.pm_host_index_node_id(h, i).decode() for i in range(N)]
-            return cls(arr(d.delta_hash, D, np.uint64), arr(d.delta_parent, D, np.int16), arr(d.delta_child, D, np.int16),
-                       arr(d.node_offsets, N + 1, np.uint64), arr(d.parent_index, N, np.uint32),
-                       d.seed.k, d.seed.s, d.seed.t, d.seed.l, d.seed.open, d.seed.hpc, ids)
+            out = cls(arr(d.delta_hash, D, np.uint64), arr(d.delta_parent, D, np.int16), arr(d.delta_child, D, np.int16),
+                      arr(d.node_offsets, N + 1, np.uint64), arr(d.parent_index, N, np.uint32),
+                      d.seed.k, d.seed.s, d.seed.t, d.seed.l, d.seed.open, d.seed.hpc, ids)
+            x = IndexExtras()
+            _ck(L.pm_host_index_extras(h, C.byref(x)))
+            if x.identical_to_parent:
+                out.identical_to_parent = arr(x.identical_to_parent, N, np.uint8)
+            if x.block_ranges:
+                out.block_ranges = arr(x.block_ranges, 2 * x.n_blocks, np.uint32).reshape(-1, 2)
+            if x.substitution_matrix:
+                out.substitution_matrix = arr(x.substitution_matrix, 16, np.float64)
+            return out
         finally:
             L.pm_host_index_free(h)
 
@@ -235,9 +280,41 @@ class Index:
     def __init__(self, host, device=0, shard=0, n_shards=1):
         self.host = host
         self._h = C.c_void_p()
+        self.cache_hit = None
+        if host is None:
+            return
         d = host.desc()
         _ck(lib().pm_index_create_shard(C.byref(d), device, shard, n_shards, C.byref(self._h)))
         self.n_nodes = host.n_nodes
+
+    @classmethod
+    def open_cached(cls, idx_path, image_path=None, device=0, shard=0, n_shards=1):
+        """open a .idx through its cached flattened image (written on a miss); .cache_hit says which way it went"""
+        self = cls(None)
+        hit = C.c_int()
+        _ck(lib().pm_index_open_cached(os.fsencode(idx_path), os.fsencode(image_path) if image_path else None, device, shard, n_shards,
+                                       C.byref(self._h), C.byref(hit)))
+        self.cache_hit = bool(hit.value)
+        self.n_nodes = int(lib().pm_index_num_nodes(self._h))
+        return self
+
+    @classmethod
+    def from_image(cls, image_path, device=0):
+        self = cls(None)
+        _ck(lib().pm_index_create_from_image(os.fsencode(image_path), device, C.byref(self._h)))
+        self.n_nodes = int(lib().pm_index_num_nodes(self._h))
+        return self
+
+    def node_id(self, i):
+        return lib().pm_index_node_id(self._h, int(i)).decode()
+
+    def node_ids(self):
+        """LiteNode ids: the host index's when there is one, else the ones that travelled with the file / image (None when there are none)"""
+        if self.host is not None:
+            return self.host.node_ids
+        if not hasattr(self, "_ids"):
+            self._ids = [self.node_id(i) for i in range(self.n_nodes)] if self.n_nodes and self.node_id(0) else None
+        return self._ids
 
     def close(self):
         if self._h:
@@ -321,7 +398,7 @@ class Workspace:
             if n:
                 _ck(lib().pm_get_tied(self._h, m, _ptr(t), n))
             tied.append(t)
-        return Placement(res, tied, self.index.host.node_ids)
+        return Placement(res, tied, self.index.node_ids())
 
     def place(self, reads, offsets, params=None):
         params = params or PlaceParams()
@@ -634,7 +711,7 @@ def read_fastx(reads1, reads2=""):
 def place_files(workspace, reads1, reads2="", out_tsv="", params=None):
     """placement::placeLite through the C++ host shim (files in, TSV out); returns the PlaceResult struct"""
     params = params or PlaceParams()
-    ids = workspace.index.host.node_ids or []
+    ids = workspace.index.node_ids() or []
     arr = (C.c_char_p * max(len(ids), 1))(*[i.encode() for i in ids])
     res = PlaceResult()
     err = C.create_string_buffer(512)

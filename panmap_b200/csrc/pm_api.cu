@@ -68,15 +68,10 @@ static void buildViews(pm_index* I) {
     V.ln2 = std::log1p(1.0);
 }
 
-static int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t nShards, pm_index** out) {
-    if (!desc || !out) return fail(PM_ERR_INVALID, "null argument");
-    *out = nullptr;
-    if (deviceCountNoThrow() <= device || device < 0)
-        return fail(PM_ERR_NO_DEVICE, "no usable CUDA device " + std::to_string(device) + " (this library has no CPU fallback)");
-    return guarded([&]() -> int {
-        std::unique_ptr<pm_index> I(new pm_index());
+// the flattened index in I->F goes to the device (everything pm_index_create does after flattenIndex; also the whole of opening a cached image)
+static void uploadIndex(pm_index* I, int device) {
+    {
         I->device = device;
-        flattenIndex(*desc, shard, nShards, I->F);
         setDevice(device);
         cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
         I->nSM = prop.multiProcessorCount;
@@ -105,11 +100,26 @@ static int createIndex(const pm_index_desc* desc, int device, uint32_t shard, ui
             I->seedTables.upload(st);
         }
         I->gMagSqHost = F.gMagSq; I->gUniqueHost = F.gUnique;
-        buildViews(I.get());
+        buildViews(I);
         // release the big host vectors (the device now owns them)
         std::vector<u32>().swap(F.dw); std::vector<u32>().swap(F.endMask); std::vector<u32>().swap(F.nodeSeg); std::vector<u32>().swap(F.evIdx); std::vector<u64>().swap(F.dictKeys);
         std::vector<u32>().swap(F.dictVals); std::vector<u64>().swap(F.dictHash);
         std::vector<double>().swap(F.gMagSq); std::vector<int64_t>().swap(F.gUnique);
+    }
+}
+
+static int noDevice(int device) {
+    return fail(PM_ERR_NO_DEVICE, "no usable CUDA device " + std::to_string(device) + " (this library has no CPU fallback)");
+}
+
+static int createIndex(const pm_index_desc* desc, int device, uint32_t shard, uint32_t nShards, pm_index** out) {
+    if (!desc || !out) return fail(PM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (deviceCountNoThrow() <= device || device < 0) return noDevice(device);
+    return guarded([&]() -> int {
+        std::unique_ptr<pm_index> I(new pm_index());
+        flattenIndex(*desc, shard, nShards, I->F);
+        uploadIndex(I.get(), device);
         *out = I.release();
         return PM_OK;
     });
@@ -552,6 +562,90 @@ int pm_host_index_desc(const pm_host_index* h, pm_index_desc* out) {
 const char* pm_host_index_node_id(const pm_host_index* h, uint64_t node) {
     if (!h || node >= h->h.nodeIds.size()) return "";
     return h->h.nodeIds[node].c_str();
+}
+
+int pm_host_index_extras(const pm_host_index* hc, pm_index_extras* out) {
+    if (!hc || !out) return fail(PM_ERR_INVALID, "null argument");
+    pm_host_index* h = const_cast<pm_host_index*>(hc);
+    if (h->idPtrs.size() != h->h.nodeIds.size()) { h->idPtrs.clear(); for (const auto& s : h->h.nodeIds) h->idPtrs.push_back(s.c_str()); }
+    out->node_ids = h->idPtrs.data();
+    out->identical_to_parent = h->h.identicalToParent.empty() ? nullptr : h->h.identicalToParent.data();
+    out->block_ranges = h->h.blockRanges.empty() ? nullptr : h->h.blockRanges.data(); out->n_blocks = h->h.blockRanges.size() / 2;
+    out->substitution_matrix = h->h.substitutionMatrix.size() == 16 ? h->h.substitutionMatrix.data() : nullptr;
+    return PM_OK;
+}
+int pm_host_index_write(const char* path, const pm_index_desc* desc, const pm_index_extras* extras, int zstd_level, uint64_t* bytes_out) {
+    if (!path || !desc) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        IdxExtras x;
+        if (extras) { x.nodeIds = extras->node_ids; x.identicalToParent = extras->identical_to_parent; x.blockRanges = extras->block_ranges;
+                      x.nBlocks = extras->n_blocks; x.substitutionMatrix = extras->substitution_matrix; }
+        const uint64_t n = writeIdxFile(path, *desc, x, zstd_level);
+        if (bytes_out) *bytes_out = n;
+        return PM_OK;
+    });
+}
+
+// ---- cached image of the flattened index (pm_image.cpp) ----
+int pm_index_image_write(const pm_index_desc* desc, const char* const* node_ids, uint32_t shard, uint32_t n_shards, const char* image_path, uint64_t* bytes_out) {
+    if (!desc || !image_path) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        FlatIndex F;
+        flattenIndex(*desc, shard, n_shards, F);
+        std::vector<std::string> ids;
+        if (node_ids) for (uint64_t i = 0; i < desc->n_nodes; ++i) ids.emplace_back(node_ids[i] ? node_ids[i] : "");
+        ImageStamp st; st.shard = shard; st.nShards = n_shards;
+        const uint64_t n = writeFlatImage(image_path, F, ids, st);
+        if (bytes_out) *bytes_out = n;
+        return PM_OK;
+    });
+}
+int pm_index_create_from_image(const char* image_path, int device, pm_index** out) {
+    if (!image_path || !out) return fail(PM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (deviceCountNoThrow() <= device || device < 0) return noDevice(device);
+    return guarded([&]() -> int {
+        std::unique_ptr<pm_index> I(new pm_index());
+        std::string why;
+        if (!readFlatImage(image_path, I->F, I->nodeIds, nullptr, &why)) throw IoError(std::string("cannot use index image ") + image_path + ": " + why);
+        uploadIndex(I.get(), device);
+        *out = I.release();
+        return PM_OK;
+    });
+}
+int pm_index_open_cached(const char* idx_path, const char* image_path, int device, uint32_t shard, uint32_t n_shards, pm_index** out, int* cache_hit) {
+    if (!idx_path || !out) return fail(PM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cache_hit) *cache_hit = 0;
+    if (deviceCountNoThrow() <= device || device < 0) return noDevice(device);
+    return guarded([&]() -> int {
+        std::string img = image_path ? image_path : std::string(idx_path) + ".pmflat";
+        if (!image_path && n_shards > 1) img += "." + std::to_string(shard) + "of" + std::to_string(n_shards);
+        const ImageStamp want = stampOfFile(idx_path, shard, n_shards);
+        std::unique_ptr<pm_index> I(new pm_index());
+        std::string why;
+        if (readFlatImage(img, I->F, I->nodeIds, &want, &why)) {
+            if (cache_hit) *cache_hit = 1;
+        } else {
+            I.reset(new pm_index());
+            HostIndex h;
+            readIdxFile(idx_path, h);
+            pm_index_desc d{};
+            d.n_nodes = h.parentIndex.size(); d.n_deltas = h.hash.size(); d.delta_hash = h.hash.data(); d.delta_parent = h.parentCount.data();
+            d.delta_child = h.childCount.data(); d.node_offsets = h.nodeOffsets.data(); d.parent_index = h.parentIndex.data(); d.seed = h.sp;
+            flattenIndex(d, shard, n_shards, I->F);
+            I->nodeIds = h.nodeIds;
+            // a cache that cannot be written (read-only directory, full disk) is not an error: the index still opens
+            try { writeFlatImage(img, I->F, I->nodeIds, want); } catch (const std::exception&) {}
+        }
+        uploadIndex(I.get(), device);
+        *out = I.release();
+        return PM_OK;
+    });
+}
+const char* pm_index_node_id(const pm_index* idx, uint64_t node) {
+    if (!idx || node >= idx->nodeIds.size()) return "";
+    return idx->nodeIds[node].c_str();
 }
 
 int pm_index_create(const pm_index_desc* desc, int device, pm_index** out) { return createIndex(desc, device, 0, 1, out); }

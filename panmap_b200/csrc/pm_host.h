@@ -20,8 +20,24 @@ struct HostIndex {
     std::vector<uint64_t> nodeOffsets;
     std::vector<uint32_t> parentIndex;
     std::vector<std::string> nodeIds;
+    // carried through unchanged for consumers other than placement (mgsr / genotyping read them): LiteNode.identicalToParent,
+    // LiteTree.blockRanges as (begin, end) pairs, the 4x4 substitution matrix
+    std::vector<uint8_t> identicalToParent;
+    std::vector<uint32_t> blockRanges;
+    std::vector<double> substitutionMatrix;
 };
 void readIdxFile(const std::string& path, HostIndex& out);
+
+// what a writer may add to the flat view of an index (every pointer may be null)
+struct IdxExtras {
+    const char* const* nodeIds = nullptr;          // [n_nodes]; "node_<i>" otherwise
+    const uint8_t* identicalToParent = nullptr;    // [n_nodes]
+    const uint32_t* blockRanges = nullptr; uint64_t nBlocks = 0;   // [2 * nBlocks]
+    const double* substitutionMatrix = nullptr;    // [16]
+};
+// `.idx` container as the reference writes it (index_single_mode.cpp:1593-1636): 32-byte PMI1 header + the LiteIndex message, raw
+// (zstdLevel < 0) or as independent 64 MB zstd frames.  Returns the number of bytes written.
+uint64_t writeIdxFile(const std::string& path, const pm_index_desc& d, const IdxExtras& x, int zstdLevel);
 
 
 // everything pm_index_create derives from a pm_index_desc before uploading (see DESIGN.md "HBM layout")
@@ -67,6 +83,17 @@ struct FlatIndex {
 };
 // shard `shard` of `nShards` (contiguous DFS ranges balanced by delta count); throws std::runtime_error on bad input
 void flattenIndex(const pm_index_desc& d, uint32_t shard, uint32_t nShards, FlatIndex& out);
+
+// ---- cached image of a flattened index (pm_image.cpp) ----
+struct ImageStamp {            // identifies what an image was flattened from
+    uint64_t srcSize = 0, srcMtimeNs = 0;
+    uint8_t srcHeader[32] = {0};   // the source's PMI1 header (seeding parameters, compression flag)
+    uint32_t shard = 0, nShards = 1;
+};
+ImageStamp stampOfFile(const std::string& idxPath, uint32_t shard, uint32_t nShards);
+uint64_t writeFlatImage(const std::string& path, FlatIndex& F, const std::vector<std::string>& nodeIds, const ImageStamp& stamp);
+// false (with the reason in *why) when there is no usable image: missing, other format version, stamp mismatch, damaged
+bool readFlatImage(const std::string& path, FlatIndex& F, std::vector<std::string>& nodeIds, const ImageStamp* expect, std::string* why);
 
 void packBlockFirst(const uint64_t* packedOff, uint64_t nReads, uint64_t nChunks, uint32_t* out);
 

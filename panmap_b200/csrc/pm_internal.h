@@ -69,7 +69,7 @@ int deviceCountNoThrow();
 
 using pm::u32; using pm::u64;
 using pm::host::DevBuf; using pm::host::PinBuf;
-struct pm_host_index { pm::HostIndex h; };
+struct pm_host_index { pm::HostIndex h; std::vector<const char*> idPtrs; };
 
 struct pm_index {
     int device = 0; int nSM = 148;
@@ -83,6 +83,7 @@ struct pm_index {
     DevBuf<pm::SeedTables> seedTables;
     pm::DevIndexView view{};
     std::vector<double> gMagSqHost; std::vector<int64_t> gUniqueHost;
+    std::vector<std::string> nodeIds;   // LiteNode.id of every node when the index came from a file or an image (empty otherwise)
 };
 
 struct pm_workspace {

@@ -359,6 +359,10 @@ extern "C" int pm_place_files(pm_index* idx, pm_workspace* ws, const char* const
     try {
         std::vector<std::string> ids(n_ids);
         for (uint64_t i = 0; i < n_ids; ++i) ids[i] = node_ids[i];
+        if (n_ids == 0 && idx) {   // indexes opened from a file or a cached image carry their LiteNode ids
+            const uint64_t n = pm_index_num_nodes(idx);
+            if (n && pm_index_node_id(idx, 0)[0]) { ids.resize(n); for (uint64_t i = 0; i < n; ++i) ids[i] = pm_index_node_id(idx, i); }
+        }
         placement::DeviceIndex D; D.index = idx; D.workspace = ws; D.nodeIds = &ids;
         placement::TraversalParams tp;
         tp.seedMaskFraction = prm ? prm->seed_mask_fraction : 0.0; tp.trimStart = prm ? prm->trim_start : 0; tp.trimEnd = prm ? prm->trim_end : 0;

@@ -365,3 +365,45 @@ int64_t hc_emulate_selection(const double* score, const uint8_t* eligible, const
     return (int64_t)t.size();
 }
 }  // extern "C"
+
+// ---- cached index image (panmap_b200/csrc/pm_image.cpp) on the host: flatten -> write -> read back -> write again; the two files must be
+// byte-identical (every field of FlatIndex survives), a wrong stamp / a flipped byte / a truncated file must be refused.
+// returns 0 when everything holds, a positive step number otherwise
+#include <cstdio>
+static std::vector<unsigned char> slurp(const std::string& p) {
+    std::vector<unsigned char> b; FILE* f = std::fopen(p.c_str(), "rb"); if (!f) return b;
+    std::fseek(f, 0, SEEK_END); const long n = std::ftell(f); std::fseek(f, 0, SEEK_SET); b.resize((size_t)n);
+    if (n && std::fread(b.data(), 1, (size_t)n, f) != (size_t)n) b.clear();
+    std::fclose(f); return b;
+}
+extern "C" int hc_image_roundtrip(const pm_index_desc* d, uint32_t shard, uint32_t nShards, const char* const* ids, const char* dir) {
+    try {
+        FlatIndex F; flattenIndex(*d, shard, nShards, F);
+        std::vector<std::string> nodeIds;
+        if (ids) for (uint64_t i = 0; i < d->n_nodes; ++i) nodeIds.emplace_back(ids[i]);
+        ImageStamp st; st.srcSize = 1234; st.srcMtimeNs = 99; st.srcHeader[3] = 7; st.shard = shard; st.nShards = nShards;
+        const std::string a = std::string(dir) + "/a.pmflat", b = std::string(dir) + "/b.pmflat", c = std::string(dir) + "/c.pmflat";
+        writeFlatImage(a, F, nodeIds, st);
+        FlatIndex G; std::vector<std::string> idsBack; std::string why;
+        if (!readFlatImage(a, G, idsBack, &st, &why)) { g_err = why; return 1; }
+        if (idsBack != nodeIds) return 2;
+        if (G.N != F.N || G.D != F.D || G.S != F.S || G.dw != F.dw || G.endMask != F.endMask || G.dictKeys != F.dictKeys || G.gMag != F.gMag ||
+            G.chainNodes != F.chainNodes || G.bfsNodes != F.bfsNodes || G.nK2Tiles != F.nK2Tiles || std::memcmp(G.homo, F.homo, sizeof(F.homo)) != 0) return 3;
+        writeFlatImage(b, G, idsBack, st);
+        const auto fa = slurp(a), fb = slurp(b);
+        if (fa.empty() || fa != fb) return 4;
+        ImageStamp other = st; other.srcMtimeNs += 1;
+        FlatIndex H; std::vector<std::string> x;
+        if (readFlatImage(a, H, x, &other, &why)) return 5;                       // the source changed
+        other = st; other.shard += 1;
+        if (readFlatImage(a, H, x, &other, &why)) return 6;                       // another shard's image
+        if (!readFlatImage(a, H, x, nullptr, &why)) return 7;                     // no expectation: accepted
+        auto bad = fa; bad[bad.size() / 2] ^= 0x10;                                // one flipped bit in the middle
+        { FILE* f = std::fopen(c.c_str(), "wb"); std::fwrite(bad.data(), 1, bad.size(), f); std::fclose(f); }
+        if (readFlatImage(c, H, x, &st, &why)) return 8;
+        { FILE* f = std::fopen(c.c_str(), "wb"); std::fwrite(fa.data(), 1, fa.size() - 4096 > 0 ? fa.size() / 2 : 1, f); std::fclose(f); }
+        if (readFlatImage(c, H, x, &st, &why)) return 9;                          // truncated
+        if (readFlatImage(std::string(dir) + "/missing.pmflat", H, x, &st, &why)) return 10;
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
