@@ -142,12 +142,30 @@ void refreshView(pm_workspace* W) {
 static u64 fitLo() { return 4; }
 static u64 fitHi() { return 8; }
 
-// grows the table in use to at least wantCap slots (never shrinks it); a prefix of a larger allocation is reused as it is
+// grows the table in use to at least wantCap slots (never shrinks it); a prefix of a larger allocation is reused as it is.
+// The table is also bound as a linear texture (first probes go through the texture path), so its size is capped by the device's
+// linear-texture width (2^27 or 2^28 16-byte slots).  Estimates above the cap are clamped to it -- callers size from the number of
+// k-mer windows, an upper bound that bacterial-scale samples (4e8 seed instances, ~5e7 distinct) overshoot by far; a sample whose
+// distinct seeds really do not fit fails when the full-size table runs tight.
+static u64 tableSlotLimit(pm_workspace* W) {
+    if (!W->tableLimit) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxTexture1DLinearWidth, W->device) != cudaSuccess || v <= 0) { cudaGetLastError(); v = 1 << 27; }
+        u64 lim = 1; while (lim * 2 <= (u64)v) lim <<= 1;
+        if (const char* e = std::getenv("PM_TABLE_SLOT_LIMIT")) { const u64 x = std::strtoull(e, nullptr, 10); if (x >= (1u << 12) && x < lim) { lim = 1; while (lim * 2 <= x) lim <<= 1; } }   // tests
+        W->tableLimit = lim;
+    }
+    return W->tableLimit;
+}
 void ensureTable(pm_workspace* W, u64 wantCap) {
+    const u64 limit = tableSlotLimit(W);
     u64 cap = 1 << 12;
-    while (cap < wantCap) cap <<= 1;
-    if (cap <= W->tableCap) return;
-    if (cap > (1ull << 27)) throw std::runtime_error("read seed table would exceed 2^27 slots");
+    while (cap < wantCap && cap < limit) cap <<= 1;
+    if (cap <= W->tableCap) {
+        if (wantCap > limit && W->tableCap >= limit)
+            throw std::runtime_error("read seed table would exceed " + std::to_string(limit) + " slots (the device's linear-texture width)");
+        return;
+    }
     if (cap <= W->table.n) { W->tableCap = cap; refreshView(W); return; }   // the allocation (and its texture) already covers it
     if (W->tableTex) { cudaDestroyTextureObject(W->tableTex); W->tableTex = 0; }
     W->table.alloc(cap); W->tableCap = cap; W->entKey.alloc(cap); W->entCnt.alloc(cap); W->entId.alloc(cap);

@@ -99,7 +99,7 @@ struct pm_workspace {
     bool uploadPending = false;  // pm_reads_upload_device enqueued copies from the pinned staging arrays and did not wait
     bool hpcDone = false;        // hpc indexes: the resident reads (and qualities) were compressed in place already, endOff is valid
     // table
-    DevBuf<pm::TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; cudaTextureObject_t tableTex = 0;
+    DevBuf<pm::TableSlot> table; u64 tableCap = 0; u64 lastEntries = 0; u64 tableLimit = 0; cudaTextureObject_t tableTex = 0;
     DevBuf<unsigned long long> dedupSlots; u64 dedupMask = 0; DevBuf<unsigned char> dupFlag;   // --dedup only
     DevBuf<u64> endOff;                                                                        // hpc indexes only
     DevBuf<u64> tileSum;                                                                       // scratch of the device-side chunk offsets

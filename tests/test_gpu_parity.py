@@ -611,6 +611,56 @@ def test_full_size_sample_matches_oracle_and_is_shard_and_call_invariant():
     assert np.array_equal(got, sc)
 
 
+def test_bacterial_shape_reduced_matches_oracle():
+    """BASELINE configs[3] shape at reduced size (the oracle needs minutes at 100k nodes x 10M reads): a 600 kb genome, lambda = 50 mutations
+    per edge, so a root of ~190 k deltas spanning hundreds of delta chunks, millions of distinct read seeds (mostly sequencing-error seeds
+    seen once), the hot-id shared-memory copy covering a sliver of the seed ids.  Whole result against the oracle, as for configs[2]."""
+    from tools.synth import synth
+    S = synth.generate(4000, 600_000, 50.0, 300_000, read_len=150, seed=3)
+    host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
+    ws = pm.Workspace(pm.Index(host))
+    res = ws.place(S.reads, S.read_offsets)
+    sc = ws.node_scores()
+    exp = cpu.place(S.reads, S.read_offsets, S, want_scores=True)
+    assert int(S.offsets[1]) > 100_000 and exp["unique_seeds"] > 1_000_000
+    assert res.raw.unique_seeds == exp["unique_seeds"] and res.raw.read_unique_seed_count == exp["kept"]
+    assert res.raw.total_read_seed_frequency == exp["total_frequency"] and res.raw.min_read_support == exp["min_support"]
+    assert H.relerr(sc, exp["scores"]).max() < RTOL
+    for m, name in enumerate(pm.METRICS):
+        assert res.best_index[name] == exp["best_index"][m], name
+        assert np.array_equal(res.tied[name], exp["tied"][m]), name
+        assert H.relerr(res.best_score[name], exp["best_score"][m]).max() < RTOL
+    assert S.truth in res.tied["log_raw"]
+    # resident path and a 2-shard index: bit-identical scores
+    ws.upload(S.reads, S.read_offsets)
+    ws.place_resident()
+    assert np.array_equal(ws.node_scores(), sc)
+
+
+def test_table_estimate_is_clamped_to_the_device_limit_and_a_real_overflow_fails(monkeypatch):
+    """the first table of a workspace is sized from the number of k-mer windows (an upper bound); at bacterial scale that estimate exceeds
+    the linear-texture width the table is bound to.  With the limit lowered: a sample whose distinct seeds fit is placed correctly in a
+    table clamped to the limit, one whose distinct seeds cannot fit is refused (no silent truncation)."""
+    rng = np.random.default_rng(5)
+    idx, _, _ = H.synthetic_index(200, rng)
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open)
+    monkeypatch.setenv("PM_TABLE_SLOT_LIMIT", str(1 << 16))
+    ws = pm.Workspace(pm.Index(host))
+    one = H.random_reads(rng, 1, lo=180, hi=181)
+    many_copies = one * 9000                               # 9000 * 160 windows / 4 = 360 k > 65,536 slots, but only ~50 distinct seeds
+    buf, off = pm.pack_reads(many_copies)
+    ws.upload(buf, off)
+    res = ws.place_resident()
+    eh, ec = cpu.seed_table(buf, off, idx.k, idx.s, idx.t, idx.l, idx.open, 0, 0, False)
+    th, tc = ws.seed_table()
+    assert res.raw.unique_seeds == eh.size and np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec)
+    big = H.random_reads(rng, 9000, lo=100, hi=200)        # ~300 k distinct random seeds: cannot fit 65,536 slots
+    with pytest.raises(pm.PanmapError):
+        ws.place(*pm.pack_reads(big))
+    res2 = ws.place(buf, off)                              # the workspace stays usable
+    assert res2.raw.unique_seeds == eh.size
+
+
 def test_hash_seq_matches_oracle_and_rejects_non_acgt():
     """seeding::hashSeq (seeding.cpp:20-30) on the GPU for a batch of k-mers of every length 1..40 (rotations wrap at 64 like the reference's)"""
     rng = np.random.default_rng(77)
