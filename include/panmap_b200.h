@@ -183,6 +183,10 @@ int pm_place_resident(pm_workspace* ws, const pm_place_params* params, pm_place_
 int pm_reads_upload_device(pm_workspace* ws, const char* d_reads, const uint64_t* d_read_offsets, const uint64_t* h_read_offsets, uint64_t n_reads);
 /* page-locked host buffers for callers that want the H2D copies of pm_place to run at full PCIe speed */
 void* pm_host_alloc(uint64_t bytes);
+/* Pinned landing buffers owned by the workspace, for a parser that writes a sample straight into memory the copy engine can read
+ * (parallelFastqSeqs, placement.cpp:96-162, fills std::strings instead): room for read_bytes bases (+ qualities when want_quals) and
+ * n_reads + 1 offsets.  Grown as needed, kept across samples, valid until the next call or pm_workspace_destroy. */
+int pm_workspace_staging(pm_workspace* ws, uint64_t read_bytes, uint64_t n_reads, int want_quals, char** reads_out, uint64_t** offsets_out, char** quals_out);
 void pm_host_free(void* p);
 
 /* after pm_place: tied node lists (sorted ascending, == tied*NodeIndices), per-node scores, read seed table */

@@ -1190,6 +1190,18 @@ int pm_last_kernel_ms(pm_workspace* ws, float* out) {
     });
 }
 
+int pm_workspace_staging(pm_workspace* ws, uint64_t read_bytes, uint64_t n_reads, int want_quals, char** reads_out, uint64_t** offsets_out, char** quals_out) {
+    if (!ws || !reads_out || !offsets_out) return fail(PM_ERR_INVALID, "null argument");
+    return guarded([&]() -> int {
+        setDevice(ws->device);
+        ws->hIngestReads.ensure(read_bytes + 64); ws->hIngestOff.ensure(n_reads + 1);
+        if (want_quals) ws->hIngestQuals.ensure(read_bytes + 64);
+        *reads_out = ws->hIngestReads.p; *offsets_out = ws->hIngestOff.p;
+        if (quals_out) *quals_out = want_quals ? ws->hIngestQuals.p : nullptr;
+        return PM_OK;
+    });
+}
+
 void* pm_host_alloc(uint64_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -94,6 +94,7 @@ struct pm_workspace {
     // inputs
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
+    PinBuf<char> hIngestReads, hIngestQuals; PinBuf<u64> hIngestOff;   // pm_workspace_staging: pinned landing buffers of a file parser
     u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
     bool residentValid = false;  // the device copy of the reads was laid out by pm_reads_upload (not by the sliced pm_place path)
     bool uploadPending = false;  // pm_reads_upload_device enqueued copies from the pinned staging arrays and did not wait

@@ -9,6 +9,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -103,22 +104,41 @@ size_t fqRecordStart(const char* d, size_t size, size_t from) {
     // fewer than four lines left after the candidate: a last record whose quality line ends the file without a newline was handled above
     return size;
 }
-bool readFastqParallel(const std::string& path, FlatReads& out, FlatReads* quals) {
-    MappedFile mf(path);
-    if (!mf.d || mf.size < 4) return false;
-    const char* d = mf.d; const size_t size = mf.size;
+// pass 1 over a mapped four-line FASTQ: where every record's bases (and qualities) lie, per thread range; then the read offsets inside
+// this file by prefix sums.  The bytes themselves are moved by fillFrom() to wherever the caller wants them.
+struct FastqScan {
+    MappedFile mf;
+    struct Range { std::vector<uint64_t> seqAt, qualAt; std::vector<uint32_t> len; uint64_t bases = 0; bool bad = false; };
+    std::vector<Range> R;
+    std::vector<uint64_t> firstRead;   // [ranges]
+    std::vector<uint64_t> off;         // [nReads + 1] offsets of the reads when this file's sequences are laid out back to back
+    uint64_t nReads = 0, nBases = 0;
+    explicit FastqScan(const std::string& path) : mf(path) {}
+};
+template <class Fn> void onThreads(size_t nT, Fn&& fn) {
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nT; ++t) th.emplace_back(fn, t);
+    fn(0);
+    for (auto& x : th) x.join();
+}
+size_t ingestThreads() { return std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16); }
+
+bool scanFastq(FastqScan& S, bool wantQuals) {
+    if (!S.mf.d || S.mf.size < 4) return false;
+    const char* d = S.mf.d; const size_t size = S.mf.size;
     if (d[0] != '@') return false;   // gzip streams (1f 8b), FASTA ('>') and anything else: the serial parser takes them
-    size_t nT = std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 16);
+    size_t nT = ingestThreads();
     if (size < (1u << 20)) nT = 1;
     std::vector<size_t> bounds(nT + 1, size);
     bounds[0] = 0;
     for (size_t i = 1; i < nT; ++i) bounds[i] = std::max(bounds[i - 1], fqRecordStart(d, size, (size / nT) * i));
-    struct Range { std::vector<uint64_t> seqAt, qualAt; std::vector<uint32_t> len; uint64_t bases = 0; bool bad = false; };
-    std::vector<Range> R(nT);
-    auto scan = [&](size_t t) {
-        Range& r = R[t];
+    S.R.assign(nT, FastqScan::Range());
+    onThreads(nT, [&](size_t t) {
+        FastqScan::Range& r = S.R[t];
         size_t o = bounds[t];
         const size_t end = bounds[t + 1];
+        const size_t guess = (end - o) / 256 + 16;
+        r.seqAt.reserve(guess); r.len.reserve(guess); if (wantQuals) r.qualAt.reserve(guess);
         while (o < end) {
             if (d[o] != '@') {   // only blank lines may follow the last record
                 for (size_t i = o; i < end; ++i) if (d[i] != '\n' && d[i] != '\r') { r.bad = true; break; }
@@ -136,36 +156,45 @@ bool readFastqParallel(const std::string& path, FlatReads& out, FlatReads* quals
             if (q1 > q0 && q0 <= size && d[q1 - 1] == '\r') --q1;
             const size_t L = s1 - s0;
             if (q0 > size || q1 - q0 != L || L > 0xFFFFFFFFull) { r.bad = true; break; }
-            for (size_t i = s0; i < s1; ++i) if (d[i] == ' ' || d[i] == '\t') { r.bad = true; break; }   // kseq would drop these
-            if (r.bad) break;
+            if (std::memchr(d + s0, ' ', L) || std::memchr(d + s0, '\t', L)) { r.bad = true; break; }   // kseq would drop these
             r.seqAt.push_back(s0); r.len.push_back(static_cast<uint32_t>(L)); r.bases += L;
-            if (quals) r.qualAt.push_back(q0);
+            if (wantQuals) r.qualAt.push_back(q0);
         }
-    };
-    auto runAll = [&](auto&& fn) {
-        std::vector<std::thread> th;
-        for (size_t t = 1; t < nT; ++t) th.emplace_back(fn, t);
-        fn(0);
-        for (auto& x : th) x.join();
-    };
-    runAll(scan);
-    uint64_t nReads = 0, nBases = 0;
-    std::vector<uint64_t> firstRead(nT), firstBase(nT);
-    for (size_t t = 0; t < nT; ++t) { if (R[t].bad) return false; firstRead[t] = nReads; firstBase[t] = nBases; nReads += R[t].len.size(); nBases += R[t].bases; }
-    out.data.resize(nBases); out.off.assign(nReads + 1, 0);
-    if (quals) { quals->data.resize(nBases); quals->off.assign(nReads + 1, 0); }
-    auto fill = [&](size_t t) {
-        const Range& r = R[t];
+    });
+    S.firstRead.assign(nT, 0);
+    std::vector<uint64_t> firstBase(nT, 0);
+    S.nReads = S.nBases = 0;
+    for (size_t t = 0; t < nT; ++t) { if (S.R[t].bad) return false; S.firstRead[t] = S.nReads; firstBase[t] = S.nBases; S.nReads += S.R[t].len.size(); S.nBases += S.R[t].bases; }
+    S.off.resize(S.nReads + 1);
+    onThreads(nT, [&](size_t t) {
         uint64_t b = firstBase[t];
+        const auto& len = S.R[t].len;
+        uint64_t* o = S.off.data() + S.firstRead[t];
+        for (size_t i = 0; i < len.size(); ++i) { o[i] = b; b += len[i]; }
+    });
+    S.off[S.nReads] = S.nBases;
+    return true;
+}
+// pass 2: read i of the file goes to bases[place(i)] (and its qualities to quals[place(i)])
+template <class Place> void fillFrom(const FastqScan& S, char* bases, char* quals, Place&& place) {
+    const char* d = S.mf.d;
+    onThreads(S.R.size(), [&](size_t t) {
+        const FastqScan::Range& r = S.R[t];
         for (size_t i = 0; i < r.len.size(); ++i) {
-            out.off[firstRead[t] + i] = b;
-            std::memcpy(&out.data[b], d + r.seqAt[i], r.len[i]);
-            if (quals) std::memcpy(&quals->data[b], d + r.qualAt[i], r.len[i]);
-            b += r.len[i];
+            const uint64_t at = place(S.firstRead[t] + i);
+            std::memcpy(bases + at, d + r.seqAt[i], r.len[i]);
+            if (quals) std::memcpy(quals + at, d + r.qualAt[i], r.len[i]);
         }
-    };
-    runAll(fill);
-    out.off[nReads] = nBases;
+    });
+}
+
+bool readFastqParallel(const std::string& path, FlatReads& out, FlatReads* quals) {
+    FastqScan S(path);
+    if (!scanFastq(S, quals != nullptr)) return false;
+    out.data.resize(S.nBases);
+    if (quals) quals->data.resize(S.nBases);
+    fillFrom(S, out.data.data(), quals ? quals->data.data() : nullptr, [&](uint64_t i) { return S.off[i]; });
+    out.off = std::move(S.off);
     if (quals) quals->off = out.off;
     return true;
 }
@@ -174,54 +203,125 @@ void readFastx(const std::string& path, FlatReads& out, FlatReads* quals) {
     if (!readFastqParallel(path, out, quals)) { out = FlatReads(); if (quals) *quals = FlatReads(); readFastxSerial(path, out, quals); }
 }
 
+// A sample's files -> (bases, offsets[, qualities]) in buffers obtained from `alloc(bytes, nReads)` -- the workspace's pinned staging
+// buffers in placeLite -- with R1/R2 pairs interleaved (seeding::perfect_shuffle, seeding.hpp:33-43).  Plain four-line FASTQ is copied from
+// the mapped file(s) straight to its final place by all threads (one copy per base, no intermediate strings); gz / FASTA / multi-line
+// files go through the kseq-style parser, the two files of a pair on two threads (inflate is serial inside one gzip stream).
+struct Landing { char* bases = nullptr; uint64_t* off = nullptr; char* quals = nullptr; };
+struct IngestClock {   // PM_INGEST_TIMING=1: phase times of the parser on stderr (tools/ingest_probe.py)
+    const bool on = std::getenv("PM_INGEST_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[pm ingest] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+template <class Alloc> uint64_t ingestSample(const std::string& path1, const std::string& path2, bool wantQuals, Alloc&& alloc, Landing& L) {
+    const bool paired = !path2.empty();
+    IngestClock clk;
+    {
+        FastqScan A(path1);
+        if (scanFastq(A, wantQuals)) {
+            clk.lap("scan (record boundaries)");
+            if (!paired) {
+                L = alloc(A.nBases, A.nReads);
+                clk.lap("landing buffers");
+                std::memcpy(L.off, A.off.data(), (A.nReads + 1) * sizeof(uint64_t));
+                fillFrom(A, L.bases, L.quals, [&](uint64_t i) { return A.off[i]; });
+                clk.lap("fill (bases to their place)");
+                return A.nReads;
+            }
+            FastqScan B(path2);
+            if (scanFastq(B, wantQuals)) {
+                if (B.nReads != A.nReads) throw std::runtime_error("File " + path2 + " does not contain the same number of reads as " + path1);
+                const uint64_t n = A.nReads;
+                L = alloc(A.nBases + B.nBases, 2 * n);
+                onThreads(ingestThreads(), [&](size_t t) {
+                    const size_t nT = ingestThreads();
+                    for (uint64_t i = n * t / nT; i < n * (t + 1) / nT; ++i) { L.off[2 * i] = A.off[i] + B.off[i]; L.off[2 * i + 1] = A.off[i + 1] + B.off[i]; }
+                });
+                L.off[2 * n] = A.nBases + B.nBases;
+                fillFrom(A, L.bases, L.quals, [&](uint64_t i) { return A.off[i] + B.off[i]; });
+                fillFrom(B, L.bases, L.quals, [&](uint64_t i) { return A.off[i + 1] + B.off[i]; });
+                return 2 * n;
+            }
+        }
+    }
+    // general route
+    FlatReads a, qa, b, qb;
+    if (paired) {
+        std::exception_ptr err;
+        std::thread other([&] { try { readFastx(path2, b, wantQuals ? &qb : nullptr); } catch (...) { err = std::current_exception(); } });
+        try { readFastx(path1, a, wantQuals ? &qa : nullptr); } catch (...) { other.join(); throw; }
+        other.join();
+        if (err) std::rethrow_exception(err);
+        if (b.size() != a.size()) throw std::runtime_error("File " + path2 + " does not contain the same number of reads as " + path1);
+    } else readFastx(path1, a, wantQuals ? &qa : nullptr);
+    const uint64_t n = a.size();
+    if (!paired) {
+        L = alloc(a.data.size(), n);
+        std::memcpy(L.off, a.off.data(), (n + 1) * sizeof(uint64_t));
+        std::memcpy(L.bases, a.data.data(), a.data.size());
+        if (wantQuals) std::memcpy(L.quals, qa.data.data(), qa.data.size());
+        return n;
+    }
+    L = alloc(a.data.size() + b.data.size(), 2 * n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t o0 = a.off[i] + b.off[i], o1 = a.off[i + 1] + b.off[i];
+        L.off[2 * i] = o0; L.off[2 * i + 1] = o1;
+        std::memcpy(L.bases + o0, &a.data[a.off[i]], a.off[i + 1] - a.off[i]);
+        std::memcpy(L.bases + o1, &b.data[b.off[i]], b.off[i + 1] - b.off[i]);
+        if (wantQuals) {
+            std::memcpy(L.quals + o0, &qa.data[a.off[i]], a.off[i + 1] - a.off[i]);
+            std::memcpy(L.quals + o1, &qb.data[b.off[i]], b.off[i + 1] - b.off[i]);
+        }
+    }
+    L.off[2 * n] = a.data.size() + b.data.size();
+    return 2 * n;
+}
+
 }  // namespace
 
 namespace placement {
 
 void extractReadSequences(const std::string& readPath1, const std::string& readPath2, std::string& bases, std::vector<uint64_t>& offsets,
                           std::string* quals) {
-    FlatReads a, qa;
-    readFastx(readPath1, a, quals ? &qa : nullptr);
-    if (readPath2.empty()) {
-        bases = std::move(a.data); offsets = std::move(a.off);
-        if (quals) *quals = std::move(qa.data);
-        return;
-    }
-    FlatReads b, qb;
-    readFastx(readPath2, b, quals ? &qb : nullptr);
-    if (b.size() != a.size()) throw std::runtime_error("File " + readPath2 + " does not contain the same number of reads as " + readPath1);
-    // seeding::perfect_shuffle (seeding.hpp:33-43): pair i becomes reads 2i, 2i+1; their places follow from the two offset arrays
-    const size_t n = a.size();
-    offsets.assign(2 * n + 1, 0);
-    bases.resize(a.data.size() + b.data.size());
-    if (quals) quals->resize(bases.size());
-    for (size_t i = 0; i < n; ++i) {
-        const uint64_t o0 = a.off[i] + b.off[i], o1 = a.off[i + 1] + b.off[i];
-        offsets[2 * i] = o0; offsets[2 * i + 1] = o1;
-        std::memcpy(&bases[o0], &a.data[a.off[i]], a.off[i + 1] - a.off[i]);
-        std::memcpy(&bases[o1], &b.data[b.off[i]], b.off[i + 1] - b.off[i]);
-        if (quals) {
-            std::memcpy(&(*quals)[o0], &qa.data[a.off[i]], a.off[i + 1] - a.off[i]);
-            std::memcpy(&(*quals)[o1], &qb.data[b.off[i]], b.off[i + 1] - b.off[i]);
-        }
-    }
-    offsets[2 * n] = bases.size();
+    Landing L;
+    ingestSample(readPath1, readPath2, quals != nullptr, [&](uint64_t bytes, uint64_t nReads) {
+        bases.resize(bytes); offsets.assign(nReads + 1, 0);
+        if (quals) quals->resize(bytes);
+        Landing x; x.bases = bases.data(); x.off = offsets.data(); x.quals = quals ? quals->data() : nullptr;
+        return x;
+    }, L);
 }
 
 void placeLite(PlacementResult& result, DeviceIndex& index, const std::string& reads1, const std::string& reads2, std::string& outputPath,
                const TraversalParams& params) {
     if (!index.index || !index.workspace) throw std::runtime_error("placeLite: device index not initialised");
-    std::string bases, quals; std::vector<uint64_t> off(1, 0);
     const bool quality = params.minSeedQuality > 0;   // placement.cpp:1131-1137: the quality strings are loaded only then
-    if (!reads1.empty()) extractReadSequences(reads1, reads2, bases, off, quality ? &quals : nullptr);
+    // the sample lands in the workspace's pinned staging buffers: the copy engine reads them directly (pageable std::strings would be staged
+    // through a bounce buffer at a fraction of the PCIe rate)
+    Landing in;
+    uint64_t nReads = 0, zero = 0;
+    if (!reads1.empty())
+        nReads = ingestSample(reads1, reads2, quality, [&](uint64_t bytes, uint64_t n) {
+            Landing x;
+            if (pm_workspace_staging(index.workspace, bytes, n, quality ? 1 : 0, &x.bases, &x.off, &x.quals) != PM_OK) throw std::runtime_error(pm_last_error());
+            return x;
+        }, in);
+    else in.off = &zero;
     pm_place_params p{};
     p.trim_start = params.trimStart; p.trim_end = params.trimEnd; p.min_read_support = params.minReadSupport;
     p.dedup_reads = params.dedupReads ? 1 : 0; p.force_leaf = params.forceLeaf ? 1 : 0; p.skip_node_index = PM_NONE;
     p.seed_mask_fraction = params.seedMaskFraction; p.want_node_scores = params.store_diagnostics ? 1 : 0;
-    p.min_seed_quality = quality && off.size() > 1 ? params.minSeedQuality : 0;   // no reads: `!allReadQualities.empty()` fails, default path
+    p.min_seed_quality = quality && nReads > 0 ? params.minSeedQuality : 0;   // no reads: `!allReadQualities.empty()` fails, default path
     pm_place_result r{};
-    const int rc = p.min_seed_quality > 0 ? pm_place_quality(index.workspace, bases.data(), quals.data(), off.data(), off.size() - 1, &p, &r)
-                                          : pm_place(index.workspace, bases.data(), off.data(), off.size() - 1, &p, &r);
+    IngestClock clk;
+    const int rc = p.min_seed_quality > 0 ? pm_place_quality(index.workspace, in.bases, in.quals, in.off, nReads, &p, &r)
+                                          : pm_place(index.workspace, in.bases, in.off, nReads, &p, &r);
+    clk.lap("pm_place (staging -> result)");
     if (rc != PM_OK) throw std::runtime_error(pm_last_error());
     double* sc[5] = {&result.bestLogRawScore, &result.bestLogCosineScore, &result.bestContainmentScore, &result.bestWeightedContainmentScore,
                      &result.bestLogContainmentScore};
