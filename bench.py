@@ -149,9 +149,49 @@ def make_workload(name, seed=0, n_reads=None):
         S = RealSample()
         w["n_reads"] = int(S.read_offsets.size - 1)
     else:
-        S = synth.generate(w["n_nodes"], w["genome"], w["lam"], n_reads or w["n_reads"], read_len=w["read_len"], seed=seed)
+        S = shared_synth(name, w, seed, n_reads or w["n_reads"])
     S.gen_seconds = time.time() - t
     return S, w
+
+
+_SYNTH_ARRAYS = ("hash", "parent", "child", "offsets", "parent_index", "reads", "read_offsets")
+_SYNTH_SCALARS = ("truth", "k", "s", "t", "l", "open", "n_nodes", "n_deltas")
+
+
+def shared_synth(name, w, seed, n_reads):
+    """the synthetic workload; under torchrun the ranks of a node share ONE generation (local rank 0 generates and leaves the arrays in
+    /dev/shm, the others wait for them): a bacterial-scale sample takes minutes to generate and N copies of the generator would share the
+    same host cores.  Generation is deterministic, so this only saves time."""
+    from tools.synth import synth
+    world, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    gen = lambda: synth.generate(w["n_nodes"], w["genome"], w["lam"], n_reads, read_len=w["read_len"], seed=seed)
+    if world <= 1 or not os.path.isdir("/dev/shm"):
+        return gen()
+    d = f"/dev/shm/pm_bench_{name}_{seed}_{n_reads}_{os.environ.get('MASTER_PORT', '0')}"
+    done = os.path.join(d, "done")
+    if local == 0:
+        S = gen()
+        os.makedirs(d, exist_ok=True)
+        for a in _SYNTH_ARRAYS:
+            np.save(os.path.join(d, a + ".npy"), getattr(S, a))
+        json.dump({k: int(getattr(S, k)) for k in _SYNTH_SCALARS}, open(os.path.join(d, "scalars.json"), "w"))
+        open(done, "w").write("1")
+        import atexit
+        import shutil
+        atexit.register(shutil.rmtree, d, True)       # the other ranks have loaded their copies long before rank 0 exits (barriers in between)
+        return S
+    t0 = time.time()
+    while not os.path.exists(done):
+        if time.time() - t0 > 1800:
+            raise SystemExit(f"waited 30 min for local rank 0 to generate {name}")
+        time.sleep(0.2)
+    S = synth.Synth()
+    for a in _SYNTH_ARRAYS:
+        setattr(S, a, np.load(os.path.join(d, a + ".npy")))
+    for k, v in json.load(open(os.path.join(d, "scalars.json"))).items():
+        setattr(S, k, v)
+    S.truth_genome = b""
+    return S
 
 
 def algorithmic_bytes(S):
