@@ -129,6 +129,7 @@ void refreshView(pm_workspace* W) {
     WorkspaceView& V = W->view;
     V.table = W->table.p; V.tableTex = W->tableTex; V.tableCap = W->tableCap; V.tableMask = W->tableCap ? W->tableCap - 1 : 0;
     V.synBuf = W->synBuf.p; V.synCount = W->synCount.p; V.missQ = W->missQ.p; V.missCap = W->missQ.n;
+    V.bktBuf = W->bktBuf.p; V.bktFill = W->bktFill.p; V.bktCount = W->bktCount; V.bktShift = W->bktShift; V.bktRegionCap = W->bktRegionCap;
     V.acc = W->acc.p; V.ell = W->ell.p; V.ellTex = W->ellTex; V.countHist = W->countHist.p; V.entKey = W->entKey.p; V.entCnt = W->entCnt.p; V.entId = W->entId.p;
     V.scanPart = W->scanPart.p; V.finPart = W->finPart.p;
     V.segRec = W->segRec.p; V.chainA = W->chainA.p; V.genRec = W->genRec.p; V.evPrefix = W->evPrefix.p;
@@ -316,6 +317,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
                         hpc ? W->endOff.p + r0 : nullptr, ascii ? W->reads.p : nullptr);
         bfBase += nBlk + 1;
     }
+    launchCountBuckets(W->view, W->st);   // partitioned counting only: the slices scattered their seeds, one pass counts them
     W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false; W->hpcDone = false;
 }
 
@@ -360,7 +362,36 @@ void uploadAndSeedPipelinedPacked(pm_workspace* W, const uint4* hPacked, const u
         launchChunkOffsets(W->off.p + r0, r1 - r0, gBase, W->tileSum.p, W->packedOff.p + r0, W->st);
         launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, nullptr, nullptr, nullptr, nullptr);
     }
+    launchCountBuckets(W->view, W->st);
     W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false; W->hpcDone = false;
+}
+
+// Partitioned counting for this sample?  Tables that do not fit L2 (PM_BUCKET_MIN_SLOTS, default 2^24 slots = 256 MB) are filled region by
+// region: plan the buckets (~32 MB of table each), size one region per (resident warp, bucket) from the expected number of seed instances
+// (closed syncmers of either strand: ~0.31 per k-mer window at k = 19, s = 8; 0.45 x 1.25 leaves room, a full region falls back to direct
+// insertion) and clear the fill counts.  windowsUpper: an upper bound of the sample's k-mer windows.
+static u64 bucketMinSlots() {   // read per call: tests drive small samples through the partitioned path with it
+    const char* e = std::getenv("PM_BUCKET_MIN_SLOTS");
+    return e ? (u64)std::strtoull(e, nullptr, 10) : (u64)1 << 24;
+}
+static void planBuckets(pm_workspace* W, u64 windowsUpper, const pm_place_params& prm) {
+    const pm_seed_params& sp = W->idx->F.sp;
+    W->bktCount = 0;
+    const bool quality = W->useQuals && prm.min_seed_quality > 0;
+    if (W->tableCap < bucketMinSlots() || quality || !bucketCountingSupports(sp.k, sp.l) || windowsUpper == 0) { refreshView(W); return; }
+    u64 B = 2;
+    while (B < 256 && W->tableCap * sizeof(TableSlot) / B > (32ull << 20)) B <<= 1;
+    unsigned shift = 0;
+    while ((W->tableCap >> shift) > B) ++shift;
+    const u64 expected = windowsUpper * 45 / 100;
+    u64 cap = expected * 5 / 4 / ((u64)kBktWarps * B) + 256;
+    cap = (cap + 3) & ~3ull;
+    if (const char* e = std::getenv("PM_BUCKET_REGION_CAP")) cap = std::max<u64>(4, std::strtoull(e, nullptr, 10));   // tests: force the full-region fallback
+    if (cap > 0x7FFFFFFFull) { refreshView(W); return; }
+    W->bktBuf.ensure((u64)kBktWarps * B * cap); W->bktFill.ensure((u64)kBktWarps * B);
+    CK(cudaMemsetAsync(W->bktFill.p, 0, (u64)kBktWarps * B * sizeof(u32), W->st));
+    W->bktCount = (u32)B; W->bktShift = shift; W->bktRegionCap = (u32)cap;
+    refreshView(W);
 }
 
 void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
@@ -395,6 +426,7 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         CK(cudaEventRecord(W->evK[2], W->st));
     } else {
         launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup, endOff, ascii ? W->reads.p : nullptr);
+        launchCountBuckets(W->view, W->st);   // partitioned counting only (no-op otherwise)
     }
     CK(cudaEventRecord(W->evK[3], W->st));
 }
@@ -513,11 +545,16 @@ static int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result
             while (cap < fitLo() * W->lastEntries / 2) cap <<= 1;
             if (cap < W->tableCap) { W->tableCap = cap; }   // keep the allocation, use a prefix
         }
-        refreshView(W);
+        if (W->tableCap == 0 && !inputsResident) {   // first sample of the workspace from host buffers: size the table here, so that the plan below sees it
+            const u64 total = n ? off[n] : 0, k = (u64)I->F.sp.k;
+            ensureTable(W, std::max<u64>(1 << 16, (total > k * n ? total - (k - 1) * n : 0) / 4));
+        }
+        planBuckets(W, inputsResident ? W->totalWindows : (n ? off[n] : 0), *prm);   // also refreshes the view
         CK(cudaEventRecord(W->ev[1], W->st));
         if (inputsResident) stageSeed(W, true, *prm);
         else if (packedHost) uploadAndSeedPipelinedPacked(W, packedHost, off, n, *prm);
         else uploadAndSeedPipelined(W, reads, off, n, *prm);   // H2D of the slices overlaps pack + seeding of earlier slices
+        W->bktCount = 0; refreshView(W);   // a per-sample decision: the staged and sharded entry points count directly
         CK(cudaEventRecord(W->ev[2], W->st));
         stageScore(W, *prm);
         launchChain(W->view, nullptr, W->st);

@@ -105,6 +105,7 @@ struct pm_workspace {
     DevBuf<u64> endOff;                                                                        // hpc indexes only
     DevBuf<u64> tileSum;                                                                       // scratch of the device-side chunk offsets
     DevBuf<u64> synBuf; DevBuf<unsigned> synCount;
+    DevBuf<u64> bktBuf; DevBuf<u32> bktFill; u32 bktCount = 0, bktShift = 0, bktRegionCap = 0;   // partitioned counting (pm_kernels.cu), set per sample by runPlace
     DevBuf<u64> missQ;   // miss queue of the counting kernels: a quarter of the syncmer slots (overflow falls back to direct insertion)
     // the small per-sample result block lives in ONE device allocation so that it comes back with a single copy:
     // [pm::SampleAcc | pm::SampleScalars | pm::Selection x 5 | first kTieHead tied nodes of every metric]

@@ -1059,39 +1059,142 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256, 1) count_seeds_lane(const u6
     }
 }
 // the miss queue of count_seeds_lane<.., QUEUE> into the global table: one seed per thread and turn, four turns in flight
+// four seeds of one thread into the global table: first probes (texture path) of all four in flight, then the claims of the new keys, then
+// the counts; true collisions go the general way (shared by count_misses and count_buckets)
+__device__ __forceinline__ void insertFour(const u64 (&sd)[4], const bool (&has)[4], TableSlot* table, u64 mask, SampleAcc* acc, cudaTextureObject_t tableTex) {
+    u64 slot[4], key[4]; bool claim[4], slow[4]; unsigned long long was[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        slot[q] = mixKey(sd[q]) & mask; key[q] = kEmptyKey;
+        if (has[q]) { const uint4 t = tex1Dfetch<uint4>(tableTex, (int)slot[q]); key[q] = (u64)t.x | ((u64)t.y << 32); }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        claim[q] = slow[q] = false;
+        if (has[q]) {
+            if (sd[q] == kEmptyKey) slow[q] = true;
+            else if (key[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u);
+            else if (key[q] == kEmptyKey) claim[q] = true;
+            else slow[q] = true;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (claim[q]) was[q] = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot[q]].key), (unsigned long long)kEmptyKey, (unsigned long long)sd[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (claim[q]) { if (was[q] == kEmptyKey || was[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u); else slow[q] = true; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (slow[q]) tableInsert(table, mask, sd[q], 1u, acc);
+}
 __global__ void __launch_bounds__(256) count_misses(const u64* __restrict__ missQ, u64 missCap, TableSlot* table, u64 mask, SampleAcc* acc,
                                                     cudaTextureObject_t tableTex) {
     const u64 n = min((u64)acc->missCount, missCap);
     const u64 T = (u64)gridDim.x * blockDim.x;
     for (u64 i0 = (u64)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * T) {
-        u64 sd[4], slot[4], key[4]; bool has[4], claim[4], slow[4]; unsigned long long was[4];
+        u64 sd[4]; bool has[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const u64 i = i0 + (u64)q * T; has[q] = i < n; sd[q] = has[q] ? __ldcs(missQ + i) : 0; slot[q] = mixKey(sd[q]) & mask; }
+        for (int q = 0; q < 4; ++q) { const u64 i = i0 + (u64)q * T; has[q] = i < n; sd[q] = has[q] ? __ldcs(missQ + i) : 0; }
+        insertFour(sd, has, table, mask, acc, tableTex);
+    }
+}
+
+// ---- partitioned counting: read tables larger than L2 (bacterial-scale samples: 4e8 seed instances, 4e7 distinct, a 2 GB table) ------------
+// Counting straight into such a table is one random DRAM sector per seed instance -- configs[3] spends 20.8 of its 27 ms there.  Instead
+// the instances are first SCATTERED by table region (bucket = high bits of the home slot, regions of ~32 MB so that one fits L2 next to the
+// streams passing through), then counted bucket after bucket by every warp at the same time: all probes and atomics of a phase land in
+// the one table region that is L2-resident, and DRAM sees only streams (the lists, the scattered seeds written and read once, the
+// table itself once).  No staging, no flush protocol: every (resident warp, bucket) pair owns a fixed region, positions come from the warp's
+// own cursors in shared memory (no cross-warp contention), the 8-byte stores of a region are consecutive and merge in L2.  A full
+// region (capacity = 1.25x the expected share + slack; hash-uniform shares vary by a few per cent) sends its seed the direct way.
+template <int KT, int LT>
+__global__ void __launch_bounds__(1024, 1) scatter_seeds_lane(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
+                                                              const u64* __restrict__ packedOff, u64 nReads, WorkspaceView W) {
+    static_assert(LT == 1 || LT == 3, "lane-per-read seed formation is specialised for l = 1 and l = 3");
+    extern __shared__ unsigned sCurAll[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, B = W.bktCount;
+    unsigned* sCur = sCurAll + warp * B;
+    const u64 gw = (u64)blockIdx.x * 32 + warp;
+    u32* fill = W.bktFill + gw * B;
+    for (unsigned b = lane; b < B; b += 32) sCur[b] = fill[b];   // cursors continue where the previous slice of the sample stopped
+    __syncwarp();
+    u64* __restrict__ region = W.bktBuf + gw * B * (u64)W.bktRegionCap;
+    const u64 mask = W.tableMask;
+    const u64 warpsTotal = (u64)gridDim.x * 32;
+    for (u64 r0 = gw * 32; r0 < nReads; r0 += warpsTotal * 32) {
+        const u64 r = r0 + lane;
+        const int n = r < nReads ? (int)__ldg(&synCount[r]) : 0;
+        const u64* __restrict__ h = synBuf + (r < nReads ? __ldg(&packedOff[r]) : 0) * 32;
+        const int nS = LT <= 1 ? n : (n >= LT ? n - LT + 1 : 0);
+        int maxS = nS;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            key[q] = kEmptyKey;
-            if (has[q]) { const uint4 t = tex1Dfetch<uint4>(tableTex, (int)slot[q]); key[q] = (u64)t.x | ((u64)t.y << 32); }
-        }
+        for (int d = 16; d > 0; d >>= 1) maxS = max(maxS, __shfl_xor_sync(0xffffffffu, maxS, d));
+        u64 h0 = 0, h1 = 0;
+        if (LT == 3 && nS > 0) { h0 = __ldg(h); h1 = __ldg(h + 1); }
+        for (int j0 = 0; j0 < maxS; j0 += 4) {
+            u64 x[4], sd[4]; bool has[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            claim[q] = slow[q] = false;
-            if (has[q]) {
-                if (sd[q] == kEmptyKey) slow[q] = true;
-                else if (key[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u);
-                else if (key[q] == kEmptyKey) claim[q] = true;
-                else slow[q] = true;
+            for (int q = 0; q < 4; q += 2) {   // 16 bytes at a time, as in count_seeds_lane
+                has[q] = j0 + q < nS; has[q + 1] = j0 + q + 1 < nS;
+                uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                if (has[q]) t = __ldcs(reinterpret_cast<const uint4*>(h + j0 + q + (LT - 1)));
+                x[q] = (u64)t.x | ((u64)t.y << 32); x[q + 1] = (u64)t.z | ((u64)t.w << 32);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (LT == 1) sd[q] = x[q];
+                else {
+                    const u64 fw = rol64(h0, (unsigned)((KT * 2) & 63)) ^ rol64(h1, (unsigned)(KT & 63)) ^ x[q];
+                    const u64 rw = h0 ^ rol64(h1, (unsigned)(KT & 63)) ^ rol64(x[q], (unsigned)((KT * 2) & 63));
+                    sd[q] = umin64(fw, rw);
+                    has[q] = has[q] && fw != rw;
+                    h0 = h1; h1 = x[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (!has[q]) continue;
+                const unsigned b = (unsigned)((mixKey(sd[q]) & mask) >> W.bktShift);
+                const unsigned pos = atomicAdd(&sCur[b], 1u);
+                if (pos < W.bktRegionCap) __stcs(region + (u64)b * W.bktRegionCap + pos, sd[q]);
+                else tableInsert(W.table, mask, sd[q], 1u, W.acc);   // region full: counted right away
             }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (claim[q]) was[q] = atomicCAS(reinterpret_cast<unsigned long long*>(&table[slot[q]].key), (unsigned long long)kEmptyKey, (unsigned long long)sd[q]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (claim[q]) { if (was[q] == kEmptyKey || was[q] == sd[q]) atomicAdd(&table[slot[q]].count, 1u); else slow[q] = true; }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (slow[q]) tableInsert(table, mask, sd[q], 1u, acc);
     }
+    __syncwarp();
+    for (unsigned b = lane; b < B; b += 32) fill[b] = min(sCur[b], W.bktRegionCap);
+}
+// second half: bucket after bucket, every warp its own region of the bucket, four seeds per lane in flight
+__global__ void __launch_bounds__(1024, 1) count_buckets(WorkspaceView W) {
+    const unsigned lane = threadIdx.x & 31u, B = W.bktCount;
+    const u64 gw = (u64)blockIdx.x * 32 + (threadIdx.x >> 5);
+    const u64* __restrict__ region = W.bktBuf + gw * B * (u64)W.bktRegionCap;
+    for (unsigned b = 0; b < B; ++b) {
+        const unsigned n = W.bktFill[gw * B + b];
+        const u64* __restrict__ src = region + (u64)b * W.bktRegionCap;
+        for (unsigned i0 = lane; i0 < n; i0 += 128) {
+            u64 sd[4]; bool has[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const unsigned i = i0 + 32u * q; has[q] = i < n; sd[q] = has[q] ? __ldcs(src + i) : 0; }
+            insertFour(sd, has, W.table, W.tableMask, W.acc, W.tableTex);
+        }
+    }
+}
+bool bucketCountingSupports(int k, int l) { return (l == 3 && (k == 19 || k == 15)) || l <= 1; }
+void launchCountBuckets(WorkspaceView W, cudaStream_t st) {
+    if (!W.bktCount) return;
+    noteLaunch(), count_buckets<<<kBktBlocks, 1024, 0, st>>>(W);
+}
+template <int KT, int LT>
+static void launchScatterT(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, const WorkspaceView& W, cudaStream_t st) {
+    const size_t sm = (size_t)32 * W.bktCount * sizeof(unsigned);
+    noteLaunch(), scatter_seeds_lane<KT, LT><<<kBktBlocks, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, W);
+}
+static void launchScatter(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, int k, int l, const WorkspaceView& W, cudaStream_t st) {
+    if (k == 19 && l == 3) return launchScatterT<19, 3>(synBuf, synCount, packedOff, nReads, W, st);
+    if (k == 15 && l == 3) return launchScatterT<15, 3>(synBuf, synCount, packedOff, nReads, W, st);
+    return launchScatterT<0, 1>(synBuf, synCount, packedOff, nReads, W, st);
 }
 // Measured on the 1M x 150 bp sample (r02f): count_seeds_lane without the global walk 328 us + count_misses 136-158 us = 475 us against
 // 393 us with the walk inside -- the walk was not the bottleneck (list loads + shared-memory probes are), and on its own the queue pass
@@ -1235,7 +1338,8 @@ void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, 
     if (nReads == 0) return;
     launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, dup, endOff, st, reads);
     if (between) cudaEventRecord(between, st);
-    launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, W.missQ, W.missCap, st);
+    if (W.bktCount) launchScatter(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W, st);   // partitioned counting: launchCountBuckets follows the last slice
+    else launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, W.missQ, W.missCap, st);
 }
 // --min-seed-quality > 0 (off by default): the generic kernels with per-syncmer pass flags; quals has one byte per base at the reads'
 // offsets (compressed in lockstep for hpc indexes), synPass one byte per synBuf entry

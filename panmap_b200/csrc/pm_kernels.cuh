@@ -95,6 +95,9 @@ struct WorkspaceView {
     SampleAcc* acc;
     u64* synBuf; unsigned* synCount;  // per-read syncmer hashes (region of read r starts at 32*packedOff[r]) and counts
     u64* missQ; u64 missCap;          // seeds that missed the per-SM tables of count_seeds_lane, waiting for count_misses
+    // partitioned counting (tables larger than L2): seed instances scattered by table region, counted region by region (bktCount == 0: off)
+    u64* bktBuf; u32* bktFill;        // [kBktWarps * bktCount][bktRegionCap] seeds and their fill counts, one region per (warp, bucket)
+    u32 bktCount, bktShift, bktRegionCap;   // buckets (power of two), bucket = home slot >> bktShift
     cudaTextureObject_t ellTex;   // ell as a linear int2 texture: scattered gathers go through the TEX data path instead of the LSU's
     long long* ell;       // [nSeeds+2] log1p(read count) * 2^53 of the seed id (an exact integer), 0 when absent; slot nSeeds stays 0
     u64* entKey; u32* entCnt; u32* entId;   // [tableCap] occupied (key, count) pairs compacted by table_scan + the seed id found for them
@@ -161,6 +164,11 @@ void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, 
 void launchSeedTableQuality(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                             const SeedTables* dTables, WorkspaceView W, cudaStream_t st, const u64* endOff, const char* quals,
                             int minSeedQuality, unsigned char* synPass);
+// partitioned counting: the grid both kernels run with (one region per resident warp and bucket), whether (k, l) has a scatter kernel, and the
+// pass over the regions that launchSeedTable's scatter leaves behind (call once after the last slice of a sample)
+constexpr u32 kBktBlocks = 148, kBktWarps = kBktBlocks * 32;
+bool bucketCountingSupports(int k, int l);
+void launchCountBuckets(WorkspaceView W, cudaStream_t st);
 // true when launchSeedTable can hash these parameters straight from the ASCII reads (pass `reads`, skip pack_reads)
 bool seedTableReadsAscii(const SeederParams& P);
 // --dedup: dup[r] = 1 when a byte-identical read holds the set already; reads [rBegin, rEnd) of the sample, `off` = all offsets

@@ -661,6 +661,42 @@ def test_table_estimate_is_clamped_to_the_device_limit_and_a_real_overflow_fails
     assert res2.raw.unique_seeds == eh.size
 
 
+@pytest.mark.parametrize("k,s,t,l", [(19, 8, 0, 3), (15, 8, 0, 3), (15, 8, 0, 1)])
+def test_partitioned_counting_gives_the_same_table(monkeypatch, k, s, t, l):
+    """tables larger than L2 are filled by scatter_seeds_lane + count_buckets (seed instances partitioned by table region, counted region by
+    region).  With the threshold lowered, a small sample goes that way through every entry point (resident, host buffers in one piece and
+    sliced, 4-bit codes) and must leave exactly the oracle's table and placement; with regions of 4 entries nearly every seed takes the
+    full-region fallback."""
+    rng = np.random.default_rng(31)
+    idx, _, _ = H.synthetic_index(200, rng, k=k, s=s, t=t, l=l)
+    host = pm.HostIndex(idx.hash, idx.parent, idx.child, idx.offsets, idx.parent_index, idx.k, idx.s, idx.t, idx.l, idx.open)
+    reads = H.random_reads(rng, 6000, lo=60, hi=260) + [b"", b"ACGT", b"N" * 70]
+    buf, off = pm.pack_reads(reads)
+    eh, ec = cpu.seed_table(buf, off, idx.k, idx.s, idx.t, idx.l, idx.open, 0, 0, False)
+    ws0 = pm.Workspace(pm.Index(host))
+    want = ws0.place(buf, off)
+    monkeypatch.setenv("PM_BUCKET_MIN_SLOTS", "4096")
+    for region_cap, slice_bytes in ((None, None), (None, "65536"), ("4", None)):
+        if region_cap:
+            monkeypatch.setenv("PM_BUCKET_REGION_CAP", region_cap)
+        if slice_bytes:
+            monkeypatch.setenv("PM_SLICE_MIN_BYTES", slice_bytes)
+        ws = pm.Workspace(pm.Index(host))
+        launches0 = pm.launch_count()
+        for how in ("host", "resident", "packed", "host"):
+            if how == "host":
+                res = ws.place(buf, off)
+            elif how == "resident":
+                ws.upload(buf, off); res = ws.place_resident()
+            else:
+                res = ws.place_packed(pm.host_pack_reads(buf, off), off)
+            th, tc = ws.seed_table()
+            assert res.raw.unique_seeds == eh.size and np.array_equal(th[tc > 0], eh) and np.array_equal(tc[tc > 0], ec), (how, region_cap, slice_bytes)
+            for m in pm.METRICS:
+                assert res.best_index[m] == want.best_index[m] and res.best_score[m] == want.best_score[m] and np.array_equal(res.tied[m], want.tied[m])
+        monkeypatch.delenv("PM_BUCKET_REGION_CAP", raising=False); monkeypatch.delenv("PM_SLICE_MIN_BYTES", raising=False)
+
+
 def test_hash_seq_matches_oracle_and_rejects_non_acgt():
     """seeding::hashSeq (seeding.cpp:20-30) on the GPU for a batch of k-mers of every length 1..40 (rotations wrap at 64 like the reference's)"""
     rng = np.random.default_rng(77)
