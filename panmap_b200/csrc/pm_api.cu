@@ -380,7 +380,9 @@ static void planBuckets(pm_workspace* W, u64 windowsUpper, const pm_place_params
     const bool quality = W->useQuals && prm.min_seed_quality > 0;
     if (W->tableCap < bucketMinSlots() || quality || !bucketCountingSupports(sp.k, sp.l) || windowsUpper == 0) { refreshView(W); return; }
     u64 B = 2;
-    while (B < 256 && W->tableCap * sizeof(TableSlot) / B > (32ull << 20)) B <<= 1;
+    const char* be = std::getenv("PM_BUCKET_BYTES");   // tuning override, read per sample (tools/count_probe.py sweeps it)
+    const u64 bucketBytes = be ? std::max<u64>(1 << 20, std::strtoull(be, nullptr, 10)) : (u64)32 << 20;
+    while (B < 256 && W->tableCap * sizeof(TableSlot) / B > bucketBytes) B <<= 1;
     unsigned shift = 0;
     while ((W->tableCap >> shift) > B) ++shift;
     const u64 expected = windowsUpper * 45 / 100;
