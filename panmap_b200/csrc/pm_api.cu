@@ -140,8 +140,11 @@ void refreshView(pm_workspace* W) {
 
 // table capacity is kept between 2x and 4x the unique seeds of the previous sample (tighter fits were measured: the insertions
 // lose what the table passes gain)
-static u64 fitLo() { return 4; }
-static u64 fitHi() { return 8; }
+static u64 fitLo() {   // tuning override PM_TABLE_FIT_LO (3 = tables between 1.5x and 3x the entries)
+    static const u64 v = [] { const char* e = std::getenv("PM_TABLE_FIT_LO"); const u64 x = e ? std::strtoull(e, nullptr, 10) : 4; return x >= 3 && x <= 16 ? x : 4; }();
+    return v;
+}
+static u64 fitHi() { return 2 * fitLo(); }
 
 // grows the table in use to at least wantCap slots (never shrinks it); a prefix of a larger allocation is reused as it is.
 // The table is also bound as a linear texture (first probes go through the texture path), so its size is capped by the device's
@@ -192,7 +195,7 @@ void checkParams(const pm_place_params* p) {
 // host side: chunk offsets of the packed layout (ceil(len/32) 16-byte chunks per read)
 static void hostPackedOffsets(pm_workspace* W, const uint64_t* off, u64 n, int k) {
     W->hPackedOff.ensure(n + 1);
-    u64 acc = 0, win = 0;
+    u64 acc = 0, win = 0, mx = 0;
     for (u64 i = 0; i < n; ++i) {
         W->hPackedOff.p[i] = acc;
         if (off[i + 1] < off[i]) throw std::runtime_error("read offsets not monotone");
@@ -200,9 +203,10 @@ static void hostPackedOffsets(pm_workspace* W, const uint64_t* off, u64 n, int k
         if (L > 0x7FFFFFF0ull) throw std::runtime_error("read longer than 2^31 bases");
         acc += (L + 31) >> 5;
         if (L >= (u64)k) win += L - (u64)k + 1;
+        mx = std::max(mx, L);
     }
     W->hPackedOff.p[n] = acc;
-    W->nChunks = acc; W->totalWindows = win;
+    W->nChunks = acc; W->totalWindows = win; W->maxReadLen = mx;
     W->hBlockFirst.ensure((acc + 255) / 256 + 1);
     packBlockFirst(W->hPackedOff.p, n, acc, W->hBlockFirst.p);
 }
@@ -276,7 +280,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     W->blockFirst.ensure(total / 32 / 256 + n / 256 + 2 * nSlices + 32);
     if (W->tableCap == 0) ensureTable(W, std::max<u64>(1 << 16, (total > (u64)k * n ? total - (u64)(k - 1) * n : 0) / 4));
     refreshView(W);
-    const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
+    SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
     CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
     launchTableClear(W->view, W->st);
     unsigned char* dup = prepareDedup(W, n, prm);
@@ -284,11 +288,12 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
     const bool hpc = I->F.sp.hpc != 0;
     if (hpc) W->endOff.ensure(n + 1);
     if (ascii) W->tileSum.ensure(n / 4096 + 2);
-    u64 chunkAcc = 0, win = 0, bfBase = 0;
+    u64 chunkAcc = 0, win = 0, bfBase = 0, mxAll = 0;
     for (int sl = 0; sl < nSlices; ++sl) {
         const u64 r0 = nSlices == 1 ? 0 : (u64)((double)n * kCut[sl]), r1 = nSlices == 1 || sl + 1 == nSlices ? n : (u64)((double)n * kCut[sl + 1]);
         if (r1 == r0) continue;
         const u64 gBase = chunkAcc;
+        u64 mx = 0;
         for (u64 i = r0; i < r1; ++i) {
             if (off[i + 1] < off[i]) throw std::runtime_error("read offsets not monotone");
             const u64 L = off[i + 1] - off[i];
@@ -296,7 +301,9 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
             if (!ascii) W->hPackedOff.p[i] = chunkAcc;
             chunkAcc += (L + 31) >> 5;
             if (L >= (u64)k) win += L - (u64)k + 1;
+            mx = std::max(mx, L);
         }
+        P.maxLen = (int)std::min<u64>(mx, 0x7FFFFFFF); mxAll = std::max(mxAll, mx);   // this slice's longest read
         const u64 nCh = chunkAcc - gBase, nBlk = (nCh + 255) / 256;
         const u64 b0 = off[r0], b1 = off[r1];
         if (b1 > b0) CK(cudaMemcpyAsync(W->reads.p + b0, reads + b0, b1 - b0, cudaMemcpyHostToDevice, W->stCopy));
@@ -318,7 +325,7 @@ void uploadAndSeedPipelined(pm_workspace* W, const char* reads, const uint64_t* 
         bfBase += nBlk + 1;
     }
     launchCountBuckets(W->view, W->st);   // partitioned counting only: the slices scattered their seeds, one pass counts them
-    W->nChunks = chunkAcc; W->totalWindows = win; W->residentValid = false; W->hpcDone = false;
+    W->nChunks = chunkAcc; W->totalWindows = win; W->maxReadLen = mxAll; W->residentValid = false; W->hpcDone = false;
 }
 
 // The same pipeline for reads that arrive as 4-bit codes (pm_place_packed): half the bytes on the wire, and the syncmer kernel takes the
@@ -398,7 +405,8 @@ static void planBuckets(pm_workspace* W, u64 windowsUpper, const pm_place_params
 
 void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
     pm_index* I = W->idx;
-    const SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
+    SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
+    P.maxLen = (int)std::min<u64>(W->maxReadLen, 0x7FFFFFFF);
     if (clearFirst) {
         CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
         launchTableClear(W->view, W->st);
@@ -427,7 +435,15 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
                                prm.min_seed_quality, W->synPass.p);
         CK(cudaEventRecord(W->evK[2], W->st));
     } else {
-        launchSeedTable(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, W->evK[2], dup, endOff, ascii ? W->reads.p : nullptr);
+        // experiment switch (PM_RESIDENT_SLICES = n): hash and count the resident sample slice after slice, so that a slice's syncmer lists are
+        // still in L2 when they are counted
+        static const int kSlices = [] { const char* e = std::getenv("PM_RESIDENT_SLICES"); const int v = e ? std::atoi(e) : 1; return v < 1 ? 1 : v > 64 ? 64 : v; }();
+        const int ns = (kSlices > 1 && ascii && !dup && !endOff && W->nReads >= (u64)kSlices * 1024) ? kSlices : 1;
+        for (int sl = 0; sl < ns; ++sl) {
+            const u64 r0 = W->nReads * (u64)sl / (u64)ns, r1 = W->nReads * (u64)(sl + 1) / (u64)ns;
+            launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, sl + 1 == ns ? W->evK[2] : nullptr,
+                            dup ? dup + r0 : nullptr, endOff ? endOff + r0 : nullptr, ascii ? W->reads.p : nullptr);
+        }
         launchCountBuckets(W->view, W->st);   // partitioned counting only (no-op otherwise)
     }
     CK(cudaEventRecord(W->evK[3], W->st));
@@ -562,8 +578,13 @@ static int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result
         launchChain(W->view, nullptr, W->st);
         launchTies(I->view, W->view, makeOpts(*prm, false), W->st);
         CK(cudaEventRecord(W->ev[6], W->st));
-        fetchSmall(W);
+        // result block D2H, then the sample's reset, then ONE host synchronisation: the reset (which touches neither the block nor the tie
+        // lists) no longer waits for the host to wake up in between
+        enqueueSmall(W);
         launchResetSample(I->view, W->view, W->st);
+        CK(cudaEventRecord(W->ev[7], W->st));
+        CK(cudaStreamSynchronize(W->st));
+        parseSmall(W);
         const bool tableTight = (u64)W->hAcc.entries * 10 > W->tableCap * 7;
         if (W->hAcc.overflow || tableTight) {
             // grow and redo: the table (or a list) was too small for this sample
@@ -574,10 +595,8 @@ static int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result
             W->lastEntries = 0;
             continue;
         }
-        fetchTies(W);
+        fetchTies(W);   // long tie lists only: one more copy + synchronisation (outside the stage timers)
         W->lastEntries = (u64)W->hAcc.entries;
-        CK(cudaEventRecord(W->ev[7], W->st));
-        CK(cudaStreamSynchronize(W->st));
         fillResult(W, res, W->nReads);
         recordStageTimes(W, res);
         W->haveResult = true;

@@ -95,7 +95,7 @@ struct pm_workspace {
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;
     PinBuf<char> hIngestReads, hIngestQuals; PinBuf<u64> hIngestOff;   // pm_workspace_staging: pinned landing buffers of a file parser
-    u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0;
+    u64 nReads = 0, nChunks = 0, totalBases = 0, totalWindows = 0, maxReadLen = 0;   // maxReadLen: longest read of the resident sample (0 = unknown)
     bool residentValid = false;  // the device copy of the reads was laid out by pm_reads_upload (not by the sliced pm_place path)
     bool uploadPending = false;  // pm_reads_upload_device enqueued copies from the pinned staging arrays and did not wait
     bool hpcDone = false;        // hpc indexes: the resident reads (and qualities) were compressed in place already, endOff is valid

@@ -515,7 +515,14 @@ __global__ void __launch_bounds__(kSeedThreads) syncmers_fast(const uint4* __res
 // returns the two per-strand "<=" predicates).  The rolling k-mer hashes -- the values that are reported -- are unchanged.
 // One persistent block per SM (the table takes 128 of its 227 KB of shared memory).
 __device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-template <int K, bool ASCII, bool NOTRIM, int THREADS>
+// STAGE (ASCII input, reads of at most kStageMaxLen bases -- the host guarantees it): the bytes of a warp's 32 consecutive reads are one
+// contiguous span of the sample, brought into the warp's own staging buffer by ONE TMA bulk copy per group (coalesced, no L1 wavefronts, no
+// sector fetched twice) instead of 32 lanes each pulling 4 bytes at a time from its own line (18 L1 wavefronts per request, a third of the
+// kernel's L1 data-pipe load, and 245 MB of DRAM reads for 150 MB of bases); the lanes then read their words from shared memory.
+constexpr int kStageMaxLen = 151;
+constexpr unsigned kStageBytes = 32u * kStageMaxLen + 32u;   // span of 32 reads + alignment of both ends to 16 bytes
+constexpr unsigned kStagePitch = kStageBytes + 16u;          // + the word past the last one (funnel shift)
+template <int K, bool ASCII, bool NOTRIM, int THREADS, bool STAGE = false>
 __global__ void __launch_bounds__(THREADS, 1) syncmers_rank(const uint4* __restrict__ packed, const u64* __restrict__ off,
                                                                  const u64* __restrict__ packedOff, u64 nReads, SeederParams P,
                                                                  const SeedTables* __restrict__ gT, u64* __restrict__ synBuf,
@@ -527,9 +534,14 @@ __global__ void __launch_bounds__(THREADS, 1) syncmers_rank(const uint4* __restr
     unsigned char* sRank = smemRaw;                                              // u16[65536]
     u64* sPair = reinterpret_cast<u64*>(smemRaw + kRankEntries * 2);             // [2][kPairStride]: fk, rk (outgoing, incoming) pair tables
     unsigned char* sLut = smemRaw + kRankEntries * 2 + 2 * kPairStride * 8;      // ASCII -> base code
+    static_assert(!STAGE || ASCII, "staging is for ASCII input");
+    unsigned char* sStage = smemRaw + kRankEntries * 2 + 2 * kPairStride * 8 + 256 + (size_t)(threadIdx.x >> 5) * kStagePitch;   // this warp's
     __shared__ __align__(8) unsigned long long sBar;
+    __shared__ __align__(8) unsigned long long sWarpBar[THREADS / 32];
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&sBar)));
+        if (STAGE)
+            for (int w = 0; w < THREADS / 32; ++w) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&sWarpBar[w])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -551,6 +563,7 @@ __global__ void __launch_bounds__(THREADS, 1) syncmers_rank(const uint4* __restr
                          : "memory");
     }
     bool tableReady = false;
+    unsigned stagePhase = 0;   // parity of this warp's staging barrier
     RankWindow<W> win;
     const unsigned lane = threadIdx.x & 31u;
     const u64 warpsTotal = (u64)gridDim.x * (blockDim.x >> 5);
@@ -570,6 +583,32 @@ __global__ void __launch_bounds__(THREADS, 1) syncmers_rank(const uint4* __restr
         int maxL = L, minL = L;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { maxL = max(maxL, __shfl_xor_sync(0xffffffffu, maxL, d)); minL = min(minL, __shfl_xor_sync(0xffffffffu, minL, d)); }
+        unsigned sOff = 0;   // STAGE: byte offset of the lane's read inside the staging buffer
+        if (STAGE) {
+            const u64 gB = __shfl_sync(0xffffffffu, b, 0);                      // lane 0 is always a valid read
+            const u64 rEnd = r0 + 32 < nReads ? r0 + 32 : nReads;
+            const u64 gE = off[rEnd];
+            const u64 g0 = gB & ~15ULL;
+            const unsigned bytes = (unsigned)(((gE + 15ULL) & ~15ULL) - g0);  // the reads buffer ends with 64 spare bytes
+            if (bytes > kStageBytes) __trap();                                  // the launcher checked the longest read
+            sOff = valid ? (unsigned)(b - g0) : 0u;
+            __syncwarp();   // every lane has consumed its words of the previous group
+            if (bytes) {
+                const unsigned wbar = smemAddr(&sWarpBar[threadIdx.x >> 5]);
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wbar), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(sStage)),
+                                 "l"(reads + g0), "r"(bytes), "r"(wbar)
+                                 : "memory");
+                }
+                unsigned ok;
+                do {
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(wbar), "r"(stagePhase) : "memory");
+                } while (!ok);
+                stagePhase ^= 1u;
+            }
+        }
         if (!tableReady) {   // first group of the warp: everything above overlapped the bulk copy
             unsigned ok;
             do {
@@ -593,9 +632,15 @@ __global__ void __launch_bounds__(THREADS, 1) syncmers_rank(const uint4* __restr
         // the next four bases (i .. i+3, i a multiple of 4) as one code byte each
         auto loadWord = [&](int i) -> unsigned {
             if (ASCII) {   // 4 bytes from an arbitrary byte address: two aligned words, one funnel shift, four table look-ups
-                const unsigned a = rshift + (unsigned)i;
-                const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + (a & ~3u));
-                const unsigned x0 = __ldg(wp), x1 = __ldg(wp + 1);
+                const unsigned a = (STAGE ? sOff : rshift) + (unsigned)i;
+                unsigned x0, x1;
+                if (STAGE) {
+                    const unsigned* wp = reinterpret_cast<const unsigned*>(sStage + (a & ~3u));
+                    x0 = wp[0]; x1 = wp[1];
+                } else {
+                    const unsigned* wp = reinterpret_cast<const unsigned*>(rbase + (a & ~3u));
+                    x0 = __ldg(wp); x1 = __ldg(wp + 1);
+                }
                 const unsigned bts = __funnelshift_r(x0, x1, (a & 3u) * 8u);
                 unsigned cw = sLut[bts >> 24];
                 cw = cw * 256u + sLut[(bts >> 16) & 0xFFu];
@@ -923,7 +968,7 @@ constexpr int kWarpQueue = 128;   // staged misses per warp
 template <int KT, int LT, bool AGG, bool QUEUE>
 __global__ void __launch_bounds__(AGG ? 1024 : 256, 1) count_seeds_lane(const u64* __restrict__ synBuf, const unsigned* __restrict__ synCount,
                                                    const u64* __restrict__ packedOff, u64 nReads, TableSlot* table,
-                                                   u64 mask, SampleAcc* acc, cudaTextureObject_t tableTex, u64* __restrict__ missQ, u64 missCap) {
+                                                   u64 mask, SampleAcc* acc, cudaTextureObject_t tableTex, u64* __restrict__ missQ, u64 missCap, int listPrefetch) {
     static_assert(LT == 1 || LT == 3, "lane-per-read counting is specialised for l = 1 and l = 3");
     static_assert(AGG || !QUEUE, "the miss queue belongs to the pre-aggregating variant");
     extern __shared__ __align__(16) unsigned char aggRaw[];
@@ -957,6 +1002,10 @@ __global__ void __launch_bounds__(AGG ? 1024 : 256, 1) count_seeds_lane(const u6
         int maxS = nS;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) maxS = max(maxS, __shfl_xor_sync(0xffffffffu, maxS, d));
+        // the whole list of the lane's read is asked for at once (L2 prefetch, one request per 128-byte line): without it every round of
+        // four seeds starts with a fresh 32-byte sector from DRAM, one exposed DRAM latency per round and lane
+        if (listPrefetch)
+            for (int e = 16; e < n; e += 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(h + e));
         u64 h0 = 0, h1 = 0;   // the two syncmers before the next one to load (l = 3)
         if (LT == 3 && nS > 0) { h0 = __ldg(h); h1 = __ldg(h + 1); }
         constexpr int R = QUEUE ? 8 : 4;   // seeds per lane and round: without the global walk there are registers for eight loads in flight
@@ -1203,6 +1252,10 @@ static bool useMissQueue() {
     static const bool v = [] { const char* e = std::getenv("PM_MISS_QUEUE"); return e ? std::atoi(e) != 0 : false; }();
     return v;
 }
+static int listPrefetch() {   // experiment switch PM_LIST_PREFETCH (0 / 1)
+    static const int v = [] { const char* e = std::getenv("PM_LIST_PREFETCH"); return e ? std::atoi(e) : 0; }();
+    return v;
+}
 template <int KT, int LT>
 static void launchCountLane(const u64* synBuf, const unsigned* synCount, const u64* packedOff, u64 nReads, TableSlot* table, u64 mask, SampleAcc* acc,
                             cudaTextureObject_t tableTex, u64* missQ, u64 missCap, cudaStream_t st) {
@@ -1212,15 +1265,15 @@ static void launchCountLane(const u64* synBuf, const unsigned* synCount, const u
             const size_t smq = sm + (size_t)32 * kWarpQueue * sizeof(u64);
             cudaMemsetAsync(&acc->missCount, 0, sizeof(acc->missCount), st);
             cudaFuncSetAttribute(count_seeds_lane<KT, LT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smq);
-            noteLaunch(), count_seeds_lane<KT, LT, true, true><<<148, 1024, smq, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, missQ, missCap);
+            noteLaunch(), count_seeds_lane<KT, LT, true, true><<<148, 1024, smq, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, missQ, missCap, listPrefetch());
             noteLaunch(), count_misses<<<148 * 8, 256, 0, st>>>(missQ, missCap, table, mask, acc, tableTex);
             return;
         }
         cudaFuncSetAttribute(count_seeds_lane<KT, LT, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        noteLaunch(), count_seeds_lane<KT, LT, true, false><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, nullptr, 0);
+        noteLaunch(), count_seeds_lane<KT, LT, true, false><<<148, 1024, sm, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, nullptr, 0, listPrefetch());
     } else {
         u64 g = (nReads + 255) / 256; if (g > 148ull * 8) g = 148ull * 8;
-        noteLaunch(), count_seeds_lane<KT, LT, false, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, nullptr, 0);
+        noteLaunch(), count_seeds_lane<KT, LT, false, false><<<(unsigned)(g ? g : 1), 256, 0, st>>>(synBuf, synCount, packedOff, nReads, table, mask, acc, tableTex, nullptr, 0, listPrefetch());
     }
 }
 template <int MODE>
@@ -1281,12 +1334,27 @@ static int rankThreads() {   // tuning override: PM_RANK_THREADS (512 or 768)
     static const int v = [] { const char* e = std::getenv("PM_RANK_THREADS"); return e ? std::atoi(e) : 512; }();
     return v;
 }
+static bool rankStage() {   // experiment switch: PM_RANK_STAGE=1 stages the reads through shared memory (TMA bulk copy per group of 32 reads)
+    static const bool v = [] { const char* e = std::getenv("PM_RANK_STAGE"); return e ? std::atoi(e) != 0 : false; }();
+    return v;
+}
 template <int K, int THREADS>
 static void launchRankT(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P, const SeedTables* dT,
                         u64* synBuf, unsigned* synCount, const unsigned char* dup, const u64* endOff, const char* reads, cudaStream_t st) {
     const size_t sm = (size_t)kRankEntries * 2 + 2 * kPairStride * sizeof(u64) + 256;
     u64 g = (nReads + THREADS - 1) / THREADS; if (g > 148) g = 148;
     const unsigned grid = (unsigned)(g ? g : 1);
+    if (THREADS == 512 && reads && P.maxLen > 0 && P.maxLen <= kStageMaxLen && rankStage()) {   // reads staged through shared memory by TMA
+        const size_t sms = sm + (size_t)(THREADS / 32) * kStagePitch;
+        if (P.trimEnd == 0) {
+            cudaFuncSetAttribute(syncmers_rank<K, true, true, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms);
+            noteLaunch(), syncmers_rank<K, true, true, THREADS, true><<<grid, THREADS, sms, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+        } else {
+            cudaFuncSetAttribute(syncmers_rank<K, true, false, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms);
+            noteLaunch(), syncmers_rank<K, true, false, THREADS, true><<<grid, THREADS, sms, st>>>(packed, off, packedOff, nReads, P, dT, synBuf, synCount, dup, endOff, reads);
+        }
+        return;
+    }
 #define PM_RANK_LAUNCH(A, N)                                                                                                        \
     do {                                                                                                                            \
         cudaFuncSetAttribute(syncmers_rank<K, A, N, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);                \

@@ -84,6 +84,7 @@ struct SeederParams {
     unsigned rotKL;  // k*l mod 64
     unsigned rotKL1; // k*(l-1) mod 64
     int trimStart, trimEnd;
+    int maxLen;      // longest read of the launch when the host knows it (0 = unknown): lets syncmers_rank stage the reads in shared memory
 };
 inline SeederParams makeSeederParams(int k, int s, int t, int l, int open, int trimStart, int trimEnd) {
     SeederParams p;
@@ -91,7 +92,7 @@ inline SeederParams makeSeederParams(int k, int s, int t, int l, int open, int t
     p.rotK = (unsigned)k & 63u;
     p.rotKL = (unsigned)((long long)k * l) & 63u;
     p.rotKL1 = (unsigned)((long long)k * (l > 0 ? l - 1 : 0)) & 63u;
-    p.trimStart = trimStart; p.trimEnd = trimEnd;
+    p.trimStart = trimStart; p.trimEnd = trimEnd; p.maxLen = 0;
     return p;
 }
 
