@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 3
+#define PM_ABI_VERSION 4
 #define PM_NONE 0xFFFFFFFFu /* "no node" (reference: UINT32_MAX, placement.hpp:159) */
 #define PM_NUM_METRICS 5    /* log_raw, log_cosine, containment, weighted_containment, log_containment */
 
@@ -197,6 +197,19 @@ int pm_get_node_metrics(pm_workspace* ws, double* out /* [n_nodes][5]: logRawNum
  * 2 count_seeds / seeds_from_syncmers (profiling aid for bench.py; the same events bracket nothing else) */
 int pm_last_kernel_ms(pm_workspace* ws, float* out /* [3] */);
 int pm_get_seed_table(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap); /* unsorted; returns n or <0 */
+
+/* ---- own index builder (reference: IndexBuilder::buildIndex, index_single_mode.cpp:1227-1392 / processNode :1647-2205,
+ *      called from main.cpp:398-428): `.panman` -> per-node seed deltas.  Every node's ungapped genome (the reference's
+ *      getStringFromReference(tree, id, aligned = false), panmap_utils.cpp:7-193) is seeded on the GPU with the read path's kernels and
+ *      diffed against its parent's: delta for delta the LiteIndex the reference builds with --flank-mask 0.  flank_mask must be 0
+ *      (PM_ERR_UNSUPPORTED otherwise: the reference's flank masking makes its index depend on the traversal history).
+ *      The result is a host index like pm_host_index_read's: pm_host_index_desc / _extras / _write / pm_index_create apply. ---- */
+int pm_index_build(const char* panman_path, const pm_seed_params* sp, int flank_mask, int device, pm_host_index** out);
+/* the builder's input half alone (host only, no GPU): every node's ungapped genome concatenated in DFS pre-order (offsets[n_nodes + 1]),
+ * parent indexes, the node ids joined by '\n' and, per base, its aligned (global scalar) coordinate; each buffer is malloc'ed (free with
+ * pm_free); parent_index / ids_joined / coords may be null */
+int pm_panman_genomes(const char* panman_path, char** bases, uint64_t** offsets, uint32_t** parent_index, char** ids_joined, uint32_t** coords,
+                      uint64_t* n_nodes);
 
 /* ---- seeding::hashSeq (seeding.hpp:123, seeding.cpp:20-30) for a batch of k-mers: forward and reverse-complement hash of each sequence;
  *      PM_ERR_INVALID ("Kmer contains non canonical base") when a sequence holds anything but ACGT/acgt, like the reference's exception ---- */

@@ -6,5 +6,5 @@ call raises :class:`PanmapError` when the library or a CUDA device is missing.
 """
 from .api import (  # noqa: F401
     PanmapError, METRICS, lib, lib_path, build, device_count, launch_count, HostIndex, Index, Workspace, PlaceParams, PlaceResult,
-    hash_seq, rolling_syncmers, read_seeds, pack_reads, read_fastx, place_files, Comm, comm_unique_id, host_pack_reads, place_multi, place_multi_resident,
+    hash_seq, rolling_syncmers, read_seeds, pack_reads, read_fastx, panman_genomes, place_files, Comm, comm_unique_id, host_pack_reads, place_multi, place_multi_resident,
 )

@@ -240,6 +240,22 @@ class HostIndex:
         L = lib()
         h = C.c_void_p()
         _ck(L.pm_host_index_read(os.fsencode(path), C.byref(h)))
+        return cls._from_handle(h)
+
+    @classmethod
+    def build_from_panman(cls, panman_path, k=19, s=8, t=0, l=3, open=0, hpc=0, flank_mask=0, device=0):
+        """the product's own index builder (pm_index_build; reference IndexBuilder::buildIndex, index_single_mode.cpp:1227-1392): every
+        node genome of the .panman seeded on the GPU and diffed against its parent's; == panmap --flank-mask 0 delta for delta"""
+        L = lib()
+        L.pm_index_build.argtypes = [C.c_char_p, C.POINTER(SeedParams), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        sp = SeedParams(int(k), int(s), int(t), int(l), int(open), int(hpc))
+        h = C.c_void_p()
+        _ck(L.pm_index_build(os.fsencode(panman_path), C.byref(sp), int(flank_mask), int(device), C.byref(h)))
+        return cls._from_handle(h)
+
+    @classmethod
+    def _from_handle(cls, h):
+        L = lib()
         try:
             d = IndexDesc()
             _ck(L.pm_host_index_desc(h, C.byref(d)))
@@ -692,6 +708,27 @@ def read_seeds(seqs, k, s, t, l, open=False, trim_start=0, trim_end=0, device=0)
     sp = SeedParams(k, s, t, l, int(bool(open)), 0)
     _ck(lib().pm_read_seeds(device, _ptr(buf), off.ctypes.data_as(C.c_void_p), n, C.byref(sp), trim_start, trim_end, _ptr(h), _ptr(c)))
     return [h[woff[i]:woff[i] + int(c[i])] for i in range(n)]
+
+
+def panman_genomes(panman_path, coords=False):
+    """every node's ungapped genome of a .panman in DFS pre-order (pm_panman_genomes; the reference's getStringFromReference,
+    panmap_utils.cpp:7-193): (uint8 bases, uint64 offsets[n + 1], uint32 parent_index[n], [ids])"""
+    L = lib()
+    L.pm_panman_genomes.argtypes = [C.c_char_p] + [C.POINTER(C.c_void_p)] * 5 + [C.POINTER(C.c_uint64)]
+    b, o, pi, ids, co, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+    _ck(L.pm_panman_genomes(os.fsencode(panman_path), C.byref(b), C.byref(o), C.byref(pi), C.byref(ids), C.byref(co) if coords else None, C.byref(n)))
+    try:
+        off = np.ctypeslib.as_array(C.cast(o, C.POINTER(C.c_uint64)), shape=(n.value + 1,)).copy()
+        tot = int(off[-1])
+        bases = np.ctypeslib.as_array(C.cast(b, C.POINTER(C.c_uint8)), shape=(max(tot, 1),))[:tot].copy()
+        par = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint32)), shape=(max(n.value, 1),))[:n.value].copy()
+        names = C.string_at(ids).decode().split("\n")[:n.value]
+        cc = np.ctypeslib.as_array(C.cast(co, C.POINTER(C.c_uint32)), shape=(max(tot, 1),))[:tot].copy() if coords else None
+    finally:
+        for q in (b, o, pi, ids, co):
+            if q:
+                L.pm_free(q)
+    return (bases, off, par, names, cc) if coords else (bases, off, par, names)
 
 
 def read_fastx(reads1, reads2=""):

@@ -927,7 +927,7 @@ int pm_get_seed_table(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t
 }
 
 // ---- seeding::rollingSyncmers / per-read seeds on the GPU (parity + drop-in for the host shim) ----
-static int seedListImpl(int device, const char* seqs, const uint64_t* off, uint64_t n, const pm_seed_params* sp, int trimStart,
+int seedListImpl(int device, const char* seqs, const uint64_t* off, uint64_t n, const pm_seed_params* sp, int trimStart,
                         int trimEnd, int mode, uint64_t* outHash, uint8_t* outRev, int64_t* outPos, uint64_t* outCount) {
     if (!off || (!seqs && n) || !sp || !outHash || !outCount) return fail(PM_ERR_INVALID, "null argument");
     if (deviceCountNoThrow() <= device || device < 0) return fail(PM_ERR_NO_DEVICE, "no usable CUDA device (this library has no CPU fallback)");

@@ -3,6 +3,7 @@
 #include "../../include/panmap_b200.h"
 #include <cstdint>
 #include <stdexcept>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -39,6 +40,24 @@ struct IdxExtras {
 // (zstdLevel < 0) or as independent 64 MB zstd frames.  Returns the number of bytes written.
 uint64_t writeIdxFile(const std::string& path, const pm_index_desc& d, const IdxExtras& x, int zstdLevel);
 
+
+// ---- `.panman` input of the index builder (pm_panman.cpp) ----
+constexpr uint32_t kNoNode = 0xFFFFFFFFu;
+struct PanmanNucMut { int32_t block, pos, gap; uint8_t len, type; uint32_t nucs; };   // gap == -1: main positions pos .. pos + len - 1
+struct PanmanBlockMut { int32_t block; bool insertion, inversion; };
+struct PanmanGapList { int32_t block; std::vector<int32_t> position, length; };
+struct PanmanNode { std::string id; uint32_t parent = kNoNode; std::vector<uint32_t> children; uint32_t nucBegin = 0, nucEnd = 0, blockBegin = 0, blockEnd = 0; };
+struct PanmanTree {
+    std::vector<PanmanNode> nodes;            // newick pre-order == the DFS order of the index
+    std::vector<PanmanNucMut> nucMuts;        // per node: [nucBegin, nucEnd)
+    std::vector<PanmanBlockMut> blockMuts;    // per node: [blockBegin, blockEnd)
+    std::vector<std::string> blocks;          // consensus of block b as characters
+    std::vector<PanmanGapList> gaps;
+};
+void readPanman(const std::string& path, PanmanTree& out);
+// one depth-first walk over the tree: visit(node, ungapped genome of the node) for every node, in pre-order
+void walkPanmanGenomes(const PanmanTree& T, const std::function<void(uint32_t, const std::string&)>& visit);
+void walkPanmanGenomesCoords(const PanmanTree& T, bool wantCoords, const std::function<void(uint32_t, const std::string&, const std::vector<uint32_t>&)>& visit);
 
 // everything pm_index_create derives from a pm_index_desc before uploading (see DESIGN.md "HBM layout")
 struct FlatIndex {

@@ -7,6 +7,7 @@
 // The message is walked with a small schema-less pointer decoder (struct / list / far pointers); the struct
 // shapes used are LiteIndex (2 data words, 11 pointers), LiteTree (0,2) and LiteNode (1,1).
 #include "pm_host.h"
+#include "pm_capnp.h"
 
 #include <dlfcn.h>
 
@@ -19,52 +20,7 @@
 namespace pm {
 namespace {
 
-struct Msg {
-    const uint8_t* base = nullptr;
-    std::vector<size_t> segStart, segWords;
-    uint64_t word(uint32_t seg, size_t w) const {
-        if (seg >= segStart.size() || w >= segWords[seg]) throw std::runtime_error("index: pointer out of range");
-        uint64_t v; std::memcpy(&v, base + segStart[seg] + 8 * w, 8); return v;
-    }
-    // checked view of `bytes` bytes that start at word w of segment seg (every list body goes through here)
-    const uint8_t* span(uint32_t seg, size_t w, uint64_t bytes) const {
-        if (seg >= segStart.size() || w > segWords[seg] || bytes > 8ull * (segWords[seg] - w)) throw std::runtime_error("index: list extends past its segment (truncated or corrupt file)");
-        return base + segStart[seg] + 8 * w;
-    }
-};
-struct Ref { int kind = 0; uint32_t seg = 0; size_t off = 0; uint32_t dataWords = 0, ptrWords = 0, elemSize = 0; uint64_t count = 0; };
-
-Ref decode(const Msg& m, uint64_t p, uint32_t seg, size_t base) {
-    Ref r; r.seg = seg;
-    const int64_t off = static_cast<int32_t>(p & 0xffffffffu) >> 2;
-    r.off = static_cast<size_t>(static_cast<int64_t>(base) + off);
-    if ((p & 3) == 0) { r.kind = 1; r.dataWords = (p >> 32) & 0xffff; r.ptrWords = (p >> 48) & 0xffff; }
-    else {
-        r.kind = 2; r.elemSize = (p >> 32) & 7; r.count = p >> 35;
-        if (r.elemSize == 7) {
-            const uint64_t tag = m.word(seg, r.off);
-            r.count = static_cast<uint32_t>(tag & 0xffffffffu) >> 2;
-            r.dataWords = (tag >> 32) & 0xffff; r.ptrWords = (tag >> 48) & 0xffff;
-            r.off += 1;
-        }
-    }
-    return r;
-}
-Ref resolve(const Msg& m, uint32_t seg, size_t w) {
-    const uint64_t p = m.word(seg, w);
-    if (p == 0) return Ref{};
-    if ((p & 3) == 2) {
-        const bool dbl = (p >> 2) & 1;
-        const size_t padOff = (p & 0xffffffffu) >> 3;
-        const uint32_t padSeg = static_cast<uint32_t>(p >> 32);
-        if (!dbl) { const uint64_t q = m.word(padSeg, padOff); return q ? decode(m, q, padSeg, padOff + 1) : Ref{}; }
-        const uint64_t far2 = m.word(padSeg, padOff), tag = m.word(padSeg, padOff + 1);
-        return decode(m, tag & 0xFFFFFFFF00000003ULL, static_cast<uint32_t>(far2 >> 32), (far2 & 0xffffffffu) >> 3);
-    }
-    if ((p & 3) == 3) throw std::runtime_error("index: unexpected capability pointer");
-    return decode(m, p, seg, w + 1);
-}
-Ref ptrOf(const Msg& m, const Ref& s, uint32_t i) { return (s.kind == 1 && i < s.ptrWords) ? resolve(m, s.seg, s.off + s.dataWords + i) : Ref{}; }
+using namespace capnp_walk;
 static const size_t kElemBytes[8] = {0, 0, 1, 2, 4, 8, 8, 0};
 
 // zstd-framed payloads (the reference's default: independent 64 MB frames, index_single_mode.cpp:1615-1633,

@@ -10,6 +10,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 SARS_IDX = os.path.join(REF_DATA, "sars_20000.k19s8t0l3.idx")
 RSV_IDX = os.path.join(REF_DATA, "rsv_4K.k19s8t0l3.idx")
 MAMMOTH_IDX = os.path.join(REF_DATA, "extended_mammoth.k15s8t0l1.idx")
+# index-builder parity: the bundled .panman files and the indexes the reference builds from them with --flank-mask 0
+SARS_PANMAN = os.path.join(REF_DATA, "sars_20000_twilight_dipper.panman")
+RSV_PANMAN = os.path.join(REF_DATA, "rsv_4K.panman")
+MAMMOTH_PANMAN = os.path.join(REF_DATA, "extended_mammoth.panman")
+SARS_IDX_F0 = os.path.join(REF_DATA, "sars_20000.k19s8t0l3.flank0.idx")
+RSV_IDX_F0 = os.path.join(REF_DATA, "rsv_4K.k19s8t0l3.flank0.idx")
+MAMMOTH_IDX_F0 = os.path.join(REF_DATA, "extended_mammoth.k15s8t0l1.flank0.idx")
 ISOLATE_R1 = os.path.join(REF_DATA, "isolate_R1.fastq.gz")
 ISOLATE_R2 = os.path.join(REF_DATA, "isolate_R2.fastq.gz")
 ISOLATE_TSV = os.path.join(REF_DATA, "isolate.placement.tsv")
