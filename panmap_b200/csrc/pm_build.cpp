@@ -59,6 +59,111 @@ void diffSorted(const std::vector<uint64_t>& par, const std::vector<uint64_t>& c
     }
 }
 
+// ---- the device pipeline: genomes materialised, seeded, sorted and diffed on the GPU; only the deltas come back ----
+// Throws Unsupported when a genome holds more seeds than the shared-memory sort takes (the caller then runs the host pipeline).
+void buildOnDevice(const PanmanTree& T, const pm_seed_params& sp, int device, HostIndex& H) {
+    PanmanFlat F;
+    flattenPanman(T, F);
+    const u32 N = (u32)T.nodes.size(), B = (u32)T.blocks.size(), A = (u32)F.tmpl.size();
+    setDevice(device);
+    cudaStream_t st; CK(cudaStreamCreate(&st));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+    auto up = [&](auto& dev, const auto& host) { dev.alloc(host.size() + 1); if (!host.empty()) CK(cudaMemcpyAsync(dev.p, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, st)); };
+    DevBuf<u32> dParent, dSlotBlock, dBlockStart, dEditBegin, dEditSlot, dBlockMutBegin, dBlockMut;
+    DevBuf<char> dTmpl, dEditChar; DevBuf<unsigned char> dEditSerial;
+    up(dParent, F.parent); up(dSlotBlock, F.slotBlock); up(dBlockStart, F.blockStart); up(dEditBegin, F.editBegin); up(dEditSlot, F.editSlot);
+    up(dBlockMutBegin, F.blockMutBegin); up(dBlockMut, F.blockMut); up(dEditSerial, F.editSerial);
+    dTmpl.alloc(F.tmpl.size() + 1); if (A) CK(cudaMemcpyAsync(dTmpl.p, F.tmpl.data(), A, cudaMemcpyHostToDevice, st));
+    dEditChar.alloc(F.editChar.size() + 1); if (!F.editChar.empty()) CK(cudaMemcpyAsync(dEditChar.p, F.editChar.data(), F.editChar.size(), cudaMemcpyHostToDevice, st));
+    BuildTreeView V{N, B, A, F.maxDepth, dParent.p, dTmpl.p, dSlotBlock.p, dBlockStart.p, dEditBegin.p, dEditSlot.p, dEditChar.p, dEditSerial.p, dBlockMutBegin.p, dBlockMut.p};
+    std::vector<SeedTables> tabs(kSeedTableElems); buildSeedTableImage(tabs.data(), sp.k, sp.s);
+    DevBuf<SeedTables> dT; dT.alloc(kSeedTableElems); CK(cudaMemcpyAsync(dT.p, tabs.data(), kSeedTableElems * sizeof(SeedTables), cudaMemcpyHostToDevice, st));
+    const SeederParams P = makeSeederParams(sp.k, sp.s, sp.t, sp.l, sp.open, 0, 0);
+
+    const u64 pitch = std::max<u64>(32, ((u64)A + 31) & ~31ull);   // bytes per genome slot: a whole number of 32-base chunks
+    const u64 perNode = pitch * 20 + (u64)B + (u64)F.maxDepth * 4 + 64;
+    const u32 nbMax = (u32)std::max<u64>(1, std::min<u64>(8192, (6ull << 30) / perNode));
+    DevBuf<u32> dPath; DevBuf<unsigned char> dBlk; DevBuf<char> dAligned, dGenomes; DevBuf<u64> dEndOff, dOff, dPOff, dWOff, dHash, dCount, dSyn, dArenaOff;
+    DevBuf<unsigned> dSynCount; DevBuf<uint4> dPacked; DevBuf<u32> dBF;
+    dPath.alloc((size_t)nbMax * F.maxDepth); dBlk.alloc((size_t)nbMax * std::max<u32>(B, 1)); dAligned.alloc((size_t)nbMax * std::max<u32>(A, 1));
+    dGenomes.alloc((size_t)nbMax * pitch + 64); dEndOff.alloc(nbMax + 1); dOff.alloc(nbMax + 1); dPOff.alloc(nbMax + 1); dWOff.alloc(nbMax + 1);
+    dHash.alloc((size_t)nbMax * pitch + 1); dCount.alloc(nbMax + 1); dSyn.alloc((size_t)nbMax * pitch + 32); dSynCount.alloc(nbMax + 1);
+    dPacked.alloc((size_t)nbMax * (pitch / 32) + 1); dArenaOff.alloc(nbMax + 1);
+    const u64 chPer = pitch / 32;
+    std::vector<u64> hOff(nbMax + 1), hPOff(nbMax + 1);
+    for (u32 i = 0; i <= nbMax; ++i) { hOff[i] = (u64)i * pitch; hPOff[i] = (u64)i * chPer; }
+    CK(cudaMemcpyAsync(dOff.p, hOff.data(), (nbMax + 1) * 8, cudaMemcpyHostToDevice, st));       // also the window offsets: one slot per base
+    CK(cudaMemcpyAsync(dPOff.p, hPOff.data(), (nbMax + 1) * 8, cudaMemcpyHostToDevice, st));
+    std::vector<u32> bf((size_t)nbMax * chPer / 256 + 2);
+    // lists of every node stay on the device (the parent of a node may sit in any earlier batch)
+    std::vector<std::unique_ptr<DevBuf<u64>>> arenas;
+    std::vector<const u64*> hListPtr(N, nullptr); std::vector<u64> hListCount(N, 0);
+    DevBuf<const u64*> dListPtr; DevBuf<u64> dListCount; dListPtr.alloc(N + 1); dListCount.alloc(N + 1);
+    const unsigned diffGrid = 148 * 2;
+    DevBuf<uint4> dScratch; dScratch.alloc((size_t)diffGrid * 2 * kBuildSortCap);
+    DevBuf<unsigned long long> dCursor, dNodeOff; DevBuf<unsigned> dNodeCnt; dCursor.alloc(1); dNodeOff.alloc(nbMax + 1); dNodeCnt.alloc(nbMax + 1);
+    u64 outCap = 4u << 20;
+    DevBuf<u64> dOutHash; DevBuf<short> dOutPc, dOutCc; dOutHash.alloc(outCap); dOutPc.alloc(outCap); dOutCc.alloc(outCap);
+    std::vector<u64> hCount(nbMax), hArenaOff(nbMax + 1), oHash; std::vector<short> oPc, oCc; std::vector<unsigned long long> hNodeOff(nbMax); std::vector<unsigned> hNodeCnt(nbMax);
+
+    for (u32 v0 = 0; v0 < N; v0 += nbMax) {
+        const u32 nb = std::min(nbMax, N - v0);
+        const u64 ch = (u64)nb * chPer;
+        launchGenomeMaterialize(V, v0, nb, dPath.p, dBlk.p, dAligned.p, dGenomes.p, pitch, dEndOff.p, st);
+        packBlockFirst(hPOff.data(), nb, ch, bf.data());
+        dBF.ensure(ch / 256 + 2);
+        CK(cudaMemcpyAsync(dBF.p, bf.data(), ((ch + 255) / 256 + 1) * sizeof(u32), cudaMemcpyHostToDevice, st));
+        launchPackReads(dGenomes.p, dOff.p, dPOff.p, dBF.p, nb, 0, ch, dPacked.p, st, dEndOff.p);
+        launchSeedListsEnd(dPacked.p, dOff.p, dEndOff.p, dPOff.p, dOff.p, nb, P, dT.p, dSyn.p, dSynCount.p, dHash.p, dCount.p, st);
+        CK(cudaMemcpyAsync(hCount.data(), dCount.p, nb * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        u64 tot = 0;
+        for (u32 i = 0; i < nb; ++i) {
+            if (hCount[i] > kBuildSortCap) throw Unsupported("a genome holds more seeds than the device sort takes");
+            hArenaOff[i] = tot; tot += hCount[i];
+        }
+        hArenaOff[nb] = tot;
+        arenas.emplace_back(new DevBuf<u64>()); arenas.back()->alloc(tot + 1);
+        for (u32 i = 0; i < nb; ++i) { hListPtr[v0 + i] = arenas.back()->p + hArenaOff[i]; hListCount[v0 + i] = hCount[i]; }
+        CK(cudaMemcpyAsync(dArenaOff.p, hArenaOff.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dListPtr.p + v0, hListPtr.data() + v0, nb * sizeof(const u64*), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(dListCount.p + v0, hListCount.data() + v0, nb * 8, cudaMemcpyHostToDevice, st));
+        launchSeedsSort(dHash.p, dOff.p, dCount.p, dArenaOff.p, arenas.back()->p, nb, st);
+        unsigned long long cursor = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            CK(cudaMemsetAsync(dCursor.p, 0, sizeof(unsigned long long), st));
+            BuildDiffArgs D{v0, nb, dParent.p, dListPtr.p, dListCount.p, dScratch.p, dCursor.p, outCap, dOutHash.p, dOutPc.p, dOutCc.p, dNodeOff.p, dNodeCnt.p};
+            launchNodeDiff(D, diffGrid, st);
+            CK(cudaMemcpyAsync(&cursor, dCursor.p, sizeof(cursor), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            if (cursor <= outCap) break;
+            if (attempt) throw std::runtime_error("builder: delta buffer overflow after regrowth");
+            outCap = cursor + 1024; dOutHash.alloc(outCap); dOutPc.alloc(outCap); dOutCc.alloc(outCap);   // now the exact size is known
+        }
+        oHash.resize(cursor + 1); oPc.resize(cursor + 1); oCc.resize(cursor + 1);
+        if (cursor) {
+            CK(cudaMemcpyAsync(oHash.data(), dOutHash.p, cursor * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(oPc.data(), dOutPc.p, cursor * 2, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(oCc.data(), dOutCc.p, cursor * 2, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaMemcpyAsync(hNodeOff.data(), dNodeOff.p, nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hNodeCnt.data(), dNodeCnt.p, nb * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (u32 i = 0; i < nb; ++i) {   // the nodes reserved their output regions in any order: put them back in pre-order
+            const u32 v = v0 + i;
+            H.nodeOffsets[v] = H.hash.size();
+            const size_t o = (size_t)hNodeOff[i], c = hNodeCnt[i];
+            H.hash.insert(H.hash.end(), oHash.begin() + o, oHash.begin() + o + c);
+            H.parentCount.insert(H.parentCount.end(), oPc.begin() + o, oPc.begin() + o + c);
+            H.childCount.insert(H.childCount.end(), oCc.begin() + o, oCc.begin() + o + c);
+            H.identicalToParent[v] = c == 0 ? 1 : 0;
+        }
+    }
+    H.nodeOffsets[N] = H.hash.size();
+}
+
 }  // namespace
 
 extern "C" {
@@ -123,8 +228,19 @@ int pm_index_build(const char* panman_path, const pm_seed_params* sp, int flank_
         std::unique_ptr<pm_host_index> hi(new pm_host_index());
         HostIndex& H = hi->h;
         H.sp = *sp;
-        H.nodeOffsets.assign(N + 1, 0); H.parentIndex.assign(N, 0); H.nodeIds.resize(N); H.identicalToParent.assign(N, 0);
-        for (size_t i = 0; i < N; ++i) { H.parentIndex[i] = T.nodes[i].parent == kNoNode ? 0u : T.nodes[i].parent; H.nodeIds[i] = T.nodes[i].id; }
+        auto reset = [&]() {
+            H.hash.clear(); H.parentCount.clear(); H.childCount.clear();
+            H.nodeOffsets.assign(N + 1, 0); H.parentIndex.assign(N, 0); H.nodeIds.resize(N); H.identicalToParent.assign(N, 0);
+            for (size_t i = 0; i < N; ++i) { H.parentIndex[i] = T.nodes[i].parent == kNoNode ? 0u : T.nodes[i].parent; H.nodeIds[i] = T.nodes[i].id; }
+        };
+        reset();
+        // the device pipeline (genomes never leave the GPU) unless the index is homopolymer-compressed, a genome is too large for the
+        // shared-memory sort, or PM_BUILD_HOST_WALK=1 asks for the host walk (the two are compared in tests/test_index_build.py)
+        const char* hw = std::getenv("PM_BUILD_HOST_WALK");
+        if (!sp->hpc && !(hw && std::atoi(hw) != 0)) {
+            try { buildOnDevice(T, *sp, device, H); *out = hi.release(); return PM_OK; }
+            catch (const Unsupported&) { reset(); }
+        }
 
         // pre-order stack of (node, its sorted seed list): the parent of the next node is always on it
         std::vector<std::pair<uint32_t, std::vector<uint64_t>>> path;

@@ -57,6 +57,13 @@ struct PanmanTree {
 void readPanman(const std::string& path, PanmanTree& out);
 // one depth-first walk over the tree: visit(node, ungapped genome of the node) for every node, in pre-order
 void walkPanmanGenomes(const PanmanTree& T, const std::function<void(uint32_t, const std::string&)>& visit);
+struct PanmanFlat {   // the tree as the device pipeline of the builder takes it (pm_kernels.cuh BuildTreeView)
+    std::vector<uint32_t> parent, slotBlock, blockStart, editBegin, editSlot, blockMutBegin, blockMut;
+    std::string tmpl, editChar;
+    std::vector<uint8_t> editSerial;
+    uint32_t maxDepth = 1;
+};
+void flattenPanman(const PanmanTree& T, PanmanFlat& out);
 void walkPanmanGenomesCoords(const PanmanTree& T, bool wantCoords, const std::function<void(uint32_t, const std::string&, const std::vector<uint32_t>&)>& visit);
 
 // everything pm_index_create derives from a pm_index_desc before uploading (see DESIGN.md "HBM layout")

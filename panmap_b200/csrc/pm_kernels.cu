@@ -1439,6 +1439,15 @@ void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, c
     }
 }
 
+// index builder (pm_build_kernels.cu): per-sequence seed lists of sequences that sit at a fixed pitch (off[r] = r * pitch) and end at
+// endOff[r]; sequence r's seeds land at outHash[winOff[r] ...], outCount[r] of them
+void launchSeedListsEnd(const uint4* packed, const u64* off, const u64* endOff, const u64* packedOff, const u64* winOff, u64 nSeqs, const SeederParams& P,
+                        const SeedTables* dTables, u64* synBuf, unsigned* synCount, u64* outHash, u64* outCount, cudaStream_t st) {
+    if (nSeqs == 0) return;
+    launchSyncmers(packed, off, packedOff, nSeqs, P, dTables, synBuf, synCount, nullptr, endOff, st);
+    launchSeedsFromSyncmers<2>(synBuf, synCount, packedOff, winOff, nSeqs, P.k, P.l, nullptr, 0, nullptr, outHash, outCount, 0, st);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // table maintenance
 // ------------------------------------------------------------------------------------------------------

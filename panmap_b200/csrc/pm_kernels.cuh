@@ -177,6 +177,38 @@ void launchDedup(const char* reads, const u64* off, u64 rBegin, u64 rEnd, unsign
 void launchSeedList(const uint4* packed, const u64* off, const u64* packedOff, const u64* winOff, u64 nReads,
                     const SeederParams& P, const SeedTables* dTables, int mode, u64* synBuf, unsigned* synCount, u64* outHash,
                     unsigned char* outRev, long long* outPos, u64* outCount, cudaStream_t st);
+void launchSeedListsEnd(const uint4* packed, const u64* off, const u64* endOff, const u64* packedOff, const u64* winOff, u64 nSeqs, const SeederParams& P,
+                        const SeedTables* dTables, u64* synBuf, unsigned* synCount, u64* outHash, u64* outCount, cudaStream_t st);
+// ---- index builder (pm_build_kernels.cu) ----
+constexpr u32 kBuildNoNode = 0xFFFFFFFFu;
+constexpr unsigned kBuildSortCap = 16384;   // seeds per genome the shared-memory sort holds (larger genomes take the host pipeline)
+struct BuildTreeView {   // the PanMAN flattened for the device: aligned template, point edits and block mutations per node
+    u32 nNodes, nBlocks, nSlots, maxDepth;
+    const u32* parent;            // [nNodes], kBuildNoNode for the root
+    const char* tmpl;             // [nSlots] the root template in aligned order (gap slots before their main position, '-' where empty)
+    const u32* slotBlock;         // [nSlots]
+    const u32* blockStart;        // [nBlocks + 1]
+    const u32* editBegin;         // [nNodes + 1] into editSlot / editChar
+    const u32* editSlot; const char* editChar;
+    const unsigned char* editSerial;   // [nNodes] 1: a slot is written twice by this node, apply in order
+    const u32* blockMutBegin;     // [nNodes + 1] into blockMut
+    const u32* blockMut;          // block << 2 | inversion << 1 | insertion
+};
+struct BuildDiffArgs {
+    u32 nodeBegin, nNodes;
+    const u32* parent;
+    const u64* const* listPtr;    // [all nodes] sorted seed list of the node (device pointers)
+    const u64* listCount;         // [all nodes]
+    void* scratch;                // gridDim.x * 2 * kBuildSortCap entries of 16 bytes
+    unsigned long long* cursor;   // deltas reserved so far
+    unsigned long long outCap;
+    u64* outHash; short* outPc; short* outCc;
+    unsigned long long* nodeOff; unsigned* nodeCnt;   // [nNodes] where the node's deltas went
+};
+void launchGenomeMaterialize(const BuildTreeView& T, u32 nodeBegin, u32 nNodes, u32* pathScratch, unsigned char* blkScratch, char* aligned, char* genomes,
+                             u64 pitch, u64* endOff, cudaStream_t st);
+void launchSeedsSort(const u64* in, const u64* winOff, const u64* count, const u64* arenaOff, u64* arena, u32 nLists, cudaStream_t st);
+void launchNodeDiff(const BuildDiffArgs& A, unsigned grid, cudaStream_t st);
 void launchTableClear(WorkspaceView W, cudaStream_t st);
 void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st);
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st);

@@ -333,4 +333,73 @@ void walkPanmanGenomesCoords(const PanmanTree& T, bool wantCoords, const std::fu
     }
 }
 
+// The tree flattened for the device pipeline of the builder (pm_build_kernels.cu genome_materialize): aligned template, one point edit per
+// mutated slot (the skip rules of panmap_utils.cpp:113-129 applied here), block mutations, parents, depth.
+void flattenPanman(const PanmanTree& T, PanmanFlat& F) {
+    F = PanmanFlat{};
+    const size_t B = T.blocks.size(), N = T.nodes.size();
+    std::vector<std::vector<uint32_t>> gapLen(B), go(B);
+    for (size_t b = 0; b < B; ++b) gapLen[b].assign(T.blocks[b].size() + 1, 0);
+    for (const PanmanGapList& g : T.gaps) {
+        if (g.block < 0 || (size_t)g.block >= B) throw std::runtime_error("panman: gap list names an unknown block");
+        for (size_t j = 0; j < g.position.size(); ++j) {
+            if (g.position[j] < 0 || (size_t)g.position[j] >= gapLen[g.block].size() || g.length[j] < 0) throw std::runtime_error("panman: gap list position out of range");
+            gapLen[g.block][g.position[j]] = (uint32_t)g.length[j];
+        }
+    }
+    F.blockStart.assign(B + 1, 0);
+    uint64_t slots = 0;
+    for (size_t b = 0; b < B; ++b) {
+        const size_t nMain = T.blocks[b].size();
+        go[b].assign(nMain + 2, 0);
+        for (size_t p = 0; p <= nMain; ++p) go[b][p + 1] = go[b][p] + gapLen[b][p];
+        F.blockStart[b] = (uint32_t)slots;
+        slots += nMain + go[b][nMain + 1];
+        if (slots > 0x7FFFFFFFull) throw Unsupported("panman: more than 2^31 aligned positions");
+    }
+    F.blockStart[B] = (uint32_t)slots;
+    F.tmpl.assign((size_t)slots, '-'); F.slotBlock.assign((size_t)slots, 0);
+    for (size_t b = 0; b < B; ++b) {
+        for (uint32_t q = F.blockStart[b]; q < F.blockStart[b + 1]; ++q) F.slotBlock[q] = (uint32_t)b;
+        for (size_t p = 0; p < T.blocks[b].size(); ++p) F.tmpl[F.blockStart[b] + p + go[b][p + 1]] = T.blocks[b][p];
+    }
+    F.parent.resize(N); F.editBegin.assign(N + 1, 0); F.blockMutBegin.assign(N + 1, 0); F.editSerial.assign(N, 0);
+    std::vector<uint32_t> depth(N, 1), seen;
+    F.maxDepth = 1;
+    for (size_t v = 0; v < N; ++v) {
+        const PanmanNode& nd = T.nodes[v];
+        F.parent[v] = nd.parent;
+        if (nd.parent != kNoNode) { depth[v] = depth[nd.parent] + 1; F.maxDepth = std::max(F.maxDepth, depth[v]); }
+        for (uint32_t i = nd.blockBegin; i < nd.blockEnd; ++i) {
+            const PanmanBlockMut& bm = T.blockMuts[i];
+            if (bm.block < 0 || (size_t)bm.block >= B) throw std::runtime_error("panman: block mutation names an unknown block");
+            F.blockMut.push_back(((uint32_t)bm.block << 2) | (bm.inversion ? 2u : 0u) | (bm.insertion ? 1u : 0u));
+        }
+        F.blockMutBegin[v + 1] = (uint32_t)F.blockMut.size();
+        const size_t e0 = F.editSlot.size();
+        for (uint32_t i = nd.nucBegin; i < nd.nucEnd; ++i) {
+            const PanmanNucMut& nm = T.nucMuts[i];
+            if (nm.block < 0 || (size_t)nm.block >= B) throw std::runtime_error("panman: nucleotide mutation names an unknown block");
+            const size_t nMain = T.blocks[nm.block].size();
+            for (int q = 0; q < (int)nm.len; ++q) {
+                const int32_t pos = nm.gap == -1 ? nm.pos + q : nm.pos, gp = nm.gap == -1 ? -1 : nm.gap + q;
+                if (pos < 0 || (size_t)pos > nMain) continue;            // beyond the sentinel
+                if ((size_t)pos == nMain && gp == -1) continue;          // the sentinel itself
+                uint32_t slot;
+                if (gp == -1) slot = F.blockStart[nm.block] + (uint32_t)pos + go[nm.block][pos + 1];
+                else {
+                    if (gp < 0 || (uint32_t)gp >= gapLen[nm.block][pos]) continue;
+                    slot = F.blockStart[nm.block] + (uint32_t)pos + go[nm.block][pos] + (uint32_t)gp;
+                }
+                F.editSlot.push_back(slot); F.editChar.push_back(nucOfCode((int)((nm.nucs >> (4 * (5 - q))) & 15u)));
+            }
+        }
+        F.editBegin[v + 1] = (uint32_t)F.editSlot.size();
+        seen.assign(F.editSlot.begin() + (long)e0, F.editSlot.end());
+        std::sort(seen.begin(), seen.end());
+        F.editSerial[v] = std::adjacent_find(seen.begin(), seen.end()) != seen.end() ? 1 : 0;
+    }
+    if (F.editSlot.size() > 0xFFFFFFF0ull) throw Unsupported("panman: more than 2^32 point edits");
+}
+
 }  // namespace pm

@@ -138,6 +138,21 @@ def test_index_build_matches_reference_flank0(case):
 
 @pytest.mark.gpu
 @needs_data
+@pytest.mark.parametrize("case", ["mammoth", "rsv"])
+def test_host_walk_pipeline_gives_the_same_index(case, monkeypatch):
+    """the two pipelines of pm_index_build -- genomes materialised, sorted and diffed on the device (default) and the host walk with host
+    sort / diff (hpc indexes, genomes too large for the device sort) -- produce identical arrays"""
+    pan, _, sp = CASES[case]
+    dev = pm.HostIndex.build_from_panman(pan, **sp)
+    monkeypatch.setenv("PM_BUILD_HOST_WALK", "1")
+    host = pm.HostIndex.build_from_panman(pan, **sp)
+    for f in ("hash", "parent", "child", "offsets", "parent_index", "identical_to_parent"):
+        assert np.array_equal(getattr(dev, f), getattr(host, f)), f
+    assert dev.node_ids == host.node_ids
+
+
+@pytest.mark.gpu
+@needs_data
 def test_index_build_refuses_flank_mask_and_bad_input(tmp_path):
     with pytest.raises(pm.PanmapError) as e:
         pm.HostIndex.build_from_panman(H.MAMMOTH_PANMAN, k=15, s=8, t=0, l=1, flank_mask=250)
@@ -153,7 +168,7 @@ def test_built_index_places_like_the_reference_built_one(tmp_path):
     when oracle/_ref is there, the REFERENCE's reader + placeLite read the written file and agree"""
     B = pm.HostIndex.build_from_panman(H.RSV_PANMAN, k=19, s=8, t=0, l=3)
     p = str(tmp_path / "built.idx")
-    B.write(p, zstd_level=3)
+    B.write(p)            # uncompressed: the oracle build of the reference's reader has no zstd
     fq = os.path.join(H.REF_DATA, "MZ515733.1.fastq")
     back = pm.HostIndex.read(p)
     ws = pm.Workspace(pm.Index(back))
