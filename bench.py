@@ -517,6 +517,26 @@ def main():
                 del i1, i2
             except Exception as e:  # reported, never fatal
                 line["index_open"] = {"error": str(e)}
+        if w.get("real") and not args.no_file_span:
+            # building the index (not part of a placement): .panman -> seed deltas, genomes materialised / seeded / sorted / diffed on the
+            # GPU, against the reference's own IndexBuilder (oracle/_ref) on the box's host cores; both with --flank-mask 0 (the mode the product builds)
+            try:
+                from tests import helpers as TH
+                if os.path.exists(TH.SARS_PANMAN):
+                    pm.HostIndex.build_from_panman(TH.MAMMOTH_PANMAN, k=15, s=8, t=0, l=1)
+                    t0 = time.perf_counter(); bi = pm.HostIndex.build_from_panman(TH.SARS_PANMAN, k=int(S.k), s=int(S.s), t=int(S.t), l=int(S.l)); tb = time.perf_counter() - t0
+                    ib = {"panman": os.path.basename(TH.SARS_PANMAN), "flank_mask": 0, "n_nodes": bi.n_nodes, "n_deltas": bi.n_deltas, "gpu_ms": 1e3 * tb}
+                    from oracle import ref as _ref
+                    if _ref.available():
+                        for th in (1, os.cpu_count() or 1):
+                            t0 = time.perf_counter(); _ref.build_index(TH.SARS_PANMAN, os.path.join(td, "ref_f0.idx"), flank_mask=0, threads=th)
+                            ib[f"reference_{th}_threads_ms"] = 1e3 * (time.perf_counter() - t0)
+                        rb = pm.HostIndex.read(os.path.join(td, "ref_f0.idx"))
+                        ib["nodes_identical_to_reference"] = int(sum(
+                            np.array_equal(bi.hash[int(bi.offsets[v]):int(bi.offsets[v + 1])], rb.hash[int(rb.offsets[v]):int(rb.offsets[v + 1])]) for v in range(bi.n_nodes)))
+                    line["index_build"] = ib
+            except Exception as e:  # reported, never fatal
+                line["index_build"] = {"error": str(e)}
         if not args.no_cpu_baseline:
             try:
                 from oracle import ref

@@ -80,6 +80,12 @@ void buildOnDevice(const PanmanTree& T, const pm_seed_params& sp, int device, Ho
     DevBuf<SeedTables> dT; dT.alloc(kSeedTableElems); CK(cudaMemcpyAsync(dT.p, tabs.data(), kSeedTableElems * sizeof(SeedTables), cudaMemcpyHostToDevice, st));
     const SeederParams P = makeSeederParams(sp.k, sp.s, sp.t, sp.l, sp.open, 0, 0);
 
+    {   // every node's sorted seed list stays on the device: refuse up front what cannot fit (the host pipeline keeps only the root path)
+        size_t freeB = 0, totalB = 0;
+        CK(cudaMemGetInfo(&freeB, &totalB));
+        const double estimate = (double)N * (double)A * 0.5 * 8.0 + 8e9;   // <= one seed per two aligned slots, + the batch scratch
+        if (estimate > 0.8 * (double)freeB) throw Unsupported("the tree's seed lists would not fit the device");
+    }
     const u64 pitch = std::max<u64>(32, ((u64)A + 31) & ~31ull);   // bytes per genome slot: a whole number of 32-base chunks
     const u64 perNode = pitch * 20 + (u64)B + (u64)F.maxDepth * 4 + 64;
     const u32 nbMax = (u32)std::max<u64>(1, std::min<u64>(8192, (6ull << 30) / perNode));
