@@ -453,8 +453,11 @@ void stageScore(pm_workspace* W, const pm_place_params& prm) {
     pm_index* I = W->idx;
     const PlaceOpts O = makeOpts(prm, W->wantMetrics);
     if (prm.seed_mask_fraction > 0.0) W->maskScratch.ensure(2);
+    static const bool kSideScalars = [] { const char* e = std::getenv("PM_SIDE_SCALARS"); return e ? std::atoi(e) != 0 : true; }();
+    const bool side = kSideScalars && prm.seed_mask_fraction <= 0.0;
     launchFinalize(I->view, W->view, O, I->homo.p, W->lastEntries ? W->lastEntries : W->tableCap / 4, I->nSM, W->st, prm.seed_mask_fraction,
-                   W->maskScratch.p);
+                   W->maskScratch.p, side ? W->stCopy : nullptr, W->evFork, W->evJoin);
+    W->joinPending = side;
     stageDeltasScoresRecords(W, prm);
 }
 void stageDeltasScoresRecords(pm_workspace* W, const pm_place_params& prm) {
@@ -463,6 +466,7 @@ void stageDeltasScoresRecords(pm_workspace* W, const pm_place_params& prm) {
     CK(cudaEventRecord(W->ev[3], W->st));
     launchDeltas(I->view, W->view, I->nSM, W->st);
     launchGeneral(I->view, W->view, W->st);
+    if (W->joinPending) { CK(cudaStreamWaitEvent(W->st, W->evJoin, 0)); W->joinPending = false; }   // the scalars (side stream) before the scores
     CK(cudaEventRecord(W->ev[4], W->st));
     launchPrefixScores(I->view, W->view, O, W->st);
     CK(cudaEventRecord(W->ev[5], W->st));
@@ -760,6 +764,7 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         for (auto& e : W->ev) CK(cudaEventCreate(&e));
         for (auto& e : W->evCopy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));   // one per slice of the host-buffer pipeline
         for (auto& e : W->evK) CK(cudaEventCreate(&e));
+        CK(cudaEventCreateWithFlags(&W->evFork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&W->evJoin, cudaEventDisableTiming));
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
         W->resultBlob.alloc(kResultBlobBytes);
@@ -807,6 +812,8 @@ void pm_workspace_destroy(pm_workspace* ws) {
     for (auto& e : ws->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ws->evCopy) if (e) cudaEventDestroy(e);
     for (auto& e : ws->evK) if (e) cudaEventDestroy(e);
+    if (ws->evFork) cudaEventDestroy(ws->evFork);
+    if (ws->evJoin) cudaEventDestroy(ws->evJoin);
     delete ws;
 }
 

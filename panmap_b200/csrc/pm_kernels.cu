@@ -1808,14 +1808,21 @@ void launchRootAndScalars(DevIndexView I, WorkspaceView W, PlaceOpts O, unsigned
     noteLaunch(), root_and_scalars<<<(unsigned)gr, 256, 0, st>>>(I, W, O.minReadSupport, nFinParts);
 }
 void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st,
-                    double seedMaskFraction, unsigned long long* maskScratch) {
+                    double seedMaskFraction, unsigned long long* maskScratch, cudaStream_t stSide, cudaEvent_t evFork, cudaEvent_t evJoin) {
     unsigned g1 = 0;
     launchTableScan(W, homo, nSM, &g1, st);
     if (seedMaskFraction > 0.0) { maskTopSeeds(W, seedMaskFraction, g1, maskScratch, st); ++g1; }   // + one partial of corrections
     // sized from the previous sample's entry count (the kernel grid-strides, so any grid is correct)
     u64 g2 = (expectedEntries + 255) / 256; if (g2 < 1) g2 = 1; if (g2 > (u64)nSM * 4) g2 = (u64)nSM * 4; if (g2 > kMaxPartials) g2 = kMaxPartials;
     noteLaunch(), entries_finalize<<<(unsigned)g2, 256, 0, st>>>(I, W, O.minReadSupport, g1);
-    launchRootAndScalars(I, W, O, (unsigned)g2, st);
+    if (stSide && evFork && evJoin) {
+        // the sample's scalars are needed by prefix_scores, not by node_deltas: the root / scalars kernel (a latency chain that ends in one block)
+        // runs beside node_deltas on a side stream; the caller makes `st` wait for evJoin before prefix_scores
+        cudaEventRecord(evFork, st);
+        cudaStreamWaitEvent(stSide, evFork, 0);
+        launchRootAndScalars(I, W, O, (unsigned)g2, stSide);
+        cudaEventRecord(evJoin, stSide);
+    } else launchRootAndScalars(I, W, O, (unsigned)g2, st);
 }
 
 // after a sample: clear exactly the ell entries it set (their ids sit next to the compacted entries) and the segment records

@@ -214,7 +214,8 @@ void launchTableImport(WorkspaceView W, const u64* hash, const long long* count,
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st);
 // seedMaskFraction > 0 (off by default): synchronises the stream a few dozen times to find the cut; maskScratch = two device words
 void launchFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, u64 expectedEntries, int nSM, cudaStream_t st,
-                    double seedMaskFraction = 0.0, unsigned long long* maskScratch = nullptr);
+                    double seedMaskFraction = 0.0, unsigned long long* maskScratch = nullptr, cudaStream_t stSide = nullptr, cudaEvent_t evFork = nullptr,
+                    cudaEvent_t evJoin = nullptr);
 void launchDeltas(DevIndexView I, WorkspaceView W, int nSM, cudaStream_t st);
 void launchGeneral(DevIndexView I, WorkspaceView W, cudaStream_t st);
 void launchPrefixScores(DevIndexView I, WorkspaceView W, PlaceOpts O, cudaStream_t st);
@@ -232,7 +233,8 @@ void launchPartitionImport(WorkspaceView W, const uint4* xRecv, u32 nRanks, u32 
 void launchPartitionFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const u64* homo, int nSM, uint2* gSend, u32 capG, u64 nLocalReads,
                              const u32* maxPairCount, u32 localEntriesHint, cudaStream_t st);
 // all ranks' gathered lists -> ell, exact magnitude sums, histogram, scalars (replaces entries_finalize + finish_scalars of the one-GPU path)
-void launchGatheredFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const uint2* gRecv, u32 nRanks, u32 capG, int nSM, cudaStream_t st);
+void launchGatheredFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const uint2* gRecv, u32 nRanks, u32 capG, int nSM, cudaStream_t st,
+                            cudaStream_t stSide = nullptr, cudaEvent_t evFork = nullptr, cudaEvent_t evJoin = nullptr);
 void launchRecordsPack(WorkspaceView W, uint4* rSend, u32 recX, cudaStream_t st);
 void launchChainGathered(WorkspaceView W, const uint4* rRecv, u32 nRanks, u32 recX, cudaStream_t st);
 void launchTiesPack(WorkspaceView W, u32* tSend, const uint2* gSend, const u32* exportInfo /* [2] from launchPartitionExport */, cudaStream_t st);

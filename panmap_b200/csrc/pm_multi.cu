@@ -323,7 +323,9 @@ void phase1(pm_comm* c, const pm_place_params& prm) {
 void phase2(pm_comm* c, const pm_place_params& prm) {
     pm_workspace* W = c->ws; pm_index* I = W->idx;
     setDevice(I->device);
-    launchGatheredFinalize(I->view, W->view, makeOpts(prm, false), c->gRecv.p, (u32)c->n, c->capG, I->nSM, W->st);
+    static const bool kSideScalars = [] { const char* e = std::getenv("PM_SIDE_SCALARS"); return e ? std::atoi(e) != 0 : true; }();
+    launchGatheredFinalize(I->view, W->view, makeOpts(prm, false), c->gRecv.p, (u32)c->n, c->capG, I->nSM, W->st, kSideScalars ? W->stCopy : nullptr, W->evFork, W->evJoin);
+    W->joinPending = kSideScalars;
     stageDeltasScoresRecords(W, prm);
     launchRecordsPack(W->view, c->rSend.p, c->recX, W->st);
 }

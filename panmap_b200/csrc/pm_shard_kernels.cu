@@ -253,10 +253,16 @@ __global__ void __launch_bounds__(256) gathered_finalize(DevIndexView I, Workspa
     }
     finalizeBlockEpilogue(W, A, sHist, &sFin);
 }
-void launchGatheredFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const uint2* gRecv, u32 nRanks, u32 capG, int nSM, cudaStream_t st) {
+void launchGatheredFinalize(DevIndexView I, WorkspaceView W, PlaceOpts O, const uint2* gRecv, u32 nRanks, u32 capG, int nSM, cudaStream_t st,
+                            cudaStream_t stSide, cudaEvent_t evFork, cudaEvent_t evJoin) {
     u64 g = ((u64)nRanks * capG + 255) / 256; if (g < 1) g = 1; if (g > (u64)nSM * 4) g = (u64)nSM * 4; if (g > kMaxPartials) g = kMaxPartials;
     noteLaunch(), gathered_finalize<<<(unsigned)g, 256, 0, st>>>(I, W, O.minReadSupport, gRecv, nRanks, capG);
-    launchRootAndScalars(I, W, O, (unsigned)g, st);
+    if (stSide && evFork && evJoin) {   // as in launchFinalize: the scalars beside node_deltas, joined before prefix_scores
+        cudaEventRecord(evFork, st);
+        cudaStreamWaitEvent(stSide, evFork, 0);
+        launchRootAndScalars(I, W, O, (unsigned)g, stSide);
+        cudaEventRecord(evJoin, stSide);
+    } else launchRootAndScalars(I, W, O, (unsigned)g, st);
 }
 // after the sample: clear exactly the ell entries it set, and the segment records that are combined with atomics
 __global__ void __launch_bounds__(256) reset_gathered(DevIndexView I, WorkspaceView W, const uint2* __restrict__ gRecv, u32 nRanks, u32 capG) {
