@@ -6,15 +6,18 @@
 // that incremental machine computes is pinned by the reference's own test (src/test/test_index.cpp:200-230): replaying a node's deltas
 // from the root gives exactly the seed multiset of seeding the node's ungapped genome directly.
 //
-// Here the definition IS the algorithm, and the seeding is the data-parallel part, so it runs on the GPU with the kernels of the read path:
-//   1. pm_panman.cpp: one depth-first walk hands out every node's ungapped genome (host, sequential, ~1 us per kb);
-//   2. batches of genomes -> seed lists on the device (one lane per genome in the syncmer kernels, one warp per genome for the k-min-mers:
-//      the same launchSeedList the read path's list utilities use, sequences of tens of kilobases instead of 150 bases);
-//   3. per node: sort the seed list (host threads, one node each), merge against the parent's sorted list -> the node's deltas, sorted by
-//      hash.  Nodes are met in pre-order, so a stack of the sorted lists on the current root path is all that is kept.
-// The result is delta-for-delta the LiteIndex the reference builds with --flank-mask 0 (tests/test_index_build.py: every node of rsv_4K,
-// extended_mammoth and sars_20000).  With the reference's default --flank-mask 250 its index is NOT a function of the node genomes: masked
-// positions are neither added nor deleted while the mask bounds move from node to node (index_single_mode.cpp:1770-1780, 1850-1925), so a
+// Here the definition IS the algorithm, because it is the data-parallel formulation.  Two pipelines, identical output (a test holds them to it):
+//   device (default; pm_build_kernels.cu): the tree flattened to an aligned root template + one point edit per mutated slot
+//     (pm_panman.cpp flattenPanman), then per batch of ~4,000 nodes genome_materialize -> pack_reads + the read path's syncmer / k-min-mer
+//     kernels on the genomes where they lie -> seeds_sort into a device arena -> node_diff; only the deltas come back.
+//   host walk (genomes too large for the shared-memory sort, lists that would not fit the device, PM_BUILD_HOST_WALK=1): one depth-first
+//     walk hands out every node's ungapped genome (pm_panman.cpp walkPanmanGenomes), batches of genomes are seeded on the device through
+//     the list path of pm_read_seeds, every list is sorted by a host thread and merged against the parent's; nodes are met in pre-order,
+//     so a stack of the sorted lists on the current root path is all that is kept.
+// The result is the LiteIndex the reference builds with --flank-mask 0 (tests/test_index_build.py compares every node: rsv_4K identical,
+// sars_20000 39,998 of 39,999 nodes, extended_mammoth 145 of 155).  With the reference's default --flank-mask 250 its index is NOT a
+// function of the node genomes: masked positions are neither added nor deleted while the mask bounds move from node to node
+// (index_single_mode.cpp:1770-1780, 1850-1925), so a
 // node keeps seeds that an ancestor happened to have (measured on rsv_4K: leaves with 8,137 indexed seeds where the genome has 4,504).
 // A genome-defined builder cannot and should not reproduce that history; flank_mask > 0 is refused here with that explanation, and the
 // reference-built default index stays readable through pm_host_index_read.
@@ -30,14 +33,6 @@ extern "C" int seedListImpl(int device, const char* seqs, const uint64_t* off, u
                             int mode, uint64_t* outHash, uint8_t* outRev, int64_t* outPos, uint64_t* outCount);
 
 namespace {
-
-// seeding::hpcCompress (seeding.cpp:286-306): runs of the same letter (case-insensitive) collapse to their first character
-void hpcCollapse(std::string& s) {
-    size_t o = 0;
-    for (size_t i = 0; i < s.size(); ++i)
-        if (i == 0 || std::toupper((unsigned char)s[i]) != std::toupper((unsigned char)s[i - 1])) s[o++] = s[i];
-    s.resize(o);
-}
 
 struct Batch {
     std::vector<uint32_t> node;
@@ -228,6 +223,8 @@ int pm_index_build(const char* panman_path, const pm_seed_params* sp, int flank_
                               "added nor deleted while the mask moves with every node's gap map), which a genome-defined builder does not reproduce; build with "
                               "flank_mask = 0 (== panmap --flank-mask 0, delta for delta) or read a reference-built .idx");
         if (sp->l < 0 || sp->l > 64) throw std::runtime_error("unsupported l");
+        if (sp->hpc)   // measured: "collapse the genome, then seed it" matches 40 of the first 300 rsv_4K nodes of the reference's hpc build
+            throw Unsupported("hpc indexes: the reference's homopolymer-compressed build is not the seeding of the compressed node genomes; read a reference-built .idx");
         PanmanTree T;
         readPanman(panman_path, T);
         const size_t N = T.nodes.size();
@@ -240,10 +237,14 @@ int pm_index_build(const char* panman_path, const pm_seed_params* sp, int flank_
             for (size_t i = 0; i < N; ++i) { H.parentIndex[i] = T.nodes[i].parent == kNoNode ? 0u : T.nodes[i].parent; H.nodeIds[i] = T.nodes[i].id; }
         };
         reset();
-        // the device pipeline (genomes never leave the GPU) unless the index is homopolymer-compressed, a genome is too large for the
-        // shared-memory sort, or PM_BUILD_HOST_WALK=1 asks for the host walk (the two are compared in tests/test_index_build.py)
+        {   // LiteTree.blockRanges (index_single_mode.cpp:1254-1259): first and last aligned coordinate of every block
+            PanmanFlat F; flattenPanman(T, F);
+            for (size_t b = 0; b + 1 < F.blockStart.size(); ++b) { H.blockRanges.push_back(F.blockStart[b]); H.blockRanges.push_back(F.blockStart[b + 1] - 1); }
+        }
+        // the device pipeline (genomes never leave the GPU) unless a genome is too large for the shared-memory sort, the lists would not fit
+        // the device, or PM_BUILD_HOST_WALK=1 asks for the host walk (the two are compared in tests/test_index_build.py)
         const char* hw = std::getenv("PM_BUILD_HOST_WALK");
-        if (!sp->hpc && !(hw && std::atoi(hw) != 0)) {
+        if (!(hw && std::atoi(hw) != 0)) {
             try { buildOnDevice(T, *sp, device, H); *out = hi.release(); return PM_OK; }
             catch (const Unsupported&) { reset(); }
         }
@@ -295,7 +296,7 @@ int pm_index_build(const char* panman_path, const pm_seed_params* sp, int flank_
         walkPanmanGenomes(T, [&](uint32_t v, const std::string& g) {
             if (!batch.node.empty() && batch.bases.size() + g.size() > kBatchBases) flush(batch);
             batch.node.push_back(v);
-            if (sp->hpc) { std::string c = g; hpcCollapse(c); batch.bases += c; } else batch.bases += g;
+            batch.bases += g;
             batch.off.push_back(batch.bases.size());
         });
         flush(batch);

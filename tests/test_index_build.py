@@ -134,6 +134,7 @@ def test_index_build_matches_reference_flank0(case):
                         B.child[int(B.offsets[v]):int(B.offsets[v + 1])]) for v in range(B.n_nodes)}
         _check_known_differences(case, _compare_nodes(R, per_node))
     assert np.array_equal(B.identical_to_parent, (np.diff(B.offsets.astype(np.int64)) == 0).astype(np.uint8))
+    assert np.array_equal(B.block_ranges, R.block_ranges)      # LiteTree.blockRanges: 1,826 blocks in rsv_4K, one in the other two
 
 
 @pytest.mark.gpu
@@ -141,7 +142,7 @@ def test_index_build_matches_reference_flank0(case):
 @pytest.mark.parametrize("case", ["mammoth", "rsv"])
 def test_host_walk_pipeline_gives_the_same_index(case, monkeypatch):
     """the two pipelines of pm_index_build -- genomes materialised, sorted and diffed on the device (default) and the host walk with host
-    sort / diff (hpc indexes, genomes too large for the device sort) -- produce identical arrays"""
+    sort / diff (genomes too large for the device sort, trees whose lists do not fit the device) -- produce identical arrays"""
     pan, _, sp = CASES[case]
     dev = pm.HostIndex.build_from_panman(pan, **sp)
     monkeypatch.setenv("PM_BUILD_HOST_WALK", "1")
@@ -157,6 +158,9 @@ def test_index_build_refuses_flank_mask_and_bad_input(tmp_path):
     with pytest.raises(pm.PanmapError) as e:
         pm.HostIndex.build_from_panman(H.MAMMOTH_PANMAN, k=15, s=8, t=0, l=1, flank_mask=250)
     assert e.value.code == -5 and "history" in str(e.value)
+    with pytest.raises(pm.PanmapError) as e:     # the reference's hpc build is not "collapse the genome, then seed it": refused, not approximated
+        pm.HostIndex.build_from_panman(H.MAMMOTH_PANMAN, k=15, s=8, t=0, l=1, hpc=1)
+    assert e.value.code == -5
     with pytest.raises(pm.PanmapError):
         pm.HostIndex.build_from_panman(str(tmp_path / "missing.panman"))
 
