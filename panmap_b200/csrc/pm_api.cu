@@ -407,11 +407,20 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
     pm_index* I = W->idx;
     SeederParams P = makeSeederParams(I->F.sp.k, I->F.sp.s, I->F.sp.t, I->F.sp.l, I->F.sp.open, prm.trim_start, prm.trim_end);
     P.maxLen = (int)std::min<u64>(W->maxReadLen, 0x7FFFFFFF);
+    const bool quality = W->useQuals && prm.min_seed_quality > 0;   // the reference's quality path never deduplicates (placement.cpp:1388)
+    // the syncmer kernel does not touch the table: whole samples clear it on the side stream in the kernel's shadow (it leaves most of the DRAM
+    // bandwidth idle) and the counting kernel waits for the event
+    static const bool kSideClear = [] { const char* e = std::getenv("PM_SIDE_CLEAR"); return e ? std::atoi(e) != 0 : true; }();
+    const bool sideClear = clearFirst && kSideClear && !quality && !prm.dedup_reads && !I->F.sp.hpc && W->nReads >= 100000;
     if (clearFirst) {
         CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
-        launchTableClear(W->view, W->st);
+        if (sideClear) {
+            CK(cudaEventRecord(W->evFork, W->st));
+            CK(cudaStreamWaitEvent(W->stCopy, W->evFork, 0));
+            launchTableClear(W->view, W->stCopy);
+            CK(cudaEventRecord(W->evJoin, W->stCopy));
+        } else launchTableClear(W->view, W->st);
     }
-    const bool quality = W->useQuals && prm.min_seed_quality > 0;   // the reference's quality path never deduplicates (placement.cpp:1388)
     unsigned char* dup = quality ? nullptr : prepareDedup(W, W->nReads, prm);
     const u64* endOff = nullptr;
     if (I->F.sp.hpc) {
@@ -442,7 +451,7 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         for (int sl = 0; sl < ns; ++sl) {
             const u64 r0 = W->nReads * (u64)sl / (u64)ns, r1 = W->nReads * (u64)(sl + 1) / (u64)ns;
             launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, sl + 1 == ns ? W->evK[2] : nullptr,
-                            dup ? dup + r0 : nullptr, endOff ? endOff + r0 : nullptr, ascii ? W->reads.p : nullptr);
+                            dup ? dup + r0 : nullptr, endOff ? endOff + r0 : nullptr, ascii ? W->reads.p : nullptr, sideClear && sl == 0 ? W->evJoin : nullptr);
         }
         launchCountBuckets(W->view, W->st);   // partitioned counting only (no-op otherwise)
     }

@@ -1402,10 +1402,11 @@ static void launchSyncmers(const uint4* packed, const u64* off, const u64* packe
 // SM can hold.)
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between, const unsigned char* dup,
-                     const u64* endOff, const char* reads) {
-    if (nReads == 0) return;
+                     const u64* endOff, const char* reads, cudaEvent_t tableReady) {
+    if (nReads == 0) { if (tableReady) cudaStreamWaitEvent(st, tableReady, 0); return; }
     launchSyncmers(packed, off, packedOff, nReads, P, dTables, W.synBuf, W.synCount, dup, endOff, st, reads);
     if (between) cudaEventRecord(between, st);
+    if (tableReady) cudaStreamWaitEvent(st, tableReady, 0);   // the table was cleared on a side stream while the syncmer kernel ran
     if (W.bktCount) launchScatter(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W, st);   // partitioned counting: launchCountBuckets follows the last slice
     else launchCountSeeds(W.synBuf, W.synCount, packedOff, nReads, P.k, P.l, W.table, W.tableMask, W.acc, W.tableTex, W.missQ, W.missCap, st);
 }

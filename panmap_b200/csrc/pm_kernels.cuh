@@ -159,7 +159,7 @@ void launchHpcCompress(char* reads, const u64* off, u64 nReads, u64* endOff, cud
 void launchChunkOffsets(const u64* off, u64 n, u64 gBase, u64* tileSum /* [n/4096 + 1] scratch */, u64* packedOff, cudaStream_t st);
 void launchSeedTable(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                      const SeedTables* dTables, WorkspaceView W, cudaStream_t st, cudaEvent_t between = nullptr,
-                     const unsigned char* dup = nullptr, const u64* endOff = nullptr, const char* reads = nullptr);
+                     const unsigned char* dup = nullptr, const u64* endOff = nullptr, const char* reads = nullptr, cudaEvent_t tableReady = nullptr);
 // --min-seed-quality > 0: needs the packed reads; quals = one byte per base at the reads' offsets, synPass = one byte per synBuf entry
 void launchSeedTableQuality(const uint4* packed, const u64* off, const u64* packedOff, u64 nReads, const SeederParams& P,
                             const SeedTables* dTables, WorkspaceView W, cudaStream_t st, const u64* endOff, const char* quals,

@@ -17,7 +17,7 @@ S = synth.generate(100_000, 30_000, 1.0, n, read_len=150, seed=0)
 host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
 ws = pm.Workspace(pm.Index(host))
 p = pm.PlaceParams()
-tag = " ".join(f"{k}={os.environ[k]}" for k in ("PM_AGG_MIN_READS", "PM_COUNT_WARP_BELOW", "PM_SLICES_ASCII", "PM_SLICES_PACKED", "PM_RANK_STAGE", "PM_RESIDENT_SLICES", "PM_TABLE_FIT_LO", "PM_LIST_PREFETCH", "PM_SIDE_SCALARS") if k in os.environ)
+tag = " ".join(f"{k}={os.environ[k]}" for k in ("PM_AGG_MIN_READS", "PM_COUNT_WARP_BELOW", "PM_SLICES_ASCII", "PM_SLICES_PACKED", "PM_RANK_STAGE", "PM_RESIDENT_SLICES", "PM_TABLE_FIT_LO", "PM_LIST_PREFETCH", "PM_SIDE_SCALARS", "PM_SIDE_CLEAR") if k in os.environ)
 if mode == "resident":
     ws.upload(S.reads, S.read_offsets)
     for _ in range(4):
