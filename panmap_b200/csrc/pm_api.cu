@@ -593,8 +593,13 @@ static int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result
         CK(cudaEventRecord(W->ev[6], W->st));
         // result block D2H, then the sample's reset, then ONE host synchronisation: the reset (which touches neither the block nor the tie
         // lists) no longer waits for the host to wake up in between
+        // ... and the reset runs on the side stream while the copy engine delivers the block (both only depend on the ties kernel)
+        CK(cudaEventRecord(W->evFork, W->st));
+        CK(cudaStreamWaitEvent(W->stCopy, W->evFork, 0));
+        launchResetSample(I->view, W->view, W->stCopy);
+        CK(cudaEventRecord(W->evJoin, W->stCopy));
         enqueueSmall(W);
-        launchResetSample(I->view, W->view, W->st);
+        CK(cudaStreamWaitEvent(W->st, W->evJoin, 0));
         CK(cudaEventRecord(W->ev[7], W->st));
         CK(cudaStreamSynchronize(W->st));
         parseSmall(W);

@@ -340,9 +340,14 @@ void phase3(pm_comm* c, const pm_place_params& prm) {
 void phase4(pm_comm* c) {
     pm_workspace* W = c->ws; pm_index* I = W->idx;
     setDevice(I->device);
+    // the reset (ell entries of the gathered pairs, boundary records) on the side stream while the copy engine delivers the two small blocks
+    CK(cudaEventRecord(W->evFork, W->st));
+    CK(cudaStreamWaitEvent(W->stCopy, W->evFork, 0));
+    launchResetGathered(I->view, W->view, c->gRecv.p, (u32)c->n, c->capG, W->stCopy);
+    CK(cudaEventRecord(W->evJoin, W->stCopy));
     enqueueSmall(W);
     CK(cudaMemcpyAsync(c->hT.p, c->tRecv.p, (size_t)c->n * kTWords * 4, cudaMemcpyDeviceToHost, W->st));
-    launchResetGathered(I->view, W->view, c->gRecv.p, (u32)c->n, c->capG, W->st);
+    CK(cudaStreamWaitEvent(W->st, W->evJoin, 0));
     CK(cudaEventRecord(W->ev[7], W->st));
 }
 

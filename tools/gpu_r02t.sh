@@ -4,8 +4,8 @@ set -u
 TAG=${1:-r02t}
 mkdir -p gpurun_out
 P="python tools/tune_probe.py 1000000 resident"
-PM_SIDE_CLEAR=0 $P 2>&1 | tail -1
-PM_SIDE_CLEAR=1 $P 2>&1 | tail -1
+
+$P 2>&1 | tail -1
 ( time timeout 1500 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -6
 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-file-span > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err || tail -5 gpurun_out/bench_${TAG}.err
 python -c "
