@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 4
+#define PM_ABI_VERSION 5
 #define PM_NONE 0xFFFFFFFFu /* "no node" (reference: UINT32_MAX, placement.hpp:159) */
 #define PM_NUM_METRICS 5    /* log_raw, log_cosine, containment, weighted_containment, log_containment */
 
@@ -195,6 +195,10 @@ int pm_get_node_scores(pm_workspace* ws, double* out /* [n_nodes][5] */);
 int pm_get_node_metrics(pm_workspace* ws, double* out /* [n_nodes][5]: logRawNum, logCosNum, presence, wcNum, logContNum */);
 /* CUDA-event time of the three seeding kernels of the last pm_place_resident call, in ms: 0 pack_reads, 1 syncmers_*,
  * 2 count_seeds / seeds_from_syncmers (profiling aid for bench.py; the same events bracket nothing else) */
+/* stage timers: CUDA events between the stages of every placement of this workspace (stage_ms[0..6], pm_last_kernel_ms).  Off by default --
+ * like the reference's own stage timers (debug output, placement.cpp:1128,1698,1836,1926) -- because the ten stream markers cost ~25 us per
+ * placement; stage_ms[7], the whole placement, is always measured.  PM_STAGE_EVENTS=1 in the environment turns them on for new workspaces. */
+int pm_workspace_set_stage_timers(pm_workspace* ws, int on);
 int pm_last_kernel_ms(pm_workspace* ws, float* out /* [3] */);
 int pm_get_seed_table(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t cap); /* unsorted; returns n or <0 */
 

@@ -114,6 +114,7 @@ def lib():
     L.pm_get_node_scores.argtypes = [C.c_void_p, C.c_void_p]
     L.pm_get_node_metrics.argtypes = [C.c_void_p, C.c_void_p]
     L.pm_last_kernel_ms.argtypes = [C.c_void_p, C.c_void_p]
+    L.pm_workspace_set_stage_timers.argtypes = [C.c_void_p, C.c_int]
     L.pm_get_seed_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
     L.pm_hash_seq.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.pm_rolling_syncmers.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -471,6 +472,10 @@ class Workspace:
         res = PlaceResult()
         _ck(lib().pm_place_resident(self._h, C.byref(params), C.byref(res)))
         return self._finish(res) if full else res
+
+    def stage_timers(self, on=True):
+        """CUDA events between the stages of a placement (stage_ms[0..6], last_kernel_ms): off by default, ~25 us per placement when on"""
+        _ck(lib().pm_workspace_set_stage_timers(self._h, 1 if on else 0))
 
     def last_kernel_ms(self):
         """CUDA-event times (ms) of pack_reads, syncmers_*, count_seeds of the last place_resident call"""

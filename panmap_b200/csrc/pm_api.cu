@@ -35,6 +35,13 @@ int deviceCountNoThrow() {
 
 
 void setDevice(int dev) { CK(cudaSetDevice(dev)); }
+// stage timers (cudaEventRecord between the kernels of a sample: ten stream markers, ~25 us per placement of the 1M-read sample).  Off unless
+// the caller asks for them (pm_workspace_set_stage_timers; the reference's own stage timers are debug output too) or PM_STAGE_EVENTS=1 makes
+// them the default; without them stage_ms[0..6] and pm_last_kernel_ms read 0 and only stage_ms[7], the whole placement, is measured.
+bool stageTimersDefault() {
+    static const bool v = [] { const char* e = std::getenv("PM_STAGE_EVENTS"); return e ? std::atoi(e) != 0 : false; }();
+    return v;
+}
 static std::mutex g_wsMutex;
 static std::vector<const pm_workspace*> g_wsLive;
 bool workspaceAlive(const pm_workspace* W) {
@@ -435,14 +442,14 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
     }
     if (dup) launchDedup(W->reads.p, W->off.p, 0, W->nReads, W->dedupSlots.p, W->dedupMask, dup, W->st, endOff);
     const bool ascii = seedTableReadsAscii(P) && !quality;
-    CK(cudaEventRecord(W->evK[0], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->evK[0], W->st));
     if (!ascii) launchPackReads(W->reads.p, W->off.p, W->packedOff.p, W->blockFirst.p, W->nReads, 0, W->nChunks, W->packed.p, W->st, endOff);
-    CK(cudaEventRecord(W->evK[1], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->evK[1], W->st));
     if (quality) {
         W->synPass.ensure(W->nChunks * 32 + 32);
         launchSeedTableQuality(W->packed.p, W->off.p, W->packedOff.p, W->nReads, P, I->seedTables.p, W->view, W->st, endOff, W->quals.p,
                                prm.min_seed_quality, W->synPass.p);
-        CK(cudaEventRecord(W->evK[2], W->st));
+        if (W->stageTimers) CK(cudaEventRecord(W->evK[2], W->st));
     } else {
         // experiment switch (PM_RESIDENT_SLICES = n): hash and count the resident sample slice after slice, so that a slice's syncmer lists are
         // still in L2 when they are counted
@@ -450,12 +457,12 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
         const int ns = (kSlices > 1 && ascii && !dup && !endOff && W->nReads >= (u64)kSlices * 1024) ? kSlices : 1;
         for (int sl = 0; sl < ns; ++sl) {
             const u64 r0 = W->nReads * (u64)sl / (u64)ns, r1 = W->nReads * (u64)(sl + 1) / (u64)ns;
-            launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, sl + 1 == ns ? W->evK[2] : nullptr,
+            launchSeedTable(W->packed.p, W->off.p + r0, W->packedOff.p + r0, r1 - r0, P, I->seedTables.p, W->view, W->st, sl + 1 == ns && W->stageTimers ? W->evK[2] : nullptr,
                             dup ? dup + r0 : nullptr, endOff ? endOff + r0 : nullptr, ascii ? W->reads.p : nullptr, sideClear && sl == 0 ? W->evJoin : nullptr);
         }
         launchCountBuckets(W->view, W->st);   // partitioned counting only (no-op otherwise)
     }
-    CK(cudaEventRecord(W->evK[3], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->evK[3], W->st));
 }
 
 void stageScore(pm_workspace* W, const pm_place_params& prm) {
@@ -472,13 +479,13 @@ void stageScore(pm_workspace* W, const pm_place_params& prm) {
 void stageDeltasScoresRecords(pm_workspace* W, const pm_place_params& prm) {
     pm_index* I = W->idx;
     const PlaceOpts O = makeOpts(prm, W->wantMetrics);
-    CK(cudaEventRecord(W->ev[3], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->ev[3], W->st));
     launchDeltas(I->view, W->view, I->nSM, W->st);
     launchGeneral(I->view, W->view, W->st);
     if (W->joinPending) { CK(cudaStreamWaitEvent(W->st, W->evJoin, 0)); W->joinPending = false; }   // the scalars (side stream) before the scores
-    CK(cudaEventRecord(W->ev[4], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->ev[4], W->st));
     launchPrefixScores(I->view, W->view, O, W->st);
-    CK(cudaEventRecord(W->ev[5], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->ev[5], W->st));
     launchRecords(I->view, W->view, O, W->st);
 }
 
@@ -552,7 +559,7 @@ static void fetchTies(pm_workspace* W) {
 }
 void recordStageTimes(pm_workspace* W, pm_place_result* res) {
     float ms = 0;
-    for (int i = 0; i < 7; ++i) { ms = 0; if (cudaEventElapsedTime(&ms, W->ev[i], W->ev[i + 1]) != cudaSuccess) cudaGetLastError(); res->stage_ms[i] = ms; }
+    for (int i = 0; i < 7; ++i) { ms = 0; if (W->stageTimers && cudaEventElapsedTime(&ms, W->ev[i], W->ev[i + 1]) != cudaSuccess) cudaGetLastError(); res->stage_ms[i] = ms; }
     ms = 0; if (cudaEventElapsedTime(&ms, W->ev[0], W->ev[7]) != cudaSuccess) cudaGetLastError(); res->stage_ms[7] = ms;
 }
 
@@ -581,16 +588,16 @@ static int runPlace(pm_workspace* W, const pm_place_params* prm, pm_place_result
             ensureTable(W, std::max<u64>(1 << 16, (total > k * n ? total - (k - 1) * n : 0) / 4));
         }
         planBuckets(W, inputsResident ? W->totalWindows : (n ? off[n] : 0), *prm);   // also refreshes the view
-        CK(cudaEventRecord(W->ev[1], W->st));
+        if (W->stageTimers) CK(cudaEventRecord(W->ev[1], W->st));
         if (inputsResident) stageSeed(W, true, *prm);
         else if (packedHost) uploadAndSeedPipelinedPacked(W, packedHost, off, n, *prm);
         else uploadAndSeedPipelined(W, reads, off, n, *prm);   // H2D of the slices overlaps pack + seeding of earlier slices
         W->bktCount = 0; refreshView(W);   // a per-sample decision: the staged and sharded entry points count directly
-        CK(cudaEventRecord(W->ev[2], W->st));
+        if (W->stageTimers) CK(cudaEventRecord(W->ev[2], W->st));
         stageScore(W, *prm);
         launchChain(W->view, nullptr, W->st);
         launchTies(I->view, W->view, makeOpts(*prm, false), W->st);
-        CK(cudaEventRecord(W->ev[6], W->st));
+        if (W->stageTimers) CK(cudaEventRecord(W->ev[6], W->st));
         // result block D2H, then the sample's reset, then ONE host synchronisation: the reset (which touches neither the block nor the tie
         // lists) no longer waits for the host to wake up in between
         // ... and the reset runs on the side stream while the copy engine delivers the block (both only depend on the ties kernel)
@@ -778,6 +785,7 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
         for (auto& e : W->ev) CK(cudaEventCreate(&e));
         for (auto& e : W->evCopy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));   // one per slice of the host-buffer pipeline
         for (auto& e : W->evK) CK(cudaEventCreate(&e));
+        W->stageTimers = stageTimersDefault();
         CK(cudaEventCreateWithFlags(&W->evFork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&W->evJoin, cudaEventDisableTiming));
         const FlatIndex& F = idx->F;
         const DevIndexView& V = idx->view;
@@ -1259,12 +1267,17 @@ int pm_stage_select(pm_workspace* ws, const uint32_t* counts, const uint32_t* co
     });
 }
 
+int pm_workspace_set_stage_timers(pm_workspace* ws, int on) {
+    if (!ws) return fail(PM_ERR_INVALID, "null workspace");
+    ws->stageTimers = on != 0;
+    return PM_OK;
+}
 int pm_last_kernel_ms(pm_workspace* ws, float* out) {
     if (!ws || !out) return fail(PM_ERR_INVALID, "null argument");
     return guarded([&]() -> int {
         setDevice(ws->idx->device);
         CK(cudaStreamSynchronize(ws->st));
-        for (int i = 0; i < 3; ++i) { out[i] = 0.f; if (cudaEventElapsedTime(&out[i], ws->evK[i], ws->evK[i + 1]) != cudaSuccess) { cudaGetLastError(); out[i] = 0.f; } }
+        for (int i = 0; i < 3; ++i) { out[i] = 0.f; if (ws->stageTimers && cudaEventElapsedTime(&out[i], ws->evK[i], ws->evK[i + 1]) != cudaSuccess) { cudaGetLastError(); out[i] = 0.f; } }
         return PM_OK;
     });
 }

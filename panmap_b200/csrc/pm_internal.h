@@ -91,7 +91,8 @@ struct pm_workspace {
     int device = 0;   // == idx->device (kept here: a binding's garbage collector may destroy the index handle first)
     cudaStream_t st = nullptr, stCopy = nullptr;
     cudaEvent_t ev[9]{}, evCopy[33]{}, evK[4]{}, evFork{}, evJoin{};   // evFork / evJoin: root_and_scalars beside node_deltas (stageScore)
-    bool joinPending = false;   // evK: around pack_reads / syncmers / count_seeds of the resident path
+    bool joinPending = false;
+    bool stageTimers = false;   // record the events between the stages of a placement (pm_workspace_set_stage_timers)   // evK: around pack_reads / syncmers / count_seeds of the resident path
     // inputs
     DevBuf<char> reads; DevBuf<u64> off, packedOff; DevBuf<uint4> packed; DevBuf<u32> blockFirst;
     PinBuf<u64> hPackedOff; PinBuf<u32> hBlockFirst;

@@ -304,12 +304,12 @@ void phase0(pm_comm* c, const pm_place_params& prm) {
     ensureTable(W, std::max(c->localCap, c->partCap));   // the allocation covers both phases; each uses its own prefix
     W->tableCap = c->localCap;
     refreshView(W);
-    CK(cudaEventRecord(W->ev[1], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->ev[1], W->st));
     if (c->resident) stageSeed(W, true, prm);
     else if (c->hPacked) uploadAndSeedPipelinedPacked(W, c->hPacked, c->hOff, c->nLocalReads, prm);
     else uploadAndSeedPipelined(W, c->hReads, c->hOff, c->nLocalReads, prm);
     launchPartitionExport(W->view, (u32)c->n, c->capPair, c->xSend.p, c->exportInfo.p, W->st);
-    CK(cudaEventRecord(W->ev[2], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->ev[2], W->st));
 }
 void phase1(pm_comm* c, const pm_place_params& prm) {
     pm_workspace* W = c->ws; pm_index* I = W->idx;
@@ -335,7 +335,7 @@ void phase3(pm_comm* c, const pm_place_params& prm) {
     launchChainGathered(W->view, c->rRecv.p, (u32)c->n, c->recX, W->st);
     launchTies(I->view, W->view, makeOpts(prm, false), W->st);
     launchTiesPack(W->view, c->tSend.p, c->gSend.p, c->exportInfo.p, W->st);
-    CK(cudaEventRecord(W->ev[6], W->st));
+    if (W->stageTimers) CK(cudaEventRecord(W->ev[6], W->st));
 }
 void phase4(pm_comm* c) {
     pm_workspace* W = c->ws; pm_index* I = W->idx;

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     L = pm.lib()
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.pm_abi_version() == 4
+    assert L.pm_abi_version() == 5
 
 
 def test_idx_reader_roundtrip_of_a_reference_written_index():

@@ -24,7 +24,7 @@ def main():
         for k in ("PM_BUCKET_MIN_SLOTS", "PM_BUCKET_BYTES"):
             os.environ.pop(k, None)
         os.environ.update(env)
-        ws = pm.Workspace(index)
+        ws = pm.Workspace(index); ws.stage_timers(True)
         ws.upload(S.reads, S.read_offsets)
         for _ in range(3):
             r = ws.place_resident(params, full=False)

@@ -3,7 +3,7 @@ sys.path.insert(0, '/root/repo')
 import bench, panmap_b200 as pm, torch
 S, w = bench.make_workload('c3')
 host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
-ws = pm.Workspace(pm.Index(host)); params = pm.PlaceParams()
+ws = pm.Workspace(pm.Index(host)); ws.stage_timers(True); params = pm.PlaceParams()
 L = pm.lib(); n = w['n_reads']; nbytes = int(S.read_offsets[-1])
 hp_reads = L.pm_host_alloc(nbytes + 64); hp_off = L.pm_host_alloc(8 * (n + 1))
 C.memmove(hp_reads, S.reads.ctypes.data, nbytes); C.memmove(hp_off, S.read_offsets.ctypes.data, 8 * (n + 1))

@@ -20,6 +20,8 @@ def main():
     host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
     wss = [pm.Workspace(pm.Index(host, device=0, shard=r, n_shards=n)) for r in range(n)]
     comms = pm.Comm.local(wss)
+    for w_ in wss:
+        w_.stage_timers(True)
     for r in range(n):
         reads, off = pmd.slice_reads(S.reads, S.read_offsets, r, n)
         wss[r].upload(reads, off)

@@ -16,8 +16,9 @@ n = int(sys.argv[1]); mode = sys.argv[2] if len(sys.argv) > 2 else "resident"
 S = synth.generate(100_000, 30_000, 1.0, n, read_len=150, seed=0)
 host = pm.HostIndex(S.hash, S.parent, S.child, S.offsets, S.parent_index, S.k, S.s, S.t, S.l)
 ws = pm.Workspace(pm.Index(host))
+ws.stage_timers(os.environ.get("PM_STAGE_EVENTS", "1") != "0")   # per-kernel events on unless the A/B is about them
 p = pm.PlaceParams()
-tag = " ".join(f"{k}={os.environ[k]}" for k in ("PM_AGG_MIN_READS", "PM_COUNT_WARP_BELOW", "PM_SLICES_ASCII", "PM_SLICES_PACKED", "PM_RANK_STAGE", "PM_RESIDENT_SLICES", "PM_TABLE_FIT_LO", "PM_LIST_PREFETCH", "PM_SIDE_SCALARS", "PM_SIDE_CLEAR") if k in os.environ)
+tag = " ".join(f"{k}={os.environ[k]}" for k in ("PM_AGG_MIN_READS", "PM_COUNT_WARP_BELOW", "PM_SLICES_ASCII", "PM_SLICES_PACKED", "PM_RANK_STAGE", "PM_RESIDENT_SLICES", "PM_TABLE_FIT_LO", "PM_LIST_PREFETCH", "PM_SIDE_SCALARS", "PM_SIDE_CLEAR", "PM_STAGE_EVENTS") if k in os.environ)
 if mode == "resident":
     ws.upload(S.reads, S.read_offsets)
     for _ in range(4):
