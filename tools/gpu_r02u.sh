@@ -4,7 +4,7 @@ set -u
 TAG=${1:-r02u}
 N=${2:-2}
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests/test_gpu_nccl.py tests/test_gpu_sharded.py -m gpu -x -q ) 2>&1 | tail -6
+( time timeout 900 python -m pytest tests/test_gpu_nccl.py -m gpu -x -q ) 2>&1 | tail -4
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n${N}_${TAG}.json 2> gpurun_out/bench_n${N}_${TAG}.err || tail -8 gpurun_out/bench_n${N}_${TAG}.err
 python -c "
 import json
