@@ -420,13 +420,15 @@ void stageSeed(pm_workspace* W, bool clearFirst, const pm_place_params& prm) {
     static const bool kSideClear = [] { const char* e = std::getenv("PM_SIDE_CLEAR"); return e ? std::atoi(e) != 0 : true; }();
     const bool sideClear = clearFirst && kSideClear && !quality && !prm.dedup_reads && !I->F.sp.hpc && W->nReads >= 100000;
     if (clearFirst) {
-        CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
-        if (sideClear) {
+        if (sideClear) {   // accumulators and table in one launch on the side stream; nothing before the counting kernel's wait touches either
             CK(cudaEventRecord(W->evFork, W->st));
             CK(cudaStreamWaitEvent(W->stCopy, W->evFork, 0));
-            launchTableClear(W->view, W->stCopy);
+            launchSampleBegin(W->view, W->stCopy);
             CK(cudaEventRecord(W->evJoin, W->stCopy));
-        } else launchTableClear(W->view, W->st);
+        } else {
+            CK(cudaMemsetAsync(W->acc.p, 0, sizeof(SampleAcc), W->st));
+            launchTableClear(W->view, W->st);
+        }
     }
     unsigned char* dup = quality ? nullptr : prepareDedup(W, W->nReads, prm);
     const u64* endOff = nullptr;
@@ -804,7 +806,7 @@ int pm_workspace_create(pm_index* idx, pm_workspace** out) {
             CK(cudaCreateTextureObject(&W->ellTex, &rd, &td, nullptr));
         } CK(cudaMemsetAsync(W->ell.p, 0, W->ell.n * sizeof(long long), W->st));   // [S] is the always-zero slot of the padding words
         W->scanPart.alloc(kMaxPartials); W->finPart.alloc(kMaxPartials);
-        W->countHist.alloc(kLog1pLut);
+        W->countHist.alloc(kLog1pLut); CK(cudaMemset(W->countHist.p, 0, kLog1pLut * sizeof(unsigned)));   // kept zero between samples by its consumer (root_and_scalars)
         W->segRec.alloc(F.nSeg + 1); CK(cudaMemsetAsync(W->segRec.p, 0, W->segRec.n * sizeof(SegRec), W->st));
         W->chainA.alloc(V.chainTotal ? V.chainTotal : 1);
         W->genRec.alloc((size_t)(F.nGenNodes ? F.nGenNodes : 1) * kGenWords); W->evPrefix.alloc((size_t)(V.nEvents ? V.nEvents : 1) * kGenWords);

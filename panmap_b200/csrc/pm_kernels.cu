@@ -1458,6 +1458,18 @@ __global__ void __launch_bounds__(256) table_clear(TableSlot* table, u64 cap) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) t[i] = e;
 }
 void launchTableClear(WorkspaceView W, cudaStream_t st) { noteLaunch(), table_clear<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W.table, W.tableCap); }
+// the same pass also zeroes the sample's accumulators (start of a sample whose first kernel, the syncmer kernel, touches neither)
+__global__ void __launch_bounds__(256) sample_begin(TableSlot* table, u64 cap, SampleAcc* acc) {
+    const uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+    uint4* t = reinterpret_cast<uint4*>(table);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (u64)gridDim.x * blockDim.x) t[i] = e;
+    if (blockIdx.x == 0) {
+        static_assert(sizeof(SampleAcc) % 4 == 0, "SampleAcc is cleared word by word");
+        u32* a = reinterpret_cast<u32*>(acc);
+        for (unsigned i = threadIdx.x; i < sizeof(SampleAcc) / 4; i += blockDim.x) a[i] = 0u;
+    }
+}
+void launchSampleBegin(WorkspaceView W, cudaStream_t st) { noteLaunch(), sample_begin<<<streamGrid(W.tableCap, 4), 256, 0, st>>>(W.table, W.tableCap, W.acc); }
 
 __global__ void __launch_bounds__(256) table_import(TableSlot* table, u64 mask, SampleAcc* acc, const u64* __restrict__ hash,
                                                     const long long* __restrict__ count, u64 n) {
@@ -1778,6 +1790,9 @@ __global__ void __launch_bounds__(256) root_and_scalars(DevIndexView I, Workspac
     }
     const double dMag = blockSumF64(eMag, sRed);
     const double dLog = blockSumF64(eLog, sRed);
+    // the histogram is consumed: its consumer leaves it zero for the next pass (every thread of this block is past its reads: the block sums above
+    // are barriers), so no memset node sits in front of the next table_scan
+    for (int i = (int)tid * 4; i < kLog1pLut; i += 4 * (int)blockDim.x) *reinterpret_cast<uint4*>(W.countHist + i) = make_uint4(0u, 0u, 0u, 0u);
     if (tid != 0) return;
     fx128 w; w.lo = __ldcg(&a->wcDen[0]); w.hi = (i64)__ldcg(&a->wcDen[1]);
     SampleScalars S;
@@ -1797,7 +1812,6 @@ __global__ void __launch_bounds__(256) root_and_scalars(DevIndexView I, Workspac
 }
 
 void launchTableScan(WorkspaceView W, const u64* homo, int nSM, unsigned* nPartsOut, cudaStream_t st) {
-    cudaMemsetAsync(W.countHist, 0, kLog1pLut * sizeof(unsigned), st);
     const u64 nBlocks = (W.tableCap + kScanSlots - 1) / kScanSlots;
     const unsigned g1 = (unsigned)std::min<u64>(std::min<u64>(nBlocks ? nBlocks : 1, (u64)nSM * 4), kMaxPartials - 1);
     noteLaunch(), table_scan<<<g1, 256, 0, st>>>(W, homo);

@@ -210,6 +210,7 @@ void launchGenomeMaterialize(const BuildTreeView& T, u32 nodeBegin, u32 nNodes, 
 void launchSeedsSort(const u64* in, const u64* winOff, const u64* count, const u64* arenaOff, u64* arena, u32 nLists, cudaStream_t st);
 void launchNodeDiff(const BuildDiffArgs& A, unsigned grid, cudaStream_t st);
 void launchTableClear(WorkspaceView W, cudaStream_t st);
+void launchSampleBegin(WorkspaceView W, cudaStream_t st);   // table clear + the sample's accumulators zeroed, one launch
 void launchTableImport(WorkspaceView W, const u64* hash, const long long* count, u64 n, cudaStream_t st);
 void launchTableExport(WorkspaceView W, u64* hash, long long* count, unsigned* counter, u64 cap, cudaStream_t st);
 // seedMaskFraction > 0 (off by default): synchronises the stream a few dozen times to find the cut; maskScratch = two device words
