@@ -407,3 +407,58 @@ extern "C" int hc_image_roundtrip(const pm_index_desc* d, uint32_t shard, uint32
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+
+// ---- index builder: what genome_materialize (pm_build_kernels.cu) does with the flattened tree, step for step on the host ----
+// template copy, block state replayed along the root -> node path, point edits level by level (root first), compaction in aligned
+// order with inverted blocks mirrored and complemented.  Every node's genome, concatenated in pre-order; returns the node count or -1.
+static char hcComplement(char c) {
+    switch (c) {
+        case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+        case 'R': return 'Y'; case 'Y': return 'R'; case 'K': return 'M'; case 'M': return 'K';
+        case 'B': return 'V'; case 'V': return 'B'; case 'D': return 'H'; case 'H': return 'D';
+        default: return c;
+    }
+}
+extern "C" int64_t hc_flat_genomes(const char* panman_path, char* out, uint64_t cap, uint64_t* offsets /* [n + 1] */, uint64_t maxNodes) {
+    try {
+        PanmanTree T; readPanman(panman_path, T);
+        PanmanFlat F; flattenPanman(T, F);
+        const size_t N = std::min<size_t>(T.nodes.size(), (size_t)maxNodes), B = F.blockStart.size() - 1, A = F.tmpl.size();   // the first maxNodes nodes in pre-order
+        uint64_t total = 0;
+        std::vector<uint32_t> path;
+        for (size_t v = 0; v < N; ++v) {
+            path.clear();
+            for (uint32_t u = (uint32_t)v;; u = F.parent[u]) { path.push_back(u); if (F.parent[u] == kNoNode) break; }
+            if (path.size() > F.maxDepth) { g_err = "maxDepth too small"; return -1; }
+            std::string al = F.tmpl;
+            std::vector<unsigned char> st(B, 2);
+            for (size_t lv = path.size(); lv-- > 0;) {
+                const uint32_t u = path[lv];
+                for (uint32_t i = F.blockMutBegin[u]; i < F.blockMutBegin[u + 1]; ++i) {
+                    const uint32_t m = F.blockMut[i], b = m >> 2;
+                    if (m & 1u) st[b] = (unsigned char)(1u | ((m & 2u) ? 0u : 2u));
+                    else if (m & 2u) st[b] ^= 2u;
+                    else st[b] = 2u;
+                }
+            }
+            for (size_t lv = path.size(); lv-- > 0;) {
+                const uint32_t u = path[lv];
+                for (uint32_t i = F.editBegin[u]; i < F.editBegin[u + 1]; ++i) al[F.editSlot[i]] = F.editChar[i];
+            }
+            offsets[v] = total;
+            for (size_t q = 0; q < A; ++q) {
+                const uint32_t b = F.slotBlock[q];
+                if (!(st[b] & 1u)) continue;
+                char c;
+                if (st[b] & 2u) c = al[q];
+                else c = hcComplement(al[F.blockStart[b] + (F.blockStart[b + 1] - 1u - q)]);
+                if (c == '-') continue;
+                if (total < cap) out[total] = c;
+                ++total;
+            }
+        }
+        offsets[N] = total;
+        if (total > cap) { g_err = "output buffer too small"; return -1; }
+        return (int64_t)N;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}

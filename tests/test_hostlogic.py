@@ -17,11 +17,11 @@ HC = os.path.join(H.ROOT, "tests", "hostcheck")
 def hc():
     so = os.path.join(HC, "libhostcheck.so")
     srcs = [os.path.join(HC, "hostcheck.cpp"), os.path.join(H.ROOT, "panmap_b200", "csrc", "pm_flatten.cpp"),
-            os.path.join(H.ROOT, "panmap_b200", "csrc", "pm_image.cpp")]
+            os.path.join(H.ROOT, "panmap_b200", "csrc", "pm_image.cpp"), os.path.join(H.ROOT, "panmap_b200", "csrc", "pm_panman.cpp")]
     deps = srcs + [os.path.join(H.ROOT, "panmap_b200", "csrc", "pm_logic.cuh"), os.path.join(H.ROOT, "panmap_b200", "csrc", "pm_host.h")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wl,--version-script=" + os.path.join(HC, "exports.map"),
-                        "-o", so] + srcs, check=True)
+                        "-o", so] + srcs + ["-ldl"], check=True)
     L = C.CDLL(so)
     L.hc_seed.restype = C.c_int64
     L.hc_last_error.restype = C.c_char_p

@@ -63,6 +63,31 @@ def test_reader_refuses_what_is_not_a_panman(tmp_path):
             pm.panman_genomes(str(q))
 
 
+@needs_data
+@pytest.mark.parametrize("case,count", [("mammoth", 155), ("rsv", 600), ("sars", 300)])
+def test_flattened_tree_materializes_the_same_genomes(case, count):
+    """the device pipeline's input (flattenPanman: aligned template, one point edit per mutated slot, block mutations) run through a host
+    restatement of genome_materialize (tests/hostcheck) == the depth-first walk, which is pinned against the reference above; rsv_4K has
+    1,826 blocks, inverted ones among them"""
+    import ctypes as C
+    so = os.path.join(H.ROOT, "tests", "hostcheck", "libhostcheck.so")
+    if not os.path.exists(so):
+        pytest.skip("tests/hostcheck/libhostcheck.so not built (__graft_entry__.build())")
+    hc = C.CDLL(so)
+    if not hasattr(hc, "hc_flat_genomes"):
+        pytest.skip("stale libhostcheck.so")
+    hc.hc_flat_genomes.restype = C.c_int64
+    hc.hc_flat_genomes.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    hc.hc_last_error.restype = C.c_char_p
+    bases, off, par, ids = pm.panman_genomes(CASES[case][0])
+    n = min(count, len(ids))
+    want = bases[:int(off[n])]
+    out = np.zeros(max(int(off[n]), 1) + 16, np.uint8); o2 = np.zeros(n + 1, np.uint64)
+    got = hc.hc_flat_genomes(os.fsencode(CASES[case][0]), out.ctypes.data, out.size, o2.ctypes.data, n)
+    assert got == n, hc.hc_last_error()
+    assert np.array_equal(o2, off[:n + 1]) and np.array_equal(out[:int(off[n])], want)
+
+
 def _deltas_by_definition(bases, off, par, sp, nodes):
     """seed every genome (C oracle), diff against the parent's multiset: (hash, parentCount, childCount) sorted by hash"""
     lists, out = {}, {}
