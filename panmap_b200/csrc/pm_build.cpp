@@ -56,9 +56,7 @@ void diffSorted(const std::vector<uint64_t>& par, const std::vector<uint64_t>& c
 
 // ---- the device pipeline: genomes materialised, seeded, sorted and diffed on the GPU; only the deltas come back ----
 // Throws Unsupported when a genome holds more seeds than the shared-memory sort takes (the caller then runs the host pipeline).
-void buildOnDevice(const PanmanTree& T, const pm_seed_params& sp, int device, HostIndex& H) {
-    PanmanFlat F;
-    flattenPanman(T, F);
+void buildOnDevice(const PanmanTree& T, const PanmanFlat& F, const pm_seed_params& sp, int device, HostIndex& H) {
     const u32 N = (u32)T.nodes.size(), B = (u32)T.blocks.size(), A = (u32)F.tmpl.size();
     setDevice(device);
     cudaStream_t st; CK(cudaStreamCreate(&st));
@@ -237,15 +235,15 @@ int pm_index_build(const char* panman_path, const pm_seed_params* sp, int flank_
             for (size_t i = 0; i < N; ++i) { H.parentIndex[i] = T.nodes[i].parent == kNoNode ? 0u : T.nodes[i].parent; H.nodeIds[i] = T.nodes[i].id; }
         };
         reset();
-        {   // LiteTree.blockRanges (index_single_mode.cpp:1254-1259): first and last aligned coordinate of every block
-            PanmanFlat F; flattenPanman(T, F);
-            for (size_t b = 0; b + 1 < F.blockStart.size(); ++b) { H.blockRanges.push_back(F.blockStart[b]); H.blockRanges.push_back(F.blockStart[b + 1] - 1); }
-        }
+        PanmanFlat F;
+        flattenPanman(T, F);
+        // LiteTree.blockRanges (index_single_mode.cpp:1254-1259): first and last aligned coordinate of every block
+        for (size_t b = 0; b + 1 < F.blockStart.size(); ++b) { H.blockRanges.push_back(F.blockStart[b]); H.blockRanges.push_back(F.blockStart[b + 1] - 1); }
         // the device pipeline (genomes never leave the GPU) unless a genome is too large for the shared-memory sort, the lists would not fit
         // the device, or PM_BUILD_HOST_WALK=1 asks for the host walk (the two are compared in tests/test_index_build.py)
         const char* hw = std::getenv("PM_BUILD_HOST_WALK");
         if (!(hw && std::atoi(hw) != 0)) {
-            try { buildOnDevice(T, *sp, device, H); *out = hi.release(); return PM_OK; }
+            try { buildOnDevice(T, F, *sp, device, H); *out = hi.release(); return PM_OK; }
             catch (const Unsupported&) { reset(); }
         }
 

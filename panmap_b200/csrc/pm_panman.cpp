@@ -148,8 +148,8 @@ void readPanman(const std::string& path, PanmanTree& T) {
                 x.pos = (int32_t)(w0 & 0xffffffffu);
                 x.gap = (w1 & 1) ? (int32_t)(w0 >> 32) : -1;
                 const uint32_t raw = (uint32_t)(w1 >> 32);
-                x.len = (uint8_t)((raw & 0xff) >> 4); x.type = (uint8_t)(raw & 0xf);
-                x.nucs = x.len <= 6 ? ((raw >> 8) << (24 - 4 * x.len)) : (raw >> 8);   // base i = (nucs >> 4 (5 - i)) & 15
+                x.len = (uint8_t)std::min<uint32_t>((raw & 0xff) >> 4, 6u); x.type = (uint8_t)(raw & 0xf);   // 24 bits hold at most six 4-bit codes
+                x.nucs = (raw >> 8) << (24 - 4 * x.len);   // base i = (nucs >> 4 (5 - i)) & 15
                 T.nucMuts.push_back(x);
             }
             if (flags & 2) T.blockMuts.push_back(PanmanBlockMut{primary, (flags >> 2 & 1) != 0, (flags >> 3 & 1) != 0});
