@@ -23,16 +23,23 @@ namespace pm {
 namespace {
 
 constexpr uint64_t kMagic = 0x0154414C464D50ull;   // "PMFLAT\x01"
-constexpr uint32_t kImageVersion = 1;
+constexpr uint32_t kImageVersion = 2;   // 2: four-lane checksum
 
 inline uint64_t mix(uint64_t h, uint64_t v) {
     h ^= v; h *= 0x9E3779B97F4A7C15ull; return h ^ (h >> 29);
 }
+// four independent lanes over 32-byte strides (one multiply chain per lane: the serial chain of a single lane ran at ~1.5 GB/s, a third of
+// the time of opening a cached image), folded at the end together with the length; the tail goes through lane 0
 uint64_t checksum(const uint8_t* p, size_t n, uint64_t h) {
+    uint64_t a = h, b = h ^ 0x9E3779B97F4A7C15ull, c = h ^ 0xC2B2AE3D27D4EB4Full, d = h ^ 0x165667B19E3779F9ull;
     size_t i = 0;
-    for (; i + 8 <= n; i += 8) { uint64_t v; std::memcpy(&v, p + i, 8); h = mix(h, v); }
-    if (i < n) { uint64_t v = 0; std::memcpy(&v, p + i, n - i); h = mix(h, v); }
-    return h;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t v[4]; std::memcpy(v, p + i, 32);
+        a = mix(a, v[0]); b = mix(b, v[1]); c = mix(c, v[2]); d = mix(d, v[3]);
+    }
+    for (; i + 8 <= n; i += 8) { uint64_t v; std::memcpy(&v, p + i, 8); a = mix(a, v); }
+    if (i < n) { uint64_t v = 0; std::memcpy(&v, p + i, n - i); a = mix(a, v); }
+    return mix(mix(mix(mix(a, b), c), d), (uint64_t)n);
 }
 
 struct Sink {   // serialises into one buffer
