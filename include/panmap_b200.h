@@ -205,8 +205,9 @@ int pm_get_seed_table(pm_workspace* ws, uint64_t* hash, int64_t* count, uint64_t
 /* ---- own index builder (reference: IndexBuilder::buildIndex, index_single_mode.cpp:1227-1392 / processNode :1647-2205,
  *      called from main.cpp:398-428): `.panman` -> per-node seed deltas.  Every node's ungapped genome (the reference's
  *      getStringFromReference(tree, id, aligned = false), panmap_utils.cpp:7-193) is seeded on the GPU with the read path's kernels and
- *      diffed against its parent's: delta for delta the LiteIndex the reference builds with --flank-mask 0.  flank_mask must be 0
- *      (PM_ERR_UNSUPPORTED otherwise: the reference's flank masking makes its index depend on the traversal history).
+ *      diffed against its parent's: the LiteIndex the reference builds with --flank-mask 0 (rsv_4K: every node; sars_20000: 39,998 of 39,999;
+ *      DESIGN.md section 8).  flank_mask and sp->hpc must be 0 (PM_ERR_UNSUPPORTED otherwise: the reference's flank masking makes its index
+ *      depend on the traversal history, and its hpc build is not the seeding of the collapsed genomes).
  *      The result is a host index like pm_host_index_read's: pm_host_index_desc / _extras / _write / pm_index_create apply. ---- */
 int pm_index_build(const char* panman_path, const pm_seed_params* sp, int flank_mask, int device, pm_host_index** out);
 /* the builder's input half alone (host only, no GPU): every node's ungapped genome concatenated in DFS pre-order (offsets[n_nodes + 1]),
